@@ -1,0 +1,147 @@
+/* muav.h -- C ABI of libmuav_b200.so: batched Multi-UAV-TA "Windowed Pop-up Strike"
+ * step path for NVIDIA B200 (sm_100a).
+ *
+ * Every entry point takes plain pointers and sizes; pointers prefixed d_ are
+ * DEVICE pointers owned by the caller (e.g. torch tensors), h_ are HOST
+ * pointers.  All calls are stream-ordered on `stream` (a cudaStream_t passed as
+ * void*; NULL = default stream) and return 0 on success or a negative errno /
+ * -1000-cudaError on failure.  No exceptions cross this boundary.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   muav_step / muav_rollout  -> MultiUAVEnv.step             mUAV_TA/DroneEnv.py:774-1206
+ *                                (+ UAV/Task bookkeeping       mUAV_TA/DroneEnvComponents.py:55-179,280-326)
+ *   muav_allocate (fused in step via muav_alloc_opts)
+ *                             -> HungarianAllocator.allocate_tasks
+ *                                                              TaskAllocation/OptimizationBased/HungarianAllocator.py:72-208
+ *                                and the driver glue           experiments/paper_eval.py:85-101, experiments/wps_eval.py:55-73
+ *   muav_lsap                 -> scipy.optimize.linear_sum_assignment call at HungarianAllocator.py:181
+ *   muav_avoid_obstacles      -> core_sim.SimCore.avoid_obstacles  core_sim/src/sim_core.rs:24-59 (PyO3 export lib.rs:10-18)
+ *   muav_tokens_pair          -> build_pair_tokens             TaskAllocation/Hybrid/PairCostHybrid.py:31-65
+ *                                (build_att_tokens             TaskAllocation/Hybrid/AttentionRAH.py:50-173)
+ *   muav_observe              -> _generate_observations/get_task_info  mUAV_TA/DroneEnv.py:365-492
+ *   muav_metrics              -> calculate_metrics / compute_s_wps / compute_s_esc  DroneEnv.py:1231-1337,2002-2011
+ *   muav_field_info / muav_record_bytes: layout of one environment record (host packing at reset,
+ *                                snapshots for the object proxies); reset itself (DroneEnv.py:522-762) stays in Python.
+ */
+#ifndef MUAV_H_
+#define MUAV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MUAV_N_UAV_TYPES 7  /* R1 R2 E1 F1 F2 T1 T2   (MultiDroneEnvData.py:15) */
+#define MUAV_N_TASK_TYPES 6 /* Hold Rec Att Def Int Det (MultiDroneEnvData.py:18) */
+#define MUAV_MAX_GROUPS 8
+#define MUAV_MAX_AGENTS 64
+#define MUAV_MAX_TASK_CAP 512
+#define MUAV_MAX_QUEUE 32
+
+typedef struct muav_config {
+  /* capacities of one environment record */
+  int32_t n_agents, task_cap, n_threats, queue_cap, event_cap, n_obstacles, n_groups;
+  /* scenario constants (DroneEnv.py:145-147,101) */
+  int32_t n_tasks_cfg, max_tasks, max_time_steps;
+  /* flags (agentEnvOptions, MultiDroneEnvUtils.py:5-105) */
+  int32_t multiple_tasks_per_agent, early_terminate, capability_mask, saturate_mask;
+  int32_t hard_windows, burst_mode, dual_region_bursts, share_knowledge, escort_enabled;
+  int32_t threat_delay, window_length, burst_size, commit_horizon;
+  int32_t escort_required_agents, escort_type_mask;
+  int32_t tape_words[3];    /* words per env in each RNG tape: agent, tgt, mission */
+  int32_t group_start[MUAV_MAX_GROUPS + 1]; /* threat ids of group g: [group_start[g], group_start[g+1]) */
+  int32_t duration[MUAV_N_TASK_TYPES];
+  int32_t reserved_i;
+  double arrival_rate, sense_radius, miss_penalty, on_time_bonus, dynamic_idle_penalty, reassign_penalty;
+  double escort_radius, escort_requirement, escort_intercept_radius, mutual_support_radius;
+  double threat_gen_prob, threat_wide, max_coord, area_w, area_h, base_x, base_y, contact_line;
+  double rw[8]; /* action distance quality s_quality time alloc time_penaulty step */
+  double speed[MUAV_N_UAV_TYPES];  /* per step, already scaled by frame rate (DroneEnv.py:611,725) */
+  double engage[MUAV_N_UAV_TYPES];
+  double cap_table[MUAV_N_UAV_TYPES][MUAV_N_TASK_TYPES];
+} muav_config;
+
+/* Allocator fused in front of each step (NULL opts = actions come from d_actions). */
+typedef struct muav_alloc_opts {
+  int32_t mode;            /* 0 none (actions come from d_actions);
+                              1 HungarianAllocator.should_replan rule: t - last_plan_step >= interval or a listed event tag
+                                (HungarianAllocator.py:27-41,88), force=False;
+                              2 hybrid rule (wps_eval.py:64-73, escort_eval.py:52-58): t == 0 or t % interval == 0 or a
+                                listed event tag, then allocate_tasks(force=True) */
+  int32_t replan_interval; /* 20 Local-Hungarian, 12 Coalition-Hungarian, 15 hybrids */
+  int32_t event_mask;      /* bit i = tag i triggers (0 Reset_Allocation 1 Agent_Fail 2 New_Threat 3 Escort_Created 4 Escort_Retired) */
+  int32_t use_visibility;  /* agent_known_ids=env.agent_visibility_map() */
+  int32_t pair_tokens;     /* 1: task list = build_pair_tokens' open list (PairCostHybrid.py:34-36, AttentionRAH.py:67-71)
+                                 and d_edge_scores is indexed in token space [live agent row, token task column] */
+  int32_t score_rows, score_cols; /* edge score tensor shape per env (max_agents, max_tasks) */
+  int32_t reserved0;
+  double max_coord;        /* HungarianAllocator(max_coord=...) */
+  const float* d_edge_scores;  /* [E, score_rows, score_cols] or NULL */
+  const double* d_priorities;  /* [E, task_cap] by task index (task_priorities) or NULL */
+  const uint8_t* d_reserved;   /* [E, n_agents] 1 = excluded (reserved_agent_names) or NULL */
+} muav_alloc_opts;
+
+/* Per-step outputs (any pointer may be NULL). */
+typedef struct muav_step_out {
+  double* d_reward;     /* [E]  the scalar every agent receives (DroneEnv.py:1164-1178; F_Reward on the last step :1202) */
+  uint8_t* d_terminated; /* [E] */
+  uint8_t* d_truncated;  /* [E] */
+  int32_t* d_n_events;   /* [E] */
+  int32_t* d_events;     /* [E, event_cap] drained events (infos['events']): (arg+1)<<8 | tag */
+  int32_t* d_n_pairs;    /* [E] allocator output this step */
+  int32_t* d_pairs;      /* [E, n_agents] (agent_id<<16) | task_id, in reference order */
+  int32_t* d_n_open;     /* [E] len(env.last_tasks_info) after the step */
+} muav_step_out;
+
+const char* muav_version(void);
+size_t muav_config_size(void);
+size_t muav_record_bytes(const muav_config* cfg);
+size_t muav_scratch_bytes(const muav_config* cfg);
+int muav_num_fields(void);
+/* name/offset/count/element size of field `idx` of the record for this config */
+int muav_field_info(const muav_config* cfg, int idx, const char** name, int64_t* offset, int64_t* count, int32_t* elem_size);
+int muav_header_index(const char* name); /* index into the hi (int32) or hf (double) header arrays, -1 if unknown */
+
+/* K env steps for E environments.  d_records: [E, record_bytes]; d_tapes: [E, sum(tape_words)] uint32;
+ * d_actions: [E, n_agents, 2] int32 ordered (agent_id, index into last_tasks_info), agent_id = -1 ends the list
+ * (ignored when opts->mode != 0).  */
+int muav_step(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* d_actions,
+              const muav_alloc_opts* opts, const muav_step_out* out, int n_envs, int n_steps, void* stream);
+/* Same call with HOST action / output buffers: copies in, runs, copies out, synchronises. */
+int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* h_actions,
+                   const muav_alloc_opts* opts, double* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
+                   int n_envs, int n_steps, void* stream);
+
+/* Batched rectangular LSAP: B problems, cost [B, nr_max, nc_max] row-major with per-problem sizes.
+ * out_col4row [B, nr_max]: column assigned to each row or -1 (SciPy tie-breaking reproduced). */
+int muav_lsap(const double* d_cost, const int32_t* d_nr, const int32_t* d_nc, int nr_max, int nc_max,
+              int32_t* d_col4row, int n_problems, void* stream);
+
+/* core_sim.SimCore.avoid_obstacles over a batch: pos [N,2], movement [N,2], obstacles [M,3] -> out [N,2] */
+int muav_avoid_obstacles(const double* d_pos, const double* d_move, const double* d_obstacles, int n_obstacles,
+                         double* d_out, int n, void* stream);
+
+/* Episode metrics: out [E, MUAV_N_METRICS] doubles, order given by muav_metric_name(). */
+#define MUAV_N_METRICS 30
+const char* muav_metric_name(int idx);
+int muav_metrics(const muav_config* cfg, const void* d_records, double* d_out, int n_envs, void* stream);
+
+/* Pair tokens: task_feats [E,max_tasks,13] f32, task_mask [E,max_tasks] u8 (1 = padding), agent_feats [E,max_agents,12] f32,
+ * agent_mask [E,max_agents] u8, edge_valid [E,max_agents,max_tasks] f32, task_ids [E,max_tasks] i32 (0 = padding). */
+int muav_tokens_pair(const muav_config* cfg, const void* d_records, int max_tasks, int max_agents,
+                     float* d_task_feats, uint8_t* d_task_mask, float* d_agent_feats, uint8_t* d_agent_mask,
+                     float* d_edge_valid, int32_t* d_task_ids, int n_envs, void* stream);
+
+/* Observation tensors (DroneEnv.py:365-492): tasks_info [E, max_tasks, 20] f64, pad_mask [E,max_tasks] u8,
+ * legal_mask [E, n_agents, max_tasks] u8, agent_obs [E, n_agents, 9] f64, event_flags [E,5] f32. */
+#define MUAV_OBS_TASK_DIM 20
+#define MUAV_OBS_AGENT_DIM 9
+int muav_observe(const muav_config* cfg, const void* d_records, double* d_tasks_info, uint8_t* d_pad_mask,
+                 uint8_t* d_legal_mask, double* d_agent_obs, float* d_event_flags, int n_envs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUAV_H_ */

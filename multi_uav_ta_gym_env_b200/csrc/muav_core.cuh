@@ -1,0 +1,1215 @@
+// Per-environment simulation core: one env step (MultiUAVEnv.step, mUAV_TA/DroneEnv.py:774-1206),
+// the visibility-masked Local/Coalition Hungarian allocator
+// (TaskAllocation/OptimizationBased/HungarianAllocator.py:72-208) and the rectangular LSAP
+// it calls (scipy.optimize.linear_sum_assignment, HungarianAllocator.py:181).
+//
+// The code operates on a View of ONE environment record (shared memory inside the kernel).
+// All arithmetic is IEEE float64 with one rounding per written operation; the translation
+// unit is compiled with -fmad=false and the single FMA NumPy's BLAS ddot performs inside
+// np.linalg.norm of a 2-vector is written explicitly.
+//
+// Control flow is sequential per environment because the reference's semantics are
+// order-dependent (dict-order actions, agent-index-order FSM with cross-agent side effects,
+// data-dependent RNG draws).  Inside the kernel the sequential sections run on the warp's
+// lane 0; the data-parallel loops (sensing, cost matrix, LSAP column scan) take
+// (lane, nlanes) and are spread over the warp.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "muav_layout.h"
+
+namespace muav {
+
+#define HIv(name) V.hi()[HI_##name]
+#define HFv(name) V.hf()[HF_##name]
+
+enum { TT_HOLD = 0, TT_REC = 1, TT_ATT = 2, TT_DEF = 3, TT_INT = 4, TT_DET = 5 };
+enum { UT_R1 = 0, UT_R2 = 1, UT_E1 = 2, UT_F1 = 3, UT_F2 = 4, UT_T1 = 5, UT_T2 = 6 };
+enum { EV_RESET = 0, EV_FAIL = 1, EV_THREAT = 2, EV_ESC_CREATED = 3, EV_ESC_RETIRED = 4 };
+
+MUAV_HD inline double norm2(double x, double y) { return sqrt(fma(y, y, x * x)); }
+MUAV_HD inline double norm2_rows(double x, double y) { return sqrt(x * x + y * y); }
+MUAV_HD inline double dmax(double a, double b) { return a > b ? a : b; }
+MUAV_HD inline double dmin(double a, double b) { return a < b ? a : b; }
+MUAV_HD inline bool is_fighter(int ut) { return ut == UT_F1 || ut == UT_F2; }
+MUAV_HD inline bool is_recon(int ut) { return ut == UT_R1 || ut == UT_R2; }
+
+#if defined(__CUDA_ARCH__)
+#define MUAV_WARP_SYNC() __syncwarp()
+#else
+#define MUAV_WARP_SYNC() ((void)0)
+#endif
+
+struct StepResult {
+  double reward;
+  int terminated, truncated;
+};
+
+struct Sim {
+  View V;
+  const muav_config* Cp;
+  const uint32_t* tape;  // this env's tapes: [agent | tgt | mission]
+  char* scratch;
+  int32_t* out_events;   // drained events of this step (may be null)
+  int n_out_events;
+  double step_reward;
+
+  MUAV_HD const muav_config& C() const { return *Cp; }
+  MUAV_HD int A() const { return V.L->D.A; }
+  MUAV_HD int QC() const { return V.L->D.QC; }
+
+  // ------------------------------------------------------------------ RNG (oracle/rng.py rules)
+  MUAV_HD uint32_t rng_word(int stream) {
+    int32_t* cur = &V.hi()[HI_CUR_AGENT + stream];
+    int off = 0;
+    for (int s = 0; s < stream; ++s) off += C().tape_words[s];
+    if (*cur >= C().tape_words[stream]) {
+      HIv(ERRFLAGS) |= ERR_TAPE_OVERFLOW;
+      return 0u;
+    }
+    uint32_t w = tape[off + *cur];
+    *cur += 1;
+    return w;
+  }
+  MUAV_HD double rng_random(int stream) {
+    uint32_t a = rng_word(stream) >> 5;
+    uint32_t b = rng_word(stream) >> 6;
+    return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+  }
+  MUAV_HD double rng_uniform(int stream, double a, double b) { return a + (b - a) * rng_random(stream); }
+  MUAV_HD int rng_below(int stream, int n) {
+    int k = 0;
+    while ((n >> k) != 0) ++k;
+    uint32_t r = rng_word(stream) >> (32 - k);
+    int guard = 0;
+    while ((int)r >= n && guard++ < 64) r = rng_word(stream) >> (32 - k);
+    return (int)r;
+  }
+
+  // ------------------------------------------------------------------ small accessors
+  MUAV_HD double cap(int a, int c) const { return V.a_caps()[c * A() + a]; }
+  MUAV_HD void set_cap(int a, int c, double v) { V.a_caps()[c * A() + a] = v; }
+  MUAV_HD double speed_of(int a) const { return C().speed[V.a_type()[a]]; }
+  MUAV_HD double engage_of(int a) const { return C().engage[V.a_type()[a]]; }
+  MUAV_HD int qlen(int a) const { return V.a_qlen()[a]; }
+  MUAV_HD int qat(int a, int s) const { return V.a_queue()[s * A() + a]; }
+  MUAV_HD int qhead(int a) const { return V.a_qlen()[a] > 0 ? V.a_queue()[a] : 0; }
+  MUAV_HD int qfind(int a, int tid) const {
+    int n = V.a_qlen()[a];
+    for (int s = 0; s < n; ++s)
+      if (V.a_queue()[s * A() + a] == tid) return s;
+    return -1;
+  }
+  MUAV_HD double qremove(int a, int slot) {
+    int n = V.a_qlen()[a];
+    int16_t* q = V.a_queue();
+    double* qt = V.a_qtime();
+    int Aa = A();
+    double t0 = qt[slot * Aa + a];
+    for (int s = slot; s + 1 < n; ++s) {
+      q[s * Aa + a] = q[(s + 1) * Aa + a];
+      qt[s * Aa + a] = qt[(s + 1) * Aa + a];
+    }
+    V.a_qlen()[a] = (int16_t)(n - 1);
+    return t0;
+  }
+  MUAV_HD void qpush(int a, int tid, double time_at) {
+    int n = V.a_qlen()[a];
+    if (n >= QC()) {
+      HIv(ERRFLAGS) |= ERR_QUEUE_OVERFLOW;
+      return;
+    }
+    V.a_queue()[n * A() + a] = (int16_t)tid;
+    V.a_qtime()[n * A() + a] = time_at;
+    V.a_qlen()[a] = (int16_t)(n + 1);
+  }
+  MUAV_HD bool known_bit(int a, int k) const { return (V.known()[(k >> 5) * A() + a] >> (k & 31)) & 1u; }
+  MUAV_HD void set_known(int a, int k) { V.known()[(k >> 5) * A() + a] |= (1u << (k & 31)); }
+  MUAV_HD void push_event(int tag, int arg) {
+    int n = HIv(N_EVENTS);
+    if (n >= V.L->D.EVC) {
+      HIv(ERRFLAGS) |= ERR_EVENT_OVERFLOW;
+      return;
+    }
+    V.events()[n] = ((arg + 1) << 8) | tag;
+    HIv(N_EVENTS) = n + 1;
+  }
+  // allocationDetails[k] is represented by the agents whose queue holds task k+1
+  MUAV_HD int details_count(int tid) const {
+    int c = 0;
+    for (int a = 0; a < A(); ++a)
+      if (qfind(a, tid) >= 0) ++c;
+    return c;
+  }
+
+  // ------------------------------------------------------------------ Task.add/removeAgentCap
+  // DroneEnvComponents.py:280-301.  `t0` is the time stored with the entry that was just removed.
+  MUAV_HD void remove_agent_cap(int k, int a, double t0) {
+    if (V.k_status()[k] == 2) return;
+    int TC = V.L->D.TC;
+    for (int c = 0; c < 6; ++c) V.k_alloc()[c * TC + k] = V.k_alloc()[c * TC + k] - cap(a, c);
+    int tid = k + 1;
+    int cnt = 0;
+    double mn = 0.0, mx = 0.0;
+    for (int b = 0; b < A(); ++b) {
+      int s = qfind(b, tid);
+      if (s >= 0) {
+        double tm = V.a_qtime()[s * A() + b];
+        if (cnt == 0) {
+          mn = mx = tm;
+        } else {
+          if (tm < mn) mn = tm;
+          if (tm > mx) mx = tm;
+        }
+        ++cnt;
+      }
+    }
+    double dur = (double)C().duration[V.k_type()[k]];
+    if (cnt > 0) {
+      if (t0 == V.k_init()[k]) V.k_init()[k] = mn;
+      if (t0 + dur == V.k_dtime()[k]) V.k_dtime()[k] = mx + dur;
+    } else {
+      V.k_init()[k] = -1.0;
+      V.k_dtime()[k] = -1.0;
+    }
+  }
+  // DroneEnvComponents.py:306-326 (the queue entry itself is pushed by the caller)
+  MUAV_HD void add_agent_cap(int k, int a, double time_at) {
+    if (V.k_status()[k] == 2) return;
+    int TC = V.L->D.TC;
+    double end = time_at + (double)C().duration[V.k_type()[k]];
+    for (int c = 0; c < 6; ++c) V.k_alloc()[c * TC + k] = V.k_alloc()[c * TC + k] + cap(a, c);
+    if (time_at < V.k_init()[k] || V.k_init()[k] == -1.0) {
+      V.k_init()[k] = time_at;
+      if (V.k_dtime()[k] == -1.0) V.k_dtime()[k] = end;
+    }
+    if (end > V.k_dtime()[k]) V.k_dtime()[k] = end;
+    V.k_status()[k] = 1;
+  }
+
+  // ------------------------------------------------------------------ UAV methods
+  // UAV.allocate (DroneEnvComponents.py:55-95), task.id != 0
+  MUAV_HD bool allocate(int a, int tid) {
+    int k = tid - 1;
+    if (qfind(a, tid) >= 0 || V.k_status()[k] == 2) return false;
+    V.a_re_eval()[a] = 0;
+    V.a_last_task()[a] = -1;
+    double t = (double)HIv(T);
+    double time_to = norm2(V.a_nfpx()[a] - V.k_posx()[k], V.a_nfpy()[a] - V.k_posy()[k]) / speed_of(a);
+    double start = (V.a_nft()[a] - t) > 0 ? V.a_nft()[a] : t;
+    double end = start + time_to + (double)C().duration[V.k_type()[k]];
+    if (qlen(a) == 0) {
+      V.a_task_start()[a] = -1;
+      V.a_state()[a] = 1;
+    }
+    qpush(a, tid, time_to);
+    V.a_nft()[a] = end;
+    V.a_nfpx()[a] = V.k_posx()[k];
+    V.a_nfpy()[a] = V.k_posy()[k];
+    add_agent_cap(k, a, time_to);
+    return true;
+  }
+  // UAV.desAllocate (DroneEnvComponents.py:97-113)
+  MUAV_HD bool des_allocate(int a, int tid) {
+    if (tid <= 0) return false;
+    int s = qfind(a, tid);
+    if (s < 0) return false;
+    double t0 = qremove(a, s);
+    V.a_nft()[a] = (double)HIv(T);
+    V.a_nfpx()[a] = V.a_posx()[a];
+    V.a_nfpy()[a] = V.a_posy()[a];
+    V.a_commit()[a] = 0;
+    remove_agent_cap(tid - 1, a, t0);
+    return true;
+  }
+  // UAV.desallocateAll (DroneEnvComponents.py:115-119): the reference iterates the list it mutates,
+  // so only the entries at even positions are removed.
+  MUAV_HD void des_allocate_all(int a) {
+    int i = 0;
+    while (i < qlen(a)) {
+      des_allocate(a, qat(a, i));
+      ++i;
+    }
+    V.a_commit()[a] = 0;
+  }
+  // UAV.outOfService (DroneEnvComponents.py:122-127)
+  MUAV_HD void out_of_service(int a) {
+    V.a_state()[a] = -1;
+    V.a_commit()[a] = 0;
+    int i = 0;
+    while (i < qlen(a)) {
+      des_allocate(a, qat(a, i));
+      ++i;
+    }
+  }
+  // EnvUtils.desallocateAll (MultiDroneEnvUtils.py:183-205), single-task mode
+  MUAV_HD void env_desallocate_all(int a) {
+    while (qlen(a) > 0) {
+      int tid = qat(a, 0);
+      des_allocate(a, tid);
+      int k = tid - 1;
+      if (a < 32) V.k_tbl_lo()[k] &= ~(1u << a);
+      else V.k_tbl_hi()[k] &= ~(1u << (a - 32));
+    }
+    V.a_nft()[a] = (double)HIv(T);
+    V.a_nfpx()[a] = V.a_posx()[a];
+    V.a_nfpy()[a] = V.a_posy()[a];
+  }
+  // UAV.taskDone (DroneEnvComponents.py:143-179); *t0 receives the popped entry's allocation time
+  MUAV_HD bool task_done(int a, int tid, double* t0) {
+    if (qlen(a) == 0 || qat(a, 0) != tid) return false;
+    *t0 = qremove(a, 0);
+    V.a_task_start()[a] = -1;
+    int k = tid - 1;
+    if (V.k_type()[k] == TT_ATT) {
+      V.a_ammo()[a] -= 1;
+      if (V.a_ammo()[a] <= 0) set_cap(a, TT_ATT, 0.0);
+    }
+    while (qlen(a) > 0 && V.k_status()[qat(a, 0) - 1] == 2) qremove(a, 0);
+    if (qlen(a) == 0) {
+      if (V.a_re_eval()[a]) {
+        V.a_last_task()[a] = -1;
+        V.a_re_eval()[a] = 0;
+      }
+      V.a_nft()[a] = 0.0;
+      V.a_nfpx()[a] = V.a_posx()[a];
+      V.a_nfpy()[a] = V.a_posy()[a];
+      V.a_state()[a] = 0;
+    } else {
+      V.a_state()[a] = 1;
+    }
+    return true;
+  }
+  // _is_task_action_valid (DroneEnv.py:341-363)
+  MUAV_HD bool is_valid(int a, int tid) const {
+    int k = tid - 1;
+    if (V.k_status()[k] == 2) return false;
+    if (qlen(a) > 0 && qat(a, 0) == tid) return true;
+    int el = V.k_elig()[k];
+    if (el != 0 && !((el >> V.a_type()[a]) & 1)) return false;
+    int ti = V.k_type()[k];
+    int TC = V.L->D.TC;
+    if (C().capability_mask && cap(a, ti) <= 0) return false;
+    if (C().saturate_mask && V.k_alloc()[ti * TC + k] >= V.k_org_ti()[k]) return false;
+    return true;
+  }
+
+  // ------------------------------------------------------------------ WPS bookkeeping
+  // _wps_mark_window_outcome (DroneEnv.py:1543-1555)
+  MUAV_HD void mark_outcome(int k, bool success) {
+    if (V.k_deadline()[k] < 0 || V.k_counted()[k]) return;
+    V.k_counted()[k] = 1;
+    if (success && HIv(T) <= V.k_deadline()[k]) {
+      HIv(N_ON_TIME) += 1;
+      HFv(F_REWARD) += C().on_time_bonus;
+    } else {
+      HIv(N_MISSED) += 1;
+      HFv(F_REWARD) -= C().miss_penalty;
+    }
+  }
+  // Task ctor + env.tasks.append (DroneEnvComponents.py:224-263); returns task id or 0 on overflow
+  MUAV_HD int new_task(double px, double py, int ti) {
+    int k = HIv(N_TASKS);
+    int TC = V.L->D.TC;
+    if (k >= TC) {
+      HIv(ERRFLAGS) |= ERR_TASK_OVERFLOW;
+      return 0;
+    }
+    HIv(N_TASKS) = k + 1;
+    V.k_posx()[k] = px;
+    V.k_posy()[k] = py;
+    V.k_type()[k] = (int16_t)ti;
+    V.k_status()[k] = 0;
+    for (int c = 0; c < 6; ++c) {
+      V.k_cur()[c * TC + k] = 0.0;
+      V.k_alloc()[c * TC + k] = 0.0;
+    }
+    V.k_done_ti()[k] = 0.0;
+    V.k_org_ti()[k] = 0.0;
+    V.k_init()[k] = -1.0;
+    V.k_dtime()[k] = -1.0;
+    V.k_created()[k] = 0;
+    V.k_deadline()[k] = -1;
+    V.k_counted()[k] = 0;
+    V.k_fq()[k] = -1;
+    V.k_kind()[k] = 0;
+    V.k_req_agents()[k] = 0;
+    V.k_elig()[k] = 0;
+    V.k_threat()[k] = -1;
+    V.k_prot_agent()[k] = -1;
+    V.k_prot_task()[k] = 0;
+    V.k_reveal()[k] = -1;
+    V.k_tbl_lo()[k] = 0;
+    V.k_tbl_hi()[k] = 0;
+    V.k_reached()[k] = 0;
+    return k + 1;
+  }
+  // _register_dynamic_task (DroneEnv.py:1491-1504)
+  MUAV_HD void register_dynamic(int tid) {
+    int k = tid - 1;
+    if (C().hard_windows && V.k_deadline()[k] < 0) {
+      V.k_deadline()[k] = (int16_t)(HIv(T) + C().window_length);
+      HIv(N_WINDOWED) += 1;
+    }
+    if (C().threat_delay > 0 || C().sense_radius > 0) {
+      int d = C().threat_delay > 0 ? C().threat_delay : 0;
+      V.k_reveal()[k] = (int16_t)(HIv(T) + d);
+    } else {
+      for (int a = 0; a < A(); ++a) set_known(a, k);
+    }
+  }
+  // _counts_for_mission_done (DroneEnv.py:1878-1886)
+  MUAV_HD bool all_done() const {
+    int n = V.hi()[HI_N_TASKS];
+    for (int k = 0; k < n; ++k) {
+      int ti = V.k_type()[k];
+      if (V.k_kind()[k] == 1 || ti == TT_DET || ti == TT_HOLD) continue;
+      if (V.k_status()[k] != 2) return false;
+    }
+    return true;
+  }
+  MUAV_HD void mark_reached(int k) {
+    if (!V.k_reached()[k]) {
+      V.k_reached()[k] = 1;
+      HIv(N_REACHED) += 1;
+    }
+  }
+
+  // releaseAllTasks (DroneEnv.py:1442-1480); for_type == -1 indexes the Det column
+  MUAV_HD void release_all(int for_type) {
+    int col = for_type < 0 ? 6 + for_type : for_type;
+    uint32_t avail = 0;
+    for (int a = 0; a < A(); ++a) {
+      if (cap(a, col) > 0) {
+        if (V.a_state()[a] != -1) {
+          V.a_re_eval()[a] = 1;
+          V.a_last_task()[a] = qhead(a);
+          des_allocate_all(a);
+          avail |= 1u << V.a_type()[a];
+        }
+      }
+    }
+    int n = HIv(N_TASKS);
+    for (int k = 0; k < n; ++k) {
+      if (V.k_status()[k] != 2 && V.k_type()[k] == for_type) {
+        bool any = false;
+        for (int ut = 0; ut < MUAV_N_UAV_TYPES; ++ut)
+          if (((avail >> ut) & 1u) && C().cap_table[ut][for_type] != 0.0) any = true;
+        if (!any) {
+          V.k_status()[k] = 2;
+          if (!V.k_reached()[k]) {
+            V.k_reached()[k] = 1;
+            HIv(N_REACHED) += 1;
+            if (HIv(N_REACHED) == C().n_tasks_cfg) HIv(CONCLUSION) = HIv(T);
+          }
+        } else {
+          V.k_status()[k] = 0;
+          V.k_tbl_lo()[k] = 0;
+          V.k_tbl_hi()[k] = 0;
+        }
+      }
+    }
+  }
+
+  // get_closest_agent (DroneEnv.py:1691-1723)
+  MUAV_HD int closest_agent(double px, double py) const {
+    double min_f = INFINITY, min_w = INFINITY;
+    int cf = -1, cw = -1;
+    for (int a = 0; a < A(); ++a) {
+      int st = V.a_state()[a];
+      if (st != -1 && st != 4) {
+        double d = norm2(V.a_posx()[a] - px, V.a_posy()[a] - py);
+        if (is_fighter(V.a_type()[a])) {
+          if (d < min_f) { min_f = d; cf = a; }
+        } else {
+          if (d < min_w) { min_w = d; cw = a; }
+        }
+      }
+    }
+    return cw != -1 ? cw : cf;
+  }
+
+  // generate_threat + TaskFromThreat (DroneEnv.py:1601-1643,1861-1876)
+  MUAV_HD void generate_threat() {
+    int t = HIv(T);
+    int TC = V.L->D.TC;
+    for (int g = 0; g < C().n_groups; ++g) {
+      int* gnext = &V.hi()[HI_GROUP_NEXT0 + g];
+      int gend = C().group_start[g + 1];
+      int left = gend - *gnext;
+      if (left > 0 && t > 40 && t % 10 == 0) {
+        if (rng_random(0) < C().threat_gen_prob) {
+          int n_spawn = 1;
+          if (C().burst_mode) n_spawn = C().burst_size < left ? C().burst_size : left;
+          for (int bi = 0; bi < n_spawn; ++bi) {
+            if (*gnext >= gend) break;
+            int hid = *gnext;
+            *gnext += 1;
+            if (C().dual_region_bursts) {
+              double mid = C().area_w * 0.5;
+              double wide = dmax(C().threat_wide, 40.0);
+              double x;
+              if ((HIv(BURST_TOGGLE) + bi) % 2 == 0) x = rng_uniform(0, wide, mid - wide);
+              else x = rng_uniform(0, mid + wide, C().area_w - wide);
+              V.h_posx()[hid] = x;
+            }
+            double hx = V.h_posx()[hid], hy = V.h_posy()[hid];
+            int tgt = closest_agent(hx, hy);
+            V.h_target()[hid] = (int16_t)tgt;
+            V.h_mission()[hid] = (int16_t)tgt;
+            int tid = new_task(hx, hy, TT_INT);
+            if (tid == 0) return;
+            int k = tid - 1;
+            int ht = V.h_type()[hid];
+            V.k_cur()[TT_INT * TC + k] = 2.0;
+            V.k_cur()[TT_ATT * TC + k] = C().cap_table[ht][3] * 2;
+            V.k_cur()[TT_DEF * TC + k] = C().cap_table[ht][2] * 2;
+            V.k_org_ti()[k] = 2.0;
+            V.k_threat()[k] = (int16_t)hid;
+            V.k_created()[k] = (int16_t)t;
+            if (ht == UT_T1) {
+              V.k_req_agents()[k] = 2;
+              V.k_elig()[k] = (int16_t)C().escort_type_mask;
+            }
+            V.h_task()[hid] = (int16_t)tid;
+            V.h_spawned()[hid] = 1;
+            V.h_order()[HIv(N_ACTIVE)] = (int16_t)hid;
+            HIv(N_ACTIVE) += 1;
+            int dk = V.h_det_task()[hid] - 1;
+            V.k_cur()[TT_DET * TC + dk] = V.k_cur()[TT_DET * TC + dk] - 1.0;
+            register_dynamic(tid);
+            push_event(EV_THREAT, tid);
+            push_event(EV_RESET, TT_INT);
+            HIv(PENDING_RESET) = 1;
+          }
+          if (C().dual_region_bursts && n_spawn > 0) HIv(BURST_TOGGLE) = (HIv(BURST_TOGGLE) + 1) % 2;
+        }
+      }
+    }
+  }
+
+  // _escort_fighters_near (DroneEnv.py:1746-1764): ids sorted by distance (stable) into out[], returns count
+  MUAV_HD int fighters_near(int prot, double radius, int16_t* out, double* dtmp) const {
+    if (prot < 0) return 0;
+    int esc = V.a_escort()[prot];
+    if (esc == 0 || V.k_status()[esc - 1] == 2) return 0;
+    double px = V.a_posx()[prot], py = V.a_posy()[prot];
+    int n = 0;
+    for (int a = 0; a < A(); ++a) {
+      if (V.a_state()[a] == -1 || !((C().escort_type_mask >> V.a_type()[a]) & 1)) continue;
+      if (qlen(a) == 0 || qat(a, 0) != esc) continue;
+      double d = norm2(V.a_posx()[a] - px, V.a_posy()[a] - py);
+      if (d <= radius) {
+        int j = n;
+        while (j > 0 && dtmp[j - 1] > d) {
+          dtmp[j] = dtmp[j - 1];
+          out[j] = out[j - 1];
+          --j;
+        }
+        dtmp[j] = d;
+        out[j] = (int16_t)a;
+        ++n;
+      }
+    }
+    return n;
+  }
+  MUAV_HD double* near_d() const { return (double*)scratch + 3 * V.L->D.A; }
+  MUAV_HD int16_t* near_i() const { return (int16_t*)((double*)scratch + 4 * V.L->D.A); }
+
+  // _retarget_threat_via_escort (DroneEnv.py:1766-1779)
+  MUAV_HD void retarget_via_escort(int hid) {
+    int mission = V.h_mission()[hid] >= 0 ? V.h_mission()[hid] : V.h_target()[hid];
+    if (mission < 0 || V.a_state()[mission] == -1) return;
+    if (!is_recon(V.a_type()[mission])) return;
+    int n = fighters_near(mission, C().escort_intercept_radius, near_i(), near_d());
+    if (n == 0) {
+      V.h_target()[hid] = (int16_t)mission;
+      return;
+    }
+    V.h_target()[hid] = near_i()[0];
+  }
+  // _release_escort_agents (DroneEnv.py:1919-1936)
+  MUAV_HD void release_escort_agents(int esc) {
+    for (int a = 0; a < A(); ++a) {
+      if (V.a_state()[a] == -1) continue;
+      if (qfind(a, esc) >= 0) {
+        des_allocate(a, esc);
+        if (qlen(a) == 0) {
+          V.a_state()[a] = 0;
+          V.a_commit()[a] = 0;
+          V.a_nft()[a] = (double)HIv(T);
+          V.a_nfpx()[a] = V.a_posx()[a];
+          V.a_nfpy()[a] = V.a_posy()[a];
+        }
+      }
+    }
+  }
+  // _retire_escort (DroneEnv.py:1938-1950)
+  MUAV_HD void retire_escort(int esc, bool failed) {
+    if (esc == 0 || V.k_status()[esc - 1] == 2) return;
+    release_escort_agents(esc);
+    V.k_status()[esc - 1] = 2;
+    int recon = V.k_prot_agent()[esc - 1];
+    if (recon >= 0) V.a_escort()[recon] = 0;
+    if (failed) HIv(ESC_FAILED) += 1;
+    else HIv(ESC_COMPLETED) += 1;
+    push_event(EV_ESC_RETIRED, esc);
+  }
+  // _create_escort_for (DroneEnv.py:1888-1917)
+  MUAV_HD void create_escort_for(int a, int rec_tid) {
+    if (!C().escort_enabled) return;
+    if (V.a_escort()[a] != 0) return;
+    int tid = new_task(V.a_posx()[a], V.a_posy()[a], TT_DEF);
+    if (tid == 0) return;
+    int k = tid - 1;
+    int TC = V.L->D.TC;
+    V.k_cur()[TT_DEF * TC + k] = C().escort_requirement;
+    V.k_org_ti()[k] = C().escort_requirement;
+    V.k_kind()[k] = 1;
+    V.k_prot_agent()[k] = (int16_t)a;
+    V.k_prot_task()[k] = (int16_t)rec_tid;
+    V.k_elig()[k] = (int16_t)C().escort_type_mask;
+    V.k_req_agents()[k] = (int16_t)C().escort_required_agents;
+    V.k_created()[k] = (int16_t)HIv(T);
+    register_dynamic(tid);
+    V.a_escort()[a] = tid;
+    HIv(ESC_REQUESTS) += 1;
+    push_event(EV_ESC_CREATED, tid);
+    push_event(EV_RESET, TT_DEF);
+    HIv(PENDING_RESET) = 1;
+  }
+
+  // handle_threat_engagement (DroneEnv.py:1781-1858)
+  MUAV_HD void engage(int hid) {
+    int nd = 0;
+    int primary = V.h_target()[hid];
+    int mission = V.h_mission()[hid] >= 0 ? V.h_mission()[hid] : primary;
+    int16_t* defenders = near_i();
+    if (C().escort_enabled && mission >= 0 && is_recon(V.a_type()[mission])) {
+      nd = fighters_near(mission, C().mutual_support_radius, defenders, near_d());
+      if (nd > 0) {
+        primary = defenders[0];
+        V.h_target()[hid] = (int16_t)primary;
+      }
+    }
+    if (primary < 0) return;
+    int ht = V.h_type()[hid];
+    double att = C().cap_table[ht][2], dfn = C().cap_table[ht][3], erng = C().engage[ht];
+    double att_d, def_d, eng_d;
+    if (nd >= 2) {
+      HIv(MUTUAL) += 1;
+      double att_sum = 0.0, def_sum = 0.0, eng_sum = 0.0;
+      for (int i = 0; i < nd; ++i) att_sum = att_sum + cap(defenders[i], 2);
+      for (int i = 0; i < nd; ++i) def_sum = def_sum + cap(defenders[i], 3);
+      for (int i = 0; i < nd; ++i) eng_sum = eng_sum + engage_of(defenders[i]);
+      eng_sum = eng_sum / (double)nd;
+      att_d = att_sum / dmax(att, 1e-6);
+      def_d = def_sum / dmax(dfn, 1e-6);
+      eng_d = eng_sum / dmax(erng, 1e-6);
+    } else {
+      att_d = cap(primary, 2) / dmax(att, 1e-6);
+      def_d = cap(primary, 3) / dmax(dfn, 1e-6);
+      eng_d = engage_of(primary) / dmax(erng, 1e-6);
+    }
+    double avg = (att_d + def_d + eng_d) / 3;
+    double prob = avg / (avg + 1);
+    double rnd = rng_random(0);
+    int tid = V.h_task()[hid];
+    int k = tid - 1;
+    if (rnd < prob) {
+      V.h_status()[hid] = 2;
+      V.k_status()[k] = 2;
+      mark_outcome(k, true);
+      HIv(INTERCEPTED) += 1;
+      V.a_ammo()[primary] -= 1;
+      if (V.a_ammo()[primary] <= 0) set_cap(primary, 3, 0.0);
+      if (qlen(primary) > 0 && qat(primary, 0) == tid) {
+        double t0;
+        task_done(primary, tid, &t0);
+      }
+      step_reward += 1.0;
+    } else {
+      V.h_ammo()[hid] -= 1;
+      V.a_ammo()[primary] -= 1;
+      if (V.a_ammo()[primary] <= 0) {
+        set_cap(primary, 3, 0.0);
+        int pt = V.a_type()[primary];
+        bool was_recon = is_recon(pt);
+        bool was_escort = (C().escort_type_mask >> pt) & 1;
+        out_of_service(primary);
+        if (was_recon) {
+          HIv(RECON_LOSSES) += 1;
+          HIv(BREACHES) += 1;
+          retire_escort(V.a_escort()[primary], true);
+        } else if (was_escort) {
+          HIv(ESCORT_LOSSES) += 1;
+        }
+        step_reward -= 1.0;
+      }
+      if (V.h_ammo()[hid] <= 0) {
+        V.h_status()[hid] = 0;
+        V.k_status()[k] = 2;
+        mark_outcome(k, false);
+      } else {
+        int tgt = closest_agent(V.h_posx()[hid], V.h_posy()[hid]);
+        V.h_target()[hid] = (int16_t)tgt;
+        V.h_mission()[hid] = (int16_t)tgt;
+      }
+    }
+  }
+
+  // update_threats (DroneEnv.py:1725-1744)
+  MUAV_HD void update_threats() {
+    int n = HIv(N_ACTIVE);
+    for (int i = 0; i < n; ++i) {
+      int hid = V.h_order()[i];
+      if (V.h_status()[hid] == 2) continue;
+      double sp = C().speed[V.h_type()[hid]];
+      double hx = V.h_posx()[hid], hy = V.h_posy()[hid];
+      if (V.h_status()[hid] == 0 || V.h_target()[hid] < 0) {
+        hx = hx + sp * 0.0;
+        hy = hy + sp * -1.0;
+        V.h_posx()[hid] = hx;
+        V.h_posy()[hid] = hy;
+      } else {
+        if (C().escort_enabled) retarget_via_escort(hid);
+        int tg = V.h_target()[hid];
+        double dx = V.a_posx()[tg] - hx, dy = V.a_posy()[tg] - hy;
+        double mag = norm2(dx, dy);
+        double nx = 0.0, ny = 0.0;
+        if (mag != 0) { nx = dx / mag; ny = dy / mag; }
+        hx = hx + sp * nx;
+        hy = hy + sp * ny;
+        V.h_posx()[hid] = hx;
+        V.h_posy()[hid] = hy;
+        if (norm2(V.a_posx()[tg] - hx, V.a_posy()[tg] - hy) < C().engage[V.h_type()[hid]]) engage(hid);
+      }
+      int k = V.h_task()[hid] - 1;
+      V.k_posx()[k] = V.h_posx()[hid];
+      V.k_posy()[k] = V.h_posy()[hid];
+      if (V.h_posy()[hid] <= 0) {
+        V.k_status()[k] = 2;
+        mark_outcome(k, false);
+      }
+    }
+  }
+
+  // random_position (DroneEnv.py:1371-1410) for mission-area draws of the target stream
+  MUAV_HD bool random_position_area(int stream, int area, double* ox, double* oy) {
+    const double* m = &V.hf()[HF_M0_X + 4 * area];
+    int nobs = V.L->D.NOBS;
+    for (int tries = 0; tries < 100; ++tries) {
+      double x = rng_uniform(stream, m[0], m[0] + m[2]);
+      double y = rng_uniform(stream, m[1], m[1] + m[3]);
+      bool ok = true;
+      for (int o = 0; o < nobs; ++o) {
+        const double* ob = &V.obst()[3 * o];
+        double d = norm2(x - ob[0], y - ob[1]) - 3;
+        if (d < ob[2] + 20) { ok = false; break; }
+      }
+      if (ok) { *ox = x; *oy = y; return true; }
+    }
+    HIv(ERRFLAGS) |= ERR_NO_SPACE;
+    return false;
+  }
+
+  // inject_dynamic_arrivals (DroneEnv.py:1646-1689); the rate draw precedes the capacity gate
+  MUAV_HD void inject_arrivals() {
+    if (C().arrival_rate <= 0 || HIv(T) < 5) return;
+    if (rng_random(1) >= C().arrival_rate) return;
+    if (HIv(N_TASKS) >= C().max_tasks - 1) return;
+    int ti = rng_below(1, 2) == 0 ? TT_ATT : TT_REC;
+    int area = rng_below(2, 3);
+    double x, y;
+    if (C().dual_region_bursts) {
+      double mid = C().area_w * 0.5;
+      double wide = 40.0;
+      if (rng_random(1) < 0.5) x = rng_uniform(1, wide, mid - wide);
+      else x = rng_uniform(1, mid + wide, C().area_w - wide);
+      y = rng_uniform(1, C().area_h * 0.2, C().area_h * 0.8);
+    } else {
+      if (!random_position_area(1, area, &x, &y)) return;
+    }
+    int tid = new_task(x, y, ti);
+    if (tid == 0) return;
+    int k = tid - 1;
+    int TC = V.L->D.TC;
+    V.k_cur()[ti * TC + k] = 1.0;
+    V.k_org_ti()[k] = 1.0;
+    V.k_created()[k] = (int16_t)HIv(T);
+    HIv(N_ARRIVALS) += 1;
+    register_dynamic(tid);
+    push_event(EV_THREAT, tid);
+    push_event(EV_RESET, ti);
+    HIv(PENDING_RESET) = 1;
+  }
+
+  // _sync_escorts (DroneEnv.py:1964-2000)
+  MUAV_HD void sync_escorts() {
+    for (int a = 0; a < A(); ++a) {
+      if (V.a_state()[a] == -1 || !is_recon(V.a_type()[a])) continue;
+      if (qlen(a) == 0) continue;
+      int cur = qat(a, 0);
+      if (V.k_type()[cur - 1] == TT_REC && V.k_status()[cur - 1] != 2 && V.a_escort()[a] == 0) create_escort_for(a, cur);
+    }
+    // dict insertion order == ascending escort task id
+    int prev = 0;
+    for (;;) {
+      int esc = 0, recon = -1;
+      for (int a = 0; a < A(); ++a) {
+        int e = V.a_escort()[a];
+        if (e > prev && (esc == 0 || e < esc)) { esc = e; recon = a; }
+      }
+      if (esc == 0) break;
+      prev = esc;
+      int k = esc - 1;
+      int rec_task = V.k_prot_task()[k];
+      bool dead = V.a_state()[recon] == -1;
+      int st = V.a_state()[recon];
+      bool idle = qlen(recon) == 0 || st == 0 || st == 3;
+      bool rec_done = rec_task != 0 && V.k_status()[rec_task - 1] == 2;
+      bool wrong = qlen(recon) > 0 && (rec_task == 0 || qat(recon, 0) != rec_task);
+      if (dead || idle || rec_done || wrong) {
+        retire_escort(esc, dead);
+        continue;
+      }
+      V.k_posx()[k] = V.a_posx()[recon];
+      V.k_posy()[k] = V.a_posy()[recon];
+      HIv(ESC_REQ_STEPS) += 1;
+      if (fighters_near(recon, C().escort_radius, near_i(), near_d()) > 0) HIv(ESC_COV_STEPS) += 1;
+    }
+  }
+
+  // _wps_update_sensing (DroneEnv.py:1506-1523): independent per (agent, task) -> spread over lanes
+  MUAV_HD void update_sensing(int lane, int nlanes) {
+    if (C().sense_radius <= 0) return;
+    int n = HIv(N_TASKS);
+    int Aa = A();
+    for (int idx = lane; idx < Aa * n; idx += nlanes) {
+      int a = idx / n, k = idx - a * n;
+      if (V.a_state()[a] == -1) continue;
+      if (V.k_status()[k] == 2 || known_bit(a, k)) continue;
+      if (V.k_created()[k] <= 0 && V.k_deadline()[k] < 0) continue;
+      double d = norm2(V.a_posx()[a] - V.k_posx()[k], V.a_posy()[a] - V.k_posy()[k]);
+      if (d <= C().sense_radius) {
+#if defined(__CUDA_ARCH__)
+        atomicOr(&V.known()[(k >> 5) * Aa + a], 1u << (k & 31));
+#else
+        set_known(a, k);
+#endif
+      }
+    }
+  }
+  // _wps_process_reveals (DroneEnv.py:1525-1541)
+  MUAV_HD void process_reveals() {
+    int n = HIv(N_TASKS);
+    int t = HIv(T);
+    for (int k = 0; k < n; ++k) {
+      int rt = V.k_reveal()[k];
+      if (rt >= 0 && t >= rt) {
+        V.k_reveal()[k] = -1;
+        if (C().share_knowledge)
+          for (int a = 0; a < A(); ++a) set_known(a, k);
+      }
+    }
+  }
+  // _wps_expire_windows (DroneEnv.py:1557-1573)
+  MUAV_HD void expire_windows() {
+    if (!C().hard_windows) return;
+    int n = HIv(N_TASKS);
+    int t = HIv(T);
+    for (int k = 0; k < n; ++k) {
+      int dl = V.k_deadline()[k];
+      if (dl < 0 || V.k_status()[k] == 2) continue;
+      if (t > dl) {
+        V.k_status()[k] = 2;
+        V.k_fq()[k] = 0;
+        mark_outcome(k, false);
+        mark_reached(k);
+        for (int a = 0; a < A(); ++a)
+          if (qlen(a) > 0 && qat(a, 0) == k + 1) des_allocate_all(a);
+      }
+    }
+  }
+
+  // core_sim::SimCore::avoid_obstacles (core_sim/src/sim_core.rs:24-59)
+  MUAV_HD static void avoid_obstacles(const double* obst, int nobs, double px, double py, double mx, double my,
+                                      double* ax, double* ay) {
+    const double PI = 3.14159265358979323846;
+    double sx = 0.0, sy = 0.0;
+    for (int o = 0; o < nobs; ++o) {
+      double dx = obst[3 * o] - px, dy = obst[3 * o + 1] - py;
+      double d = sqrt(dx * dx + dy * dy);
+      double dz = d - obst[3 * o + 2];
+      if (dz < 40.0) {
+        double nx = dx / dz, ny = dy / dz;
+        double f = 0.5 / (1.0 - log(dmax(1.05, dz)));
+        double ang = atan2(my, mx) - atan2(dy, dx);
+        ang = fmod(ang + PI, 2.0 * PI) - PI;
+        double rx, ry;
+        if (ang > 0.0) { rx = ny; ry = -nx; }
+        else { rx = -ny; ry = nx; }
+        sx += rx * f;
+        sy += ry * f;
+      }
+    }
+    *ax = sx;
+    *ay = sy;
+  }
+
+  // NumPy pairwise_sum for n <= 128 (np.sum(dists), DroneEnv.py:1138)
+  MUAV_HD static double np_sum(const double* a, int n) {
+    if (n < 8) {
+      double res = 0.0;
+      for (int i = 0; i < n; ++i) res += a[i];
+      return res;
+    }
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    int lim = n - (n % 8);
+    for (; i < lim; i += 8)
+      for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+  }
+
+  // task id of the idx-th open task of last_tasks_info (DroneEnv.py:492,827-830); 0 if out of range
+  MUAV_HD int open_task_at(int idx) const {
+    int n_open = V.hi()[HI_N_OPEN];
+    if (idx < 0) idx += n_open;  // Python negative indexing
+    if (idx < 0 || idx >= n_open) return 0;
+    int KW = V.L->D.KW;
+    for (int w = 0; w < KW; ++w) {
+      uint32_t m = V.open_mask()[w];
+      int c = 0;
+      uint32_t mm = m;
+      while (mm) { mm &= mm - 1; ++c; }
+      if (idx < c) {
+        for (int b = 0; b < 32; ++b)
+          if ((m >> b) & 1u) {
+            if (idx == 0) return w * 32 + b + 1;
+            --idx;
+          }
+      }
+      idx -= c;
+    }
+    return 0;
+  }
+  MUAV_HD bool in_last_open(int tid) const { return (V.open_mask()[(tid - 1) >> 5] >> ((tid - 1) & 31)) & 1u; }
+
+  // ------------------------------------------------------------------ step: part 1 (lane 0)
+  // events drain, actions, kinematics FSM, distances, threats, arrivals, escorts.
+  // act_agent/act_tid: ordered (agent, task id) pairs, tid == 0 encodes an out-of-range index.
+  struct Acc {
+    double action_reward, distance_reward, quality_reward, S_q, time_pen, alloc_reward;
+  };
+
+  MUAV_HD void step_pre(const int16_t* act_agent, const int16_t* act_tid, int n_act, Acc& acc) {
+    acc.action_reward = 0.0;
+    acc.distance_reward = 0.0;
+    acc.quality_reward = 0.0;
+    acc.S_q = 0.0;
+    step_reward = 0.0;
+    int Aa = A();
+    int TC = V.L->D.TC;
+    HIv(T) += 1;
+    int t = HIv(T);
+    double* prev_x = (double*)scratch;
+    double* prev_y = prev_x + Aa;
+    double* dists = prev_y + Aa;
+    for (int a = 0; a < Aa; ++a) {
+      prev_x[a] = V.a_posx()[a];
+      prev_y[a] = V.a_posy()[a];
+    }
+    // drain events (DroneEnv.py:800-805)
+    int nev = HIv(N_EVENTS);
+    int tagmask = 0;
+    n_out_events = nev;
+    HIv(N_EVENTS) = 0;
+    // events are processed from a private copy because release_all never appends (asserted by the oracle)
+    for (int i = 0; i < nev; ++i) {
+      int ev = V.events()[i];
+      if (out_events) out_events[i] = ev;
+      int tag = ev & 0xff;
+      tagmask |= 1 << tag;
+    }
+    HIv(EV_TAGMASK) = tagmask;
+    for (int i = 0; i < nev; ++i) {
+      int ev = V.events()[i];
+      if ((ev & 0xff) == EV_RESET) release_all((ev >> 8) - 1);
+    }
+
+    // ---- actions (DroneEnv.py:810-933)
+    for (int i = 0; i < n_act; ++i) {
+      int a = act_agent[i];
+      if (a < 0 || a >= Aa) continue;
+      if (V.a_state()[a] == -1) continue;
+      int tid = act_tid[i];
+      if (tid <= 0) {
+        acc.action_reward += -1;
+        continue;
+      }
+      int k = tid - 1;
+      int head = qhead(a);
+      if (head != tid) {
+        if (head != 0) {
+          acc.S_q -= 0.1;
+          acc.S_q -= cap(a, V.k_type()[head - 1]);
+          HIv(N_REALLOC) += 1;
+          HIv(N_SWITCH) += 1;
+          V.a_commit()[a] = 0;
+          double ax = V.a_posx()[a], ay = V.a_posy()[a];
+          double d_old = norm2(ax - V.k_posx()[head - 1], ay - V.k_posy()[head - 1]);
+          double d_new = norm2(ax - V.k_posx()[k], ay - V.k_posy()[k]);
+          acc.distance_reward += (d_old - d_new) / C().max_coord;
+        } else {
+          acc.S_q += 0.05;
+          if (HIv(PENDING_RESET) && C().dynamic_idle_penalty != 0.0) acc.S_q -= C().dynamic_idle_penalty;
+        }
+      } else {
+        acc.S_q += 0.05;
+        continue;
+      }
+      if (!C().multiple_tasks_per_agent) env_desallocate_all(a);
+      if (!is_valid(a, tid)) {
+        acc.action_reward += -1;
+        continue;
+      }
+      if (allocate(a, tid)) {
+        if (a < 32) V.k_tbl_lo()[k] |= 1u << a;
+        else V.k_tbl_hi()[k] |= 1u << (a - 32);
+        int ti = V.k_type()[k];
+        double cp = cap(a, ti);
+        double missing = V.k_cur()[ti * TC + k] - (V.k_alloc()[ti * TC + k] - cp);
+        missing = missing > 0 ? missing : 0.0;
+        double rest = missing - cp;
+        double added = missing - (rest > 0 ? rest : 0.0);
+        if (added <= 0) acc.S_q -= 1.5;
+        acc.S_q += added;
+        V.k_status()[k] = 1;
+        // calculate_agent_expected_reward (DroneEnv.py:1216-1229)
+        double rx, ry;
+        int ql = qlen(a);
+        if (ql >= 2) {
+          int pk = qat(a, ql - 2) - 1;
+          rx = V.k_posx()[pk];
+          ry = V.k_posy()[pk];
+        } else {
+          rx = V.a_posx()[a];
+          ry = V.a_posy()[a];
+        }
+        acc.distance_reward += -1.0 * norm2(V.a_nfpx()[a] - rx, V.a_nfpy()[a] - ry) / C().max_coord;
+        if (V.a_state()[a] != 1 && V.a_state()[a] != -1) V.a_state()[a] = 1;
+        if (C().escort_enabled && ti == TT_REC && is_recon(V.a_type()[a]) && V.a_escort()[a] == 0) create_escort_for(a, tid);
+      }
+    }
+
+    // ---- kinematics FSM (DroneEnv.py:965-1129)
+    const double bx = C().base_x, by = C().base_y;
+    int nobs = V.L->D.NOBS;
+    for (int a = 0; a < Aa; ++a) {
+      if (V.a_state()[a] == -1) continue;
+      if (V.a_fail_event()[a] == t) {
+        V.a_state()[a] = -1;
+        des_allocate_all(a);
+        push_event(EV_RESET, -1);
+        push_event(EV_FAIL, a);
+        HIv(PENDING_RESET) = 1;
+        continue;
+      }
+      double mvx = 0.0, mvy = 0.0, avx = 0.0, avy = 0.0;
+      double px = V.a_posx()[a], py = V.a_posy()[a];
+      double speed = speed_of(a);
+      if (V.a_state()[a] == 0 && !V.a_re_eval()[a]) {
+        if (qlen(a) == 0 && norm2(px - bx, py - by) > speed + 5) V.a_state()[a] = 3;
+      }
+      int cur = V.a_re_eval()[a] ? V.a_last_task()[a] : qhead(a);
+      if (cur > 0 && V.k_status()[cur - 1] == 2) {
+        des_allocate(a, cur);
+        V.a_re_eval()[a] = 0;
+        V.a_last_task()[a] = -1;
+      } else if (cur > 0) {
+        int k = cur - 1;
+        int ti = V.k_type()[k];
+        double tx = V.k_posx()[k], ty = V.k_posy()[k];
+        if (V.a_state()[a] == 1) {
+          double dx = tx - px, dy = ty - py;
+          double d = norm2(dx, dy);
+          double nx = 0.0, ny = 0.0;
+          if (!(fabs(d) < 1e-12)) { nx = dx / d; ny = dy / d; }
+          if (ti == TT_INT) {
+            if (d < engage_of(a)) {
+              V.a_state()[a] = 2;
+              V.h_target()[V.k_threat()[k]] = (int16_t)a;
+              V.a_task_start()[a] = t;
+            } else {
+              mvx = nx; mvy = ny;
+              avoid_obstacles(V.obst(), nobs, px, py, mvx, mvy, &avx, &avy);
+            }
+          } else if (d < speed) {
+            V.a_state()[a] = 2;
+            V.a_task_start()[a] = t;
+            V.a_posx()[a] = px = tx;
+            V.a_posy()[a] = py = ty;
+          } else {
+            mvx = nx; mvy = ny;
+            avoid_obstacles(V.obst(), nobs, px, py, mvx, mvy, &avx, &avy);
+          }
+        } else if (V.a_state()[a] == 2) {
+          if (ti == TT_INT) {
+            double d = norm2(tx - px, ty - py);
+            if (d >= engage_of(a)) V.a_state()[a] = 1;
+          }
+          if (V.a_task_start()[a] == -1) {
+            V.a_task_start()[a] = t;
+            V.a_posx()[a] = px = tx;
+            V.a_posy()[a] = py = ty;
+          } else if ((t - V.a_task_start()[a]) >= C().duration[ti] && (ti == TT_REC || ti == TT_ATT) && V.k_status()[k] != 2) {
+            double t0 = 0.0;
+            bool popped = task_done(a, cur, &t0);
+            V.k_done_ti()[k] = V.k_done_ti()[k] + cap(a, ti);
+            for (int c = 0; c < 6; ++c) V.k_cur()[c * TC + k] = V.k_cur()[c * TC + k] - cap(a, c);
+            if (popped) {
+              remove_agent_cap(k, a, t0);
+            } else if (qfind(a, cur) >= 0) {
+              HIv(ERRFLAGS) |= 64;  // details/queue invariant broken (never observed)
+            }
+            if (V.k_done_ti()[k] >= V.k_org_ti()[k]) {
+              if (V.k_kind()[k] != 1) mark_reached(k);
+              if (V.k_status()[k] != 2) {
+                acc.quality_reward += V.k_org_ti()[k] * 2;
+                HFv(F_REWARD) += V.k_org_ti()[k] * 1 / HFv(NORM_FACTOR);
+                if (V.k_kind()[k] != 1) mark_outcome(k, true);
+                V.k_status()[k] = 2;
+                if (ti == TT_REC && is_recon(V.a_type()[a])) {
+                  HIv(PROT_REC_DONE) += 1;
+                  retire_escort(V.a_escort()[a], false);
+                }
+                if (all_done()) HIv(CONCLUSION) = t;
+              }
+            } else {
+              acc.quality_reward += cap(a, ti);
+            }
+          }
+        }
+      }
+      if (V.a_state()[a] == 3) {
+        px = V.a_posx()[a];
+        py = V.a_posy()[a];
+        if (norm2(px - bx, py - by) < speed + 5) {
+          V.a_state()[a] = 0;
+        } else {
+          double dx = bx - px, dy = by - py;
+          double mag = norm2(dx, dy);
+          if (mag == 0) { mvx = 0.0; mvy = 0.0; }
+          else { mvx = dx / mag; mvy = dy / mag; }
+          avoid_obstacles(V.obst(), nobs, px, py, mvx, mvy, &avx, &avy);
+        }
+      }
+      double sx = mvx + avx, sy = mvy + avy;
+      double mag = norm2(sx, sy);
+      double ux = 0.0, uy = 0.0;
+      if (mag != 0) { ux = sx / mag; uy = sy / mag; }
+      px = V.a_posx()[a] + ux * speed;
+      py = V.a_posy()[a] + uy * speed;
+      px = dmin(dmax(px, 0.0), C().area_w);
+      py = dmin(dmax(py, 0.0), C().area_h);
+      V.a_posx()[a] = px;
+      V.a_posy()[a] = py;
+    }
+
+    // ---- travelled distance (DroneEnv.py:1131-1138)
+    for (int a = 0; a < Aa; ++a) {
+      dists[a] = norm2_rows(V.a_posx()[a] - prev_x[a], V.a_posy()[a] - prev_y[a]);
+      V.a_dist()[a] += dists[a];
+    }
+    HFv(TOTAL_DIST) += np_sum(dists, Aa);
+
+    // time_penaulty / alloc_reward are evaluated here in the reference (DroneEnv.py:1140-1145)
+    {
+      double nt = (double)C().n_tasks_cfg;
+      acc.time_pen = -(double)(C().n_tasks_cfg - HIv(N_REACHED)) / nt * ((double)t / (double)C().max_time_steps);
+      acc.alloc_reward = 0.0;
+      if (t > C().n_tasks_cfg + 1) {
+        int unalloc = 1;  // bucket 0 (idle) is always empty
+        int n = HIv(N_TASKS);
+        for (int k = 0; k < n; ++k)
+          if (V.k_tbl_lo()[k] == 0 && V.k_tbl_hi()[k] == 0) ++unalloc;
+        acc.alloc_reward = -(double)unalloc;
+      }
+    }
+
+    generate_threat();
+    update_threats();
+    inject_arrivals();
+    if (C().escort_enabled) sync_escorts();
+  }
+
+  // ------------------------------------------------------------------ step: part 3 (lane 0)
+  MUAV_HD StepResult step_post(const Acc& acc) {
+    int Aa = A();
+    process_reveals();
+    expire_windows();
+    // _wps_track_reserve (DroneEnv.py:1575-1580) and the _pending_reset clear (:1156-1160)
+    int idle = 0;
+    bool any_busy = false;
+    for (int a = 0; a < Aa; ++a) {
+      if (V.a_state()[a] == -1) continue;
+      if (qlen(a) == 0) ++idle;
+      else any_busy = true;
+    }
+    HIv(IDLE_RESERVE) += idle;
+    if (HIv(PENDING_RESET) && any_busy) HIv(PENDING_RESET) = 0;
+
+    const double* rw = C().rw;
+    double time_reward = 0.0;
+    double reward = (rw[0] * acc.action_reward + rw[1] * acc.distance_reward + rw[2] * acc.quality_reward +
+                     rw[3] * acc.S_q + rw[4] * (double)C().n_tasks_cfg * time_reward + rw[5] * acc.alloc_reward +
+                     rw[6] * acc.time_pen + rw[7] * step_reward) /
+                    HFv(NORM_FACTOR) / (double)C().max_time_steps;
+    int t = HIv(T);
+    int n = HIv(N_TASKS);
+    bool alld = n > 0 && all_done();
+    bool timed_out = (t >= C().max_time_steps) && (C().max_time_steps > 0);
+    bool done = timed_out || (C().early_terminate && alld);
+    if (alld && HIv(CONCLUSION) > C().max_time_steps) HIv(CONCLUSION) = t;
+    StepResult r;
+    r.terminated = (C().early_terminate && alld && !timed_out) ? 1 : 0;
+    r.truncated = timed_out ? 1 : 0;
+    // last_tasks_info (DroneEnv.py:492)
+    int KW = V.L->D.KW;
+    int n_open = 0;
+    for (int w = 0; w < KW; ++w) V.open_mask()[w] = 0;
+    for (int k = 0; k < n; ++k)
+      if (V.k_status()[k] != 2) {
+        V.open_mask()[k >> 5] |= 1u << (k & 31);
+        ++n_open;
+      }
+    HIv(N_OPEN) = n_open;
+    if (done) {
+      reward = HFv(F_REWARD);
+      HIv(DONE) = 1;
+    }
+    HFv(LAST_REWARD) = reward;
+    r.reward = reward;
+    return r;
+  }
+
+  // whole step; lane/nlanes partition the data-parallel middle section
+  MUAV_HD StepResult step(const int16_t* act_agent, const int16_t* act_tid, int n_act, int lane, int nlanes) {
+    Acc acc;  // meaningful on lane 0 only
+    if (lane == 0) step_pre(act_agent, act_tid, n_act, acc);
+    MUAV_WARP_SYNC();
+    update_sensing(lane, nlanes);
+    MUAV_WARP_SYNC();
+    StepResult r;
+    r.reward = 0.0;
+    r.terminated = r.truncated = 0;
+    if (lane == 0) r = step_post(acc);
+    return r;
+  }
+};
+
+}  // namespace muav

@@ -1,0 +1,183 @@
+// Record layout of one environment (struct-of-arrays inside the record; the record is one
+// contiguous, 16-byte aligned block in HBM so that a warp can stage it into shared memory
+// with a single bulk async copy).  The field list is an X-macro so that the device view,
+// the offset table exported through muav_field_info() and the Python packer agree by
+// construction.
+#pragma once
+#include <stdint.h>
+#include "../../include/muav.h"
+
+#if defined(__CUDACC__)
+#define MUAV_HD __host__ __device__
+#else
+#define MUAV_HD
+#endif
+
+namespace muav {
+
+// ---- header (int32) indices -------------------------------------------------
+#define MUAV_HI_LIST(X)                                                                           \
+  X(T) X(N_TASKS) X(N_ACTIVE) X(N_EVENTS) X(N_REALLOC) X(N_SWITCH) X(N_ARRIVALS) X(PENDING_RESET) \
+  X(N_MISSED) X(N_ON_TIME) X(N_WINDOWED) X(IDLE_RESERVE) X(BURST_TOGGLE) X(ESC_REQUESTS)          \
+  X(ESC_COMPLETED) X(ESC_FAILED) X(ESC_REQ_STEPS) X(ESC_COV_STEPS) X(BREACHES) X(INTERCEPTED)     \
+  X(RECON_LOSSES) X(ESCORT_LOSSES) X(MUTUAL) X(PROT_REC_DONE) X(N_REACHED) X(CONCLUSION)          \
+  X(CUR_AGENT) X(CUR_TGT) X(CUR_MISSION) X(ERRFLAGS) X(DONE) X(LAST_PLAN_STEP) X(N_REPLANS)       \
+  X(N_CALLS) X(EV_TAGMASK) X(N_OPEN) X(GROUP_NEXT0) X(GROUP_NEXT1) X(GROUP_NEXT2) X(GROUP_NEXT3)  \
+  X(GROUP_NEXT4) X(GROUP_NEXT5) X(GROUP_NEXT6) X(GROUP_NEXT7) X(N_LSAP) X(PAD0) X(PAD1) X(PAD2)
+
+enum HdrI {
+#define X(n) HI_##n,
+  MUAV_HI_LIST(X)
+#undef X
+      HI_COUNT
+};
+
+// ---- header (double) indices ------------------------------------------------
+#define MUAV_HF_LIST(X) \
+  X(F_REWARD) X(TOTAL_DIST) X(NORM_FACTOR) X(LAST_REWARD) X(M0_X) X(M0_Y) X(M0_W) X(M0_H) X(M1_X) X(M1_Y) X(M1_W) \
+  X(M1_H) X(M2_X) X(M2_Y) X(M2_W) X(M2_H)
+
+enum HdrF {
+#define X(n) HF_##n,
+  MUAV_HF_LIST(X)
+#undef X
+      HF_COUNT
+};
+
+// error flag bits
+enum ErrBits {
+  ERR_QUEUE_OVERFLOW = 1,
+  ERR_TASK_OVERFLOW = 2,
+  ERR_EVENT_OVERFLOW = 4,
+  ERR_TAPE_OVERFLOW = 8,
+  ERR_NO_SPACE = 16,
+  ERR_LSAP_INFEASIBLE = 32,
+};
+
+struct Dims {
+  int A, TC, HC, QC, EVC, NOBS, KW;
+};
+
+MUAV_HD inline Dims dims_of(const muav_config& c) {
+  Dims d;
+  d.A = c.n_agents;
+  d.TC = c.task_cap;
+  d.HC = c.n_threats;
+  d.QC = c.queue_cap;
+  d.EVC = c.event_cap;
+  d.NOBS = c.n_obstacles;
+  d.KW = (c.task_cap + 31) / 32;
+  return d;
+}
+
+// name, C type, element count.  Ordered by decreasing alignment (8, 4, 2 bytes).
+#define MUAV_FIELDS(X)              \
+  X(hf, double, HF_COUNT)           \
+  X(a_posx, double, D.A)            \
+  X(a_posy, double, D.A)            \
+  X(a_nfpx, double, D.A)            \
+  X(a_nfpy, double, D.A)            \
+  X(a_nft, double, D.A)             \
+  X(a_dist, double, D.A)            \
+  X(a_caps, double, 6 * D.A)        \
+  X(a_qtime, double, D.QC * D.A)    \
+  X(k_posx, double, D.TC)           \
+  X(k_posy, double, D.TC)           \
+  X(k_cur, double, 6 * D.TC)        \
+  X(k_alloc, double, 6 * D.TC)      \
+  X(k_done_ti, double, D.TC)        \
+  X(k_org_ti, double, D.TC)         \
+  X(k_init, double, D.TC)           \
+  X(k_dtime, double, D.TC)          \
+  X(h_posx, double, D.HC)           \
+  X(h_posy, double, D.HC)           \
+  X(obst, double, 3 * D.NOBS)       \
+  X(hi, int32_t, HI_COUNT)          \
+  X(a_state, int32_t, D.A)          \
+  X(a_task_start, int32_t, D.A)     \
+  X(a_fail_event, int32_t, D.A)     \
+  X(a_ammo, int32_t, D.A)           \
+  X(a_last_task, int32_t, D.A)      \
+  X(a_commit, int32_t, D.A)         \
+  X(a_escort, int32_t, D.A)         \
+  X(k_tbl_lo, uint32_t, D.TC)       \
+  X(k_tbl_hi, uint32_t, D.TC)       \
+  X(known, uint32_t, D.KW * D.A)    \
+  X(open_mask, uint32_t, D.KW)      \
+  X(events, int32_t, D.EVC)         \
+  X(a_queue, int16_t, D.QC * D.A)   \
+  X(a_type, int16_t, D.A)           \
+  X(a_re_eval, int16_t, D.A)        \
+  X(a_qlen, int16_t, D.A)           \
+  X(k_deadline, int16_t, D.TC)      \
+  X(k_created, int16_t, D.TC)       \
+  X(k_reveal, int16_t, D.TC)        \
+  X(k_prot_task, int16_t, D.TC)     \
+  X(k_type, int16_t, D.TC)          \
+  X(k_status, int16_t, D.TC)        \
+  X(k_kind, int16_t, D.TC)          \
+  X(k_req_agents, int16_t, D.TC)    \
+  X(k_elig, int16_t, D.TC)          \
+  X(k_counted, int16_t, D.TC)       \
+  X(k_fq, int16_t, D.TC)            \
+  X(k_reached, int16_t, D.TC)       \
+  X(k_threat, int16_t, D.TC)        \
+  X(k_prot_agent, int16_t, D.TC)    \
+  X(h_task, int16_t, D.HC)          \
+  X(h_det_task, int16_t, D.HC)      \
+  X(h_status, int16_t, D.HC)        \
+  X(h_type, int16_t, D.HC)          \
+  X(h_group, int16_t, D.HC)         \
+  X(h_ammo, int16_t, D.HC)          \
+  X(h_target, int16_t, D.HC)        \
+  X(h_mission, int16_t, D.HC)       \
+  X(h_spawned, int16_t, D.HC)       \
+  X(h_order, int16_t, D.HC)
+
+struct Layout {
+#define X(name, type, count) int32_t o_##name;
+  MUAV_FIELDS(X)
+#undef X
+  int32_t record_bytes;
+  int32_t scratch_bytes;
+  Dims D;
+};
+
+MUAV_HD inline int32_t align_up(int32_t x, int32_t a) { return (x + a - 1) / a * a; }
+
+MUAV_HD inline Layout make_layout(const muav_config& c) {
+  Layout L;
+  Dims D = dims_of(c);
+  L.D = D;
+  int32_t off = 0;
+#define X(name, type, count)                 \
+  off = align_up(off, (int32_t)sizeof(type)); \
+  L.o_##name = off;                          \
+  off += (int32_t)sizeof(type) * (int32_t)(count);
+  MUAV_FIELDS(X)
+#undef X
+  L.record_bytes = align_up(off, 16);
+  // allocator scratch: cost matrix + LSAP work arrays (see muav_core.cuh alloc_scratch)
+  int32_t nr = D.A, nc = D.TC;
+  int32_t s = 0;
+  s += 8 * nr * nc;            // cost (possibly transposed copy reuses it in place via index map)
+  s += 8 * (nr + nc) * 2;      // u, v (sized for either orientation)
+  s += 8 * (nr + nc);          // shortest path costs
+  s += 8 * nc;                 // residuals per round task
+  s += 2 * (nr + nc) * 6;      // path,col4row,row4col,remaining,SR,SC (int16)
+  s += 2 * (nr + nc) * 2;      // free agents, round tasks (int16)
+  s += 2 * nc;                 // pair-token column of each task (int16)
+  L.scratch_bytes = align_up(s, 16);
+  return L;
+}
+
+struct View {
+  char* base;
+  const Layout* L;
+#define X(name, type, count) \
+  MUAV_HD inline type* name() const { return (type*)(base + L->o_##name); }
+  MUAV_FIELDS(X)
+#undef X
+};
+
+}  // namespace muav

@@ -1,0 +1,183 @@
+"""Generate golden fixtures by running the UNMODIFIED reference (/root/reference,
+imported read-only through tests/golden/refshim.py) in the authoring container.
+
+    python tests/golden/gen_golden.py            # writes tests/golden/*.json.gz
+
+Each fixture holds, per episode: the ordered actions fed to env.step, the
+allocator's ordered (agent_id, task_id) pairs, the drained events, the step
+reward (float hex), termination flags, a 64-bit digest of the full canonical
+state after every step (tests/golden/refsnap.py) and the terminal metrics dict.
+Floats are stored as float.hex() strings, so fixtures are bit-exact.
+
+Drivers (all restate the reference's own episode loops):
+  local_hungarian   experiments/wps_eval.py:123-133 (interval 20, visibility map)
+  coalition         experiments/escort_eval.py:137-148 (interval 12)
+  global_hungarian  experiments/wps_eval.py:117-122 (no visibility mask)
+  pair_injected     experiments/wps_eval.py:226-230 via PairCostHybrid.plan(scores=...) with
+                    deterministic injected edge scores (PairCostHybrid.py:308-328), replan rule :64-73
+  random_actions    env.step driven by a seeded random policy (valid, stale and out-of-range indices)
+"""
+from __future__ import annotations
+
+import gzip
+import json
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+import refshim  # noqa: E402
+import refsnap  # noqa: E402
+
+
+def fhex(x):
+    return float(x).hex()
+
+
+def ref_open_tasks(env):
+    def res(t):
+        if getattr(t, "kind", None) == "Escort" or float(getattr(t, "required_agents", 0) or 0) > 0:
+            return max(float(getattr(t, "required_agents", 1) or 1) - len(t.allocationDetails), 0.0)
+        return max(float(t.currentReqs[t.typeIdx] - t.allocatedReqs[t.typeIdx]), 0.0)
+
+    return [t for t in env.tasks if t.id != 0 and t.status != 2 and res(t) > 0]
+
+
+def injected_scores(seed, t, n_rows, n_cols):
+    """Deterministic pseudo-random edge scores in [-0.35, 0.35] (float32)."""
+    i = np.arange(n_rows, dtype=np.uint64)[:, None]
+    j = np.arange(n_cols, dtype=np.uint64)[None, :]
+    x = (np.uint64(seed) * np.uint64(1000003) + np.uint64(t) * np.uint64(7919)
+         + i * np.uint64(104729) + j * np.uint64(1299709) + np.uint64(12345))
+    x = (x * np.uint64(2654435761)) % np.uint64(2001)
+    return ((x.astype(np.float64) - 1000.0) / 1000.0 * 0.35).astype(np.float32)
+
+
+def hybrid_should_replan(env, events, interval=15):
+    return (env.time_steps == 0 or env.time_steps % interval == 0
+            or any(ev[0] in ("Reset_Allocation", "New_Threat", "Agent_Fail") for ev in events))
+
+
+def run_episode(case, seed, driver, overrides=None):
+    refshim.install()
+    from mUAV_TA.DroneEnv import MultiUAVEnv
+    from TaskAllocation.OptimizationBased.HungarianAllocator import HungarianAllocator
+
+    cfg = refshim.wps_config(case, **(overrides or {}))
+    env = MultiUAVEnv(cfg)
+    obs, info = env.reset(seed=seed)
+    interval = 12 if driver == "coalition" else 20
+    hung = HungarianAllocator(replan_interval=interval, max_coord=env.max_coord)
+    pair = None
+    if driver == "pair_injected":
+        from TaskAllocation.Hybrid.PairCostHybrid import PairCostHybrid
+        pair = PairCostHybrid(use_attention=False, device="cpu")
+    rnd = random.Random(seed * 7919 + 13)
+    ep = {"case": case, "seed": seed, "driver": driver, "overrides": overrides or {},
+          "agent_names": [a.name for a in env.agents_obj],
+          "digest0": str(refsnap.digest(refsnap.snapshot(env))), "steps": []}
+    while True:
+        events = list(info.get("events") or []) if isinstance(info, dict) else []
+        pairs = []
+        if driver in ("local_hungarian", "coalition"):
+            res = hung.allocate_tasks(env.get_live_agents(), ref_open_tasks(env), time_step=env.time_steps,
+                                      events=events, agent_known_ids=env.agent_visibility_map())
+            pairs = res
+        elif driver == "global_hungarian":
+            pairs = hung.allocate_tasks(env.get_live_agents(), ref_open_tasks(env), time_step=env.time_steps,
+                                        events=events)
+        elif driver == "pair_injected":
+            if hybrid_should_replan(env, events):
+                sc = injected_scores(seed, env.time_steps, pair.max_agents, pair.max_tasks)
+                pairs = pair.plan(env, hung, events=events, explore=False, force=True, scores=sc)[0]
+        actions = {}
+        if driver == "random_actions":
+            n_open = len(env.last_tasks_info)
+            for a in env.agents_obj:
+                u = rnd.random()
+                if u < 0.08:
+                    actions[a.name] = rnd.randrange(0, max(n_open, 1))
+                elif u < 0.09:
+                    actions[a.name] = n_open + rnd.randrange(0, 3)
+        else:
+            for name, task in pairs:
+                if env.last_tasks_info and task in env.last_tasks_info and name not in actions:
+                    actions[name] = env.last_tasks_info.index(task)
+        obs, rew, term, trunc, info = env.step(actions)
+        snap = refsnap.snapshot(env)
+        r0 = next(iter(rew.values()))
+        assert all(v == r0 for v in rew.values())
+        ep["steps"].append({
+            "pairs": [[env.agent_by_name[n].id, int(t.id)] for n, t in pairs],
+            "actions": [[env.agent_by_name[n].id, int(i)] for n, i in actions.items()],
+            "events": [[refsnap.EVENT_TAGS.index(e[0]), int(e[1])] for e in info["events"]],
+            "reward": fhex(r0),
+            "term": bool(all(term.values())), "trunc": bool(all(trunc.values())),
+            "n_open": len(env.last_tasks_info),
+            "digest": str(refsnap.digest(snap)),
+        })
+        if all(term.values()) or all(trunc.values()):
+            break
+    m = info["metrics"]
+    ep["metrics"] = {k: (fhex(v) if isinstance(v, (float, np.floating)) else int(v)) for k, v in m.items()}
+    ep["n_replans"] = int(hung.n_replans)
+    return ep
+
+
+PLAN = [
+    # (file, case, driver, seeds, overrides)
+    ("wps_easy_local", "WPS_easy", "local_hungarian", range(0, 8), None),
+    ("wps_hard_local", "WPS_hard", "local_hungarian", range(0, 16), None),
+    ("wps_burst_local", "WPS_burst", "local_hungarian", range(0, 8), None),
+    ("wps_commit_local", "WPS_commit", "local_hungarian", range(0, 8), None),
+    ("wps_escort_coalition", "WPS_escort", "coalition", range(0, 8), None),
+    ("wps_hard_global", "WPS_hard", "global_hungarian", range(0, 4), None),
+    ("wps_hard_pair", "WPS_hard", "pair_injected", range(0, 12), None),
+    ("wps_commit_pair", "WPS_commit", "pair_injected", range(0, 4), None),
+    ("wps_hard_random", "WPS_hard", "random_actions", range(0, 8), None),
+    ("wps_escort_random", "WPS_escort", "random_actions", range(0, 4), None),
+    ("wps_attn_xl_local", "WPS_attn_XL", "local_hungarian", range(0, 2), None),
+    ("wps_hard_single_task", "WPS_hard", "local_hungarian", range(0, 3), {"multiple_tasks_per_agent": False}),
+]
+
+
+def main(only=None):
+    for fname, case, driver, seeds, ov in PLAN:
+        if only and fname not in only:
+            continue
+        eps = []
+        for seed in seeds:
+            cfg_over = dict(ov or {})
+            ep = run_episode(case, seed, driver, None)if not cfg_over else run_episode_over(case, seed, driver, cfg_over)
+            eps.append(ep)
+        path = os.path.join(HERE, fname + ".json.gz")
+        with gzip.open(path, "wt", compresslevel=9) as f:
+            json.dump({"episodes": eps}, f, separators=(",", ":"))
+        print(fname, len(eps), os.path.getsize(path))
+
+
+def run_episode_over(case, seed, driver, over):
+    """Overrides that wps_config applies AFTER its own multiple_tasks_per_agent=True."""
+    orig = refshim.wps_config
+
+    def patched(case_id, **kw):
+        cfg = orig(case_id, **kw)
+        for k, v in over.items():
+            setattr(cfg, k, v)
+        return cfg
+
+    refshim.wps_config = patched
+    try:
+        ep = run_episode(case, seed, driver, None)
+    finally:
+        refshim.wps_config = orig
+    ep["overrides"] = over
+    return ep
+
+
+if __name__ == "__main__":
+    main(set(sys.argv[1:]) or None)
