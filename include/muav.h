@@ -134,12 +134,16 @@ int muav_tokens_pair(const muav_config* cfg, const void* d_records, int max_task
                      float* d_task_feats, uint8_t* d_task_mask, float* d_agent_feats, uint8_t* d_agent_mask,
                      float* d_edge_valid, int32_t* d_task_ids, int n_envs, void* stream);
 
-/* Observation tensors (DroneEnv.py:365-492): tasks_info [E, max_tasks, 20] f64, pad_mask [E,max_tasks] u8,
- * legal_mask [E, n_agents, max_tasks] u8, agent_obs [E, n_agents, 9] f64, event_flags [E,5] f32. */
-#define MUAV_OBS_TASK_DIM 20
+/* Observation tensors (DroneEnv.py:365-492).  tasks_info [E, max_rows, 21] f64 per open task:
+ * id, x/max_coord, y/max_coord, status, current_reqs[6], alloc_reqs[6], init_time, end_time, type_idx, unmet, age
+ * (status = -1 marks padding rows); pad_mask [E,max_rows] u8 ("mask"); legal_mask [E, n_agents, max_rows] u8;
+ * agent_obs [E, n_agents, 9] f64: agent_position[2], agent_caps[6], alloc_task; event_flags [E,5] f32;
+ * n_rows [E] i32 = number of rows the reference would emit before padding (> max_rows means truncated). */
+#define MUAV_OBS_TASK_DIM 21
 #define MUAV_OBS_AGENT_DIM 9
-int muav_observe(const muav_config* cfg, const void* d_records, double* d_tasks_info, uint8_t* d_pad_mask,
-                 uint8_t* d_legal_mask, double* d_agent_obs, float* d_event_flags, int n_envs, void* stream);
+int muav_observe(const muav_config* cfg, const void* d_records, int max_rows, double* d_tasks_info, uint8_t* d_pad_mask,
+                 uint8_t* d_legal_mask, double* d_agent_obs, float* d_event_flags, int32_t* d_n_rows, int n_envs,
+                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,237 @@
+"""Batched WPS environment: E independent MultiUAVEnv instances resident in HBM, stepped by the
+CUDA kernels behind the C ABI (include/muav.h).  This is the "batched-tensor step added
+alongside" the PettingZoo surface (multi_uav_ta_gym_env_b200/env.py wraps it with E = 1).
+
+Reference semantics: MultiUAVEnv.reset/step (mUAV_TA/DroneEnv.py:522-762, 774-1206) and, when an
+`AllocSpec` is given, HungarianAllocator.allocate_tasks + the drivers' glue
+(HungarianAllocator.py:72-208, experiments/wps_eval.py:55-73,123-133, escort_eval.py:137-148).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, reset as _reset, state as _state
+from .config import EVENT_TAGS
+
+ALL_EVENTS = 0x1F
+HYBRID_EVENTS = 0b00111  # Reset_Allocation, Agent_Fail, New_Threat (wps_eval.py:64-73)
+
+
+@dataclass
+class AllocSpec:
+    """How the fused allocator runs in front of each step (see muav_alloc_opts in include/muav.h)."""
+
+    mode: int = 1                 # 1: HungarianAllocator.should_replan rule; 2: hybrid cadence + force
+    replan_interval: int = 20
+    event_mask: int = ALL_EVENTS
+    use_visibility: bool = True
+    pair_tokens: bool = False
+    max_coord: float = 1200.0
+
+    @staticmethod
+    def local_hungarian(interval=20):
+        return AllocSpec(1, interval, ALL_EVENTS, True, False)
+
+    @staticmethod
+    def global_hungarian(interval=20):
+        return AllocSpec(1, interval, ALL_EVENTS, False, False)
+
+    @staticmethod
+    def coalition_hungarian(interval=12):
+        return AllocSpec(1, interval, ALL_EVENTS, True, False)
+
+    @staticmethod
+    def pair_hybrid(interval=15):
+        return AllocSpec(2, interval, HYBRID_EVENTS, True, True)
+
+
+class BatchedMultiUAVEnv:
+    def __init__(self, config, n_envs: int, device="cuda:0", task_cap=None, queue_cap=8):
+        self.lib = _lib.cuda_lib()  # raises if the CUDA library is not built: no CPU fallback
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedMultiUAVEnv needs a CUDA device (B200); there is no CPU path")
+        self.config = config
+        self.n_envs = int(n_envs)
+        self.device = torch.device(device)
+        self.cfg = _lib.build_config(config, task_cap=task_cap, queue_cap=queue_cap)
+        self.codec = _state.RecordCodec(self.lib, self.cfg)
+        self.record_bytes = self.codec.record_bytes
+        self.n_agents = self.cfg.n_agents
+        self.task_cap = self.cfg.task_cap
+        self.max_coord = 1200.0
+        self.possible_agents = [f"{t[0:2]}_agent{i}" for t, n in config.agents.items() for i in range(n)]
+        E, A = self.n_envs, self.n_agents
+        dev = self.device
+        self.records = None
+        self.tapes = None
+        self.reward = torch.zeros(E, dtype=torch.float64, device=dev)
+        self.terminated = torch.zeros(E, dtype=torch.uint8, device=dev)
+        self.truncated = torch.zeros(E, dtype=torch.uint8, device=dev)
+        self.n_events = torch.zeros(E, dtype=torch.int32, device=dev)
+        self.events = torch.zeros(E, self.cfg.event_cap, dtype=torch.int32, device=dev)
+        self.n_pairs = torch.zeros(E, dtype=torch.int32, device=dev)
+        self.pairs = torch.zeros(E, A, dtype=torch.int32, device=dev)
+        self.n_open = torch.zeros(E, dtype=torch.int32, device=dev)
+        self._out = _lib.MuavStepOut()
+        self._out.d_reward = self.reward.data_ptr()
+        self._out.d_terminated = self.terminated.data_ptr()
+        self._out.d_truncated = self.truncated.data_ptr()
+        self._out.d_n_events = self.n_events.data_ptr()
+        self._out.d_events = self.events.data_ptr()
+        self._out.d_n_pairs = self.n_pairs.data_ptr()
+        self._out.d_pairs = self.pairs.data_ptr()
+        self._out.d_n_open = self.n_open.data_ptr()
+        self.scenarios = None
+        self.agent_names = None
+        self.launches = 0
+
+    # ------------------------------------------------------------------ reset
+    def reset(self, seeds: Optional[Sequence[int]] = None):
+        """Host scenario generation per seed (DroneEnv.py:522-762) + one upload."""
+        if seeds is None:
+            seeds = range(self.n_envs)
+        seeds = list(seeds)
+        if len(seeds) != self.n_envs:
+            raise ValueError("need one seed per environment")
+        tw = list(self.cfg.tape_words)
+        self.scenarios = [_reset.generate_scenario(self.config, int(s), tw) for s in seeds]
+        self.agent_names = [sc.agent_names for sc in self.scenarios]
+        rec, tapes = _reset.pack_records(self.lib, self.cfg, self.scenarios)
+        self._records0 = torch.from_numpy(rec).to(self.device)
+        self.records = self._records0.clone()
+        self.tapes = torch.from_numpy(tapes.view(np.int32)).to(self.device)
+        self.n_open.fill_(int(self.codec.header(rec[0], "N_OPEN")))
+        return self
+
+    def restore(self):
+        """Rewind every environment to its reset state (device-to-device copy, no host work)."""
+        self.records.copy_(self._records0)
+
+    # ------------------------------------------------------------------ step
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def step_batched(self, actions: torch.Tensor, n_steps: int = 1):
+        """actions: int32 [E, A, 2] ordered (agent_id, index into last_tasks_info) pairs, agent_id = -1
+        terminates an env's list; or int32 [E, A] with one index per agent id (-1 = no action), applied
+        in ascending agent id.  Returns (reward f64[E], terminated u8[E], truncated u8[E])."""
+        if actions.dim() == 2:
+            E, A = actions.shape
+            ids = torch.arange(A, device=actions.device, dtype=torch.int32).expand(E, A)
+            valid = actions >= 0
+            order = torch.argsort((~valid).to(torch.int8), dim=1, stable=True)
+            a_sorted = torch.gather(torch.where(valid, ids, torch.full_like(ids, -1)), 1, order)
+            i_sorted = torch.gather(actions.to(torch.int32), 1, order)
+            actions = torch.stack([a_sorted, i_sorted], dim=2)
+        actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+        rc = self.lib.dll.muav_step(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(),
+                                    actions.data_ptr(), None, C.byref(self._out), self.n_envs, n_steps, self._stream())
+        _lib.check(rc, "muav_step")
+        self.launches += 1
+        return self.reward, self.terminated, self.truncated
+
+    def step_allocated(self, spec: AllocSpec, n_steps: int = 1, edge_scores: Optional[torch.Tensor] = None,
+                       priorities: Optional[torch.Tensor] = None, reserved: Optional[torch.Tensor] = None):
+        """n_steps fused (allocate -> step) iterations per environment, state resident in shared memory."""
+        O = _lib.MuavAllocOpts()
+        O.mode = spec.mode
+        O.replan_interval = spec.replan_interval
+        O.event_mask = spec.event_mask
+        O.use_visibility = int(spec.use_visibility)
+        O.pair_tokens = int(spec.pair_tokens)
+        O.max_coord = spec.max_coord
+        keep = []
+        if edge_scores is not None:
+            es = edge_scores.to(device=self.device, dtype=torch.float32).contiguous()
+            keep.append(es)
+            O.score_rows, O.score_cols = int(es.shape[1]), int(es.shape[2])
+            O.d_edge_scores = es.data_ptr()
+        if priorities is not None:
+            pr = priorities.to(device=self.device, dtype=torch.float64).contiguous()
+            keep.append(pr)
+            O.d_priorities = pr.data_ptr()
+        if reserved is not None:
+            rs = reserved.to(device=self.device, dtype=torch.uint8).contiguous()
+            keep.append(rs)
+            O.d_reserved = rs.data_ptr()
+        rc = self.lib.dll.muav_step(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(), None,
+                                    C.byref(O), C.byref(self._out), self.n_envs, n_steps, self._stream())
+        _lib.check(rc, "muav_step")
+        self.launches += 1
+        return self.reward, self.terminated, self.truncated
+
+    # ------------------------------------------------------------------ views
+    def metrics(self) -> torch.Tensor:
+        out = torch.empty(self.n_envs, _lib.N_METRICS, dtype=torch.float64, device=self.device)
+        rc = self.lib.dll.muav_metrics(C.byref(self.cfg), self.records.data_ptr(), out.data_ptr(), self.n_envs,
+                                       self._stream())
+        _lib.check(rc, "muav_metrics")
+        self.launches += 1
+        return out
+
+    def metric_dict(self, e: int) -> dict:
+        m = self.metrics()[e].cpu().numpy()
+        return dict(zip(self.lib.metric_names(), m.tolist()))
+
+    def tokens_pair(self, max_tasks=32, max_agents=16):
+        E, dev = self.n_envs, self.device
+        tf = torch.empty(E, max_tasks, 13, dtype=torch.float32, device=dev)
+        tm = torch.empty(E, max_tasks, dtype=torch.uint8, device=dev)
+        af = torch.empty(E, max_agents, 12, dtype=torch.float32, device=dev)
+        am = torch.empty(E, max_agents, dtype=torch.uint8, device=dev)
+        ev = torch.empty(E, max_agents, max_tasks, dtype=torch.float32, device=dev)
+        ids = torch.empty(E, max_tasks, dtype=torch.int32, device=dev)
+        rc = self.lib.dll.muav_tokens_pair(C.byref(self.cfg), self.records.data_ptr(), max_tasks, max_agents,
+                                           tf.data_ptr(), tm.data_ptr(), af.data_ptr(), am.data_ptr(), ev.data_ptr(),
+                                           ids.data_ptr(), E, self._stream())
+        _lib.check(rc, "muav_tokens_pair")
+        self.launches += 1
+        return {"task_feats": tf, "task_mask": tm.bool(), "agent_feats": af, "agent_mask": am.bool(),
+                "edge_valid": ev, "task_ids": ids}
+
+    def observe(self, max_rows: Optional[int] = None):
+        """Observation tensors of _generate_observations (DroneEnv.py:468-492); see include/muav.h."""
+        E, A, dev = self.n_envs, self.n_agents, self.device
+        mr = int(max_rows or self.cfg.max_tasks)
+        ti = torch.empty(E, mr, 21, dtype=torch.float64, device=dev)
+        pm = torch.empty(E, mr, dtype=torch.uint8, device=dev)
+        lm = torch.empty(E, A, mr, dtype=torch.uint8, device=dev)
+        ao = torch.empty(E, A, 9, dtype=torch.float64, device=dev)
+        ef = torch.empty(E, 5, dtype=torch.float32, device=dev)
+        nr = torch.empty(E, dtype=torch.int32, device=dev)
+        rc = self.lib.dll.muav_observe(C.byref(self.cfg), self.records.data_ptr(), mr, ti.data_ptr(), pm.data_ptr(),
+                                       lm.data_ptr(), ao.data_ptr(), ef.data_ptr(), nr.data_ptr(), E, self._stream())
+        _lib.check(rc, "muav_observe")
+        self.launches += 1
+        return {"tasks_info": ti, "mask": pm.bool(), "legal_mask": lm.bool(), "agent_obs": ao, "event_flags": ef,
+                "n_rows": nr}
+
+    def record_host(self, e: int) -> np.ndarray:
+        return self.records[e].cpu().numpy()
+
+    def snapshot(self, e: int) -> dict:
+        return self.codec.snapshot(self.record_host(e))
+
+    def error_flags(self) -> torch.Tensor:
+        off, cnt, dt = self.codec.F["hi"]
+        idx = self.codec.extra["ERRFLAGS"]
+        hi = self.records[:, off:off + cnt * 4].view(torch.int32)
+        return hi[:, idx]
+
+    def header_int(self, name: str) -> torch.Tensor:
+        off, cnt, dt = self.codec.F["hi"]
+        hi = self.records[:, off:off + cnt * 4].view(torch.int32)
+        return hi[:, self.lib.header_index(name)]
+
+    def events_of(self, e: int) -> list:
+        return _state.decode_events(int(self.n_events[e].item()), self.events[e].cpu().numpy())
+
+    def pairs_of(self, e: int) -> list:
+        n = int(self.n_pairs[e].item())
+        p = self.pairs[e, :n].cpu().numpy()
+        return [[int(x) >> 16, int(x) & 0xFFFF] for x in p]

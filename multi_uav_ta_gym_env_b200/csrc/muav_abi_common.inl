@@ -1,0 +1,61 @@
+// Host-only part of the C ABI (layout queries).  Included inside an extern "C" block by
+// muav_kernels.cu (the product library) and by tests/hostcheck/hostcheck.cpp (CPU build of the
+// same simulation core, used by the `-m "not gpu"` tests only).
+const char* muav_version(void) { return "muav_b200 0.1 (sm_100a)"; }
+size_t muav_config_size(void) { return sizeof(muav_config); }
+size_t muav_record_bytes(const muav_config* cfg) { return (size_t)make_layout(*cfg).record_bytes; }
+size_t muav_scratch_bytes(const muav_config* cfg) { return (size_t)make_layout(*cfg).scratch_bytes; }
+
+int muav_num_fields(void) {
+  int n = 0;
+#define X(name, type, count) ++n;
+  MUAV_FIELDS(X)
+#undef X
+  return n;
+}
+
+int muav_field_info(const muav_config* cfg, int idx, const char** name, int64_t* offset, int64_t* count, int32_t* elem_size) {
+  Layout L = make_layout(*cfg);
+  Dims D = L.D;
+  (void)D;
+  int i = 0;
+#define X(fname, type, cnt)             \
+  if (i == idx) {                       \
+    *name = #fname;                     \
+    *offset = L.o_##fname;              \
+    *count = (int64_t)(cnt);            \
+    *elem_size = (int32_t)sizeof(type); \
+    return 0;                           \
+  }                                     \
+  ++i;
+  MUAV_FIELDS(X)
+#undef X
+  return -22;
+}
+
+int muav_header_index(const char* name) {
+  int i = 0;
+#define X(n)                                   \
+  if (strcmp(name, #n) == 0) return i;         \
+  ++i;
+  MUAV_HI_LIST(X)
+#undef X
+  i = 0;
+#define X(n)                                   \
+  if (strcmp(name, #n) == 0) return i;         \
+  ++i;
+  MUAV_HF_LIST(X)
+#undef X
+  return -1;
+}
+
+static int check_cfg(const muav_config* c) {
+  if (!c) return -22;
+  if (c->n_agents < 1 || c->n_agents > MUAV_MAX_AGENTS) return -22;
+  if (c->task_cap < 1 || c->task_cap > MUAV_MAX_TASK_CAP) return -22;
+  if (c->queue_cap < 1 || c->queue_cap > MUAV_MAX_QUEUE) return -22;
+  if (c->n_groups < 0 || c->n_groups > MUAV_MAX_GROUPS) return -22;
+  if (c->n_threats < 0 || c->event_cap < 1 || c->n_obstacles < 0) return -22;
+  return 0;
+}
+

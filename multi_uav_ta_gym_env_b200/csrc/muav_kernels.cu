@@ -1,0 +1,432 @@
+// libmuav_b200.so -- CUDA kernels (sm_100a) and the C ABI declared in include/muav.h.
+//
+// Execution model: one warp per environment.  The environment record (struct-of-arrays, one
+// contiguous 16-byte aligned block, ~10 KB for WPS_hard) is staged HBM -> shared memory with a
+// single bulk async copy (cp.async.bulk + mbarrier, the 1-D TMA path; SASS: UBLKCP), the step
+// (and optionally the Hungarian allocator in front of it) runs entirely out of shared memory,
+// and the record goes back with one bulk store.  Per-step outputs are a few scalars per env.
+// Compile with -fmad=false: every float64 operation must round exactly like the reference's.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "muav_alloc.cuh"
+#include "muav_views.cuh"
+
+namespace muav {
+
+// ------------------------------------------------------------------ bulk async copy helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(phase)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+struct StepParams {
+  muav_config cfg;
+  Layout L;
+  muav_alloc_opts opts;
+  muav_step_out out;
+  char* records;
+  const uint32_t* tapes;
+  const int32_t* actions;
+  int n_envs, n_steps, tape_stride, use_bulk;
+};
+
+// One warp (= one CTA) per environment.
+__global__ void __launch_bounds__(32) muav_step_kernel(const __grid_constant__ StepParams P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int16_t act_agent[MUAV_MAX_AGENTS];
+  __shared__ int16_t act_tid[MUAV_MAX_AGENTS];
+  __shared__ int n_act_s;
+  const int e = blockIdx.x;
+  const int lane = threadIdx.x;
+  if (e >= P.n_envs) return;
+  const Layout& L = P.L;
+  char* rec = (char*)smem;
+  char* scratch = rec + L.record_bytes;
+  char* grec = P.records + (size_t)e * L.record_bytes;
+
+  // ---- stage the record into shared memory
+  if (P.use_bulk) {
+    if (lane == 0) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    if (lane == 0) {
+      mbar_expect_tx(&bar, (uint32_t)L.record_bytes);
+      bulk_g2s(rec, grec, (uint32_t)L.record_bytes, &bar);
+    }
+    mbar_wait(&bar, 0);
+  } else {
+    const uint4* src = (const uint4*)grec;
+    uint4* dst = (uint4*)rec;
+    for (int i = lane; i < L.record_bytes / 16; i += 32) dst[i] = src[i];
+  }
+  __syncwarp();
+
+  Sim S;
+  S.V.base = rec;
+  S.V.L = &L;
+  S.Cp = &P.cfg;
+  S.tape = P.tapes + (size_t)e * P.tape_stride;
+  S.scratch = scratch;
+  S.out_events = P.out.d_events ? P.out.d_events + (size_t)e * L.D.EVC : nullptr;
+  S.n_out_events = 0;
+  S.step_reward = 0.0;
+  View& V = S.V;
+  const int A = L.D.A;
+
+  for (int s = 0; s < P.n_steps; ++s) {
+    if (HIv(DONE)) break;
+    if (lane == 0) {
+      int n_act = 0;
+      if (P.opts.mode != 0) {
+        int np = allocate_tasks(S, P.opts, e, act_agent, act_tid);
+        if (P.out.d_n_pairs) P.out.d_n_pairs[e] = np;
+        if (P.out.d_pairs)
+          for (int i = 0; i < np; ++i) P.out.d_pairs[(size_t)e * A + i] = ((int)act_agent[i] << 16) | (int)act_tid[i];
+        // _apply_assign (wps_eval.py:55-61): only tasks present in last_tasks_info become actions
+        for (int i = 0; i < np; ++i) {
+          if (HIv(N_OPEN) > 0 && S.in_last_open(act_tid[i])) {
+            act_agent[n_act] = act_agent[i];
+            act_tid[n_act] = act_tid[i];
+            ++n_act;
+          }
+        }
+      } else if (P.actions) {
+        const int32_t* act = P.actions + (size_t)e * A * 2;
+        for (int i = 0; i < A; ++i) {
+          int a = act[2 * i];
+          if (a < 0) break;
+          act_agent[n_act] = (int16_t)a;
+          act_tid[n_act] = (int16_t)S.open_task_at(act[2 * i + 1]);
+          ++n_act;
+        }
+      }
+      n_act_s = n_act;
+    }
+    __syncwarp();
+    StepResult r = S.step(act_agent, act_tid, n_act_s, lane, 32);
+    if (lane == 0) {
+      if (P.out.d_reward) P.out.d_reward[e] = r.reward;
+      if (P.out.d_terminated) P.out.d_terminated[e] = (uint8_t)r.terminated;
+      if (P.out.d_truncated) P.out.d_truncated[e] = (uint8_t)r.truncated;
+      if (P.out.d_n_events) P.out.d_n_events[e] = S.n_out_events;
+      if (P.out.d_n_open) P.out.d_n_open[e] = HIv(N_OPEN);
+    }
+    __syncwarp();
+  }
+
+  // ---- write the record back
+  __syncwarp();
+  if (P.use_bulk) {
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_s2g(grec, rec, (uint32_t)L.record_bytes);
+      bulk_wait_all();
+    }
+  } else {
+    const uint4* src = (const uint4*)rec;
+    uint4* dst = (uint4*)grec;
+    for (int i = lane; i < L.record_bytes / 16; i += 32) dst[i] = src[i];
+  }
+}
+
+// ------------------------------------------------------------------ standalone batched LSAP
+__global__ void __launch_bounds__(32) muav_lsap_kernel(const double* cost, const int32_t* nr_arr, const int32_t* nc_arr,
+                                                       int nr_max, int nc_max, int32_t* col4row, int n) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int b = blockIdx.x;
+  if (b >= n) return;
+  const int lane = threadIdx.x;
+  const int nr = nr_arr[b], nc = nc_arr[b];
+  AllocScratch W = carve_scratch((char*)smem, nr_max, nc_max);
+  const double* src = cost + (size_t)b * nr_max * nc_max;
+  for (int idx = lane; idx < nr * nc; idx += 32) {
+    int i = idx / nc, j = idx - i * nc;
+    W.cost[idx] = src[i * nc_max + j];
+  }
+  __syncwarp();
+  if (lane == 0) {
+    bool ok = (nr > 0 && nc > 0) ? lsap_solve(W.cost, nr, nc, W, W.col_of_row) : true;
+    for (int i = 0; i < nr_max; ++i) col4row[(size_t)b * nr_max + i] = (ok && i < nr && nr > 0 && nc > 0) ? W.col_of_row[i] : -1;
+  }
+}
+
+__global__ void muav_avoid_kernel(const double* pos, const double* mv, const double* obst, int nobs, double* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double ax, ay;
+  Sim::avoid_obstacles(obst, nobs, pos[2 * i], pos[2 * i + 1], mv[2 * i], mv[2 * i + 1], &ax, &ay);
+  out[2 * i] = ax;
+  out[2 * i + 1] = ay;
+}
+
+// ------------------------------------------------------------------ metrics (DroneEnv.py:1231-1319)
+static const char* const kMetricNames[MUAV_N_METRICS] = {
+    "F_time", "F_distance", "F_quality", "F_Reward", "S_WPS", "S_ESC", "Losses", "Kills", "makespan", "total_distance",
+    "n_reallocations", "n_task_switches", "n_arrivals", "n_tasks_final", "n_reached", "n_missed_windows", "n_on_time",
+    "n_windowed_tasks", "on_time_rate", "reserve_idle_fraction", "escort_coverage_rate", "protected_rec_completed",
+    "recon_losses", "escort_losses", "threats_intercepted", "mutual_support_engagements", "protection_breaches",
+    "escort_requests", "escort_completed", "escort_failed"};
+
+__global__ void muav_metrics_kernel(const __grid_constant__ muav_config cfg, const __grid_constant__ Layout L,
+                                    const char* records, double* out, int n) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  View V;
+  V.base = (char*)records + (size_t)e * L.record_bytes;
+  V.L = &L;
+  double* o = out + (size_t)e * MUAV_N_METRICS;
+  const int A = L.D.A;
+  const int T = HIv(N_TASKS);
+  double td = HFv(TOTAL_DIST);
+  // compute_s_wps (DroneEnv.py:1321-1337)
+  double dist_term = 0.01 * td / dmax(cfg.max_coord, 1.0);
+  double rematch = cfg.reassign_penalty * (double)HIv(N_SWITCH);
+  double s_wps = 12.0 * (double)HIv(N_ON_TIME) - 30.0 * (double)HIv(N_MISSED) - dist_term - rematch;
+  int req = HIv(ESC_REQ_STEPS);
+  double cov = (double)HIv(ESC_COV_STEPS) / (double)(req > 1 ? req : 1);
+  double s_esc = s_wps + 20.0 * (double)HIv(PROT_REC_DONE) - 30.0 * (double)HIv(RECON_LOSSES) + 20.0 * cov;
+  int losses = 0;
+  for (int a = 0; a < A; ++a) losses += V.a_state()[a] == -1;
+  int kills = 0;
+  for (int i = 0; i < HIv(N_ACTIVE); ++i) kills += V.h_status()[V.h_order()[i]] == 2;
+  double fq = 0.0;  // final_quality is -1 (counted as 0) or 0.0 (DroneEnv.py:1249,1566)
+  o[0] = 1.0 / (double)HIv(CONCLUSION) * (double)cfg.max_time_steps;
+  o[1] = td > 0 ? 1.0 / td * cfg.max_coord : 0.0;
+  o[2] = T > 0 ? fq / (double)T : nan("");
+  o[3] = HFv(F_REWARD);
+  o[4] = s_wps;
+  o[5] = s_esc;
+  o[6] = losses;
+  o[7] = kills;
+  o[8] = (double)HIv(CONCLUSION);
+  o[9] = td;
+  o[10] = HIv(N_REALLOC);
+  o[11] = HIv(N_SWITCH);
+  o[12] = HIv(N_ARRIVALS);
+  o[13] = T;
+  o[14] = HIv(N_REACHED);
+  o[15] = HIv(N_MISSED);
+  o[16] = HIv(N_ON_TIME);
+  o[17] = HIv(N_WINDOWED);
+  int den = HIv(N_ON_TIME) + HIv(N_MISSED);
+  o[18] = (double)HIv(N_ON_TIME) / (double)(den > 1 ? den : 1);
+  int den2 = HIv(T) * (A > 1 ? A : 1);
+  o[19] = (double)HIv(IDLE_RESERVE) / (double)(den2 > 1 ? den2 : 1);
+  o[20] = cov;
+  o[21] = HIv(PROT_REC_DONE);
+  o[22] = HIv(RECON_LOSSES);
+  o[23] = HIv(ESCORT_LOSSES);
+  o[24] = HIv(INTERCEPTED);
+  o[25] = HIv(MUTUAL);
+  o[26] = HIv(BREACHES);
+  o[27] = HIv(ESC_REQUESTS);
+  o[28] = HIv(ESC_COMPLETED);
+  o[29] = HIv(ESC_FAILED);
+}
+
+__global__ void muav_tokens_pair_kernel(const __grid_constant__ muav_config cfg, const __grid_constant__ Layout L,
+                                        const char* records, int max_tasks, int max_agents, float* tf, uint8_t* tm,
+                                        float* af, uint8_t* am, float* ev, int32_t* ids, int n) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  View V;
+  V.base = (char*)records + (size_t)e * L.record_bytes;
+  V.L = &L;
+  tokens_pair_env(V, cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * 13, tm + (size_t)e * max_tasks,
+                  af + (size_t)e * max_agents * 12, am + (size_t)e * max_agents,
+                  ev + (size_t)e * max_agents * max_tasks, ids + (size_t)e * max_tasks);
+}
+
+__global__ void muav_observe_kernel(const __grid_constant__ muav_config cfg, const __grid_constant__ Layout L,
+                                    const char* records, int max_rows, double* ti, uint8_t* pad, uint8_t* legal,
+                                    double* ao, float* ef, int32_t* n_rows, int n) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  View V;
+  V.base = (char*)records + (size_t)e * L.record_bytes;
+  V.L = &L;
+  int32_t nr = 0;
+  observe_env(V, cfg, max_rows, ti + (size_t)e * max_rows * MUAV_OBS_TASK_DIM, pad + (size_t)e * max_rows,
+              legal + (size_t)e * L.D.A * max_rows, ao + (size_t)e * L.D.A * MUAV_OBS_AGENT_DIM, ef + (size_t)e * 5, &nr);
+  if (n_rows) n_rows[e] = nr;
+}
+
+}  // namespace muav
+
+// ====================================================================== C ABI
+using namespace muav;
+
+static int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : -1000 - (int)e; }
+
+extern "C" {
+
+#include "muav_abi_common.inl"
+
+int muav_step(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* d_actions,
+              const muav_alloc_opts* opts, const muav_step_out* out, int n_envs, int n_steps, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (!d_records || n_envs < 0 || n_steps < 0) return -22;
+  if (n_envs == 0 || n_steps == 0) return 0;
+  StepParams P;
+  memset(&P, 0, sizeof(P));
+  P.cfg = *cfg;
+  P.L = make_layout(*cfg);
+  if (opts) P.opts = *opts;
+  if (out) P.out = *out;
+  P.records = (char*)d_records;
+  P.tapes = d_tapes;
+  P.actions = d_actions;
+  P.n_envs = n_envs;
+  P.n_steps = n_steps;
+  P.tape_stride = cfg->tape_words[0] + cfg->tape_words[1] + cfg->tape_words[2];
+  const char* st = getenv("MUAV_STAGE");
+  P.use_bulk = !(st && strcmp(st, "ldst") == 0);
+  size_t smem = (size_t)P.L.record_bytes + (size_t)P.L.scratch_bytes;
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(muav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_rc(e);
+    smem_set = smem;
+  }
+  muav_step_kernel<<<n_envs, 32, smem, (cudaStream_t)stream>>>(P);
+  return cuda_rc(cudaGetLastError());
+}
+
+int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* h_actions,
+                   const muav_alloc_opts* opts, double* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
+                   int n_envs, int n_steps, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  static void* d_buf = nullptr;
+  static size_t d_cap = 0;
+  size_t act_bytes = h_actions ? (size_t)n_envs * cfg->n_agents * 2 * sizeof(int32_t) : 0;
+  size_t off_rew = (act_bytes + 15) / 16 * 16;
+  size_t off_term = off_rew + (size_t)n_envs * 8;
+  size_t off_trunc = off_term + (size_t)n_envs;
+  size_t need = off_trunc + (size_t)n_envs;
+  if (need > d_cap) {
+    if (d_buf) cudaFree(d_buf);
+    cudaError_t e = cudaMalloc(&d_buf, need);
+    if (e != cudaSuccess) { d_buf = nullptr; d_cap = 0; return cuda_rc(e); }
+    d_cap = need;
+  }
+  char* b = (char*)d_buf;
+  if (h_actions) {
+    cudaError_t e = cudaMemcpyAsync(b, h_actions, act_bytes, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return cuda_rc(e);
+  }
+  muav_step_out out;
+  memset(&out, 0, sizeof(out));
+  out.d_reward = (double*)(b + off_rew);
+  out.d_terminated = (uint8_t*)(b + off_term);
+  out.d_truncated = (uint8_t*)(b + off_trunc);
+  rc = muav_step(cfg, d_records, d_tapes, h_actions ? (const int32_t*)b : nullptr, opts, &out, n_envs, n_steps, stream);
+  if (rc) return rc;
+  if (h_reward) cudaMemcpyAsync(h_reward, out.d_reward, (size_t)n_envs * 8, cudaMemcpyDeviceToHost, s);
+  if (h_terminated) cudaMemcpyAsync(h_terminated, out.d_terminated, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
+  if (h_truncated) cudaMemcpyAsync(h_truncated, out.d_truncated, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
+  return cuda_rc(cudaStreamSynchronize(s));
+}
+
+int muav_lsap(const double* d_cost, const int32_t* d_nr, const int32_t* d_nc, int nr_max, int nc_max, int32_t* d_col4row,
+              int n_problems, void* stream) {
+  if (!d_cost || !d_nr || !d_nc || !d_col4row || nr_max < 1 || nc_max < 1 || n_problems < 0) return -22;
+  if (n_problems == 0) return 0;
+  size_t smem = (size_t)alloc_scratch_bytes(nr_max, nc_max);
+  if (smem > 200 * 1024) return -7;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(muav_lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_rc(e);
+  }
+  muav_lsap_kernel<<<n_problems, 32, smem, (cudaStream_t)stream>>>(d_cost, d_nr, d_nc, nr_max, nc_max, d_col4row, n_problems);
+  return cuda_rc(cudaGetLastError());
+}
+
+int muav_avoid_obstacles(const double* d_pos, const double* d_move, const double* d_obstacles, int n_obstacles, double* d_out,
+                         int n, void* stream) {
+  if (n < 0 || n_obstacles < 0) return -22;
+  if (n == 0) return 0;
+  muav_avoid_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_pos, d_move, d_obstacles, n_obstacles, d_out, n);
+  return cuda_rc(cudaGetLastError());
+}
+
+const char* muav_metric_name(int idx) { return (idx >= 0 && idx < MUAV_N_METRICS) ? kMetricNames[idx] : nullptr; }
+
+int muav_metrics(const muav_config* cfg, const void* d_records, double* d_out, int n_envs, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (n_envs <= 0) return n_envs == 0 ? 0 : -22;
+  Layout L = make_layout(*cfg);
+  muav_metrics_kernel<<<(n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*cfg, L, (const char*)d_records, d_out, n_envs);
+  return cuda_rc(cudaGetLastError());
+}
+
+int muav_tokens_pair(const muav_config* cfg, const void* d_records, int max_tasks, int max_agents, float* d_task_feats,
+                     uint8_t* d_task_mask, float* d_agent_feats, uint8_t* d_agent_mask, float* d_edge_valid,
+                     int32_t* d_task_ids, int n_envs, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (n_envs <= 0) return n_envs == 0 ? 0 : -22;
+  if (max_tasks < 1 || max_agents < 1) return -22;
+  Layout L = make_layout(*cfg);
+  muav_tokens_pair_kernel<<<(n_envs + 63) / 64, 64, 0, (cudaStream_t)stream>>>(
+      *cfg, L, (const char*)d_records, max_tasks, max_agents, d_task_feats, d_task_mask, d_agent_feats, d_agent_mask,
+      d_edge_valid, d_task_ids, n_envs);
+  return cuda_rc(cudaGetLastError());
+}
+
+int muav_observe(const muav_config* cfg, const void* d_records, int max_rows, double* d_tasks_info, uint8_t* d_pad_mask,
+                 uint8_t* d_legal_mask, double* d_agent_obs, float* d_event_flags, int32_t* d_n_rows, int n_envs,
+                 void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (n_envs <= 0) return n_envs == 0 ? 0 : -22;
+  if (max_rows < 1) return -22;
+  Layout L = make_layout(*cfg);
+  muav_observe_kernel<<<(n_envs + 63) / 64, 64, 0, (cudaStream_t)stream>>>(*cfg, L, (const char*)d_records, max_rows,
+                                                                         d_tasks_info, d_pad_mask, d_legal_mask,
+                                                                         d_agent_obs, d_event_flags, d_n_rows, n_envs);
+  return cuda_rc(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -145,6 +145,14 @@ struct Layout {
 
 MUAV_HD inline int32_t align_up(int32_t x, int32_t a) { return (x + a - 1) / a * a; }
 
+// bytes of allocator scratch: cost[A*TC], u/v/spc[M], resid[TC] doubles + 6 M-sized and 2A+3TC int16 arrays
+MUAV_HD inline int32_t alloc_scratch_bytes(int A, int TC) {
+  int M = A > TC ? A : TC;
+  int b = 8 * (A * TC + 3 * M + TC);
+  b += 2 * (6 * M + 2 * A + 3 * TC);
+  return (b + 15) / 16 * 16;
+}
+
 MUAV_HD inline Layout make_layout(const muav_config& c) {
   Layout L;
   Dims D = dims_of(c);
@@ -157,16 +165,10 @@ MUAV_HD inline Layout make_layout(const muav_config& c) {
   MUAV_FIELDS(X)
 #undef X
   L.record_bytes = align_up(off, 16);
-  // allocator scratch: cost matrix + LSAP work arrays (see muav_core.cuh alloc_scratch)
-  int32_t nr = D.A, nc = D.TC;
-  int32_t s = 0;
-  s += 8 * nr * nc;            // cost (possibly transposed copy reuses it in place via index map)
-  s += 8 * (nr + nc) * 2;      // u, v (sized for either orientation)
-  s += 8 * (nr + nc);          // shortest path costs
-  s += 8 * nc;                 // residuals per round task
-  s += 2 * (nr + nc) * 6;      // path,col4row,row4col,remaining,SR,SC (int16)
-  s += 2 * (nr + nc) * 2;      // free agents, round tasks (int16)
-  s += 2 * nc;                 // pair-token column of each task (int16)
+  // per-warp scratch: allocator work arrays (muav_alloc.cuh carve_scratch) or the step's temporaries
+  int32_t s = alloc_scratch_bytes(D.A, D.TC);
+  int32_t s2 = 8 * 4 * D.A + 2 * D.A + 16;
+  if (s2 > s) s = s2;
   L.scratch_bytes = align_up(s, 16);
   return L;
 }

@@ -1,0 +1,232 @@
+// Read-only views of an environment record: pair tokens for the learned scorers and the
+// observation tensors.
+//   tokens_pair_env  -> build_pair_tokens (TaskAllocation/Hybrid/PairCostHybrid.py:31-65) over
+//                       build_att_tokens  (TaskAllocation/Hybrid/AttentionRAH.py:50-173, raw=False)
+//   observe_env      -> _generate_observations / get_task_info / _event_flag_vector
+//                       (mUAV_TA/DroneEnv.py:365-492)
+// Values are computed in float64 exactly as the reference's Python floats and narrowed to
+// float32 only where the reference stores float32 (np.float32 token matrices, event flags).
+#pragma once
+#include "muav_core.cuh"
+
+namespace muav {
+
+MUAV_HD inline double urgency_of(const View& V, int k, int t) {
+  int dl = V.k_deadline()[k];
+  if (dl < 0) return 0.0;
+  int rem = dl - t;
+  if (rem < 0) rem = 0;
+  return 1.0 - dmin((double)rem / 40.0, 1.0);
+}
+
+MUAV_HD inline bool view_known(const View& V, int a, int k) {
+  return (V.known()[(k >> 5) * V.L->D.A + a] >> (k & 31)) & 1u;
+}
+
+// task_feats [max_tasks,13] f32, task_mask [max_tasks] u8 (1 = padding), agent_feats [max_agents,12] f32,
+// agent_mask [max_agents] u8, edge_valid [max_agents,max_tasks] f32, task_ids [max_tasks] i32
+MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max_tasks, int max_agents, float* tf,
+                                    uint8_t* tm, float* af, uint8_t* am, float* ev, int32_t* ids) {
+  const int A = V.L->D.A, TC = V.L->D.TC;
+  const int n = V.hi()[HI_N_TASKS];
+  const int t = V.hi()[HI_T];
+  const double mc = C.max_coord;
+  const int horizon = C.max_time_steps > 1 ? C.max_time_steps : 1;
+  const double mid_x = C.area_w * 0.5;
+  const bool vis_none = !(C.sense_radius != 0.0) && !(C.threat_delay != 0);
+  const double urgent_thr = 1.0 - 12.0 / 40.0;
+  int n_live = 0;
+  for (int a = 0; a < A; ++a) n_live += V.a_state()[a] != -1;
+  const int n_agents = n_live > 1 ? n_live : 1;
+  for (int i = 0; i < max_tasks; ++i) {
+    tm[i] = 1;
+    ids[i] = 0;
+    for (int c = 0; c < 13; ++c) tf[i * 13 + c] = 0.0f;
+  }
+  for (int i = 0; i < max_agents; ++i) {
+    am[i] = 1;
+    for (int c = 0; c < 12; ++c) af[i * 12 + c] = 0.0f;
+    for (int j = 0; j < max_tasks; ++j) ev[i * max_tasks + j] = 0.0f;
+  }
+  // tasks
+  int n_open_all = 0;
+  int col = 0;
+  for (int k = 0; k < n; ++k) {
+    if (V.k_status()[k] == 2) continue;
+    int ti = V.k_type()[k];
+    double cur = V.k_cur()[ti * TC + k], al = V.k_alloc()[ti * TC + k];
+    if (!(al < cur)) continue;
+    ++n_open_all;
+    if (col >= max_tasks) continue;
+    double urg = urgency_of(V, k, t);
+    int n_know_i = 0;
+    for (int a = 0; a < A; ++a) n_know_i += view_known(V, a, k) ? 1 : 0;
+    double scar = 0.0;
+    if (!vis_none) scar = 1.0 - dmin((double)n_know_i / (double)n_agents, 1.0);
+    double rem = dmax(cur - al, 0.0);
+    double is_dyn = V.k_deadline()[k] >= 0 ? 1.0 : 0.0;
+    double n_know = vis_none ? 1.0 : (double)n_know_i;
+    double d_spec = mc;
+    bool any_spec = false;
+    for (int a = 0; a < A; ++a) {
+      if (V.a_state()[a] == -1 || V.a_type()[a] != UT_F2) continue;
+      double d = norm2(V.a_posx()[a] - V.k_posx()[k], V.a_posy()[a] - V.k_posy()[k]);
+      if (!any_spec || d < d_spec) d_spec = d;
+      any_spec = true;
+    }
+    float* f = tf + col * 13;
+    f[0] = (float)(V.k_posx()[k] / mc);
+    f[1] = (float)(V.k_posy()[k] / mc);
+    f[2] = (float)((double)ti / 8.0);
+    f[3] = ti == TT_ATT ? 1.0f : 0.0f;
+    f[4] = ti == TT_REC ? 1.0f : 0.0f;
+    f[5] = ti == TT_INT ? 1.0f : 0.0f;
+    f[6] = (float)urg;
+    f[7] = (float)scar;
+    f[8] = (float)dmin(rem / 4.0, 1.0);
+    f[9] = (float)is_dyn;
+    f[10] = (float)dmin(n_know / (double)n_agents, 1.0);
+    f[11] = (float)dmin(d_spec / mc, 1.0);
+    f[12] = V.k_posx()[k] < mid_x ? 0.0f : 1.0f;
+    tm[col] = 0;
+    ids[col] = k + 1;
+    ++col;
+  }
+  // agents
+  int row = 0;
+  for (int a = 0; a < A && row < max_agents; ++a) {
+    if (V.a_state()[a] == -1) continue;
+    int at = V.a_type()[a];
+    double cap_rec = V.a_caps()[1 * A + a], cap_att = V.a_caps()[2 * A + a], cap_def = V.a_caps()[3 * A + a];
+    int n_known_urgent = 0;
+    for (int k = 0; k < n; ++k) {
+      if (V.k_status()[k] == 2) continue;
+      int ti = V.k_type()[k];
+      if (!(V.k_alloc()[ti * TC + k] < V.k_cur()[ti * TC + k])) continue;
+      if (!vis_none && !view_known(V, a, k)) continue;
+      if (V.k_deadline()[k] >= 0 && urgency_of(V, k, t) >= urgent_thr) ++n_known_urgent;
+    }
+    float* f = af + row * 12;
+    f[0] = (float)(V.a_posx()[a] / mc);
+    f[1] = (float)(V.a_posy()[a] / mc);
+    f[2] = is_fighter(at) ? 1.0f : 0.0f;
+    f[3] = is_recon(at) ? 1.0f : 0.0f;
+    f[4] = V.a_qlen()[a] == 0 ? 1.0f : 0.0f;
+    f[5] = (float)dmin(cap_att / 2.0, 1.0);
+    f[6] = (float)dmin(cap_def / 2.0, 1.0);
+    f[7] = (float)dmin(cap_rec / 2.0, 1.0);
+    f[8] = (float)((double)V.a_state()[a] / 5.0);
+    f[9] = (float)((double)t / (double)horizon);
+    f[10] = (float)dmin((double)n_known_urgent / (double)(n_open_all > 1 ? n_open_all : 1), 1.0);
+    f[11] = at == UT_F2 ? 1.0f : 0.0f;
+    am[row] = 0;
+    // edge_valid (PairCostHybrid.py:41-60)
+    for (int j = 0; j < col; ++j) {
+      int k = ids[j] - 1;
+      if (!vis_none && !view_known(V, a, k)) continue;
+      int el = V.k_elig()[k];
+      if (el != 0 && !((el >> at) & 1)) continue;
+      if (V.a_caps()[V.k_type()[k] * A + a] <= 0) continue;
+      ev[row * max_tasks + j] = 1.0f;
+    }
+    ++row;
+  }
+}
+
+#define MUAV_OBS_TASK_DIM_ 21
+// tasks_info [max_rows, 21] f64: id, x, y, status, cur[6], alloc[6], init_time, end_time, type_idx, unmet, age
+// (status = -1 marks padding); pad_mask [max_rows]; legal_mask [A, max_rows]; agent_obs [A, 9]; event_flags [5] f32.
+MUAV_HD inline void observe_env(const View& V, const muav_config& C, int max_rows, double* ti_out, uint8_t* pad,
+                                uint8_t* legal, double* ao, float* ef, int32_t* n_rows_out) {
+  const int A = V.L->D.A, TC = V.L->D.TC;
+  const int n = V.hi()[HI_N_TASKS];
+  const int t = V.hi()[HI_T];
+  const double mc = C.max_coord;
+  const double mt = (double)(C.max_time_steps > 1 ? C.max_time_steps : 1);
+  for (int r = 0; r < max_rows; ++r) {
+    pad[r] = 0;
+    for (int c = 0; c < MUAV_OBS_TASK_DIM_; ++c) ti_out[r * MUAV_OBS_TASK_DIM_ + c] = 0.0;
+    ti_out[r * MUAV_OBS_TASK_DIM_ + 3] = -1.0;
+    for (int a = 0; a < A; ++a) legal[a * max_rows + r] = 0;
+  }
+  int rows = 0, n_open = 0;
+  for (int k = 0; k < n; ++k) {
+    if (V.k_status()[k] == 2) continue;
+    ++n_open;
+    if (rows >= max_rows) continue;
+    double* o = ti_out + rows * MUAV_OBS_TASK_DIM_;
+    int tt = V.k_type()[k];
+    o[0] = (double)(k + 1);
+    o[1] = V.k_posx()[k] / mc;
+    o[2] = V.k_posy()[k] / mc;
+    o[3] = (double)V.k_status()[k];
+    for (int c = 0; c < 6; ++c) {
+      o[4 + c] = V.k_cur()[c * TC + k];
+      o[10 + c] = V.k_alloc()[c * TC + k];
+    }
+    o[16] = (V.k_init()[k] - (double)t) / mt;
+    o[17] = (V.k_dtime()[k] - (double)t) / mt;
+    o[18] = (double)tt / 6.0;
+    double unmet = dmax(V.k_cur()[tt * TC + k] - V.k_alloc()[tt * TC + k], 0.0);
+    o[19] = unmet / dmax(V.k_org_ti()[k], 1e-6);
+    o[20] = dmin(((double)t - (double)V.k_created()[k]) / mt, 1.0);
+    pad[rows] = 1;
+    ++rows;
+  }
+  if (n_open == 0) {
+    // single idle row (DroneEnv.py:387-396)
+    ti_out[3] = 0.0;
+    pad[0] = 1;
+    for (int a = 0; a < A; ++a) {
+      int head = V.a_qlen()[a] > 0 ? V.a_queue()[a] : 0;
+      legal[a * max_rows] = (V.a_state()[a] == 2) ? (head == 0 ? 1 : 0) : 1;
+    }
+    rows = 1;
+  } else {
+    Sim S;
+    S.V = V;
+    S.Cp = &C;
+    for (int a = 0; a < A; ++a) {
+      uint8_t* lm = legal + a * max_rows;
+      int head = V.a_qlen()[a] > 0 ? V.a_queue()[a] : 0;
+      bool any = false;
+      for (int r = 0; r < rows; ++r) {
+        int tid = (int)ti_out[r * MUAV_OBS_TASK_DIM_];
+        lm[r] = S.is_valid(a, tid) ? 1 : 0;
+        any = any || lm[r];
+      }
+      if (!any) {
+        int hit = -1;
+        for (int r = 0; r < rows; ++r)
+          if ((int)ti_out[r * MUAV_OBS_TASK_DIM_] == head) { hit = r; break; }
+        lm[hit >= 0 ? hit : 0] = 1;
+      }
+      if (V.a_state()[a] == 2) {
+        for (int r = 0; r < rows; ++r) lm[r] = ((int)ti_out[r * MUAV_OBS_TASK_DIM_] == head) ? 1 : 0;
+      }
+    }
+  }
+  *n_rows_out = n_open == 0 ? 1 : n_open;
+  for (int a = 0; a < A; ++a) {
+    double* o = ao + a * 9;
+    o[0] = V.a_posx()[a] / mc;
+    o[1] = V.a_posy()[a] / mc;
+    for (int c = 0; c < 6; ++c) o[2 + c] = V.a_caps()[c * A + a];
+    o[8] = (double)(V.a_qlen()[a] > 0 ? V.a_queue()[a] : 0);
+  }
+  float fail = 0.0f, thr = 0.0f, rst = 0.0f;
+  int nev = V.hi()[HI_N_EVENTS];
+  for (int i = 0; i < nev; ++i) {
+    int tag = V.events()[i] & 0xff;
+    if (tag == EV_FAIL) fail = 1.0f;
+    else if (tag == EV_THREAT) thr = 1.0f;
+    else if (tag == EV_RESET) rst = 1.0f;
+  }
+  ef[0] = fail;
+  ef[1] = thr;
+  ef[2] = rst;
+  ef[3] = (float)((double)t / mt);
+  ef[4] = (float)((double)n_open / (double)(C.max_tasks > 1 ? C.max_tasks : 1));
+}
+
+}  // namespace muav

@@ -1,0 +1,190 @@
+"""TEST INFRASTRUCTURE (oracle) -- not part of the product path.
+
+Restates, over the oracle's flat state (oracle/sim.py):
+  build_att_tokens (raw=False)     TaskAllocation/Hybrid/AttentionRAH.py:50-173  (_urgency :29-34, _scarcity :37-41,
+                                   _known_by_count :44-47)
+  build_pair_tokens                TaskAllocation/Hybrid/PairCostHybrid.py:31-65
+  edge_score_dict + plan(scores=)  TaskAllocation/Hybrid/PairCostHybrid.py:280-291, 308-328
+  hybrid replan cadence            experiments/wps_eval.py:64-73
+  _generate_observations / get_task_info / _event_flag_vector   mUAV_TA/DroneEnv.py:365-492
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .fparith import norm2
+from .sim import UAV_TYPES, T_ATT, T_INT, T_REC, EV_FAIL, EV_RESET, EV_THREAT
+
+
+def urgency(env, k, t):
+    dl = env.k_deadline[k]
+    if dl < 0:
+        return 0.0
+    remaining = max(dl - t, 0)
+    return 1.0 - min(remaining / 40.0, 1.0)
+
+
+def hybrid_should_replan(env, events, interval=15):
+    return env.t == 0 or env.t % interval == 0 or any(ev[0] in (EV_RESET, EV_THREAT, EV_FAIL) for ev in events)
+
+
+def build_pair_tokens(env, max_tasks=32, max_agents=16):
+    A = env.n_agents
+    T = len(env.k_pos)
+    max_coord = float(env.max_coord)
+    horizon = max(env.max_time_steps, 1)
+    mid_x = float(env.area_width) * 0.5
+    vis = env.visibility()
+    live = env.live_agents()
+    n_agents = max(len(live), 1)
+    specialists = [a for a in live if UAV_TYPES[env.a_type[a]] == "F2"]
+    open_tasks = [k for k in range(T)
+                  if env.k_status[k] != 2 and env.k_alloc[k][env.k_type[k]] < env.k_cur[k][env.k_type[k]]]
+    task_feats = np.zeros((max_tasks, 13), dtype=np.float32)
+    task_mask = np.ones(max_tasks, dtype=bool)
+    task_ids = []
+    thr = 1.0 - 12.0 / 40.0
+    for i, k in enumerate(open_tasks[:max_tasks]):
+        ti = env.k_type[k]
+        urg = urgency(env, k, env.t)
+        if vis is None:
+            scar = 0.0
+            n_know = 1.0
+        else:
+            cnt = sum(1 for a in range(A) if vis[a][k])
+            scar = 1.0 - min(cnt / max(n_agents, 1), 1.0)
+            n_know = float(cnt)
+        rem = max(float(env.k_cur[k][ti] - env.k_alloc[k][ti]), 0.0)
+        is_dynamic = 1.0 if env.k_deadline[k] >= 0 else 0.0
+        tp = env.k_pos[k]
+        if specialists:
+            d_spec = min(norm2(env.a_pos[a][0] - tp[0], env.a_pos[a][1] - tp[1]) for a in specialists)
+        else:
+            d_spec = max_coord
+        region = 0.0 if float(tp[0]) < mid_x else 1.0
+        task_feats[i] = [
+            float(tp[0]) / max_coord, float(tp[1]) / max_coord, float(ti) / 8.0,
+            1.0 if ti == T_ATT else 0.0, 1.0 if ti == T_REC else 0.0, 1.0 if ti == T_INT else 0.0,
+            urg, scar, min(rem / 4.0, 1.0), is_dynamic, min(n_know / max(n_agents, 1), 1.0),
+            min(d_spec / max_coord, 1.0), region,
+        ]
+        task_mask[i] = False
+        task_ids.append(k + 1)
+    agent_feats = np.zeros((max_agents, 12), dtype=np.float32)
+    agent_mask = np.ones(max_agents, dtype=bool)
+    for i, a in enumerate(live[:max_agents]):
+        caps = env.a_caps[a]
+        atype = UAV_TYPES[env.a_type[a]]
+        n_known_urgent = 0
+        for k in open_tasks:
+            if vis is not None and not vis[a][k]:
+                continue
+            if urgency(env, k, env.t) >= thr and env.k_deadline[k] >= 0:
+                n_known_urgent += 1
+        agent_feats[i] = [
+            float(env.a_pos[a][0]) / max_coord, float(env.a_pos[a][1]) / max_coord,
+            1.0 if atype.startswith("F") else 0.0, 1.0 if atype.startswith("R") else 0.0,
+            1.0 if not env.a_queue[a] else 0.0,
+            min(float(caps[2]) / 2.0, 1.0), min(float(caps[3]) / 2.0, 1.0), min(float(caps[1]) / 2.0, 1.0),
+            float(env.a_state[a]) / 5.0, float(env.t) / horizon,
+            min(n_known_urgent / max(len(open_tasks), 1), 1.0), 1.0 if atype == "F2" else 0.0,
+        ]
+        agent_mask[i] = False
+    kept = open_tasks[:max_tasks]
+    edge_valid = np.zeros((max_agents, max_tasks), dtype=np.float32)
+    for i, a in enumerate(live[:max_agents]):
+        for j, k in enumerate(kept):
+            if vis is not None and not vis[a][k]:
+                continue
+            el = env.k_elig[k]
+            if el != 0 and not (el >> env.a_type[a]) & 1:
+                continue
+            if float(env.a_caps[a][env.k_type[k]]) <= 0:
+                continue
+            edge_valid[i, j] = 1.0
+    ids = np.zeros(max_tasks, dtype=np.int32)
+    ids[: len(task_ids)] = task_ids
+    return {"task_feats": task_feats, "task_mask": task_mask, "agent_feats": agent_feats, "agent_mask": agent_mask,
+            "edge_valid": edge_valid, "task_ids": ids, "open_tasks": [k + 1 for k in kept], "live": live, "vis": vis}
+
+
+def pair_plan(env, hung, scores, max_tasks=32, max_agents=16):
+    """PairCostHybrid.plan(scores=...) -> ordered [(agent_id, task_id)]."""
+    tok = build_pair_tokens(env, max_tasks, max_agents)
+    edge = {}
+    for i, a in enumerate(tok["live"][:max_agents]):
+        for j, tid in enumerate(tok["open_tasks"]):
+            if tok["edge_valid"][i, j] < 0.5:
+                continue
+            edge[(a, int(tid))] = float(scores[i, j])
+    return hung.allocate(env, agents=env.live_agents(), tasks=tok["open_tasks"], time_step=env.t,
+                         events=env.last_events, force=True, known=tok["vis"], edge_scores=edge)
+
+
+def observe(env, max_rows=None):
+    """Tensor form of _generate_observations (layout documented in include/muav.h, muav_observe)."""
+    A = env.n_agents
+    T = len(env.k_pos)
+    mc = float(env.max_coord)
+    mt = max(env.max_time_steps, 1)
+    max_rows = int(max_rows or env.max_tasks)
+    ti_out = np.zeros((max_rows, 21))
+    ti_out[:, 3] = -1.0
+    pad = np.zeros(max_rows, dtype=bool)
+    legal = np.zeros((A, max_rows), dtype=bool)
+    open_k = [k for k in range(T) if env.k_status[k] != 2]
+    rows = open_k[:max_rows]
+    for r, k in enumerate(rows):
+        tt = env.k_type[k]
+        o = ti_out[r]
+        o[0] = k + 1
+        o[1] = env.k_pos[k][0] / mc
+        o[2] = env.k_pos[k][1] / mc
+        o[3] = env.k_status[k]
+        o[4:10] = env.k_cur[k]
+        o[10:16] = env.k_alloc[k]
+        o[16] = (env.k_init_time[k] - env.t) / mt
+        o[17] = (env.k_done_time[k] - env.t) / mt
+        o[18] = float(tt) / 6.0
+        unmet = float(max(env.k_cur[k][tt] - env.k_alloc[k][tt], 0.0))
+        o[19] = unmet / max(float(env.k_org[k][tt]), 1e-6)
+        o[20] = min((env.t - float(env.k_created_at[k] or 0)) / mt, 1.0)
+        pad[r] = True
+    if not open_k:
+        ti_out[0, 3] = 0.0
+        pad[0] = True
+        for a in range(A):
+            head = env.a_queue[a][0] if env.a_queue[a] else 0
+            legal[a, 0] = (head == 0) if env.a_state[a] == 2 else True
+        n_rows = 1
+    else:
+        for a in range(A):
+            head = env.a_queue[a][0] if env.a_queue[a] else 0
+            m = [env._is_valid(a, k + 1) for k in rows]
+            if not any(m):
+                for r, k in enumerate(rows):
+                    if k + 1 == head:
+                        m[r] = True
+                        break
+                else:
+                    m[0] = True
+            if env.a_state[a] == 2:
+                m = [(k + 1) == head for k in rows]
+            legal[a, : len(rows)] = m
+        n_rows = len(open_k)
+    ao = np.zeros((A, 9))
+    for a in range(A):
+        ao[a, 0] = env.a_pos[a][0] / mc
+        ao[a, 1] = env.a_pos[a][1] / mc
+        ao[a, 2:8] = env.a_caps[a]
+        ao[a, 8] = env.a_queue[a][0] if env.a_queue[a] else 0
+    fail = threat = rst = 0.0
+    for ev in env.events:
+        if ev[0] == EV_FAIL:
+            fail = 1.0
+        elif ev[0] == EV_THREAT:
+            threat = 1.0
+        elif ev[0] == EV_RESET:
+            rst = 1.0
+    ef = np.asarray([fail, threat, rst, env.t / mt, len(open_k) / max(env.max_tasks, 1)], dtype=np.float32)
+    return {"tasks_info": ti_out, "mask": pad, "legal_mask": legal, "agent_obs": ao, "event_flags": ef, "n_rows": n_rows}

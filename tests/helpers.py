@@ -1,0 +1,153 @@
+"""Shared test helpers: golden-fixture loading and the CPU build of the kernel core."""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+for p in (ROOT, GOLDEN):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import refsnap  # noqa: E402
+from multi_uav_ta_gym_env_b200 import _lib, config, reset, state  # noqa: E402
+
+
+def load_golden(name):
+    with gzip.open(os.path.join(GOLDEN, name + ".json.gz"), "rt") as f:
+        return json.load(f)["episodes"]
+
+
+def golden_config(ep):
+    return config.wps_config(ep["case"], **ep.get("overrides", {}))
+
+
+def injected_scores(seed, t, n_rows, n_cols):
+    """Same generator as tests/golden/gen_golden.py (kept here so the GPU box needs no reference)."""
+    i = np.arange(n_rows, dtype=np.uint64)[:, None]
+    j = np.arange(n_cols, dtype=np.uint64)[None, :]
+    x = (np.uint64(seed) * np.uint64(1000003) + np.uint64(t) * np.uint64(7919)
+         + i * np.uint64(104729) + j * np.uint64(1299709) + np.uint64(12345))
+    x = (x * np.uint64(2654435761)) % np.uint64(2001)
+    return ((x.astype(np.float64) - 1000.0) / 1000.0 * 0.35).astype(np.float32)
+
+
+def alloc_opts_for(driver):
+    O = _lib.MuavAllocOpts()
+    O.max_coord = 1200.0
+    if driver in ("local_hungarian", "coalition", "global_hungarian"):
+        O.mode = 1
+        O.replan_interval = 12 if driver == "coalition" else 20
+        O.event_mask = 0x1F
+        O.use_visibility = 0 if driver == "global_hungarian" else 1
+    elif driver == "pair_injected":
+        O.mode = 2
+        O.replan_interval = 15
+        O.event_mask = 0b111
+        O.use_visibility = 1
+        O.pair_tokens = 1
+        O.score_rows = 16
+        O.score_cols = 32
+    else:
+        raise ValueError(driver)
+    return O
+
+
+class HostCheck:
+    """tests/hostcheck: the CUDA simulation core compiled for the CPU (never used by the product)."""
+
+    def __init__(self):
+        import __graft_entry__ as ge
+
+        path = ge.build_hostcheck()
+        self.lib = _lib.Lib(path)
+        P = C.c_void_p
+        d = self.lib.dll
+        d.hostcheck_step.restype = C.c_int
+        d.hostcheck_step.argtypes = [C.POINTER(_lib.MuavConfig), P, P, P, C.POINTER(_lib.MuavAllocOpts),
+                                     C.POINTER(_lib.MuavStepOut), C.c_int, C.c_int]
+        d.hostcheck_lsap.restype = C.c_int
+        d.hostcheck_lsap.argtypes = [P, P, P, C.c_int, C.c_int, P, C.c_int]
+
+    def make(self, opts, seeds, queue_cap=8):
+        return HostEnv(self, opts, seeds, queue_cap)
+
+    def lsap(self, cost, nr, nc):
+        cost = np.ascontiguousarray(cost, dtype=np.float64)
+        B, nr_max, nc_max = cost.shape
+        nr = np.ascontiguousarray(nr, dtype=np.int32)
+        nc = np.ascontiguousarray(nc, dtype=np.int32)
+        out = np.full((B, nr_max), -7, np.int32)
+        rc = self.lib.dll.hostcheck_lsap(cost.ctypes.data, nr.ctypes.data, nc.ctypes.data, nr_max, nc_max,
+                                         out.ctypes.data, B)
+        assert rc == 0
+        return out
+
+
+class HostEnv:
+    def __init__(self, hc, opts, seeds, queue_cap=8):
+        self.hc = hc
+        self.lib = hc.lib
+        self.opts = opts
+        self.cfg = _lib.build_config(opts, queue_cap=queue_cap)
+        self.E = len(seeds)
+        sc = [reset.generate_scenario(opts, int(s), list(self.cfg.tape_words)) for s in seeds]
+        self.rec, self.tapes = reset.pack_records(self.lib, self.cfg, sc)
+        self.codec = state.RecordCodec(self.lib, self.cfg)
+        E, A = self.E, self.cfg.n_agents
+        self.reward = np.zeros(E)
+        self.term = np.zeros(E, np.uint8)
+        self.trunc = np.zeros(E, np.uint8)
+        self.n_events = np.zeros(E, np.int32)
+        self.events = np.zeros((E, self.cfg.event_cap), np.int32)
+        self.n_pairs = np.zeros(E, np.int32)
+        self.pairs = np.zeros((E, A), np.int32)
+        self.n_open = np.zeros(E, np.int32)
+        out = _lib.MuavStepOut()
+        out.d_reward = self.reward.ctypes.data
+        out.d_terminated = self.term.ctypes.data
+        out.d_truncated = self.trunc.ctypes.data
+        out.d_n_events = self.n_events.ctypes.data
+        out.d_events = self.events.ctypes.data
+        out.d_n_pairs = self.n_pairs.ctypes.data
+        out.d_pairs = self.pairs.ctypes.data
+        out.d_n_open = self.n_open.ctypes.data
+        self.out = out
+
+    def step_actions(self, actions, n_steps=1):
+        """actions: per env ordered list of (agent, idx)."""
+        A = self.cfg.n_agents
+        act = np.full((self.E, A, 2), -1, np.int32)
+        for e, lst in enumerate(actions):
+            for i, (a, idx) in enumerate(lst):
+                act[e, i] = (a, idx)
+        rc = self.lib.dll.hostcheck_step(C.byref(self.cfg), self.rec.ctypes.data, self.tapes.ctypes.data,
+                                         act.ctypes.data, None, C.byref(self.out), self.E, n_steps)
+        assert rc == 0
+
+    def step_alloc(self, O, n_steps=1):
+        self.n_pairs[:] = 0
+        rc = self.lib.dll.hostcheck_step(C.byref(self.cfg), self.rec.ctypes.data, self.tapes.ctypes.data, None,
+                                         C.byref(O), C.byref(self.out), self.E, n_steps)
+        assert rc == 0
+
+    def snapshot(self, e):
+        return self.codec.snapshot(self.rec[e])
+
+    def digest(self, e):
+        return refsnap.digest(self.snapshot(e))
+
+    def pairs_of(self, e):
+        return [[int(p) >> 16, int(p) & 0xFFFF] for p in self.pairs[e, : self.n_pairs[e]]]
+
+    def events_of(self, e):
+        return [[int(v) & 0xFF, (int(v) >> 8) - 1] for v in self.events[e, : self.n_events[e]]]
+
+    def err(self, e):
+        return self.codec.header(self.rec[e], "ERRFLAGS")

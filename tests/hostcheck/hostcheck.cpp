@@ -1,0 +1,100 @@
+// TEST INFRASTRUCTURE -- CPU compile of the CUDA simulation core (muav_core.cuh / muav_alloc.cuh are
+// __host__ __device__) so that the kernel's logic can be diffed against the oracle and the golden
+// fixtures in the GPU-less authoring container.  Built by tests/hostcheck/build.py into
+// tests/hostcheck/_build/libmuav_hostcheck.so and loaded ONLY by tests (never by the package,
+// bench.py or smoke()): the product path has no CPU fallback.
+// g++ -O2 -ffp-contract=off: no FMA contraction, same rounding as nvcc -fmad=false.
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../multi_uav_ta_gym_env_b200/csrc/muav_alloc.cuh"
+
+using namespace muav;
+
+extern "C" {
+
+#include "../../multi_uav_ta_gym_env_b200/csrc/muav_abi_common.inl"
+
+// Same contract as muav_step but every pointer is a HOST pointer.
+int hostcheck_step(const muav_config* cfg, void* records, const uint32_t* tapes, const int32_t* actions,
+                   const muav_alloc_opts* opts, const muav_step_out* out, int n_envs, int n_steps) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  Layout L = make_layout(*cfg);
+  muav_alloc_opts O;
+  memset(&O, 0, sizeof(O));
+  if (opts) O = *opts;
+  muav_step_out Z;
+  memset(&Z, 0, sizeof(Z));
+  if (out) Z = *out;
+  char* scratch = (char*)malloc((size_t)L.scratch_bytes + 64);
+  int tape_stride = cfg->tape_words[0] + cfg->tape_words[1] + cfg->tape_words[2];
+  const int A = L.D.A;
+  int16_t act_agent[MUAV_MAX_AGENTS], act_tid[MUAV_MAX_AGENTS];
+  for (int e = 0; e < n_envs; ++e) {
+    Sim S;
+    S.V.base = (char*)records + (size_t)e * L.record_bytes;
+    S.V.L = &L;
+    S.Cp = cfg;
+    S.tape = tapes + (size_t)e * tape_stride;
+    S.scratch = scratch;
+    S.out_events = Z.d_events ? Z.d_events + (size_t)e * L.D.EVC : nullptr;
+    S.n_out_events = 0;
+    S.step_reward = 0.0;
+    View& V = S.V;
+    for (int s = 0; s < n_steps; ++s) {
+      if (HIv(DONE)) break;
+      int n_act = 0;
+      if (O.mode != 0) {
+        int np = allocate_tasks(S, O, e, act_agent, act_tid);
+        if (Z.d_n_pairs) Z.d_n_pairs[e] = np;
+        if (Z.d_pairs)
+          for (int i = 0; i < np; ++i) Z.d_pairs[(size_t)e * A + i] = ((int)act_agent[i] << 16) | (int)act_tid[i];
+        for (int i = 0; i < np; ++i) {
+          if (HIv(N_OPEN) > 0 && S.in_last_open(act_tid[i])) {
+            act_agent[n_act] = act_agent[i];
+            act_tid[n_act] = act_tid[i];
+            ++n_act;
+          }
+        }
+      } else if (actions) {
+        const int32_t* act = actions + (size_t)e * A * 2;
+        for (int i = 0; i < A; ++i) {
+          int a = act[2 * i];
+          if (a < 0) break;
+          act_agent[n_act] = (int16_t)a;
+          act_tid[n_act] = (int16_t)S.open_task_at(act[2 * i + 1]);
+          ++n_act;
+        }
+      }
+      StepResult r = S.step(act_agent, act_tid, n_act, 0, 1);
+      if (Z.d_reward) Z.d_reward[e] = r.reward;
+      if (Z.d_terminated) Z.d_terminated[e] = (uint8_t)r.terminated;
+      if (Z.d_truncated) Z.d_truncated[e] = (uint8_t)r.truncated;
+      if (Z.d_n_events) Z.d_n_events[e] = S.n_out_events;
+      if (Z.d_n_open) Z.d_n_open[e] = HIv(N_OPEN);
+    }
+  }
+  free(scratch);
+  return 0;
+}
+
+int hostcheck_lsap(const double* cost, const int32_t* nr_arr, const int32_t* nc_arr, int nr_max, int nc_max,
+                   int32_t* col4row, int n) {
+  char* scratch = (char*)malloc((size_t)alloc_scratch_bytes(nr_max, nc_max) + 64);
+  for (int b = 0; b < n; ++b) {
+    int nr = nr_arr[b], nc = nc_arr[b];
+    AllocScratch W = carve_scratch(scratch, nr_max, nc_max);
+    const double* src = cost + (size_t)b * nr_max * nc_max;
+    for (int i = 0; i < nr; ++i)
+      for (int j = 0; j < nc; ++j) W.cost[i * nc + j] = src[i * nc_max + j];
+    bool ok = (nr > 0 && nc > 0) ? lsap_solve(W.cost, nr, nc, W, W.col_of_row) : true;
+    for (int i = 0; i < nr_max; ++i) col4row[(size_t)b * nr_max + i] = (ok && i < nr && nc > 0) ? W.col_of_row[i] : -1;
+  }
+  free(scratch);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+"""The oracle (oracle/) against the golden fixtures produced by the UNMODIFIED reference
+(tests/golden/gen_golden.py): per-step digests of the full canonical state, rewards, drained
+events, allocator pairs and terminal metrics must be identical (bit-exact)."""
+import pytest
+
+from helpers import injected_scores, load_golden, golden_config
+import refsnap
+from oracle.hungarian import OracleHungarian, apply_assign, open_tasks
+from oracle.sim import OracleEnv
+from oracle import tokens as otok
+
+# (fixture, max episodes replayed on CPU -- keeps the CPU suite short; the GPU suite replays all)
+CASES = [
+    ("wps_easy_local", 3), ("wps_hard_local", 4), ("wps_burst_local", 2), ("wps_commit_local", 2),
+    ("wps_escort_coalition", 2), ("wps_hard_global", 2), ("wps_hard_pair", 3), ("wps_commit_pair", 1),
+    ("wps_hard_random", 3), ("wps_escort_random", 1), ("wps_attn_xl_local", 1), ("wps_hard_single_task", 2),
+]
+
+
+def replay(ep):
+    cfg = golden_config(ep)
+    o = OracleEnv(cfg).reset(ep["seed"])
+    assert str(refsnap.digest(o.snapshot())) == ep["digest0"]
+    drv = ep["driver"]
+    interval = 12 if drv == "coalition" else 20
+    hung = OracleHungarian(interval, o.max_coord)
+    for t, st in enumerate(ep["steps"]):
+        if drv in ("local_hungarian", "coalition", "global_hungarian"):
+            known = None if drv == "global_hungarian" else o.visibility()
+            pairs = hung.allocate(o, time_step=o.t, events=o.last_events, known=known)
+            assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
+            assert [list(a) for a in apply_assign(o, pairs)] == st["actions"], (ep["seed"], t)
+        elif drv == "pair_injected":
+            pairs = []
+            if otok.hybrid_should_replan(o, o.last_events, 15):
+                sc = injected_scores(ep["seed"], o.t, 16, 32)
+                pairs = otok.pair_plan(o, hung, sc)
+            assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
+        r, term, trunc, ev = o.step([tuple(a) for a in st["actions"]])
+        assert [list(e) for e in ev] == st["events"], (ep["seed"], t)
+        assert r == float.fromhex(st["reward"]), (ep["seed"], t)
+        assert (term, trunc) == (st["term"], st["trunc"])
+        assert len(o.last_open) == st["n_open"]
+        assert str(refsnap.digest(o.snapshot())) == st["digest"], (ep["seed"], t)
+    m = o.calculate_metrics()
+    for k, v in ep["metrics"].items():
+        want = float.fromhex(v) if isinstance(v, str) else v
+        assert m[k] == want or (m[k] != m[k] and want != want), k
+    if drv != "pair_injected":
+        assert hung.n_replans == ep["n_replans"]
+
+
+@pytest.mark.parametrize("name,n", CASES)
+def test_oracle_replays_reference(name, n):
+    for ep in load_golden(name)[:n]:
+        replay(ep)
+
+
+def test_known_answers_wps_easy_seed0():
+    """BASELINE.md section 2 / SURVEY.md 8(d) config 1: WPS_easy, seed 0, Local-Hungarian interval 20."""
+    ep = load_golden("wps_easy_local")[0]
+    assert ep["seed"] == 0
+    m = ep["metrics"]
+    assert (m["n_on_time"], m["n_missed_windows"], m["n_windowed_tasks"]) == (8, 4, 15)
+    assert (m["Kills"], m["Losses"], m["n_arrivals"], m["n_tasks_final"], m["n_task_switches"]) == (5, 4, 8, 27, 15)
+    assert abs(float.fromhex(m["S_WPS"]) - (-24.1033)) < 1e-3
+    assert abs(float.fromhex(m["total_distance"]) - 12399.0425) < 1e-3
+    ep = load_golden("wps_hard_local")[0]
+    m = ep["metrics"]
+    assert (m["n_on_time"], m["n_missed_windows"], m["n_windowed_tasks"], m["Kills"], m["Losses"]) == (8, 14, 26, 7, 4)
+    assert abs(float.fromhex(m["S_WPS"]) - (-324.0840)) < 1e-3
