@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the batched WPS step path (BASELINE.json metric: WPS_hard env-steps/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores
+
+A "step" is one pass of the hot path over the whole batch: pair tokens -> Att-Pair scorer (torch,
+random init, only for environments whose replan rule fires) -> fused Local-Hungarian allocate +
+env step kernel, for 4096 WPS_hard environments per GPU (BASELINE config 2).  Environments are
+independent, so N GPUs run N shards (weak scaling) and meet only in one NCCL all-reduce of the
+episode metric vector every 150 steps.
+
+Timed numbers:
+  value     env-steps/s, state resident in HBM, every step bracketed by CUDA events on the launching
+            stream, L2 flushed (256 MB write) between timed steps because the 46 MB state would
+            otherwise stay resident in the 126 MB L2; max over ranks.
+  e2e       same metric through the host-buffer path: allocator decisions are copied to pinned host
+            memory, fed back through muav_step_host (H2D actions, D2H reward/terminated/truncated).
+  roofline  algorithmic bytes of the step kernel / its measured launch time, against the measured
+            HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the oracle port (oracle/, the CPU restatement of the reference's Python path) on all
+            host cores, one env process per core, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CASE = "WPS_hard"
+ENVS_PER_GPU = 4096
+EPISODE = 150
+HYBRID_INTERVAL = 15
+METRIC = "WPS_hard env-steps/sec (batched, 1/2/4/8 B200) vs ref CPU; % HBM roofline"
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def _cpu_worker(args):
+    """One env process: the reference's Att-Pair episode loop (wps_eval.py:226-230, PairCostHybrid.plan)
+    restated on the oracle: tokens -> AttPairNet (CPU torch, 1 thread) -> Hungarian -> env.step."""
+    wid, min_steps, min_seconds, warmup = args
+    import torch
+
+    torch.set_num_threads(1)
+    from multi_uav_ta_gym_env_b200.config import wps_config
+    from multi_uav_ta_gym_env_b200.scorers import AttPairNet
+    from oracle.hungarian import OracleHungarian, apply_assign
+    from oracle.sim import OracleEnv
+    from oracle import tokens as otok
+
+    torch.manual_seed(0)
+    net = AttPairNet().eval()
+    cfg = wps_config(CASE)
+
+    def episode(seed, budget):
+        env = OracleEnv(cfg).reset(seed)
+        hung = OracleHungarian(20, env.max_coord)
+        n = 0
+        while n < budget and env.t < EPISODE:
+            pairs = []
+            if otok.hybrid_should_replan(env, env.last_events, HYBRID_INTERVAL):
+                tok = otok.build_pair_tokens(env, 32, 16)
+                with torch.no_grad():
+                    logits, _ = net(torch.from_numpy(tok["task_feats"])[None], torch.from_numpy(tok["task_mask"])[None],
+                                    torch.from_numpy(tok["agent_feats"])[None], torch.from_numpy(tok["agent_mask"])[None])
+                scores = (torch.tanh(logits[0]) * 0.35).numpy() * tok["edge_valid"]
+                pairs = otok.pair_plan(env, hung, scores)
+            env.step(apply_assign(env, pairs))
+            n += 1
+        return n
+
+    seed = 10_000 * (wid + 1)
+    done = 0
+    while done < warmup:
+        done += episode(seed, warmup - done)
+        seed += 1
+    t0 = time.perf_counter()
+    steps = 0
+    while steps < min_steps or (time.perf_counter() - t0) < min_seconds:
+        steps += episode(seed, 10**9)
+        seed += 1
+    return steps, time.perf_counter() - t0
+
+
+def run_cpu_arm(min_steps, warmup, min_seconds=12.0, procs=None):
+    import multiprocessing as mp
+
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_worker, [(w, min_steps, min_seconds, warmup) for w in range(procs)])
+    total = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return {"value": total / wall, "unit": "env-steps/s", "cores": procs, "kind": "port",
+            "sample": f"{procs} oracle env processes x >= {min_seconds:.0f} s of WPS_hard Att-Pair episodes "
+                      f"({total} env-steps, torch CPU scorer 1 thread/process)",
+            "env_steps": total, "seconds": wall}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.samples = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from multi_uav_ta_gym_env_b200 import AllocSpec, BatchedMultiUAVEnv, wps_config
+    from multi_uav_ta_gym_env_b200.scorers import AttPairNet, pair_scores
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = run_cpu_arm(EPISODE, 30, min_seconds=args.cpu_seconds)  # before CUDA is initialised (fork)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E = args.envs
+    cfg = wps_config(CASE)
+    env = BatchedMultiUAVEnv(cfg, E, device=dev).reset(range(rank * E, (rank + 1) * E))
+    torch.manual_seed(0)
+    net = AttPairNet().to(dev).eval()
+    spec = AllocSpec.pair_hybrid(HYBRID_INTERVAL)
+    scores = torch.zeros(E, 16, 32, dtype=torch.float32, device=dev)
+    tag_off, tag_cnt, _ = env.codec.F["hi"]
+    tag_idx = env.lib.header_index("EV_TAGMASK")
+    hi_view = env.records[:, tag_off:tag_off + tag_cnt * 4].view(torch.int32)
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    metric_acc = torch.zeros(32, dtype=torch.float64, device=dev)
+    names = env.lib.metric_names()
+    launches = {"n": 0}
+
+    def score_step(t):
+        """tokens + scorer for the environments whose hybrid replan rule fires at time t."""
+        if t == 0 or t % HYBRID_INTERVAL == 0:
+            idx = None
+        else:
+            need = (hi_view[:, tag_idx] & 0b111) != 0
+            idx = need.nonzero(as_tuple=True)[0]
+            if idx.numel() == 0:
+                return
+        tok = env.tokens_pair(32, 16)
+        launches["n"] += 1
+        if idx is None:
+            scores.copy_(pair_scores(net, tok))
+        else:
+            sub = {k: v.index_select(0, idx) for k, v in tok.items()}
+            scores.index_copy_(0, idx, pair_scores(net, sub))
+
+    def episode_end():
+        m = env.metrics()
+        launches["n"] += 1
+        vec = torch.zeros(32, dtype=torch.float64, device=dev)
+        vec[0] = E
+        vec[1] = m[:, names.index("S_WPS")].sum()
+        vec[2] = (m[:, names.index("S_WPS")] ** 2).sum()
+        vec[3] = m[:, names.index("n_on_time")].sum()
+        vec[4] = m[:, names.index("n_missed_windows")].sum()
+        vec[5] = m[:, names.index("Kills")].sum()
+        vec[6] = m[:, names.index("Losses")].sum()
+        vec[7] = m[:, names.index("total_distance")].sum()
+        vec[8] = m[:, names.index("n_task_switches")].sum()
+        vec[9] = m[:, names.index("S_ESC")].sum()
+        if world > 1:
+            dist.all_reduce(vec)  # the path's only collective: end-of-episode metric sum over NVLink
+        metric_acc.add_(vec)
+        env.restore()
+
+    def device_step(t):
+        score_step(t)
+        env.step_allocated(spec, 1, edge_scores=scores)
+        launches["n"] += 1
+        if t + 1 == EPISODE:
+            episode_end()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up (then rewind so that the timed region starts at an episode boundary)
+    for w in range(max(args.warmup, 3)):
+        device_step(w % EPISODE)
+    env.restore()
+    metric_acc.zero_()
+    barrier()
+
+    # ---- timed: K steps, each bracketed by CUDA events, L2 flushed between steps
+    K = args.steps
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches["n"] = 0
+    barrier()
+    for k in range(K):
+        t = k % EPISODE
+        flush_buf.fill_(k & 0xFF)
+        ev[k][0].record()
+        score_step(t)
+        ev[k][1].record()
+        env.step_allocated(spec, 1, edge_scores=scores)
+        launches["n"] += 1
+        ev[k][2].record()
+        if t + 1 == EPISODE:
+            episode_end()
+    barrier()
+    clocks = sampler.stop()
+    step_ms = sum(a.elapsed_time(c) for a, b, c in ev)
+    kern_ms = sum(b.elapsed_time(c) for a, b, c in ev)
+    gpu_launches = launches["n"]
+    t_all = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    step_ms, kern_ms = t_all.tolist()
+    value = world * E * K / (step_ms / 1e3)
+
+    # ---- end-to-end through the host-buffer entry point
+    env.restore()
+    A = env.n_agents
+    h_act = torch.empty(E, A, 2, dtype=torch.int32).pin_memory()
+    d_act = torch.empty(E, A, 2, dtype=torch.int32, device=dev)
+    h_rew = torch.empty(E, dtype=torch.float64).pin_memory()
+    h_term = torch.empty(E, dtype=torch.uint8).pin_memory()
+    h_trunc = torch.empty(E, dtype=torch.uint8).pin_memory()
+    import ctypes as C
+    Ke = min(K, 2 * EPISODE)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(Ke):
+        t = k % EPISODE
+        score_step(t)
+        env.allocate(spec, edge_scores=scores, actions_out=d_act)
+        h_act.copy_(d_act, non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller now holds the allocator's decision
+        rc = env.lib.dll.muav_step_host(C.byref(env.cfg), env.records.data_ptr(), env.tapes.data_ptr(), h_act.data_ptr(),
+                                        None, h_rew.data_ptr(), h_term.data_ptr(), h_trunc.data_ptr(), E, 1,
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        if t + 1 == EPISODE:
+            episode_end()
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * E * Ke / (e2e_ms.item() / 1e3)
+    act_bytes = E * A * 2 * 4
+
+    if rank == 0:
+        rb = env.record_bytes
+        out_bytes = 8 + 1 + 1 + 4 + 4 + 4
+        b_alg = 2 * rb + out_bytes
+        peak, peak_src = hbm_peak()
+        achieved = E * b_alg / (kern_ms / K / 1e3) / 1e9
+        macc = metric_acc.cpu().numpy()
+        n_eps = max(macc[0], 1.0)
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{CASE} (8 agents), {E} envs per GPU, Local-Hungarian + random-init Att-Pair "
+                                   f"edge scores, hybrid replan rule t%15/events, seeds = env index",
+                       "envs_per_gpu": E, "global_envs": world * E, "parallelism": f"env-shard x{world}",
+                       "l2": "flushed between timed steps (256 MB write); state 46 MB < 126 MB L2",
+                       "record_bytes": rb, "agent_steps_per_s": value * A},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes,
+                    "d2h_bytes_per_step": act_bytes + E * 10, "steps": Ke},
+            "gpu_launches": gpu_launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "muav_step_kernel", "bytes_per_env_step": b_alg,
+                         "kernel_ms_per_launch": kern_ms / K, "peak_source": peak_src,
+                         "kernel_share_of_step": kern_ms / step_ms},
+            "episode_stats": {"episodes": float(macc[0]), "mean_S_WPS": float(macc[1] / n_eps),
+                              "mean_on_time": float(macc[3] / n_eps), "mean_missed": float(macc[4] / n_eps)},
+        }
+        if cpu_base is not None:
+            line["cpu_baseline"] = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = run_cpu_arm(max(args.steps, 1), max(args.warmup, 3), min_seconds=args.cpu_seconds)
+    value = res["value"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": int(args.gpus),
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 / value if value else None,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{CASE} (8 agents), one env process per host core, Local-Hungarian + random-init "
+                               f"Att-Pair edge scores (reference algorithm restated in oracle/; the Python reference "
+                               f"itself cannot travel to the GPU box)"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -10,7 +10,7 @@
  * Reference interfaces replaced (paths relative to the reference repo):
  *   muav_step / muav_rollout  -> MultiUAVEnv.step             mUAV_TA/DroneEnv.py:774-1206
  *                                (+ UAV/Task bookkeeping       mUAV_TA/DroneEnvComponents.py:55-179,280-326)
- *   muav_allocate (fused in step via muav_alloc_opts)
+ *   muav_allocate (also fused in muav_step via muav_alloc_opts)
  *                             -> HungarianAllocator.allocate_tasks
  *                                                              TaskAllocation/OptimizationBased/HungarianAllocator.py:72-208
  *                                and the driver glue           experiments/paper_eval.py:85-101, experiments/wps_eval.py:55-73
@@ -109,6 +109,11 @@ int muav_header_index(const char* name); /* index into the hi (int32) or hf (dou
  * (ignored when opts->mode != 0).  */
 int muav_step(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* d_actions,
               const muav_alloc_opts* opts, const muav_step_out* out, int n_envs, int n_steps, void* stream);
+/* Allocator only (HungarianAllocator.allocate_tasks + _apply_assign): no env step.  Writes out->d_pairs / d_n_pairs and,
+ * when d_actions_out != NULL, the ordered action list [E, n_agents, 2] (agent_id, index into last_tasks_info; agent_id -1
+ * terminates) that muav_step accepts.  Per-env allocator state (last_plan_step, n_replans, n_calls) advances. */
+int muav_allocate(const muav_config* cfg, void* d_records, const muav_alloc_opts* opts, const muav_step_out* out,
+                  int32_t* d_actions_out, int n_envs, void* stream);
 /* Same call with HOST action / output buffers: copies in, runs, copies out, synchronises. */
 int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* h_actions,
                    const muav_alloc_opts* opts, double* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,

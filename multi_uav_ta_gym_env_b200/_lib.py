@@ -67,7 +67,7 @@ class MuavStepOut(C.Structure):
 # every symbol include/muav.h declares
 ABI_SYMBOLS = [
     "muav_version", "muav_config_size", "muav_record_bytes", "muav_scratch_bytes", "muav_num_fields",
-    "muav_field_info", "muav_header_index", "muav_step", "muav_step_host", "muav_lsap",
+    "muav_field_info", "muav_header_index", "muav_step", "muav_allocate", "muav_step_host", "muav_lsap",
     "muav_avoid_obstacles", "muav_metric_name", "muav_metrics", "muav_tokens_pair", "muav_observe",
 ]
 
@@ -150,6 +150,9 @@ class CudaLib(Lib):
         d.muav_step.restype = C.c_int
         d.muav_step.argtypes = [C.POINTER(MuavConfig), P, P, P, C.POINTER(MuavAllocOpts), C.POINTER(MuavStepOut),
                                 C.c_int, C.c_int, P]
+        d.muav_allocate.restype = C.c_int
+        d.muav_allocate.argtypes = [C.POINTER(MuavConfig), P, C.POINTER(MuavAllocOpts), C.POINTER(MuavStepOut), P,
+                                    C.c_int, P]
         d.muav_step_host.restype = C.c_int
         d.muav_step_host.argtypes = [C.POINTER(MuavConfig), P, P, P, C.POINTER(MuavAllocOpts), P, P, P,
                                      C.c_int, C.c_int, P]

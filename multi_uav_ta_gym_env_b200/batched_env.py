@@ -135,9 +135,7 @@ class BatchedMultiUAVEnv:
         self.launches += 1
         return self.reward, self.terminated, self.truncated
 
-    def step_allocated(self, spec: AllocSpec, n_steps: int = 1, edge_scores: Optional[torch.Tensor] = None,
-                       priorities: Optional[torch.Tensor] = None, reserved: Optional[torch.Tensor] = None):
-        """n_steps fused (allocate -> step) iterations per environment, state resident in shared memory."""
+    def _alloc_opts(self, spec, edge_scores, priorities, reserved):
         O = _lib.MuavAllocOpts()
         O.mode = spec.mode
         O.replan_interval = spec.replan_interval
@@ -159,11 +157,31 @@ class BatchedMultiUAVEnv:
             rs = reserved.to(device=self.device, dtype=torch.uint8).contiguous()
             keep.append(rs)
             O.d_reserved = rs.data_ptr()
+        return O, keep
+
+    def step_allocated(self, spec: AllocSpec, n_steps: int = 1, edge_scores: Optional[torch.Tensor] = None,
+                       priorities: Optional[torch.Tensor] = None, reserved: Optional[torch.Tensor] = None):
+        """n_steps fused (allocate -> step) iterations per environment, state resident in shared memory."""
+        O, keep = self._alloc_opts(spec, edge_scores, priorities, reserved)
         rc = self.lib.dll.muav_step(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(), None,
                                     C.byref(O), C.byref(self._out), self.n_envs, n_steps, self._stream())
         _lib.check(rc, "muav_step")
         self.launches += 1
         return self.reward, self.terminated, self.truncated
+
+    def allocate(self, spec: AllocSpec, edge_scores: Optional[torch.Tensor] = None,
+                 priorities: Optional[torch.Tensor] = None, reserved: Optional[torch.Tensor] = None,
+                 actions_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Allocator only: fills self.pairs / self.n_pairs and returns the ordered action tensor
+        int32 [E, A, 2] that step_batched accepts (allocate_tasks + _apply_assign)."""
+        O, keep = self._alloc_opts(spec, edge_scores, priorities, reserved)
+        if actions_out is None:
+            actions_out = torch.empty(self.n_envs, self.n_agents, 2, dtype=torch.int32, device=self.device)
+        rc = self.lib.dll.muav_allocate(C.byref(self.cfg), self.records.data_ptr(), C.byref(O), C.byref(self._out),
+                                        actions_out.data_ptr(), self.n_envs, self._stream())
+        _lib.check(rc, "muav_allocate")
+        self.launches += 1
+        return actions_out
 
     # ------------------------------------------------------------------ views
     def metrics(self) -> torch.Tensor:

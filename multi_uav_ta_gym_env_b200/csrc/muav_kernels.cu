@@ -61,7 +61,8 @@ struct StepParams {
   char* records;
   const uint32_t* tapes;
   const int32_t* actions;
-  int n_envs, n_steps, tape_stride, use_bulk;
+  int32_t* actions_out;  // allocate-only mode: ordered (agent, index) list per env
+  int n_envs, n_steps, tape_stride, use_bulk, alloc_only;
 };
 
 // One warp (= one CTA) per environment.
@@ -109,6 +110,28 @@ __global__ void __launch_bounds__(32) muav_step_kernel(const __grid_constant__ S
   S.step_reward = 0.0;
   View& V = S.V;
   const int A = L.D.A;
+
+  if (P.alloc_only) {
+    if (lane == 0) {
+      int np = HIv(DONE) ? 0 : allocate_tasks(S, P.opts, e, act_agent, act_tid);
+      if (P.out.d_n_pairs) P.out.d_n_pairs[e] = np;
+      int n_act = 0;
+      for (int i = 0; i < np; ++i) {
+        if (P.out.d_pairs) P.out.d_pairs[(size_t)e * A + i] = ((int)act_agent[i] << 16) | (int)act_tid[i];
+        if (P.actions_out && HIv(N_OPEN) > 0 && S.in_last_open(act_tid[i])) {
+          // index of the task inside last_tasks_info = number of open tasks with a smaller id
+          int k = act_tid[i] - 1, idx = 0;
+          for (int w = 0; w < (k >> 5); ++w) idx += __popc(V.open_mask()[w]);
+          idx += __popc(V.open_mask()[k >> 5] & ((1u << (k & 31)) - 1u));
+          P.actions_out[((size_t)e * A + n_act) * 2] = act_agent[i];
+          P.actions_out[((size_t)e * A + n_act) * 2 + 1] = idx;
+          ++n_act;
+        }
+      }
+      if (P.actions_out && n_act < A) P.actions_out[((size_t)e * A + n_act) * 2] = -1;
+    }
+    __syncwarp();
+  }
 
   for (int s = 0; s < P.n_steps; ++s) {
     if (HIv(DONE)) break;
@@ -300,6 +323,18 @@ extern "C" {
 
 #include "muav_abi_common.inl"
 
+static int launch_step(const StepParams& P, void* stream) {
+  size_t smem = (size_t)P.L.record_bytes + (size_t)P.L.scratch_bytes;
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(muav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_rc(e);
+    smem_set = smem;
+  }
+  muav_step_kernel<<<P.n_envs, 32, smem, (cudaStream_t)stream>>>(P);
+  return cuda_rc(cudaGetLastError());
+}
+
 int muav_step(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* d_actions,
               const muav_alloc_opts* opts, const muav_step_out* out, int n_envs, int n_steps, void* stream) {
   int rc = check_cfg(cfg);
@@ -320,15 +355,29 @@ int muav_step(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, 
   P.tape_stride = cfg->tape_words[0] + cfg->tape_words[1] + cfg->tape_words[2];
   const char* st = getenv("MUAV_STAGE");
   P.use_bulk = !(st && strcmp(st, "ldst") == 0);
-  size_t smem = (size_t)P.L.record_bytes + (size_t)P.L.scratch_bytes;
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(muav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_rc(e);
-    smem_set = smem;
-  }
-  muav_step_kernel<<<n_envs, 32, smem, (cudaStream_t)stream>>>(P);
-  return cuda_rc(cudaGetLastError());
+  return launch_step(P, stream);
+}
+
+int muav_allocate(const muav_config* cfg, void* d_records, const muav_alloc_opts* opts, const muav_step_out* out,
+                  int32_t* d_actions_out, int n_envs, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (!d_records || !opts || n_envs < 0) return -22;
+  if (n_envs == 0) return 0;
+  StepParams P;
+  memset(&P, 0, sizeof(P));
+  P.cfg = *cfg;
+  P.L = make_layout(*cfg);
+  P.opts = *opts;
+  if (out) P.out = *out;
+  P.records = (char*)d_records;
+  P.actions_out = d_actions_out;
+  P.n_envs = n_envs;
+  P.n_steps = 0;
+  P.alloc_only = 1;
+  const char* st = getenv("MUAV_STAGE");
+  P.use_bulk = !(st && strcmp(st, "ldst") == 0);
+  return launch_step(P, stream);
 }
 
 int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* h_actions,
