@@ -170,7 +170,7 @@ def run_gpu_arm(args):
     import torch.distributed as dist
 
     from multi_uav_ta_gym_env_b200 import AllocSpec, BatchedMultiUAVEnv, wps_config
-    from multi_uav_ta_gym_env_b200.scorers import AttPairNet, pair_scores
+    from multi_uav_ta_gym_env_b200.scorers import AttPairNet, GraphedPairScorer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -189,30 +189,25 @@ def run_gpu_arm(args):
     net = AttPairNet().to(dev).eval()
     spec = AllocSpec.pair_hybrid(HYBRID_INTERVAL)
     scores = torch.zeros(E, 16, 32, dtype=torch.float32, device=dev)
-    tag_off, tag_cnt, _ = env.codec.F["hi"]
-    tag_idx = env.lib.header_index("EV_TAGMASK")
-    hi_view = env.records[:, tag_off:tag_off + tag_cnt * 4].view(torch.int32)
+    # the step kernel emits the pair tokens of every env that will replan before the next step
+    tok = env.enable_fused_tokens(32, 16, HYBRID_INTERVAL, 0b111)
+    scorer = GraphedPairScorer(net, E, dev)
+    scorer.warm()
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     metric_acc = torch.zeros(32, dtype=torch.float64, device=dev)
     names = env.lib.metric_names()
     launches = {"n": 0}
 
     def score_step(t):
-        """tokens + scorer for the environments whose hybrid replan rule fires at time t."""
-        if t == 0 or t % HYBRID_INTERVAL == 0:
-            idx = None
-        else:
-            need = (hi_view[:, tag_idx] & 0b111) != 0
-            idx = need.nonzero(as_tuple=True)[0]
-            if idx.numel() == 0:
-                return
-        tok = env.tokens_pair(32, 16)
-        launches["n"] += 1
-        if idx is None:
-            scores.copy_(pair_scores(net, tok))
-        else:
-            sub = {k: v.index_select(0, idx) for k, v in tok.items()}
-            scores.index_copy_(0, idx, pair_scores(net, sub))
+        """Att-Pair scorer for the environments whose hybrid replan rule fires at time t (wps_eval.py:64-73)."""
+        if t == 0:
+            env.refresh_fused_tokens()  # episode start: standalone token kernel for all envs
+            launches["n"] += 1
+        if t % HYBRID_INTERVAL == 0:
+            scorer.score_all(tok, scores)
+            return
+        idx = tok["need"].nonzero(as_tuple=True)[0]   # one 4-byte sync: how many environments replan now
+        scorer.score_subset(tok, idx, scores)
 
     def episode_end():
         m = env.metrics()
@@ -302,7 +297,7 @@ def run_gpu_arm(args):
         h_act.copy_(d_act, non_blocking=True)
         torch.cuda.current_stream().synchronize()          # the caller now holds the allocator's decision
         rc = env.lib.dll.muav_step_host(C.byref(env.cfg), env.records.data_ptr(), env.tapes.data_ptr(), h_act.data_ptr(),
-                                        None, h_rew.data_ptr(), h_term.data_ptr(), h_trunc.data_ptr(), E, 1,
+                                        None, env._tok_ref(), h_rew.data_ptr(), h_term.data_ptr(), h_trunc.data_ptr(), E, 1,
                                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
         assert rc == 0
         if t + 1 == EPISODE:

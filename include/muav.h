@@ -95,6 +95,20 @@ typedef struct muav_step_out {
   int32_t* d_n_open;     /* [E] len(env.last_tasks_info) after the step */
 } muav_step_out;
 
+/* Optional pair-token emission fused at the end of each step (saves the separate muav_tokens_pair pass):
+ * for every env whose hybrid replan rule will fire before the NEXT step -- (T % interval == 0) or a listed
+ * event tag among the events this step drained -- d_need[e] = 1 and the env's token rows are written. */
+typedef struct muav_token_out {
+  float* d_task_feats;    /* [E, max_tasks, 13] */
+  uint8_t* d_task_mask;   /* [E, max_tasks] 1 = padding */
+  float* d_agent_feats;   /* [E, max_agents, 12] */
+  uint8_t* d_agent_mask;  /* [E, max_agents] */
+  float* d_edge_valid;    /* [E, max_agents, max_tasks] */
+  int32_t* d_task_ids;    /* [E, max_tasks] */
+  uint8_t* d_need;        /* [E] */
+  int32_t max_tasks, max_agents, interval, event_mask;
+} muav_token_out;
+
 const char* muav_version(void);
 size_t muav_config_size(void);
 size_t muav_record_bytes(const muav_config* cfg);
@@ -108,7 +122,8 @@ int muav_header_index(const char* name); /* index into the hi (int32) or hf (dou
  * d_actions: [E, n_agents, 2] int32 ordered (agent_id, index into last_tasks_info), agent_id = -1 ends the list
  * (ignored when opts->mode != 0).  */
 int muav_step(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* d_actions,
-              const muav_alloc_opts* opts, const muav_step_out* out, int n_envs, int n_steps, void* stream);
+              const muav_alloc_opts* opts, const muav_step_out* out, const muav_token_out* tok, int n_envs, int n_steps,
+              void* stream);
 /* Allocator only (HungarianAllocator.allocate_tasks + _apply_assign): no env step.  Writes out->d_pairs / d_n_pairs and,
  * when d_actions_out != NULL, the ordered action list [E, n_agents, 2] (agent_id, index into last_tasks_info; agent_id -1
  * terminates) that muav_step accepts.  Per-env allocator state (last_plan_step, n_replans, n_calls) advances. */
@@ -116,8 +131,8 @@ int muav_allocate(const muav_config* cfg, void* d_records, const muav_alloc_opts
                   int32_t* d_actions_out, int n_envs, void* stream);
 /* Same call with HOST action / output buffers: copies in, runs, copies out, synchronises. */
 int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* h_actions,
-                   const muav_alloc_opts* opts, double* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
-                   int n_envs, int n_steps, void* stream);
+                   const muav_alloc_opts* opts, const muav_token_out* tok, double* h_reward, uint8_t* h_terminated,
+                   uint8_t* h_truncated, int n_envs, int n_steps, void* stream);
 
 /* Batched rectangular LSAP: B problems, cost [B, nr_max, nc_max] row-major with per-problem sizes.
  * out_col4row [B, nr_max]: column assigned to each row or -1 (SciPy tie-breaking reproduced). */

@@ -64,6 +64,14 @@ class MuavStepOut(C.Structure):
     ]
 
 
+class MuavTokenOut(C.Structure):
+    _fields_ = [
+        ("d_task_feats", C.c_void_p), ("d_task_mask", C.c_void_p), ("d_agent_feats", C.c_void_p),
+        ("d_agent_mask", C.c_void_p), ("d_edge_valid", C.c_void_p), ("d_task_ids", C.c_void_p), ("d_need", C.c_void_p),
+        ("max_tasks", C.c_int32), ("max_agents", C.c_int32), ("interval", C.c_int32), ("event_mask", C.c_int32),
+    ]
+
+
 # every symbol include/muav.h declares
 ABI_SYMBOLS = [
     "muav_version", "muav_config_size", "muav_record_bytes", "muav_scratch_bytes", "muav_num_fields",
@@ -149,13 +157,13 @@ class CudaLib(Lib):
         P = C.c_void_p
         d.muav_step.restype = C.c_int
         d.muav_step.argtypes = [C.POINTER(MuavConfig), P, P, P, C.POINTER(MuavAllocOpts), C.POINTER(MuavStepOut),
-                                C.c_int, C.c_int, P]
+                                C.POINTER(MuavTokenOut), C.c_int, C.c_int, P]
         d.muav_allocate.restype = C.c_int
         d.muav_allocate.argtypes = [C.POINTER(MuavConfig), P, C.POINTER(MuavAllocOpts), C.POINTER(MuavStepOut), P,
                                     C.c_int, P]
         d.muav_step_host.restype = C.c_int
-        d.muav_step_host.argtypes = [C.POINTER(MuavConfig), P, P, P, C.POINTER(MuavAllocOpts), P, P, P,
-                                     C.c_int, C.c_int, P]
+        d.muav_step_host.argtypes = [C.POINTER(MuavConfig), P, P, P, C.POINTER(MuavAllocOpts), C.POINTER(MuavTokenOut),
+                                     P, P, P, C.c_int, C.c_int, P]
         d.muav_lsap.restype = C.c_int
         d.muav_lsap.argtypes = [P, P, P, C.c_int, C.c_int, P, C.c_int, P]
         d.muav_avoid_obstacles.restype = C.c_int

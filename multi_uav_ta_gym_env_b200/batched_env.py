@@ -112,6 +112,47 @@ class BatchedMultiUAVEnv:
         """Rewind every environment to its reset state (device-to-device copy, no host work)."""
         self.records.copy_(self._records0)
 
+    # ------------------------------------------------------------------ fused token emission
+    def enable_fused_tokens(self, max_tasks=32, max_agents=16, interval=15, event_mask=HYBRID_EVENTS):
+        """Ask the step kernel to emit pair tokens for the environments that will replan before the next
+        step (muav_token_out).  Returns the token dict (tensors are updated in place by every step) with
+        `need` u8[E]."""
+        E, dev = self.n_envs, self.device
+        tok = {
+            "task_feats": torch.zeros(E, max_tasks, 13, dtype=torch.float32, device=dev),
+            "task_mask_u8": torch.ones(E, max_tasks, dtype=torch.uint8, device=dev),
+            "agent_feats": torch.zeros(E, max_agents, 12, dtype=torch.float32, device=dev),
+            "agent_mask_u8": torch.ones(E, max_agents, dtype=torch.uint8, device=dev),
+            "edge_valid": torch.zeros(E, max_agents, max_tasks, dtype=torch.float32, device=dev),
+            "task_ids": torch.zeros(E, max_tasks, dtype=torch.int32, device=dev),
+            "need": torch.zeros(E, dtype=torch.uint8, device=dev),
+        }
+        T = _lib.MuavTokenOut()
+        T.d_task_feats = tok["task_feats"].data_ptr()
+        T.d_task_mask = tok["task_mask_u8"].data_ptr()
+        T.d_agent_feats = tok["agent_feats"].data_ptr()
+        T.d_agent_mask = tok["agent_mask_u8"].data_ptr()
+        T.d_edge_valid = tok["edge_valid"].data_ptr()
+        T.d_task_ids = tok["task_ids"].data_ptr()
+        T.d_need = tok["need"].data_ptr()
+        T.max_tasks, T.max_agents, T.interval, T.event_mask = max_tasks, max_agents, interval, event_mask
+        self._tok = T
+        self.fused_tokens = tok
+        return tok
+
+    def refresh_fused_tokens(self):
+        """Fill the fused token tensors for ALL environments with the standalone kernel (after reset/restore)."""
+        tok, T = self.fused_tokens, self._tok
+        rc = self.lib.dll.muav_tokens_pair(C.byref(self.cfg), self.records.data_ptr(), T.max_tasks, T.max_agents,
+                                           T.d_task_feats, T.d_task_mask, T.d_agent_feats, T.d_agent_mask,
+                                           T.d_edge_valid, T.d_task_ids, self.n_envs, self._stream())
+        _lib.check(rc, "muav_tokens_pair")
+        tok["need"].fill_(1)
+        self.launches += 1
+
+    def _tok_ref(self):
+        return C.byref(self._tok) if getattr(self, "_tok", None) is not None else None
+
     # ------------------------------------------------------------------ step
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -130,7 +171,8 @@ class BatchedMultiUAVEnv:
             actions = torch.stack([a_sorted, i_sorted], dim=2)
         actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
         rc = self.lib.dll.muav_step(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(),
-                                    actions.data_ptr(), None, C.byref(self._out), self.n_envs, n_steps, self._stream())
+                                    actions.data_ptr(), None, C.byref(self._out), self._tok_ref(), self.n_envs, n_steps,
+                                    self._stream())
         _lib.check(rc, "muav_step")
         self.launches += 1
         return self.reward, self.terminated, self.truncated
@@ -164,7 +206,8 @@ class BatchedMultiUAVEnv:
         """n_steps fused (allocate -> step) iterations per environment, state resident in shared memory."""
         O, keep = self._alloc_opts(spec, edge_scores, priorities, reserved)
         rc = self.lib.dll.muav_step(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(), None,
-                                    C.byref(O), C.byref(self._out), self.n_envs, n_steps, self._stream())
+                                    C.byref(O), C.byref(self._out), self._tok_ref(), self.n_envs, n_steps,
+                                    self._stream())
         _lib.check(rc, "muav_step")
         self.launches += 1
         return self.reward, self.terminated, self.truncated

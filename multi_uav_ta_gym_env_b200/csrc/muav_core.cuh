@@ -233,7 +233,7 @@ struct Sim {
     V.a_commit()[a] = 0;
   }
   // UAV.outOfService (DroneEnvComponents.py:122-127)
-  MUAV_HD void out_of_service(int a) {
+  MUAV_HD MUAV_NOINLINE void out_of_service(int a) {
     V.a_state()[a] = -1;
     V.a_commit()[a] = 0;
     int i = 0;
@@ -243,7 +243,7 @@ struct Sim {
     }
   }
   // EnvUtils.desallocateAll (MultiDroneEnvUtils.py:183-205), single-task mode
-  MUAV_HD void env_desallocate_all(int a) {
+  MUAV_HD MUAV_NOINLINE void env_desallocate_all(int a) {
     while (qlen(a) > 0) {
       int tid = qat(a, 0);
       des_allocate(a, tid);
@@ -308,7 +308,7 @@ struct Sim {
     }
   }
   // Task ctor + env.tasks.append (DroneEnvComponents.py:224-263); returns task id or 0 on overflow
-  MUAV_HD int new_task(double px, double py, int ti) {
+  MUAV_HD MUAV_NOINLINE int new_task(double px, double py, int ti) {
     int k = HIv(N_TASKS);
     int TC = V.L->D.TC;
     if (k >= TC) {
@@ -376,7 +376,7 @@ struct Sim {
   }
 
   // releaseAllTasks (DroneEnv.py:1442-1480); for_type == -1 indexes the Det column
-  MUAV_HD void release_all(int for_type) {
+  MUAV_HD MUAV_NOINLINE void release_all(int for_type) {
     int col = for_type < 0 ? 6 + for_type : for_type;
     uint32_t avail = 0;
     for (int a = 0; a < A(); ++a) {
@@ -489,7 +489,7 @@ struct Sim {
   }
 
   // _escort_fighters_near (DroneEnv.py:1746-1764): ids sorted by distance (stable) into out[], returns count
-  MUAV_HD int fighters_near(int prot, double radius, int16_t* out, double* dtmp) const {
+  MUAV_HD MUAV_NOINLINE int fighters_near(int prot, double radius, int16_t* out, double* dtmp) const {
     if (prot < 0) return 0;
     int esc = V.a_escort()[prot];
     if (esc == 0 || V.k_status()[esc - 1] == 2) return 0;
@@ -529,7 +529,7 @@ struct Sim {
     V.h_target()[hid] = near_i()[0];
   }
   // _release_escort_agents (DroneEnv.py:1919-1936)
-  MUAV_HD void release_escort_agents(int esc) {
+  MUAV_HD MUAV_NOINLINE void release_escort_agents(int esc) {
     for (int a = 0; a < A(); ++a) {
       if (V.a_state()[a] == -1) continue;
       if (qfind(a, esc) >= 0) {
@@ -545,7 +545,7 @@ struct Sim {
     }
   }
   // _retire_escort (DroneEnv.py:1938-1950)
-  MUAV_HD void retire_escort(int esc, bool failed) {
+  MUAV_HD MUAV_NOINLINE void retire_escort(int esc, bool failed) {
     if (esc == 0 || V.k_status()[esc - 1] == 2) return;
     release_escort_agents(esc);
     V.k_status()[esc - 1] = 2;
@@ -556,7 +556,7 @@ struct Sim {
     push_event(EV_ESC_RETIRED, esc);
   }
   // _create_escort_for (DroneEnv.py:1888-1917)
-  MUAV_HD void create_escort_for(int a, int rec_tid) {
+  MUAV_HD MUAV_NOINLINE void create_escort_for(int a, int rec_tid) {
     if (!C().escort_enabled) return;
     if (V.a_escort()[a] != 0) return;
     int tid = new_task(V.a_posx()[a], V.a_posy()[a], TT_DEF);
@@ -580,7 +580,7 @@ struct Sim {
   }
 
   // handle_threat_engagement (DroneEnv.py:1781-1858)
-  MUAV_HD void engage(int hid) {
+  MUAV_HD MUAV_NOINLINE void engage(int hid) {
     int nd = 0;
     int primary = V.h_target()[hid];
     int mission = V.h_mission()[hid] >= 0 ? V.h_mission()[hid] : primary;
@@ -745,7 +745,7 @@ struct Sim {
   }
 
   // _sync_escorts (DroneEnv.py:1964-2000)
-  MUAV_HD void sync_escorts() {
+  MUAV_HD MUAV_NOINLINE void sync_escorts() {
     for (int a = 0; a < A(); ++a) {
       if (V.a_state()[a] == -1 || !is_recon(V.a_type()[a])) continue;
       if (qlen(a) == 0) continue;
@@ -821,20 +821,13 @@ struct Sim {
     for (int k = 0; k < n; ++k) {
       int dl = V.k_deadline()[k];
       if (dl < 0 || V.k_status()[k] == 2) continue;
-      if (t > dl) {
-        V.k_status()[k] = 2;
-        V.k_fq()[k] = 0;
-        mark_outcome(k, false);
-        mark_reached(k);
-        for (int a = 0; a < A(); ++a)
-          if (qlen(a) > 0 && qat(a, 0) == k + 1) des_allocate_all(a);
-      }
+      if (t > dl) expire_one(k);
     }
   }
 
   // core_sim::SimCore::avoid_obstacles (core_sim/src/sim_core.rs:24-59)
-  MUAV_HD static void avoid_obstacles(const double* obst, int nobs, double px, double py, double mx, double my,
-                                      double* ax, double* ay) {
+  MUAV_HD MUAV_NOINLINE static void avoid_obstacles(const double* obst, int nobs, double px, double py, double mx, double my,
+                                                    double* ax, double* ay) {
     const double PI = 3.14159265358979323846;
     double sx = 0.0, sy = 0.0;
     for (int o = 0; o < nobs; ++o) {
@@ -1046,7 +1039,7 @@ struct Sim {
               V.a_task_start()[a] = t;
             } else {
               mvx = nx; mvy = ny;
-              avoid_obstacles(V.obst(), nobs, px, py, mvx, mvy, &avx, &avy);
+              if (nobs > 0) avoid_obstacles(V.obst(), nobs, px, py, mvx, mvy, &avx, &avy);
             }
           } else if (d < speed) {
             V.a_state()[a] = 2;
@@ -1055,7 +1048,7 @@ struct Sim {
             V.a_posy()[a] = py = ty;
           } else {
             mvx = nx; mvy = ny;
-            avoid_obstacles(V.obst(), nobs, px, py, mvx, mvy, &avx, &avy);
+            if (nobs > 0) avoid_obstacles(V.obst(), nobs, px, py, mvx, mvy, &avx, &avy);
           }
         } else if (V.a_state()[a] == 2) {
           if (ti == TT_INT) {
@@ -1105,7 +1098,7 @@ struct Sim {
           double mag = norm2(dx, dy);
           if (mag == 0) { mvx = 0.0; mvy = 0.0; }
           else { mvx = dx / mag; mvy = dy / mag; }
-          avoid_obstacles(V.obst(), nobs, px, py, mvx, mvy, &avx, &avy);
+          if (nobs > 0) avoid_obstacles(V.obst(), nobs, px, py, mvx, mvy, &avx, &avy);
         }
       }
       double sx = mvx + avx, sy = mvy + avy;
@@ -1132,7 +1125,7 @@ struct Sim {
       double nt = (double)C().n_tasks_cfg;
       acc.time_pen = -(double)(C().n_tasks_cfg - HIv(N_REACHED)) / nt * ((double)t / (double)C().max_time_steps);
       acc.alloc_reward = 0.0;
-      if (t > C().n_tasks_cfg + 1) {
+      if (t > C().n_tasks_cfg + 1 && C().rw[5] != 0.0) {  // weight 0 (WPS flags): the count cannot reach the reward
         int unalloc = 1;  // bucket 0 (idle) is always empty
         int n = HIv(N_TASKS);
         for (int k = 0; k < n; ++k)
@@ -1147,11 +1140,78 @@ struct Sim {
     if (C().escort_enabled) sync_escorts();
   }
 
+  // ------------------------------------------------------------------ warp-parallel task scans
+#if defined(__CUDA_ARCH__)
+  // _wps_process_reveals over 32 tasks per iteration (lane <-> task, one known-word per iteration)
+  __device__ void process_reveals_warp(int lane) {
+    const int n = HIv(N_TASKS), t = HIv(T), Aa = A();
+    const int words = (n + 31) >> 5;
+    for (int w = 0; w < words; ++w) {
+      const int k = (w << 5) + lane;
+      const bool rev = k < n && V.k_reveal()[k] >= 0 && t >= V.k_reveal()[k];
+      const unsigned m = __ballot_sync(0xffffffffu, rev);
+      if (rev) V.k_reveal()[k] = -1;
+      if (m != 0u && C().share_knowledge)
+        for (int a = lane; a < Aa; a += 32) V.known()[w * Aa + a] |= m;
+    }
+    __syncwarp();
+  }
+  // _wps_expire_windows: detection in parallel, the (rare) expiries are applied by lane 0 in task order
+  __device__ void expire_windows_warp(int lane) {
+    if (!C().hard_windows) return;
+    const int n = HIv(N_TASKS), t = HIv(T);
+    const int words = (n + 31) >> 5;
+    for (int w = 0; w < words; ++w) {
+      const int k = (w << 5) + lane;
+      const bool ex = k < n && V.k_deadline()[k] >= 0 && V.k_status()[k] != 2 && t > V.k_deadline()[k];
+      unsigned m = __ballot_sync(0xffffffffu, ex);
+      if (m != 0u) {
+        if (lane == 0) {
+          while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            expire_one((w << 5) + b);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  // last_tasks_info mask + _counts_for_mission_done over all tasks; results are warp-uniform
+  __device__ void scan_open_warp(int lane, int* n_open_out, bool* all_done_out) {
+    const int n = HIv(N_TASKS);
+    const int KW = V.L->D.KW;
+    int n_open = 0;
+    bool blocking = false;
+    for (int w = 0; w < KW; ++w) {
+      const int k = (w << 5) + lane;
+      const bool open = k < n && V.k_status()[k] != 2;
+      const int ti = k < n ? V.k_type()[k] : 0;
+      const bool blk = open && !(V.k_kind()[k] == 1 || ti == TT_DET || ti == TT_HOLD);
+      const unsigned mo = __ballot_sync(0xffffffffu, open);
+      const unsigned mb = __ballot_sync(0xffffffffu, blk);
+      if (lane == 0) V.open_mask()[w] = mo;
+      n_open += __popc(mo);
+      blocking = blocking || mb != 0u;
+    }
+    *n_open_out = n_open;
+    *all_done_out = !blocking;
+  }
+#endif
+
+  MUAV_HD void expire_one(int k) {
+    V.k_status()[k] = 2;
+    V.k_fq()[k] = 0;
+    mark_outcome(k, false);
+    mark_reached(k);
+    for (int a = 0; a < A(); ++a)
+      if (qlen(a) > 0 && qat(a, 0) == k + 1) des_allocate_all(a);
+  }
+
   // ------------------------------------------------------------------ step: part 3 (lane 0)
-  MUAV_HD StepResult step_post(const Acc& acc) {
+  // reserve tracking, reward, termination; `alld` / `n_open` come from the task scan
+  MUAV_HD StepResult step_post(const Acc& acc, bool alld_scan, int n_open) {
     int Aa = A();
-    process_reveals();
-    expire_windows();
     // _wps_track_reserve (DroneEnv.py:1575-1580) and the _pending_reset clear (:1156-1160)
     int idle = 0;
     bool any_busy = false;
@@ -1171,23 +1231,14 @@ struct Sim {
                     HFv(NORM_FACTOR) / (double)C().max_time_steps;
     int t = HIv(T);
     int n = HIv(N_TASKS);
-    bool alld = n > 0 && all_done();
+    bool alld = n > 0 && alld_scan;
     bool timed_out = (t >= C().max_time_steps) && (C().max_time_steps > 0);
     bool done = timed_out || (C().early_terminate && alld);
     if (alld && HIv(CONCLUSION) > C().max_time_steps) HIv(CONCLUSION) = t;
     StepResult r;
     r.terminated = (C().early_terminate && alld && !timed_out) ? 1 : 0;
     r.truncated = timed_out ? 1 : 0;
-    // last_tasks_info (DroneEnv.py:492)
-    int KW = V.L->D.KW;
-    int n_open = 0;
-    for (int w = 0; w < KW; ++w) V.open_mask()[w] = 0;
-    for (int k = 0; k < n; ++k)
-      if (V.k_status()[k] != 2) {
-        V.open_mask()[k >> 5] |= 1u << (k & 31);
-        ++n_open;
-      }
-    HIv(N_OPEN) = n_open;
+    HIv(N_OPEN) = n_open;  // last_tasks_info (DroneEnv.py:492); the mask was written by the scan
     if (done) {
       reward = HFv(F_REWARD);
       HIv(DONE) = 1;
@@ -1197,17 +1248,39 @@ struct Sim {
     return r;
   }
 
-  // whole step; lane/nlanes partition the data-parallel middle section
+  // whole step.  Sequential phases run on lane 0, the task/agent scans are spread over the warp.
   MUAV_HD StepResult step(const int16_t* act_agent, const int16_t* act_tid, int n_act, int lane, int nlanes) {
     Acc acc;  // meaningful on lane 0 only
     if (lane == 0) step_pre(act_agent, act_tid, n_act, acc);
     MUAV_WARP_SYNC();
     update_sensing(lane, nlanes);
     MUAV_WARP_SYNC();
+    int n_open = 0;
+    bool alld = true;
+#if defined(__CUDA_ARCH__)
+    process_reveals_warp(lane);
+    expire_windows_warp(lane);
+    __syncwarp();
+    scan_open_warp(lane, &n_open, &alld);
+#else
+    process_reveals();
+    expire_windows();
+    {
+      const int n = HIv(N_TASKS);
+      const int KW = V.L->D.KW;
+      for (int w = 0; w < KW; ++w) V.open_mask()[w] = 0;
+      for (int k = 0; k < n; ++k)
+        if (V.k_status()[k] != 2) {
+          V.open_mask()[k >> 5] |= 1u << (k & 31);
+          ++n_open;
+        }
+      alld = all_done();
+    }
+#endif
     StepResult r;
     r.reward = 0.0;
     r.terminated = r.truncated = 0;
-    if (lane == 0) r = step_post(acc);
+    if (lane == 0) r = step_post(acc, alld, n_open);
     return r;
   }
 };

@@ -58,6 +58,7 @@ struct StepParams {
   Layout L;
   muav_alloc_opts opts;
   muav_step_out out;
+  muav_token_out tok;
   char* records;
   const uint32_t* tapes;
   const int32_t* actions;
@@ -112,8 +113,8 @@ __global__ void __launch_bounds__(32) muav_step_kernel(const __grid_constant__ S
   const int A = L.D.A;
 
   if (P.alloc_only) {
+    const int np = HIv(DONE) ? 0 : allocate_tasks(S, P.opts, e, act_agent, act_tid, lane, 32);
     if (lane == 0) {
-      int np = HIv(DONE) ? 0 : allocate_tasks(S, P.opts, e, act_agent, act_tid);
       if (P.out.d_n_pairs) P.out.d_n_pairs[e] = np;
       int n_act = 0;
       for (int i = 0; i < np; ++i) {
@@ -135,10 +136,11 @@ __global__ void __launch_bounds__(32) muav_step_kernel(const __grid_constant__ S
 
   for (int s = 0; s < P.n_steps; ++s) {
     if (HIv(DONE)) break;
+    int np = 0;
+    if (P.opts.mode != 0) np = allocate_tasks(S, P.opts, e, act_agent, act_tid, lane, 32);
     if (lane == 0) {
       int n_act = 0;
       if (P.opts.mode != 0) {
-        int np = allocate_tasks(S, P.opts, e, act_agent, act_tid);
         if (P.out.d_n_pairs) P.out.d_n_pairs[e] = np;
         if (P.out.d_pairs)
           for (int i = 0; i < np; ++i) P.out.d_pairs[(size_t)e * A + i] = ((int)act_agent[i] << 16) | (int)act_tid[i];
@@ -172,6 +174,19 @@ __global__ void __launch_bounds__(32) muav_step_kernel(const __grid_constant__ S
       if (P.out.d_n_open) P.out.d_n_open[e] = HIv(N_OPEN);
     }
     __syncwarp();
+    if (P.tok.d_need) {
+      const int iv = P.tok.interval > 0 ? P.tok.interval : 1;
+      const bool need = !HIv(DONE) && ((HIv(T) % iv) == 0 || (HIv(EV_TAGMASK) & P.tok.event_mask) != 0);
+      if (lane == 0) P.tok.d_need[e] = need ? 1 : 0;
+      if (need && P.tok.d_task_feats) {
+        const int mt = P.tok.max_tasks, ma = P.tok.max_agents;
+        tokens_pair_env(V, P.cfg, mt, ma, P.tok.d_task_feats + (size_t)e * mt * 13, P.tok.d_task_mask + (size_t)e * mt,
+                        P.tok.d_agent_feats + (size_t)e * ma * 12, P.tok.d_agent_mask + (size_t)e * ma,
+                        P.tok.d_edge_valid + (size_t)e * ma * mt, P.tok.d_task_ids + (size_t)e * mt, (int16_t*)scratch,
+                        lane, 32);
+      }
+      __syncwarp();
+    }
   }
 
   // ---- write the record back
@@ -205,10 +220,9 @@ __global__ void __launch_bounds__(32) muav_lsap_kernel(const double* cost, const
     W.cost[idx] = src[i * nc_max + j];
   }
   __syncwarp();
-  if (lane == 0) {
-    bool ok = (nr > 0 && nc > 0) ? lsap_solve(W.cost, nr, nc, W, W.col_of_row) : true;
-    for (int i = 0; i < nr_max; ++i) col4row[(size_t)b * nr_max + i] = (ok && i < nr && nr > 0 && nc > 0) ? W.col_of_row[i] : -1;
-  }
+  const bool ok = (nr > 0 && nc > 0) ? lsap_solve(W.cost, nr, nc, W, W.col_of_row, lane, 32) : true;
+  for (int i = lane; i < nr_max; i += 32)
+    col4row[(size_t)b * nr_max + i] = (ok && i < nr && nr > 0 && nc > 0) ? W.col_of_row[i] : -1;
 }
 
 __global__ void muav_avoid_kernel(const double* pos, const double* mv, const double* obst, int nobs, double* out, int n) {
@@ -285,17 +299,20 @@ __global__ void muav_metrics_kernel(const __grid_constant__ muav_config cfg, con
   o[29] = HIv(ESC_FAILED);
 }
 
-__global__ void muav_tokens_pair_kernel(const __grid_constant__ muav_config cfg, const __grid_constant__ Layout L,
-                                        const char* records, int max_tasks, int max_agents, float* tf, uint8_t* tm,
-                                        float* af, uint8_t* am, float* ev, int32_t* ids, int n) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) muav_tokens_pair_kernel(const __grid_constant__ muav_config cfg,
+                                                               const __grid_constant__ Layout L, const char* records,
+                                                               int max_tasks, int max_agents, float* tf, uint8_t* tm,
+                                                               float* af, uint8_t* am, float* ev, int32_t* ids, int n) {
+  __shared__ int16_t cols[4][MUAV_MAX_TASK_CAP + 2];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * 4 + w;
   if (e >= n) return;
   View V;
   V.base = (char*)records + (size_t)e * L.record_bytes;
   V.L = &L;
   tokens_pair_env(V, cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * 13, tm + (size_t)e * max_tasks,
                   af + (size_t)e * max_agents * 12, am + (size_t)e * max_agents,
-                  ev + (size_t)e * max_agents * max_tasks, ids + (size_t)e * max_tasks);
+                  ev + (size_t)e * max_agents * max_tasks, ids + (size_t)e * max_tasks, cols[w], lane, 32);
 }
 
 __global__ void muav_observe_kernel(const __grid_constant__ muav_config cfg, const __grid_constant__ Layout L,
@@ -336,7 +353,8 @@ static int launch_step(const StepParams& P, void* stream) {
 }
 
 int muav_step(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* d_actions,
-              const muav_alloc_opts* opts, const muav_step_out* out, int n_envs, int n_steps, void* stream) {
+              const muav_alloc_opts* opts, const muav_step_out* out, const muav_token_out* tok, int n_envs, int n_steps,
+              void* stream) {
   int rc = check_cfg(cfg);
   if (rc) return rc;
   if (!d_records || n_envs < 0 || n_steps < 0) return -22;
@@ -347,6 +365,10 @@ int muav_step(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, 
   P.L = make_layout(*cfg);
   if (opts) P.opts = *opts;
   if (out) P.out = *out;
+  if (tok) {
+    if (tok->max_tasks < 1 || tok->max_agents < 1 || tok->max_tasks > cfg->task_cap) return -22;
+    P.tok = *tok;
+  }
   P.records = (char*)d_records;
   P.tapes = d_tapes;
   P.actions = d_actions;
@@ -381,8 +403,8 @@ int muav_allocate(const muav_config* cfg, void* d_records, const muav_alloc_opts
 }
 
 int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* h_actions,
-                   const muav_alloc_opts* opts, double* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
-                   int n_envs, int n_steps, void* stream) {
+                   const muav_alloc_opts* opts, const muav_token_out* tok, double* h_reward, uint8_t* h_terminated,
+                   uint8_t* h_truncated, int n_envs, int n_steps, void* stream) {
   int rc = check_cfg(cfg);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
@@ -409,7 +431,8 @@ int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_ta
   out.d_reward = (double*)(b + off_rew);
   out.d_terminated = (uint8_t*)(b + off_term);
   out.d_truncated = (uint8_t*)(b + off_trunc);
-  rc = muav_step(cfg, d_records, d_tapes, h_actions ? (const int32_t*)b : nullptr, opts, &out, n_envs, n_steps, stream);
+  rc = muav_step(cfg, d_records, d_tapes, h_actions ? (const int32_t*)b : nullptr, opts, &out, tok, n_envs, n_steps,
+                 stream);
   if (rc) return rc;
   if (h_reward) cudaMemcpyAsync(h_reward, out.d_reward, (size_t)n_envs * 8, cudaMemcpyDeviceToHost, s);
   if (h_terminated) cudaMemcpyAsync(h_terminated, out.d_terminated, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
@@ -458,7 +481,8 @@ int muav_tokens_pair(const muav_config* cfg, const void* d_records, int max_task
   if (n_envs <= 0) return n_envs == 0 ? 0 : -22;
   if (max_tasks < 1 || max_agents < 1) return -22;
   Layout L = make_layout(*cfg);
-  muav_tokens_pair_kernel<<<(n_envs + 63) / 64, 64, 0, (cudaStream_t)stream>>>(
+  if (max_tasks > MUAV_MAX_TASK_CAP) return -22;
+  muav_tokens_pair_kernel<<<(n_envs + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
       *cfg, L, (const char*)d_records, max_tasks, max_agents, d_task_feats, d_task_mask, d_agent_feats, d_agent_mask,
       d_edge_valid, d_task_ids, n_envs);
   return cuda_rc(cudaGetLastError());

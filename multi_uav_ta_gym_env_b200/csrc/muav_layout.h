@@ -9,8 +9,10 @@
 
 #if defined(__CUDACC__)
 #define MUAV_HD __host__ __device__
+#define MUAV_NOINLINE __noinline__
 #else
 #define MUAV_HD
+#define MUAV_NOINLINE __attribute__((noinline))
 #endif
 
 namespace muav {
@@ -148,8 +150,8 @@ MUAV_HD inline int32_t align_up(int32_t x, int32_t a) { return (x + a - 1) / a *
 // bytes of allocator scratch: cost[A*TC], u/v/spc[M], resid[TC] doubles + 6 M-sized and 2A+3TC int16 arrays
 MUAV_HD inline int32_t alloc_scratch_bytes(int A, int TC) {
   int M = A > TC ? A : TC;
-  int b = 8 * (A * TC + 3 * M + TC);
-  b += 2 * (6 * M + 2 * A + 3 * TC);
+  int b = 8 * (A * TC + 3 * M + TC + 4);
+  b += 2 * (6 * M + 3 * A + 3 * TC);
   return (b + 15) / 16 * 16;
 }
 

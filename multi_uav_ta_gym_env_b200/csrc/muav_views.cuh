@@ -24,9 +24,12 @@ MUAV_HD inline bool view_known(const View& V, int a, int k) {
 }
 
 // task_feats [max_tasks,13] f32, task_mask [max_tasks] u8 (1 = padding), agent_feats [max_agents,12] f32,
-// agent_mask [max_agents] u8, edge_valid [max_agents,max_tasks] f32, task_ids [max_tasks] i32
+// agent_mask [max_agents] u8, edge_valid [max_agents,max_tasks] f32, task_ids [max_tasks] i32.
+// Work is spread over (lane, nlanes): lane 0 builds the ordered token-task list in `cols`
+// (int16 scratch, >= max_tasks entries + 2), then columns and agent rows are independent.
 MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max_tasks, int max_agents, float* tf,
-                                    uint8_t* tm, float* af, uint8_t* am, float* ev, int32_t* ids) {
+                                    uint8_t* tm, float* af, uint8_t* am, float* ev, int32_t* ids, int16_t* cols,
+                                    int lane, int nlanes) {
   const int A = V.L->D.A, TC = V.L->D.TC;
   const int n = V.hi()[HI_N_TASKS];
   const int t = V.hi()[HI_T];
@@ -35,29 +38,36 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
   const double mid_x = C.area_w * 0.5;
   const bool vis_none = !(C.sense_radius != 0.0) && !(C.threat_delay != 0);
   const double urgent_thr = 1.0 - 12.0 / 40.0;
+  if (lane == 0) {
+    int n_open_all = 0, col = 0;
+    for (int k = 0; k < n; ++k) {
+      if (V.k_status()[k] == 2) continue;
+      int ti = V.k_type()[k];
+      if (!(V.k_alloc()[ti * TC + k] < V.k_cur()[ti * TC + k])) continue;  // AttentionRAH.py:67-71
+      ++n_open_all;
+      if (col < max_tasks) cols[col++] = (int16_t)k;
+    }
+    cols[max_tasks] = (int16_t)col;
+    cols[max_tasks + 1] = (int16_t)n_open_all;
+  }
+  MUAV_WARP_SYNC();
+  const int ncol = cols[max_tasks];
+  const int n_open_all = cols[max_tasks + 1];
   int n_live = 0;
   for (int a = 0; a < A; ++a) n_live += V.a_state()[a] != -1;
   const int n_agents = n_live > 1 ? n_live : 1;
-  for (int i = 0; i < max_tasks; ++i) {
-    tm[i] = 1;
-    ids[i] = 0;
-    for (int c = 0; c < 13; ++c) tf[i * 13 + c] = 0.0f;
-  }
-  for (int i = 0; i < max_agents; ++i) {
-    am[i] = 1;
-    for (int c = 0; c < 12; ++c) af[i * 12 + c] = 0.0f;
-    for (int j = 0; j < max_tasks; ++j) ev[i * max_tasks + j] = 0.0f;
-  }
-  // tasks
-  int n_open_all = 0;
-  int col = 0;
-  for (int k = 0; k < n; ++k) {
-    if (V.k_status()[k] == 2) continue;
-    int ti = V.k_type()[k];
-    double cur = V.k_cur()[ti * TC + k], al = V.k_alloc()[ti * TC + k];
-    if (!(al < cur)) continue;
-    ++n_open_all;
-    if (col >= max_tasks) continue;
+  // ---- task columns
+  for (int j = lane; j < max_tasks; j += nlanes) {
+    float* f = tf + j * 13;
+    if (j >= ncol) {
+      tm[j] = 1;
+      ids[j] = 0;
+      for (int c = 0; c < 13; ++c) f[c] = 0.0f;
+      continue;
+    }
+    const int k = cols[j];
+    const int ti = V.k_type()[k];
+    const double cur = V.k_cur()[ti * TC + k], al = V.k_alloc()[ti * TC + k];
     double urg = urgency_of(V, k, t);
     int n_know_i = 0;
     for (int a = 0; a < A; ++a) n_know_i += view_known(V, a, k) ? 1 : 0;
@@ -74,7 +84,6 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
       if (!any_spec || d < d_spec) d_spec = d;
       any_spec = true;
     }
-    float* f = tf + col * 13;
     f[0] = (float)(V.k_posx()[k] / mc);
     f[1] = (float)(V.k_posy()[k] / mc);
     f[2] = (float)((double)ti / 8.0);
@@ -88,25 +97,36 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
     f[10] = (float)dmin(n_know / (double)n_agents, 1.0);
     f[11] = (float)dmin(d_spec / mc, 1.0);
     f[12] = V.k_posx()[k] < mid_x ? 0.0f : 1.0f;
-    tm[col] = 0;
-    ids[col] = k + 1;
-    ++col;
+    tm[j] = 0;
+    ids[j] = k + 1;
   }
-  // agents
-  int row = 0;
-  for (int a = 0; a < A && row < max_agents; ++a) {
-    if (V.a_state()[a] == -1) continue;
+  // ---- agent rows (row i = i-th live agent)
+  for (int i = lane; i < max_agents; i += nlanes) {
+    float* f = af + i * 12;
+    float* evr = ev + i * max_tasks;
+    int a = -1, seen = 0;
+    for (int b = 0; b < A; ++b) {
+      if (V.a_state()[b] == -1) continue;
+      if (seen == i) { a = b; break; }
+      ++seen;
+    }
+    if (a < 0) {
+      am[i] = 1;
+      for (int c = 0; c < 12; ++c) f[c] = 0.0f;
+      for (int j = 0; j < max_tasks; ++j) evr[j] = 0.0f;
+      continue;
+    }
     int at = V.a_type()[a];
     double cap_rec = V.a_caps()[1 * A + a], cap_att = V.a_caps()[2 * A + a], cap_def = V.a_caps()[3 * A + a];
     int n_known_urgent = 0;
     for (int k = 0; k < n; ++k) {
       if (V.k_status()[k] == 2) continue;
+      if (V.k_deadline()[k] < 0) continue;
       int ti = V.k_type()[k];
       if (!(V.k_alloc()[ti * TC + k] < V.k_cur()[ti * TC + k])) continue;
       if (!vis_none && !view_known(V, a, k)) continue;
-      if (V.k_deadline()[k] >= 0 && urgency_of(V, k, t) >= urgent_thr) ++n_known_urgent;
+      if (urgency_of(V, k, t) >= urgent_thr) ++n_known_urgent;
     }
-    float* f = af + row * 12;
     f[0] = (float)(V.a_posx()[a] / mc);
     f[1] = (float)(V.a_posy()[a] / mc);
     f[2] = is_fighter(at) ? 1.0f : 0.0f;
@@ -119,17 +139,19 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
     f[9] = (float)((double)t / (double)horizon);
     f[10] = (float)dmin((double)n_known_urgent / (double)(n_open_all > 1 ? n_open_all : 1), 1.0);
     f[11] = at == UT_F2 ? 1.0f : 0.0f;
-    am[row] = 0;
+    am[i] = 0;
     // edge_valid (PairCostHybrid.py:41-60)
-    for (int j = 0; j < col; ++j) {
-      int k = ids[j] - 1;
-      if (!vis_none && !view_known(V, a, k)) continue;
-      int el = V.k_elig()[k];
-      if (el != 0 && !((el >> at) & 1)) continue;
-      if (V.a_caps()[V.k_type()[k] * A + a] <= 0) continue;
-      ev[row * max_tasks + j] = 1.0f;
+    for (int j = 0; j < max_tasks; ++j) {
+      float v = 0.0f;
+      if (j < ncol) {
+        int k = cols[j];
+        int el = V.k_elig()[k];
+        bool ok = (vis_none || view_known(V, a, k)) && (el == 0 || ((el >> at) & 1)) &&
+                  V.a_caps()[V.k_type()[k] * A + a] > 0;
+        v = ok ? 1.0f : 0.0f;
+      }
+      evr[j] = v;
     }
-    ++row;
   }
 }
 

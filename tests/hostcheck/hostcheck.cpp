@@ -48,7 +48,7 @@ int hostcheck_step(const muav_config* cfg, void* records, const uint32_t* tapes,
       if (HIv(DONE)) break;
       int n_act = 0;
       if (O.mode != 0) {
-        int np = allocate_tasks(S, O, e, act_agent, act_tid);
+        int np = allocate_tasks(S, O, e, act_agent, act_tid, 0, 1);
         if (Z.d_n_pairs) Z.d_n_pairs[e] = np;
         if (Z.d_pairs)
           for (int i = 0; i < np; ++i) Z.d_pairs[(size_t)e * A + i] = ((int)act_agent[i] << 16) | (int)act_tid[i];
@@ -90,7 +90,7 @@ int hostcheck_lsap(const double* cost, const int32_t* nr_arr, const int32_t* nc_
     const double* src = cost + (size_t)b * nr_max * nc_max;
     for (int i = 0; i < nr; ++i)
       for (int j = 0; j < nc; ++j) W.cost[i * nc + j] = src[i * nc_max + j];
-    bool ok = (nr > 0 && nc > 0) ? lsap_solve(W.cost, nr, nc, W, W.col_of_row) : true;
+    bool ok = (nr > 0 && nc > 0) ? lsap_solve(W.cost, nr, nc, W, W.col_of_row, 0, 1) : true;
     for (int i = 0; i < nr_max; ++i) col4row[(size_t)b * nr_max + i] = (ok && i < nr && nc > 0) ? W.col_of_row[i] : -1;
   }
   free(scratch);

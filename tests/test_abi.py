@@ -44,8 +44,8 @@ def test_layout_is_consistent():
 def test_bad_arguments_are_rejected_without_gpu():
     lib = _lib.cuda_lib()
     cfg = _lib.build_config(config.wps_config("WPS_hard"))
-    assert lib.dll.muav_step(None, None, None, None, None, None, 1, 1, None) == -22
-    assert lib.dll.muav_step(C.byref(cfg), None, None, None, None, None, 1, 1, None) == -22
+    assert lib.dll.muav_step(None, None, None, None, None, None, None, 1, 1, None) == -22
+    assert lib.dll.muav_step(C.byref(cfg), None, None, None, None, None, None, 1, 1, None) == -22
     bad = _lib.build_config(config.wps_config("WPS_hard"))
     bad.n_agents = 1000
     assert lib.dll.muav_metrics(C.byref(bad), None, None, 1, None) == -22

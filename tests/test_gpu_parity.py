@@ -183,6 +183,42 @@ def test_tokens_and_observations_match_oracle():
                 o.step(apply_assign(o, pairs))
 
 
+def test_fused_token_emission_and_split_allocate():
+    """(a) tokens emitted by the step kernel for replanning envs == standalone token kernel;
+    (b) muav_allocate followed by muav_step(actions) == the fused allocate+step launch."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+
+    cfg = wps_config("WPS_hard")
+    seeds = list(range(200, 232))
+    fused = make_env(cfg, seeds)
+    split = make_env(cfg, seeds)
+    tok = fused.enable_fused_tokens(32, 16, 15, 0b111)
+    fused.refresh_fused_tokens()
+    spec = AllocSpec.pair_hybrid(15)
+    n_need = 0
+    for t in range(150):
+        scores = torch.from_numpy(np.stack([injected_scores(s, t, 16, 32) for s in seeds]))
+        fused.step_allocated(spec, 1, edge_scores=scores)
+        act = split.allocate(spec, edge_scores=scores)
+        split.step_batched(act)
+        assert torch.equal(fused.records, split.records), t
+        assert torch.equal(fused.reward, split.reward)
+        ref = split.tokens_pair(32, 16)
+        need = tok["need"].bool()
+        tagmask = split.header_int("EV_TAGMASK")
+        want_need = (((t + 1) % 15) == 0) | ((tagmask & 0b111) != 0)
+        if t + 1 == 150:
+            want_need = torch.zeros_like(want_need)
+        assert torch.equal(need, want_need), t
+        n_need += int(need.sum())
+        for k, k2 in (("task_feats", "task_feats"), ("agent_feats", "agent_feats"), ("edge_valid", "edge_valid"),
+                      ("task_ids", "task_ids")):
+            assert torch.equal(tok[k][need], ref[k2][need]), (t, k)
+        assert torch.equal(tok["task_mask_u8"][need].bool(), ref["task_mask"][need])
+        assert torch.equal(tok["agent_mask_u8"][need].bool(), ref["agent_mask"][need])
+    assert n_need > 300
+
+
 def test_step_host_entry_point_matches_device_path():
     """muav_step_host (host action/reward buffers, copies inside) == muav_step."""
     from multi_uav_ta_gym_env_b200 import _lib, wps_config
@@ -200,7 +236,7 @@ def test_step_host_entry_point_matches_device_path():
             for i, (a, idx) in enumerate(ep["steps"][t]["actions"]):
                 act[e, i] = (a, idx)
         rc = env.lib.dll.muav_step_host(C.byref(env.cfg), env.records.data_ptr(), env.tapes.data_ptr(), act.ctypes.data,
-                                        None, rew.ctypes.data, term.ctypes.data, trunc.ctypes.data, E, 1, None)
+                                        None, None, rew.ctypes.data, term.ctypes.data, trunc.ctypes.data, E, 1, None)
         assert rc == 0
         for e, ep in enumerate(eps):
             assert rew[e] == float.fromhex(ep["steps"][t]["reward"])
@@ -270,3 +306,32 @@ def test_avoid_obstacles_matches_oracle():
     # transcendental functions (ln, atan2) are not bit-reproducible across libm / CUDA: tolerance 1e-9 relative
     assert np.allclose(out.cpu().numpy(), want, rtol=1e-9, atol=1e-12)
     assert (np.abs(want).sum(axis=1) > 0).sum() > 50
+
+
+def test_graphed_scorer_matches_eager_forward():
+    """Split pair head + CUDA-graph replay vs the reference-shaped eager forward (fp32, tolerance 2e-5)."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+    from multi_uav_ta_gym_env_b200.scorers import AttPairNet, GraphedPairScorer, pair_scores
+
+    cfg = wps_config("WPS_hard")
+    E = 300
+    env = make_env(cfg, list(range(E)))
+    env.step_allocated(AllocSpec.local_hungarian(20), n_steps=60)
+    tok = env.enable_fused_tokens(32, 16, 15, 0b111)
+    env.refresh_fused_tokens()
+    torch.manual_seed(0)
+    net = AttPairNet().cuda().eval()
+    eager_tok = {"task_feats": tok["task_feats"], "task_mask": tok["task_mask_u8"].bool(),
+                 "agent_feats": tok["agent_feats"], "agent_mask": tok["agent_mask_u8"].bool(),
+                 "edge_valid": tok["edge_valid"]}
+    want = pair_scores(net, eager_tok)
+    scorer = GraphedPairScorer(net, E, torch.device("cuda"), buckets=(64, 128))
+    got = torch.zeros_like(want)
+    scorer.score_all(tok, got)
+    assert (got - want).abs().max().item() < 2e-5
+    assert want.abs().max().item() > 1e-3
+    idx = torch.arange(5, 105, device="cuda")
+    got2 = torch.zeros_like(want)
+    scorer.score_subset(tok, idx, got2)
+    assert (got2[idx] - want[idx]).abs().max().item() < 2e-5
+    assert got2[:5].abs().max().item() == 0.0
