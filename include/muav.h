@@ -69,18 +69,22 @@ typedef struct muav_alloc_opts {
                               1 HungarianAllocator.should_replan rule: t - last_plan_step >= interval or a listed event tag
                                 (HungarianAllocator.py:27-41,88), force=False;
                               2 hybrid rule (wps_eval.py:64-73, escort_eval.py:52-58): t == 0 or t % interval == 0 or a
-                                listed event tag, then allocate_tasks(force=True) */
+                                listed event tag, then allocate_tasks(force=True);
+                              3 allocate_tasks(force=True) unconditionally (the caller evaluated its own rule) */
   int32_t replan_interval; /* 20 Local-Hungarian, 12 Coalition-Hungarian, 15 hybrids */
   int32_t event_mask;      /* bit i = tag i triggers (0 Reset_Allocation 1 Agent_Fail 2 New_Threat 3 Escort_Created 4 Escort_Retired) */
   int32_t use_visibility;  /* agent_known_ids=env.agent_visibility_map() */
   int32_t pair_tokens;     /* 1: task list = build_pair_tokens' open list (PairCostHybrid.py:34-36, AttentionRAH.py:67-71)
                                  and d_edge_scores is indexed in token space [live agent row, token task column] */
   int32_t score_rows, score_cols; /* edge score tensor shape per env (max_agents, max_tasks) */
-  int32_t reserved0;
+  int32_t score_f64;       /* 1: d_edge_scores points to double, else float */
   double max_coord;        /* HungarianAllocator(max_coord=...) */
-  const float* d_edge_scores;  /* [E, score_rows, score_cols] or NULL */
+  const void* d_edge_scores;   /* [E, score_rows, score_cols] float (or double when score_f64) or NULL;
+                                  pair_tokens=0: indexed [agent id, task index] */
   const double* d_priorities;  /* [E, task_cap] by task index (task_priorities) or NULL */
   const uint8_t* d_reserved;   /* [E, n_agents] 1 = excluded (reserved_agent_names) or NULL */
+  const int32_t* d_task_order; /* [E, task_cap] the `tasks` argument: task indices (id-1) in the caller's order, -1 terminated;
+                                  NULL = every open task in id order (_open_tasks, paper_eval.py:96-101) */
 } muav_alloc_opts;
 
 /* Per-step outputs (any pointer may be NULL). */

@@ -50,9 +50,10 @@ class MuavAllocOpts(C.Structure):
     _fields_ = [
         ("mode", C.c_int32), ("replan_interval", C.c_int32), ("event_mask", C.c_int32),
         ("use_visibility", C.c_int32), ("pair_tokens", C.c_int32), ("score_rows", C.c_int32),
-        ("score_cols", C.c_int32), ("reserved0", C.c_int32),
+        ("score_cols", C.c_int32), ("score_f64", C.c_int32),
         ("max_coord", C.c_double),
         ("d_edge_scores", C.c_void_p), ("d_priorities", C.c_void_p), ("d_reserved", C.c_void_p),
+        ("d_task_order", C.c_void_p),
     ]
 
 

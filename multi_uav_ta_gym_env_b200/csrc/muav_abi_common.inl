@@ -59,3 +59,14 @@ static int check_cfg(const muav_config* c) {
   return 0;
 }
 
+
+// metric order of muav_metrics (calculate_metrics, DroneEnv.py:1286-1319)
+static const char* const kMetricNames[MUAV_N_METRICS] = {
+    "F_time", "F_distance", "F_quality", "F_Reward", "S_WPS", "S_ESC", "Losses", "Kills", "makespan", "total_distance",
+    "n_reallocations", "n_task_switches", "n_arrivals", "n_tasks_final", "n_reached", "n_missed_windows", "n_on_time",
+    "n_windowed_tasks", "on_time_rate", "reserve_idle_fraction", "escort_coverage_rate", "protected_rec_completed",
+    "recon_losses", "escort_losses", "threats_intercepted", "mutual_support_engagements", "protection_breaches",
+    "escort_requests", "escort_completed", "escort_failed"};
+
+
+const char* muav_metric_name(int idx) { return (idx >= 0 && idx < MUAV_N_METRICS) ? kMetricNames[idx] : nullptr; }

@@ -195,7 +195,9 @@ MUAV_HD inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, int e, int16
   AllocScratch W = carve_scratch(S.scratch, A, TC);
   const uint8_t* reserved = O.d_reserved ? O.d_reserved + (size_t)e * A : nullptr;
   const double* pri = O.d_priorities ? O.d_priorities + (size_t)e * TC : nullptr;
-  const float* scores = O.d_edge_scores ? O.d_edge_scores + (size_t)e * O.score_rows * O.score_cols : nullptr;
+  const size_t sc_off = (size_t)e * O.score_rows * O.score_cols;
+  const float* scores = (O.d_edge_scores && !O.score_f64) ? (const float*)O.d_edge_scores + sc_off : nullptr;
+  const double* scores64 = (O.d_edge_scores && O.score_f64) ? (const double*)O.d_edge_scores + sc_off : nullptr;
   enum { C_GO = 0, C_NFREE = 1, C_NOPEN = 2, C_NC = 3, C_NPAIRS = 4, C_STOP = 5 };
   if (lane == 0) {
     HIv(N_CALLS) += 1;
@@ -204,7 +206,7 @@ MUAV_HD inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, int e, int16
     bool go;
     if (O.mode == 1) go = (t - HIv(LAST_PLAN_STEP)) >= interval || ev_hit;
     else if (O.mode == 2) go = t == 0 || (t % interval) == 0 || ev_hit;
-    else go = false;
+    else go = O.mode == 3;
     int n_free = 0, n_open = 0;
     if (go) {
       const int n_tasks = HIv(N_TASKS);
@@ -220,7 +222,14 @@ MUAV_HD inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, int e, int16
       }
       // open task list (+ residuals, + pair-token column of each task)
       int tok_j = 0;
-      for (int k = 0; k < n_tasks; ++k) {
+      const int32_t* order = O.d_task_order ? O.d_task_order + (size_t)e * TC : nullptr;
+      for (int it = 0; it < (order ? TC : n_tasks); ++it) {
+        int k = it;
+        if (order) {
+          k = order[it];
+          if (k < 0) break;
+          if (k >= n_tasks) continue;
+        }
         if (V.k_status()[k] == 2) continue;
         int col = -1;
         if (O.pair_tokens) {
@@ -292,7 +301,9 @@ MUAV_HD inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, int e, int16
         }
         if (base < 1e5 / 2) {
           double sc = 0.0;
-          if (scores) {
+          if (scores64) {
+            if (a < O.score_rows && k < O.score_cols) sc = scores64[a * O.score_cols + k];
+          } else if (scores) {
             if (O.pair_tokens) {
               // edge_score_dict (PairCostHybrid.py:280-291): only valid edges carry a score
               const int col = W.tokcol[q];

@@ -234,14 +234,6 @@ __global__ void muav_avoid_kernel(const double* pos, const double* mv, const dou
   out[2 * i + 1] = ay;
 }
 
-// ------------------------------------------------------------------ metrics (DroneEnv.py:1231-1319)
-static const char* const kMetricNames[MUAV_N_METRICS] = {
-    "F_time", "F_distance", "F_quality", "F_Reward", "S_WPS", "S_ESC", "Losses", "Kills", "makespan", "total_distance",
-    "n_reallocations", "n_task_switches", "n_arrivals", "n_tasks_final", "n_reached", "n_missed_windows", "n_on_time",
-    "n_windowed_tasks", "on_time_rate", "reserve_idle_fraction", "escort_coverage_rate", "protected_rec_completed",
-    "recon_losses", "escort_losses", "threats_intercepted", "mutual_support_engagements", "protection_breaches",
-    "escort_requests", "escort_completed", "escort_failed"};
-
 __global__ void muav_metrics_kernel(const __grid_constant__ muav_config cfg, const __grid_constant__ Layout L,
                                     const char* records, double* out, int n) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -249,54 +241,7 @@ __global__ void muav_metrics_kernel(const __grid_constant__ muav_config cfg, con
   View V;
   V.base = (char*)records + (size_t)e * L.record_bytes;
   V.L = &L;
-  double* o = out + (size_t)e * MUAV_N_METRICS;
-  const int A = L.D.A;
-  const int T = HIv(N_TASKS);
-  double td = HFv(TOTAL_DIST);
-  // compute_s_wps (DroneEnv.py:1321-1337)
-  double dist_term = 0.01 * td / dmax(cfg.max_coord, 1.0);
-  double rematch = cfg.reassign_penalty * (double)HIv(N_SWITCH);
-  double s_wps = 12.0 * (double)HIv(N_ON_TIME) - 30.0 * (double)HIv(N_MISSED) - dist_term - rematch;
-  int req = HIv(ESC_REQ_STEPS);
-  double cov = (double)HIv(ESC_COV_STEPS) / (double)(req > 1 ? req : 1);
-  double s_esc = s_wps + 20.0 * (double)HIv(PROT_REC_DONE) - 30.0 * (double)HIv(RECON_LOSSES) + 20.0 * cov;
-  int losses = 0;
-  for (int a = 0; a < A; ++a) losses += V.a_state()[a] == -1;
-  int kills = 0;
-  for (int i = 0; i < HIv(N_ACTIVE); ++i) kills += V.h_status()[V.h_order()[i]] == 2;
-  double fq = 0.0;  // final_quality is -1 (counted as 0) or 0.0 (DroneEnv.py:1249,1566)
-  o[0] = 1.0 / (double)HIv(CONCLUSION) * (double)cfg.max_time_steps;
-  o[1] = td > 0 ? 1.0 / td * cfg.max_coord : 0.0;
-  o[2] = T > 0 ? fq / (double)T : nan("");
-  o[3] = HFv(F_REWARD);
-  o[4] = s_wps;
-  o[5] = s_esc;
-  o[6] = losses;
-  o[7] = kills;
-  o[8] = (double)HIv(CONCLUSION);
-  o[9] = td;
-  o[10] = HIv(N_REALLOC);
-  o[11] = HIv(N_SWITCH);
-  o[12] = HIv(N_ARRIVALS);
-  o[13] = T;
-  o[14] = HIv(N_REACHED);
-  o[15] = HIv(N_MISSED);
-  o[16] = HIv(N_ON_TIME);
-  o[17] = HIv(N_WINDOWED);
-  int den = HIv(N_ON_TIME) + HIv(N_MISSED);
-  o[18] = (double)HIv(N_ON_TIME) / (double)(den > 1 ? den : 1);
-  int den2 = HIv(T) * (A > 1 ? A : 1);
-  o[19] = (double)HIv(IDLE_RESERVE) / (double)(den2 > 1 ? den2 : 1);
-  o[20] = cov;
-  o[21] = HIv(PROT_REC_DONE);
-  o[22] = HIv(RECON_LOSSES);
-  o[23] = HIv(ESCORT_LOSSES);
-  o[24] = HIv(INTERCEPTED);
-  o[25] = HIv(MUTUAL);
-  o[26] = HIv(BREACHES);
-  o[27] = HIv(ESC_REQUESTS);
-  o[28] = HIv(ESC_COMPLETED);
-  o[29] = HIv(ESC_FAILED);
+  metrics_env(V, cfg, out + (size_t)e * MUAV_N_METRICS);
 }
 
 __global__ void __launch_bounds__(128) muav_tokens_pair_kernel(const __grid_constant__ muav_config cfg,
@@ -462,7 +407,6 @@ int muav_avoid_obstacles(const double* d_pos, const double* d_move, const double
   return cuda_rc(cudaGetLastError());
 }
 
-const char* muav_metric_name(int idx) { return (idx >= 0 && idx < MUAV_N_METRICS) ? kMetricNames[idx] : nullptr; }
 
 int muav_metrics(const muav_config* cfg, const void* d_records, double* d_out, int n_envs, void* stream) {
   int rc = check_cfg(cfg);

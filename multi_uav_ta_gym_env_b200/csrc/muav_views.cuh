@@ -251,4 +251,57 @@ MUAV_HD inline void observe_env(const View& V, const muav_config& C, int max_row
   ef[4] = (float)((double)n_open / (double)(C.max_tasks > 1 ? C.max_tasks : 1));
 }
 
+// calculate_metrics / compute_s_wps / compute_s_esc (mUAV_TA/DroneEnv.py:1231-1337,2002-2011);
+// o[0..29] in the order of muav_metric_name()
+MUAV_HD inline void metrics_env(const View& V, const muav_config& cfg, double* o) {
+  const Layout& L = *V.L;
+  const int A = L.D.A;
+  const int T = HIv(N_TASKS);
+  double td = HFv(TOTAL_DIST);
+  // compute_s_wps (DroneEnv.py:1321-1337)
+  double dist_term = 0.01 * td / dmax(cfg.max_coord, 1.0);
+  double rematch = cfg.reassign_penalty * (double)HIv(N_SWITCH);
+  double s_wps = 12.0 * (double)HIv(N_ON_TIME) - 30.0 * (double)HIv(N_MISSED) - dist_term - rematch;
+  int req = HIv(ESC_REQ_STEPS);
+  double cov = (double)HIv(ESC_COV_STEPS) / (double)(req > 1 ? req : 1);
+  double s_esc = s_wps + 20.0 * (double)HIv(PROT_REC_DONE) - 30.0 * (double)HIv(RECON_LOSSES) + 20.0 * cov;
+  int losses = 0;
+  for (int a = 0; a < A; ++a) losses += V.a_state()[a] == -1;
+  int kills = 0;
+  for (int i = 0; i < HIv(N_ACTIVE); ++i) kills += V.h_status()[V.h_order()[i]] == 2;
+  double fq = 0.0;  // final_quality is -1 (counted as 0) or 0.0 (DroneEnv.py:1249,1566)
+  o[0] = 1.0 / (double)HIv(CONCLUSION) * (double)cfg.max_time_steps;
+  o[1] = td > 0 ? 1.0 / td * cfg.max_coord : 0.0;
+  o[2] = T > 0 ? fq / (double)T : nan("");
+  o[3] = HFv(F_REWARD);
+  o[4] = s_wps;
+  o[5] = s_esc;
+  o[6] = losses;
+  o[7] = kills;
+  o[8] = (double)HIv(CONCLUSION);
+  o[9] = td;
+  o[10] = HIv(N_REALLOC);
+  o[11] = HIv(N_SWITCH);
+  o[12] = HIv(N_ARRIVALS);
+  o[13] = T;
+  o[14] = HIv(N_REACHED);
+  o[15] = HIv(N_MISSED);
+  o[16] = HIv(N_ON_TIME);
+  o[17] = HIv(N_WINDOWED);
+  int den = HIv(N_ON_TIME) + HIv(N_MISSED);
+  o[18] = (double)HIv(N_ON_TIME) / (double)(den > 1 ? den : 1);
+  int den2 = HIv(T) * (A > 1 ? A : 1);
+  o[19] = (double)HIv(IDLE_RESERVE) / (double)(den2 > 1 ? den2 : 1);
+  o[20] = cov;
+  o[21] = HIv(PROT_REC_DONE);
+  o[22] = HIv(RECON_LOSSES);
+  o[23] = HIv(ESCORT_LOSSES);
+  o[24] = HIv(INTERCEPTED);
+  o[25] = HIv(MUTUAL);
+  o[26] = HIv(BREACHES);
+  o[27] = HIv(ESC_REQUESTS);
+  o[28] = HIv(ESC_COMPLETED);
+  o[29] = HIv(ESC_FAILED);
+}
+
 }  // namespace muav

@@ -151,3 +151,122 @@ class HostEnv:
 
     def err(self, e):
         return self.codec.header(self.rec[e], "ERRFLAGS")
+
+
+class HostBackend:
+    """Test-only backend of multi_uav_ta_gym_env_b200.env.MultiUAVEnv over the CPU build of the kernel core,
+    so the single-env facade (proxies, observation dicts, allocator class) can be exercised -- and driven by
+    the UNMODIFIED reference hybrids -- in the GPU-less authoring container.  Never used by the product."""
+
+    _hc = None
+
+    def __init__(self, opts, queue_cap=16):
+        if HostBackend._hc is None:
+            HostBackend._hc = HostCheck()
+        hc = HostBackend._hc
+        self.lib = hc.lib
+        self.opts = opts
+        self.cfg = _lib.build_config(opts, queue_cap=queue_cap)
+        self.codec = state.RecordCodec(self.lib, self.cfg)
+        d = self.lib.dll
+        P = C.c_void_p
+        d.hostcheck_allocate.restype = C.c_int
+        d.hostcheck_allocate.argtypes = [C.POINTER(_lib.MuavConfig), P, C.POINTER(_lib.MuavAllocOpts),
+                                         C.POINTER(_lib.MuavStepOut), P, C.c_int]
+        d.hostcheck_observe.restype = C.c_int
+        d.hostcheck_observe.argtypes = [C.POINTER(_lib.MuavConfig), P, C.c_int, P, P, P, P, P, P, C.c_int]
+        d.hostcheck_metrics.restype = C.c_int
+        d.hostcheck_metrics.argtypes = [C.POINTER(_lib.MuavConfig), P, P, C.c_int]
+        d.hostcheck_tokens_pair.restype = C.c_int
+        d.hostcheck_tokens_pair.argtypes = [C.POINTER(_lib.MuavConfig), P, C.c_int, C.c_int, P, P, P, P, P, P, C.c_int]
+
+    def reset(self, seed):
+        sc = reset.generate_scenario(self.opts, int(seed), list(self.cfg.tape_words))
+        self.rec, self.tapes = reset.pack_records(self.lib, self.cfg, [sc])
+        return sc
+
+    def record(self):
+        return self.rec[0]
+
+    def step(self, actions):
+        A = self.cfg.n_agents
+        rew = np.zeros(1)
+        term = np.zeros(1, np.uint8)
+        trunc = np.zeros(1, np.uint8)
+        nev = np.zeros(1, np.int32)
+        evs = np.zeros((1, self.cfg.event_cap), np.int32)
+        out = _lib.MuavStepOut()
+        out.d_reward, out.d_terminated, out.d_truncated = rew.ctypes.data, term.ctypes.data, trunc.ctypes.data
+        out.d_n_events, out.d_events = nev.ctypes.data, evs.ctypes.data
+        act = np.ascontiguousarray(actions.reshape(1, A, 2), dtype=np.int32)
+        rc = self.lib.dll.hostcheck_step(C.byref(self.cfg), self.rec.ctypes.data, self.tapes.ctypes.data, act.ctypes.data,
+                                         None, C.byref(out), 1, 1)
+        assert rc == 0
+        return float(rew[0]), bool(term[0]), bool(trunc[0]), state.decode_events(nev[0], evs[0])
+
+    def allocate(self, spec, scores, priorities, reserved, order):
+        A = self.cfg.n_agents
+        O = _lib.MuavAllocOpts()
+        O.mode, O.replan_interval, O.event_mask = spec.mode, spec.replan_interval, spec.event_mask
+        O.use_visibility, O.pair_tokens, O.max_coord = int(spec.use_visibility), int(spec.pair_tokens), spec.max_coord
+        keep = []
+        if scores is not None:
+            sc = np.ascontiguousarray(scores, dtype=np.float64)
+            keep.append(sc)
+            O.d_edge_scores, O.score_rows, O.score_cols, O.score_f64 = sc.ctypes.data, sc.shape[0], sc.shape[1], 1
+        if priorities is not None:
+            pr = np.ascontiguousarray(priorities, dtype=np.float64)
+            keep.append(pr)
+            O.d_priorities = pr.ctypes.data
+        if reserved is not None:
+            rs = np.ascontiguousarray(reserved, dtype=np.uint8)
+            keep.append(rs)
+            O.d_reserved = rs.ctypes.data
+        if order is not None:
+            od = np.ascontiguousarray(order, dtype=np.int32)
+            keep.append(od)
+            O.d_task_order = od.ctypes.data
+        npairs = np.zeros(1, np.int32)
+        pairs = np.zeros((1, A), np.int32)
+        out = _lib.MuavStepOut()
+        out.d_n_pairs, out.d_pairs = npairs.ctypes.data, pairs.ctypes.data
+        rc = self.lib.dll.hostcheck_allocate(C.byref(self.cfg), self.rec.ctypes.data, C.byref(O), C.byref(out), None, 1)
+        assert rc == 0
+        return [[int(p) >> 16, int(p) & 0xFFFF] for p in pairs[0, : npairs[0]]]
+
+    def observe(self, max_rows):
+        A = self.cfg.n_agents
+        ti = np.zeros((max_rows, 21))
+        pm = np.zeros(max_rows, np.uint8)
+        lm = np.zeros((A, max_rows), np.uint8)
+        ao = np.zeros((A, 9))
+        ef = np.zeros(5, np.float32)
+        nr = np.zeros(1, np.int32)
+        rc = self.lib.dll.hostcheck_observe(C.byref(self.cfg), self.rec.ctypes.data, max_rows, ti.ctypes.data, pm.ctypes.data,
+                                            lm.ctypes.data, ao.ctypes.data, ef.ctypes.data, nr.ctypes.data, 1)
+        assert rc == 0
+        return {"tasks_info": ti, "mask": pm.astype(bool), "legal_mask": lm.astype(bool), "agent_obs": ao,
+                "event_flags": ef, "n_rows": nr[0]}
+
+    def tokens_pair(self, max_tasks=32, max_agents=16):
+        tf = np.zeros((max_tasks, 13), np.float32)
+        tm = np.zeros(max_tasks, np.uint8)
+        af = np.zeros((max_agents, 12), np.float32)
+        am = np.zeros(max_agents, np.uint8)
+        ev = np.zeros((max_agents, max_tasks), np.float32)
+        ids = np.zeros(max_tasks, np.int32)
+        rc = self.lib.dll.hostcheck_tokens_pair(C.byref(self.cfg), self.rec.ctypes.data, max_tasks, max_agents, tf.ctypes.data,
+                                                tm.ctypes.data, af.ctypes.data, am.ctypes.data, ev.ctypes.data,
+                                                ids.ctypes.data, 1)
+        assert rc == 0
+        return {"task_feats": tf, "task_mask": tm.astype(bool), "agent_feats": af, "agent_mask": am.astype(bool),
+                "edge_valid": ev, "task_ids": ids}
+
+    def metrics(self):
+        m = np.zeros(30)
+        rc = self.lib.dll.hostcheck_metrics(C.byref(self.cfg), self.rec.ctypes.data, m.ctypes.data, 1)
+        assert rc == 0
+        return m
+
+    def patch_field(self, name, index, value):
+        self.codec.field(self.rec[0], name)[index] = value

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include "../../multi_uav_ta_gym_env_b200/csrc/muav_alloc.cuh"
+#include "../../multi_uav_ta_gym_env_b200/csrc/muav_views.cuh"
 
 using namespace muav;
 
@@ -78,6 +79,88 @@ int hostcheck_step(const muav_config* cfg, void* records, const uint32_t* tapes,
     }
   }
   free(scratch);
+  return 0;
+}
+
+// muav_allocate with host pointers
+int hostcheck_allocate(const muav_config* cfg, void* records, const muav_alloc_opts* opts, const muav_step_out* out,
+                       int32_t* actions_out, int n_envs) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  Layout L = make_layout(*cfg);
+  muav_step_out Z;
+  memset(&Z, 0, sizeof(Z));
+  if (out) Z = *out;
+  char* scratch = (char*)malloc((size_t)L.scratch_bytes + 64);
+  const int A = L.D.A;
+  int16_t act_agent[MUAV_MAX_AGENTS], act_tid[MUAV_MAX_AGENTS];
+  for (int e = 0; e < n_envs; ++e) {
+    Sim S;
+    S.V.base = (char*)records + (size_t)e * L.record_bytes;
+    S.V.L = &L;
+    S.Cp = cfg;
+    S.tape = nullptr;
+    S.scratch = scratch;
+    S.out_events = nullptr;
+    View& V = S.V;
+    int np = HIv(DONE) ? 0 : allocate_tasks(S, *opts, e, act_agent, act_tid, 0, 1);
+    if (Z.d_n_pairs) Z.d_n_pairs[e] = np;
+    int n_act = 0;
+    for (int i = 0; i < np; ++i) {
+      if (Z.d_pairs) Z.d_pairs[(size_t)e * A + i] = ((int)act_agent[i] << 16) | (int)act_tid[i];
+      if (actions_out && HIv(N_OPEN) > 0 && S.in_last_open(act_tid[i])) {
+        int k = act_tid[i] - 1, idx = 0;
+        for (int kk = 0; kk < k; ++kk) idx += (V.open_mask()[kk >> 5] >> (kk & 31)) & 1u;
+        actions_out[((size_t)e * A + n_act) * 2] = act_agent[i];
+        actions_out[((size_t)e * A + n_act) * 2 + 1] = idx;
+        ++n_act;
+      }
+    }
+    if (actions_out && n_act < A) actions_out[((size_t)e * A + n_act) * 2] = -1;
+  }
+  free(scratch);
+  return 0;
+}
+
+int hostcheck_tokens_pair(const muav_config* cfg, const void* records, int max_tasks, int max_agents, float* tf,
+                          uint8_t* tm, float* af, uint8_t* am, float* ev, int32_t* ids, int n_envs) {
+  Layout L = make_layout(*cfg);
+  int16_t* cols = (int16_t*)malloc(sizeof(int16_t) * (max_tasks + 2));
+  for (int e = 0; e < n_envs; ++e) {
+    View V;
+    V.base = (char*)records + (size_t)e * L.record_bytes;
+    V.L = &L;
+    tokens_pair_env(V, *cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * 13, tm + (size_t)e * max_tasks,
+                    af + (size_t)e * max_agents * 12, am + (size_t)e * max_agents, ev + (size_t)e * max_agents * max_tasks,
+                    ids + (size_t)e * max_tasks, cols, 0, 1);
+  }
+  free(cols);
+  return 0;
+}
+
+int hostcheck_observe(const muav_config* cfg, const void* records, int max_rows, double* ti, uint8_t* pad, uint8_t* legal,
+                      double* ao, float* ef, int32_t* n_rows, int n_envs) {
+  Layout L = make_layout(*cfg);
+  for (int e = 0; e < n_envs; ++e) {
+    View V;
+    V.base = (char*)records + (size_t)e * L.record_bytes;
+    V.L = &L;
+    int32_t nr = 0;
+    observe_env(V, *cfg, max_rows, ti + (size_t)e * max_rows * 21, pad + (size_t)e * max_rows,
+                legal + (size_t)e * L.D.A * max_rows, ao + (size_t)e * L.D.A * 9, ef + (size_t)e * 5, &nr);
+    if (n_rows) n_rows[e] = nr;
+  }
+  return 0;
+}
+
+int hostcheck_metrics(const muav_config* cfg, const void* records, double* out, int n_envs) {
+  Layout L = make_layout(*cfg);
+  for (int e = 0; e < n_envs; ++e) {
+    View V;
+    V.base = (char*)records + (size_t)e * L.record_bytes;
+    V.L = &L;
+    metrics_env(V, *cfg, out + (size_t)e * 30);
+  }
   return 0;
 }
 

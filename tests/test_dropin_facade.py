@@ -1,0 +1,215 @@
+"""Drop-in surface: the PettingZoo-shaped MultiUAVEnv facade, its object proxies
+and the HungarianAllocator class, driven by the UNMODIFIED reference planners imported from
+/root/reference and compared with the reference environment step by step.
+
+These tests need the reference tree (authoring container only) and use the CPU build of the kernel
+core as the facade's backend (tests/helpers.HostBackend); on the GPU box tests/test_gpu_facade.py
+runs the facade on its real CUDA backend against the golden fixtures."""
+import numpy as np
+import pytest
+
+import refshim
+import refsnap
+from helpers import HostBackend, injected_scores
+
+pytestmark = pytest.mark.skipif(not refshim.reference_available(), reason="reference tree not present")
+
+
+def make_pair(case, seed, **over):
+    refshim.install()
+    from mUAV_TA.DroneEnv import MultiUAVEnv as RefEnv
+    from multi_uav_ta_gym_env_b200.env import MultiUAVEnv
+
+    rcfg = refshim.wps_config(case)
+    for k, v in over.items():
+        setattr(rcfg, k, v)
+    ref = RefEnv(rcfg)
+    ref_obs, ref_info = ref.reset(seed=seed)
+    from multi_uav_ta_gym_env_b200 import wps_config
+
+    mine = MultiUAVEnv(wps_config(case, **over), _test_backend_factory=lambda c: HostBackend(c))
+    my_obs, my_info = mine.reset(seed=seed)
+    return ref, ref_obs, ref_info, mine, my_obs, my_info
+
+
+def same_obs(a, b):
+    assert list(a.keys()) == list(b.keys())
+    for name in a:
+        oa, ob = a[name], b[name]
+        assert set(oa.keys()) == set(ob.keys()), name
+        assert np.array_equal(np.asarray(oa["agent_position"], float), np.asarray(ob["agent_position"], float))
+        assert np.array_equal(np.asarray(oa["agent_caps"]), np.asarray(ob["agent_caps"]))
+        assert oa["alloc_task"] == ob["alloc_task"]
+        assert list(oa["mask"]) == list(ob["mask"])
+        assert list(oa["legal_mask"]) == list(ob["legal_mask"]), name
+        assert np.array_equal(oa["event_flags"], ob["event_flags"])
+        assert len(oa["tasks_info"]) == len(ob["tasks_info"])
+        for ta, tb in zip(oa["tasks_info"], ob["tasks_info"]):
+            assert set(ta.keys()) == set(tb.keys())
+            for k in ta:
+                assert np.array_equal(np.asarray(ta[k], float), np.asarray(tb[k], float)), (name, k)
+
+
+def to_ids(env, result):
+    return [(env.agent_by_name[n].id, t.id) for n, t in result]
+
+
+def apply_assign(env, pairs):
+    actions = {}
+    for name, task in pairs:
+        if env.last_tasks_info and task in env.last_tasks_info and name not in actions:
+            actions[name] = env.last_tasks_info.index(task)
+    return actions
+
+
+def ref_open_tasks(env):
+    import gen_golden
+
+    return gen_golden.ref_open_tasks(env)
+
+
+@pytest.mark.parametrize("case,seed,interval", [("WPS_hard", 3, 20), ("WPS_escort", 1, 12), ("WPS_commit", 2, 20)])
+def test_env_and_allocator_facade_follow_the_reference_loop(case, seed, interval):
+    """wps_eval.run_wps_episode / escort_eval loop: reference env + reference allocator vs facade env + facade allocator;
+    observations, rewards, infos, pairs and state compared every step."""
+    refshim.install()
+    from TaskAllocation.OptimizationBased.HungarianAllocator import HungarianAllocator as RefHung
+    from multi_uav_ta_gym_env_b200.env import HungarianAllocator
+
+    ref, ro, ri, mine, mo, mi = make_pair(case, seed)
+    assert ref.possible_agents == mine.possible_agents and [a.name for a in ref.agents_obj] == [a.name for a in mine.agents_obj]
+    same_obs(ro, mo)
+    rh, mh = RefHung(interval, ref.max_coord), HungarianAllocator(interval, mine.max_coord)
+    for t in range(150):
+        revents = list(ri.get("events") or []) if isinstance(ri, dict) else []
+        mevents = list(mi.get("events") or []) if isinstance(mi, dict) else []
+        assert revents == mevents
+        rres = rh.allocate_tasks(ref.get_live_agents(), ref_open_tasks(ref), time_step=ref.time_steps, events=revents,
+                                 agent_known_ids=ref.agent_visibility_map())
+        mres = mh.allocate_tasks(mine.get_live_agents(), ref_open_tasks(mine), time_step=mine.time_steps, events=mevents,
+                                 agent_known_ids=mine.agent_visibility_map())
+        assert to_ids(ref, rres) == to_ids(mine, mres), t
+        ract, mact = apply_assign(ref, rres), apply_assign(mine, mres)
+        assert ract == mact
+        ro, rr, rterm, rtrunc, ri = ref.step(ract)
+        mo, mr, mterm, mtrunc, mi = mine.step(mact)
+        assert rr == mr and rterm == mterm and rtrunc == mtrunc, t
+        assert ri["selected"] == mi["selected"] and ri["events"] == mi["events"]
+        if t % 10 == 0 or t > 140:
+            same_obs(ro, mo)
+        assert refsnap.digest(refsnap.snapshot(ref)) == refsnap.digest(mine._snap), t
+        assert ref.agent_visibility_map() == mine.agent_visibility_map()
+    assert (rh.n_replans, rh.n_calls, rh.last_plan_step) == (mh.n_replans, mh.n_calls, mh.last_plan_step)
+    rm, mm = ri["metrics"], mi["metrics"]
+    assert set(rm) == set(mm)
+    for k in rm:
+        assert rm[k] == mm[k] or (rm[k] != rm[k] and mm[k] != mm[k]), k
+    assert ref.compute_s_wps() == mine.compute_s_wps() and ref.compute_s_esc() == mine.compute_s_esc()
+
+
+def hybrid_should_replan(env, events, interval, tags):
+    return env.time_steps == 0 or env.time_steps % interval == 0 or any(ev[0] in tags for ev in events)
+
+
+HYB_TAGS = ("Reset_Allocation", "New_Threat", "Agent_Fail")
+ESC_TAGS = HYB_TAGS + ("Escort_Created", "Escort_Retired")
+
+
+@pytest.mark.parametrize("planner,case,seed", [
+    ("urgency_pair", "WPS_hard", 5), ("pair_injected", "WPS_hard", 6), ("urgency_commit", "WPS_commit", 1),
+    ("urgency_coalition", "WPS_escort", 2)])
+@pytest.mark.parametrize("allocator", ["reference_class_on_proxies", "facade_class"])
+def test_unmodified_reference_hybrids_run_on_the_facade(planner, case, seed, allocator):
+    """PairCostHybrid / UrgencyPair / UrgencyCommit / UrgencyCoalition from the reference tree plan on the proxies
+    (tokens, commit_until writes, priorities, reserved agents, edge scores) exactly as on the reference env."""
+    refshim.install()
+    from TaskAllocation.Hybrid.AttentionCommit import UrgencyCommit
+    from TaskAllocation.Hybrid.AttentionEscort import UrgencyCoalition
+    from TaskAllocation.Hybrid.PairCostHybrid import PairCostHybrid, UrgencyPair
+    from TaskAllocation.OptimizationBased.HungarianAllocator import HungarianAllocator as RefHung
+    from multi_uav_ta_gym_env_b200.env import HungarianAllocator
+
+    ref, ro, ri, mine, mo, mi = make_pair(case, seed)
+    interval = 12 if planner == "urgency_coalition" else 15
+    tags = ESC_TAGS if planner == "urgency_coalition" else HYB_TAGS
+    rh = RefHung(10**9 if planner == "urgency_coalition" else 20, ref.max_coord)
+    mh = (RefHung if allocator == "reference_class_on_proxies" else HungarianAllocator)(rh.replan_interval, mine.max_coord)
+    mk = {"urgency_pair": UrgencyPair, "urgency_commit": UrgencyCommit, "urgency_coalition": UrgencyCoalition,
+          "pair_injected": lambda: PairCostHybrid(use_attention=False, device="cpu")}[planner]
+    rp, mp = mk(), mk()
+    n_plans = 0
+    for t in range(150):
+        revents = list(ri.get("events") or []) if isinstance(ri, dict) else []
+        mevents = list(mi.get("events") or []) if isinstance(mi, dict) else []
+        rres, mres = [], []
+        if hybrid_should_replan(ref, revents, interval, tags):
+            assert hybrid_should_replan(mine, mevents, interval, tags)
+            n_plans += 1
+            if planner == "pair_injected":
+                sc = injected_scores(seed, ref.time_steps, 16, 32)
+                rout = rp.plan(ref, rh, events=revents, explore=False, force=True, scores=sc)
+                mout = mp.plan(mine, mh, events=mevents, explore=False, force=True, scores=sc)
+                rres, mres = rout[0], mout[0]
+                for k in ("task_feats", "task_mask", "agent_feats", "agent_mask", "edge_valid"):
+                    assert np.array_equal(rout[1][k], mout[1][k]), (t, k)
+                kt = mine._backend.tokens_pair(32, 16)   # the kernel's own token builder == build_pair_tokens on the reference
+                for k in ("task_feats", "task_mask", "agent_feats", "agent_mask", "edge_valid"):
+                    assert np.array_equal(rout[1][k], kt[k]), (t, k)
+            elif planner == "urgency_coalition":
+                rres = rp.plan(ref, rh, events=revents, force=True)
+                mres = mp.plan(mine, mh, events=mevents, force=True)
+            else:
+                rres = rp.plan(ref, rh, events=revents, force=True)[0]
+                mres = mp.plan(mine, mh, events=mevents, force=True)[0]
+            assert to_ids(ref, rres) == to_ids(mine, mres), t
+            assert [a.commit_until for a in ref.agents_obj] == [a.commit_until for a in mine.agents_obj], t
+        ro, rr, rterm, rtrunc, ri = ref.step(apply_assign(ref, rres))
+        mo, mr, mterm, mtrunc, mi = mine.step(apply_assign(mine, mres))
+        assert rr == mr, t
+        assert refsnap.digest(refsnap.snapshot(ref)) == refsnap.digest(mine._snap), t
+    assert n_plans > 15
+    assert ri["metrics"]["S_WPS"] == mi["metrics"]["S_WPS"] and ri["metrics"]["S_ESC"] == mi["metrics"]["S_ESC"]
+
+
+@pytest.mark.parametrize("case,seed", [("WPS_hard", 11), ("WPS_escort", 4)])
+def test_oracle_tokens_and_observations_match_the_reference(case, seed):
+    """oracle/tokens.py (the checker used by the GPU suite) pinned against build_pair_tokens and
+    _generate_observations of the live reference."""
+    refshim.install()
+    from mUAV_TA.DroneEnv import MultiUAVEnv as RefEnv
+    from TaskAllocation.Hybrid.PairCostHybrid import build_pair_tokens
+    from TaskAllocation.OptimizationBased.HungarianAllocator import HungarianAllocator as RefHung
+    from oracle import tokens as otok
+    from oracle.sim import OracleEnv
+
+    cfg = refshim.wps_config(case)
+    ref = RefEnv(cfg)
+    obs, info = ref.reset(seed=seed)
+    orc = OracleEnv(cfg).reset(seed)
+    hung = RefHung(12 if case == "WPS_escort" else 20, ref.max_coord)
+    for t in range(150):
+        if t % 5 == 0:
+            want = build_pair_tokens(ref, 32, 16)
+            got = otok.build_pair_tokens(orc, 32, 16)
+            for k in ("task_feats", "task_mask", "agent_feats", "agent_mask", "edge_valid"):
+                assert np.array_equal(want[k], got[k]), (t, k)
+            assert list(got["task_ids"][: len(want["task_ids"])]) == list(want["task_ids"])
+            o = otok.observe(orc, max(ref.max_tasks, len(ref.last_tasks_info)))
+            name0 = ref.agents_obj[0].name
+            rows = [d for d in obs[name0]["tasks_info"] if d.get("status", -1) != -1]
+            assert len(rows) == o["n_rows"] or (len(ref.last_tasks_info) == 0)
+            for r, d in enumerate(rows):
+                row = o["tasks_info"][r]
+                assert d["id"] == int(row[0]) and d["status"] == int(row[3])
+                assert np.array_equal(np.asarray(d["position"], float), row[1:3])
+                assert np.array_equal(d["current_reqs"], row[4:10]) and np.array_equal(d["alloc_reqs"], row[10:16])
+                assert (d["init_time"], d["end_time"], d["type_idx"], d["unmet"], d["age"]) == tuple(row[16:21])
+            for a in ref.agents_obj:
+                assert list(obs[a.name]["legal_mask"][: o["n_rows"]]) == list(o["legal_mask"][a.id][: o["n_rows"]])
+            assert np.array_equal(obs[name0]["event_flags"], o["event_flags"])
+        events = list(info.get("events") or []) if isinstance(info, dict) else []
+        res = hung.allocate_tasks(ref.get_live_agents(), ref_open_tasks(ref), time_step=ref.time_steps, events=events,
+                                  agent_known_ids=ref.agent_visibility_map())
+        actions = apply_assign(ref, res)
+        obs, _, _, _, info = ref.step(actions)
+        orc.step([(ref.agent_by_name[n].id, i) for n, i in actions.items()])
