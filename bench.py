@@ -169,7 +169,7 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
 
-    from multi_uav_ta_gym_env_b200 import AllocSpec, BatchedMultiUAVEnv, wps_config
+    from multi_uav_ta_gym_env_b200 import AllocSpec, BatchedMultiUAVEnv, sharding, wps_config
     from multi_uav_ta_gym_env_b200.scorers import AttPairNet, GraphedPairScorer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -184,7 +184,7 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     E = args.envs
     cfg = wps_config(CASE)
-    env = BatchedMultiUAVEnv(cfg, E, device=dev).reset(range(rank * E, (rank + 1) * E))
+    env = BatchedMultiUAVEnv(cfg, E, device=dev).reset(sharding.shard_range(E, rank))
     torch.manual_seed(0)
     net = AttPairNet().to(dev).eval()
     spec = AllocSpec.pair_hybrid(HYBRID_INTERVAL)
@@ -212,20 +212,9 @@ def run_gpu_arm(args):
     def episode_end():
         m = env.metrics()
         launches["n"] += 1
-        vec = torch.zeros(32, dtype=torch.float64, device=dev)
-        vec[0] = E
-        vec[1] = m[:, names.index("S_WPS")].sum()
-        vec[2] = (m[:, names.index("S_WPS")] ** 2).sum()
-        vec[3] = m[:, names.index("n_on_time")].sum()
-        vec[4] = m[:, names.index("n_missed_windows")].sum()
-        vec[5] = m[:, names.index("Kills")].sum()
-        vec[6] = m[:, names.index("Losses")].sum()
-        vec[7] = m[:, names.index("total_distance")].sum()
-        vec[8] = m[:, names.index("n_task_switches")].sum()
-        vec[9] = m[:, names.index("S_ESC")].sum()
-        if world > 1:
-            dist.all_reduce(vec)  # the path's only collective: end-of-episode metric sum over NVLink
-        metric_acc.add_(vec)
+        vec = sharding.metric_vector(m, names)
+        sharding.allreduce_metric_vector(vec)  # the path's only collective: end-of-episode metric sums (NCCL/NVLink)
+        metric_acc[: vec.numel()].add_(vec)
         env.restore()
 
     def device_step(t):
@@ -316,8 +305,7 @@ def run_gpu_arm(args):
         b_alg = 2 * rb + out_bytes
         peak, peak_src = hbm_peak()
         achieved = E * b_alg / (kern_ms / K / 1e3) / 1e9
-        macc = metric_acc.cpu().numpy()
-        n_eps = max(macc[0], 1.0)
+        stats = sharding.summarize(metric_acc[: len(sharding.METRIC_VECTOR)].cpu())
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "weak",
@@ -335,8 +323,8 @@ def run_gpu_arm(args):
                          "traffic": None, "kernel": "muav_step_kernel", "bytes_per_env_step": b_alg,
                          "kernel_ms_per_launch": kern_ms / K, "peak_source": peak_src,
                          "kernel_share_of_step": kern_ms / step_ms},
-            "episode_stats": {"episodes": float(macc[0]), "mean_S_WPS": float(macc[1] / n_eps),
-                              "mean_on_time": float(macc[3] / n_eps), "mean_missed": float(macc[4] / n_eps)},
+            "episode_stats": {k: stats[k] for k in ("episodes", "mean_S_WPS", "sd_S_WPS", "mean_n_on_time",
+                                                    "mean_n_missed_windows", "mean_on_time_rate", "mean_Kills")},
         }
         if cpu_base is not None:
             line["cpu_baseline"] = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -7,6 +7,9 @@ Public surface:
 from .config import CASE_SPECS, WPS_ENV_FLAGS, agentEnvOptions, burst_scaled_spec, make_config, wps_config  # noqa: F401
 
 
+from . import sharding  # noqa: E402,F401
+
+
 def __getattr__(name):
     # torch / CUDA dependent parts are imported lazily so that config-only users stay light
     if name in ("BatchedMultiUAVEnv", "AllocSpec"):

@@ -52,7 +52,7 @@ def test_core_sim_shim():
     obst = [[300.0, 300.0, 50.0], [700.0, 200.0, 80.0]]
     o = OracleEnv(wps_config("WPS_hard"))
     o.obstacles = [tuple(r) for r in obst]
-    for pos, mv in (([340.0, 330.0], [1.0, 0.0]), ([650.0, 260.0], [-0.6, 0.8]), ([10.0, 10.0], [0.0, 1.0])):
+    for pos, mv in (([341.0, 333.0], [1.0, 0.0]), ([650.0, 260.0], [-0.6, 0.8]), ([10.0, 10.0], [0.0, 1.0])):
         got = core_sim.SimCore.avoid_obstacles(pos, obst, mv)
         want = o._avoid(pos[0], pos[1], mv[0], mv[1])
         assert np.allclose(got, want, rtol=1e-9, atol=1e-12)
