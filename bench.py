@@ -191,7 +191,7 @@ def run_gpu_arm(args):
     scores = torch.zeros(E, 16, 32, dtype=torch.float32, device=dev)
     # the step kernel emits the pair tokens of every env that will replan before the next step
     tok = env.enable_fused_tokens(32, 16, HYBRID_INTERVAL, 0b111)
-    scorer = GraphedPairScorer(net, E, dev)
+    scorer = GraphedPairScorer(net, E, dev, live_agents=env.n_agents)
     scorer.warm()
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     metric_acc = torch.zeros(32, dtype=torch.float64, device=dev)

@@ -78,6 +78,12 @@ typedef struct muav_alloc_opts {
                                  and d_edge_scores is indexed in token space [live agent row, token task column] */
   int32_t score_rows, score_cols; /* edge score tensor shape per env (max_agents, max_tasks) */
   int32_t score_f64;       /* 1: d_edge_scores points to double, else float */
+  int32_t planner;         /* 0 none; 1 UrgencyCommit.plan (AttentionCommit.py:310-357): priorities 0.6 urg + 0.4 scarcity,
+                                committed agents reserved, lock ranking, commit_until writes;
+                              2 UrgencyCoalition.plan (AttentionEscort.py:720-767): engineered edge scores, committed agents
+                                reserved, every assigned agent locked for commit_horizon */
+  int32_t reserved1;
+  double commit_fraction;  /* UrgencyCommit(commit_fraction=0.35) */
   double max_coord;        /* HungarianAllocator(max_coord=...) */
   const void* d_edge_scores;   /* [E, score_rows, score_cols] float (or double when score_f64) or NULL;
                                   pair_tokens=0: indexed [agent id, task index] */

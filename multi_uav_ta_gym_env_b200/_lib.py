@@ -13,7 +13,7 @@ from .config import CAP_TABLE, ENGAGE_RANGE, MAX_SPEEDS, RW_KEYS, TASK_DURATION,
 MAX_GROUPS = 8
 N_METRICS = 30
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-CUDA_LIB_PATH = os.path.join(PKG_DIR, "libmuav_b200.so")
+CUDA_LIB_PATH = os.environ.get("MUAV_LIB_OVERRIDE") or os.path.join(PKG_DIR, "libmuav_b200.so")  # override: tuning builds only
 
 
 class MuavConfig(C.Structure):
@@ -51,6 +51,8 @@ class MuavAllocOpts(C.Structure):
         ("mode", C.c_int32), ("replan_interval", C.c_int32), ("event_mask", C.c_int32),
         ("use_visibility", C.c_int32), ("pair_tokens", C.c_int32), ("score_rows", C.c_int32),
         ("score_cols", C.c_int32), ("score_f64", C.c_int32),
+        ("planner", C.c_int32), ("reserved1", C.c_int32),
+        ("commit_fraction", C.c_double),
         ("max_coord", C.c_double),
         ("d_edge_scores", C.c_void_p), ("d_priorities", C.c_void_p), ("d_reserved", C.c_void_p),
         ("d_task_order", C.c_void_p),

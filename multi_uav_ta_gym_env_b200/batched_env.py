@@ -32,6 +32,8 @@ class AllocSpec:
     use_visibility: bool = True
     pair_tokens: bool = False
     max_coord: float = 1200.0
+    planner: int = 0              # 1: UrgencyCommit.plan, 2: UrgencyCoalition.plan (device-side planners)
+    commit_fraction: float = 0.35
 
     @staticmethod
     def local_hungarian(interval=20):
@@ -48,6 +50,16 @@ class AllocSpec:
     @staticmethod
     def pair_hybrid(interval=15):
         return AllocSpec(2, interval, HYBRID_EVENTS, True, True)
+
+    @staticmethod
+    def urgency_commit(interval=15, commit_fraction=0.35):
+        """UrgencyCommit under the hybrid cadence of wps_eval.py:64-73,207-213."""
+        return AllocSpec(2, interval, HYBRID_EVENTS, True, False, planner=1, commit_fraction=commit_fraction)
+
+    @staticmethod
+    def urgency_coalition(interval=12):
+        """UrgencyCoalition under escort_eval.py:52-58,175-179 (every event tag triggers)."""
+        return AllocSpec(2, interval, ALL_EVENTS, True, False, planner=2)
 
 
 class BatchedMultiUAVEnv:
@@ -185,6 +197,8 @@ class BatchedMultiUAVEnv:
         O.use_visibility = int(spec.use_visibility)
         O.pair_tokens = int(spec.pair_tokens)
         O.max_coord = spec.max_coord
+        O.planner = spec.planner
+        O.commit_fraction = spec.commit_fraction
         keep = []
         if edge_scores is not None:
             es = edge_scores.to(device=self.device, dtype=torch.float32).contiguous()

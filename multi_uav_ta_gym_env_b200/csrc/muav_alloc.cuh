@@ -13,6 +13,8 @@ struct AllocScratch {
   int32_t* ctrl;  // small control block shared by the lanes
   int16_t *path, *col4row, *row4col, *remaining, *SR, *SC, *free_agents, *round_tasks, *open_t, *tokcol, *col_of_row,
       *live_row;
+  double *plan_pri, *plan_score;  // planner: task priorities [TC], lock scores [A]
+  uint8_t* plan_reserved;         // planner: reserved agents [A]
 };
 
 MUAV_HD inline AllocScratch carve_scratch(char* p, int A, int TC) {
@@ -38,6 +40,11 @@ MUAV_HD inline AllocScratch carve_scratch(char* p, int A, int TC) {
   S.round_tasks = s; s += TC;
   S.open_t = s; s += TC;
   S.tokcol = s; s += TC;
+  // planner block starts at the next 8-byte boundary
+  uintptr_t q = ((uintptr_t)s + 7) & ~(uintptr_t)7;
+  S.plan_pri = (double*)q;
+  S.plan_score = S.plan_pri + TC;
+  S.plan_reserved = (uint8_t*)(S.plan_score + A);
   return S;
 }
 
@@ -63,7 +70,7 @@ inline int warp_max_i32(int v) { return v; }
 // SciPy's sequential column scan is spread over the lanes; its tie rule -- among equal minima the
 // LAST scanned unassigned column wins, otherwise the FIRST scanned column -- is reproduced by
 // reducing (min value, first index, last unassigned index) over the lanes.
-MUAV_HD inline bool lsap_solve(const double* cost, int nr, int nc, AllocScratch& S, int16_t* col_of_row, int lane,
+MUAV_HD MUAV_NI_A inline bool lsap_solve(const double* cost, int nr, int nc, AllocScratch& S, int16_t* col_of_row, int lane,
                                int nlanes) {
   const bool tr = nc < nr;
   const int R = tr ? nc : nr;
@@ -187,14 +194,17 @@ MUAV_HD inline double residual_demand(const Sim& S, int k) {
 // Warp-collective (host: lane 0 of 1): lane 0 takes the sequential decisions (replan rule, open list,
 // residuals, acceptance in row order), the cost matrix and the LSAP scans are spread over the lanes.
 // Writes ordered (agent, task id) pairs; returns their count (same value on every lane).
-MUAV_HD inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, int e, int16_t* out_agent, int16_t* out_tid, int lane,
-                                  int nlanes) {
+MUAV_HD inline double coalition_edge_score(const Sim& S, int a, int k, int t);
+
+MUAV_HD MUAV_NI_A inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, int e, int16_t* out_agent, int16_t* out_tid, int lane,
+                                  int nlanes, bool local_ptrs = false) {
   View& V = S.V;
   const int A = V.L->D.A, TC = V.L->D.TC;
   const int t = HIv(T);
   AllocScratch W = carve_scratch(S.scratch, A, TC);
-  const uint8_t* reserved = O.d_reserved ? O.d_reserved + (size_t)e * A : nullptr;
-  const double* pri = O.d_priorities ? O.d_priorities + (size_t)e * TC : nullptr;
+  const size_t eo = local_ptrs ? 0 : (size_t)e;  // planner-produced arrays live in this env's scratch
+  const uint8_t* reserved = O.d_reserved ? O.d_reserved + eo * A : nullptr;
+  const double* pri = O.d_priorities ? O.d_priorities + eo * TC : nullptr;
   const size_t sc_off = (size_t)e * O.score_rows * O.score_cols;
   const float* scores = (O.d_edge_scores && !O.score_f64) ? (const float*)O.d_edge_scores + sc_off : nullptr;
   const double* scores64 = (O.d_edge_scores && O.score_f64) ? (const double*)O.d_edge_scores + sc_off : nullptr;
@@ -288,7 +298,7 @@ MUAV_HD inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, int e, int16
         if (dl >= 0) {
           int rem = dl - t;
           if (rem < 0) rem = 0;
-          urgency = 1.0 - dmin((double)rem / 40.0, 1.0);
+          urgency = 1.0 - dmin(ddiv((double)rem, 40.0), 1.0);
         }
         const int ti = V.k_type()[k];
         const double delivered = is_coalition(S, k) ? 1.0 : S.cap(a, ti);
@@ -297,11 +307,13 @@ MUAV_HD inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, int e, int16
           const double dist = norm2(V.a_posx()[a] - V.k_posx()[k], V.a_posy()[a] - V.k_posy()[k]);
           const double missing = dmax(W.resid[q], 1e-6);
           const double p = pri ? pri[k] : 0.0;
-          base = dist / mc - 0.5 * dmin(delivered, missing) - 0.4 * p - 0.6 * urgency;
+          base = ddiv(dist, mc) - 0.5 * dmin(delivered, missing) - 0.4 * p - 0.6 * urgency;
         }
         if (base < 1e5 / 2) {
           double sc = 0.0;
-          if (scores64) {
+          if (O.planner == 2) {
+            sc = coalition_edge_score(S, a, k, t);
+          } else if (scores64) {
             if (a < O.score_rows && k < O.score_cols) sc = scores64[a * O.score_cols + k];
           } else if (scores) {
             if (O.pair_tokens) {
@@ -368,6 +380,155 @@ MUAV_HD inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, int e, int16
   const int n_pairs = W.ctrl[C_NPAIRS];
   MUAV_WARP_SYNC();
   return n_pairs;
+}
+
+// urgency (_urgency, AttentionRAH.py:29-34)
+MUAV_HD inline double task_urgency(const View& V, int k, int t) {
+  int dl = V.k_deadline()[k];
+  if (dl < 0) return 0.0;
+  int rem = dl - t;
+  if (rem < 0) rem = 0;
+  return 1.0 - dmin(ddiv((double)rem, 40.0), 1.0);
+}
+
+// UrgencyCoalition edge score (AttentionEscort.py:727-751) incl. _threat_stats pressure (:46-65)
+MUAV_HD inline double coalition_edge_score(const Sim& S, int a, int k, int t) {
+  const View& V = S.V;
+  const double mc = S.C().max_coord;
+  double ax = V.k_posx()[k], ay = V.k_posy()[k];
+  int prot = V.k_prot_agent()[k];
+  if (prot >= 0) { ax = V.a_posx()[prot]; ay = V.a_posy()[prot]; }
+  double best = mc;
+  const int na = V.hi()[HI_N_ACTIVE];
+  for (int i = 0; i < na; ++i) {
+    int hid = V.h_order()[i];
+    if (V.h_status()[hid] == 2) continue;
+    double d = norm2(V.h_posx()[hid] - ax, V.h_posy()[hid] - ay);
+    best = dmin(best, d);
+  }
+  const double pressure = 1.0 - dmin(ddiv(best, mc), 1.0);
+  const double urg = task_urgency(V, k, t);
+  const int ti = V.k_type()[k];
+  const int at = V.a_type()[a];
+  const double is_escort = V.k_kind()[k] == 1 ? 1.0 : 0.0;
+  const double cp = S.cap(a, ti) > 0 ? S.cap(a, ti) : 0.0;
+  const double dist = ddiv(norm2(V.a_posx()[a] - V.k_posx()[k], V.a_posy()[a] - V.k_posy()[k]), mc);
+  double score = 0.45 * urg + 0.35 * pressure * (0.5 + 0.5 * is_escort) + 0.3 * dmin(cp, 1.0) - 0.25 * dist;
+  if (is_fighter(at) && (is_escort != 0.0 || ti == TT_INT)) score += 0.2;
+  if (is_recon(at) && ti == TT_REC) score += 0.2;
+  return dmin(dmax(score, 0.0), 1.0);
+}
+
+// apply_agent_commits (AttentionCommit.py:33-46): only agents that currently hold a real task are locked
+MUAV_HD inline void apply_commit(Sim& S, int a, int horizon) {
+  View& V = S.V;
+  if (horizon <= 0 || V.a_state()[a] == -1) return;
+  if (V.a_qlen()[a] > 0) V.a_commit()[a] = HIv(T) + horizon;
+}
+
+// Planner front ends (muav_alloc_opts.planner) + allocate_tasks.  Warp-collective.
+MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, int16_t* out_agent, int16_t* out_tid, int lane,
+                                     int nlanes) {
+  if (O.planner == 0) return allocate_tasks(S, O, e, out_agent, out_tid, lane, nlanes);
+  View& V = S.V;
+  const muav_config& C = S.C();
+  const int A = V.L->D.A, TC = V.L->D.TC;
+  const int t = HIv(T);
+  AllocScratch W = carve_scratch(S.scratch, A, TC);
+  // the caller's cadence (wps_eval.py:64-73 / escort_eval.py:52-58), then plan(force=True)
+  const int interval = O.replan_interval > 0 ? O.replan_interval : 1;
+  const bool go = O.mode == 3 || t == 0 || (t % interval) == 0 || (HIv(EV_TAGMASK) & O.event_mask) != 0;
+  if (!go) return 0;
+  const bool vis_none = !(C.sense_radius != 0.0) && !(C.threat_delay != 0);
+  if (lane == 0) {
+    // committed_names (AttentionCommit.py:24-30)
+    for (int a = 0; a < A; ++a) W.plan_reserved[a] = (V.a_state()[a] != -1 && V.a_commit()[a] > t) ? 1 : 0;
+  }
+  if (O.planner == 1) {
+    int n_live = 0;
+    for (int a = 0; a < A; ++a) n_live += V.a_state()[a] != -1;
+    const double nl = (double)(n_live > 1 ? n_live : 1);
+    const int n = HIv(N_TASKS);
+    for (int k = lane; k < n; k += nlanes) {
+      double p = 0.0;
+      if (V.k_status()[k] != 2) {
+        double scar = 0.0;
+        if (!vis_none) {
+          int cnt = 0;
+          for (int a = 0; a < A; ++a) cnt += S.known_bit(a, k) ? 1 : 0;
+          scar = 1.0 - dmin(ddiv((double)cnt, nl), 1.0);
+        }
+        p = 0.6 * task_urgency(V, k, t) + 0.4 * scar;
+      }
+      W.plan_pri[k] = p;
+    }
+  }
+  MUAV_WARP_SYNC();
+  muav_alloc_opts P = O;
+  P.mode = 3;
+  P.d_reserved = W.plan_reserved;
+  P.d_edge_scores = nullptr;
+  P.d_task_order = nullptr;
+  if (O.planner == 1) {
+    P.d_priorities = W.plan_pri;
+    P.pair_tokens = 1;      // task list = build_att_tokens' open list (alloc < cur), not truncated
+    P.score_cols = TC;
+    P.score_rows = 0;
+    P.use_visibility = 1;
+  } else {
+    P.d_priorities = nullptr;
+    P.pair_tokens = 0;
+    P.use_visibility = 1;
+  }
+  const int np = allocate_tasks(S, P, e, out_agent, out_tid, lane, nlanes, true);
+  if (lane == 0 && np > 0) {
+    if (O.planner == 2) {
+      for (int i = 0; i < np; ++i) apply_commit(S, out_agent[i], C.commit_horizon);
+    } else {
+      // UrgencyCommit lock ranking (AttentionCommit.py:334-355)
+      const double thr = 1.0 - 12.0 / 40.0;
+      const int n = HIv(N_TASKS);
+      uint64_t assigned = 0;
+      int n_free = 0;
+      for (int i = 0; i < np; ++i) assigned |= (uint64_t)1 << out_agent[i];
+      for (int a = 0; a < A; ++a) {
+        W.plan_score[a] = -1.0;
+        if (!((assigned >> a) & 1) || V.a_state()[a] == -1 || W.plan_reserved[a]) continue;
+        double dmn = 0.0;
+        bool any = false;
+        for (int k = 0; k < n; ++k) {
+          if (V.k_status()[k] == 2 || V.k_deadline()[k] < 0) continue;
+          int ti = V.k_type()[k];
+          if (!(V.k_alloc()[ti * TC + k] < V.k_cur()[ti * TC + k])) continue;
+          if (!vis_none && !S.known_bit(a, k)) continue;
+          if (!(task_urgency(V, k, t) >= thr)) continue;
+          double d = norm2(V.a_posx()[a] - V.k_posx()[k], V.a_posy()[a] - V.k_posy()[k]);
+          if (!any || d < dmn) dmn = d;
+          any = true;
+        }
+        W.plan_score[a] = dmn + (V.a_type()[a] == UT_F2 ? 500.0 : 0.0);
+        ++n_free;
+      }
+      int n_lock = (int)rint(O.commit_fraction * (double)(n_free > 1 ? n_free : 1));
+      if (n_lock < 1) n_lock = 1;
+      const int horizon = C.commit_horizon != 0 ? C.commit_horizon : 25;
+      // top n_lock by (score, name) descending
+      for (int r = 0; r < n_lock && r < n_free; ++r) {
+        int best = -1;
+        for (int a = 0; a < A; ++a) {
+          if (W.plan_score[a] < 0.0) continue;
+          if (best < 0 || W.plan_score[a] > W.plan_score[best] ||
+              (W.plan_score[a] == W.plan_score[best] && V.a_name_rank()[a] > V.a_name_rank()[best]))
+            best = a;
+        }
+        if (best < 0) break;
+        W.plan_score[best] = -1.0;
+        apply_commit(S, best, horizon);
+      }
+    }
+  }
+  MUAV_WARP_SYNC();
+  return np;
 }
 
 }  // namespace muav

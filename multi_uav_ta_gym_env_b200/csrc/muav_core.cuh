@@ -27,8 +27,11 @@ enum { TT_HOLD = 0, TT_REC = 1, TT_ATT = 2, TT_DEF = 3, TT_INT = 4, TT_DET = 5 }
 enum { UT_R1 = 0, UT_R2 = 1, UT_E1 = 2, UT_F1 = 3, UT_F2 = 4, UT_T1 = 5, UT_T2 = 6 };
 enum { EV_RESET = 0, EV_FAIL = 1, EV_THREAT = 2, EV_ESC_CREATED = 3, EV_ESC_RETIRED = 4 };
 
-MUAV_HD inline double norm2(double x, double y) { return sqrt(fma(y, y, x * x)); }
-MUAV_HD inline double norm2_rows(double x, double y) { return sqrt(x * x + y * y); }
+// Out of line on purpose: float64 sqrt / divide expand to ~25 SASS instructions each; the kernel is
+// instruction-fetch bound (profiles/r01_step_kernel_ncu.md), so all call sites share one copy.
+MUAV_HD MUAV_NOINLINE inline double norm2(double x, double y) { return sqrt(fma(y, y, x * x)); }
+MUAV_HD MUAV_NOINLINE inline double norm2_rows(double x, double y) { return sqrt(x * x + y * y); }
+MUAV_HD MUAV_NOINLINE inline double ddiv(double a, double b) { return a / b; }
 MUAV_HD inline double dmax(double a, double b) { return a > b ? a : b; }
 MUAV_HD inline double dmin(double a, double b) { return a < b ? a : b; }
 MUAV_HD inline bool is_fighter(int ut) { return ut == UT_F1 || ut == UT_F2; }
@@ -38,6 +41,19 @@ MUAV_HD inline bool is_recon(int ut) { return ut == UT_R1 || ut == UT_R2; }
 #define MUAV_WARP_SYNC() __syncwarp()
 #else
 #define MUAV_WARP_SYNC() ((void)0)
+#endif
+
+#if defined(MUAV_PHASE_TIMING) && defined(__CUDA_ARCH__)
+#define MUAV_TICK(slot)                                   \
+  do {                                                    \
+    long long _now = clock64();                           \
+    if (phase_cycles) phase_cycles[slot] += _now - _tick; \
+    _tick = _now;                                         \
+  } while (0)
+#define MUAV_TICK_START() long long _tick = clock64()
+#else
+#define MUAV_TICK(slot) ((void)0)
+#define MUAV_TICK_START() ((void)0)
 #endif
 
 struct StepResult {
@@ -53,6 +69,7 @@ struct Sim {
   int32_t* out_events;   // drained events of this step (may be null)
   int n_out_events;
   double step_reward;
+  long long* phase_cycles;  // MUAV_PHASE_TIMING only: per-warp cycle sums by phase
 
   MUAV_HD const muav_config& C() const { return *Cp; }
   MUAV_HD int A() const { return V.L->D.A; }
@@ -144,10 +161,10 @@ struct Sim {
 
   // ------------------------------------------------------------------ Task.add/removeAgentCap
   // DroneEnvComponents.py:280-301.  `t0` is the time stored with the entry that was just removed.
-  MUAV_HD void remove_agent_cap(int k, int a, double t0) {
+  MUAV_HD MUAV_NI_H void remove_agent_cap(int k, int a, double t0) {
     if (V.k_status()[k] == 2) return;
     int TC = V.L->D.TC;
-    for (int c = 0; c < 6; ++c) V.k_alloc()[c * TC + k] = V.k_alloc()[c * TC + k] - cap(a, c);
+    _Pragma("unroll 1") for (int c = 0; c < 6; ++c) V.k_alloc()[c * TC + k] = V.k_alloc()[c * TC + k] - cap(a, c);
     int tid = k + 1;
     int cnt = 0;
     double mn = 0.0, mx = 0.0;
@@ -174,11 +191,11 @@ struct Sim {
     }
   }
   // DroneEnvComponents.py:306-326 (the queue entry itself is pushed by the caller)
-  MUAV_HD void add_agent_cap(int k, int a, double time_at) {
+  MUAV_HD MUAV_NI_H void add_agent_cap(int k, int a, double time_at) {
     if (V.k_status()[k] == 2) return;
     int TC = V.L->D.TC;
     double end = time_at + (double)C().duration[V.k_type()[k]];
-    for (int c = 0; c < 6; ++c) V.k_alloc()[c * TC + k] = V.k_alloc()[c * TC + k] + cap(a, c);
+    _Pragma("unroll 1") for (int c = 0; c < 6; ++c) V.k_alloc()[c * TC + k] = V.k_alloc()[c * TC + k] + cap(a, c);
     if (time_at < V.k_init()[k] || V.k_init()[k] == -1.0) {
       V.k_init()[k] = time_at;
       if (V.k_dtime()[k] == -1.0) V.k_dtime()[k] = end;
@@ -189,13 +206,13 @@ struct Sim {
 
   // ------------------------------------------------------------------ UAV methods
   // UAV.allocate (DroneEnvComponents.py:55-95), task.id != 0
-  MUAV_HD bool allocate(int a, int tid) {
+  MUAV_HD MUAV_NI_H bool allocate(int a, int tid) {
     int k = tid - 1;
     if (qfind(a, tid) >= 0 || V.k_status()[k] == 2) return false;
     V.a_re_eval()[a] = 0;
     V.a_last_task()[a] = -1;
     double t = (double)HIv(T);
-    double time_to = norm2(V.a_nfpx()[a] - V.k_posx()[k], V.a_nfpy()[a] - V.k_posy()[k]) / speed_of(a);
+    double time_to = ddiv(norm2(V.a_nfpx()[a] - V.k_posx()[k], V.a_nfpy()[a] - V.k_posy()[k]), speed_of(a));
     double start = (V.a_nft()[a] - t) > 0 ? V.a_nft()[a] : t;
     double end = start + time_to + (double)C().duration[V.k_type()[k]];
     if (qlen(a) == 0) {
@@ -210,7 +227,7 @@ struct Sim {
     return true;
   }
   // UAV.desAllocate (DroneEnvComponents.py:97-113)
-  MUAV_HD bool des_allocate(int a, int tid) {
+  MUAV_HD MUAV_NI_H bool des_allocate(int a, int tid) {
     if (tid <= 0) return false;
     int s = qfind(a, tid);
     if (s < 0) return false;
@@ -224,7 +241,7 @@ struct Sim {
   }
   // UAV.desallocateAll (DroneEnvComponents.py:115-119): the reference iterates the list it mutates,
   // so only the entries at even positions are removed.
-  MUAV_HD void des_allocate_all(int a) {
+  MUAV_HD MUAV_NI_H void des_allocate_all(int a) {
     int i = 0;
     while (i < qlen(a)) {
       des_allocate(a, qat(a, i));
@@ -256,7 +273,7 @@ struct Sim {
     V.a_nfpy()[a] = V.a_posy()[a];
   }
   // UAV.taskDone (DroneEnvComponents.py:143-179); *t0 receives the popped entry's allocation time
-  MUAV_HD bool task_done(int a, int tid, double* t0) {
+  MUAV_HD MUAV_NI_H bool task_done(int a, int tid, double* t0) {
     if (qlen(a) == 0 || qat(a, 0) != tid) return false;
     *t0 = qremove(a, 0);
     V.a_task_start()[a] = -1;
@@ -296,7 +313,7 @@ struct Sim {
 
   // ------------------------------------------------------------------ WPS bookkeeping
   // _wps_mark_window_outcome (DroneEnv.py:1543-1555)
-  MUAV_HD void mark_outcome(int k, bool success) {
+  MUAV_HD MUAV_NI_H void mark_outcome(int k, bool success) {
     if (V.k_deadline()[k] < 0 || V.k_counted()[k]) return;
     V.k_counted()[k] = 1;
     if (success && HIv(T) <= V.k_deadline()[k]) {
@@ -320,7 +337,7 @@ struct Sim {
     V.k_posy()[k] = py;
     V.k_type()[k] = (int16_t)ti;
     V.k_status()[k] = 0;
-    for (int c = 0; c < 6; ++c) {
+    _Pragma("unroll 1") for (int c = 0; c < 6; ++c) {
       V.k_cur()[c * TC + k] = 0.0;
       V.k_alloc()[c * TC + k] = 0.0;
     }
@@ -345,7 +362,7 @@ struct Sim {
     return k + 1;
   }
   // _register_dynamic_task (DroneEnv.py:1491-1504)
-  MUAV_HD void register_dynamic(int tid) {
+  MUAV_HD MUAV_NI_H void register_dynamic(int tid) {
     int k = tid - 1;
     if (C().hard_windows && V.k_deadline()[k] < 0) {
       V.k_deadline()[k] = (int16_t)(HIv(T) + C().window_length);
@@ -359,7 +376,7 @@ struct Sim {
     }
   }
   // _counts_for_mission_done (DroneEnv.py:1878-1886)
-  MUAV_HD bool all_done() const {
+  MUAV_HD MUAV_NI_H bool all_done() const {
     int n = V.hi()[HI_N_TASKS];
     for (int k = 0; k < n; ++k) {
       int ti = V.k_type()[k];
@@ -412,7 +429,7 @@ struct Sim {
   }
 
   // get_closest_agent (DroneEnv.py:1691-1723)
-  MUAV_HD int closest_agent(double px, double py) const {
+  MUAV_HD MUAV_NI_H int closest_agent(double px, double py) const {
     double min_f = INFINITY, min_w = INFINITY;
     int cf = -1, cw = -1;
     for (int a = 0; a < A(); ++a) {
@@ -430,7 +447,7 @@ struct Sim {
   }
 
   // generate_threat + TaskFromThreat (DroneEnv.py:1601-1643,1861-1876)
-  MUAV_HD void generate_threat() {
+  MUAV_HD MUAV_NI_H void generate_threat() {
     int t = HIv(T);
     int TC = V.L->D.TC;
     for (int g = 0; g < C().n_groups; ++g) {
@@ -659,7 +676,7 @@ struct Sim {
   }
 
   // update_threats (DroneEnv.py:1725-1744)
-  MUAV_HD void update_threats() {
+  MUAV_HD MUAV_NI_H void update_threats() {
     int n = HIv(N_ACTIVE);
     for (int i = 0; i < n; ++i) {
       int hid = V.h_order()[i];
@@ -677,7 +694,7 @@ struct Sim {
         double dx = V.a_posx()[tg] - hx, dy = V.a_posy()[tg] - hy;
         double mag = norm2(dx, dy);
         double nx = 0.0, ny = 0.0;
-        if (mag != 0) { nx = dx / mag; ny = dy / mag; }
+        if (mag != 0) { nx = ddiv(dx, mag); ny = ddiv(dy, mag); }
         hx = hx + sp * nx;
         hy = hy + sp * ny;
         V.h_posx()[hid] = hx;
@@ -714,7 +731,7 @@ struct Sim {
   }
 
   // inject_dynamic_arrivals (DroneEnv.py:1646-1689); the rate draw precedes the capacity gate
-  MUAV_HD void inject_arrivals() {
+  MUAV_HD MUAV_NI_H void inject_arrivals() {
     if (C().arrival_rate <= 0 || HIv(T) < 5) return;
     if (rng_random(1) >= C().arrival_rate) return;
     if (HIv(N_TASKS) >= C().max_tasks - 1) return;
@@ -905,6 +922,7 @@ struct Sim {
     acc.quality_reward = 0.0;
     acc.S_q = 0.0;
     step_reward = 0.0;
+    MUAV_TICK_START();
     int Aa = A();
     int TC = V.L->D.TC;
     HIv(T) += 1;
@@ -934,6 +952,7 @@ struct Sim {
       if ((ev & 0xff) == EV_RESET) release_all((ev >> 8) - 1);
     }
 
+    MUAV_TICK(1);
     // ---- actions (DroneEnv.py:810-933)
     for (int i = 0; i < n_act; ++i) {
       int a = act_agent[i];
@@ -956,7 +975,7 @@ struct Sim {
           double ax = V.a_posx()[a], ay = V.a_posy()[a];
           double d_old = norm2(ax - V.k_posx()[head - 1], ay - V.k_posy()[head - 1]);
           double d_new = norm2(ax - V.k_posx()[k], ay - V.k_posy()[k]);
-          acc.distance_reward += (d_old - d_new) / C().max_coord;
+          acc.distance_reward += ddiv(d_old - d_new, C().max_coord);
         } else {
           acc.S_q += 0.05;
           if (HIv(PENDING_RESET) && C().dynamic_idle_penalty != 0.0) acc.S_q -= C().dynamic_idle_penalty;
@@ -993,12 +1012,13 @@ struct Sim {
           rx = V.a_posx()[a];
           ry = V.a_posy()[a];
         }
-        acc.distance_reward += -1.0 * norm2(V.a_nfpx()[a] - rx, V.a_nfpy()[a] - ry) / C().max_coord;
+        acc.distance_reward += ddiv(-1.0 * norm2(V.a_nfpx()[a] - rx, V.a_nfpy()[a] - ry), C().max_coord);
         if (V.a_state()[a] != 1 && V.a_state()[a] != -1) V.a_state()[a] = 1;
         if (C().escort_enabled && ti == TT_REC && is_recon(V.a_type()[a]) && V.a_escort()[a] == 0) create_escort_for(a, tid);
       }
     }
 
+    MUAV_TICK(2);
     // ---- kinematics FSM (DroneEnv.py:965-1129)
     const double bx = C().base_x, by = C().base_y;
     int nobs = V.L->D.NOBS;
@@ -1031,7 +1051,7 @@ struct Sim {
           double dx = tx - px, dy = ty - py;
           double d = norm2(dx, dy);
           double nx = 0.0, ny = 0.0;
-          if (!(fabs(d) < 1e-12)) { nx = dx / d; ny = dy / d; }
+          if (!(fabs(d) < 1e-12)) { nx = ddiv(dx, d); ny = ddiv(dy, d); }
           if (ti == TT_INT) {
             if (d < engage_of(a)) {
               V.a_state()[a] = 2;
@@ -1063,7 +1083,7 @@ struct Sim {
             double t0 = 0.0;
             bool popped = task_done(a, cur, &t0);
             V.k_done_ti()[k] = V.k_done_ti()[k] + cap(a, ti);
-            for (int c = 0; c < 6; ++c) V.k_cur()[c * TC + k] = V.k_cur()[c * TC + k] - cap(a, c);
+            _Pragma("unroll 1") for (int c = 0; c < 6; ++c) V.k_cur()[c * TC + k] = V.k_cur()[c * TC + k] - cap(a, c);
             if (popped) {
               remove_agent_cap(k, a, t0);
             } else if (qfind(a, cur) >= 0) {
@@ -1073,7 +1093,7 @@ struct Sim {
               if (V.k_kind()[k] != 1) mark_reached(k);
               if (V.k_status()[k] != 2) {
                 acc.quality_reward += V.k_org_ti()[k] * 2;
-                HFv(F_REWARD) += V.k_org_ti()[k] * 1 / HFv(NORM_FACTOR);
+                HFv(F_REWARD) += ddiv(V.k_org_ti()[k] * 1, HFv(NORM_FACTOR));
                 if (V.k_kind()[k] != 1) mark_outcome(k, true);
                 V.k_status()[k] = 2;
                 if (ti == TT_REC && is_recon(V.a_type()[a])) {
@@ -1097,14 +1117,14 @@ struct Sim {
           double dx = bx - px, dy = by - py;
           double mag = norm2(dx, dy);
           if (mag == 0) { mvx = 0.0; mvy = 0.0; }
-          else { mvx = dx / mag; mvy = dy / mag; }
+          else { mvx = ddiv(dx, mag); mvy = ddiv(dy, mag); }
           if (nobs > 0) avoid_obstacles(V.obst(), nobs, px, py, mvx, mvy, &avx, &avy);
         }
       }
       double sx = mvx + avx, sy = mvy + avy;
       double mag = norm2(sx, sy);
       double ux = 0.0, uy = 0.0;
-      if (mag != 0) { ux = sx / mag; uy = sy / mag; }
+      if (mag != 0) { ux = ddiv(sx, mag); uy = ddiv(sy, mag); }
       px = V.a_posx()[a] + ux * speed;
       py = V.a_posy()[a] + uy * speed;
       px = dmin(dmax(px, 0.0), C().area_w);
@@ -1113,6 +1133,7 @@ struct Sim {
       V.a_posy()[a] = py;
     }
 
+    MUAV_TICK(3);
     // ---- travelled distance (DroneEnv.py:1131-1138)
     for (int a = 0; a < Aa; ++a) {
       dists[a] = norm2_rows(V.a_posx()[a] - prev_x[a], V.a_posy()[a] - prev_y[a]);
@@ -1123,7 +1144,7 @@ struct Sim {
     // time_penaulty / alloc_reward are evaluated here in the reference (DroneEnv.py:1140-1145)
     {
       double nt = (double)C().n_tasks_cfg;
-      acc.time_pen = -(double)(C().n_tasks_cfg - HIv(N_REACHED)) / nt * ((double)t / (double)C().max_time_steps);
+      acc.time_pen = ddiv(-(double)(C().n_tasks_cfg - HIv(N_REACHED)), nt) * ddiv((double)t, (double)C().max_time_steps);
       acc.alloc_reward = 0.0;
       if (t > C().n_tasks_cfg + 1 && C().rw[5] != 0.0) {  // weight 0 (WPS flags): the count cannot reach the reward
         int unalloc = 1;  // bucket 0 (idle) is always empty
@@ -1134,10 +1155,13 @@ struct Sim {
       }
     }
 
+    MUAV_TICK(4);
     generate_threat();
     update_threats();
+    MUAV_TICK(5);
     inject_arrivals();
     if (C().escort_enabled) sync_escorts();
+    MUAV_TICK(6);
   }
 
   // ------------------------------------------------------------------ warp-parallel task scans
@@ -1199,7 +1223,7 @@ struct Sim {
   }
 #endif
 
-  MUAV_HD void expire_one(int k) {
+  MUAV_HD MUAV_NI_H void expire_one(int k) {
     V.k_status()[k] = 2;
     V.k_fq()[k] = 0;
     mark_outcome(k, false);
@@ -1227,8 +1251,8 @@ struct Sim {
     double time_reward = 0.0;
     double reward = (rw[0] * acc.action_reward + rw[1] * acc.distance_reward + rw[2] * acc.quality_reward +
                      rw[3] * acc.S_q + rw[4] * (double)C().n_tasks_cfg * time_reward + rw[5] * acc.alloc_reward +
-                     rw[6] * acc.time_pen + rw[7] * step_reward) /
-                    HFv(NORM_FACTOR) / (double)C().max_time_steps;
+                     rw[6] * acc.time_pen + rw[7] * step_reward);
+    reward = ddiv(ddiv(reward, HFv(NORM_FACTOR)), (double)C().max_time_steps);
     int t = HIv(T);
     int n = HIv(N_TASKS);
     bool alld = n > 0 && alld_scan;
@@ -1253,8 +1277,10 @@ struct Sim {
     Acc acc;  // meaningful on lane 0 only
     if (lane == 0) step_pre(act_agent, act_tid, n_act, acc);
     MUAV_WARP_SYNC();
+    MUAV_TICK_START();
     update_sensing(lane, nlanes);
     MUAV_WARP_SYNC();
+    MUAV_TICK(7);
     int n_open = 0;
     bool alld = true;
 #if defined(__CUDA_ARCH__)
@@ -1262,6 +1288,7 @@ struct Sim {
     expire_windows_warp(lane);
     __syncwarp();
     scan_open_warp(lane, &n_open, &alld);
+    MUAV_TICK(8);
 #else
     process_reveals();
     expire_windows();
@@ -1281,6 +1308,7 @@ struct Sim {
     r.reward = 0.0;
     r.terminated = r.truncated = 0;
     if (lane == 0) r = step_post(acc, alld, n_open);
+    MUAV_TICK(9);
     return r;
   }
 };

@@ -8,6 +8,8 @@
 // Compile with -fmad=false: every float64 operation must round exactly like the reference's.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "muav_alloc.cuh"
@@ -63,6 +65,7 @@ struct StepParams {
   const uint32_t* tapes;
   const int32_t* actions;
   int32_t* actions_out;  // allocate-only mode: ordered (agent, index) list per env
+  long long* phase_out;  // MUAV_PHASE_TIMING builds: 16 cycle counters summed over warps
   int n_envs, n_steps, tape_stride, use_bulk, alloc_only;
 };
 
@@ -109,11 +112,19 @@ __global__ void __launch_bounds__(32) muav_step_kernel(const __grid_constant__ S
   S.out_events = P.out.d_events ? P.out.d_events + (size_t)e * L.D.EVC : nullptr;
   S.n_out_events = 0;
   S.step_reward = 0.0;
+  S.phase_cycles = nullptr;
+#if defined(MUAV_PHASE_TIMING)
+  __shared__ long long phase_sh[16];
+  if (lane < 16) phase_sh[lane] = 0;
+  __syncwarp();
+  if (lane == 0) S.phase_cycles = phase_sh;
+  long long t_begin = clock64();
+#endif
   View& V = S.V;
   const int A = L.D.A;
 
   if (P.alloc_only) {
-    const int np = HIv(DONE) ? 0 : allocate_tasks(S, P.opts, e, act_agent, act_tid, lane, 32);
+    const int np = HIv(DONE) ? 0 : plan_and_allocate(S, P.opts, e, act_agent, act_tid, lane, 32);
     if (lane == 0) {
       if (P.out.d_n_pairs) P.out.d_n_pairs[e] = np;
       int n_act = 0;
@@ -137,7 +148,13 @@ __global__ void __launch_bounds__(32) muav_step_kernel(const __grid_constant__ S
   for (int s = 0; s < P.n_steps; ++s) {
     if (HIv(DONE)) break;
     int np = 0;
-    if (P.opts.mode != 0) np = allocate_tasks(S, P.opts, e, act_agent, act_tid, lane, 32);
+#if defined(MUAV_PHASE_TIMING)
+    long long t_al = clock64();
+#endif
+    if (P.opts.mode != 0) np = plan_and_allocate(S, P.opts, e, act_agent, act_tid, lane, 32);
+#if defined(MUAV_PHASE_TIMING)
+    if (lane == 0) phase_sh[0] += clock64() - t_al;
+#endif
     if (lane == 0) {
       int n_act = 0;
       if (P.opts.mode != 0) {
@@ -189,6 +206,12 @@ __global__ void __launch_bounds__(32) muav_step_kernel(const __grid_constant__ S
     }
   }
 
+#if defined(MUAV_PHASE_TIMING)
+  if (lane == 0 && P.phase_out) {
+    phase_sh[15] = clock64() - t_begin;
+    for (int i = 0; i < 16; ++i) atomicAdd((unsigned long long*)&P.phase_out[i], (unsigned long long)phase_sh[i]);
+  }
+#endif
   // ---- write the record back
   __syncwarp();
   if (P.use_bulk) {
@@ -322,6 +345,23 @@ int muav_step(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, 
   P.tape_stride = cfg->tape_words[0] + cfg->tape_words[1] + cfg->tape_words[2];
   const char* st = getenv("MUAV_STAGE");
   P.use_bulk = !(st && strcmp(st, "ldst") == 0);
+#if defined(MUAV_PHASE_TIMING)
+  {
+    static long long* d_phase = nullptr;
+    if (!d_phase) {
+      cudaMalloc(&d_phase, 16 * sizeof(long long));
+      cudaMemset(d_phase, 0, 16 * sizeof(long long));
+    }
+    P.phase_out = d_phase;
+    const char* dump = getenv("MUAV_PHASE_DUMP");
+    if (dump) {
+      long long h[16];
+      cudaMemcpy(h, d_phase, sizeof(h), cudaMemcpyDeviceToHost);
+      for (int i = 0; i < 16; ++i) fprintf(stderr, "phase %d %lld\n", i, h[i]);
+      cudaMemset(d_phase, 0, 16 * sizeof(long long));
+    }
+  }
+#endif
   return launch_step(P, stream);
 }
 

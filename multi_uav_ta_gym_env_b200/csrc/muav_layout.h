@@ -14,6 +14,17 @@
 #define MUAV_HD
 #define MUAV_NOINLINE __attribute__((noinline))
 #endif
+// tuning switches (see tools/kbench.py): out-of-line copies of the frequently used helpers / the allocator
+#if defined(MUAV_NI_HOT)
+#define MUAV_NI_H MUAV_NOINLINE
+#else
+#define MUAV_NI_H
+#endif
+#if defined(MUAV_NI_ALLOC)
+#define MUAV_NI_A MUAV_NOINLINE
+#else
+#define MUAV_NI_A
+#endif
 
 namespace muav {
 
@@ -111,6 +122,7 @@ MUAV_HD inline Dims dims_of(const muav_config& c) {
   X(a_type, int16_t, D.A)           \
   X(a_re_eval, int16_t, D.A)        \
   X(a_qlen, int16_t, D.A)           \
+  X(a_name_rank, int16_t, D.A)      \
   X(k_deadline, int16_t, D.TC)      \
   X(k_created, int16_t, D.TC)       \
   X(k_reveal, int16_t, D.TC)        \
@@ -152,6 +164,7 @@ MUAV_HD inline int32_t alloc_scratch_bytes(int A, int TC) {
   int M = A > TC ? A : TC;
   int b = 8 * (A * TC + 3 * M + TC + 4);
   b += 2 * (6 * M + 3 * A + 3 * TC);
+  b += 8 * TC + 8 * A + ((A + 7) / 8) * 8;  // planner priorities, lock scores, reserved mask
   return (b + 15) / 16 * 16;
 }
 

@@ -184,6 +184,12 @@ def pack_records(lib, cfg, scenarios) -> tuple[np.ndarray, np.ndarray]:
     view("a_caps")[:] = caps.transpose(0, 2, 1).reshape(E, 6 * A)
     ammo = np.where((atype == UAV_TYPES.index("F1")) | (atype == UAV_TYPES.index("F2")), 10, 0)
     view("a_ammo")[:] = ammo
+    ranks = np.zeros((E, A), dtype=np.int64)
+    for e, sc in enumerate(scenarios):
+        order = sorted(range(A), key=lambda a: sc.agent_names[a])
+        for r, a in enumerate(order):
+            ranks[e, a] = r
+    view("a_name_rank")[:] = ranks  # string order of the agent names (tie-break of UrgencyCommit's lock ranking)
     view("a_task_start")[:] = -1
     view("a_fail_event")[:] = np.array([s.fail_event for s in scenarios], dtype=np.int64)
     view("a_last_task")[:] = -1

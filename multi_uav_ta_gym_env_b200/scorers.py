@@ -7,6 +7,8 @@ noise (:266-278): scores = tanh(logits) * 0.35 * edge_valid.
 """
 from __future__ import annotations
 
+from typing import Optional
+
 import torch
 import torch.nn as nn
 
@@ -94,8 +96,9 @@ def att_pair_logits_split(net: AttPairNet, task_feats, task_mask, agent_feats, a
     tokens = torch.cat([a_emb, t_emb], dim=1)
     pad_mask = torch.cat([agent_mask, task_mask], dim=1)
     h = net.self_encoder(tokens, src_key_padding_mask=pad_mask)
-    a_h = h[:, : net.max_agents, :]
-    t_h = h[:, net.max_agents:, :]
+    n_a = agent_feats.shape[1]  # may be smaller than net.max_agents: padded agent rows carry no information
+    a_h = h[:, :n_a, :]
+    t_h = h[:, n_a:, :]
     a_ctx, _ = net.cross_a2t(a_h, t_h, t_h, key_padding_mask=task_mask, need_weights=False)
     t_ctx, _ = net.cross_t2a(t_h, a_h, a_h, key_padding_mask=agent_mask, need_weights=False)
     a_h = a_h + a_ctx
@@ -137,7 +140,12 @@ class GraphedPairScorer:
     is data dependent (padded rows are masked out downstream either way).
     """
 
-    def __init__(self, net: AttPairNet, n_envs: int, device, buckets=None, max_tasks: int = 32, max_agents: int = 16):
+    def __init__(self, net: AttPairNet, n_envs: int, device, buckets=None, max_tasks: int = 32, max_agents: int = 16,
+                 live_agents: Optional[int] = None):
+        """live_agents: upper bound of live agents (the fleet size).  Agent rows beyond it are always padding
+        (masked keys, masked logits, zero edge_valid), so they are dropped from the forward: the valid
+        outputs are unchanged up to fp32 summation order."""
+        self.n_a = min(max_agents, live_agents) if live_agents else max_agents
         if buckets is None:
             buckets = list(range(128, 1537, 128)) + [2048, 3072]
         self.net = net.eval()
@@ -154,6 +162,7 @@ class GraphedPairScorer:
                 "task_mask_u8": torch.ones(B, max_tasks, dtype=torch.uint8, device=device),
                 "agent_feats": torch.zeros(B, max_agents, AGENT_FEAT_DIM, device=device),
                 "agent_mask_u8": torch.ones(B, max_agents, dtype=torch.uint8, device=device),
+                "out_live": torch.zeros(B, self.n_a, max_tasks, device=device),
                 "edge_valid": torch.zeros(B, max_agents, max_tasks, device=device),
                 "out": torch.zeros(B, max_agents, max_tasks, device=device),
             }
@@ -162,10 +171,11 @@ class GraphedPairScorer:
             self.state[B] = {"bufs": bufs, "graph": None}
 
     def _forward(self, b):
+        n = self.n_a
         tok = {"task_feats": b["task_feats"], "task_mask": b["task_mask_u8"].bool(),
-               "agent_feats": b["agent_feats"], "agent_mask": b["agent_mask_u8"].bool(),
-               "edge_valid": b["edge_valid"]}
-        b["out"].copy_(pair_scores_fast(self.net, tok))
+               "agent_feats": b["agent_feats"][:, :n], "agent_mask": b["agent_mask_u8"][:, :n].bool(),
+               "edge_valid": b["edge_valid"][:, :n]}
+        b["out"][:, :n].copy_(pair_scores_fast(self.net, tok))
 
     def _graph(self, B):
         st = self.state[B]

@@ -16,6 +16,8 @@ Drivers (all restate the reference's own episode loops):
   pair_injected     experiments/wps_eval.py:226-230 via PairCostHybrid.plan(scores=...) with
                     deterministic injected edge scores (PairCostHybrid.py:308-328), replan rule :64-73
   random_actions    env.step driven by a seeded random policy (valid, stale and out-of-range indices)
+  urgency_commit    UrgencyCommit.plan (AttentionCommit.py:310-357) under the hybrid cadence wps_eval.py:64-73
+  urgency_coalition UrgencyCoalition.plan (AttentionEscort.py:720-767) under escort_eval.py:52-58, interval 12
 """
 from __future__ import annotations
 
@@ -76,6 +78,14 @@ def run_episode(case, seed, driver, overrides=None):
     if driver == "pair_injected":
         from TaskAllocation.Hybrid.PairCostHybrid import PairCostHybrid
         pair = PairCostHybrid(use_attention=False, device="cpu")
+    planner = None
+    if driver == "urgency_commit":
+        from TaskAllocation.Hybrid.AttentionCommit import UrgencyCommit
+        planner = UrgencyCommit()
+    elif driver == "urgency_coalition":
+        from TaskAllocation.Hybrid.AttentionEscort import UrgencyCoalition
+        planner = UrgencyCoalition()
+        hung = HungarianAllocator(replan_interval=10**9, max_coord=env.max_coord)
     rnd = random.Random(seed * 7919 + 13)
     ep = {"case": case, "seed": seed, "driver": driver, "overrides": overrides or {},
           "agent_names": [a.name for a in env.agents_obj],
@@ -94,6 +104,14 @@ def run_episode(case, seed, driver, overrides=None):
             if hybrid_should_replan(env, events):
                 sc = injected_scores(seed, env.time_steps, pair.max_agents, pair.max_tasks)
                 pairs = pair.plan(env, hung, events=events, explore=False, force=True, scores=sc)[0]
+        elif driver == "urgency_commit":
+            if hybrid_should_replan(env, events):
+                pairs = planner.plan(env, hung, events=events, force=True)[0]
+        elif driver == "urgency_coalition":
+            if (env.time_steps == 0 or env.time_steps % 12 == 0 or any(
+                    ev[0] in ("Reset_Allocation", "New_Threat", "Agent_Fail", "Escort_Created", "Escort_Retired")
+                    for ev in events)):
+                pairs = planner.plan(env, hung, events=events, force=True)
         actions = {}
         if driver == "random_actions":
             n_open = len(env.last_tasks_info)
@@ -142,6 +160,9 @@ PLAN = [
     ("wps_escort_random", "WPS_escort", "random_actions", range(0, 4), None),
     ("wps_attn_xl_local", "WPS_attn_XL", "local_hungarian", range(0, 2), None),
     ("wps_hard_single_task", "WPS_hard", "local_hungarian", range(0, 3), {"multiple_tasks_per_agent": False}),
+    ("wps_commit_urgency", "WPS_commit", "urgency_commit", range(0, 8), None),
+    ("wps_escort_urgency", "WPS_escort", "urgency_coalition", range(0, 6), None),
+    ("wps_hard_obstacles", "WPS_hard", "local_hungarian", range(0, 4), {"num_obstacles": 4}),
 ]
 
 

@@ -54,6 +54,12 @@ def alloc_opts_for(driver):
         O.pair_tokens = 1
         O.score_rows = 16
         O.score_cols = 32
+    elif driver == "urgency_commit":
+        O.mode, O.replan_interval, O.event_mask, O.use_visibility = 2, 15, 0b111, 1
+        O.planner, O.commit_fraction = 1, 0.35
+    elif driver == "urgency_coalition":
+        O.mode, O.replan_interval, O.event_mask, O.use_visibility = 2, 12, 0x1F, 1
+        O.planner = 2
     else:
         raise ValueError(driver)
     return O
@@ -209,6 +215,7 @@ class HostBackend:
         O = _lib.MuavAllocOpts()
         O.mode, O.replan_interval, O.event_mask = spec.mode, spec.replan_interval, spec.event_mask
         O.use_visibility, O.pair_tokens, O.max_coord = int(spec.use_visibility), int(spec.pair_tokens), spec.max_coord
+        O.planner, O.commit_fraction = spec.planner, spec.commit_fraction
         keep = []
         if scores is not None:
             sc = np.ascontiguousarray(scores, dtype=np.float64)

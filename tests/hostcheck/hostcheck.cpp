@@ -44,12 +44,13 @@ int hostcheck_step(const muav_config* cfg, void* records, const uint32_t* tapes,
     S.out_events = Z.d_events ? Z.d_events + (size_t)e * L.D.EVC : nullptr;
     S.n_out_events = 0;
     S.step_reward = 0.0;
+    S.phase_cycles = nullptr;
     View& V = S.V;
     for (int s = 0; s < n_steps; ++s) {
       if (HIv(DONE)) break;
       int n_act = 0;
       if (O.mode != 0) {
-        int np = allocate_tasks(S, O, e, act_agent, act_tid, 0, 1);
+        int np = plan_and_allocate(S, O, e, act_agent, act_tid, 0, 1);
         if (Z.d_n_pairs) Z.d_n_pairs[e] = np;
         if (Z.d_pairs)
           for (int i = 0; i < np; ++i) Z.d_pairs[(size_t)e * A + i] = ((int)act_agent[i] << 16) | (int)act_tid[i];
@@ -102,8 +103,9 @@ int hostcheck_allocate(const muav_config* cfg, void* records, const muav_alloc_o
     S.tape = nullptr;
     S.scratch = scratch;
     S.out_events = nullptr;
+    S.phase_cycles = nullptr;
     View& V = S.V;
-    int np = HIv(DONE) ? 0 : allocate_tasks(S, *opts, e, act_agent, act_tid, 0, 1);
+    int np = HIv(DONE) ? 0 : plan_and_allocate(S, *opts, e, act_agent, act_tid, 0, 1);
     if (Z.d_n_pairs) Z.d_n_pairs[e] = np;
     int n_act = 0;
     for (int i = 0; i < np; ++i) {

@@ -8,8 +8,9 @@ from helpers import alloc_opts_for, golden_config, injected_scores, load_golden
 
 STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit_local", "wps_escort_coalition",
               "wps_hard_global", "wps_hard_pair", "wps_commit_pair", "wps_hard_random", "wps_escort_random",
-              "wps_attn_xl_local", "wps_hard_single_task"]
-ALLOC_CASES = [c for c in STEP_CASES if "random" not in c]
+              "wps_attn_xl_local", "wps_hard_single_task", "wps_hard_obstacles"]
+# planner fixtures mutate commit_until between steps: they are replayed through the fused planner only
+ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + ["wps_commit_urgency", "wps_escort_urgency"]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)
@@ -46,7 +47,7 @@ def test_fused_allocator(hostcheck, name):
             assert env.pairs_of(e) == st["pairs"], (name, ep["seed"], t)
             assert env.reward[e] == float.fromhex(st["reward"])
             assert str(env.digest(e)) == st["digest"], (name, ep["seed"], t)
-    if drv != "pair_injected":
+    if drv not in ("pair_injected", "urgency_commit", "urgency_coalition"):
         for e, ep in enumerate(eps):
             assert env.codec.header(env.rec[e], "N_REPLANS") == ep["n_replans"]
 

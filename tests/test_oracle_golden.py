@@ -8,12 +8,14 @@ import refsnap
 from oracle.hungarian import OracleHungarian, apply_assign, open_tasks
 from oracle.sim import OracleEnv
 from oracle import tokens as otok
+from oracle import planners as oplan
 
 # (fixture, max episodes replayed on CPU -- keeps the CPU suite short; the GPU suite replays all)
 CASES = [
     ("wps_easy_local", 3), ("wps_hard_local", 4), ("wps_burst_local", 2), ("wps_commit_local", 2),
     ("wps_escort_coalition", 2), ("wps_hard_global", 2), ("wps_hard_pair", 3), ("wps_commit_pair", 1),
     ("wps_hard_random", 3), ("wps_escort_random", 1), ("wps_attn_xl_local", 1), ("wps_hard_single_task", 2),
+    ("wps_commit_urgency", 3), ("wps_escort_urgency", 2), ("wps_hard_obstacles", 2),
 ]
 
 
@@ -22,7 +24,7 @@ def replay(ep):
     o = OracleEnv(cfg).reset(ep["seed"])
     assert str(refsnap.digest(o.snapshot())) == ep["digest0"]
     drv = ep["driver"]
-    interval = 12 if drv == "coalition" else 20
+    interval = 12 if drv == "coalition" else (10**9 if drv == "urgency_coalition" else 20)
     hung = OracleHungarian(interval, o.max_coord)
     for t, st in enumerate(ep["steps"]):
         if drv in ("local_hungarian", "coalition", "global_hungarian"):
@@ -36,6 +38,16 @@ def replay(ep):
                 sc = injected_scores(ep["seed"], o.t, 16, 32)
                 pairs = otok.pair_plan(o, hung, sc)
             assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
+        elif drv == "urgency_commit":
+            pairs = []
+            if otok.hybrid_should_replan(o, o.last_events, 15):
+                pairs = oplan.urgency_commit_plan(o, hung)
+            assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
+        elif drv == "urgency_coalition":
+            pairs = []
+            if o.t == 0 or o.t % 12 == 0 or len(o.last_events) > 0:
+                pairs = oplan.urgency_coalition_plan(o, hung)
+            assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
         r, term, trunc, ev = o.step([tuple(a) for a in st["actions"]])
         assert [list(e) for e in ev] == st["events"], (ep["seed"], t)
         assert r == float.fromhex(st["reward"]), (ep["seed"], t)
@@ -46,7 +58,7 @@ def replay(ep):
     for k, v in ep["metrics"].items():
         want = float.fromhex(v) if isinstance(v, str) else v
         assert m[k] == want or (m[k] != m[k] and want != want), k
-    if drv != "pair_injected":
+    if drv not in ("pair_injected", "urgency_commit", "urgency_coalition"):
         assert hung.n_replans == ep["n_replans"]
 
 
