@@ -39,8 +39,16 @@ MUAV_HD inline bool is_recon(int ut) { return ut == UT_R1 || ut == UT_R2; }
 
 #if defined(__CUDA_ARCH__)
 #define MUAV_WARP_SYNC() __syncwarp()
+// Phase alignment of the warps (= environments) of one CTA: the kernel is instruction-fetch bound, so
+// warps that run the same phase at the same time share the fetched lines.  Purely a scheduling hint:
+// no data is exchanged between the warps.
+#define MUAV_CTA_SYNC(on) \
+  do {                    \
+    if (on) __syncthreads(); \
+  } while (0)
 #else
 #define MUAV_WARP_SYNC() ((void)0)
+#define MUAV_CTA_SYNC(on) ((void)0)
 #endif
 
 #if defined(MUAV_PHASE_TIMING) && defined(__CUDA_ARCH__)
@@ -916,7 +924,10 @@ struct Sim {
     double action_reward, distance_reward, quality_reward, S_q, time_pen, alloc_reward;
   };
 
-  MUAV_HD void step_pre(const int16_t* act_agent, const int16_t* act_tid, int n_act, Acc& acc) {
+  Acc acc;  // reward accumulators of the current step (meaningful on lane 0)
+
+  // step part 1a: events drain + ordered actions
+  MUAV_HD void step_pre_a(const int16_t* act_agent, const int16_t* act_tid, int n_act) {
     acc.action_reward = 0.0;
     acc.distance_reward = 0.0;
     acc.quality_reward = 0.0;
@@ -926,10 +937,8 @@ struct Sim {
     int Aa = A();
     int TC = V.L->D.TC;
     HIv(T) += 1;
-    int t = HIv(T);
     double* prev_x = (double*)scratch;
     double* prev_y = prev_x + Aa;
-    double* dists = prev_y + Aa;
     for (int a = 0; a < Aa; ++a) {
       prev_x[a] = V.a_posx()[a];
       prev_y[a] = V.a_posy()[a];
@@ -1019,7 +1028,14 @@ struct Sim {
     }
 
     MUAV_TICK(2);
-    // ---- kinematics FSM (DroneEnv.py:965-1129)
+  }
+
+  // step part 1b: kinematics FSM (DroneEnv.py:965-1129)
+  MUAV_HD void step_pre_b() {
+    MUAV_TICK_START();
+    const int Aa = A();
+    const int TC = V.L->D.TC;
+    const int t = HIv(T);
     const double bx = C().base_x, by = C().base_y;
     int nobs = V.L->D.NOBS;
     for (int a = 0; a < Aa; ++a) {
@@ -1134,6 +1150,16 @@ struct Sim {
     }
 
     MUAV_TICK(3);
+  }
+
+  // step part 1c: travelled distance, threats, arrivals, escorts
+  MUAV_HD void step_pre_c() {
+    MUAV_TICK_START();
+    const int Aa = A();
+    const int t = HIv(T);
+    double* prev_x = (double*)scratch;
+    double* prev_y = prev_x + Aa;
+    double* dists = prev_y + Aa;
     // ---- travelled distance (DroneEnv.py:1131-1138)
     for (int a = 0; a < Aa; ++a) {
       dists[a] = norm2_rows(V.a_posx()[a] - prev_x[a], V.a_posy()[a] - prev_y[a]);
@@ -1234,7 +1260,7 @@ struct Sim {
 
   // ------------------------------------------------------------------ step: part 3 (lane 0)
   // reserve tracking, reward, termination; `alld` / `n_open` come from the task scan
-  MUAV_HD StepResult step_post(const Acc& acc, bool alld_scan, int n_open) {
+  MUAV_HD StepResult step_post(bool alld_scan, int n_open) {
     int Aa = A();
     // _wps_track_reserve (DroneEnv.py:1575-1580) and the _pending_reset clear (:1156-1160)
     int idle = 0;
@@ -1273,42 +1299,53 @@ struct Sim {
   }
 
   // whole step.  Sequential phases run on lane 0, the task/agent scans are spread over the warp.
-  MUAV_HD StepResult step(const int16_t* act_agent, const int16_t* act_tid, int n_act, int lane, int nlanes) {
-    Acc acc;  // meaningful on lane 0 only
-    if (lane == 0) step_pre(act_agent, act_tid, n_act, acc);
+  // `alive` = this warp has an environment to step; `cta_sync` = align the CTA's warps between phases.
+  MUAV_HD StepResult step(const int16_t* act_agent, const int16_t* act_tid, int n_act, int lane, int nlanes,
+                          bool alive = true, bool cta_sync = false) {
+    if (alive && lane == 0) step_pre_a(act_agent, act_tid, n_act);
     MUAV_WARP_SYNC();
-    MUAV_TICK_START();
-    update_sensing(lane, nlanes);
+    MUAV_CTA_SYNC(cta_sync);
+    if (alive && lane == 0) step_pre_b();
     MUAV_WARP_SYNC();
-    MUAV_TICK(7);
-    int n_open = 0;
-    bool alld = true;
-#if defined(__CUDA_ARCH__)
-    process_reveals_warp(lane);
-    expire_windows_warp(lane);
-    __syncwarp();
-    scan_open_warp(lane, &n_open, &alld);
-    MUAV_TICK(8);
-#else
-    process_reveals();
-    expire_windows();
-    {
-      const int n = HIv(N_TASKS);
-      const int KW = V.L->D.KW;
-      for (int w = 0; w < KW; ++w) V.open_mask()[w] = 0;
-      for (int k = 0; k < n; ++k)
-        if (V.k_status()[k] != 2) {
-          V.open_mask()[k >> 5] |= 1u << (k & 31);
-          ++n_open;
-        }
-      alld = all_done();
-    }
-#endif
+    MUAV_CTA_SYNC(cta_sync);
+    if (alive && lane == 0) step_pre_c();
+    MUAV_WARP_SYNC();
+    MUAV_CTA_SYNC(cta_sync);
     StepResult r;
     r.reward = 0.0;
     r.terminated = r.truncated = 0;
-    if (lane == 0) r = step_post(acc, alld, n_open);
-    MUAV_TICK(9);
+    if (alive) {
+      MUAV_TICK_START();
+      update_sensing(lane, nlanes);
+      MUAV_WARP_SYNC();
+      MUAV_TICK(7);
+      int n_open = 0;
+      bool alld = true;
+#if defined(__CUDA_ARCH__)
+      process_reveals_warp(lane);
+      expire_windows_warp(lane);
+      __syncwarp();
+      scan_open_warp(lane, &n_open, &alld);
+      MUAV_TICK(8);
+#else
+      process_reveals();
+      expire_windows();
+      {
+        const int n = HIv(N_TASKS);
+        const int KW = V.L->D.KW;
+        for (int w = 0; w < KW; ++w) V.open_mask()[w] = 0;
+        for (int k = 0; k < n; ++k)
+          if (V.k_status()[k] != 2) {
+            V.open_mask()[k >> 5] |= 1u << (k & 31);
+            ++n_open;
+          }
+        alld = all_done();
+      }
+#endif
+      if (lane == 0) r = step_post(alld, n_open);
+      MUAV_TICK(9);
+    }
+    MUAV_CTA_SYNC(cta_sync);
     return r;
   }
 };

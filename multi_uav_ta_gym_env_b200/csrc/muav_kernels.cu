@@ -66,40 +66,51 @@ struct StepParams {
   const int32_t* actions;
   int32_t* actions_out;  // allocate-only mode: ordered (agent, index) list per env
   long long* phase_out;  // MUAV_PHASE_TIMING builds: 16 cycle counters summed over warps
-  int n_envs, n_steps, tape_stride, use_bulk, alloc_only;
+  int n_envs, n_steps, tape_stride, use_bulk, alloc_only, cta_warps;
 };
 
-// One warp (= one CTA) per environment.
-__global__ void __launch_bounds__(32) muav_step_kernel(const __grid_constant__ StepParams P) {
+#define MUAV_MAX_CTA_WARPS 16
+
+// One warp per environment; a CTA holds `cta_warps` environments whose warps are phase-aligned with
+// CTA barriers (no data is shared between them).
+__global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS) muav_step_kernel(const __grid_constant__ StepParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar;
-  __shared__ int16_t act_agent[MUAV_MAX_AGENTS];
-  __shared__ int16_t act_tid[MUAV_MAX_AGENTS];
-  __shared__ int n_act_s;
-  const int e = blockIdx.x;
-  const int lane = threadIdx.x;
-  if (e >= P.n_envs) return;
+  __shared__ __align__(8) uint64_t bar[MUAV_MAX_CTA_WARPS];
+  __shared__ int16_t act_agent_s[MUAV_MAX_CTA_WARPS][MUAV_MAX_AGENTS];
+  __shared__ int16_t act_tid_s[MUAV_MAX_CTA_WARPS][MUAV_MAX_AGENTS];
+  __shared__ int n_act_s[MUAV_MAX_CTA_WARPS];
+  const int W = P.cta_warps;
+  const int w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int e = blockIdx.x * W + w;
+  const bool has_env = e < P.n_envs;
+  const bool cta_sync = W > 1;
   const Layout& L = P.L;
-  char* rec = (char*)smem;
+  const int slot_bytes = L.record_bytes + L.scratch_bytes;
+  char* rec = (char*)smem + (size_t)w * slot_bytes;
   char* scratch = rec + L.record_bytes;
-  char* grec = P.records + (size_t)e * L.record_bytes;
+  char* grec = P.records + (size_t)(has_env ? e : 0) * L.record_bytes;
+  int16_t* act_agent = act_agent_s[w];
+  int16_t* act_tid = act_tid_s[w];
 
   // ---- stage the record into shared memory
-  if (P.use_bulk) {
-    if (lane == 0) {
-      mbar_init(&bar, 1);
-      fence_mbar_init();
+  if (has_env) {
+    if (P.use_bulk) {
+      if (lane == 0) {
+        mbar_init(&bar[w], 1);
+        fence_mbar_init();
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_expect_tx(&bar[w], (uint32_t)L.record_bytes);
+        bulk_g2s(rec, grec, (uint32_t)L.record_bytes, &bar[w]);
+      }
+      mbar_wait(&bar[w], 0);
+    } else {
+      const uint4* src = (const uint4*)grec;
+      uint4* dst = (uint4*)rec;
+      for (int i = lane; i < L.record_bytes / 16; i += 32) dst[i] = src[i];
     }
-    __syncwarp();
-    if (lane == 0) {
-      mbar_expect_tx(&bar, (uint32_t)L.record_bytes);
-      bulk_g2s(rec, grec, (uint32_t)L.record_bytes, &bar);
-    }
-    mbar_wait(&bar, 0);
-  } else {
-    const uint4* src = (const uint4*)grec;
-    uint4* dst = (uint4*)rec;
-    for (int i = lane; i < L.record_bytes / 16; i += 32) dst[i] = src[i];
   }
   __syncwarp();
 
@@ -107,23 +118,23 @@ __global__ void __launch_bounds__(32) muav_step_kernel(const __grid_constant__ S
   S.V.base = rec;
   S.V.L = &L;
   S.Cp = &P.cfg;
-  S.tape = P.tapes + (size_t)e * P.tape_stride;
+  S.tape = P.tapes + (size_t)(has_env ? e : 0) * P.tape_stride;
   S.scratch = scratch;
-  S.out_events = P.out.d_events ? P.out.d_events + (size_t)e * L.D.EVC : nullptr;
+  S.out_events = (P.out.d_events && has_env) ? P.out.d_events + (size_t)e * L.D.EVC : nullptr;
   S.n_out_events = 0;
   S.step_reward = 0.0;
   S.phase_cycles = nullptr;
 #if defined(MUAV_PHASE_TIMING)
   __shared__ long long phase_sh[16];
-  if (lane < 16) phase_sh[lane] = 0;
-  __syncwarp();
-  if (lane == 0) S.phase_cycles = phase_sh;
+  if (threadIdx.x < 16) phase_sh[threadIdx.x] = 0;
+  __syncthreads();
+  if (lane == 0 && w == 0) S.phase_cycles = phase_sh;
   long long t_begin = clock64();
 #endif
   View& V = S.V;
   const int A = L.D.A;
 
-  if (P.alloc_only) {
+  if (P.alloc_only && has_env) {
     const int np = HIv(DONE) ? 0 : plan_and_allocate(S, P.opts, e, act_agent, act_tid, lane, 32);
     if (lane == 0) {
       if (P.out.d_n_pairs) P.out.d_n_pairs[e] = np;
@@ -133,7 +144,7 @@ __global__ void __launch_bounds__(32) muav_step_kernel(const __grid_constant__ S
         if (P.actions_out && HIv(N_OPEN) > 0 && S.in_last_open(act_tid[i])) {
           // index of the task inside last_tasks_info = number of open tasks with a smaller id
           int k = act_tid[i] - 1, idx = 0;
-          for (int w = 0; w < (k >> 5); ++w) idx += __popc(V.open_mask()[w]);
+          for (int ww = 0; ww < (k >> 5); ++ww) idx += __popc(V.open_mask()[ww]);
           idx += __popc(V.open_mask()[k >> 5] & ((1u << (k & 31)) - 1u));
           P.actions_out[((size_t)e * A + n_act) * 2] = act_agent[i];
           P.actions_out[((size_t)e * A + n_act) * 2 + 1] = idx;
@@ -146,16 +157,16 @@ __global__ void __launch_bounds__(32) muav_step_kernel(const __grid_constant__ S
   }
 
   for (int s = 0; s < P.n_steps; ++s) {
-    if (HIv(DONE)) break;
+    const bool alive = has_env && !HIv(DONE);
     int np = 0;
 #if defined(MUAV_PHASE_TIMING)
     long long t_al = clock64();
 #endif
-    if (P.opts.mode != 0) np = plan_and_allocate(S, P.opts, e, act_agent, act_tid, lane, 32);
+    if (alive && P.opts.mode != 0) np = plan_and_allocate(S, P.opts, e, act_agent, act_tid, lane, 32);
 #if defined(MUAV_PHASE_TIMING)
-    if (lane == 0) phase_sh[0] += clock64() - t_al;
+    if (lane == 0 && w == 0) phase_sh[0] += clock64() - t_al;
 #endif
-    if (lane == 0) {
+    if (alive && lane == 0) {
       int n_act = 0;
       if (P.opts.mode != 0) {
         if (P.out.d_n_pairs) P.out.d_n_pairs[e] = np;
@@ -179,11 +190,12 @@ __global__ void __launch_bounds__(32) muav_step_kernel(const __grid_constant__ S
           ++n_act;
         }
       }
-      n_act_s = n_act;
+      n_act_s[w] = n_act;
     }
     __syncwarp();
-    StepResult r = S.step(act_agent, act_tid, n_act_s, lane, 32);
-    if (lane == 0) {
+    MUAV_CTA_SYNC(cta_sync);
+    StepResult r = S.step(act_agent, act_tid, alive ? n_act_s[w] : 0, lane, 32, alive, cta_sync);
+    if (alive && lane == 0) {
       if (P.out.d_reward) P.out.d_reward[e] = r.reward;
       if (P.out.d_terminated) P.out.d_terminated[e] = (uint8_t)r.terminated;
       if (P.out.d_truncated) P.out.d_truncated[e] = (uint8_t)r.truncated;
@@ -191,7 +203,7 @@ __global__ void __launch_bounds__(32) muav_step_kernel(const __grid_constant__ S
       if (P.out.d_n_open) P.out.d_n_open[e] = HIv(N_OPEN);
     }
     __syncwarp();
-    if (P.tok.d_need) {
+    if (P.tok.d_need && has_env) {
       const int iv = P.tok.interval > 0 ? P.tok.interval : 1;
       const bool need = !HIv(DONE) && ((HIv(T) % iv) == 0 || (HIv(EV_TAGMASK) & P.tok.event_mask) != 0);
       if (lane == 0) P.tok.d_need[e] = need ? 1 : 0;
@@ -207,24 +219,27 @@ __global__ void __launch_bounds__(32) muav_step_kernel(const __grid_constant__ S
   }
 
 #if defined(MUAV_PHASE_TIMING)
-  if (lane == 0 && P.phase_out) {
+  __syncthreads();
+  if (lane == 0 && w == 0 && P.phase_out) {
     phase_sh[15] = clock64() - t_begin;
     for (int i = 0; i < 16; ++i) atomicAdd((unsigned long long*)&P.phase_out[i], (unsigned long long)phase_sh[i]);
   }
 #endif
   // ---- write the record back
   __syncwarp();
-  if (P.use_bulk) {
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
-      bulk_s2g(grec, rec, (uint32_t)L.record_bytes);
-      bulk_wait_all();
+  if (has_env) {
+    if (P.use_bulk) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        bulk_s2g(grec, rec, (uint32_t)L.record_bytes);
+        bulk_wait_all();
+      }
+    } else {
+      const uint4* src = (const uint4*)rec;
+      uint4* dst = (uint4*)grec;
+      for (int i = lane; i < L.record_bytes / 16; i += 32) dst[i] = src[i];
     }
-  } else {
-    const uint4* src = (const uint4*)rec;
-    uint4* dst = (uint4*)grec;
-    for (int i = lane; i < L.record_bytes / 16; i += 32) dst[i] = src[i];
   }
 }
 
@@ -308,15 +323,27 @@ extern "C" {
 
 #include "muav_abi_common.inl"
 
-static int launch_step(const StepParams& P, void* stream) {
-  size_t smem = (size_t)P.L.record_bytes + (size_t)P.L.scratch_bytes;
+static int launch_step(StepParams& P, void* stream) {
+  const size_t slot = (size_t)P.L.record_bytes + (size_t)P.L.scratch_bytes;
+  // environments (warps) per CTA: two CTAs per SM (~113 KB of shared memory each); MUAV_CTA_WARPS overrides.
+  // Measured on B200, WPS_hard 4096 envs (tools/kbench.py): W=1 0.273 ms, 2 0.261, 4 0.231, 6 0.218, 12 0.218.
+  int W = (int)((113 * 1024) / slot);
+  const char* ev = getenv("MUAV_CTA_WARPS");
+  if (ev) W = atoi(ev);
+  if (W < 1) W = 1;
+  if (W > MUAV_MAX_CTA_WARPS) W = MUAV_MAX_CTA_WARPS;
+  while (W > 1 && slot * W > 200 * 1024) --W;
+  if (slot > 226 * 1024) return -12;
+  P.cta_warps = W;
+  const size_t smem = slot * W;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(muav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_rc(e);
     smem_set = smem;
   }
-  muav_step_kernel<<<P.n_envs, 32, smem, (cudaStream_t)stream>>>(P);
+  const int grid = (P.n_envs + W - 1) / W;
+  muav_step_kernel<<<grid, 32 * W, smem, (cudaStream_t)stream>>>(P);
   return cuda_rc(cudaGetLastError());
 }
 

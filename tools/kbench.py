@@ -14,10 +14,19 @@ from multi_uav_ta_gym_env_b200 import AllocSpec, BatchedMultiUAVEnv, wps_config 
 case = sys.argv[1] if len(sys.argv) > 1 else "WPS_hard"
 E = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 interval = 12 if case == "WPS_escort" else 20
-env = BatchedMultiUAVEnv(wps_config(case), E).reset(range(E))
+if case.startswith("burst_x"):
+    from multi_uav_ta_gym_env_b200 import burst_scaled_spec
+    cfg = wps_config(burst_scaled_spec(int(case[7:])))
+else:
+    cfg = wps_config(case)
+env = BatchedMultiUAVEnv(cfg, E).reset(range(E))
 spec = AllocSpec(1, interval, 0x1F, True, False)
+if len(sys.argv) > 3 and sys.argv[3] == "urgency_commit":
+    spec = AllocSpec.urgency_commit(15)
+if len(sys.argv) > 3 and sys.argv[3] == "urgency_coalition":
+    spec = AllocSpec.urgency_coalition(12)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-res = {"case": case, "envs": E, "record_bytes": env.record_bytes}
+res = {"case": case, "envs": E, "record_bytes": env.record_bytes, "agents": env.n_agents, "task_cap": env.task_cap}
 
 
 def run(flush_l2, nsteps=150):
