@@ -170,7 +170,7 @@ def run_gpu_arm(args):
     import torch.distributed as dist
 
     from multi_uav_ta_gym_env_b200 import AllocSpec, BatchedMultiUAVEnv, sharding, wps_config
-    from multi_uav_ta_gym_env_b200.scorers import AttPairNet, GraphedPairScorer
+    from multi_uav_ta_gym_env_b200.scorers import AttPairNet, FusedAttPairScorer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -191,8 +191,7 @@ def run_gpu_arm(args):
     scores = torch.zeros(E, 16, 32, dtype=torch.float32, device=dev)
     # the step kernel emits the pair tokens of every env that will replan before the next step
     tok = env.enable_fused_tokens(32, 16, HYBRID_INTERVAL, 0b111)
-    scorer = GraphedPairScorer(net, E, dev, live_agents=env.n_agents)
-    scorer.warm()
+    scorer = FusedAttPairScorer(net, dev)   # hand-written fused forward (csrc/muav_scorer.cu)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     metric_acc = torch.zeros(32, dtype=torch.float64, device=dev)
     names = env.lib.metric_names()
@@ -203,11 +202,10 @@ def run_gpu_arm(args):
         if t == 0:
             env.refresh_fused_tokens()  # episode start: standalone token kernel for all envs
             launches["n"] += 1
-        if t % HYBRID_INTERVAL == 0:
-            scorer.score_all(tok, scores)
-            return
-        idx = tok["need"].nonzero(as_tuple=True)[0]   # one 4-byte sync: how many environments replan now
-        scorer.score_subset(tok, idx, scores)
+        # every environment whose replan rule fires (need flag set by the step kernel) is scored; the others are
+        # skipped on the device, so there is no host synchronisation in the loop
+        scorer.score(tok, scores, use_need=True)
+        launches["n"] += 1
 
     def episode_end():
         m = env.metrics()

@@ -175,6 +175,24 @@ int muav_observe(const muav_config* cfg, const void* d_records, int max_rows, do
                  uint8_t* d_legal_mask, double* d_agent_obs, float* d_event_flags, int32_t* d_n_rows, int n_envs,
                  void* stream);
 
+/* Fused Att-Pair scorer forward (AttPairNet, PairCostHybrid.py:89-151; scores = tanh(logits) * clamp * edge_valid,
+ * :266-278) for n environments in one launch.  d_params: the module's float32 parameters packed in one buffer,
+ * offsets (in floats) below; d_env_idx: optional list of environment indices (NULL = 0..n-1) into the token tensors
+ * and d_scores [E, max_agents, max_tasks]; d_need: optional [E] flags (muav_token_out.d_need) -- environments whose flag
+ * is 0 are skipped on the device, so no host synchronisation is needed to select the replanning subset.
+ * d_model 64, 4 heads, 1 encoder layer, feed-forward 128 are fixed. */
+typedef struct muav_attpair_offsets {
+  int32_t agent_proj_w, agent_proj_b, task_proj_w, task_proj_b, type_embed;
+  int32_t enc_in_w, enc_in_b, enc_out_w, enc_out_b, enc_l1_w, enc_l1_b, enc_l2_w, enc_l2_b;
+  int32_t enc_n1_w, enc_n1_b, enc_n2_w, enc_n2_b;
+  int32_t a2t_in_w, a2t_in_b, a2t_out_w, a2t_out_b, t2a_in_w, t2a_in_b, t2a_out_w, t2a_out_b;
+  int32_t head1_w, head1_b, head2_w, head2_b, head3_w, head3_b;
+} muav_attpair_offsets;
+int muav_att_pair_scores(const float* d_params, const muav_attpair_offsets* offsets, const float* d_task_feats,
+                         const uint8_t* d_task_mask, const float* d_agent_feats, const uint8_t* d_agent_mask,
+                         const float* d_edge_valid, const int32_t* d_env_idx, const uint8_t* d_need, int n, int max_tasks,
+                         int max_agents, float score_clamp, float* d_scores, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,11 +75,21 @@ class MuavTokenOut(C.Structure):
     ]
 
 
+class MuavAttPairOffsets(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "agent_proj_w", "agent_proj_b", "task_proj_w", "task_proj_b", "type_embed",
+        "enc_in_w", "enc_in_b", "enc_out_w", "enc_out_b", "enc_l1_w", "enc_l1_b", "enc_l2_w", "enc_l2_b",
+        "enc_n1_w", "enc_n1_b", "enc_n2_w", "enc_n2_b",
+        "a2t_in_w", "a2t_in_b", "a2t_out_w", "a2t_out_b", "t2a_in_w", "t2a_in_b", "t2a_out_w", "t2a_out_b",
+        "head1_w", "head1_b", "head2_w", "head2_b", "head3_w", "head3_b")]
+
+
 # every symbol include/muav.h declares
 ABI_SYMBOLS = [
     "muav_version", "muav_config_size", "muav_record_bytes", "muav_scratch_bytes", "muav_num_fields",
     "muav_field_info", "muav_header_index", "muav_step", "muav_allocate", "muav_step_host", "muav_lsap",
     "muav_avoid_obstacles", "muav_metric_name", "muav_metrics", "muav_tokens_pair", "muav_observe",
+    "muav_att_pair_scores",
 ]
 
 
@@ -177,6 +187,9 @@ class CudaLib(Lib):
         d.muav_metrics.argtypes = [C.POINTER(MuavConfig), P, P, C.c_int, P]
         d.muav_tokens_pair.restype = C.c_int
         d.muav_tokens_pair.argtypes = [C.POINTER(MuavConfig), P, C.c_int, C.c_int, P, P, P, P, P, P, C.c_int, P]
+        d.muav_att_pair_scores.restype = C.c_int
+        d.muav_att_pair_scores.argtypes = [P, C.POINTER(MuavAttPairOffsets), P, P, P, P, P, P, P, C.c_int, C.c_int,
+                                           C.c_int, C.c_float, P, P]
         d.muav_observe.restype = C.c_int
         d.muav_observe.argtypes = [C.POINTER(MuavConfig), P, C.c_int, P, P, P, P, P, P, C.c_int, P]
 

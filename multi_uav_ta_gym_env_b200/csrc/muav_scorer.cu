@@ -1,0 +1,326 @@
+// Fused Att-Pair scorer forward (AttPairNet, TaskAllocation/Hybrid/PairCostHybrid.py:89-151, then
+// scores = tanh(logits) * clamp * edge_valid, :266-278) as ONE kernel: one CTA per environment, every
+// activation in shared memory, weights streamed from L2 (the whole network is 330 KB).
+//
+// Same function and parameters as the PyTorch module (fp32, FMA allowed like cuBLAS); differences are
+// summation order only (tests: <= 2e-5 on scores).  Work that the reference spends on padding is skipped:
+// only the live agents (rows with agent_mask == 0) and the valid task columns (task_mask == 0) are
+// tokens -- padded tokens are masked keys / masked logits in the module, so they never influence a
+// valid output.
+//
+// This translation unit is compiled WITHOUT -fmad=false (unlike muav_kernels.cu): it is float32 network
+// arithmetic, not the bit-exact float64 simulation.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/muav.h"
+
+namespace muav_scorer {
+
+constexpr int D = 64;      // d_model
+constexpr int NH = 4;      // heads
+constexpr int HD = 16;     // head dim
+constexpr int FF = 128;    // dim_feedforward
+constexpr int TS = 52;     // token stride of transposed activations [feature][token] (>= 48, multiple of 4)
+constexpr int WS = 68;     // row stride of the staged transposed weight tile [k][o]
+constexpr int NT = 256;    // threads per CTA
+constexpr int TF = 13, AF = 12;
+
+struct Params {
+  const float* w;  // packed parameters
+  muav_attpair_offsets o;
+  const float* task_feats;
+  const uint8_t* task_mask;
+  const float* agent_feats;
+  const uint8_t* agent_mask;
+  const float* edge_valid;
+  const int32_t* env_idx;
+  const uint8_t* need;
+  float* scores;
+  int n, max_tasks, max_agents;
+  float clamp;
+};
+
+// out_t[o][r] = act( sum_k in_t[k][r] * W[o][k] + b[o] (+ res_t[o][r]) ), r < R, o < O.
+// W is row-major in global memory with row stride ldw; the tile W^T is staged in `wt` ([K<=64][WS]).
+// Each thread owns a 4 (tokens) x 4 (outputs) register tile.
+__device__ void linear_t(const float* __restrict__ in_t, int R, int K, const float* __restrict__ Wg, int ldw,
+                         const float* __restrict__ bg, int O, float* __restrict__ out_t, float* __restrict__ wt,
+                         const float* __restrict__ res_t, bool relu, bool accumulate) {
+  const int tid = threadIdx.x;
+  const int og = tid & 15, rg = tid >> 4;
+  const int r4 = rg * 4;
+  for (int o0 = 0; o0 < O; o0 += 64) {
+    const int ow = (O - o0) < 64 ? (O - o0) : 64;
+    __syncthreads();
+    for (int idx = tid; idx < ow * K; idx += NT) {
+      const int o = idx / K, k = idx - o * K;
+      wt[k * WS + o] = Wg[(size_t)(o0 + o) * ldw + k];
+    }
+    __syncthreads();
+    const int o4 = og * 4;
+    if (r4 < R && o4 < ow) {
+      float acc[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float b = (bg && !accumulate) ? bg[o0 + o4 + j] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = b;
+      }
+      for (int k = 0; k < K; ++k) {
+        const float4 a = *(const float4*)&in_t[k * TS + r4];
+        const float4 w = *(const float4*)&wt[k * WS + o4];
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(av[i], wv[j], acc[j][i]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float* dst = &out_t[(o0 + o4 + j) * TS + r4];
+        float4 v = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+        if (accumulate) {
+          const float4 p = *(const float4*)dst;
+          v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+        }
+        if (res_t) {
+          const float4 p = *(const float4*)&res_t[(o0 + o4 + j) * TS + r4];
+          v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+        }
+        if (relu) {
+          v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
+        }
+        *(float4*)dst = v;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// LayerNorm over the feature axis (eps 1e-5, biased variance), in place on x_t[D][TS]
+__device__ void layer_norm_t(float* x_t, int R, const float* __restrict__ g, const float* __restrict__ b) {
+  const int r = threadIdx.x;
+  if (r < R) {
+    float mean = 0.0f;
+    for (int k = 0; k < D; ++k) mean += x_t[k * TS + r];
+    mean *= (1.0f / D);
+    float var = 0.0f;
+    for (int k = 0; k < D; ++k) {
+      const float d = x_t[k * TS + r] - mean;
+      var = fmaf(d, d, var);
+    }
+    const float inv = rsqrtf(var * (1.0f / D) + 1e-5f);
+    for (int k = 0; k < D; ++k) x_t[k * TS + r] = (x_t[k * TS + r] - mean) * inv * g[k] + b[k];
+  }
+  __syncthreads();
+}
+
+// softmax(q k^T / sqrt(HD)) v for queries [q0, q1) against keys [k0, k1); qkv_t rows: q 0..63, k 64..127, v 128..191
+__device__ void attention_t(const float* __restrict__ qkv_t, int q0, int q1, int k0, int k1, float* __restrict__ out_t) {
+  const int h = threadIdx.x >> 6;
+  const int i = q0 + (threadIdx.x & 63);
+  if (i < q1) {
+    float q[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) q[d] = qkv_t[(h * HD + d) * TS + i] * 0.25f;
+    float m = -INFINITY;
+    for (int j = k0; j < k1; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) s = fmaf(q[d], qkv_t[(D + h * HD + d) * TS + j], s);
+      m = fmaxf(m, s);
+    }
+    float l = 0.0f;
+    float acc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = 0.0f;
+    for (int j = k0; j < k1; ++j) {
+      float s = 0.0f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) s = fmaf(q[d], qkv_t[(D + h * HD + d) * TS + j], s);
+      const float p = __expf(s - m);
+      l += p;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc[d] = fmaf(p, qkv_t[(2 * D + h * HD + d) * TS + j], acc[d]);
+    }
+    const float inv = 1.0f / l;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) out_t[(h * HD + d) * TS + i] = acc[d] * inv;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT) att_pair_kernel(const __grid_constant__ Params P) {
+  extern __shared__ __align__(16) float sm[];
+  float* x_t = sm;                       // [D][TS]   tokens / encoder output h
+  float* y_t = x_t + D * TS;             // [D][TS]   attention output / residual sums / a_h', t_h'
+  float* z_t = y_t + D * TS;             // [D][TS]   scratch (cross contexts, ha / ht)
+  float* big_t = z_t + D * TS;           // [3D][TS]  qkv or FF hidden
+  float* wt = big_t + 3 * D * TS;        // [64][WS]  staged weight tile
+  __shared__ int s_na, s_nt;
+  const int tid = threadIdx.x;
+  const int b = blockIdx.x;
+  if (b >= P.n) return;
+  const int e = P.env_idx ? P.env_idx[b] : b;
+  if (P.need && !P.need[e]) return;  // this environment does not replan now: its score rows stay as they are
+  const int MT = P.max_tasks, MA = P.max_agents;
+  const float* w = P.w;
+  const muav_attpair_offsets& o = P.o;
+  const uint8_t* am = P.agent_mask + (size_t)e * MA;
+  const uint8_t* tm = P.task_mask + (size_t)e * MT;
+  if (tid == 0) {
+    int na = 0, nt = 0;
+    while (na < MA && am[na] == 0) ++na;  // valid rows / columns are a prefix by construction of the token builders
+    while (nt < MT && tm[nt] == 0) ++nt;
+    s_na = na;
+    s_nt = nt;
+  }
+  __syncthreads();
+  const int na = s_na, nt = s_nt;
+  const int R = na + nt;
+  float* sc = P.scores + (size_t)e * MA * MT;
+  for (int idx = tid; idx < MA * MT; idx += NT) sc[idx] = 0.0f;
+  if (na == 0 || nt == 0) return;
+
+  // ---- token embeddings: x = proj(feats) + type_embed  (PairCostHybrid.py:131-133)
+  // Linear layers act on each token independently and the register tiles are 4 tokens wide, so token
+  // columns beyond the valid range may hold anything: they never reach a valid output.
+  for (int idx = tid; idx < AF * na; idx += NT) {
+    const int r = idx / AF, k = idx - r * AF;
+    big_t[k * TS + r] = P.agent_feats[((size_t)e * MA + r) * AF + k];
+  }
+  for (int idx = tid; idx < TF * nt; idx += NT) {
+    const int r = idx / TF, k = idx - r * TF;
+    z_t[k * TS + r] = P.task_feats[((size_t)e * MT + r) * TF + k];
+  }
+  __syncthreads();
+  linear_t(big_t, na, AF, w + o.agent_proj_w, AF, w + o.agent_proj_b, D, x_t, wt, nullptr, false, false);  // agents -> x[:, :na]
+  linear_t(z_t, nt, TF, w + o.task_proj_w, TF, w + o.task_proj_b, D, y_t, wt, nullptr, false, false);       // tasks  -> y[:, :nt]
+  for (int idx = tid; idx < D * R; idx += NT) {
+    const int k = idx / R, r = idx - k * R;
+    if (r < na) x_t[k * TS + r] += w[o.type_embed + k];
+    else x_t[k * TS + r] = y_t[k * TS + (r - na)] + w[o.type_embed + D + k];
+  }
+  __syncthreads();
+
+  // ---- TransformerEncoderLayer (post-norm, relu, eval): x1 = LN1(x + SA(x)); x2 = LN2(x1 + FF(x1))
+  linear_t(x_t, R, D, w + o.enc_in_w, D, w + o.enc_in_b, 3 * D, big_t, wt, nullptr, false, false);
+  attention_t(big_t, 0, R, 0, R, y_t);
+  linear_t(y_t, R, D, w + o.enc_out_w, D, w + o.enc_out_b, D, z_t, wt, x_t, false, false);   // z = x + out_proj(attn)
+  layer_norm_t(z_t, R, w + o.enc_n1_w, w + o.enc_n1_b);                                    // z = x1
+  linear_t(z_t, R, D, w + o.enc_l1_w, D, w + o.enc_l1_b, FF, big_t, wt, nullptr, true, false);  // hidden
+  // linear2: K = 128 > 64 -> two accumulating passes over the hidden features
+  linear_t(big_t, R, 64, w + o.enc_l2_w, FF, w + o.enc_l2_b, D, x_t, wt, z_t, false, false);      // x = x1 + b + W[:, :64] h[:64]
+  linear_t(big_t + 64 * TS, R, 64, w + o.enc_l2_w + 64, FF, nullptr, D, x_t, wt, nullptr, false, true);
+  layer_norm_t(x_t, R, w + o.enc_n2_w, w + o.enc_n2_b);                                    // x = h (encoder output)
+
+  // ---- cross attention (both use the ORIGINAL h): a' = a + MHA_a2t(a, t, t); t' = t + MHA_t2a(t, a, a)
+  linear_t(x_t, R, D, w + o.a2t_in_w, D, w + o.a2t_in_b, 3 * D, big_t, wt, nullptr, false, false);
+  attention_t(big_t, 0, na, na, R, y_t);
+  __syncthreads();
+  linear_t(y_t, na, D, w + o.a2t_out_w, D, w + o.a2t_out_b, D, z_t, wt, x_t, false, false);  // z[:, :na] = a'
+  linear_t(x_t, R, D, w + o.t2a_in_w, D, w + o.t2a_in_b, 3 * D, big_t, wt, nullptr, false, false);
+  attention_t(big_t, na, R, 0, na, y_t);
+  // out-projection of the task rows: the register tiles start at token 0, rows < na are recomputed garbage
+  // that is discarded (y_t rows < na still hold the a2t attention output; harmless)
+  linear_t(y_t, R, D, w + o.t2a_out_w, D, w + o.t2a_out_b, D, big_t, wt, x_t, false, false);  // big[:, na:R] = t'
+  for (int idx = tid; idx < D * nt; idx += NT) {
+    const int k = idx / nt, r = idx - k * nt;
+    z_t[k * TS + na + r] = big_t[k * TS + na + r];
+  }
+  __syncthreads();
+  // z_t now holds [a' | t'] for tokens [0, R)
+
+  // ---- pair head: logits[i, j] = w3 . relu(W2 relu(Wat (a_i * t_j) + Wa a_i + Wt t_j + b1) + b2) + b3
+  // ha[o][i] (agents) and ht[o][j] (tasks, with bias) share one buffer y_t: columns [0,na) / [na,R)
+  linear_t(z_t, R, D, w + o.head1_w, 3 * D, nullptr, D, y_t, wt, nullptr, false, false);             // Wa x for all tokens
+  linear_t(z_t, R, D, w + o.head1_w + D, 3 * D, w + o.head1_b, D, x_t, wt, nullptr, false, false);   // Wt x + b1 for all tokens
+  // stage Wat [o][d] (row-major, stride WS) and W2^T [o][p]
+  float* wat = big_t;               // [64][WS]
+  float* w2t = big_t + 64 * WS;     // [64][36]
+  for (int idx = tid; idx < D * D; idx += NT) {
+    const int oo = idx >> 6, d = idx & 63;
+    wat[oo * WS + d] = w[o.head1_w + (size_t)oo * 3 * D + 2 * D + d];
+  }
+  for (int idx = tid; idx < 32 * D; idx += NT) {
+    const int p = idx >> 6, oo = idx & 63;
+    w2t[oo * 36 + p] = w[o.head2_w + (size_t)p * D + oo];
+  }
+  __syncthreads();
+  const float* ev = P.edge_valid + (size_t)e * MA * MT;
+  for (int pair = tid; pair < na * nt; pair += NT) {
+    const int i = pair / nt, j = pair - i * nt;
+    float u[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) u[d] = z_t[d * TS + i] * z_t[d * TS + na + j];
+    float h2[32];
+#pragma unroll
+    for (int p = 0; p < 32; ++p) h2[p] = w[o.head2_b + p];
+    for (int oo = 0; oo < D; ++oo) {
+      float acc = y_t[oo * TS + i] + x_t[oo * TS + na + j];
+      const float4* wr = (const float4*)&wat[oo * WS];
+#pragma unroll
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 ww = wr[d4];
+        acc = fmaf(ww.x, u[4 * d4], acc);
+        acc = fmaf(ww.y, u[4 * d4 + 1], acc);
+        acc = fmaf(ww.z, u[4 * d4 + 2], acc);
+        acc = fmaf(ww.w, u[4 * d4 + 3], acc);
+      }
+      acc = fmaxf(acc, 0.0f);
+      const float4* w2 = (const float4*)&w2t[oo * 36];
+#pragma unroll
+      for (int p4 = 0; p4 < 8; ++p4) {
+        const float4 ww = w2[p4];
+        h2[4 * p4] = fmaf(ww.x, acc, h2[4 * p4]);
+        h2[4 * p4 + 1] = fmaf(ww.y, acc, h2[4 * p4 + 1]);
+        h2[4 * p4 + 2] = fmaf(ww.z, acc, h2[4 * p4 + 2]);
+        h2[4 * p4 + 3] = fmaf(ww.w, acc, h2[4 * p4 + 3]);
+      }
+    }
+    float logit = w[o.head3_b];
+#pragma unroll
+    for (int p = 0; p < 32; ++p) logit = fmaf(w[o.head3_w + p], fmaxf(h2[p], 0.0f), logit);
+    sc[i * MT + j] = tanhf(logit) * P.clamp * ev[i * MT + j];
+  }
+}
+
+}  // namespace muav_scorer
+
+extern "C" int muav_att_pair_scores(const float* d_params, const muav_attpair_offsets* offsets, const float* d_task_feats,
+                                    const uint8_t* d_task_mask, const float* d_agent_feats, const uint8_t* d_agent_mask,
+                                    const float* d_edge_valid, const int32_t* d_env_idx, const uint8_t* d_need, int n,
+                                    int max_tasks, int max_agents, float score_clamp, float* d_scores, void* stream) {
+  using namespace muav_scorer;
+  if (!d_params || !offsets || !d_task_feats || !d_task_mask || !d_agent_feats || !d_agent_mask || !d_edge_valid || !d_scores)
+    return -22;
+  if (n < 0 || max_tasks < 1 || max_agents < 1 || max_agents + max_tasks > 48 || max_agents > 16) return -22;
+  if (n == 0) return 0;
+  Params P;
+  P.w = d_params;
+  P.o = *offsets;
+  P.task_feats = d_task_feats;
+  P.task_mask = d_task_mask;
+  P.agent_feats = d_agent_feats;
+  P.agent_mask = d_agent_mask;
+  P.edge_valid = d_edge_valid;
+  P.env_idx = d_env_idx;
+  P.need = d_need;
+  P.scores = d_scores;
+  P.n = n;
+  P.max_tasks = max_tasks;
+  P.max_agents = max_agents;
+  P.clamp = score_clamp;
+  const size_t smem = sizeof(float) * (size_t)(3 * D * TS + 3 * D * TS + 64 * WS);
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(att_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -1000 - (int)e;
+    set = true;
+  }
+  att_pair_kernel<<<n, NT, smem, (cudaStream_t)stream>>>(P);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -1000 - (int)e;
+}

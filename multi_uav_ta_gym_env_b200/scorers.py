@@ -218,3 +218,77 @@ class GraphedPairScorer:
             torch.index_select(tok[k], 0, idx, out=b[k][:n])
         self._graph(B).replay()
         scores_out.index_copy_(0, idx, b["out"][:n])
+
+
+class FusedAttPairScorer:
+    """AttPairNet forward as one CUDA kernel (csrc/muav_scorer.cu, C ABI muav_att_pair_scores): one CTA per
+    environment, only live agents / valid task columns are tokens, scores are written straight into the
+    [E, max_agents, max_tasks] tensor the allocator reads (no gather / scatter, no intermediates in HBM).
+    Parameters are the module's own (packed once); arithmetic is fp32 like the module."""
+
+    _ORDER = [
+        ("agent_proj_w", "agent_proj.weight"), ("agent_proj_b", "agent_proj.bias"),
+        ("task_proj_w", "task_proj.weight"), ("task_proj_b", "task_proj.bias"), ("type_embed", "type_embed.weight"),
+        ("enc_in_w", "self_encoder.layers.0.self_attn.in_proj_weight"),
+        ("enc_in_b", "self_encoder.layers.0.self_attn.in_proj_bias"),
+        ("enc_out_w", "self_encoder.layers.0.self_attn.out_proj.weight"),
+        ("enc_out_b", "self_encoder.layers.0.self_attn.out_proj.bias"),
+        ("enc_l1_w", "self_encoder.layers.0.linear1.weight"), ("enc_l1_b", "self_encoder.layers.0.linear1.bias"),
+        ("enc_l2_w", "self_encoder.layers.0.linear2.weight"), ("enc_l2_b", "self_encoder.layers.0.linear2.bias"),
+        ("enc_n1_w", "self_encoder.layers.0.norm1.weight"), ("enc_n1_b", "self_encoder.layers.0.norm1.bias"),
+        ("enc_n2_w", "self_encoder.layers.0.norm2.weight"), ("enc_n2_b", "self_encoder.layers.0.norm2.bias"),
+        ("a2t_in_w", "cross_a2t.in_proj_weight"), ("a2t_in_b", "cross_a2t.in_proj_bias"),
+        ("a2t_out_w", "cross_a2t.out_proj.weight"), ("a2t_out_b", "cross_a2t.out_proj.bias"),
+        ("t2a_in_w", "cross_t2a.in_proj_weight"), ("t2a_in_b", "cross_t2a.in_proj_bias"),
+        ("t2a_out_w", "cross_t2a.out_proj.weight"), ("t2a_out_b", "cross_t2a.out_proj.bias"),
+        ("head1_w", "pair_head.0.weight"), ("head1_b", "pair_head.0.bias"), ("head2_w", "pair_head.2.weight"),
+        ("head2_b", "pair_head.2.bias"), ("head3_w", "pair_head.4.weight"), ("head3_b", "pair_head.4.bias"),
+    ]
+
+    def __init__(self, net: AttPairNet, device, score_clamp: float = SCORE_CLAMP):
+        import ctypes as C
+
+        from . import _lib
+
+        sd = net.state_dict()
+        if len(net.self_encoder.layers) != 1 or sd["task_proj.weight"].shape != (64, TASK_FEAT_DIM) \
+                or sd["self_encoder.layers.0.linear1.weight"].shape != (128, 64) \
+                or net.cross_a2t.num_heads != 4:
+            raise ValueError("the fused kernel implements the default AttPairNet (d_model 64, 4 heads, 2 layers)")
+        self.lib = _lib.cuda_lib()
+        self.offsets = _lib.MuavAttPairOffsets()
+        chunks, pos = [], 0
+        for field, key in self._ORDER:
+            t = sd[key].detach().to(torch.float32).reshape(-1)
+            pos = (pos + 3) // 4 * 4  # keep every tensor 16-byte aligned
+            setattr(self.offsets, field, pos)
+            chunks.append((pos, t))
+            pos += t.numel()
+        buf = torch.zeros(pos, dtype=torch.float32)
+        for p, t in chunks:
+            buf[p:p + t.numel()] = t.cpu()
+        self.params = buf.to(device)
+        self.device = device
+        self.clamp = float(score_clamp)
+        self._C = C
+
+    @torch.no_grad()
+    def score(self, tok: dict, scores_out: torch.Tensor, idx: Optional[torch.Tensor] = None, use_need: bool = False):
+        """tok: fused token tensors of BatchedMultiUAVEnv.enable_fused_tokens (masks as uint8); idx: int32 env indices
+        or None for all environments; use_need: skip (on the device) every environment whose tok["need"] flag is 0.
+        Rows of environments not scored are left untouched."""
+        C = self._C
+        E, MA, MT = scores_out.shape
+        n = E if idx is None else int(idx.numel())
+        if n == 0:
+            return
+        if idx is not None and idx.dtype != torch.int32:
+            idx = idx.to(torch.int32)
+        rc = self.lib.dll.muav_att_pair_scores(
+            self.params.data_ptr(), C.byref(self.offsets), tok["task_feats"].data_ptr(), tok["task_mask_u8"].data_ptr(),
+            tok["agent_feats"].data_ptr(), tok["agent_mask_u8"].data_ptr(), tok["edge_valid"].data_ptr(),
+            None if idx is None else idx.data_ptr(), tok["need"].data_ptr() if use_need else None, n, MT, MA,
+            C.c_float(self.clamp), scores_out.data_ptr(),
+            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"muav_att_pair_scores failed: {rc}")

@@ -393,3 +393,40 @@ def test_obstacle_avoidance_in_the_step_kernel():
             assert np.allclose(got["total_distance"], want["total_distance"], rtol=1e-9)
     assert sum(same) >= 4, same
     assert int(env.error_flags().abs().max().item()) == 0
+
+
+def test_fused_scorer_kernel_matches_torch_module():
+    """csrc/muav_scorer.cu vs the PyTorch AttPairNet forward on real tokens (fp32, tolerance 2e-5 on scores)."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+    from multi_uav_ta_gym_env_b200.scorers import AttPairNet, FusedAttPairScorer, pair_scores
+
+    for case, steps in (("WPS_hard", 60), ("WPS_commit", 75), ("WPS_hard", 0)):
+        cfg = wps_config(case)
+        E = 200
+        env = make_env(cfg, list(range(E)))
+        if steps:
+            env.step_allocated(AllocSpec.local_hungarian(20), n_steps=steps)
+        tok = env.enable_fused_tokens(32, 16, 15, 0b111)
+        env.refresh_fused_tokens()
+        torch.manual_seed(1)
+        net = AttPairNet().cuda().eval()
+        eager_tok = {"task_feats": tok["task_feats"], "task_mask": tok["task_mask_u8"].bool(),
+                     "agent_feats": tok["agent_feats"], "agent_mask": tok["agent_mask_u8"].bool(),
+                     "edge_valid": tok["edge_valid"]}
+        want = pair_scores(net, eager_tok)
+        fused = FusedAttPairScorer(net, torch.device("cuda"))
+        got = torch.full_like(want, 7.0)
+        fused.score(tok, got)
+        assert (got - want).abs().max().item() < 2e-5, (case, (got - want).abs().max().item())
+        assert want.abs().max().item() > 1e-3
+        idx = torch.arange(3, 150, 2, device="cuda", dtype=torch.int32)
+        got2 = torch.full_like(want, 7.0)
+        fused.score(tok, got2, idx)
+        assert (got2[idx.long()] - want[idx.long()]).abs().max().item() < 2e-5
+        assert bool((got2[0] == 7.0).all())
+        tok["need"].zero_()
+        tok["need"][10:20] = 1
+        got3 = torch.full_like(want, 7.0)
+        fused.score(tok, got3, use_need=True)
+        assert (got3[10:20] - want[10:20]).abs().max().item() < 2e-5
+        assert bool((got3[:10] == 7.0).all()) and bool((got3[20:] == 7.0).all())
