@@ -2,6 +2,7 @@
 // scores = tanh(logits) * clamp * edge_valid, :266-278) as ONE kernel: one CTA per environment, every
 // activation in shared memory, weights streamed from L2 (the whole network is 330 KB).
 //
+// Weight matrices are packed TRANSPOSED ([in][out]) by the host (scorers.FusedAttPairScorer).
 // Same function and parameters as the PyTorch module (fp32, FMA allowed like cuBLAS); differences are
 // summation order only (tests: <= 2e-5 on scores).  Work that the reference spends on padding is skipped:
 // only the live agents (rows with agent_mask == 0) and the valid task columns (task_mask == 0) are
@@ -42,34 +43,28 @@ struct Params {
 };
 
 // out_t[o][r] = act( sum_k in_t[k][r] * W[o][k] + b[o] (+ res_t[o][r]) ), r < R, o < O.
-// W is row-major in global memory with row stride ldw; the tile W^T is staged in `wt` ([K<=64][WS]).
+// WT is the TRANSPOSED weight ([K][ldo] row-major, packed that way by the host), read through the
+// read-only path (L1-resident: every CTA on the SM streams the same 330 KB of parameters).
 // Each thread owns a 4 (tokens) x 4 (outputs) register tile.
-__device__ void linear_t(const float* __restrict__ in_t, int R, int K, const float* __restrict__ Wg, int ldw,
-                         const float* __restrict__ bg, int O, float* __restrict__ out_t, float* __restrict__ wt,
-                         const float* __restrict__ res_t, bool relu, bool accumulate) {
+__device__ void linear_t(const float* __restrict__ in_t, int R, int K, const float* __restrict__ WT, int ldo,
+                         const float* __restrict__ bg, int O, float* __restrict__ out_t,
+                         const float* __restrict__ res_t, bool relu) {
   const int tid = threadIdx.x;
   const int og = tid & 15, rg = tid >> 4;
   const int r4 = rg * 4;
-  for (int o0 = 0; o0 < O; o0 += 64) {
-    const int ow = (O - o0) < 64 ? (O - o0) : 64;
-    __syncthreads();
-    for (int idx = tid; idx < ow * K; idx += NT) {
-      const int o = idx / K, k = idx - o * K;
-      wt[k * WS + o] = Wg[(size_t)(o0 + o) * ldw + k];
-    }
-    __syncthreads();
-    const int o4 = og * 4;
-    if (r4 < R && o4 < ow) {
+  if (r4 < R) {
+    for (int o4 = og * 4; o4 < O; o4 += 64) {
       float acc[4][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float b = (bg && !accumulate) ? bg[o0 + o4 + j] : 0.0f;
+        const float b = bg ? bg[o4 + j] : 0.0f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[j][i] = b;
       }
+#pragma unroll 4
       for (int k = 0; k < K; ++k) {
         const float4 a = *(const float4*)&in_t[k * TS + r4];
-        const float4 w = *(const float4*)&wt[k * WS + o4];
+        const float4 w = __ldg((const float4*)&WT[(size_t)k * ldo + o4]);
         const float av[4] = {a.x, a.y, a.z, a.w};
         const float wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
@@ -79,20 +74,15 @@ __device__ void linear_t(const float* __restrict__ in_t, int R, int K, const flo
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float* dst = &out_t[(o0 + o4 + j) * TS + r4];
         float4 v = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-        if (accumulate) {
-          const float4 p = *(const float4*)dst;
-          v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
-        }
         if (res_t) {
-          const float4 p = *(const float4*)&res_t[(o0 + o4 + j) * TS + r4];
+          const float4 p = *(const float4*)&res_t[(o4 + j) * TS + r4];
           v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
         }
         if (relu) {
           v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
         }
-        *(float4*)dst = v;
+        *(float4*)&out_t[(o4 + j) * TS + r4] = v;
       }
     }
   }
@@ -152,13 +142,12 @@ __device__ void attention_t(const float* __restrict__ qkv_t, int q0, int q1, int
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(NT) att_pair_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(16) float sm[];
   float* x_t = sm;                       // [D][TS]   tokens / encoder output h
   float* y_t = x_t + D * TS;             // [D][TS]   attention output / residual sums / a_h', t_h'
   float* z_t = y_t + D * TS;             // [D][TS]   scratch (cross contexts, ha / ht)
-  float* big_t = z_t + D * TS;           // [3D][TS]  qkv or FF hidden
-  float* wt = big_t + 3 * D * TS;        // [64][WS]  staged weight tile
+  float* big_t = z_t + D * TS;           // [3D][TS]  qkv or FF hidden; pair-head weight tiles
   __shared__ int s_na, s_nt;
   const int tid = threadIdx.x;
   const int b = blockIdx.x;
@@ -196,8 +185,8 @@ __global__ void __launch_bounds__(NT) att_pair_kernel(const __grid_constant__ Pa
     z_t[k * TS + r] = P.task_feats[((size_t)e * MT + r) * TF + k];
   }
   __syncthreads();
-  linear_t(big_t, na, AF, w + o.agent_proj_w, AF, w + o.agent_proj_b, D, x_t, wt, nullptr, false, false);  // agents -> x[:, :na]
-  linear_t(z_t, nt, TF, w + o.task_proj_w, TF, w + o.task_proj_b, D, y_t, wt, nullptr, false, false);       // tasks  -> y[:, :nt]
+  linear_t(big_t, na, AF, w + o.agent_proj_w, D, w + o.agent_proj_b, D, x_t, nullptr, false);  // agents -> x[:, :na]
+  linear_t(z_t, nt, TF, w + o.task_proj_w, D, w + o.task_proj_b, D, y_t, nullptr, false);       // tasks  -> y[:, :nt]
   for (int idx = tid; idx < D * R; idx += NT) {
     const int k = idx / R, r = idx - k * R;
     if (r < na) x_t[k * TS + r] += w[o.type_embed + k];
@@ -206,26 +195,24 @@ __global__ void __launch_bounds__(NT) att_pair_kernel(const __grid_constant__ Pa
   __syncthreads();
 
   // ---- TransformerEncoderLayer (post-norm, relu, eval): x1 = LN1(x + SA(x)); x2 = LN2(x1 + FF(x1))
-  linear_t(x_t, R, D, w + o.enc_in_w, D, w + o.enc_in_b, 3 * D, big_t, wt, nullptr, false, false);
+  linear_t(x_t, R, D, w + o.enc_in_w, 3 * D, w + o.enc_in_b, 3 * D, big_t, nullptr, false);
   attention_t(big_t, 0, R, 0, R, y_t);
-  linear_t(y_t, R, D, w + o.enc_out_w, D, w + o.enc_out_b, D, z_t, wt, x_t, false, false);   // z = x + out_proj(attn)
+  linear_t(y_t, R, D, w + o.enc_out_w, D, w + o.enc_out_b, D, z_t, x_t, false);   // z = x + out_proj(attn)
   layer_norm_t(z_t, R, w + o.enc_n1_w, w + o.enc_n1_b);                                    // z = x1
-  linear_t(z_t, R, D, w + o.enc_l1_w, D, w + o.enc_l1_b, FF, big_t, wt, nullptr, true, false);  // hidden
-  // linear2: K = 128 > 64 -> two accumulating passes over the hidden features
-  linear_t(big_t, R, 64, w + o.enc_l2_w, FF, w + o.enc_l2_b, D, x_t, wt, z_t, false, false);      // x = x1 + b + W[:, :64] h[:64]
-  linear_t(big_t + 64 * TS, R, 64, w + o.enc_l2_w + 64, FF, nullptr, D, x_t, wt, nullptr, false, true);
+  linear_t(z_t, R, D, w + o.enc_l1_w, FF, w + o.enc_l1_b, FF, big_t, nullptr, true);  // hidden
+  linear_t(big_t, R, FF, w + o.enc_l2_w, D, w + o.enc_l2_b, D, x_t, z_t, false);                 // x = x1 + FF(x1)
   layer_norm_t(x_t, R, w + o.enc_n2_w, w + o.enc_n2_b);                                    // x = h (encoder output)
 
   // ---- cross attention (both use the ORIGINAL h): a' = a + MHA_a2t(a, t, t); t' = t + MHA_t2a(t, a, a)
-  linear_t(x_t, R, D, w + o.a2t_in_w, D, w + o.a2t_in_b, 3 * D, big_t, wt, nullptr, false, false);
+  linear_t(x_t, R, D, w + o.a2t_in_w, 3 * D, w + o.a2t_in_b, 3 * D, big_t, nullptr, false);
   attention_t(big_t, 0, na, na, R, y_t);
   __syncthreads();
-  linear_t(y_t, na, D, w + o.a2t_out_w, D, w + o.a2t_out_b, D, z_t, wt, x_t, false, false);  // z[:, :na] = a'
-  linear_t(x_t, R, D, w + o.t2a_in_w, D, w + o.t2a_in_b, 3 * D, big_t, wt, nullptr, false, false);
+  linear_t(y_t, na, D, w + o.a2t_out_w, D, w + o.a2t_out_b, D, z_t, x_t, false);  // z[:, :na] = a'
+  linear_t(x_t, R, D, w + o.t2a_in_w, 3 * D, w + o.t2a_in_b, 3 * D, big_t, nullptr, false);
   attention_t(big_t, na, R, 0, na, y_t);
   // out-projection of the task rows: the register tiles start at token 0, rows < na are recomputed garbage
   // that is discarded (y_t rows < na still hold the a2t attention output; harmless)
-  linear_t(y_t, R, D, w + o.t2a_out_w, D, w + o.t2a_out_b, D, big_t, wt, x_t, false, false);  // big[:, na:R] = t'
+  linear_t(y_t, R, D, w + o.t2a_out_w, D, w + o.t2a_out_b, D, big_t, x_t, false);  // big[:, na:R] = t'
   for (int idx = tid; idx < D * nt; idx += NT) {
     const int k = idx / nt, r = idx - k * nt;
     z_t[k * TS + na + r] = big_t[k * TS + na + r];
@@ -235,18 +222,18 @@ __global__ void __launch_bounds__(NT) att_pair_kernel(const __grid_constant__ Pa
 
   // ---- pair head: logits[i, j] = w3 . relu(W2 relu(Wat (a_i * t_j) + Wa a_i + Wt t_j + b1) + b2) + b3
   // ha[o][i] (agents) and ht[o][j] (tasks, with bias) share one buffer y_t: columns [0,na) / [na,R)
-  linear_t(z_t, R, D, w + o.head1_w, 3 * D, nullptr, D, y_t, wt, nullptr, false, false);             // Wa x for all tokens
-  linear_t(z_t, R, D, w + o.head1_w + D, 3 * D, w + o.head1_b, D, x_t, wt, nullptr, false, false);   // Wt x + b1 for all tokens
+  linear_t(z_t, R, D, w + o.head1_w, D, nullptr, D, y_t, nullptr, false);             // Wa x for all tokens
+  linear_t(z_t, R, D, w + o.head1_w + D * D, D, w + o.head1_b, D, x_t, nullptr, false);   // Wt x + b1 for all tokens
   // stage Wat [o][d] (row-major, stride WS) and W2^T [o][p]
   float* wat = big_t;               // [64][WS]
   float* w2t = big_t + 64 * WS;     // [64][36]
   for (int idx = tid; idx < D * D; idx += NT) {
     const int oo = idx >> 6, d = idx & 63;
-    wat[oo * WS + d] = w[o.head1_w + (size_t)oo * 3 * D + 2 * D + d];
+    wat[oo * WS + d] = w[o.head1_w + (size_t)(2 * D + d) * D + oo];
   }
   for (int idx = tid; idx < 32 * D; idx += NT) {
     const int p = idx >> 6, oo = idx & 63;
-    w2t[oo * 36 + p] = w[o.head2_w + (size_t)p * D + oo];
+    w2t[oo * 36 + p] = w[o.head2_w + (size_t)oo * 32 + p];  // head2^T is [64][32]
   }
   __syncthreads();
   const float* ev = P.edge_valid + (size_t)e * MA * MT;
@@ -313,7 +300,7 @@ extern "C" int muav_att_pair_scores(const float* d_params, const muav_attpair_of
   P.max_tasks = max_tasks;
   P.max_agents = max_agents;
   P.clamp = score_clamp;
-  const size_t smem = sizeof(float) * (size_t)(3 * D * TS + 3 * D * TS + 64 * WS);
+  const size_t smem = sizeof(float) * (size_t)(3 * D * TS + 3 * D * TS);
   static bool set = false;
   if (!set) {
     cudaError_t e = cudaFuncSetAttribute(att_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -259,7 +259,10 @@ class FusedAttPairScorer:
         self.offsets = _lib.MuavAttPairOffsets()
         chunks, pos = [], 0
         for field, key in self._ORDER:
-            t = sd[key].detach().to(torch.float32).reshape(-1)
+            t = sd[key].detach().to(torch.float32)
+            if t.dim() == 2 and field != "type_embed":
+                t = t.t().contiguous()  # the kernel streams W^T ([in][out]) rows as float4
+            t = t.reshape(-1)
             pos = (pos + 3) // 4 * 4  # keep every tensor 16-byte aligned
             setattr(self.offsets, field, pos)
             chunks.append((pos, t))
