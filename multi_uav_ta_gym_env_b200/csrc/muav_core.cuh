@@ -684,11 +684,15 @@ struct Sim {
   }
 
   // update_threats (DroneEnv.py:1725-1744)
-  MUAV_HD MUAV_NI_H void update_threats() {
+  MUAV_HD void update_threats() {
     int n = HIv(N_ACTIVE);
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < n; ++i) update_threat(i);
+  }
+  // one iteration of update_threats (i indexes env.threats, spawn order)
+  MUAV_HD MUAV_NI_H void update_threat(int i) {
+    {
       int hid = V.h_order()[i];
-      if (V.h_status()[hid] == 2) continue;
+      if (V.h_status()[hid] == 2) return;
       double sp = C().speed[V.h_type()[hid]];
       double hx = V.h_posx()[hid], hy = V.h_posy()[hid];
       if (V.h_status()[hid] == 0 || V.h_target()[hid] < 0) {
@@ -1034,19 +1038,25 @@ struct Sim {
   MUAV_HD void step_pre_b() {
     MUAV_TICK_START();
     const int Aa = A();
+    for (int a = 0; a < Aa; ++a) fsm_agent(a);
+    MUAV_TICK(3);
+  }
+
+  // kinematics FSM of one agent (one iteration of the loop at DroneEnv.py:965-1129)
+  MUAV_HD void fsm_agent(int a) {
     const int TC = V.L->D.TC;
     const int t = HIv(T);
     const double bx = C().base_x, by = C().base_y;
-    int nobs = V.L->D.NOBS;
-    for (int a = 0; a < Aa; ++a) {
-      if (V.a_state()[a] == -1) continue;
+    const int nobs = V.L->D.NOBS;
+    {
+      if (V.a_state()[a] == -1) return;
       if (V.a_fail_event()[a] == t) {
         V.a_state()[a] = -1;
         des_allocate_all(a);
         push_event(EV_RESET, -1);
         push_event(EV_FAIL, a);
         HIv(PENDING_RESET) = 1;
-        continue;
+        return;
       }
       double mvx = 0.0, mvy = 0.0, avx = 0.0, avy = 0.0;
       double px = V.a_posx()[a], py = V.a_posy()[a];
@@ -1149,7 +1159,6 @@ struct Sim {
       V.a_posy()[a] = py;
     }
 
-    MUAV_TICK(3);
   }
 
   // step part 1c: travelled distance, threats, arrivals, escorts
@@ -1183,8 +1192,10 @@ struct Sim {
 
     MUAV_TICK(4);
     generate_threat();
-    update_threats();
-    MUAV_TICK(5);
+  }
+  // step part 1d: arrivals, escorts (after update_threats)
+  MUAV_HD void step_pre_d() {
+    MUAV_TICK_START();
     inject_arrivals();
     if (C().escort_enabled) sync_escorts();
     MUAV_TICK(6);
@@ -1301,16 +1312,39 @@ struct Sim {
   // whole step.  Sequential phases run on lane 0, the task/agent scans are spread over the warp.
   // `alive` = this warp has an environment to step; `cta_sync` = align the CTA's warps between phases.
   MUAV_HD StepResult step(const int16_t* act_agent, const int16_t* act_tid, int n_act, int lane, int nlanes,
-                          bool alive = true, bool cta_sync = false) {
+                          bool alive = true, int sync_mask = 0) {
     if (alive && lane == 0) step_pre_a(act_agent, act_tid, n_act);
     MUAV_WARP_SYNC();
-    MUAV_CTA_SYNC(cta_sync);
-    if (alive && lane == 0) step_pre_b();
-    MUAV_WARP_SYNC();
-    MUAV_CTA_SYNC(cta_sync);
+    MUAV_CTA_SYNC(sync_mask & 2);
+    if (sync_mask & 32) {
+      // one alignment point per agent: the FSM body is the longest straight-line stretch of the step
+      const int Aa = A();
+      for (int a = 0; a < Aa; ++a) {
+        if (alive && lane == 0) fsm_agent(a);
+        MUAV_WARP_SYNC();
+        MUAV_CTA_SYNC(1);
+      }
+    } else {
+      if (alive && lane == 0) step_pre_b();
+      MUAV_WARP_SYNC();
+      MUAV_CTA_SYNC(sync_mask & 4);
+    }
     if (alive && lane == 0) step_pre_c();
     MUAV_WARP_SYNC();
-    MUAV_CTA_SYNC(cta_sync);
+    if (sync_mask & 64) {
+      const int HCc = V.L->D.HC;
+      for (int i = 0; i < HCc; ++i) {
+        if (alive && lane == 0 && i < HIv(N_ACTIVE)) update_threat(i);
+        MUAV_WARP_SYNC();
+        MUAV_CTA_SYNC(1);
+      }
+    } else {
+      if (alive && lane == 0) update_threats();
+      MUAV_WARP_SYNC();
+    }
+    if (alive && lane == 0) step_pre_d();
+    MUAV_WARP_SYNC();
+    MUAV_CTA_SYNC(sync_mask & 8);
     StepResult r;
     r.reward = 0.0;
     r.terminated = r.truncated = 0;
@@ -1345,7 +1379,7 @@ struct Sim {
       if (lane == 0) r = step_post(alld, n_open);
       MUAV_TICK(9);
     }
-    MUAV_CTA_SYNC(cta_sync);
+    MUAV_CTA_SYNC(sync_mask & 16);
     return r;
   }
 };

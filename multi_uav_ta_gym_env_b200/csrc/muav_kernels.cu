@@ -66,7 +66,7 @@ struct StepParams {
   const int32_t* actions;
   int32_t* actions_out;  // allocate-only mode: ordered (agent, index) list per env
   long long* phase_out;  // MUAV_PHASE_TIMING builds: 16 cycle counters summed over warps
-  int n_envs, n_steps, tape_stride, use_bulk, alloc_only, cta_warps;
+  int n_envs, n_steps, tape_stride, use_bulk, alloc_only, cta_warps, sync_mask;
 };
 
 #define MUAV_MAX_CTA_WARPS 16
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS) muav_step_kernel(cons
   const int lane = threadIdx.x & 31;
   const int e = blockIdx.x * W + w;
   const bool has_env = e < P.n_envs;
-  const bool cta_sync = W > 1;
+  const int sync_mask = W > 1 ? P.sync_mask : 0;
   const Layout& L = P.L;
   const int slot_bytes = L.record_bytes + L.scratch_bytes;
   char* rec = (char*)smem + (size_t)w * slot_bytes;
@@ -133,6 +133,23 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS) muav_step_kernel(cons
 #endif
   View& V = S.V;
   const int A = L.D.A;
+
+  // Warm L1 with the few global lines the sequential code will touch (RNG tape at the current cursors, this
+  // environment's edge-score tile): lane 0 would otherwise eat a full DRAM/L2 latency per access.
+  if (has_env) {
+    if (lane < 3 && P.tapes) {
+      int off = 0;
+      for (int s = 0; s < lane; ++s) off += P.cfg.tape_words[s];
+      const uint32_t* p = S.tape + off + V.hi()[HI_CUR_AGENT + lane];
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 32));
+    }
+    if (P.opts.d_edge_scores && P.opts.mode != 0 && !P.opts.score_f64) {
+      const int tile_bytes = P.opts.score_rows * P.opts.score_cols * 4;
+      const char* sp = (const char*)P.opts.d_edge_scores + (size_t)e * tile_bytes;
+      for (int o = lane * 128; o < tile_bytes; o += 32 * 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + o));
+    }
+  }
 
   if (P.alloc_only && has_env) {
     const int np = HIv(DONE) ? 0 : plan_and_allocate(S, P.opts, e, act_agent, act_tid, lane, 32);
@@ -193,8 +210,8 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS) muav_step_kernel(cons
       n_act_s[w] = n_act;
     }
     __syncwarp();
-    MUAV_CTA_SYNC(cta_sync);
-    StepResult r = S.step(act_agent, act_tid, alive ? n_act_s[w] : 0, lane, 32, alive, cta_sync);
+    MUAV_CTA_SYNC(sync_mask & 1);
+    StepResult r = S.step(act_agent, act_tid, alive ? n_act_s[w] : 0, lane, 32, alive, sync_mask);
     if (alive && lane == 0) {
       if (P.out.d_reward) P.out.d_reward[e] = r.reward;
       if (P.out.d_terminated) P.out.d_terminated[e] = (uint8_t)r.terminated;
@@ -335,6 +352,10 @@ static int launch_step(StepParams& P, void* stream) {
   while (W > 1 && slot * W > 200 * 1024) --W;
   if (slot > 226 * 1024) return -12;
   P.cta_warps = W;
+  // phase-alignment barriers (bit 0: before the step, 1..3: after its three sequential parts, 4: end of step)
+  P.sync_mask = 31;
+  const char* sm = getenv("MUAV_SYNC_MASK");
+  if (sm) P.sync_mask = atoi(sm);
   const size_t smem = slot * W;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {

@@ -100,7 +100,7 @@ class RecordCodec:
                 if tid > 0 and s["k_status"][tid - 1] != 2:
                     det[tid - 1, a] = qt[a, sl]
         s["k_det_time"] = det
-        s["k_tbl_mask"] = i64(f("k_tbl_lo")[:T].astype(np.int64) | (f("k_tbl_hi")[:T].astype(np.int64) << 32))
+        s["k_tbl_mask"] = (f("k_tbl_lo")[:T].astype(np.uint64) | (f("k_tbl_hi")[:T].astype(np.uint64) << np.uint64(32))).view(np.int64)
         s["k_reached"] = i64(f("k_reached")[:T])
         s["h_pos"] = np.stack([f("h_posx"), f("h_posy")], axis=1).astype(np.float64).reshape(HC, 2)
         for n in ("h_status", "h_type", "h_group", "h_ammo", "h_target", "h_mission", "h_task", "h_det_task", "h_spawned"):

@@ -174,7 +174,7 @@ def snapshot(env) -> dict:
         if t.id < len(env.allocation_table):
             for name in env.allocation_table[t.id]:
                 m |= 1 << name_to_id[name]
-        ki["k_tbl_mask"][k] = m
+        ki["k_tbl_mask"][k] = np.uint64(m).view(np.int64) if m >= 2**63 else m
         ki["k_reached"][k] = int(t.id in env.reached_tasks)
     s.update(k_pos=k_pos, k_cur=k_cur, k_alloc=k_alloc, k_det_time=k_det_time, **kf, **ki)
 

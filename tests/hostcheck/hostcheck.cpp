@@ -71,7 +71,7 @@ int hostcheck_step(const muav_config* cfg, void* records, const uint32_t* tapes,
           ++n_act;
         }
       }
-      StepResult r = S.step(act_agent, act_tid, n_act, 0, 1, true, false);
+      StepResult r = S.step(act_agent, act_tid, n_act, 0, 1, true, 0);
       if (Z.d_reward) Z.d_reward[e] = r.reward;
       if (Z.d_terminated) Z.d_terminated[e] = (uint8_t)r.terminated;
       if (Z.d_truncated) Z.d_truncated[e] = (uint8_t)r.truncated;

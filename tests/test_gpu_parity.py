@@ -430,3 +430,87 @@ def test_fused_scorer_kernel_matches_torch_module():
         fused.score(tok, got3, use_need=True)
         assert (got3[10:20] - want[10:20]).abs().max().item() < 2e-5
         assert bool((got3[:10] == 7.0).all()) and bool((got3[20:] == 7.0).all())
+
+
+def test_edge_cases_and_error_flags():
+    """Empty / ragged inputs and capacity limits: zero environments, zero steps, steps without actions,
+    out-of-range and negative indices, queue / task capacity overflow flags, finished episodes."""
+    import ctypes as C
+    from multi_uav_ta_gym_env_b200 import AllocSpec, _lib, wps_config
+
+    cfg = wps_config("WPS_hard")
+    env = make_env(cfg, [0, 1, 2])
+    lib = env.lib
+    # n_envs == 0 and n_steps == 0 are no-ops
+    assert lib.dll.muav_step(C.byref(env.cfg), env.records.data_ptr(), env.tapes.data_ptr(), None, None, None, None, 0, 1, None) == 0
+    before = env.records.clone()
+    assert lib.dll.muav_step(C.byref(env.cfg), env.records.data_ptr(), env.tapes.data_ptr(), None, None, None, None, 3, 0, None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(env.records, before)
+    # a step with no actions at all (NULL action pointer) == a step with an empty action list
+    a = make_env(cfg, [5])
+    b = make_env(cfg, [5])
+    lib.dll.muav_step(C.byref(a.cfg), a.records.data_ptr(), a.tapes.data_ptr(), None, None, C.byref(a._out), None, 1, 1, None)
+    b.step_batched(torch.full((1, 8, 2), -1, dtype=torch.int32))
+    assert torch.equal(a.records, b.records)
+    # out-of-range index costs action_reward (weight 0 here) and changes nothing else; negative index = Python indexing
+    c = make_env(cfg, [5])
+    act = torch.full((1, 8, 2), -1, dtype=torch.int32)
+    act[0, 0] = torch.tensor([0, 999])
+    c.step_batched(act)
+    assert torch.equal(c.records, b.records)
+    d1, d2 = make_env(cfg, [5]), make_env(cfg, [5])
+    n_open = int(d1.n_open[0])
+    a1 = torch.full((1, 8, 2), -1, dtype=torch.int32)
+    a1[0, 0] = torch.tensor([3, -1])
+    a2 = a1.clone()
+    a2[0, 0] = torch.tensor([3, n_open - 1])
+    d1.step_batched(a1)
+    d2.step_batched(a2)
+    assert torch.equal(d1.records, d2.records)
+    # per-agent index form [E, A] (ascending agent id) == ordered pair form
+    e1, e2 = make_env(cfg, [9]), make_env(cfg, [9])
+    per_agent = torch.tensor([[2, -1, 0, -1, -1, 4, -1, 1]], dtype=torch.int32)
+    pairs = torch.tensor([[[0, 2], [2, 0], [5, 4], [7, 1], [-1, 0], [-1, 0], [-1, 0], [-1, 0]]], dtype=torch.int32)
+    e1.step_batched(per_agent.cuda())
+    e2.step_batched(pairs)
+    assert torch.equal(e1.records, e2.records)
+    # queue capacity overflow raises the sticky error flag instead of corrupting memory
+    q = make_env(cfg, [0], queue_cap=2)
+    for idx in range(4):
+        act = torch.full((1, 8, 2), -1, dtype=torch.int32)
+        act[0, 0] = torch.tensor([0, idx])
+        q.step_batched(act)
+    assert int(q.error_flags()[0]) & 1
+    # task capacity overflow flag
+    t = make_env(cfg, list(range(8)), task_cap=12)
+    t.step_allocated(AllocSpec.local_hungarian(20), n_steps=150)
+    assert bool(((t.error_flags() & 2) != 0).any())
+    # stepping a finished episode is a no-op
+    f = make_env(cfg, [0])
+    f.step_allocated(AllocSpec.local_hungarian(20), n_steps=150)
+    done_rec = f.records.clone()
+    f.step_allocated(AllocSpec.local_hungarian(20), n_steps=5)
+    assert torch.equal(f.records, done_rec)
+    # invalid configurations are rejected
+    bad = _lib.build_config(cfg)
+    bad.queue_cap = 1000
+    assert lib.dll.muav_step(C.byref(bad), env.records.data_ptr(), env.tapes.data_ptr(), None, None, None, None, 1, 1, None) == -22
+
+
+def test_largest_shape_burst_x8():
+    """64 agents (MUAV_MAX_AGENTS), 160-task capacity: runs clean and matches the oracle on one seed."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, burst_scaled_spec, wps_config
+    from oracle.hungarian import OracleHungarian, apply_assign
+    from oracle.sim import OracleEnv
+
+    cfg = wps_config(burst_scaled_spec(8))
+    env = make_env(cfg, [0, 1])
+    assert env.n_agents == 64
+    env.step_allocated(AllocSpec.local_hungarian(20), n_steps=150)
+    assert int(env.error_flags().abs().max().item()) == 0
+    o = OracleEnv(cfg).reset(0)
+    h = OracleHungarian(20, 1200.0)
+    for _ in range(150):
+        o.step(apply_assign(o, h.allocate(o, time_step=o.t, events=o.last_events, known=o.visibility())))
+    assert refsnap.digest(env.snapshot(0)) == refsnap.digest(o.snapshot())
