@@ -182,16 +182,38 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    # workload: the default is BASELINE config 2; the others are BASELINE configs 3-5 (extra lines for profiles/)
+    wl = args.workload
+    use_scorer = wl == "hard_pair"
+    if wl == "hard_pair":
+        case_name, cfg, spec = CASE, wps_config(CASE), AllocSpec.pair_hybrid(HYBRID_INTERVAL)
+        desc = "Local-Hungarian + random-init Att-Pair edge scores, hybrid replan rule t%15/events"
+    elif wl == "hard_local":
+        case_name, cfg, spec = CASE, wps_config(CASE), AllocSpec.local_hungarian(20)
+        desc = "Local-Hungarian interval 20 (no scorer)"
+    elif wl == "commit_urgency":
+        case_name, cfg, spec = "WPS_commit", wps_config("WPS_commit"), AllocSpec.urgency_commit(HYBRID_INTERVAL)
+        desc = "UrgencyCommit planner on the device (commit locks, rematch penalty), hybrid replan rule"
+    elif wl == "escort_coalition":
+        case_name, cfg, spec = "WPS_escort", wps_config("WPS_escort"), AllocSpec.coalition_hungarian(12)
+        desc = "Coalition-Hungarian interval 12 with visibility map"
+    elif wl.startswith("burst_x"):
+        from multi_uav_ta_gym_env_b200 import burst_scaled_spec
+        k = int(wl[7:])
+        case_name, cfg, spec = f"WPS_burst x{k}", wps_config(burst_scaled_spec(k)), AllocSpec.local_hungarian(20)
+        desc = f"agents/tasks/threats scaled x{k}, Local-Hungarian interval 20"
+    else:
+        raise SystemExit(f"unknown workload {wl}")
     E = args.envs
-    cfg = wps_config(CASE)
     env = BatchedMultiUAVEnv(cfg, E, device=dev).reset(sharding.shard_range(E, rank))
     torch.manual_seed(0)
-    net = AttPairNet().to(dev).eval()
-    spec = AllocSpec.pair_hybrid(HYBRID_INTERVAL)
-    scores = torch.zeros(E, 16, 32, dtype=torch.float32, device=dev)
-    # the step kernel emits the pair tokens of every env that will replan before the next step
-    tok = env.enable_fused_tokens(32, 16, HYBRID_INTERVAL, 0b111)
-    scorer = FusedAttPairScorer(net, dev)   # hand-written fused forward (csrc/muav_scorer.cu)
+    scores = tok = scorer = None
+    if use_scorer:
+        net = AttPairNet().to(dev).eval()
+        scores = torch.zeros(E, 16, 32, dtype=torch.float32, device=dev)
+        # the step kernel emits the pair tokens of every env that will replan before the next step
+        tok = env.enable_fused_tokens(32, 16, HYBRID_INTERVAL, 0b111)
+        scorer = FusedAttPairScorer(net, dev)   # hand-written fused forward (csrc/muav_scorer.cu)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     metric_acc = torch.zeros(32, dtype=torch.float64, device=dev)
     names = env.lib.metric_names()
@@ -199,6 +221,8 @@ def run_gpu_arm(args):
 
     def score_step(t):
         """Att-Pair scorer for the environments whose hybrid replan rule fires at time t (wps_eval.py:64-73)."""
+        if not use_scorer:
+            return
         if t == 0:
             env.refresh_fused_tokens()  # episode start: standalone token kernel for all envs
             launches["n"] += 1
@@ -308,10 +332,9 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{CASE} (8 agents), {E} envs per GPU, Local-Hungarian + random-init Att-Pair "
-                                   f"edge scores, hybrid replan rule t%15/events, seeds = env index",
+            "config": {"workload": f"{case_name} ({A} agents), {E} envs per GPU, {desc}, seeds = env index",
                        "envs_per_gpu": E, "global_envs": world * E, "parallelism": f"env-shard x{world}",
-                       "l2": "flushed between timed steps (256 MB write); state 46 MB < 126 MB L2",
+                       "l2": f"flushed between timed steps (256 MB write); state {E * rb / 1e6:.0f} MB vs 126 MB L2",
                        "record_bytes": rb, "agent_steps_per_s": value * A},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes,
                     "d2h_bytes_per_step": act_bytes + E * 10, "steps": Ke},
@@ -357,6 +380,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
+    ap.add_argument("--workload", default="hard_pair",
+                    help="hard_pair (default, BASELINE config 2) | hard_local | commit_urgency | escort_coalition | burst_xK")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
