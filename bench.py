@@ -128,7 +128,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        return len(self.samples)
+
+    def stop(self, first=0):
+        """Summary of the samples taken from index `first` on (the timed region); when the region was too short for
+        three samples, every sample since start() is used (the warm-up runs the same load)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -138,7 +143,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        use = self.samples[first:] if len(self.samples) - first >= 3 else self.samples
+        for s in use:
             parts = [p.strip() for p in s.split(",")]
             if len(parts) < 7:
                 continue
@@ -252,6 +258,8 @@ def run_gpu_arm(args):
         torch.cuda.synchronize(dev)
 
     # ---- warm-up (then rewind so that the timed region starts at an episode boundary)
+    sampler = ClockSampler(local)
+    sampler.start()
     for w in range(max(args.warmup, 3)):
         device_step(w % EPISODE)
     env.restore()
@@ -260,8 +268,7 @@ def run_gpu_arm(args):
 
     # ---- timed: K steps, each bracketed by CUDA events, L2 flushed between steps
     K = args.steps
-    sampler = ClockSampler(local)
-    sampler.start()
+    first_sample = sampler.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
            torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     launches["n"] = 0
@@ -278,7 +285,7 @@ def run_gpu_arm(args):
         if t + 1 == EPISODE:
             episode_end()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(first_sample)
     step_ms = sum(a.elapsed_time(c) for a, b, c in ev)
     kern_ms = sum(b.elapsed_time(c) for a, b, c in ev)
     gpu_launches = launches["n"]
@@ -349,7 +356,7 @@ def run_gpu_arm(args):
         }
         if cpu_base is not None:
             line["cpu_baseline"] = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -370,14 +377,46 @@ def run_reference_arm(args):
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
+
+
+class _QuietStdout:
+    """Route fd 1 to stderr while the run is in progress (NCCL prints its version banner to stdout), so that the
+    process emits exactly ONE line on stdout: the JSON result."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+_OUT = None
+
+
+def emit_line(obj):
+    text = json.dumps(obj)
+    if _OUT is not None:
+        _OUT.emit(text)
+    else:
+        print(text, flush=True)
 
 
 def main():
+    global _OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1500)
+    ap.add_argument("--warmup", type=int, default=150)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
     ap.add_argument("--workload", default="hard_pair",
@@ -385,10 +424,13 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_gpu_arm(args)
+    with _QuietStdout() as q:
+        _OUT = q
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_gpu_arm(args)
+        _OUT = None
 
 
 if __name__ == "__main__":
