@@ -37,7 +37,8 @@ extern "C" {
 #define MUAV_N_TASK_TYPES 6 /* Hold Rec Att Def Int Det (MultiDroneEnvData.py:18) */
 #define MUAV_MAX_GROUPS 8
 #define MUAV_MAX_AGENTS 64
-#define MUAV_MAX_TASK_CAP 512
+#define MUAV_MAX_TASK_CAP 512 /* task slots (open or still referenced tasks) */
+#define MUAV_MAX_ID_CAP 2048  /* tasks ever created in one episode */
 #define MUAV_MAX_QUEUE 32
 
 typedef struct muav_config {
@@ -53,7 +54,7 @@ typedef struct muav_config {
   int32_t tape_words[3];    /* words per env in each RNG tape: agent, tgt, mission */
   int32_t group_start[MUAV_MAX_GROUPS + 1]; /* threat ids of group g: [group_start[g], group_start[g+1]) */
   int32_t duration[MUAV_N_TASK_TYPES];
-  int32_t reserved_i;
+  int32_t id_cap;           /* task ids per episode (>= task_cap); 0 = task_cap */
   double arrival_rate, sense_radius, miss_penalty, on_time_bonus, dynamic_idle_penalty, reassign_penalty;
   double escort_radius, escort_requirement, escort_intercept_radius, mutual_support_radius;
   double threat_gen_prob, threat_wide, max_coord, area_w, area_h, base_x, base_y, contact_line;
@@ -87,9 +88,9 @@ typedef struct muav_alloc_opts {
   double max_coord;        /* HungarianAllocator(max_coord=...) */
   const void* d_edge_scores;   /* [E, score_rows, score_cols] float (or double when score_f64) or NULL;
                                   pair_tokens=0: indexed [agent id, task index] */
-  const double* d_priorities;  /* [E, task_cap] by task index (task_priorities) or NULL */
+  const double* d_priorities;  /* [E, id_cap] by task index = id - 1 (task_priorities) or NULL */
   const uint8_t* d_reserved;   /* [E, n_agents] 1 = excluded (reserved_agent_names) or NULL */
-  const int32_t* d_task_order; /* [E, task_cap] the `tasks` argument: task indices (id-1) in the caller's order, -1 terminated;
+  const int32_t* d_task_order; /* [E, id_cap] the `tasks` argument: task indices (id-1) in the caller's order, -1 terminated;
                                   NULL = every open task in id order (_open_tasks, paper_eval.py:96-101) */
 } muav_alloc_opts;
 

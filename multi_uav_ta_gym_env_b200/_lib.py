@@ -31,7 +31,7 @@ class MuavConfig(C.Structure):
         ("tape_words", C.c_int32 * 3),
         ("group_start", C.c_int32 * (MAX_GROUPS + 1)),
         ("duration", C.c_int32 * 6),
-        ("reserved_i", C.c_int32),
+        ("id_cap", C.c_int32),
         ("arrival_rate", C.c_double), ("sense_radius", C.c_double), ("miss_penalty", C.c_double),
         ("on_time_bonus", C.c_double), ("dynamic_idle_penalty", C.c_double), ("reassign_penalty", C.c_double),
         ("escort_radius", C.c_double), ("escort_requirement", C.c_double),
@@ -202,7 +202,7 @@ def check(rc: int, what: str):
         raise RuntimeError(f"{what} failed with code {rc}" + (f" (cudaError {-1000 - rc})" if rc <= -1000 else ""))
 
 
-def build_config(opts, task_cap=None, queue_cap=8, event_cap=None) -> MuavConfig:
+def build_config(opts, task_cap=None, queue_cap=8, event_cap=None, id_cap=None) -> MuavConfig:
     """agentEnvOptions -> muav_config.  Derived constants follow MultiUAVEnv.__init__
     (mUAV_TA/DroneEnv.py:73-323) and the entity constructors."""
     g = lambda n, d=None: getattr(opts, n, d)
@@ -219,16 +219,22 @@ def build_config(opts, task_cap=None, queue_cap=8, event_cap=None) -> MuavConfig
     if not g("multiple_agents_per_task", True):
         raise NotImplementedError("multiple_agents_per_task=False is a dead branch in the reference (DroneEnv.py:935)")
     escort = bool(g("escort_enabled", False))
+    # Task ids: arrivals stop at max_tasks-1 (DroneEnv.py:1652), every threat adds one Int task, escorts are re-created
+    # every step a recon sits on a Rec (~250 tasks per WPS_escort episode).
+    base = max(max_tasks - 1, sum(tasks.values()) + len(threats)) + n_threats
+    if id_cap is None:
+        id_cap = base + (320 if escort else 0)
+        id_cap = (id_cap + 31) // 32 * 32
+    # Task slots: open tasks plus closed ones that a queue / the escort map / a live threat still references.
     if task_cap is None:
-        # arrivals stop at max_tasks-1 (DroneEnv.py:1652); every threat adds one Int task; escorts are unbounded
-        task_cap = max(max_tasks - 1, sum(tasks.values()) + len(threats)) + n_threats
-        if escort:
-            task_cap += 280
+        task_cap = base + (24 if escort else 0)
         task_cap = (task_cap + 15) // 16 * 16
+    id_cap = max(int(id_cap), int(task_cap))
     if event_cap is None:
         event_cap = max(32, 4 * n_agents + 2 * n_threats + 8)
     cfg.n_agents = n_agents
     cfg.task_cap = int(task_cap)
+    cfg.id_cap = int(id_cap)
     cfg.n_threats = n_threats
     cfg.queue_cap = int(queue_cap)
     cfg.event_cap = int(event_cap)

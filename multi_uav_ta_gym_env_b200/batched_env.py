@@ -63,14 +63,14 @@ class AllocSpec:
 
 
 class BatchedMultiUAVEnv:
-    def __init__(self, config, n_envs: int, device="cuda:0", task_cap=None, queue_cap=8):
+    def __init__(self, config, n_envs: int, device="cuda:0", task_cap=None, queue_cap=8, id_cap=None):
         self.lib = _lib.cuda_lib()  # raises if the CUDA library is not built: no CPU fallback
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedMultiUAVEnv needs a CUDA device (B200); there is no CPU path")
         self.config = config
         self.n_envs = int(n_envs)
         self.device = torch.device(device)
-        self.cfg = _lib.build_config(config, task_cap=task_cap, queue_cap=queue_cap)
+        self.cfg = _lib.build_config(config, task_cap=task_cap, queue_cap=queue_cap, id_cap=id_cap)
         self.codec = _state.RecordCodec(self.lib, self.cfg)
         self.record_bytes = self.codec.record_bytes
         self.n_agents = self.cfg.n_agents

@@ -9,7 +9,7 @@ size_t muav_scratch_bytes(const muav_config* cfg) { return (size_t)make_layout(*
 int muav_num_fields(void) {
   int n = 0;
 #define X(name, type, count) ++n;
-  MUAV_FIELDS(X)
+  MUAV_FIELDS(X, X)
 #undef X
   return n;
 }
@@ -28,7 +28,7 @@ int muav_field_info(const muav_config* cfg, int idx, const char** name, int64_t*
     return 0;                           \
   }                                     \
   ++i;
-  MUAV_FIELDS(X)
+  MUAV_FIELDS(X, X)
 #undef X
   return -22;
 }
@@ -53,6 +53,7 @@ static int check_cfg(const muav_config* c) {
   if (!c) return -22;
   if (c->n_agents < 1 || c->n_agents > MUAV_MAX_AGENTS) return -22;
   if (c->task_cap < 1 || c->task_cap > MUAV_MAX_TASK_CAP) return -22;
+  if (c->id_cap > MUAV_MAX_ID_CAP) return -22;
   if (c->queue_cap < 1 || c->queue_cap > MUAV_MAX_QUEUE) return -22;
   if (c->n_groups < 0 || c->n_groups > MUAV_MAX_GROUPS) return -22;
   if (c->n_threats < 0 || c->event_cap < 1 || c->n_obstacles < 0) return -22;

@@ -17,7 +17,7 @@ struct AllocScratch {
   uint8_t* plan_reserved;         // planner: reserved agents [A]
 };
 
-MUAV_HD inline AllocScratch carve_scratch(char* p, int A, int TC) {
+MUAV_HD inline AllocScratch carve_scratch(char* p, int A, int TC, int IC = 0) {
   AllocScratch S;
   int M = A > TC ? A : TC;
   double* d = (double*)p;
@@ -43,7 +43,7 @@ MUAV_HD inline AllocScratch carve_scratch(char* p, int A, int TC) {
   // planner block starts at the next 8-byte boundary
   uintptr_t q = ((uintptr_t)s + 7) & ~(uintptr_t)7;
   S.plan_pri = (double*)q;
-  S.plan_score = S.plan_pri + TC;
+  S.plan_score = S.plan_pri + (IC > TC ? IC : TC);  // priorities are indexed by task id
   S.plan_reserved = (uint8_t*)(S.plan_score + A);
   return S;
 }
@@ -186,7 +186,7 @@ MUAV_HD inline double residual_demand(const Sim& S, int k) {
   }
   int ti = S.V.k_type()[k];
   int TC = S.V.L->D.TC;
-  double r = S.V.k_cur()[ti * TC + k] - S.V.k_alloc()[ti * TC + k];
+  double r = S.V.k_cur2(ti, k) - S.V.k_alloc2(ti, k);
   return r > 0.0 ? r : 0.0;
 }
 
@@ -204,7 +204,8 @@ MUAV_HD MUAV_NI_A inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, in
   AllocScratch W = carve_scratch(S.scratch, A, TC);
   const size_t eo = local_ptrs ? 0 : (size_t)e;  // planner-produced arrays live in this env's scratch
   const uint8_t* reserved = O.d_reserved ? O.d_reserved + eo * A : nullptr;
-  const double* pri = O.d_priorities ? O.d_priorities + eo * TC : nullptr;
+  const int IC = V.L->D.IC;
+  const double* pri = O.d_priorities ? O.d_priorities + eo * IC : nullptr;
   const size_t sc_off = (size_t)e * O.score_rows * O.score_cols;
   const float* scores = (O.d_edge_scores && !O.score_f64) ? (const float*)O.d_edge_scores + sc_off : nullptr;
   const double* scores64 = (O.d_edge_scores && O.score_f64) ? (const double*)O.d_edge_scores + sc_off : nullptr;
@@ -232,8 +233,8 @@ MUAV_HD MUAV_NI_A inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, in
       }
       // open task list (+ residuals, + pair-token column of each task)
       int tok_j = 0;
-      const int32_t* order = O.d_task_order ? O.d_task_order + (size_t)e * TC : nullptr;
-      for (int it = 0; it < (order ? TC : n_tasks); ++it) {
+      const int32_t* order = O.d_task_order ? O.d_task_order + (size_t)e * IC : nullptr;
+      for (int it = 0; it < (order ? IC : n_tasks); ++it) {
         int k = it;
         if (order) {
           k = order[it];
@@ -244,12 +245,12 @@ MUAV_HD MUAV_NI_A inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, in
         int col = -1;
         if (O.pair_tokens) {
           int ti = V.k_type()[k];
-          if (!(V.k_alloc()[ti * TC + k] < V.k_cur()[ti * TC + k])) continue;  // AttentionRAH.py:67-71
+          if (!(V.k_alloc2(ti, k) < V.k_cur2(ti, k))) continue;  // AttentionRAH.py:67-71
           if (tok_j >= O.score_cols) break;                                    // open_tasks[:max_tasks]
           col = tok_j++;
         }
         double r = residual_demand(S, k);
-        if (r > 0) {
+        if (r > 0 && n_open < TC) {
           W.open_t[n_open] = (int16_t)k;
           W.resid[n_open] = r;
           W.tokcol[n_open] = (int16_t)col;
@@ -434,7 +435,7 @@ MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, in
   const muav_config& C = S.C();
   const int A = V.L->D.A, TC = V.L->D.TC;
   const int t = HIv(T);
-  AllocScratch W = carve_scratch(S.scratch, A, TC);
+  AllocScratch W = carve_scratch(S.scratch, A, TC, V.L->D.IC);
   // the caller's cadence (wps_eval.py:64-73 / escort_eval.py:52-58), then plan(force=True)
   const int interval = O.replan_interval > 0 ? O.replan_interval : 1;
   const bool go = O.mode == 3 || t == 0 || (t % interval) == 0 || (HIv(EV_TAGMASK) & O.event_mask) != 0;
@@ -472,7 +473,7 @@ MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, in
   if (O.planner == 1) {
     P.d_priorities = W.plan_pri;
     P.pair_tokens = 1;      // task list = build_att_tokens' open list (alloc < cur), not truncated
-    P.score_cols = TC;
+    P.score_cols = V.L->D.IC;
     P.score_rows = 0;
     P.use_visibility = 1;
   } else {
@@ -499,7 +500,7 @@ MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, in
         for (int k = 0; k < n; ++k) {
           if (V.k_status()[k] == 2 || V.k_deadline()[k] < 0) continue;
           int ti = V.k_type()[k];
-          if (!(V.k_alloc()[ti * TC + k] < V.k_cur()[ti * TC + k])) continue;
+          if (!(V.k_alloc2(ti, k) < V.k_cur2(ti, k))) continue;
           if (!vis_none && !S.known_bit(a, k)) continue;
           if (!(task_urgency(V, k, t) >= thr)) continue;
           double d = norm2(V.a_posx()[a] - V.k_posx()[k], V.a_posy()[a] - V.k_posy()[k]);

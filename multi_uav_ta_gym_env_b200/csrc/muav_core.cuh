@@ -172,7 +172,7 @@ struct Sim {
   MUAV_HD MUAV_NI_H void remove_agent_cap(int k, int a, double t0) {
     if (V.k_status()[k] == 2) return;
     int TC = V.L->D.TC;
-    _Pragma("unroll 1") for (int c = 0; c < 6; ++c) V.k_alloc()[c * TC + k] = V.k_alloc()[c * TC + k] - cap(a, c);
+    _Pragma("unroll 1") for (int c = 0; c < 6; ++c) V.k_alloc2(c, k) = V.k_alloc2(c, k) - cap(a, c);
     int tid = k + 1;
     int cnt = 0;
     double mn = 0.0, mx = 0.0;
@@ -203,7 +203,7 @@ struct Sim {
     if (V.k_status()[k] == 2) return;
     int TC = V.L->D.TC;
     double end = time_at + (double)C().duration[V.k_type()[k]];
-    _Pragma("unroll 1") for (int c = 0; c < 6; ++c) V.k_alloc()[c * TC + k] = V.k_alloc()[c * TC + k] + cap(a, c);
+    _Pragma("unroll 1") for (int c = 0; c < 6; ++c) V.k_alloc2(c, k) = V.k_alloc2(c, k) + cap(a, c);
     if (time_at < V.k_init()[k] || V.k_init()[k] == -1.0) {
       V.k_init()[k] = time_at;
       if (V.k_dtime()[k] == -1.0) V.k_dtime()[k] = end;
@@ -315,7 +315,7 @@ struct Sim {
     int ti = V.k_type()[k];
     int TC = V.L->D.TC;
     if (C().capability_mask && cap(a, ti) <= 0) return false;
-    if (C().saturate_mask && V.k_alloc()[ti * TC + k] >= V.k_org_ti()[k]) return false;
+    if (C().saturate_mask && V.k_alloc2(ti, k) >= V.k_org_ti()[k]) return false;
     return true;
   }
 
@@ -335,19 +335,29 @@ struct Sim {
   // Task ctor + env.tasks.append (DroneEnvComponents.py:224-263); returns task id or 0 on overflow
   MUAV_HD MUAV_NOINLINE int new_task(double px, double py, int ti) {
     int k = HIv(N_TASKS);
-    int TC = V.L->D.TC;
-    if (k >= TC) {
+    const int TC = V.L->D.TC, IC = V.L->D.IC;
+    if (k >= IC) {
+      HIv(ERRFLAGS) |= ERR_TASK_OVERFLOW;
+      return 0;
+    }
+    int slot = -1;
+    for (int sidx = 0; sidx < TC; ++sidx)
+      if (V.s_used()[sidx] == 0) { slot = sidx; break; }
+    if (slot < 0) {
       HIv(ERRFLAGS) |= ERR_TASK_OVERFLOW;
       return 0;
     }
     HIv(N_TASKS) = k + 1;
+    HIv(N_SLOTS_USED) += 1;
+    V.s_used()[slot] = (int16_t)(k + 1);
+    V.k_slot()[k] = (int16_t)slot;
     V.k_posx()[k] = px;
     V.k_posy()[k] = py;
     V.k_type()[k] = (int16_t)ti;
     V.k_status()[k] = 0;
-    _Pragma("unroll 1") for (int c = 0; c < 6; ++c) {
-      V.k_cur()[c * TC + k] = 0.0;
-      V.k_alloc()[c * TC + k] = 0.0;
+    for (int c = 0; c < 6; ++c) {
+      V.k_cur2(c, k) = 0.0;
+      V.k_alloc2(c, k) = 0.0;
     }
     V.k_done_ti()[k] = 0.0;
     V.k_org_ti()[k] = 0.0;
@@ -369,6 +379,44 @@ struct Sim {
     V.k_reached()[k] = 0;
     return k + 1;
   }
+  // A closed task keeps its slot only while something still refers to it: an agent queue or last_task (the
+  // switch penalty reads its type and position, DroneEnv.py:852,859), the escort map (_sync_escorts keeps visiting
+  // stale entries, :1977-2000) or a threat that is not destroyed (update_threats keeps writing its position, :1740).
+  // Everything else about a closed task is dead data in the reference (closed tasks never reopen, :1460), so the
+  // slot is recycled.  Spread over the lanes: lane <-> slot.
+  MUAV_HD void free_dead_tasks(int lane, int nlanes) {
+    const int TC = V.L->D.TC, Aa = A();
+    for (int sidx = lane; sidx < TC; sidx += nlanes) {
+      const int tid = V.s_used()[sidx];
+      if (tid == 0 || V.k_status()[tid - 1] != 2) continue;
+      bool ref = false;
+      for (int a = 0; a < Aa && !ref; ++a) {
+        if (V.a_last_task()[a] == tid || V.a_escort()[a] == tid) ref = true;
+        const int n = V.a_qlen()[a];
+        for (int q = 0; q < n && !ref; ++q) ref = V.a_queue()[q * Aa + a] == tid;
+      }
+      const int na = V.hi()[HI_N_ACTIVE];
+      for (int i = 0; i < na && !ref; ++i) {
+        const int hid = V.h_order()[i];
+        ref = V.h_status()[hid] != 2 && V.h_task()[hid] == tid;
+      }
+      if (ref) continue;
+      if (V.k_tbl_lo_raw()[sidx] == 0 && V.k_tbl_hi_raw()[sidx] == 0) {
+#if defined(__CUDA_ARCH__)
+        atomicAdd(&V.hi()[HI_N_FREED_EMPTY_TBL], 1);
+#else
+        V.hi()[HI_N_FREED_EMPTY_TBL] += 1;
+#endif
+      }
+#if defined(__CUDA_ARCH__)
+      atomicSub(&V.hi()[HI_N_SLOTS_USED], 1);
+#else
+      V.hi()[HI_N_SLOTS_USED] -= 1;
+#endif
+      V.s_used()[sidx] = 0;
+      V.k_slot()[tid - 1] = -1;
+    }
+  }
   // _register_dynamic_task (DroneEnv.py:1491-1504)
   MUAV_HD MUAV_NI_H void register_dynamic(int tid) {
     int k = tid - 1;
@@ -387,9 +435,10 @@ struct Sim {
   MUAV_HD MUAV_NI_H bool all_done() const {
     int n = V.hi()[HI_N_TASKS];
     for (int k = 0; k < n; ++k) {
+      if (V.k_status()[k] == 2) continue;  // closed tasks never block (and may have given their slot back)
       int ti = V.k_type()[k];
       if (V.k_kind()[k] == 1 || ti == TT_DET || ti == TT_HOLD) continue;
-      if (V.k_status()[k] != 2) return false;
+      return false;
     }
     return true;
   }
@@ -486,9 +535,9 @@ struct Sim {
             if (tid == 0) return;
             int k = tid - 1;
             int ht = V.h_type()[hid];
-            V.k_cur()[TT_INT * TC + k] = 2.0;
-            V.k_cur()[TT_ATT * TC + k] = C().cap_table[ht][3] * 2;
-            V.k_cur()[TT_DEF * TC + k] = C().cap_table[ht][2] * 2;
+            V.k_cur2(TT_INT, k) = 2.0;
+            V.k_cur2(TT_ATT, k) = C().cap_table[ht][3] * 2;
+            V.k_cur2(TT_DEF, k) = C().cap_table[ht][2] * 2;
             V.k_org_ti()[k] = 2.0;
             V.k_threat()[k] = (int16_t)hid;
             V.k_created()[k] = (int16_t)t;
@@ -501,7 +550,7 @@ struct Sim {
             V.h_order()[HIv(N_ACTIVE)] = (int16_t)hid;
             HIv(N_ACTIVE) += 1;
             int dk = V.h_det_task()[hid] - 1;
-            V.k_cur()[TT_DET * TC + dk] = V.k_cur()[TT_DET * TC + dk] - 1.0;
+            V.k_cur2(TT_DET, dk) = V.k_cur2(TT_DET, dk) - 1.0;
             register_dynamic(tid);
             push_event(EV_THREAT, tid);
             push_event(EV_RESET, TT_INT);
@@ -588,7 +637,7 @@ struct Sim {
     if (tid == 0) return;
     int k = tid - 1;
     int TC = V.L->D.TC;
-    V.k_cur()[TT_DEF * TC + k] = C().escort_requirement;
+    V.k_cur2(TT_DEF, k) = C().escort_requirement;
     V.k_org_ti()[k] = C().escort_requirement;
     V.k_kind()[k] = 1;
     V.k_prot_agent()[k] = (int16_t)a;
@@ -763,7 +812,7 @@ struct Sim {
     if (tid == 0) return;
     int k = tid - 1;
     int TC = V.L->D.TC;
-    V.k_cur()[ti * TC + k] = 1.0;
+    V.k_cur2(ti, k) = 1.0;
     V.k_org_ti()[k] = 1.0;
     V.k_created()[k] = (int16_t)HIv(T);
     HIv(N_ARRIVALS) += 1;
@@ -848,8 +897,9 @@ struct Sim {
     int n = HIv(N_TASKS);
     int t = HIv(T);
     for (int k = 0; k < n; ++k) {
+      if (V.k_status()[k] == 2) continue;
       int dl = V.k_deadline()[k];
-      if (dl < 0 || V.k_status()[k] == 2) continue;
+      if (dl < 0) continue;
       if (t > dl) expire_one(k);
     }
   }
@@ -1007,7 +1057,7 @@ struct Sim {
         else V.k_tbl_hi()[k] |= 1u << (a - 32);
         int ti = V.k_type()[k];
         double cp = cap(a, ti);
-        double missing = V.k_cur()[ti * TC + k] - (V.k_alloc()[ti * TC + k] - cp);
+        double missing = V.k_cur2(ti, k) - (V.k_alloc2(ti, k) - cp);
         missing = missing > 0 ? missing : 0.0;
         double rest = missing - cp;
         double added = missing - (rest > 0 ? rest : 0.0);
@@ -1109,7 +1159,7 @@ struct Sim {
             double t0 = 0.0;
             bool popped = task_done(a, cur, &t0);
             V.k_done_ti()[k] = V.k_done_ti()[k] + cap(a, ti);
-            _Pragma("unroll 1") for (int c = 0; c < 6; ++c) V.k_cur()[c * TC + k] = V.k_cur()[c * TC + k] - cap(a, c);
+            _Pragma("unroll 1") for (int c = 0; c < 6; ++c) V.k_cur2(c, k) = V.k_cur2(c, k) - cap(a, c);
             if (popped) {
               remove_agent_cap(k, a, t0);
             } else if (qfind(a, cur) >= 0) {
@@ -1182,10 +1232,10 @@ struct Sim {
       acc.time_pen = ddiv(-(double)(C().n_tasks_cfg - HIv(N_REACHED)), nt) * ddiv((double)t, (double)C().max_time_steps);
       acc.alloc_reward = 0.0;
       if (t > C().n_tasks_cfg + 1 && C().rw[5] != 0.0) {  // weight 0 (WPS flags): the count cannot reach the reward
-        int unalloc = 1;  // bucket 0 (idle) is always empty
+        int unalloc = 1 + HIv(N_FREED_EMPTY_TBL);  // bucket 0 (idle) is always empty; recycled tasks are counted
         int n = HIv(N_TASKS);
         for (int k = 0; k < n; ++k)
-          if (V.k_tbl_lo()[k] == 0 && V.k_tbl_hi()[k] == 0) ++unalloc;
+          if (V.k_slot()[k] >= 0 && V.k_tbl_lo()[k] == 0 && V.k_tbl_hi()[k] == 0) ++unalloc;
         acc.alloc_reward = -(double)unalloc;
       }
     }
@@ -1224,7 +1274,7 @@ struct Sim {
     const int words = (n + 31) >> 5;
     for (int w = 0; w < words; ++w) {
       const int k = (w << 5) + lane;
-      const bool ex = k < n && V.k_deadline()[k] >= 0 && V.k_status()[k] != 2 && t > V.k_deadline()[k];
+      const bool ex = k < n && V.k_status()[k] != 2 && V.k_deadline()[k] >= 0 && t > V.k_deadline()[k];
       unsigned m = __ballot_sync(0xffffffffu, ex);
       if (m != 0u) {
         if (lane == 0) {
@@ -1377,6 +1427,9 @@ struct Sim {
       }
 #endif
       if (lane == 0) r = step_post(alld, n_open);
+      MUAV_WARP_SYNC();
+      free_dead_tasks(lane, nlanes);
+      MUAV_WARP_SYNC();
       MUAV_TICK(9);
     }
     MUAV_CTA_SYNC(sync_mask & 16);

@@ -36,7 +36,7 @@ namespace muav {
   X(RECON_LOSSES) X(ESCORT_LOSSES) X(MUTUAL) X(PROT_REC_DONE) X(N_REACHED) X(CONCLUSION)          \
   X(CUR_AGENT) X(CUR_TGT) X(CUR_MISSION) X(ERRFLAGS) X(DONE) X(LAST_PLAN_STEP) X(N_REPLANS)       \
   X(N_CALLS) X(EV_TAGMASK) X(N_OPEN) X(GROUP_NEXT0) X(GROUP_NEXT1) X(GROUP_NEXT2) X(GROUP_NEXT3)  \
-  X(GROUP_NEXT4) X(GROUP_NEXT5) X(GROUP_NEXT6) X(GROUP_NEXT7) X(N_LSAP) X(PAD0) X(PAD1) X(PAD2)
+  X(GROUP_NEXT4) X(GROUP_NEXT5) X(GROUP_NEXT6) X(GROUP_NEXT7) X(N_LSAP) X(N_FREED_EMPTY_TBL) X(N_SLOTS_USED) X(PAD2)
 
 enum HdrI {
 #define X(n) HI_##n,
@@ -67,24 +67,28 @@ enum ErrBits {
   ERR_LSAP_INFEASIBLE = 32,
 };
 
+// TC = task SLOT capacity (tasks that are open or still referenced), IC = task ID capacity (tasks ever created)
 struct Dims {
-  int A, TC, HC, QC, EVC, NOBS, KW;
+  int A, TC, IC, HC, QC, EVC, NOBS, KW;
 };
 
 MUAV_HD inline Dims dims_of(const muav_config& c) {
   Dims d;
   d.A = c.n_agents;
   d.TC = c.task_cap;
+  d.IC = c.id_cap > c.task_cap ? c.id_cap : c.task_cap;
   d.HC = c.n_threats;
   d.QC = c.queue_cap;
   d.EVC = c.event_cap;
   d.NOBS = c.n_obstacles;
-  d.KW = (c.task_cap + 31) / 32;
+  d.KW = (d.IC + 31) / 32;
   return d;
 }
 
 // name, C type, element count.  Ordered by decreasing alignment (8, 4, 2 bytes).
-#define MUAV_FIELDS(X)              \
+// X  = plain array; XS = per-task array indexed by SLOT and accessed by task index through k_slot
+// (closed tasks that nothing references any more give their slot back, see Sim::free_dead_tasks).
+#define MUAV_FIELDS(X, XS)          \
   X(hf, double, HF_COUNT)           \
   X(a_posx, double, D.A)            \
   X(a_posy, double, D.A)            \
@@ -94,14 +98,14 @@ MUAV_HD inline Dims dims_of(const muav_config& c) {
   X(a_dist, double, D.A)            \
   X(a_caps, double, 6 * D.A)        \
   X(a_qtime, double, D.QC * D.A)    \
-  X(k_posx, double, D.TC)           \
-  X(k_posy, double, D.TC)           \
+  XS(k_posx, double, D.TC)          \
+  XS(k_posy, double, D.TC)          \
   X(k_cur, double, 6 * D.TC)        \
   X(k_alloc, double, 6 * D.TC)      \
-  X(k_done_ti, double, D.TC)        \
-  X(k_org_ti, double, D.TC)         \
-  X(k_init, double, D.TC)           \
-  X(k_dtime, double, D.TC)          \
+  XS(k_done_ti, double, D.TC)       \
+  XS(k_org_ti, double, D.TC)        \
+  XS(k_init, double, D.TC)          \
+  XS(k_dtime, double, D.TC)         \
   X(h_posx, double, D.HC)           \
   X(h_posy, double, D.HC)           \
   X(obst, double, 3 * D.NOBS)       \
@@ -113,8 +117,8 @@ MUAV_HD inline Dims dims_of(const muav_config& c) {
   X(a_last_task, int32_t, D.A)      \
   X(a_commit, int32_t, D.A)         \
   X(a_escort, int32_t, D.A)         \
-  X(k_tbl_lo, uint32_t, D.TC)       \
-  X(k_tbl_hi, uint32_t, D.TC)       \
+  XS(k_tbl_lo, uint32_t, D.TC)      \
+  XS(k_tbl_hi, uint32_t, D.TC)      \
   X(known, uint32_t, D.KW * D.A)    \
   X(open_mask, uint32_t, D.KW)      \
   X(events, int32_t, D.EVC)         \
@@ -123,20 +127,22 @@ MUAV_HD inline Dims dims_of(const muav_config& c) {
   X(a_re_eval, int16_t, D.A)        \
   X(a_qlen, int16_t, D.A)           \
   X(a_name_rank, int16_t, D.A)      \
-  X(k_deadline, int16_t, D.TC)      \
-  X(k_created, int16_t, D.TC)       \
-  X(k_reveal, int16_t, D.TC)        \
-  X(k_prot_task, int16_t, D.TC)     \
-  X(k_type, int16_t, D.TC)          \
-  X(k_status, int16_t, D.TC)        \
-  X(k_kind, int16_t, D.TC)          \
-  X(k_req_agents, int16_t, D.TC)    \
-  X(k_elig, int16_t, D.TC)          \
-  X(k_counted, int16_t, D.TC)       \
-  X(k_fq, int16_t, D.TC)            \
-  X(k_reached, int16_t, D.TC)       \
-  X(k_threat, int16_t, D.TC)        \
-  X(k_prot_agent, int16_t, D.TC)    \
+  X(k_slot, int16_t, D.IC)          \
+  X(k_status, int16_t, D.IC)        \
+  X(k_type, int16_t, D.IC)          \
+  X(k_reveal, int16_t, D.IC)        \
+  X(s_used, int16_t, D.TC)          \
+  XS(k_deadline, int16_t, D.TC)     \
+  XS(k_created, int16_t, D.TC)      \
+  XS(k_prot_task, int16_t, D.TC)    \
+  XS(k_kind, int16_t, D.TC)         \
+  XS(k_req_agents, int16_t, D.TC)   \
+  XS(k_elig, int16_t, D.TC)         \
+  XS(k_counted, int16_t, D.TC)      \
+  XS(k_fq, int16_t, D.TC)           \
+  XS(k_reached, int16_t, D.TC)      \
+  XS(k_threat, int16_t, D.TC)       \
+  XS(k_prot_agent, int16_t, D.TC)   \
   X(h_task, int16_t, D.HC)          \
   X(h_det_task, int16_t, D.HC)      \
   X(h_status, int16_t, D.HC)        \
@@ -150,7 +156,7 @@ MUAV_HD inline Dims dims_of(const muav_config& c) {
 
 struct Layout {
 #define X(name, type, count) int32_t o_##name;
-  MUAV_FIELDS(X)
+  MUAV_FIELDS(X, X)
 #undef X
   int32_t record_bytes;
   int32_t scratch_bytes;
@@ -177,24 +183,41 @@ MUAV_HD inline Layout make_layout(const muav_config& c) {
   off = align_up(off, (int32_t)sizeof(type)); \
   L.o_##name = off;                          \
   off += (int32_t)sizeof(type) * (int32_t)(count);
-  MUAV_FIELDS(X)
+  MUAV_FIELDS(X, X)
 #undef X
   L.record_bytes = align_up(off, 16);
   // per-warp scratch: allocator work arrays (muav_alloc.cuh carve_scratch) or the step's temporaries
-  int32_t s = alloc_scratch_bytes(D.A, D.TC);
+  int32_t s = alloc_scratch_bytes(D.A, D.TC) + 8 * (D.IC - D.TC);  // planner priorities are indexed by task id
   int32_t s2 = 8 * 4 * D.A + 2 * D.A + 16;
   if (s2 > s) s = s2;
   L.scratch_bytes = align_up(s, 16);
   return L;
 }
 
+// array of a slot-indexed task field, addressed by task index (id - 1)
+template <class T>
+struct SlotRef {
+  T* p;
+  const int16_t* slot;
+  MUAV_HD inline T& operator[](int k) const { return p[slot[k]]; }
+};
+
 struct View {
   char* base;
   const Layout* L;
 #define X(name, type, count) \
   MUAV_HD inline type* name() const { return (type*)(base + L->o_##name); }
-  MUAV_FIELDS(X)
+#define XS(name, type, count)                                                                   \
+  MUAV_HD inline SlotRef<type> name() const {                                                   \
+    return SlotRef<type>{(type*)(base + L->o_##name), (const int16_t*)(base + L->o_k_slot)};    \
+  }                                                                                             \
+  MUAV_HD inline type* name##_raw() const { return (type*)(base + L->o_##name); }
+  MUAV_FIELDS(X, XS)
 #undef X
+#undef XS
+  // requirement vectors: component c of task index k
+  MUAV_HD inline double& k_cur2(int c, int k) const { return k_cur()[c * L->D.TC + k_slot()[k]]; }
+  MUAV_HD inline double& k_alloc2(int c, int k) const { return k_alloc()[c * L->D.TC + k_slot()[k]]; }
 };
 
 }  // namespace muav

@@ -43,7 +43,7 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
     for (int k = 0; k < n; ++k) {
       if (V.k_status()[k] == 2) continue;
       int ti = V.k_type()[k];
-      if (!(V.k_alloc()[ti * TC + k] < V.k_cur()[ti * TC + k])) continue;  // AttentionRAH.py:67-71
+      if (!(V.k_alloc2(ti, k) < V.k_cur2(ti, k))) continue;  // AttentionRAH.py:67-71
       ++n_open_all;
       if (col < max_tasks) cols[col++] = (int16_t)k;
     }
@@ -67,7 +67,7 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
     }
     const int k = cols[j];
     const int ti = V.k_type()[k];
-    const double cur = V.k_cur()[ti * TC + k], al = V.k_alloc()[ti * TC + k];
+    const double cur = V.k_cur2(ti, k), al = V.k_alloc2(ti, k);
     double urg = urgency_of(V, k, t);
     int n_know_i = 0;
     for (int a = 0; a < A; ++a) n_know_i += view_known(V, a, k) ? 1 : 0;
@@ -123,7 +123,7 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
       if (V.k_status()[k] == 2) continue;
       if (V.k_deadline()[k] < 0) continue;
       int ti = V.k_type()[k];
-      if (!(V.k_alloc()[ti * TC + k] < V.k_cur()[ti * TC + k])) continue;
+      if (!(V.k_alloc2(ti, k) < V.k_cur2(ti, k))) continue;
       if (!vis_none && !view_known(V, a, k)) continue;
       if (urgency_of(V, k, t) >= urgent_thr) ++n_known_urgent;
     }
@@ -183,13 +183,13 @@ MUAV_HD inline void observe_env(const View& V, const muav_config& C, int max_row
     o[2] = V.k_posy()[k] / mc;
     o[3] = (double)V.k_status()[k];
     for (int c = 0; c < 6; ++c) {
-      o[4 + c] = V.k_cur()[c * TC + k];
-      o[10 + c] = V.k_alloc()[c * TC + k];
+      o[4 + c] = V.k_cur2(c, k);
+      o[10 + c] = V.k_alloc2(c, k);
     }
     o[16] = (V.k_init()[k] - (double)t) / mt;
     o[17] = (V.k_dtime()[k] - (double)t) / mt;
     o[18] = (double)tt / 6.0;
-    double unmet = dmax(V.k_cur()[tt * TC + k] - V.k_alloc()[tt * TC + k], 0.0);
+    double unmet = dmax(V.k_cur2(tt, k) - V.k_alloc2(tt, k), 0.0);
     o[19] = unmet / dmax(V.k_org_ti()[k], 1e-6);
     o[20] = dmin(((double)t - (double)V.k_created()[k]) / mt, 1.0);
     pad[rows] = 1;

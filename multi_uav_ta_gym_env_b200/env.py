@@ -605,7 +605,7 @@ class HungarianAllocator:
         if int(time_step) != int(env.time_steps):
             raise ValueError("time_step must be env.time_steps (the device allocator reads the env clock)")
         cfg = env._backend.cfg
-        A, TC = cfg.n_agents, cfg.task_cap
+        A, TC = cfg.n_agents, max(cfg.id_cap, cfg.task_cap)  # per-task arguments are indexed by task id
         reserved_names = set(reserved_agent_names or [])
         given = {a.id for a in agents}
         reserved = np.zeros(A, dtype=np.uint8)

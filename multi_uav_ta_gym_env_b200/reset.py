@@ -150,7 +150,8 @@ def pack_records(lib, cfg, scenarios) -> tuple[np.ndarray, np.ndarray]:
     F = lib.fields(cfg)
     rec = np.zeros((E, rb), dtype=np.uint8)
     A, TC, HC, QC = cfg.n_agents, cfg.task_cap, cfg.n_threats, cfg.queue_cap
-    KW = (TC + 31) // 32
+    IC = max(cfg.id_cap, TC)
+    KW = (IC + 31) // 32
 
     def view(name):
         off, cnt, dt = F[name]
@@ -163,6 +164,11 @@ def pack_records(lib, cfg, scenarios) -> tuple[np.ndarray, np.ndarray]:
     if n_tasks0 > TC:
         raise ValueError("task_cap too small")
     hi[:, H("N_TASKS")] = n_tasks0
+    hi[:, H("N_SLOTS_USED")] = n_tasks0
+    # initial tasks occupy slots 0..n0-1 (identity id -> slot map); every other id has no slot yet
+    view("k_slot")[:] = -1
+    view("k_slot")[:, :n_tasks0] = np.arange(n_tasks0)
+    view("s_used")[:, :n_tasks0] = np.arange(1, n_tasks0 + 1)
     hi[:, H("CONCLUSION")] = cfg.max_time_steps + 1
     hi[:, H("LAST_PLAN_STEP")] = -10**9
     hi[:, H("N_OPEN")] = n_tasks0

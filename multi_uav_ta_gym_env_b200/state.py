@@ -42,7 +42,8 @@ class RecordCodec:
         """Canonical snapshot (same keys and conventions as tests/golden/refsnap.snapshot)."""
         cfg = self.cfg
         A, TC, HC, QC = cfg.n_agents, cfg.task_cap, cfg.n_threats, cfg.queue_cap
-        KW = (TC + 31) // 32
+        IC = max(cfg.id_cap, TC)
+        KW = (IC + 31) // 32
         f = lambda n: self.field(rec_row, n)
         hi = f("hi")
         hf = f("hf")
@@ -73,35 +74,53 @@ class RecordCodec:
         s["a_queue"] = aq
         s["a_dist"] = f("a_dist").astype(np.float64)
         s["a_escort"] = i64(f("a_escort"))
-        s["k_pos"] = np.stack([f("k_posx")[:T], f("k_posy")[:T]], axis=1).astype(np.float64)
+        # per-task fields live in slots; tasks that gave their slot back (closed, unreferenced) read as blanks,
+        # which is also how the canonical snapshot treats them (tests/golden/refsnap.canonicalize)
+        slot = i64(f("k_slot")[:T])
+        has = slot >= 0
+        sl = np.where(has, slot, 0)
+
+        def per_task(name, blank=0):
+            v = f(name)[sl].astype(np.float64 if f(name).dtype.kind == "f" else np.int64)
+            v[~has] = blank
+            return v
+
+        s["k_pos"] = np.stack([per_task("k_posx"), per_task("k_posy")], axis=1)
         s["k_type"] = i64(f("k_type")[:T])
         s["k_status"] = i64(f("k_status")[:T])
-        s["k_cur"] = f("k_cur").reshape(6, TC)[:, :T].T.copy()
-        s["k_alloc"] = f("k_alloc").reshape(6, TC)[:, :T].T.copy()
-        s["k_done_ti"] = f("k_done_ti")[:T].astype(np.float64)
-        s["k_org_ti"] = f("k_org_ti")[:T].astype(np.float64)
-        s["k_init_time"] = f("k_init")[:T].astype(np.float64)
-        s["k_done_time"] = f("k_dtime")[:T].astype(np.float64)
-        s["k_created_at"] = i64(f("k_created")[:T])
-        s["k_deadline"] = i64(f("k_deadline")[:T])
-        s["k_counted"] = i64(f("k_counted")[:T])
-        s["k_final_quality"] = f("k_fq")[:T].astype(np.float64)
-        s["k_kind"] = i64(f("k_kind")[:T])
-        s["k_required_agents"] = i64(f("k_req_agents")[:T])
-        s["k_elig"] = i64(f("k_elig")[:T])
-        s["k_threat"] = i64(f("k_threat")[:T])
-        s["k_prot_agent"] = i64(f("k_prot_agent")[:T])
-        s["k_prot_task"] = i64(f("k_prot_task")[:T])
+        cur = f("k_cur").reshape(6, TC)[:, sl].T.copy()
+        alloc = f("k_alloc").reshape(6, TC)[:, sl].T.copy()
+        cur[~has] = 0.0
+        alloc[~has] = 0.0
+        s["k_cur"] = cur
+        s["k_alloc"] = alloc
+        s["k_done_ti"] = per_task("k_done_ti")
+        s["k_org_ti"] = per_task("k_org_ti")
+        s["k_init_time"] = per_task("k_init")
+        s["k_done_time"] = per_task("k_dtime")
+        s["k_created_at"] = per_task("k_created")
+        s["k_deadline"] = per_task("k_deadline")
+        s["k_counted"] = per_task("k_counted")
+        s["k_final_quality"] = per_task("k_fq").astype(np.float64)
+        s["k_kind"] = per_task("k_kind")
+        s["k_required_agents"] = per_task("k_req_agents")
+        s["k_elig"] = per_task("k_elig")
+        s["k_threat"] = per_task("k_threat")
+        s["k_prot_agent"] = per_task("k_prot_agent")
+        s["k_prot_task"] = per_task("k_prot_task")
         s["k_reveal_t"] = i64(f("k_reveal")[:T])
         det = np.full((T, A), -1.0)
         for a in range(A):
-            for sl in range(qlen[a]):
-                tid = int(q[a, sl])
+            for q_i in range(qlen[a]):
+                tid = int(q[a, q_i])
                 if tid > 0 and s["k_status"][tid - 1] != 2:
-                    det[tid - 1, a] = qt[a, sl]
+                    det[tid - 1, a] = qt[a, q_i]
         s["k_det_time"] = det
-        s["k_tbl_mask"] = (f("k_tbl_lo")[:T].astype(np.uint64) | (f("k_tbl_hi")[:T].astype(np.uint64) << np.uint64(32))).view(np.int64)
-        s["k_reached"] = i64(f("k_reached")[:T])
+        tbl = (f("k_tbl_lo")[sl].astype(np.uint64) | (f("k_tbl_hi")[sl].astype(np.uint64) << np.uint64(32)))
+        tbl[~has] = 0
+        s["k_tbl_mask"] = tbl.view(np.int64)
+        s["k_reached"] = per_task("k_reached")
+        s["k_has_slot"] = has.astype(np.int64)
         s["h_pos"] = np.stack([f("h_posx"), f("h_posy")], axis=1).astype(np.float64).reshape(HC, 2)
         for n in ("h_status", "h_type", "h_group", "h_ammo", "h_target", "h_mission", "h_task", "h_det_task", "h_spawned"):
             s[n] = i64(f(n))
@@ -118,9 +137,9 @@ class RecordCodec:
 
     def open_task_ids(self, rec_row):
         """env.last_tasks_info as task ids."""
-        TC = self.cfg.task_cap
+        IC = max(self.cfg.id_cap, self.cfg.task_cap)
         om = self.field(rec_row, "open_mask")
-        return [k + 1 for k in range(TC) if (int(om[k >> 5]) >> (k & 31)) & 1]
+        return [k + 1 for k in range(IC) if (int(om[k >> 5]) >> (k & 31)) & 1]
 
 
 def decode_events(n_events: int, events_row) -> list:

@@ -215,15 +215,54 @@ def snapshot(env) -> dict:
     return s
 
 
+DEAD_BLANK = {"k_pos": 0.0, "k_cur": 0.0, "k_alloc": 0.0, "k_done_ti": 0.0, "k_org_ti": 0.0, "k_init_time": 0.0,
+              "k_done_time": 0.0, "k_created_at": 0, "k_deadline": 0, "k_counted": 0, "k_final_quality": 0.0,
+              "k_kind": 0, "k_required_agents": 0, "k_elig": 0, "k_threat": 0, "k_prot_agent": 0, "k_prot_task": 0,
+              "k_tbl_mask": 0, "k_reached": 0}
+
+
+def dead_tasks(s: dict) -> np.ndarray:
+    """Closed tasks that nothing refers to any more: no agent queue or last_task (the switch penalty reads the old
+    head's type / position, DroneEnv.py:852,859), not an entry of _escort_by_recon (:1977-2000 keeps visiting stale
+    entries), not the task of a threat that is not destroyed (update_threats keeps writing its position, :1740).
+    Closed tasks never reopen (:1460), so every other field of such a task is dead data in the reference; the
+    batched state recycles their storage."""
+    status = np.asarray(s["k_status"])
+    T = len(status)
+    ref = np.zeros(T + 1, dtype=bool)
+    qlen = np.asarray(s["a_qlen"])
+    queue = np.asarray(s["a_queue"])
+    for a in range(len(qlen)):
+        for tid in queue[a, : qlen[a]]:
+            ref[int(tid)] = True
+    for tid in np.asarray(s["a_last_task"]):
+        if tid > 0:
+            ref[int(tid)] = True
+    for tid in np.asarray(s["a_escort"]):
+        if tid > 0:
+            ref[int(tid)] = True
+    h_status, h_task = np.asarray(s["h_status"]), np.asarray(s["h_task"])
+    for hid in np.asarray(s["h_order"]):
+        if h_status[hid] != 2 and h_task[hid] > 0:
+            ref[int(h_task[hid])] = True
+    return (status == 2) & ~ref[1:]
+
+
 def canonicalize(s: dict) -> dict:
-    """allocationDetails of a CLOSED task are dead data (Task.removeAgentCap is a no-op once
-    status == 2, DroneEnvComponents.py:282, and closed tasks never reopen, DroneEnv.py:1460):
-    the reference keeps stale entries, the batched state does not. Blank them."""
+    """(1) allocationDetails of a CLOSED task are dead data (Task.removeAgentCap is a no-op once status == 2,
+    DroneEnvComponents.py:282): the reference keeps stale entries, the batched state does not.
+    (2) every per-task field of a dead task (see dead_tasks) is blanked."""
+    out = dict(s)
     det = np.array(s["k_det_time"], dtype=np.float64, copy=True)
     closed = np.asarray(s["k_status"]) == 2
     det[closed, :] = -1.0
-    out = dict(s)
     out["k_det_time"] = det
+    dead = dead_tasks(s)
+    for name, blank in DEAD_BLANK.items():
+        v = np.array(s[name], copy=True)
+        v[dead] = blank
+        out[name] = v
+    out.pop("k_has_slot", None)
     return out
 
 
