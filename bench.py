@@ -286,6 +286,7 @@ def run_gpu_arm(args):
             episode_end()
     barrier()
     clocks = sampler.stop(first_sample)
+    err_flags = int(env.error_flags().abs().max().item())  # capacity / tape overflow bits: must stay 0
     step_ms = sum(a.elapsed_time(c) for a, b, c in ev)
     kern_ms = sum(b.elapsed_time(c) for a, b, c in ev)
     gpu_launches = launches["n"]
@@ -346,6 +347,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes,
                     "d2h_bytes_per_step": act_bytes + E * 10, "steps": Ke},
             "gpu_launches": gpu_launches,
+            "error_flags": err_flags,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "muav_step_kernel", "bytes_per_env_step": b_alg,

@@ -1428,8 +1428,12 @@ struct Sim {
 #endif
       if (lane == 0) r = step_post(alld, n_open);
       MUAV_WARP_SYNC();
-      free_dead_tasks(lane, nlanes);
-      MUAV_WARP_SYNC();
+      // recycle slots lazily: only when the next step could run out of them (new tasks per step <= threats in a
+      // burst + one arrival + one escort per agent).  Dead tasks are dead data whether recycled or not.
+      if (HIv(N_SLOTS_USED) + A() + V.L->D.HC + 2 > V.L->D.TC) {
+        free_dead_tasks(lane, nlanes);
+        MUAV_WARP_SYNC();
+      }
       MUAV_TICK(9);
     }
     MUAV_CTA_SYNC(sync_mask & 16);
