@@ -514,3 +514,38 @@ def test_largest_shape_burst_x8():
     for _ in range(150):
         o.step(apply_assign(o, h.allocate(o, time_step=o.t, events=o.last_events, known=o.visibility())))
     assert refsnap.digest(env.snapshot(0)) == refsnap.digest(o.snapshot())
+
+
+@pytest.mark.parametrize("case,planner", [("WPS_hard", "local"), ("WPS_commit", "urgency_commit"), ("WPS_escort", "urgency_coalition")])
+def test_random_members_of_a_large_batch_match_the_oracle(case, planner):
+    """Full-size batches (2048 / 4096 envs, one 150-step launch); a random sample of members is re-run on the oracle."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+    from oracle.hungarian import OracleHungarian, apply_assign
+    from oracle import planners as oplan
+    from oracle import tokens as otok
+    from oracle.sim import OracleEnv
+
+    cfg = wps_config(case)
+    E = 4096 if case != "WPS_escort" else 2048
+    base = 50_000
+    env = make_env(cfg, list(range(base, base + E)))
+    spec = {"local": AllocSpec.local_hungarian(20), "urgency_commit": AllocSpec.urgency_commit(15),
+            "urgency_coalition": AllocSpec.urgency_coalition(12)}[planner]
+    env.step_allocated(spec, n_steps=150)
+    assert int(env.error_flags().abs().max().item()) == 0
+    rng = np.random.default_rng(7)
+    for e in sorted(rng.choice(E, size=10, replace=False).tolist()):
+        o = OracleEnv(cfg).reset(base + e)
+        h = OracleHungarian(10**9 if planner == "urgency_coalition" else 20, 1200.0)
+        for _ in range(150):
+            pairs = []
+            if planner == "local":
+                pairs = h.allocate(o, time_step=o.t, events=o.last_events, known=o.visibility())
+            elif planner == "urgency_commit":
+                if otok.hybrid_should_replan(o, o.last_events, 15):
+                    pairs = oplan.urgency_commit_plan(o, h)
+            else:
+                if o.t == 0 or o.t % 12 == 0 or len(o.last_events) > 0:
+                    pairs = oplan.urgency_coalition_plan(o, h)
+            o.step(apply_assign(o, pairs))
+        assert refsnap.digest(env.snapshot(e)) == refsnap.digest(o.snapshot()), (case, base + e)
