@@ -40,6 +40,9 @@ ENVS_PER_GPU = 4096
 EPISODE = 150
 HYBRID_INTERVAL = 15
 METRIC = "WPS_hard env-steps/sec (batched, 1/2/4/8 B200) vs ref CPU; % HBM roofline"
+# dram__bytes_read.sum + dram__bytes_write.sum per muav_step_kernel launch (4096 WPS_hard envs), ncu --set full capture
+# gpurun_out/prof_step_r1_h.ncu-rep summarised in profiles/r01_step_kernel_ncu_v2.md: 50.7 MB + 5.1..6.6 MB
+NCU_TRAFFIC_BYTES = 56.6e6
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
@@ -350,7 +353,12 @@ def run_gpu_arm(args):
             "error_flags": err_flags,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "muav_step_kernel", "bytes_per_env_step": b_alg,
+                         "traffic": NCU_TRAFFIC_BYTES if (wl == "hard_pair" and E == ENVS_PER_GPU) else None,
+                         "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
+                                         "capture (profiles/r01_step_kernel_ncu_v2.md); the write-back of the records is "
+                                         "still in L2 when the kernel ends, so it is below the algorithmic bytes",
+                         "algorithmic_bytes_per_launch": E * b_alg,
+                         "kernel": "muav_step_kernel", "bytes_per_env_step": b_alg,
                          "kernel_ms_per_launch": kern_ms / K, "peak_source": peak_src,
                          "kernel_share_of_step": kern_ms / step_ms},
             "episode_stats": {k: stats[k] for k in ("episodes", "mean_S_WPS", "sd_S_WPS", "mean_n_on_time",

@@ -165,6 +165,13 @@ int muav_tokens_pair(const muav_config* cfg, const void* d_records, int max_task
                      float* d_task_feats, uint8_t* d_task_mask, float* d_agent_feats, uint8_t* d_agent_mask,
                      float* d_edge_valid, int32_t* d_task_ids, int n_envs, void* stream);
 
+/* Commit tokens = enrich_commit_tokens(build_att_tokens(env)) (AttentionCommit.py:49-62, AttentionRAH.py:50-173):
+ * as muav_tokens_pair but agent_feats is [E, max_agents, 13] (last column: remaining commit-lock fraction) and there is
+ * no edge_valid. */
+int muav_tokens_commit(const muav_config* cfg, const void* d_records, int max_tasks, int max_agents, float* d_task_feats,
+                       uint8_t* d_task_mask, float* d_agent_feats13, uint8_t* d_agent_mask, int32_t* d_task_ids, int n_envs,
+                       void* stream);
+
 /* Observation tensors (DroneEnv.py:365-492).  tasks_info [E, max_rows, 21] f64 per open task:
  * id, x/max_coord, y/max_coord, status, current_reqs[6], alloc_reqs[6], init_time, end_time, type_idx, unmet, age
  * (status = -1 marks padding rows); pad_mask [E,max_rows] u8 ("mask"); legal_mask [E, n_agents, max_rows] u8;

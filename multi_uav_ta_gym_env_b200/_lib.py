@@ -88,7 +88,7 @@ class MuavAttPairOffsets(C.Structure):
 ABI_SYMBOLS = [
     "muav_version", "muav_config_size", "muav_record_bytes", "muav_scratch_bytes", "muav_num_fields",
     "muav_field_info", "muav_header_index", "muav_step", "muav_allocate", "muav_step_host", "muav_lsap",
-    "muav_avoid_obstacles", "muav_metric_name", "muav_metrics", "muav_tokens_pair", "muav_observe",
+    "muav_avoid_obstacles", "muav_metric_name", "muav_metrics", "muav_tokens_pair", "muav_tokens_commit", "muav_observe",
     "muav_att_pair_scores",
 ]
 
@@ -187,6 +187,8 @@ class CudaLib(Lib):
         d.muav_metrics.argtypes = [C.POINTER(MuavConfig), P, P, C.c_int, P]
         d.muav_tokens_pair.restype = C.c_int
         d.muav_tokens_pair.argtypes = [C.POINTER(MuavConfig), P, C.c_int, C.c_int, P, P, P, P, P, P, C.c_int, P]
+        d.muav_tokens_commit.restype = C.c_int
+        d.muav_tokens_commit.argtypes = [C.POINTER(MuavConfig), P, C.c_int, C.c_int, P, P, P, P, P, C.c_int, P]
         d.muav_att_pair_scores.restype = C.c_int
         d.muav_att_pair_scores.argtypes = [P, C.POINTER(MuavAttPairOffsets), P, P, P, P, P, P, P, C.c_int, C.c_int,
                                            C.c_int, C.c_float, P, P]

@@ -269,6 +269,21 @@ class BatchedMultiUAVEnv:
         return {"task_feats": tf, "task_mask": tm.bool(), "agent_feats": af, "agent_mask": am.bool(),
                 "edge_valid": ev, "task_ids": ids}
 
+    def tokens_commit(self, max_tasks=32, max_agents=16):
+        """enrich_commit_tokens(build_att_tokens(env)) for every environment (AttentionCommit.py:49-62)."""
+        E, dev = self.n_envs, self.device
+        tf = torch.empty(E, max_tasks, 13, dtype=torch.float32, device=dev)
+        tm = torch.empty(E, max_tasks, dtype=torch.uint8, device=dev)
+        af = torch.empty(E, max_agents, 13, dtype=torch.float32, device=dev)
+        am = torch.empty(E, max_agents, dtype=torch.uint8, device=dev)
+        ids = torch.empty(E, max_tasks, dtype=torch.int32, device=dev)
+        rc = self.lib.dll.muav_tokens_commit(C.byref(self.cfg), self.records.data_ptr(), max_tasks, max_agents,
+                                             tf.data_ptr(), tm.data_ptr(), af.data_ptr(), am.data_ptr(), ids.data_ptr(),
+                                             E, self._stream())
+        _lib.check(rc, "muav_tokens_commit")
+        self.launches += 1
+        return {"task_feats": tf, "task_mask": tm.bool(), "agent_feats": af, "agent_mask": am.bool(), "task_ids": ids}
+
     def observe(self, max_rows: Optional[int] = None):
         """Observation tensors of _generate_observations (DroneEnv.py:468-492); see include/muav.h."""
         E, A, dev = self.n_envs, self.n_agents, self.device

@@ -302,7 +302,8 @@ __global__ void muav_metrics_kernel(const __grid_constant__ muav_config cfg, con
 __global__ void __launch_bounds__(128) muav_tokens_pair_kernel(const __grid_constant__ muav_config cfg,
                                                                const __grid_constant__ Layout L, const char* records,
                                                                int max_tasks, int max_agents, float* tf, uint8_t* tm,
-                                                               float* af, uint8_t* am, float* ev, int32_t* ids, int n) {
+                                                               float* af, uint8_t* am, float* ev, int32_t* ids, int n,
+                                                               int af_dim) {
   __shared__ int16_t cols[4][MUAV_MAX_TASK_CAP + 2];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * 4 + w;
@@ -311,8 +312,9 @@ __global__ void __launch_bounds__(128) muav_tokens_pair_kernel(const __grid_cons
   V.base = (char*)records + (size_t)e * L.record_bytes;
   V.L = &L;
   tokens_pair_env(V, cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * 13, tm + (size_t)e * max_tasks,
-                  af + (size_t)e * max_agents * 12, am + (size_t)e * max_agents,
-                  ev + (size_t)e * max_agents * max_tasks, ids + (size_t)e * max_tasks, cols[w], lane, 32);
+                  af + (size_t)e * max_agents * af_dim, am + (size_t)e * max_agents,
+                  ev ? ev + (size_t)e * max_agents * max_tasks : nullptr, ids + (size_t)e * max_tasks, cols[w], lane, 32,
+                  af_dim);
 }
 
 __global__ void muav_observe_kernel(const __grid_constant__ muav_config cfg, const __grid_constant__ Layout L,
@@ -516,7 +518,21 @@ int muav_tokens_pair(const muav_config* cfg, const void* d_records, int max_task
   if (max_tasks > MUAV_MAX_TASK_CAP) return -22;
   muav_tokens_pair_kernel<<<(n_envs + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
       *cfg, L, (const char*)d_records, max_tasks, max_agents, d_task_feats, d_task_mask, d_agent_feats, d_agent_mask,
-      d_edge_valid, d_task_ids, n_envs);
+      d_edge_valid, d_task_ids, n_envs, 12);
+  return cuda_rc(cudaGetLastError());
+}
+
+int muav_tokens_commit(const muav_config* cfg, const void* d_records, int max_tasks, int max_agents, float* d_task_feats,
+                       uint8_t* d_task_mask, float* d_agent_feats13, uint8_t* d_agent_mask, int32_t* d_task_ids, int n_envs,
+                       void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (n_envs <= 0) return n_envs == 0 ? 0 : -22;
+  if (max_tasks < 1 || max_agents < 1 || max_tasks > MUAV_MAX_TASK_CAP) return -22;
+  Layout L = make_layout(*cfg);
+  muav_tokens_pair_kernel<<<(n_envs + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+      *cfg, L, (const char*)d_records, max_tasks, max_agents, d_task_feats, d_task_mask, d_agent_feats13, d_agent_mask,
+      nullptr, d_task_ids, n_envs, 13);
   return cuda_rc(cudaGetLastError());
 }
 

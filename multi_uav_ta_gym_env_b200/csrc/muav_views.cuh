@@ -27,9 +27,11 @@ MUAV_HD inline bool view_known(const View& V, int a, int k) {
 // agent_mask [max_agents] u8, edge_valid [max_agents,max_tasks] f32, task_ids [max_tasks] i32.
 // Work is spread over (lane, nlanes): lane 0 builds the ordered token-task list in `cols`
 // (int16 scratch, >= max_tasks entries + 2), then columns and agent rows are independent.
+// af_dim = 12 (Att-Pair / Att-RAH agent features) or 13: enrich_commit_tokens (AttentionCommit.py:49-62) appends the
+// remaining commit-lock fraction min(max(commit_until - t, 0) / max(commit_horizon or 25, 1), 1); ev may be null.
 MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max_tasks, int max_agents, float* tf,
                                     uint8_t* tm, float* af, uint8_t* am, float* ev, int32_t* ids, int16_t* cols,
-                                    int lane, int nlanes) {
+                                    int lane, int nlanes, int af_dim = 12) {
   const int A = V.L->D.A, TC = V.L->D.TC;
   const int n = V.hi()[HI_N_TASKS];
   const int t = V.hi()[HI_T];
@@ -102,8 +104,8 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
   }
   // ---- agent rows (row i = i-th live agent)
   for (int i = lane; i < max_agents; i += nlanes) {
-    float* f = af + i * 12;
-    float* evr = ev + i * max_tasks;
+    float* f = af + i * af_dim;
+    float* evr = ev ? ev + i * max_tasks : nullptr;
     int a = -1, seen = 0;
     for (int b = 0; b < A; ++b) {
       if (V.a_state()[b] == -1) continue;
@@ -112,8 +114,9 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
     }
     if (a < 0) {
       am[i] = 1;
-      for (int c = 0; c < 12; ++c) f[c] = 0.0f;
-      for (int j = 0; j < max_tasks; ++j) evr[j] = 0.0f;
+      for (int c = 0; c < af_dim; ++c) f[c] = 0.0f;
+      if (evr)
+        for (int j = 0; j < max_tasks; ++j) evr[j] = 0.0f;
       continue;
     }
     int at = V.a_type()[a];
@@ -139,9 +142,14 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
     f[9] = (float)((double)t / (double)horizon);
     f[10] = (float)dmin((double)n_known_urgent / (double)(n_open_all > 1 ? n_open_all : 1), 1.0);
     f[11] = at == UT_F2 ? 1.0f : 0.0f;
+    if (af_dim > 12) {
+      const int hz = C.commit_horizon != 0 ? C.commit_horizon : 25;
+      const double rem = dmax((double)V.a_commit()[a] - (double)t, 0.0);
+      f[12] = (float)dmin(rem / (double)(hz > 1 ? hz : 1), 1.0);
+    }
     am[i] = 0;
     // edge_valid (PairCostHybrid.py:41-60)
-    for (int j = 0; j < max_tasks; ++j) {
+    for (int j = 0; evr && j < max_tasks; ++j) {
       float v = 0.0f;
       if (j < ncol) {
         int k = cols[j];

@@ -108,6 +108,21 @@ def build_pair_tokens(env, max_tasks=32, max_agents=16):
             "edge_valid": edge_valid, "task_ids": ids, "open_tasks": [k + 1 for k in kept], "live": live, "vis": vis}
 
 
+def commit_tokens(env, max_tasks=32, max_agents=16):
+    """enrich_commit_tokens(build_att_tokens(env)) (AttentionCommit.py:49-62): agent feature 13 = commit-lock remainder."""
+    tok = build_pair_tokens(env, max_tasks, max_agents)
+    af = tok["agent_feats"]
+    horizon = max(int(env.commit_horizon or 25), 1)
+    extra = np.zeros((af.shape[0], 1), dtype=np.float32)
+    for i, a in enumerate(tok["live"][: af.shape[0]]):
+        rem = max(float(env.a_commit_until[a] or 0) - float(env.t), 0.0)
+        extra[i, 0] = min(rem / horizon, 1.0)
+    out = dict(tok)
+    out["agent_feats"] = np.concatenate([af, extra], axis=1)
+    out.pop("edge_valid")
+    return out
+
+
 def pair_plan(env, hung, scores, max_tasks=32, max_agents=16):
     """PairCostHybrid.plan(scores=...) -> ordered [(agent_id, task_id)]."""
     tok = build_pair_tokens(env, max_tasks, max_agents)

@@ -107,6 +107,28 @@ def test_env_and_allocator_facade_follow_the_reference_loop(case, seed, interval
     assert ref.compute_s_wps() == mine.compute_s_wps() and ref.compute_s_esc() == mine.compute_s_esc()
 
 
+def _load_oracle_from_snapshot(orc, facade_env):
+    """Minimal oracle view of the facade's current state (only what the token builders read)."""
+    s = facade_env._snap
+    A, T = len(s["a_state"]), s["n_tasks"]
+    orc.t = s["t"]
+    orc.n_agents = A
+    orc.a_pos = [tuple(p) for p in s["a_pos"]]
+    orc.a_state = list(s["a_state"])
+    orc.a_type = list(s["a_type"])
+    orc.a_caps = [list(c) for c in s["a_caps"]]
+    orc.a_commit_until = [a.commit_until for a in facade_env.agents_obj]  # planners write locks between steps
+    orc.a_queue = [list(s["a_queue"][a][: s["a_qlen"][a]]) for a in range(A)]
+    orc.k_pos = [tuple(p) for p in s["k_pos"]]
+    orc.k_status = list(s["k_status"])
+    orc.k_type = list(s["k_type"])
+    orc.k_cur = [list(c) for c in s["k_cur"]]
+    orc.k_alloc = [list(c) for c in s["k_alloc"]]
+    orc.k_deadline = list(s["k_deadline"])
+    orc.k_elig = list(s["k_elig"])
+    orc.known = [list(r) for r in s["known"]]
+
+
 def hybrid_should_replan(env, events, interval, tags):
     return env.time_steps == 0 or env.time_steps % interval == 0 or any(ev[0] in tags for ev in events)
 
@@ -163,6 +185,18 @@ def test_unmodified_reference_hybrids_run_on_the_facade(planner, case, seed, all
                 mres = mp.plan(mine, mh, events=mevents, force=True)[0]
             assert to_ids(ref, rres) == to_ids(mine, mres), t
             assert [a.commit_until for a in ref.agents_obj] == [a.commit_until for a in mine.agents_obj], t
+            if planner == "urgency_commit" and t % 15 == 0:
+                # oracle restatement of enrich_commit_tokens(build_att_tokens) pinned against the reference
+                from TaskAllocation.Hybrid.AttentionCommit import enrich_commit_tokens
+                from TaskAllocation.Hybrid.AttentionRAH import build_att_tokens
+                from oracle import tokens as otok
+                from oracle.sim import OracleEnv
+                want = enrich_commit_tokens(ref, build_att_tokens(ref))
+                shadow = OracleEnv(refshim.wps_config(case))
+                _load_oracle_from_snapshot(shadow, mine)
+                got = otok.commit_tokens(shadow, 32, 16)
+                for k in ("task_feats", "task_mask", "agent_feats", "agent_mask"):
+                    assert np.array_equal(want[k], got[k]), (t, k)
         ro, rr, rterm, rtrunc, ri = ref.step(apply_assign(ref, rres))
         mo, mr, mterm, mtrunc, mi = mine.step(apply_assign(mine, mres))
         assert rr == mr, t

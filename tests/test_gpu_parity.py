@@ -549,3 +549,32 @@ def test_random_members_of_a_large_batch_match_the_oracle(case, planner):
                     pairs = oplan.urgency_coalition_plan(o, h)
             o.step(apply_assign(o, pairs))
         assert refsnap.digest(env.snapshot(e)) == refsnap.digest(o.snapshot()), (case, base + e)
+
+
+def test_commit_tokens_match_oracle():
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+    from oracle.hungarian import OracleHungarian, apply_assign
+    from oracle import planners as oplan
+    from oracle import tokens as otok
+    from oracle.sim import OracleEnv
+
+    cfg = wps_config("WPS_commit")
+    seeds = [2, 3]
+    env = make_env(cfg, seeds)
+    oracles = [OracleEnv(cfg).reset(s) for s in seeds]
+    hungs = [OracleHungarian(20, 1200.0) for _ in seeds]
+    spec = AllocSpec.urgency_commit(15)
+    saw_lock = False
+    for t in range(120):
+        if t % 6 == 0:
+            tok = {k: v.cpu().numpy() for k, v in env.tokens_commit(32, 16).items()}
+            for e, o in enumerate(oracles):
+                want = otok.commit_tokens(o, 32, 16)
+                for k in ("task_feats", "task_mask", "agent_feats", "agent_mask", "task_ids"):
+                    assert np.array_equal(tok[k][e], want[k]), (t, e, k)
+                saw_lock = saw_lock or bool((want["agent_feats"][:, 12] > 0).any())
+        env.step_allocated(spec, 1)
+        for e, o in enumerate(oracles):
+            pairs = oplan.urgency_commit_plan(o, hungs[e]) if otok.hybrid_should_replan(o, o.last_events, 15) else []
+            o.step(apply_assign(o, pairs))
+    assert saw_lock
