@@ -22,7 +22,7 @@ constexpr int D = 64;      // d_model
 constexpr int NH = 4;      // heads
 constexpr int HD = 16;     // head dim
 constexpr int FF = 128;    // dim_feedforward
-constexpr int TS = 52;     // token stride of transposed activations [feature][token] (>= 48, multiple of 4)
+constexpr int TS = 48;     // token stride of transposed activations [feature][token] (max 48 tokens, multiple of 4)
 constexpr int WS = 68;     // row stride of the staged transposed weight tile [k][o]
 constexpr int NT = 256;    // threads per CTA
 constexpr int TF = 13, AF = 12;
@@ -142,7 +142,7 @@ __device__ void attention_t(const float* __restrict__ qkv_t, int q0, int q1, int
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(NT, 3) att_pair_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(16) float sm[];
   float* x_t = sm;                       // [D][TS]   tokens / encoder output h
   float* y_t = x_t + D * TS;             // [D][TS]   attention output / residual sums / a_h', t_h'
@@ -237,29 +237,39 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
   }
   __syncthreads();
   const float* ev = P.edge_valid + (size_t)e * MA * MT;
-  for (int pair = tid; pair < na * nt; pair += NT) {
-    const int i = pair / nt, j = pair - i * nt;
-    float u[D];
+  // two lanes per pair: each owns half of the 64 product features (first layer) and half of the 32 hidden
+  // units (second layer); partial sums meet through a shuffle.  Keeps the register count low enough for
+  // three CTAs per SM.
+  const int npairs = na * nt;
+  const int hp = tid & 1;
+  const int d0 = hp * 32, p0 = hp * 16;
+  for (int base = 0; base < npairs; base += NT / 2) {
+    const int pair = base + (tid >> 1);
+    const bool valid = pair < npairs;
+    const int pc = valid ? pair : 0;
+    const int i = pc / nt, j = pc - i * nt;
+    float u[32];
 #pragma unroll
-    for (int d = 0; d < D; ++d) u[d] = z_t[d * TS + i] * z_t[d * TS + na + j];
-    float h2[32];
+    for (int d = 0; d < 32; ++d) u[d] = z_t[(d0 + d) * TS + i] * z_t[(d0 + d) * TS + na + j];
+    float h2[16];
 #pragma unroll
-    for (int p = 0; p < 32; ++p) h2[p] = w[o.head2_b + p];
+    for (int p = 0; p < 16; ++p) h2[p] = w[o.head2_b + p0 + p];
     for (int oo = 0; oo < D; ++oo) {
-      float acc = y_t[oo * TS + i] + x_t[oo * TS + na + j];
-      const float4* wr = (const float4*)&wat[oo * WS];
+      float acc = 0.0f;
+      const float4* wr = (const float4*)&wat[oo * WS + d0];
 #pragma unroll
-      for (int d4 = 0; d4 < D / 4; ++d4) {
+      for (int d4 = 0; d4 < 8; ++d4) {
         const float4 ww = wr[d4];
         acc = fmaf(ww.x, u[4 * d4], acc);
         acc = fmaf(ww.y, u[4 * d4 + 1], acc);
         acc = fmaf(ww.z, u[4 * d4 + 2], acc);
         acc = fmaf(ww.w, u[4 * d4 + 3], acc);
       }
-      acc = fmaxf(acc, 0.0f);
-      const float4* w2 = (const float4*)&w2t[oo * 36];
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc = fmaxf(acc + y_t[oo * TS + i] + x_t[oo * TS + na + j], 0.0f);
+      const float4* w2 = (const float4*)&w2t[oo * 36 + p0];
 #pragma unroll
-      for (int p4 = 0; p4 < 8; ++p4) {
+      for (int p4 = 0; p4 < 4; ++p4) {
         const float4 ww = w2[p4];
         h2[4 * p4] = fmaf(ww.x, acc, h2[4 * p4]);
         h2[4 * p4 + 1] = fmaf(ww.y, acc, h2[4 * p4 + 1]);
@@ -267,10 +277,12 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
         h2[4 * p4 + 3] = fmaf(ww.w, acc, h2[4 * p4 + 3]);
       }
     }
-    float logit = w[o.head3_b];
+    float logit = 0.0f;
 #pragma unroll
-    for (int p = 0; p < 32; ++p) logit = fmaf(w[o.head3_w + p], fmaxf(h2[p], 0.0f), logit);
-    sc[i * MT + j] = tanhf(logit) * P.clamp * ev[i * MT + j];
+    for (int p = 0; p < 16; ++p) logit = fmaf(w[o.head3_w + p0 + p], fmaxf(h2[p], 0.0f), logit);
+    logit += __shfl_xor_sync(0xffffffffu, logit, 1);
+    logit += w[o.head3_b];
+    if (valid && hp == 0) sc[i * MT + j] = tanhf(logit) * P.clamp * ev[i * MT + j];
   }
 }
 
