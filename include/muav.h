@@ -18,6 +18,8 @@
  *   muav_avoid_obstacles      -> core_sim.SimCore.avoid_obstacles  core_sim/src/sim_core.rs:24-59 (PyO3 export lib.rs:10-18)
  *   muav_tokens_pair          -> build_pair_tokens             TaskAllocation/Hybrid/PairCostHybrid.py:31-65
  *                                (build_att_tokens             TaskAllocation/Hybrid/AttentionRAH.py:50-173)
+ *   muav_tokens_commit        -> enrich_commit_tokens          TaskAllocation/Hybrid/AttentionCommit.py:49-62
+ *   muav_tokens_escort        -> build_escort_tokens           TaskAllocation/Hybrid/AttentionEscort.py:76-241
  *   muav_observe              -> _generate_observations/get_task_info  mUAV_TA/DroneEnv.py:365-492
  *   muav_metrics              -> calculate_metrics / compute_s_wps / compute_s_esc  DroneEnv.py:1231-1337,2002-2011
  *   muav_field_info / muav_record_bytes: layout of one environment record (host packing at reset,
@@ -76,13 +78,21 @@ typedef struct muav_alloc_opts {
   int32_t event_mask;      /* bit i = tag i triggers (0 Reset_Allocation 1 Agent_Fail 2 New_Threat 3 Escort_Created 4 Escort_Retired) */
   int32_t use_visibility;  /* agent_known_ids=env.agent_visibility_map() */
   int32_t pair_tokens;     /* 1: task list = build_pair_tokens' open list (PairCostHybrid.py:34-36, AttentionRAH.py:67-71)
-                                 and d_edge_scores is indexed in token space [live agent row, token task column] */
+                                 and d_edge_scores is indexed in token space [live agent row, token task column];
+                              2: d_edge_scores is indexed [live agent row, position in d_task_order] (the layout of
+                                 muav_tokens_escort; AttentionEscort.edge_score_dict, AttentionEscort.py:478-489) */
   int32_t score_rows, score_cols; /* edge score tensor shape per env (max_agents, max_tasks) */
   int32_t score_f64;       /* 1: d_edge_scores points to double, else float */
   int32_t planner;         /* 0 none; 1 UrgencyCommit.plan (AttentionCommit.py:310-357): priorities 0.6 urg + 0.4 scarcity,
                                 committed agents reserved, lock ranking, commit_until writes;
                               2 UrgencyCoalition.plan (AttentionEscort.py:720-767): engineered edge scores, committed agents
-                                reserved, every assigned agent locked for commit_horizon */
+                                reserved, every assigned agent locked for commit_horizon;
+                              3 AttentionCommit._plan_from_scores (AttentionCommit.py:266-300): priorities
+                                0.35 urg + 0.40 d_plan_pri[column] + 0.25 scarcity over build_att_tokens' open list, committed
+                                agents reserved, free assigned agents whose d_plan_commit[row] >= commit_threshold are locked;
+                              4 AttentionEscort._plan_from_scores (AttentionEscort.py:500-517): d_edge_scores in
+                                muav_tokens_escort layout over d_task_order, committed agents reserved, every assigned
+                                agent locked for commit_horizon */
   int32_t reserved1;
   double commit_fraction;  /* UrgencyCommit(commit_fraction=0.35) */
   double max_coord;        /* HungarianAllocator(max_coord=...) */
@@ -92,6 +102,9 @@ typedef struct muav_alloc_opts {
   const uint8_t* d_reserved;   /* [E, n_agents] 1 = excluded (reserved_agent_names) or NULL */
   const int32_t* d_task_order; /* [E, id_cap] the `tasks` argument: task indices (id-1) in the caller's order, -1 terminated;
                                   NULL = every open task in id order (_open_tasks, paper_eval.py:96-101) */
+  const float* d_plan_pri;     /* planner 3: [E, score_cols] AttCommitNet priorities by token task column */
+  const float* d_plan_commit;  /* planner 3: [E, score_rows] AttCommitNet commit gates by live-agent row */
+  double commit_threshold;     /* planner 3: AttentionCommit(commit_threshold=0.5) */
 } muav_alloc_opts;
 
 /* Per-step outputs (any pointer may be NULL). */
@@ -171,6 +184,17 @@ int muav_tokens_pair(const muav_config* cfg, const void* d_records, int max_task
 int muav_tokens_commit(const muav_config* cfg, const void* d_records, int max_tasks, int max_agents, float* d_task_feats,
                        uint8_t* d_task_mask, float* d_agent_feats13, uint8_t* d_agent_mask, int32_t* d_task_ids, int n_envs,
                        void* stream);
+
+/* Escort tokens = build_escort_tokens(env, max_tasks=48, max_agents=16) (AttentionEscort.py:76-241, with
+ * _open_tasks_residual :31-43, _threat_stats :46-65, _task_priority_key :68-73): tasks known to at least one live agent
+ * (all open tasks if none), sorted by the priority key (stable), first max_tasks kept.
+ * task_feats [E,max_tasks,22] f32, task_mask [E,max_tasks] u8, agent_feats [E,max_agents,16] f32, agent_mask [E,max_agents] u8,
+ * edge_valid [E,max_agents,max_tasks] f32, task_ids [E,max_tasks] i32 in column order (0 = padding); d_task_order
+ * (optional) [E, id_cap] i32: the kept task indices (id-1) in column order, -1 terminated -- the `tasks` argument and the
+ * score layout of planner 4 (muav_alloc_opts). */
+int muav_tokens_escort(const muav_config* cfg, const void* d_records, int max_tasks, int max_agents, float* d_task_feats22,
+                       uint8_t* d_task_mask, float* d_agent_feats16, uint8_t* d_agent_mask, float* d_edge_valid,
+                       int32_t* d_task_ids, int32_t* d_task_order, int n_envs, void* stream);
 
 /* Observation tensors (DroneEnv.py:365-492).  tasks_info [E, max_rows, 21] f64 per open task:
  * id, x/max_coord, y/max_coord, status, current_reqs[6], alloc_reqs[6], init_time, end_time, type_idx, unmet, age

@@ -56,6 +56,7 @@ class MuavAllocOpts(C.Structure):
         ("max_coord", C.c_double),
         ("d_edge_scores", C.c_void_p), ("d_priorities", C.c_void_p), ("d_reserved", C.c_void_p),
         ("d_task_order", C.c_void_p),
+        ("d_plan_pri", C.c_void_p), ("d_plan_commit", C.c_void_p), ("commit_threshold", C.c_double),
     ]
 
 
@@ -88,7 +89,7 @@ class MuavAttPairOffsets(C.Structure):
 ABI_SYMBOLS = [
     "muav_version", "muav_config_size", "muav_record_bytes", "muav_scratch_bytes", "muav_num_fields",
     "muav_field_info", "muav_header_index", "muav_step", "muav_allocate", "muav_step_host", "muav_lsap",
-    "muav_avoid_obstacles", "muav_metric_name", "muav_metrics", "muav_tokens_pair", "muav_tokens_commit", "muav_observe",
+    "muav_avoid_obstacles", "muav_metric_name", "muav_metrics", "muav_tokens_pair", "muav_tokens_commit", "muav_tokens_escort", "muav_observe",
     "muav_att_pair_scores",
 ]
 
@@ -189,6 +190,8 @@ class CudaLib(Lib):
         d.muav_tokens_pair.argtypes = [C.POINTER(MuavConfig), P, C.c_int, C.c_int, P, P, P, P, P, P, C.c_int, P]
         d.muav_tokens_commit.restype = C.c_int
         d.muav_tokens_commit.argtypes = [C.POINTER(MuavConfig), P, C.c_int, C.c_int, P, P, P, P, P, C.c_int, P]
+        d.muav_tokens_escort.restype = C.c_int
+        d.muav_tokens_escort.argtypes = [C.POINTER(MuavConfig), P, C.c_int, C.c_int, P, P, P, P, P, P, P, C.c_int, P]
         d.muav_att_pair_scores.restype = C.c_int
         d.muav_att_pair_scores.argtypes = [P, C.POINTER(MuavAttPairOffsets), P, P, P, P, P, P, P, C.c_int, C.c_int,
                                            C.c_int, C.c_float, P, P]

@@ -32,8 +32,10 @@ class AllocSpec:
     use_visibility: bool = True
     pair_tokens: bool = False
     max_coord: float = 1200.0
-    planner: int = 0              # 1: UrgencyCommit.plan, 2: UrgencyCoalition.plan (device-side planners)
+    planner: int = 0              # 1: UrgencyCommit.plan, 2: UrgencyCoalition.plan (device-side planners),
+                                  # 3: AttentionCommit._plan_from_scores, 4: AttentionEscort._plan_from_scores
     commit_fraction: float = 0.35
+    commit_threshold: float = 0.5
 
     @staticmethod
     def local_hungarian(interval=20):
@@ -60,6 +62,19 @@ class AllocSpec:
     def urgency_coalition(interval=12):
         """UrgencyCoalition under escort_eval.py:52-58,175-179 (every event tag triggers)."""
         return AllocSpec(2, interval, ALL_EVENTS, True, False, planner=2)
+
+
+    @staticmethod
+    def att_commit(interval=15, commit_threshold=0.5):
+        """AttentionCommit.plan under the hybrid cadence (wps_eval.py:64-73): step_allocated(..., plan_pri=, plan_commit=)
+        take the network's priority / commit vectors in muav_tokens_commit layout."""
+        return AllocSpec(2, interval, HYBRID_EVENTS, True, False, planner=3, commit_threshold=commit_threshold)
+
+    @staticmethod
+    def att_escort(interval=12):
+        """AttentionEscort.plan under escort_eval.py:52-58: step_allocated(..., edge_scores=, task_order=) take the
+        scores and the task order of tokens_escort()."""
+        return AllocSpec(2, interval, ALL_EVENTS, True, False, planner=4)
 
 
 class BatchedMultiUAVEnv:
@@ -189,7 +204,7 @@ class BatchedMultiUAVEnv:
         self.launches += 1
         return self.reward, self.terminated, self.truncated
 
-    def _alloc_opts(self, spec, edge_scores, priorities, reserved):
+    def _alloc_opts(self, spec, edge_scores, priorities, reserved, task_order=None, plan_pri=None, plan_commit=None):
         O = _lib.MuavAllocOpts()
         O.mode = spec.mode
         O.replan_interval = spec.replan_interval
@@ -213,12 +228,31 @@ class BatchedMultiUAVEnv:
             rs = reserved.to(device=self.device, dtype=torch.uint8).contiguous()
             keep.append(rs)
             O.d_reserved = rs.data_ptr()
+        if task_order is not None:
+            to = task_order.to(device=self.device, dtype=torch.int32).contiguous()
+            if to.shape != (self.n_envs, max(self.cfg.id_cap, self.cfg.task_cap)):
+                raise ValueError("task_order must be [n_envs, id_cap]")
+            keep.append(to)
+            O.d_task_order = to.data_ptr()
+        O.commit_threshold = spec.commit_threshold
+        if spec.planner == 3:
+            if plan_pri is None or plan_commit is None:
+                raise ValueError("planner 3 needs plan_pri [E, max_tasks] and plan_commit [E, max_agents]")
+            pp = plan_pri.to(device=self.device, dtype=torch.float32).contiguous()
+            pc = plan_commit.to(device=self.device, dtype=torch.float32).contiguous()
+            keep += [pp, pc]
+            O.score_cols, O.score_rows = int(pp.shape[1]), int(pc.shape[1])
+            O.d_plan_pri, O.d_plan_commit = pp.data_ptr(), pc.data_ptr()
+        if spec.planner == 4 and (edge_scores is None or task_order is None):
+            raise ValueError("planner 4 needs edge_scores [E, max_agents, max_tasks] and task_order from tokens_escort()")
         return O, keep
 
     def step_allocated(self, spec: AllocSpec, n_steps: int = 1, edge_scores: Optional[torch.Tensor] = None,
-                       priorities: Optional[torch.Tensor] = None, reserved: Optional[torch.Tensor] = None):
+                       priorities: Optional[torch.Tensor] = None, reserved: Optional[torch.Tensor] = None,
+                       task_order: Optional[torch.Tensor] = None, plan_pri: Optional[torch.Tensor] = None,
+                       plan_commit: Optional[torch.Tensor] = None):
         """n_steps fused (allocate -> step) iterations per environment, state resident in shared memory."""
-        O, keep = self._alloc_opts(spec, edge_scores, priorities, reserved)
+        O, keep = self._alloc_opts(spec, edge_scores, priorities, reserved, task_order, plan_pri, plan_commit)
         rc = self.lib.dll.muav_step(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(), None,
                                     C.byref(O), C.byref(self._out), self._tok_ref(), self.n_envs, n_steps,
                                     self._stream())
@@ -283,6 +317,25 @@ class BatchedMultiUAVEnv:
         _lib.check(rc, "muav_tokens_commit")
         self.launches += 1
         return {"task_feats": tf, "task_mask": tm.bool(), "agent_feats": af, "agent_mask": am.bool(), "task_ids": ids}
+
+    def tokens_escort(self, max_tasks=48, max_agents=16):
+        """build_escort_tokens(env) for every environment (AttentionEscort.py:76-241).  `task_order` [E, id_cap] is the
+        `tasks` argument / score layout that AllocSpec.att_escort() expects."""
+        E, dev = self.n_envs, self.device
+        tf = torch.empty(E, max_tasks, 22, dtype=torch.float32, device=dev)
+        tm = torch.empty(E, max_tasks, dtype=torch.uint8, device=dev)
+        af = torch.empty(E, max_agents, 16, dtype=torch.float32, device=dev)
+        am = torch.empty(E, max_agents, dtype=torch.uint8, device=dev)
+        ev = torch.empty(E, max_agents, max_tasks, dtype=torch.float32, device=dev)
+        ids = torch.empty(E, max_tasks, dtype=torch.int32, device=dev)
+        order = torch.empty(E, max(self.cfg.id_cap, self.cfg.task_cap), dtype=torch.int32, device=dev)
+        rc = self.lib.dll.muav_tokens_escort(C.byref(self.cfg), self.records.data_ptr(), max_tasks, max_agents,
+                                             tf.data_ptr(), tm.data_ptr(), af.data_ptr(), am.data_ptr(), ev.data_ptr(),
+                                             ids.data_ptr(), order.data_ptr(), E, self._stream())
+        _lib.check(rc, "muav_tokens_escort")
+        self.launches += 1
+        return {"task_feats": tf, "task_mask": tm.bool(), "agent_feats": af, "agent_mask": am.bool(),
+                "edge_valid": ev, "task_ids": ids, "task_order": order}
 
     def observe(self, max_rows: Optional[int] = None):
         """Observation tensors of _generate_observations (DroneEnv.py:468-492); see include/muav.h."""

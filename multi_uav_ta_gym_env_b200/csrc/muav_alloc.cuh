@@ -243,7 +243,9 @@ MUAV_HD MUAV_NI_A inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, in
         }
         if (V.k_status()[k] == 2) continue;
         int col = -1;
-        if (O.pair_tokens) {
+        if (O.pair_tokens == 2) {
+          col = it < O.score_cols ? it : -1;  // column = position in the escort token list
+        } else if (O.pair_tokens) {
           int ti = V.k_type()[k];
           if (!(V.k_alloc2(ti, k) < V.k_cur2(ti, k))) continue;  // AttentionRAH.py:67-71
           if (tok_j >= O.score_cols) break;                                    // open_tasks[:max_tasks]
@@ -317,7 +319,12 @@ MUAV_HD MUAV_NI_A inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, in
           } else if (scores64) {
             if (a < O.score_rows && k < O.score_cols) sc = scores64[a * O.score_cols + k];
           } else if (scores) {
-            if (O.pair_tokens) {
+            if (O.pair_tokens == 2) {
+              // AttentionEscort.edge_score_dict (AttentionEscort.py:478-489): every unpadded (row, column)
+              const int col = W.tokcol[q];
+              const int row = W.live_row[i];
+              if (row < O.score_rows && col >= 0) sc = (double)scores[row * O.score_cols + col];
+            } else if (O.pair_tokens) {
               // edge_score_dict (PairCostHybrid.py:280-291): only valid edges carry a score
               const int col = W.tokcol[q];
               const int row = W.live_row[i];
@@ -445,6 +452,44 @@ MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, in
     // committed_names (AttentionCommit.py:24-30)
     for (int a = 0; a < A; ++a) W.plan_reserved[a] = (V.a_state()[a] != -1 && V.a_commit()[a] > t) ? 1 : 0;
   }
+  if (O.planner == 3) {
+    // token column of each task in build_att_tokens' open list (AttentionRAH.py:67-71); -1 = no learned priority
+    if (lane == 0) {
+      const int n = HIv(N_TASKS);
+      int col = 0;
+      for (int k = 0; k < n; ++k) {
+        double c = -1.0;
+        if (V.k_status()[k] != 2) {
+          const int ti = V.k_type()[k];
+          if (V.k_alloc2(ti, k) < V.k_cur2(ti, k)) {
+            if (col < O.score_cols) c = (double)col;
+            ++col;
+          }
+        }
+        W.plan_pri[k] = c;
+      }
+    }
+    MUAV_WARP_SYNC();
+    int n_live = 0;
+    for (int a = 0; a < A; ++a) n_live += V.a_state()[a] != -1;
+    const double nl = (double)(n_live > 1 ? n_live : 1);
+    const int n = HIv(N_TASKS);
+    const float* pv = O.d_plan_pri + (size_t)e * O.score_cols;
+    for (int k = lane; k < n; k += nlanes) {
+      const double c = W.plan_pri[k];
+      double p = 0.0;
+      if (c >= 0.0) {
+        double scar = 0.0;
+        if (!vis_none) {
+          int cnt = 0;
+          for (int a = 0; a < A; ++a) cnt += S.known_bit(a, k) ? 1 : 0;
+          scar = 1.0 - dmin(ddiv((double)cnt, nl), 1.0);
+        }
+        p = 0.35 * task_urgency(V, k, t) + 0.40 * (double)pv[(int)c] + 0.25 * scar;
+      }
+      W.plan_pri[k] = p;
+    }
+  }
   if (O.planner == 1) {
     int n_live = 0;
     for (int a = 0; a < A; ++a) n_live += V.a_state()[a] != -1;
@@ -470,11 +515,18 @@ MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, in
   P.d_reserved = W.plan_reserved;
   P.d_edge_scores = nullptr;
   P.d_task_order = nullptr;
-  if (O.planner == 1) {
+  if (O.planner == 1 || O.planner == 3) {
     P.d_priorities = W.plan_pri;
     P.pair_tokens = 1;      // task list = build_att_tokens' open list (alloc < cur), not truncated
     P.score_cols = V.L->D.IC;
     P.score_rows = 0;
+    P.use_visibility = 1;
+  } else if (O.planner == 4) {
+    P.d_priorities = nullptr;
+    P.d_edge_scores = O.d_edge_scores;
+    P.score_f64 = 0;
+    P.d_task_order = O.d_task_order;
+    P.pair_tokens = 2;
     P.use_visibility = 1;
   } else {
     P.d_priorities = nullptr;
@@ -483,8 +535,21 @@ MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, in
   }
   const int np = allocate_tasks(S, P, e, out_agent, out_tid, lane, nlanes, true);
   if (lane == 0 && np > 0) {
-    if (O.planner == 2) {
+    if (O.planner == 2 || O.planner == 4) {
       for (int i = 0; i < np; ++i) apply_commit(S, out_agent[i], C.commit_horizon);
+    } else if (O.planner == 3) {
+      // AttentionCommit._plan_from_scores (AttentionCommit.py:289-298): gate by the commit head, row = live-agent index
+      uint64_t assigned = 0;
+      for (int i = 0; i < np; ++i) assigned |= (uint64_t)1 << out_agent[i];
+      const float* cv = O.d_plan_commit + (size_t)e * O.score_rows;
+      const int horizon = C.commit_horizon != 0 ? C.commit_horizon : 25;
+      int row = 0;
+      for (int a = 0; a < A && row < O.score_rows; ++a) {
+        if (V.a_state()[a] == -1) continue;
+        const int r = row++;
+        if (W.plan_reserved[a] || !((assigned >> a) & 1)) continue;
+        if ((double)cv[r] >= O.commit_threshold) apply_commit(S, a, horizon);
+      }
     } else {
       // UrgencyCommit lock ranking (AttentionCommit.py:334-355)
       const double thr = 1.0 - 12.0 / 40.0;

@@ -317,6 +317,24 @@ __global__ void __launch_bounds__(128) muav_tokens_pair_kernel(const __grid_cons
                   af_dim);
 }
 
+__global__ void __launch_bounds__(128) muav_tokens_escort_kernel(const __grid_constant__ muav_config cfg,
+                                                                 const __grid_constant__ Layout L, const char* records,
+                                                                 int max_tasks, int max_agents, float* tf, uint8_t* tm,
+                                                                 float* af, uint8_t* am, float* ev, int32_t* ids,
+                                                                 int32_t* order, int n, int per_warp) {
+  extern __shared__ __align__(16) char esc_smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * 4 + w;
+  if (e >= n) return;
+  View V;
+  V.base = (char*)records + (size_t)e * L.record_bytes;
+  V.L = &L;
+  EscortTokScratch W = carve_escort_tok(esc_smem + (size_t)w * per_warp, L.D.TC, max_tasks);
+  tokens_escort_env(V, cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * 22, tm + (size_t)e * max_tasks,
+                    af + (size_t)e * max_agents * 16, am + (size_t)e * max_agents, ev + (size_t)e * max_agents * max_tasks,
+                    ids + (size_t)e * max_tasks, order ? order + (size_t)e * L.D.IC : nullptr, W, lane, 32);
+}
+
 __global__ void muav_observe_kernel(const __grid_constant__ muav_config cfg, const __grid_constant__ Layout L,
                                     const char* records, int max_rows, double* ti, uint8_t* pad, uint8_t* legal,
                                     double* ao, float* ef, int32_t* n_rows, int n) {
@@ -533,6 +551,22 @@ int muav_tokens_commit(const muav_config* cfg, const void* d_records, int max_ta
   muav_tokens_pair_kernel<<<(n_envs + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
       *cfg, L, (const char*)d_records, max_tasks, max_agents, d_task_feats, d_task_mask, d_agent_feats13, d_agent_mask,
       nullptr, d_task_ids, n_envs, 13);
+  return cuda_rc(cudaGetLastError());
+}
+
+int muav_tokens_escort(const muav_config* cfg, const void* d_records, int max_tasks, int max_agents, float* d_task_feats22,
+                       uint8_t* d_task_mask, float* d_agent_feats16, uint8_t* d_agent_mask, float* d_edge_valid,
+                       int32_t* d_task_ids, int32_t* d_task_order, int n_envs, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (n_envs <= 0) return n_envs == 0 ? 0 : -22;
+  if (max_tasks < 1 || max_agents < 1 || max_tasks > MUAV_MAX_TASK_CAP) return -22;
+  if (!d_task_feats22 || !d_task_mask || !d_agent_feats16 || !d_agent_mask || !d_edge_valid || !d_task_ids) return -22;
+  Layout L = make_layout(*cfg);
+  const int per_warp = (int)escort_tok_scratch_bytes(L.D.TC, max_tasks);
+  muav_tokens_escort_kernel<<<(n_envs + 3) / 4, 128, (size_t)per_warp * 4, (cudaStream_t)stream>>>(
+      *cfg, L, (const char*)d_records, max_tasks, max_agents, d_task_feats22, d_task_mask, d_agent_feats16, d_agent_mask,
+      d_edge_valid, d_task_ids, d_task_order, n_envs, per_warp);
   return cuda_rc(cudaGetLastError());
 }
 

@@ -163,6 +163,294 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// build_escort_tokens (TaskAllocation/Hybrid/AttentionEscort.py:76-241).
+struct EscortTokScratch {
+  double* keys;    // [TC] priority key of each candidate
+  int16_t* cand;   // [TC] non-closed task indices in id order
+  int16_t* sel;    // [TC] candidates that enter the sort (indices into cand)
+  uint8_t* flag;   // [TC] bit 0: residual-open (_open_tasks_residual), bit 1: known to a live agent
+  int16_t* cols;   // [max_tasks + 4] kept task index per column; [max_tasks] = #columns, [max_tasks+1] = #candidates,
+                   //                 [max_tasks+2] = #selected
+};
+
+MUAV_HD inline size_t escort_tok_scratch_bytes(int TC, int max_tasks) {
+  size_t b = (size_t)TC * 13 + (size_t)(max_tasks + 4) * 2;
+  return (b + 15) & ~(size_t)15;
+}
+MUAV_HD inline EscortTokScratch carve_escort_tok(char* p, int TC, int max_tasks) {
+  EscortTokScratch W;
+  W.keys = (double*)p;
+  W.cand = (int16_t*)(p + (size_t)TC * 8);
+  W.sel = W.cand + TC;
+  W.cols = W.sel + TC;
+  W.flag = (uint8_t*)(W.cols + max_tasks + 4);
+  return W;
+}
+
+MUAV_HD inline bool view_in_queue(const View& V, int a, int tid) {
+  const int A = V.L->D.A;
+  const int ql = V.a_qlen()[a];
+  for (int q = 0; q < ql; ++q)
+    if (V.a_queue()[q * A + a] == tid) return true;
+  return false;
+}
+
+// _threat_stats (AttentionEscort.py:46-65)
+MUAV_HD inline void view_threat_stats(const View& V, const muav_config& C, int k, double* pressure, double* dist_n,
+                                      double* fighter_pressure) {
+  const double mc = C.max_coord;
+  double ax = V.k_posx()[k], ay = V.k_posy()[k];
+  const int prot = V.k_prot_agent()[k];
+  if (prot >= 0) { ax = V.a_posx()[prot]; ay = V.a_posy()[prot]; }
+  double best = mc;
+  int n_near = 0;
+  const int na = V.hi()[HI_N_ACTIVE];
+  for (int i = 0; i < na; ++i) {
+    const int hid = V.h_order()[i];
+    if (V.h_status()[hid] == 2) continue;
+    const double d = norm2(V.h_posx()[hid] - ax, V.h_posy()[hid] - ay);
+    best = dmin(best, d);
+    if (d < 150.0) ++n_near;
+  }
+  *pressure = 1.0 - dmin(best / mc, 1.0);
+  *dist_n = dmin(best / mc, 1.0);
+  *fighter_pressure = dmin((double)n_near / 4.0, 1.0);
+}
+
+MUAV_HD inline void tokens_escort_env(const View& V, const muav_config& C, int max_tasks, int max_agents, float* tf,
+                                      uint8_t* tm, float* af, uint8_t* am, float* ev, int32_t* ids, int32_t* order,
+                                      EscortTokScratch W, int lane, int nlanes) {
+  const int A = V.L->D.A, TC = V.L->D.TC, IC = V.L->D.IC;
+  const int n = V.hi()[HI_N_TASKS];
+  const int t = V.hi()[HI_T];
+  const double mc = C.max_coord;
+  const double mid_x = C.area_w * 0.5;
+  const bool vis_none = !(C.sense_radius != 0.0) && !(C.threat_delay != 0);
+  const double urgent_thr = 1.0 - 12.0 / 40.0;
+  int16_t* cols = W.cols;
+  if (lane == 0) {
+    int nc = 0;
+    for (int k = 0; k < n && nc < TC; ++k)
+      if (V.k_status()[k] != 2) W.cand[nc++] = (int16_t)k;
+    cols[max_tasks + 1] = (int16_t)nc;
+  }
+  MUAV_WARP_SYNC();
+  const int ncand = cols[max_tasks + 1];
+  // ---- per candidate: residual-open, known to a live agent, priority key
+  for (int c = lane; c < ncand; c += nlanes) {
+    const int k = W.cand[c];
+    const int ti = V.k_type()[k];
+    uint8_t fl = 0;
+    if (V.k_kind()[k] == 1 || V.k_req_agents()[k] > 0) {
+      const int ra = V.k_req_agents()[k];
+      int cnt = 0;
+      for (int a = 0; a < A; ++a) cnt += view_in_queue(V, a, k + 1) ? 1 : 0;
+      if ((double)(ra != 0 ? ra : 1) - (double)cnt > 0.0) fl = 1;
+    } else if (V.k_alloc2(ti, k) < V.k_cur2(ti, k)) {
+      fl = 1;
+    }
+    double key = 0.0;
+    if (fl) {
+      for (int a = 0; a < A; ++a)
+        if (V.a_state()[a] != -1 && view_known(V, a, k)) { fl |= 2; break; }
+      double pressure, dn, fp;
+      view_threat_stats(V, C, k, &pressure, &dn, &fp);
+      const double urg = urgency_of(V, k, t);
+      const double is_escort = V.k_kind()[k] == 1 ? 1.0 : 0.0;
+      const double is_int = ti == TT_INT ? 1.0 : 0.0;
+      key = -(1.5 * urg + 1.2 * pressure + 0.8 * is_escort + 0.5 * is_int);
+    }
+    W.flag[c] = fl;
+    W.keys[c] = key;
+  }
+  MUAV_WARP_SYNC();
+  if (lane == 0) {
+    bool any_known = false;
+    for (int c = 0; c < ncand; ++c)
+      if ((W.flag[c] & 3) == 3) { any_known = true; break; }
+    const bool filter = !vis_none && any_known;
+    int m = 0;
+    for (int c = 0; c < ncand; ++c) {
+      if (!(W.flag[c] & 1)) continue;
+      if (filter && !(W.flag[c] & 2)) continue;
+      W.sel[m++] = (int16_t)c;
+    }
+    cols[max_tasks + 2] = (int16_t)m;
+    cols[max_tasks] = (int16_t)(m < max_tasks ? m : max_tasks);
+  }
+  MUAV_WARP_SYNC();
+  const int m = cols[max_tasks + 2];
+  const int ncol = cols[max_tasks];
+  // ---- stable sort by key: rank = number of entries that come first
+  for (int i = lane; i < m; i += nlanes) {
+    const double ki = W.keys[W.sel[i]];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const double kj = W.keys[W.sel[j]];
+      rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+    }
+    if (rank < max_tasks) cols[rank] = W.cand[W.sel[i]];
+  }
+  MUAV_WARP_SYNC();
+  int n_live = 0;
+  for (int a = 0; a < A; ++a) n_live += V.a_state()[a] != -1;
+  const int n_agents = n_live > 1 ? n_live : 1;
+  if (order)
+    for (int j = lane; j < IC; j += nlanes) order[j] = j < ncol ? (int32_t)cols[j] : -1;
+  // ---- task columns
+  for (int j = lane; j < max_tasks; j += nlanes) {
+    float* f = tf + j * 22;
+    if (j >= ncol) {
+      tm[j] = 1;
+      ids[j] = 0;
+      for (int c = 0; c < 22; ++c) f[c] = 0.0f;
+      continue;
+    }
+    const int k = cols[j];
+    const int ti = V.k_type()[k];
+    const double urg = urgency_of(V, k, t);
+    int n_know_i = 0;
+    for (int a = 0; a < A; ++a) n_know_i += view_known(V, a, k) ? 1 : 0;
+    double scar = 0.0, n_know = 0.0;
+    if (!vis_none) {
+      scar = 1.0 - dmin((double)n_know_i / (double)n_agents, 1.0);
+      n_know = (double)n_know_i;
+    }
+    double rem, req_agents;
+    if (V.k_kind()[k] == 1 || V.k_req_agents()[k] > 0) {
+      const int ra = V.k_req_agents()[k];
+      int cnt = 0;
+      for (int a = 0; a < A; ++a) cnt += view_in_queue(V, a, k + 1) ? 1 : 0;
+      req_agents = (double)(ra != 0 ? ra : 1);
+      rem = dmax(req_agents - (double)cnt, 0.0);
+    } else {
+      rem = dmax(V.k_cur2(ti, k) - V.k_alloc2(ti, k), 0.0);
+      req_agents = 1.0;
+    }
+    double d_spec = mc;
+    bool any_spec = false;
+    for (int a = 0; a < A; ++a) {
+      if (V.a_state()[a] == -1 || V.a_type()[a] != UT_F2) continue;
+      const double d = norm2(V.a_posx()[a] - V.k_posx()[k], V.a_posy()[a] - V.k_posy()[k]);
+      if (!any_spec || d < d_spec) d_spec = d;
+      any_spec = true;
+    }
+    const double deficit = dmin(rem / 4.0, 1.0);
+    double pressure, threat_dist, fighter_pressure;
+    view_threat_stats(V, C, k, &pressure, &threat_dist, &fighter_pressure);
+    const int prot = V.k_prot_agent()[k];
+    double prot_x = V.k_posx()[k] / mc, prot_y = V.k_posy()[k] / mc, prot_alive = 0.0;
+    if (prot >= 0) {
+      prot_x = V.a_posx()[prot] / mc;
+      prot_y = V.a_posy()[prot] / mc;
+      prot_alive = V.a_state()[prot] == -1 ? 0.0 : 1.0;
+    }
+    f[0] = (float)(V.k_posx()[k] / mc);
+    f[1] = (float)(V.k_posy()[k] / mc);
+    f[2] = (float)((double)ti / 8.0);
+    f[3] = ti == TT_ATT ? 1.0f : 0.0f;
+    f[4] = ti == TT_REC ? 1.0f : 0.0f;
+    f[5] = ti == TT_INT ? 1.0f : 0.0f;
+    f[6] = (float)urg;
+    f[7] = (float)scar;
+    f[8] = (float)deficit;
+    f[9] = V.k_deadline()[k] >= 0 ? 1.0f : 0.0f;
+    f[10] = (float)dmin(n_know / (double)n_agents, 1.0);
+    f[11] = (float)dmin(d_spec / mc, 1.0);
+    f[12] = V.k_posx()[k] < mid_x ? 0.0f : 1.0f;
+    f[13] = V.k_kind()[k] == 1 ? 1.0f : 0.0f;
+    f[14] = (float)deficit;
+    f[15] = (float)pressure;
+    f[16] = (float)prot_x;
+    f[17] = (float)prot_y;
+    f[18] = (float)dmin(req_agents / 4.0, 1.0);
+    f[19] = (float)threat_dist;
+    f[20] = (float)prot_alive;
+    f[21] = (float)fighter_pressure;
+    tm[j] = 0;
+    ids[j] = k + 1;
+  }
+  // ---- agent rows (row i = i-th live agent)
+  const int hz0 = C.commit_horizon != 0 ? C.commit_horizon : 20;
+  const double horizon = (double)(hz0 > 1 ? hz0 : 1);
+  const int mt_steps = C.max_time_steps > 1 ? C.max_time_steps : 1;
+  for (int i = lane; i < max_agents; i += nlanes) {
+    float* f = af + i * 16;
+    float* evr = ev + i * max_tasks;
+    int a = -1, seen = 0;
+    for (int b = 0; b < A; ++b) {
+      if (V.a_state()[b] == -1) continue;
+      if (seen == i) { a = b; break; }
+      ++seen;
+    }
+    if (a < 0) {
+      am[i] = 1;
+      for (int c = 0; c < 16; ++c) f[c] = 0.0f;
+      for (int j = 0; j < max_tasks; ++j) evr[j] = 0.0f;
+      continue;
+    }
+    const int at = V.a_type()[a];
+    const double cap_rec = V.a_caps()[1 * A + a], cap_att = V.a_caps()[2 * A + a], cap_def = V.a_caps()[3 * A + a];
+    int n_known_urgent = 0;
+    for (int c = 0; c < ncand; ++c) {
+      if (!(W.flag[c] & 1)) continue;
+      const int k = W.cand[c];
+      if (V.k_deadline()[k] < 0) continue;
+      if (!vis_none && !view_known(V, a, k)) continue;
+      if (urgency_of(V, k, t) >= urgent_thr) ++n_known_urgent;
+    }
+    int n_known_tasks = 0;
+    if (!vis_none) {
+      const int KWn = (n + 31) >> 5;
+      for (int w = 0; w < KWn; ++w) {
+        uint32_t bits = V.known()[w * A + a];
+        if (w == KWn - 1 && (n & 31)) bits &= (1u << (n & 31)) - 1u;
+        while (bits) { bits &= bits - 1; ++n_known_tasks; }
+      }
+    }
+    double is_escorting = 0.0, dist_prot = 1.0, near_escort = 0.0;
+    if (V.a_qlen()[a] > 0) {
+      const int hk = V.a_queue()[a] - 1;
+      if (hk >= 0 && V.k_kind()[hk] == 1) {
+        is_escorting = 1.0;
+        const int prot = V.k_prot_agent()[hk];
+        if (prot >= 0) {
+          dist_prot = dmin(norm2(V.a_posx()[a] - V.a_posx()[prot], V.a_posy()[a] - V.a_posy()[prot]) / mc, 1.0);
+          near_escort = 1.0 - dist_prot;
+        }
+      }
+    }
+    const double rem_commit = dmax((double)V.a_commit()[a] - (double)t, 0.0);
+    f[0] = (float)(V.a_posx()[a] / mc);
+    f[1] = (float)(V.a_posy()[a] / mc);
+    f[2] = is_fighter(at) ? 1.0f : 0.0f;
+    f[3] = is_recon(at) ? 1.0f : 0.0f;
+    f[4] = V.a_qlen()[a] == 0 ? 1.0f : 0.0f;
+    f[5] = (float)dmin(cap_att / 2.0, 1.0);
+    f[6] = (float)dmin(cap_def / 2.0, 1.0);
+    f[7] = (float)dmin(cap_rec / 2.0, 1.0);
+    f[8] = (float)((double)V.a_state()[a] / 5.0);
+    f[9] = (float)((double)t / (double)mt_steps);
+    f[10] = (float)dmin((double)n_known_urgent / 8.0, 1.0);
+    f[11] = at == UT_F2 ? 1.0f : 0.0f;
+    f[12] = (float)is_escorting;
+    f[13] = (float)dist_prot;
+    f[14] = (float)dmin(rem_commit / horizon, 1.0);
+    f[15] = (float)dmin(near_escort + (double)n_known_tasks / 16.0, 1.0);
+    am[i] = 0;
+    for (int j = 0; j < max_tasks; ++j) {
+      float v = 0.0f;
+      if (j < ncol) {
+        const int k = cols[j];
+        const int el = V.k_elig()[k];
+        v = ((vis_none || view_known(V, a, k)) && (el == 0 || ((el >> at) & 1))) ? 1.0f : 0.0f;
+      }
+      evr[j] = v;
+    }
+  }
+}
+
 #define MUAV_OBS_TASK_DIM_ 21
 // tasks_info [max_rows, 21] f64: id, x, y, status, cur[6], alloc[6], init_time, end_time, type_idx, unmet, age
 // (status = -1 marks padding); pad_mask [max_rows]; legal_mask [A, max_rows]; agent_obs [A, 9]; event_flags [5] f32.

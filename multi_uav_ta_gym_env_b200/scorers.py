@@ -19,13 +19,13 @@ SCORE_CLAMP = 0.35
 
 class AttPairNet(nn.Module):
     def __init__(self, max_tasks=32, max_agents=16, d_model=64, nhead=4, n_layers=2, dropout=0.1,
-                 task_feat_dim=TASK_FEAT_DIM, agent_feat_dim=AGENT_FEAT_DIM):
+                 task_feat_dim=TASK_FEAT_DIM, agent_feat_dim=AGENT_FEAT_DIM, ff_mult=2):
         super().__init__()
         self.max_tasks, self.max_agents = max_tasks, max_agents
         self.task_proj = nn.Linear(task_feat_dim, d_model)
         self.agent_proj = nn.Linear(agent_feat_dim, d_model)
         self.type_embed = nn.Embedding(2, d_model)
-        layer = nn.TransformerEncoderLayer(d_model=d_model, nhead=nhead, dim_feedforward=d_model * 2,
+        layer = nn.TransformerEncoderLayer(d_model=d_model, nhead=nhead, dim_feedforward=d_model * ff_mult,
                                            batch_first=True, dropout=dropout)
         self.self_encoder = nn.TransformerEncoder(layer, num_layers=max(1, n_layers - 1))
         self.cross_a2t = nn.MultiheadAttention(d_model, nhead, dropout=dropout, batch_first=True)
@@ -82,6 +82,110 @@ class MLPPairNet(nn.Module):
         t_pool = (task_feats * tm).sum(1) / tm.sum(1).clamp(min=1.0)
         value = self.value_mlp(torch.cat([a_pool, t_pool], dim=-1)).squeeze(-1)
         return logits, value
+
+
+TASK_FEAT_DIM_E = 22   # build_escort_tokens task features (AttentionEscort.py:23)
+AGENT_FEAT_DIM_E = 16  # build_escort_tokens agent features (AttentionEscort.py:25)
+AGENT_FEAT_DIM_C = AGENT_FEAT_DIM + 1  # enrich_commit_tokens (AttentionCommit.py:65)
+
+
+class AttCoalitionNet(AttPairNet):
+    """AttCoalitionNet (AttentionEscort.py:244-330): the Att-Pair architecture at d_model 128, three layers, feed-forward
+    4 d_model, over escort tokens [48, 22] / [16, 16].  Same construction order as the reference class."""
+
+    def __init__(self, max_tasks=48, max_agents=16, d_model=128, nhead=4, n_layers=3, dropout=0.1):
+        super().__init__(max_tasks, max_agents, d_model, nhead, n_layers, dropout, TASK_FEAT_DIM_E, AGENT_FEAT_DIM_E,
+                         ff_mult=4)
+
+
+class MLPCoalitionNet(nn.Module):
+    """MLPCoalitionNet (AttentionEscort.py:333-375)."""
+
+    def __init__(self, max_tasks=48, max_agents=16, hidden=256, **_):
+        super().__init__()
+        self.max_tasks, self.max_agents = max_tasks, max_agents
+        in_dim = TASK_FEAT_DIM_E + AGENT_FEAT_DIM_E
+        self.pair_mlp = nn.Sequential(nn.Linear(in_dim, hidden), nn.ReLU(), nn.Linear(hidden, hidden), nn.ReLU(),
+                                      nn.Linear(hidden, 1))
+        self.value_mlp = nn.Sequential(nn.Linear(max_tasks * TASK_FEAT_DIM_E + max_agents * AGENT_FEAT_DIM_E, hidden),
+                                       nn.ReLU(), nn.Linear(hidden, 1))
+
+    def forward(self, task_feats, task_mask, agent_feats, agent_mask):
+        b, a, _ = agent_feats.shape
+        t = task_feats.size(1)
+        a_exp = agent_feats.unsqueeze(2).expand(-1, -1, t, -1)
+        t_exp = task_feats.unsqueeze(1).expand(-1, a, -1, -1)
+        logits = self.pair_mlp(torch.cat([a_exp, t_exp], dim=-1)).squeeze(-1)
+        logits = logits.masked_fill(agent_mask.unsqueeze(2), -1e9)
+        logits = logits.masked_fill(task_mask.unsqueeze(1), -1e9)
+        flat = torch.cat([task_feats.reshape(b, -1), agent_feats.reshape(b, -1)], dim=1)
+        return logits, self.value_mlp(flat).squeeze(-1)
+
+
+class AttCommitNet(nn.Module):
+    """AttCommitNet (AttentionCommit.py:68-101): joint encoder over agent + task tokens, sigmoid priority head per task
+    and commit head per agent."""
+
+    def __init__(self, max_tasks=32, max_agents=16, d_model=64, nhead=4, n_layers=2):
+        super().__init__()
+        self.max_tasks, self.max_agents = max_tasks, max_agents
+        self.task_proj = nn.Linear(TASK_FEAT_DIM, d_model)
+        self.agent_proj = nn.Linear(AGENT_FEAT_DIM_C, d_model)
+        self.type_embed = nn.Embedding(2, d_model)
+        enc_layer = nn.TransformerEncoderLayer(d_model=d_model, nhead=nhead, dim_feedforward=d_model * 2,
+                                               batch_first=True, dropout=0.1)
+        self.encoder = nn.TransformerEncoder(enc_layer, num_layers=n_layers)
+        self.priority_head = nn.Linear(d_model, 1)
+        self.commit_head = nn.Linear(d_model, 1)
+
+    def forward(self, task_feats, task_mask, agent_feats, agent_mask):
+        t_emb = self.task_proj(task_feats) + self.type_embed.weight[1]
+        a_emb = self.agent_proj(agent_feats) + self.type_embed.weight[0]
+        tokens = torch.cat([a_emb, t_emb], dim=1)
+        pad_mask = torch.cat([agent_mask, task_mask], dim=1)
+        h = self.encoder(tokens, src_key_padding_mask=pad_mask)
+        a_h = h[:, : self.max_agents, :]
+        t_h = h[:, self.max_agents:, :]
+        priorities = torch.sigmoid(self.priority_head(t_h).squeeze(-1)).masked_fill(task_mask, 0.0)
+        commits = torch.sigmoid(self.commit_head(a_h).squeeze(-1)).masked_fill(agent_mask, 0.0)
+        return priorities, commits
+
+
+class MLPCommitNet(nn.Module):
+    """MLPCommitNet (AttentionCommit.py:104-129)."""
+
+    def __init__(self, max_tasks=32, max_agents=16, hidden=128):
+        super().__init__()
+        self.max_tasks, self.max_agents = max_tasks, max_agents
+        in_dim = max_tasks * TASK_FEAT_DIM + max_agents * AGENT_FEAT_DIM_C
+        self.backbone = nn.Sequential(nn.Linear(in_dim, hidden), nn.ReLU(), nn.Linear(hidden, hidden), nn.ReLU())
+        self.priority_head = nn.Linear(hidden, max_tasks)
+        self.commit_head = nn.Linear(hidden, max_agents)
+
+    def forward(self, task_feats, task_mask, agent_feats, agent_mask):
+        b = task_feats.size(0)
+        h = self.backbone(torch.cat([task_feats.reshape(b, -1), agent_feats.reshape(b, -1)], dim=1))
+        priorities = torch.sigmoid(self.priority_head(h)).masked_fill(task_mask, 0.0)
+        commits = torch.sigmoid(self.commit_head(h)).masked_fill(agent_mask, 0.0)
+        return priorities, commits
+
+
+@torch.no_grad()
+def commit_vectors(net: nn.Module, tok: dict):
+    """tokens (BatchedMultiUAVEnv.tokens_commit) -> (priorities f32 [B, max_tasks], commits f32 [B, max_agents]):
+    AttentionCommit.act without exploration (AttentionCommit.py:167-175); feed to AllocSpec.att_commit()."""
+    return net(tok["task_feats"], tok["task_mask"], tok["agent_feats"], tok["agent_mask"])
+
+
+@torch.no_grad()
+def coalition_scores(net: nn.Module, tok: dict) -> torch.Tensor:
+    """tokens (BatchedMultiUAVEnv.tokens_escort) -> edge scores f32 [B, max_agents, max_tasks]: AttentionEscort.act
+    without exploration (AttentionEscort.py:449-466): sigmoid of the logits clipped to +-20, zero on invalid edges
+    and on padded rows / columns; feed to AllocSpec.att_escort() together with tok["task_order"]."""
+    logits, _ = net(tok["task_feats"], tok["task_mask"], tok["agent_feats"], tok["agent_mask"])
+    scores = 1.0 / (1.0 + torch.exp(-logits.clamp(-20.0, 20.0)))
+    scores = scores * tok["edge_valid"]
+    return scores * (~tok["agent_mask"]).unsqueeze(2) * (~tok["task_mask"]).unsqueeze(1)
 
 
 @torch.no_grad()

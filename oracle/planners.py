@@ -5,6 +5,8 @@ Deterministic hybrid planners restated over the oracle state:
   UrgencyCommit.plan                      TaskAllocation/Hybrid/AttentionCommit.py:310-357
   _open_tasks_residual / _threat_stats    TaskAllocation/Hybrid/AttentionEscort.py:31-65
   UrgencyCoalition.plan                   TaskAllocation/Hybrid/AttentionEscort.py:720-767
+  AttentionCommit._plan_from_scores       TaskAllocation/Hybrid/AttentionCommit.py:266-300
+  AttentionEscort._plan_from_scores       TaskAllocation/Hybrid/AttentionEscort.py:500-517 (edge_score_dict :478-489)
 """
 from __future__ import annotations
 
@@ -120,5 +122,52 @@ def urgency_coalition_plan(env, hung):
     reserved = committed(env)
     result = hung.allocate(env, agents=live, tasks=open_tasks, time_step=env.t, events=env.last_events, force=True,
                            reserved=reserved, known=env.visibility(), edge_scores=edge)
+    apply_commits(env, [a for a, tid in result if tid != 0], int(env.commit_horizon or 0))
+    return result
+
+
+def att_commit_plan_from_scores(env, hung, pri_vec, com_vec, commit_threshold=0.5, max_tasks=32, max_agents=16):
+    """Priorities / commit gates of a commit network -> Local-Hungarian on the free agents -> commit locks."""
+    A = env.n_agents
+    T = len(env.k_pos)
+    vis = env.visibility()
+    live = env.live_agents()
+    open_known = [k + 1 for k in range(T)
+                  if env.k_status[k] != 2 and env.k_alloc[k][env.k_type[k]] < env.k_cur[k][env.k_type[k]]]
+    reserved = committed(env)
+    n = max(len(live), 1)
+    pri = {}
+    for i, tid in enumerate(open_known[:max_tasks]):
+        k = tid - 1
+        urg = urgency(env, k, env.t)
+        if vis is None:
+            scar = 0.0
+        else:
+            cnt = sum(1 for a in range(A) if vis[a][k])
+            scar = 1.0 - min(cnt / max(n, 1), 1.0)
+        pri[tid] = 0.35 * urg + 0.40 * float(pri_vec[i]) + 0.25 * scar
+    result = hung.allocate(env, agents=live, tasks=open_known, time_step=env.t, events=env.last_events, force=True,
+                           task_priorities=pri, reserved=reserved, known=vis)
+    assigned = {a for a, _ in result}
+    to_commit = [a for i, a in enumerate(live[:max_agents])
+                 if a not in reserved and a in assigned and float(com_vec[i]) >= commit_threshold]
+    apply_commits(env, to_commit, int(env.commit_horizon or 25))
+    return result
+
+
+def att_escort_plan_from_scores(env, hung, scores, max_tasks=48, max_agents=16):
+    """Edge scores in build_escort_tokens' layout -> Coalition-Hungarian over the token's (sorted, truncated)
+    task list -> every assigned agent is locked."""
+    from .tokens import build_escort_tokens
+
+    tok = build_escort_tokens(env, max_tasks, max_agents)
+    edge = {}
+    for i, a in enumerate(tok["live"][:max_agents]):
+        for j, tid in enumerate(tok["open_tasks"]):
+            edge[(a, int(tid))] = float(scores[i, j])
+    reserved = committed(env)
+    result = hung.allocate(env, agents=env.live_agents(), tasks=tok["open_tasks"], time_step=env.t,
+                           events=env.last_events, force=True, reserved=reserved, known=env.visibility(),
+                           edge_scores=edge)
     apply_commits(env, [a for a, tid in result if tid != 0], int(env.commit_horizon or 0))
     return result

@@ -7,6 +7,8 @@ Restates, over the oracle's flat state (oracle/sim.py):
   edge_score_dict + plan(scores=)  TaskAllocation/Hybrid/PairCostHybrid.py:280-291, 308-328
   hybrid replan cadence            experiments/wps_eval.py:64-73
   _generate_observations / get_task_info / _event_flag_vector   mUAV_TA/DroneEnv.py:365-492
+  _open_tasks_residual / _threat_stats / _task_priority_key / build_escort_tokens
+                                   TaskAllocation/Hybrid/AttentionEscort.py:31-241
 """
 from __future__ import annotations
 
@@ -121,6 +123,154 @@ def commit_tokens(env, max_tasks=32, max_agents=16):
     out["agent_feats"] = np.concatenate([af, extra], axis=1)
     out.pop("edge_valid")
     return out
+
+
+def open_tasks_residual(env):
+    """_open_tasks_residual (AttentionEscort.py:31-43) -> 0-based task indices."""
+    out = []
+    for k in range(len(env.k_pos)):
+        if env.k_status[k] == 2:
+            continue
+        if env.k_kind[k] == 1 or float(env.k_required_agents[k] or 0) > 0:
+            if float(env.k_required_agents[k] or 1) - len(env.k_details[k]) > 0:
+                out.append(k)
+        elif env.k_alloc[k][env.k_type[k]] < env.k_cur[k][env.k_type[k]]:
+            out.append(k)
+    return out
+
+
+def threat_stats(env, k):
+    """_threat_stats (AttentionEscort.py:46-65): (pressure, nearest threat distance / max_coord, fighter pressure)."""
+    mc = float(env.max_coord)
+    anchor = env.k_pos[k]
+    prot = env.k_prot_agent[k]
+    if prot >= 0:
+        anchor = env.a_pos[prot]
+    best = mc
+    n_near = 0
+    for hid in env.h_order:
+        if env.h_status[hid] == 2:
+            continue
+        d = norm2(env.h_pos[hid][0] - anchor[0], env.h_pos[hid][1] - anchor[1])
+        best = min(best, d)
+        if d < 150.0:
+            n_near += 1
+    return 1.0 - min(best / mc, 1.0), min(best / mc, 1.0), min(n_near / 4.0, 1.0)
+
+
+def escort_priority_key(env, k):
+    """_task_priority_key (AttentionEscort.py:68-73)."""
+    urg = urgency(env, k, env.t)
+    pressure = threat_stats(env, k)[0]
+    is_escort = 1.0 if env.k_kind[k] == 1 else 0.0
+    is_int = 1.0 if env.k_type[k] == T_INT else 0.0
+    return -(1.5 * urg + 1.2 * pressure + 0.8 * is_escort + 0.5 * is_int)
+
+
+def build_escort_tokens(env, max_tasks=48, max_agents=16):
+    """build_escort_tokens (AttentionEscort.py:76-241).  task_ids / open_tasks are in the priority-sorted order."""
+    A = env.n_agents
+    mc = float(env.max_coord)
+    mid_x = float(env.area_width) * 0.5
+    vis = env.visibility()
+    live = env.live_agents()
+    n_agents = max(len(live), 1)
+    specialists = [a for a in live if UAV_TYPES[env.a_type[a]] == "F2"]
+    open_all = open_tasks_residual(env)
+    if vis is None:
+        open_tasks = list(open_all)
+    else:
+        open_tasks = [k for k in open_all if any(vis[a][k] for a in live)]
+        if not open_tasks:
+            open_tasks = list(open_all)
+    open_tasks.sort(key=lambda k: escort_priority_key(env, k))
+    horizon = max(int(env.commit_horizon or 20), 1)
+    t_now = float(env.t)
+    task_feats = np.zeros((max_tasks, 22), dtype=np.float32)
+    task_mask = np.ones(max_tasks, dtype=bool)
+    kept = open_tasks[:max_tasks]
+    for i, k in enumerate(kept):
+        ti = env.k_type[k]
+        urg = urgency(env, k, env.t)
+        if vis is None:
+            scar, n_know = 0.0, 0.0
+        else:
+            cnt = sum(1 for a in range(A) if vis[a][k])
+            scar = 1.0 - min(cnt / max(n_agents, 1), 1.0)
+            n_know = float(cnt)
+        if env.k_kind[k] == 1 or float(env.k_required_agents[k] or 0) > 0:
+            rem = max(float(env.k_required_agents[k] or 1) - len(env.k_details[k]), 0.0)
+            req_agents = float(env.k_required_agents[k] or 1)
+        else:
+            rem = max(float(env.k_cur[k][ti] - env.k_alloc[k][ti]), 0.0)
+            req_agents = 1.0
+        is_dynamic = 1.0 if env.k_deadline[k] >= 0 else 0.0
+        tp = env.k_pos[k]
+        if specialists:
+            d_spec = min(norm2(env.a_pos[a][0] - tp[0], env.a_pos[a][1] - tp[1]) for a in specialists)
+        else:
+            d_spec = mc
+        region = 0.0 if float(tp[0]) < mid_x else 1.0
+        deficit = min(rem / 4.0, 1.0)
+        pressure, threat_dist, fighter_pressure = threat_stats(env, k)
+        prot = env.k_prot_agent[k]
+        prot_alive = 0.0
+        if prot >= 0:
+            prot_x, prot_y = float(env.a_pos[prot][0]) / mc, float(env.a_pos[prot][1]) / mc
+            prot_alive = 0.0 if env.a_state[prot] == -1 else 1.0
+        else:
+            prot_x, prot_y = float(tp[0]) / mc, float(tp[1]) / mc
+        task_feats[i] = [
+            float(tp[0]) / mc, float(tp[1]) / mc, float(ti) / 8.0,
+            1.0 if ti == T_ATT else 0.0, 1.0 if ti == T_REC else 0.0, 1.0 if ti == T_INT else 0.0,
+            urg, scar, deficit, is_dynamic, min(n_know / max(n_agents, 1), 1.0), min(d_spec / mc, 1.0), region,
+            1.0 if env.k_kind[k] == 1 else 0.0, deficit, pressure, prot_x, prot_y, min(req_agents / 4.0, 1.0),
+            threat_dist, prot_alive, fighter_pressure,
+        ]
+        task_mask[i] = False
+    agent_feats = np.zeros((max_agents, 16), dtype=np.float32)
+    agent_mask = np.ones(max_agents, dtype=bool)
+    edge_valid = np.zeros((max_agents, max_tasks), dtype=np.float32)
+    thr = 1.0 - 12.0 / 40.0
+    for i, a in enumerate(live[:max_agents]):
+        caps = env.a_caps[a]
+        atype = UAV_TYPES[env.a_type[a]]
+        n_known_urgent = 0
+        n_known_tasks = 0 if vis is None else int(sum(1 for v in vis[a] if v))
+        for k in open_all:
+            if vis is not None and not vis[a][k]:
+                continue
+            if urgency(env, k, env.t) >= thr and env.k_deadline[k] >= 0:
+                n_known_urgent += 1
+        is_escorting, dist_prot, near_escort = 0.0, 1.0, 0.0
+        if env.a_queue[a] and env.k_kind[env.a_queue[a][0] - 1] == 1:
+            is_escorting = 1.0
+            prot = env.k_prot_agent[env.a_queue[a][0] - 1]
+            if prot >= 0:
+                dist_prot = min(norm2(env.a_pos[a][0] - env.a_pos[prot][0], env.a_pos[a][1] - env.a_pos[prot][1]) / mc, 1.0)
+                near_escort = 1.0 - dist_prot
+        rem_commit = max(float(env.a_commit_until[a] or 0) - t_now, 0.0)
+        agent_feats[i] = [
+            float(env.a_pos[a][0]) / mc, float(env.a_pos[a][1]) / mc,
+            1.0 if atype.startswith("F") else 0.0, 1.0 if atype.startswith("R") else 0.0,
+            1.0 if not env.a_queue[a] else 0.0,
+            min(float(caps[2]) / 2.0, 1.0), min(float(caps[3]) / 2.0, 1.0), min(float(caps[1]) / 2.0, 1.0),
+            float(env.a_state[a]) / 5.0, float(env.t) / max(env.max_time_steps, 1),
+            min(n_known_urgent / 8.0, 1.0), 1.0 if atype == "F2" else 0.0, is_escorting, dist_prot,
+            min(rem_commit / horizon, 1.0), min(near_escort + n_known_tasks / 16.0, 1.0),
+        ]
+        agent_mask[i] = False
+        for j, k in enumerate(kept):
+            if vis is not None and not vis[a][k]:
+                continue
+            el = env.k_elig[k]
+            if el != 0 and not (el >> env.a_type[a]) & 1:
+                continue
+            edge_valid[i, j] = 1.0
+    ids = np.zeros(max_tasks, dtype=np.int32)
+    ids[: len(kept)] = [k + 1 for k in kept]
+    return {"task_feats": task_feats, "task_mask": task_mask, "agent_feats": agent_feats, "agent_mask": agent_mask,
+            "edge_valid": edge_valid, "task_ids": ids, "open_tasks": [k + 1 for k in kept], "live": live, "vis": vis}
 
 
 def pair_plan(env, hung, scores, max_tasks=32, max_agents=16):

@@ -18,6 +18,11 @@ Drivers (all restate the reference's own episode loops):
   random_actions    env.step driven by a seeded random policy (valid, stale and out-of-range indices)
   urgency_commit    UrgencyCommit.plan (AttentionCommit.py:310-357) under the hybrid cadence wps_eval.py:64-73
   urgency_coalition UrgencyCoalition.plan (AttentionEscort.py:720-767) under escort_eval.py:52-58, interval 12
+  att_commit_injected  AttentionCommit.plan (AttentionCommit.py:260-300) with the network replaced by injected
+                    (priority, commit) vectors, hybrid cadence wps_eval.py:64-73
+  att_escort_injected  AttentionEscort.plan (AttentionEscort.py:519-524: build_escort_tokens -> act -> _plan_from_scores)
+                    with the network replaced by injected logits, cadence escort_eval.py:52-58 (interval 12);
+                    the reference tokens of every 4th plan are stored too
 """
 from __future__ import annotations
 
@@ -59,6 +64,37 @@ def injected_scores(seed, t, n_rows, n_cols):
     return ((x.astype(np.float64) - 1000.0) / 1000.0 * 0.35).astype(np.float32)
 
 
+def injected_commit_vectors(seed, t):
+    """(pri_vec [32], com_vec [16]) in [0, 1] (float32), standing in for AttCommitNet's sigmoid heads."""
+    m = injected_scores(seed, t, 2, 32)
+    v = ((m.astype(np.float64) / 0.35 + 1.0) * 0.5).astype(np.float32)
+    return v[0], v[1, :16]
+
+
+def injected_logits(seed, t, n_rows, n_cols):
+    """Pair logits in [-3.5, 3.5] (float32), standing in for AttCoalitionNet."""
+    return (injected_scores(seed, t, n_rows, n_cols) * np.float32(10.0)).astype(np.float32)
+
+
+class _InjectedNet:
+    """Stands in for planner.net: returns what the episode loop put into `.out` (torch tensors, batch of 1)."""
+
+    def __init__(self):
+        self.out = None
+
+    def eval(self):
+        return self
+
+    def __call__(self, *a, **k):
+        return self.out
+
+
+def tok_dump(tok):
+    return {k: np.asarray(tok[k]).astype(np.float64).tolist() if k in ("task_feats", "agent_feats", "edge_valid")
+            else [int(x) for x in np.asarray(tok[k]).reshape(-1)]
+            for k in ("task_feats", "task_mask", "agent_feats", "agent_mask", "edge_valid", "task_ids") if k in tok}
+
+
 def hybrid_should_replan(env, events, interval=15):
     return (env.time_steps == 0 or env.time_steps % interval == 0
             or any(ev[0] in ("Reset_Allocation", "New_Threat", "Agent_Fail") for ev in events))
@@ -86,6 +122,18 @@ def run_episode(case, seed, driver, overrides=None):
         from TaskAllocation.Hybrid.AttentionEscort import UrgencyCoalition
         planner = UrgencyCoalition()
         hung = HungarianAllocator(replan_interval=10**9, max_coord=env.max_coord)
+    elif driver == "att_commit_injected":
+        import torch
+        from TaskAllocation.Hybrid.AttentionCommit import AttentionCommit
+        planner = AttentionCommit(use_attention=False, device="cpu")
+        planner.net = _InjectedNet()
+    elif driver == "att_escort_injected":
+        import torch
+        from TaskAllocation.Hybrid.AttentionEscort import AttentionEscort
+        planner = AttentionEscort(use_attention=False, device="cpu", d_model=16)
+        planner.net = _InjectedNet()
+        hung = HungarianAllocator(replan_interval=10**9, max_coord=env.max_coord)
+    n_plans = 0
     rnd = random.Random(seed * 7919 + 13)
     ep = {"case": case, "seed": seed, "driver": driver, "overrides": overrides or {},
           "agent_names": [a.name for a in env.agents_obj],
@@ -93,6 +141,7 @@ def run_episode(case, seed, driver, overrides=None):
     while True:
         events = list(info.get("events") or []) if isinstance(info, dict) else []
         pairs = []
+        tok_rec = None
         if driver in ("local_hungarian", "coalition"):
             res = hung.allocate_tasks(env.get_live_agents(), ref_open_tasks(env), time_step=env.time_steps,
                                       events=events, agent_known_ids=env.agent_visibility_map())
@@ -112,6 +161,22 @@ def run_episode(case, seed, driver, overrides=None):
                     ev[0] in ("Reset_Allocation", "New_Threat", "Agent_Fail", "Escort_Created", "Escort_Retired")
                     for ev in events)):
                 pairs = planner.plan(env, hung, events=events, force=True)
+        elif driver == "att_commit_injected":
+            if hybrid_should_replan(env, events):
+                pv, cv = injected_commit_vectors(seed, env.time_steps)
+                planner.net.out = (torch.tensor(pv)[None], torch.tensor(cv)[None])
+                pairs = planner.plan(env, hung, events=events, force=True)[0]
+        elif driver == "att_escort_injected":
+            if (env.time_steps == 0 or env.time_steps % 12 == 0 or any(
+                    ev[0] in ("Reset_Allocation", "New_Threat", "Agent_Fail", "Escort_Created", "Escort_Retired")
+                    for ev in events)):
+                lg = injected_logits(seed, env.time_steps, planner.max_agents, planner.max_tasks)
+                planner.net.out = (torch.tensor(lg)[None], torch.zeros(1))
+                out = planner.plan(env, hung, events=events, explore=False, force=True)
+                pairs = out[0]
+                if n_plans % 4 == 0:
+                    tok_rec = {"t": int(env.time_steps), "tok": tok_dump(out[1])}
+                n_plans += 1
         actions = {}
         if driver == "random_actions":
             n_open = len(env.last_tasks_info)
@@ -138,6 +203,8 @@ def run_episode(case, seed, driver, overrides=None):
             "n_open": len(env.last_tasks_info),
             "digest": str(refsnap.digest(snap)),
         })
+        if tok_rec is not None:
+            ep["steps"][-1]["escort_tokens"] = tok_rec["tok"]
         if all(term.values()) or all(trunc.values()):
             break
     m = info["metrics"]
@@ -163,6 +230,8 @@ PLAN = [
     ("wps_commit_urgency", "WPS_commit", "urgency_commit", range(0, 8), None),
     ("wps_escort_urgency", "WPS_escort", "urgency_coalition", range(0, 6), None),
     ("wps_hard_obstacles", "WPS_hard", "local_hungarian", range(0, 4), {"num_obstacles": 4}),
+    ("wps_commit_attcommit", "WPS_commit", "att_commit_injected", range(0, 6), None),
+    ("wps_escort_attescort", "WPS_escort", "att_escort_injected", range(0, 6), None),
 ]
 
 

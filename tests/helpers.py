@@ -38,6 +38,26 @@ def injected_scores(seed, t, n_rows, n_cols):
     return ((x.astype(np.float64) - 1000.0) / 1000.0 * 0.35).astype(np.float32)
 
 
+def injected_commit_vectors(seed, t):
+    """Same generator as tests/golden/gen_golden.py: (pri_vec [32], com_vec [16]) float32 in [0, 1]."""
+    m = injected_scores(seed, t, 2, 32)
+    v = ((m.astype(np.float64) / 0.35 + 1.0) * 0.5).astype(np.float32)
+    return v[0], v[1, :16]
+
+
+def injected_logits(seed, t, n_rows, n_cols):
+    return (injected_scores(seed, t, n_rows, n_cols) * np.float32(10.0)).astype(np.float32)
+
+
+def escort_scores_from_logits(logits, edge_valid, agent_mask, task_mask):
+    """AttentionEscort.act with explore=False (AttentionEscort.py:449-466): float32 sigmoid of the clipped logits,
+    zeroed on invalid edges and padded rows / columns."""
+    scores = 1.0 / (1.0 + np.exp(-np.clip(logits, -20, 20)))
+    scores = scores * edge_valid
+    scores = scores * (~np.asarray(agent_mask, bool))[:, None] * (~np.asarray(task_mask, bool))[None, :]
+    return scores.astype(np.float32)
+
+
 def alloc_opts_for(driver):
     O = _lib.MuavAllocOpts()
     O.max_coord = 1200.0
@@ -60,6 +80,12 @@ def alloc_opts_for(driver):
     elif driver == "urgency_coalition":
         O.mode, O.replan_interval, O.event_mask, O.use_visibility = 2, 12, 0x1F, 1
         O.planner = 2
+    elif driver == "att_commit_injected":
+        O.mode, O.replan_interval, O.event_mask, O.use_visibility = 2, 15, 0b111, 1
+        O.planner, O.commit_threshold, O.score_rows, O.score_cols = 3, 0.5, 16, 32
+    elif driver == "att_escort_injected":
+        O.mode, O.replan_interval, O.event_mask, O.use_visibility = 2, 12, 0x1F, 1
+        O.planner, O.score_rows, O.score_cols = 4, 16, 48
     else:
         raise ValueError(driver)
     return O
@@ -78,6 +104,8 @@ class HostCheck:
         d.hostcheck_step.restype = C.c_int
         d.hostcheck_step.argtypes = [C.POINTER(_lib.MuavConfig), P, P, P, C.POINTER(_lib.MuavAllocOpts),
                                      C.POINTER(_lib.MuavStepOut), C.c_int, C.c_int]
+        d.hostcheck_tokens_escort.restype = C.c_int
+        d.hostcheck_tokens_escort.argtypes = [C.POINTER(_lib.MuavConfig), P, C.c_int, C.c_int, P, P, P, P, P, P, P, C.c_int]
         d.hostcheck_lsap.restype = C.c_int
         d.hostcheck_lsap.argtypes = [P, P, P, C.c_int, C.c_int, P, C.c_int]
 
@@ -142,6 +170,20 @@ class HostEnv:
         rc = self.lib.dll.hostcheck_step(C.byref(self.cfg), self.rec.ctypes.data, self.tapes.ctypes.data, None,
                                          C.byref(O), C.byref(self.out), self.E, n_steps)
         assert rc == 0
+
+    def tokens_escort(self, max_tasks=48, max_agents=16):
+        E = self.E
+        IC = max(self.cfg.id_cap, self.cfg.task_cap)
+        tok = {"task_feats": np.zeros((E, max_tasks, 22), np.float32), "task_mask": np.zeros((E, max_tasks), np.uint8),
+               "agent_feats": np.zeros((E, max_agents, 16), np.float32), "agent_mask": np.zeros((E, max_agents), np.uint8),
+               "edge_valid": np.zeros((E, max_agents, max_tasks), np.float32), "task_ids": np.zeros((E, max_tasks), np.int32),
+               "task_order": np.zeros((E, IC), np.int32)}
+        rc = self.lib.dll.hostcheck_tokens_escort(
+            C.byref(self.cfg), self.rec.ctypes.data, max_tasks, max_agents, tok["task_feats"].ctypes.data,
+            tok["task_mask"].ctypes.data, tok["agent_feats"].ctypes.data, tok["agent_mask"].ctypes.data,
+            tok["edge_valid"].ctypes.data, tok["task_ids"].ctypes.data, tok["task_order"].ctypes.data, E)
+        assert rc == 0
+        return tok
 
     def snapshot(self, e):
         return self.codec.snapshot(self.rec[e])

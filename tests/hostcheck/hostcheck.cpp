@@ -140,6 +140,23 @@ int hostcheck_tokens_pair(const muav_config* cfg, const void* records, int max_t
   return 0;
 }
 
+int hostcheck_tokens_escort(const muav_config* cfg, const void* records, int max_tasks, int max_agents, float* tf,
+                            uint8_t* tm, float* af, uint8_t* am, float* ev, int32_t* ids, int32_t* order, int n_envs) {
+  Layout L = make_layout(*cfg);
+  char* scratch = (char*)malloc(escort_tok_scratch_bytes(L.D.TC, max_tasks));
+  EscortTokScratch W = carve_escort_tok(scratch, L.D.TC, max_tasks);
+  for (int e = 0; e < n_envs; ++e) {
+    View V;
+    V.base = (char*)records + (size_t)e * L.record_bytes;
+    V.L = &L;
+    tokens_escort_env(V, *cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * 22, tm + (size_t)e * max_tasks,
+                      af + (size_t)e * max_agents * 16, am + (size_t)e * max_agents, ev + (size_t)e * max_agents * max_tasks,
+                      ids + (size_t)e * max_tasks, order ? order + (size_t)e * L.D.IC : nullptr, W, 0, 1);
+  }
+  free(scratch);
+  return 0;
+}
+
 int hostcheck_observe(const muav_config* cfg, const void* records, int max_rows, double* ti, uint8_t* pad, uint8_t* legal,
                       double* ao, float* ef, int32_t* n_rows, int n_envs) {
   Layout L = make_layout(*cfg);

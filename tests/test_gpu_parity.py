@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import golden_config, injected_scores, load_golden
+from helpers import (escort_scores_from_logits, golden_config, injected_commit_vectors, injected_logits, injected_scores,
+                     load_golden)
 import refsnap
 
 pytestmark = pytest.mark.gpu
@@ -19,7 +20,8 @@ STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit
               "wps_hard_global", "wps_hard_pair", "wps_commit_pair", "wps_hard_random", "wps_escort_random",
               "wps_attn_xl_local", "wps_hard_single_task"]
 # planner fixtures mutate commit_until between steps: they are replayed through the fused planner only
-ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + ["wps_commit_urgency", "wps_escort_urgency"]
+ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
+    "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort"]
 
 
 def make_env(cfg, seeds, **kw):
@@ -33,7 +35,8 @@ def spec_for(driver):
 
     return {"local_hungarian": AllocSpec.local_hungarian(20), "coalition": AllocSpec.coalition_hungarian(12),
             "global_hungarian": AllocSpec.global_hungarian(20), "pair_injected": AllocSpec.pair_hybrid(15),
-            "urgency_commit": AllocSpec.urgency_commit(15), "urgency_coalition": AllocSpec.urgency_coalition(12)}[driver]
+            "urgency_commit": AllocSpec.urgency_commit(15), "urgency_coalition": AllocSpec.urgency_coalition(12),
+            "att_commit_injected": AllocSpec.att_commit(15), "att_escort_injected": AllocSpec.att_escort(12)}[driver]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)
@@ -82,7 +85,29 @@ def test_cuda_fused_allocator_matches_reference_golden(name):
         scores = None
         if drv == "pair_injected":
             scores = torch.from_numpy(np.stack([injected_scores(ep["seed"], t, 16, 32) for ep in eps]))
-        env.step_allocated(spec, 1, edge_scores=scores)
+        kw = {}
+        if drv == "att_commit_injected":
+            vec = [injected_commit_vectors(ep["seed"], t) for ep in eps]
+            kw = {"plan_pri": torch.from_numpy(np.stack([v[0] for v in vec])),
+                  "plan_commit": torch.from_numpy(np.stack([v[1] for v in vec]))}
+        elif drv == "att_escort_injected":
+            dtok = env.tokens_escort(48, 16)
+            tok = {k: v.cpu().numpy() for k, v in dtok.items()}
+            for e, ep in enumerate(eps):
+                ref_tok = ep["steps"][t].get("escort_tokens")   # build_escort_tokens of the reference at this step
+                if ref_tok is None:
+                    continue
+                for k in ("task_feats", "agent_feats", "edge_valid"):
+                    assert np.array_equal(np.asarray(ref_tok[k], np.float32), tok[k][e]), (ep["seed"], t, k)
+                for k in ("task_mask", "agent_mask"):
+                    assert [int(x) for x in tok[k][e]] == ref_tok[k], (ep["seed"], t, k)
+                nk = len(ref_tok["task_ids"])
+                assert [int(x) for x in tok["task_ids"][e][:nk]] == ref_tok["task_ids"] and not tok["task_ids"][e][nk:].any()
+            scores = torch.from_numpy(np.stack([
+                escort_scores_from_logits(injected_logits(ep["seed"], t, 16, 48), tok["edge_valid"][e], tok["agent_mask"][e],
+                                          tok["task_mask"][e]) for e, ep in enumerate(eps)]))
+            kw = {"task_order": dtok["task_order"]}
+        env.step_allocated(spec, 1, edge_scores=scores, **kw)
         rew = env.reward.cpu().numpy()
         recs = env.records.cpu().numpy()
         for e, ep in enumerate(eps):
@@ -90,7 +115,7 @@ def test_cuda_fused_allocator_matches_reference_golden(name):
             assert env.pairs_of(e) == st["pairs"], (name, ep["seed"], t)
             assert rew[e] == float.fromhex(st["reward"]), (name, ep["seed"], t)
             assert str(refsnap.digest(env.codec.snapshot(recs[e]))) == st["digest"], (name, ep["seed"], t)
-    if drv not in ("pair_injected", "urgency_commit", "urgency_coalition"):
+    if drv in ("local_hungarian", "coalition", "global_hungarian"):
         nrep = env.header_int("N_REPLANS").cpu().numpy()
         for e, ep in enumerate(eps):
             assert int(nrep[e]) == ep["n_replans"]
@@ -578,3 +603,78 @@ def test_commit_tokens_match_oracle():
             pairs = oplan.urgency_commit_plan(o, hungs[e]) if otok.hybrid_should_replan(o, o.last_events, 15) else []
             o.step(apply_assign(o, pairs))
     assert saw_lock
+
+
+def test_escort_tokens_and_learned_coalition_pipeline_match_oracle():
+    """tokens_escort -> AttCoalitionNet (random init) -> coalition_scores -> AllocSpec.att_escort on the device, against
+    the oracle fed with the same scores, on fresh seeds: tokens bit-exact every replan, state digests every step."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+    from multi_uav_ta_gym_env_b200.scorers import AttCoalitionNet, coalition_scores
+    from oracle.hungarian import OracleHungarian, apply_assign
+    from oracle import planners as oplan
+    from oracle import tokens as otok
+    from oracle.sim import OracleEnv
+
+    cfg = wps_config("WPS_escort")
+    seeds = [21, 22, 23]
+    env = make_env(cfg, seeds)
+    torch.manual_seed(0)
+    net = AttCoalitionNet().cuda().eval()
+    oracles = [OracleEnv(cfg).reset(s) for s in seeds]
+    hungs = [OracleHungarian(10**9, 1200.0) for _ in seeds]
+    spec = AllocSpec.att_escort(12)
+    for t in range(150):
+        tok = env.tokens_escort(48, 16)
+        scores = coalition_scores(net, tok)
+        host = {k: v.cpu().numpy() for k, v in tok.items()}
+        sc = scores.cpu().numpy()
+        for e, o in enumerate(oracles):
+            pairs = []
+            if o.t == 0 or o.t % 12 == 0 or len(o.last_events) > 0:
+                want = otok.build_escort_tokens(o, 48, 16)
+                for k in ("task_feats", "task_mask", "agent_feats", "agent_mask", "edge_valid", "task_ids"):
+                    assert np.array_equal(host[k][e], want[k]), (t, e, k)
+                pairs = oplan.att_escort_plan_from_scores(o, hungs[e], sc[e])
+            o.step(apply_assign(o, pairs))
+        env.step_allocated(spec, 1, edge_scores=scores, task_order=tok["task_order"])
+        recs = env.records.cpu().numpy()
+        for e, o in enumerate(oracles):
+            assert refsnap.digest(env.codec.snapshot(recs[e])) == refsnap.digest(o.snapshot()), (t, e)
+    assert int(env.error_flags().abs().max().item()) == 0
+
+
+def test_learned_commit_pipeline_matches_oracle():
+    """tokens_commit -> AttCommitNet (random init) -> AllocSpec.att_commit on the device vs the oracle with the same vectors."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+    from multi_uav_ta_gym_env_b200.scorers import AttCommitNet, commit_vectors
+    from oracle.hungarian import OracleHungarian, apply_assign
+    from oracle import planners as oplan
+    from oracle import tokens as otok
+    from oracle.sim import OracleEnv
+
+    cfg = wps_config("WPS_commit")
+    seeds = [31, 32, 33]
+    env = make_env(cfg, seeds)
+    torch.manual_seed(0)
+    net = AttCommitNet().cuda().eval()
+    oracles = [OracleEnv(cfg).reset(s) for s in seeds]
+    hungs = [OracleHungarian(20, 1200.0) for _ in seeds]
+    com0 = commit_vectors(net, env.tokens_commit(32, 16))[1]
+    thr = float(com0[com0 > 0].median().item())   # a random-init commit head hovers around one value: gate at its median
+    spec = AllocSpec.att_commit(15, commit_threshold=thr)
+    locks = 0
+    for t in range(150):
+        tok = env.tokens_commit(32, 16)
+        pri, com = commit_vectors(net, tok)
+        hp, hc = pri.cpu().numpy(), com.cpu().numpy()
+        for e, o in enumerate(oracles):
+            pairs = []
+            if otok.hybrid_should_replan(o, o.last_events, 15):
+                pairs = oplan.att_commit_plan_from_scores(o, hungs[e], hp[e], hc[e], thr)
+                locks += sum(1 for a in range(o.n_agents) if int(o.a_commit_until[a] or 0) > o.t)
+            o.step(apply_assign(o, pairs))
+        env.step_allocated(spec, 1, plan_pri=pri, plan_commit=com)
+        recs = env.records.cpu().numpy()
+        for e, o in enumerate(oracles):
+            assert refsnap.digest(env.codec.snapshot(recs[e])) == refsnap.digest(o.snapshot()), (t, e)
+    assert locks > 0

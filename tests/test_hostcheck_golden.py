@@ -4,13 +4,15 @@ repeats these checks through the C ABI on the device."""
 import numpy as np
 import pytest
 
-from helpers import alloc_opts_for, golden_config, injected_scores, load_golden
+from helpers import (alloc_opts_for, escort_scores_from_logits, golden_config, injected_commit_vectors, injected_logits,
+                     injected_scores, load_golden)
 
 STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit_local", "wps_escort_coalition",
               "wps_hard_global", "wps_hard_pair", "wps_commit_pair", "wps_hard_random", "wps_escort_random",
               "wps_attn_xl_local", "wps_hard_single_task", "wps_hard_obstacles"]
 # planner fixtures mutate commit_until between steps: they are replayed through the fused planner only
-ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + ["wps_commit_urgency", "wps_escort_urgency"]
+ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
+    "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort"]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)
@@ -41,13 +43,34 @@ def test_fused_allocator(hostcheck, name):
         if drv == "pair_injected":
             sc = np.stack([injected_scores(ep["seed"], t, 16, 32) for ep in eps])
             O.d_edge_scores = sc.ctypes.data
+        elif drv == "att_commit_injected":
+            vec = [injected_commit_vectors(ep["seed"], t) for ep in eps]
+            pv = np.stack([v[0] for v in vec])
+            cv = np.stack([v[1] for v in vec])
+            O.d_plan_pri, O.d_plan_commit = pv.ctypes.data, cv.ctypes.data
+        elif drv == "att_escort_injected":
+            tok = env.tokens_escort(48, 16)
+            for e, ep in enumerate(eps):
+                ref_tok = ep["steps"][t].get("escort_tokens")
+                if ref_tok is None:
+                    continue
+                for k in ("task_feats", "agent_feats", "edge_valid"):
+                    assert np.array_equal(np.asarray(ref_tok[k], np.float32), tok[k][e]), (ep["seed"], t, k)
+                for k in ("task_mask", "agent_mask"):
+                    assert [int(x) for x in tok[k][e]] == ref_tok[k], (ep["seed"], t, k)
+                nk = len(ref_tok["task_ids"])
+                assert [int(x) for x in tok["task_ids"][e][:nk]] == ref_tok["task_ids"] and not tok["task_ids"][e][nk:].any()
+                assert [int(x) + 1 for x in tok["task_order"][e][:nk]] == ref_tok["task_ids"] and tok["task_order"][e][nk] == -1
+            sc = np.stack([escort_scores_from_logits(injected_logits(ep["seed"], t, 16, 48), tok["edge_valid"][e],
+                                                     tok["agent_mask"][e], tok["task_mask"][e]) for e, ep in enumerate(eps)])
+            O.d_edge_scores, O.d_task_order = sc.ctypes.data, tok["task_order"].ctypes.data
         env.step_alloc(O)
         for e, ep in enumerate(eps):
             st = ep["steps"][t]
             assert env.pairs_of(e) == st["pairs"], (name, ep["seed"], t)
             assert env.reward[e] == float.fromhex(st["reward"])
             assert str(env.digest(e)) == st["digest"], (name, ep["seed"], t)
-    if drv not in ("pair_injected", "urgency_commit", "urgency_coalition"):
+    if drv in ("local_hungarian", "coalition", "global_hungarian"):
         for e, ep in enumerate(eps):
             assert env.codec.header(env.rec[e], "N_REPLANS") == ep["n_replans"]
 

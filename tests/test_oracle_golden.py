@@ -3,7 +3,10 @@
 events, allocator pairs and terminal metrics must be identical (bit-exact)."""
 import pytest
 
-from helpers import injected_scores, load_golden, golden_config
+import numpy as np
+
+from helpers import (escort_scores_from_logits, injected_commit_vectors, injected_logits, injected_scores, load_golden,
+                     golden_config)
 import refsnap
 from oracle.hungarian import OracleHungarian, apply_assign, open_tasks
 from oracle.sim import OracleEnv
@@ -16,6 +19,7 @@ CASES = [
     ("wps_escort_coalition", 2), ("wps_hard_global", 2), ("wps_hard_pair", 3), ("wps_commit_pair", 1),
     ("wps_hard_random", 3), ("wps_escort_random", 1), ("wps_attn_xl_local", 1), ("wps_hard_single_task", 2),
     ("wps_commit_urgency", 3), ("wps_escort_urgency", 2), ("wps_hard_obstacles", 2),
+    ("wps_commit_attcommit", 3), ("wps_escort_attescort", 3),
 ]
 
 
@@ -24,7 +28,7 @@ def replay(ep):
     o = OracleEnv(cfg).reset(ep["seed"])
     assert str(refsnap.digest(o.snapshot())) == ep["digest0"]
     drv = ep["driver"]
-    interval = 12 if drv == "coalition" else (10**9 if drv == "urgency_coalition" else 20)
+    interval = 12 if drv == "coalition" else (10**9 if drv in ("urgency_coalition", "att_escort_injected") else 20)
     hung = OracleHungarian(interval, o.max_coord)
     for t, st in enumerate(ep["steps"]):
         if drv in ("local_hungarian", "coalition", "global_hungarian"):
@@ -48,6 +52,27 @@ def replay(ep):
             if o.t == 0 or o.t % 12 == 0 or len(o.last_events) > 0:
                 pairs = oplan.urgency_coalition_plan(o, hung)
             assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
+        elif drv == "att_commit_injected":
+            pairs = []
+            if otok.hybrid_should_replan(o, o.last_events, 15):
+                pv, cv = injected_commit_vectors(ep["seed"], o.t)
+                pairs = oplan.att_commit_plan_from_scores(o, hung, pv, cv)
+            assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
+        elif drv == "att_escort_injected":
+            pairs = []
+            if o.t == 0 or o.t % 12 == 0 or len(o.last_events) > 0:
+                tok = otok.build_escort_tokens(o, 48, 16)
+                if "escort_tokens" in st:   # the reference's own build_escort_tokens output at this step
+                    ref_tok = st["escort_tokens"]
+                    for k in ("task_feats", "agent_feats", "edge_valid"):
+                        assert np.array_equal(np.asarray(ref_tok[k], np.float32), tok[k]), (ep["seed"], t, k)
+                    for k in ("task_mask", "agent_mask"):
+                        assert [int(x) for x in tok[k]] == ref_tok[k], (ep["seed"], t, k)
+                    assert [int(x) for x in tok["task_ids"][: len(ref_tok["task_ids"])]] == ref_tok["task_ids"]
+                lg = injected_logits(ep["seed"], o.t, 16, 48)
+                sc = escort_scores_from_logits(lg, tok["edge_valid"], tok["agent_mask"], tok["task_mask"])
+                pairs = oplan.att_escort_plan_from_scores(o, hung, sc)
+            assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
         r, term, trunc, ev = o.step([tuple(a) for a in st["actions"]])
         assert [list(e) for e in ev] == st["events"], (ep["seed"], t)
         assert r == float.fromhex(st["reward"]), (ep["seed"], t)
@@ -58,7 +83,7 @@ def replay(ep):
     for k, v in ep["metrics"].items():
         want = float.fromhex(v) if isinstance(v, str) else v
         assert m[k] == want or (m[k] != m[k] and want != want), k
-    if drv not in ("pair_injected", "urgency_commit", "urgency_coalition"):
+    if drv in ("local_hungarian", "coalition", "global_hungarian"):
         assert hung.n_replans == ep["n_replans"]
 
 

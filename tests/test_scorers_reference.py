@@ -1,0 +1,75 @@
+"""multi_uav_ta_gym_env_b200.scorers against the reference network classes (authoring container only): the same
+torch seed followed by construction gives identical parameters, and the forward passes agree exactly on CPU.
+Pins AttPairNet / MLPPairNet (PairCostHybrid.py:89-196), AttCommitNet / MLPCommitNet (AttentionCommit.py:68-129) and
+AttCoalitionNet / MLPCoalitionNet (AttentionEscort.py:244-375)."""
+import numpy as np
+import pytest
+import torch
+
+import refshim
+
+pytestmark = pytest.mark.skipif(not refshim.reference_available(), reason="reference tree not present")
+
+
+def _pairs():
+    refshim.install()
+    from TaskAllocation.Hybrid import AttentionCommit as RC
+    from TaskAllocation.Hybrid import AttentionEscort as RE
+    from TaskAllocation.Hybrid import PairCostHybrid as RP
+    from multi_uav_ta_gym_env_b200 import scorers as S
+
+    return [
+        ("att_pair", RP.AttPairNet, S.AttPairNet, (32, 13), (16, 12)),
+        ("mlp_pair", RP.MLPPairNet, S.MLPPairNet, (32, 13), (16, 12)),
+        ("att_commit", RC.AttCommitNet, S.AttCommitNet, (32, 13), (16, 13)),
+        ("mlp_commit", RC.MLPCommitNet, S.MLPCommitNet, (32, 13), (16, 13)),
+        ("att_coalition", RE.AttCoalitionNet, S.AttCoalitionNet, (48, 22), (16, 16)),
+        ("mlp_coalition", RE.MLPCoalitionNet, S.MLPCoalitionNet, (48, 22), (16, 16)),
+    ]
+
+
+@pytest.mark.parametrize("idx", range(6))
+def test_same_seed_same_parameters_same_forward(idx):
+    name, Ref, Mine, tshape, ashape = _pairs()[idx]
+    torch.manual_seed(7)
+    ref = Ref().eval()
+    torch.manual_seed(7)
+    mine = Mine().eval()
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs.keys()) == list(ms.keys()), name
+    for k in rs:
+        assert torch.equal(rs[k], ms[k]), (name, k)
+    g = torch.Generator().manual_seed(3)
+    B = 5
+    tf = torch.rand(B, *tshape, generator=g)
+    af = torch.rand(B, *ashape, generator=g)
+    tm = torch.zeros(B, tshape[0], dtype=torch.bool)
+    am = torch.zeros(B, ashape[0], dtype=torch.bool)
+    for b in range(B):
+        tm[b, 5 + 3 * b:] = True
+        am[b, 6 + b:] = True
+    with torch.no_grad():
+        ro = ref(tf, tm, af, am)
+        mo = mine(tf, tm, af, am)
+    for r, m in zip(ro, mo):
+        assert torch.equal(r, m), name
+
+
+def test_coalition_scores_follow_act():
+    """scorers.coalition_scores == AttentionEscort.act(explore=False) (AttentionEscort.py:449-466)."""
+    refshim.install()
+    from TaskAllocation.Hybrid.AttentionEscort import AttentionEscort
+    from multi_uav_ta_gym_env_b200 import scorers as S
+
+    torch.manual_seed(11)
+    pol = AttentionEscort(device="cpu", use_attention=False)
+    g = torch.Generator().manual_seed(5)
+    tok = {"task_feats": torch.rand(48, 22, generator=g).numpy(), "agent_feats": torch.rand(16, 16, generator=g).numpy(),
+           "task_mask": np.arange(48) >= 20, "agent_mask": np.arange(16) >= 9,
+           "edge_valid": (torch.rand(16, 48, generator=g) > 0.3).float().numpy()}
+    want, _, _ = pol.act(tok, explore=False)
+    mine = S.MLPCoalitionNet(hidden=max(128, 128 * 2))
+    mine.load_state_dict(pol.net.state_dict())
+    tt = {k: torch.as_tensor(v)[None] for k, v in tok.items()}
+    got = S.coalition_scores(mine.eval(), tt)[0].numpy()
+    assert np.allclose(got, want, atol=1e-6, rtol=0)

@@ -19,7 +19,8 @@ if case.startswith("burst_x"):
     cfg = wps_config(burst_scaled_spec(int(case[7:])))
 else:
     cfg = wps_config(case)
-env = BatchedMultiUAVEnv(cfg, E).reset(range(E))
+tc = int(os.environ["KB_TASK_CAP"]) if "KB_TASK_CAP" in os.environ else None
+env = BatchedMultiUAVEnv(cfg, E, task_cap=tc).reset(range(E))
 spec = AllocSpec(1, interval, 0x1F, True, False)
 if len(sys.argv) > 3 and sys.argv[3] == "urgency_commit":
     spec = AllocSpec.urgency_commit(15)
