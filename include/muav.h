@@ -92,7 +92,9 @@ typedef struct muav_alloc_opts {
                                 agents reserved, free assigned agents whose d_plan_commit[row] >= commit_threshold are locked;
                               4 AttentionEscort._plan_from_scores (AttentionEscort.py:500-517): d_edge_scores in
                                 muav_tokens_escort layout over d_task_order, committed agents reserved, every assigned
-                                agent locked for commit_horizon */
+                                agent locked for commit_horizon;
+                              5 UrgencyPair.plan (PairCostHybrid.py:520-550): urgency_edge_scores (:68-86) on the valid
+                                edges of build_pair_tokens(score_cols = max_tasks, score_rows = max_agents), no locks */
   int32_t reserved1;
   double commit_fraction;  /* UrgencyCommit(commit_fraction=0.35) */
   double max_coord;        /* HungarianAllocator(max_coord=...) */
@@ -157,6 +159,22 @@ int muav_allocate(const muav_config* cfg, void* d_records, const muav_alloc_opts
 int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* h_actions,
                    const muav_alloc_opts* opts, const muav_token_out* tok, double* h_reward, uint8_t* h_terminated,
                    uint8_t* h_truncated, int n_envs, int n_steps, void* stream);
+
+/* K fused (plan -> allocate -> step) iterations with the state resident on chip: muav_step with a fused allocator and
+ * no external actions (the episode loops of experiments/wps_eval.py:96-140 and escort_eval.py:85-200 without the
+ * Python round trip). */
+int muav_rollout(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const muav_alloc_opts* opts,
+                 const muav_step_out* out, const muav_token_out* tok, int n_envs, int n_steps, void* stream);
+/* Bytes of device memory the caller allocates for n_envs records / RNG tapes. */
+size_t muav_state_bytes(const muav_config* cfg, int n_envs);
+size_t muav_tape_bytes(const muav_config* cfg, int n_envs);
+/* Upload the host-packed reset state (MultiUAVEnv.reset runs on the host, DroneEnv.py:522-762): h_records
+ * [n_envs, record_bytes], h_tapes [n_envs, sum(tape_words)] uint32 -> device, stream-ordered. */
+int muav_reset_upload(const muav_config* cfg, void* d_records, uint32_t* d_tapes, const void* h_records,
+                      const uint32_t* h_tapes, int n_envs, void* stream);
+/* Copy the record of environment `env_index` to the host (record_bytes; decoded with muav_field_info) and wait for it:
+ * what the object proxies and the parity snapshots read. */
+int muav_snapshot(const muav_config* cfg, const void* d_records, int env_index, void* h_record, void* stream);
 
 /* Batched rectangular LSAP: B problems, cost [B, nr_max, nc_max] row-major with per-problem sizes.
  * out_col4row [B, nr_max]: column assigned to each row or -1 (SciPy tie-breaking reproduced). */

@@ -63,6 +63,10 @@ class AllocSpec:
         """UrgencyCoalition under escort_eval.py:52-58,175-179 (every event tag triggers)."""
         return AllocSpec(2, interval, ALL_EVENTS, True, False, planner=2)
 
+    @staticmethod
+    def urgency_pair(interval=15):
+        """UrgencyPair.plan (PairCostHybrid.py:520-550) under the hybrid cadence; scores are computed on the device."""
+        return AllocSpec(2, interval, HYBRID_EVENTS, True, True, planner=5)
 
     @staticmethod
     def att_commit(interval=15, commit_threshold=0.5):
@@ -129,9 +133,16 @@ class BatchedMultiUAVEnv:
         self.scenarios = [_reset.generate_scenario(self.config, int(s), tw) for s in seeds]
         self.agent_names = [sc.agent_names for sc in self.scenarios]
         rec, tapes = _reset.pack_records(self.lib, self.cfg, self.scenarios)
-        self._records0 = torch.from_numpy(rec).to(self.device)
-        self.records = self._records0.clone()
-        self.tapes = torch.from_numpy(tapes.view(np.int32)).to(self.device)
+        E = self.n_envs
+        dll = self.lib.dll
+        assert dll.muav_state_bytes(C.byref(self.cfg), E) == rec.nbytes and dll.muav_tape_bytes(C.byref(self.cfg), E) == tapes.nbytes
+        self.records = torch.empty(E, rec.shape[1], dtype=torch.uint8, device=self.device)
+        self.tapes = torch.empty(E, tapes.shape[1], dtype=torch.int32, device=self.device)
+        rc = dll.muav_reset_upload(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(), rec.ctypes.data,
+                                   tapes.ctypes.data, E, self._stream())
+        _lib.check(rc, "muav_reset_upload")
+        torch.cuda.current_stream(self.device).synchronize()
+        self._records0 = self.records.clone()
         self.n_open.fill_(int(self.codec.header(rec[0], "N_OPEN")))
         return self
 
@@ -253,10 +264,9 @@ class BatchedMultiUAVEnv:
                        plan_commit: Optional[torch.Tensor] = None):
         """n_steps fused (allocate -> step) iterations per environment, state resident in shared memory."""
         O, keep = self._alloc_opts(spec, edge_scores, priorities, reserved, task_order, plan_pri, plan_commit)
-        rc = self.lib.dll.muav_step(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(), None,
-                                    C.byref(O), C.byref(self._out), self._tok_ref(), self.n_envs, n_steps,
-                                    self._stream())
-        _lib.check(rc, "muav_step")
+        rc = self.lib.dll.muav_rollout(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(), C.byref(O),
+                                       C.byref(self._out), self._tok_ref(), self.n_envs, n_steps, self._stream())
+        _lib.check(rc, "muav_rollout")
         self.launches += 1
         return self.reward, self.terminated, self.truncated
 
@@ -355,7 +365,10 @@ class BatchedMultiUAVEnv:
                 "n_rows": nr}
 
     def record_host(self, e: int) -> np.ndarray:
-        return self.records[e].cpu().numpy()
+        buf = np.empty(self.record_bytes, dtype=np.uint8)
+        rc = self.lib.dll.muav_snapshot(C.byref(self.cfg), self.records.data_ptr(), int(e), buf.ctypes.data, self._stream())
+        _lib.check(rc, "muav_snapshot")
+        return buf
 
     def snapshot(self, e: int) -> dict:
         return self.codec.snapshot(self.record_host(e))

@@ -316,6 +316,25 @@ MUAV_HD MUAV_NI_A inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, in
           double sc = 0.0;
           if (O.planner == 2) {
             sc = coalition_edge_score(S, a, k, t);
+          } else if (O.planner == 5) {
+            // urgency_edge_scores (PairCostHybrid.py:68-86) on the valid edges of the pair tokens; stored as float32
+            const int col = W.tokcol[q];
+            const int row = W.live_row[i];
+            if (row < O.score_rows && col >= 0 && S.known_bit(a, k) && S.cap(a, ti) > 0) {
+              double scar = 0.0;
+              if (!(!(S.C().sense_radius != 0.0) && !(S.C().threat_delay != 0))) {
+                int cnt = 0, n_live = 0;
+                for (int b = 0; b < A; ++b) {
+                  cnt += S.known_bit(b, k) ? 1 : 0;
+                  n_live += V.a_state()[b] != -1;
+                }
+                scar = 1.0 - dmin(ddiv((double)cnt, (double)(n_live > 1 ? n_live : 1)), 1.0);
+              }
+              const double d = ddiv(norm2(V.a_posx()[a] - V.k_posx()[k], V.a_posy()[a] - V.k_posy()[k]),
+                                    dmax(S.C().max_coord, 1.0));
+              const double raw = 0.5 * urgency + 0.3 * scar - 0.4 * d;
+              sc = (double)(float)dmin(dmax(raw, -0.35), 0.35);
+            }
           } else if (scores64) {
             if (a < O.score_rows && k < O.score_cols) sc = scores64[a * O.score_cols + k];
           } else if (scores) {
@@ -521,6 +540,13 @@ MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, in
     P.score_cols = V.L->D.IC;
     P.score_rows = 0;
     P.use_visibility = 1;
+  } else if (O.planner == 5) {
+    P.d_priorities = nullptr;
+    P.pair_tokens = 1;      // build_pair_tokens' kept list: open_tasks[:max_tasks]
+    P.score_rows = O.score_rows > 0 ? O.score_rows : 16;
+    P.score_cols = O.score_cols > 0 ? O.score_cols : 32;
+    P.use_visibility = 1;
+    P.d_reserved = nullptr;  // UrgencyPair.plan passes no reserved agents
   } else if (O.planner == 4) {
     P.d_priorities = nullptr;
     P.d_edge_scores = O.d_edge_scores;
@@ -535,7 +561,9 @@ MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, in
   }
   const int np = allocate_tasks(S, P, e, out_agent, out_tid, lane, nlanes, true);
   if (lane == 0 && np > 0) {
-    if (O.planner == 2 || O.planner == 4) {
+    if (O.planner == 5) {
+      // UrgencyPair.plan takes no commit locks
+    } else if (O.planner == 2 || O.planner == 4) {
       for (int i = 0; i < np; ++i) apply_commit(S, out_agent[i], C.commit_horizon);
     } else if (O.planner == 3) {
       // AttentionCommit._plan_from_scores (AttentionCommit.py:289-298): gate by the commit head, row = live-agent index

@@ -455,6 +455,45 @@ int muav_allocate(const muav_config* cfg, void* d_records, const muav_alloc_opts
   return launch_step(P, stream);
 }
 
+int muav_rollout(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const muav_alloc_opts* opts,
+                 const muav_step_out* out, const muav_token_out* tok, int n_envs, int n_steps, void* stream) {
+  if (!opts || opts->mode == 0) return -22;  // a rollout needs the fused allocator
+  return muav_step(cfg, d_records, d_tapes, nullptr, opts, out, tok, n_envs, n_steps, stream);
+}
+
+size_t muav_state_bytes(const muav_config* cfg, int n_envs) {
+  if (check_cfg(cfg) || n_envs < 0) return 0;
+  return muav_record_bytes(cfg) * (size_t)n_envs;
+}
+
+size_t muav_tape_bytes(const muav_config* cfg, int n_envs) {
+  if (check_cfg(cfg) || n_envs < 0) return 0;
+  return (size_t)(cfg->tape_words[0] + cfg->tape_words[1] + cfg->tape_words[2]) * sizeof(uint32_t) * (size_t)n_envs;
+}
+
+int muav_reset_upload(const muav_config* cfg, void* d_records, uint32_t* d_tapes, const void* h_records,
+                      const uint32_t* h_tapes, int n_envs, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (n_envs <= 0) return n_envs == 0 ? 0 : -22;
+  if (!d_records || !d_tapes || !h_records || !h_tapes) return -22;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemcpyAsync(d_records, h_records, muav_state_bytes(cfg, n_envs), cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cuda_rc(e);
+  return cuda_rc(cudaMemcpyAsync(d_tapes, h_tapes, muav_tape_bytes(cfg, n_envs), cudaMemcpyHostToDevice, s));
+}
+
+int muav_snapshot(const muav_config* cfg, const void* d_records, int env_index, void* h_record, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (!d_records || !h_record || env_index < 0) return -22;
+  const size_t rb = muav_record_bytes(cfg);
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemcpyAsync(h_record, (const char*)d_records + rb * (size_t)env_index, rb, cudaMemcpyDeviceToHost, s);
+  if (e != cudaSuccess) return cuda_rc(e);
+  return cuda_rc(cudaStreamSynchronize(s));
+}
+
 int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* h_actions,
                    const muav_alloc_opts* opts, const muav_token_out* tok, double* h_reward, uint8_t* h_terminated,
                    uint8_t* h_truncated, int n_envs, int n_steps, void* stream) {

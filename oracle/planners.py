@@ -5,6 +5,7 @@ Deterministic hybrid planners restated over the oracle state:
   UrgencyCommit.plan                      TaskAllocation/Hybrid/AttentionCommit.py:310-357
   _open_tasks_residual / _threat_stats    TaskAllocation/Hybrid/AttentionEscort.py:31-65
   UrgencyCoalition.plan                   TaskAllocation/Hybrid/AttentionEscort.py:720-767
+  urgency_edge_scores / UrgencyPair.plan  TaskAllocation/Hybrid/PairCostHybrid.py:68-86, 520-550
   AttentionCommit._plan_from_scores       TaskAllocation/Hybrid/AttentionCommit.py:266-300
   AttentionEscort._plan_from_scores       TaskAllocation/Hybrid/AttentionEscort.py:500-517 (edge_score_dict :478-489)
 """
@@ -171,3 +172,34 @@ def att_escort_plan_from_scores(env, hung, scores, max_tasks=48, max_agents=16):
                            edge_scores=edge)
     apply_commits(env, [a for a, tid in result if tid != 0], int(env.commit_horizon or 0))
     return result
+
+
+def urgency_pair_plan(env, hung, max_tasks=32, max_agents=16):
+    """UrgencyPair.plan: hand-made edge residuals clip(0.5 urg + 0.3 scar - 0.4 dist, +-0.35) stored as float32."""
+    import numpy as np
+
+    from .tokens import build_pair_tokens
+
+    tok = build_pair_tokens(env, max_tasks, max_agents)
+    A = env.n_agents
+    vis = tok["vis"]
+    live = tok["live"]
+    n_agents = max(len(live), 1)
+    mc = max(float(env.max_coord), 1.0)
+    edge = {}
+    for i, a in enumerate(live[:max_agents]):
+        for j, tid in enumerate(tok["open_tasks"]):
+            if tok["edge_valid"][i, j] < 0.5:
+                continue
+            k = tid - 1
+            urg = urgency(env, k, env.t)
+            if vis is None:
+                scar = 0.0
+            else:
+                cnt = sum(1 for b in range(A) if vis[b][k])
+                scar = 1.0 - min(cnt / max(n_agents, 1), 1.0)
+            dist = norm2(env.a_pos[a][0] - env.k_pos[k][0], env.a_pos[a][1] - env.k_pos[k][1]) / mc
+            raw = 0.5 * urg + 0.3 * scar - 0.4 * dist
+            edge[(a, int(tid))] = float(np.float32(min(max(raw, -0.35), 0.35)))
+    return hung.allocate(env, agents=env.live_agents(), tasks=tok["open_tasks"], time_step=env.t, events=env.last_events,
+                         force=True, known=vis, edge_scores=edge)

@@ -18,6 +18,7 @@ Drivers (all restate the reference's own episode loops):
   random_actions    env.step driven by a seeded random policy (valid, stale and out-of-range indices)
   urgency_commit    UrgencyCommit.plan (AttentionCommit.py:310-357) under the hybrid cadence wps_eval.py:64-73
   urgency_coalition UrgencyCoalition.plan (AttentionEscort.py:720-767) under escort_eval.py:52-58, interval 12
+  urgency_pair      UrgencyPair.plan (PairCostHybrid.py:520-550) under the hybrid cadence wps_eval.py:64-73
   att_commit_injected  AttentionCommit.plan (AttentionCommit.py:260-300) with the network replaced by injected
                     (priority, commit) vectors, hybrid cadence wps_eval.py:64-73
   att_escort_injected  AttentionEscort.plan (AttentionEscort.py:519-524: build_escort_tokens -> act -> _plan_from_scores)
@@ -122,6 +123,9 @@ def run_episode(case, seed, driver, overrides=None):
         from TaskAllocation.Hybrid.AttentionEscort import UrgencyCoalition
         planner = UrgencyCoalition()
         hung = HungarianAllocator(replan_interval=10**9, max_coord=env.max_coord)
+    elif driver == "urgency_pair":
+        from TaskAllocation.Hybrid.PairCostHybrid import UrgencyPair
+        planner = UrgencyPair()
     elif driver == "att_commit_injected":
         import torch
         from TaskAllocation.Hybrid.AttentionCommit import AttentionCommit
@@ -161,6 +165,9 @@ def run_episode(case, seed, driver, overrides=None):
                     ev[0] in ("Reset_Allocation", "New_Threat", "Agent_Fail", "Escort_Created", "Escort_Retired")
                     for ev in events)):
                 pairs = planner.plan(env, hung, events=events, force=True)
+        elif driver == "urgency_pair":
+            if hybrid_should_replan(env, events):
+                pairs = planner.plan(env, hung, events=events, force=True)[0]
         elif driver == "att_commit_injected":
             if hybrid_should_replan(env, events):
                 pv, cv = injected_commit_vectors(seed, env.time_steps)
@@ -230,6 +237,7 @@ PLAN = [
     ("wps_commit_urgency", "WPS_commit", "urgency_commit", range(0, 8), None),
     ("wps_escort_urgency", "WPS_escort", "urgency_coalition", range(0, 6), None),
     ("wps_hard_obstacles", "WPS_hard", "local_hungarian", range(0, 4), {"num_obstacles": 4}),
+    ("wps_hard_urgency_pair", "WPS_hard", "urgency_pair", range(0, 6), None),
     ("wps_commit_attcommit", "WPS_commit", "att_commit_injected", range(0, 6), None),
     ("wps_escort_attescort", "WPS_escort", "att_escort_injected", range(0, 6), None),
 ]

@@ -80,6 +80,9 @@ def alloc_opts_for(driver):
     elif driver == "urgency_coalition":
         O.mode, O.replan_interval, O.event_mask, O.use_visibility = 2, 12, 0x1F, 1
         O.planner = 2
+    elif driver == "urgency_pair":
+        O.mode, O.replan_interval, O.event_mask, O.use_visibility = 2, 15, 0b111, 1
+        O.planner, O.score_rows, O.score_cols = 5, 16, 32
     elif driver == "att_commit_injected":
         O.mode, O.replan_interval, O.event_mask, O.use_visibility = 2, 15, 0b111, 1
         O.planner, O.commit_threshold, O.score_rows, O.score_cols = 3, 0.5, 16, 32

@@ -21,7 +21,7 @@ STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit
               "wps_attn_xl_local", "wps_hard_single_task"]
 # planner fixtures mutate commit_until between steps: they are replayed through the fused planner only
 ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
-    "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort"]
+    "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair"]
 
 
 def make_env(cfg, seeds, **kw):
@@ -36,7 +36,7 @@ def spec_for(driver):
     return {"local_hungarian": AllocSpec.local_hungarian(20), "coalition": AllocSpec.coalition_hungarian(12),
             "global_hungarian": AllocSpec.global_hungarian(20), "pair_injected": AllocSpec.pair_hybrid(15),
             "urgency_commit": AllocSpec.urgency_commit(15), "urgency_coalition": AllocSpec.urgency_coalition(12),
-            "att_commit_injected": AllocSpec.att_commit(15), "att_escort_injected": AllocSpec.att_escort(12)}[driver]
+            "urgency_pair": AllocSpec.urgency_pair(15), "att_commit_injected": AllocSpec.att_commit(15), "att_escort_injected": AllocSpec.att_escort(12)}[driver]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)

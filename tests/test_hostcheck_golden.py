@@ -12,7 +12,7 @@ STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit
               "wps_attn_xl_local", "wps_hard_single_task", "wps_hard_obstacles"]
 # planner fixtures mutate commit_until between steps: they are replayed through the fused planner only
 ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
-    "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort"]
+    "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair"]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)

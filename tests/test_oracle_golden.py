@@ -19,7 +19,7 @@ CASES = [
     ("wps_escort_coalition", 2), ("wps_hard_global", 2), ("wps_hard_pair", 3), ("wps_commit_pair", 1),
     ("wps_hard_random", 3), ("wps_escort_random", 1), ("wps_attn_xl_local", 1), ("wps_hard_single_task", 2),
     ("wps_commit_urgency", 3), ("wps_escort_urgency", 2), ("wps_hard_obstacles", 2),
-    ("wps_commit_attcommit", 3), ("wps_escort_attescort", 3),
+    ("wps_hard_urgency_pair", 3), ("wps_commit_attcommit", 3), ("wps_escort_attescort", 3),
 ]
 
 
@@ -51,6 +51,11 @@ def replay(ep):
             pairs = []
             if o.t == 0 or o.t % 12 == 0 or len(o.last_events) > 0:
                 pairs = oplan.urgency_coalition_plan(o, hung)
+            assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
+        elif drv == "urgency_pair":
+            pairs = []
+            if otok.hybrid_should_replan(o, o.last_events, 15):
+                pairs = oplan.urgency_pair_plan(o, hung)
             assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
         elif drv == "att_commit_injected":
             pairs = []
