@@ -335,7 +335,8 @@ def run_gpu_arm(args):
     if rank == 0:
         rb = env.record_bytes
         out_bytes = 8 + 1 + 1 + 4 + 4 + 4
-        b_alg = 2 * rb + out_bytes
+        b_rec = 2 * rb + out_bytes     # what this build actually moves per env-step: record in + out, step outputs
+        b_alg, b_alg_src = survey_b_alg(wl, A, env)
         peak, peak_src = hbm_peak()
         achieved = E * b_alg / (kern_ms / K / 1e3) / 1e9
         stats = sharding.summarize(metric_acc[: len(sharding.METRIC_VECTOR)].cpu())
@@ -358,7 +359,9 @@ def run_gpu_arm(args):
                                          "capture (profiles/r01_step_kernel_ncu_v2.md); the write-back of the records is "
                                          "still in L2 when the kernel ends, so it is below the algorithmic bytes",
                          "algorithmic_bytes_per_launch": E * b_alg,
-                         "kernel": "muav_step_kernel", "bytes_per_env_step": b_alg,
+                         "kernel": "muav_step_kernel", "bytes_per_env_step": b_alg, "bytes_per_env_step_source": b_alg_src,
+                         "record_io_bytes_per_env_step": b_rec,
+                         "record_io_gbs": E * b_rec / (kern_ms / K / 1e3) / 1e9,
                          "kernel_ms_per_launch": kern_ms / K, "peak_source": peak_src,
                          "kernel_share_of_step": kern_ms / step_ms},
             "episode_stats": {k: stats[k] for k in ("episodes", "mean_S_WPS", "sd_S_WPS", "mean_n_on_time",
@@ -369,6 +372,20 @@ def run_gpu_arm(args):
         emit_line(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def survey_b_alg(wl, A, env):
+    """Algorithmic bytes per env-step, SURVEY.md 8(d) (fp64 parity build): the stated figures for the registered
+    configs (WPS_hard 14.4 KB, WPS_commit 21 KB, WPS_escort 25 KB), else the section's own formula
+    B_alg = 2 S_env + O_env with agent 104 B, live task 100 + 8 A B, threat 32 B, known bitmask 4 A ceil(Tcap / 32) B,
+    pending reveals 4 x 48 B, scalars 128 B, RNG tape 44 B per step, O_env = 4 A + 16 B."""
+    stated = {"hard_pair": 14400, "hard_local": 14400, "commit_urgency": 21000, "escort_coalition": 25000}
+    if wl in stated:
+        return stated[wl], "SURVEY.md 8(d), stated figure"
+    H = int(env.cfg.n_threats)
+    t_live = int(env.cfg.max_tasks) + H
+    s_env = 104 * A + (100 + 8 * A) * t_live + 32 * H + 4 * A * ((t_live + 31) // 32) + 4 * 48 + 128
+    return 2 * s_env + 44 + 4 * A + 16, "SURVEY.md 8(d), formula"
 
 
 def run_reference_arm(args):
