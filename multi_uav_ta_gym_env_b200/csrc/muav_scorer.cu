@@ -1,6 +1,8 @@
 // Fused Att-Pair scorer forward (AttPairNet, TaskAllocation/Hybrid/PairCostHybrid.py:89-151, then
-// scores = tanh(logits) * clamp * edge_valid, :266-278) as ONE kernel: one CTA per environment, every
-// activation in shared memory, weights streamed from L2 (the whole network is 330 KB).
+// scores = tanh(logits) * clamp * edge_valid, :266-278) as ONE kernel: each CTA packs up to four environments
+// (their tokens side by side, 64 per pass, attention block-diagonal) so that the 4 x 4 register tiles of the linear
+// layers are full and the 330 KB of weights are streamed from L2 once per pass instead of once per environment;
+// every activation stays in shared memory.
 //
 // Weight matrices are packed TRANSPOSED ([in][out]) by the host (scorers.FusedAttPairScorer).
 // Same function and parameters as the PyTorch module (fp32, FMA allowed like cuBLAS); differences are
@@ -13,6 +15,7 @@
 // arithmetic, not the bit-exact float64 simulation.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/muav.h"
 
@@ -22,7 +25,7 @@ constexpr int D = 64;      // d_model
 constexpr int NH = 4;      // heads
 constexpr int HD = 16;     // head dim
 constexpr int FF = 128;    // dim_feedforward
-constexpr int TS = 48;     // token stride of transposed activations [feature][token] (max 48 tokens, multiple of 4)
+constexpr int TS = 64;     // token stride of transposed activations [feature][token]: tokens of one pass
 constexpr int WS = 68;     // row stride of the staged transposed weight tile [k][o]
 constexpr int NT = 256;    // threads per CTA
 constexpr int TF = 13, AF = 12;
@@ -107,182 +110,299 @@ __device__ void layer_norm_t(float* x_t, int R, const float* __restrict__ g, con
   __syncthreads();
 }
 
-// softmax(q k^T / sqrt(HD)) v for queries [q0, q1) against keys [k0, k1); qkv_t rows: q 0..63, k 64..127, v 128..191
-__device__ void attention_t(const float* __restrict__ qkv_t, int q0, int q1, int k0, int k1, float* __restrict__ out_t) {
+// Segment table of the environments packed into one pass (shared memory)
+struct Seg {
+  int e;     // environment index
+  int base;  // first token: [base, base+na) agents, [base+na, base+na+nt) tasks
+  int na, nt;
+  int poff;  // first pair index
+};
+
+// softmax(q k^T / sqrt(HD)) v, block-diagonal over the packed environments.
+// mode 0: every token attends to its environment's tokens; 1: agent tokens attend to their environment's task tokens;
+// 2: task tokens attend to their environment's agent tokens.  qkv_t rows: q 0..63, k 64..127, v 128..191.
+__device__ void attention_t(const float* __restrict__ qkv_t, int R, const Seg* __restrict__ seg,
+                            const uint8_t* __restrict__ seg_of, int mode, float* __restrict__ out_t) {
   const int h = threadIdx.x >> 6;
-  const int i = q0 + (threadIdx.x & 63);
-  if (i < q1) {
-    float q[HD];
+  const int i = threadIdx.x & 63;
+  if (i < R) {
+    const Seg sg = seg[seg_of[i]];
+    const bool is_agent = i < sg.base + sg.na;
+    int k0 = sg.base, k1 = sg.base + sg.na + sg.nt;
+    bool active = true;
+    if (mode == 1) { active = is_agent; k0 = sg.base + sg.na; }
+    if (mode == 2) { active = !is_agent; k1 = sg.base + sg.na; }
+    if (active) {
+      float q[HD];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) q[d] = qkv_t[(h * HD + d) * TS + i] * 0.25f;
-    float m = -INFINITY;
-    for (int j = k0; j < k1; ++j) {
-      float s = 0.0f;
+      for (int d = 0; d < HD; ++d) q[d] = qkv_t[(h * HD + d) * TS + i] * 0.25f;
+      float m = -INFINITY;
+      for (int j = k0; j < k1; ++j) {
+        float s = 0.0f;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) s = fmaf(q[d], qkv_t[(D + h * HD + d) * TS + j], s);
-      m = fmaxf(m, s);
+        for (int d = 0; d < HD; ++d) s = fmaf(q[d], qkv_t[(D + h * HD + d) * TS + j], s);
+        m = fmaxf(m, s);
+      }
+      float l = 0.0f;
+      float acc[HD];
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc[d] = 0.0f;
+      for (int j = k0; j < k1; ++j) {
+        float s = 0.0f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) s = fmaf(q[d], qkv_t[(D + h * HD + d) * TS + j], s);
+        const float p = __expf(s - m);
+        l += p;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc[d] = fmaf(p, qkv_t[(2 * D + h * HD + d) * TS + j], acc[d]);
+      }
+      const float inv = 1.0f / l;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) out_t[(h * HD + d) * TS + i] = acc[d] * inv;
     }
-    float l = 0.0f;
-    float acc[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] = 0.0f;
-    for (int j = k0; j < k1; ++j) {
-      float s = 0.0f;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) s = fmaf(q[d], qkv_t[(D + h * HD + d) * TS + j], s);
-      const float p = __expf(s - m);
-      l += p;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) acc[d] = fmaf(p, qkv_t[(2 * D + h * HD + d) * TS + j], acc[d]);
-    }
-    const float inv = 1.0f / l;
-#pragma unroll
-    for (int d = 0; d < HD; ++d) out_t[(h * HD + d) * TS + i] = acc[d] * inv;
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(NT, 3) att_pair_kernel(const __grid_constant__ Params P) {
+constexpr int GMAX = 4;   // environments per pass (their tokens must fit TS)
+constexpr int GLIST = 8;  // environments per CTA (launch parameter `group` <= GLIST)
+
+// Which environments does this CTA score?  Launch slots b in [0, n) map to environments e = env_idx ? env_idx[b] : b;
+// a slot counts when need == NULL or need[e] != 0; CTA c takes the counted slots of rank [c*group, (c+1)*group).
+__device__ int pick_envs(const Params& P, int group, int* s_env, int* s_scan) {
+  const int tid = threadIdx.x;
+  const int c = blockIdx.x;
+  if (!P.need) {
+    const int m = min(group, P.n - c * group);
+    if (tid < m) s_env[tid] = P.env_idx ? P.env_idx[c * group + tid] : c * group + tid;
+    __syncthreads();
+    return m > 0 ? m : 0;
+  }
+  const int chunk = (P.n + NT - 1) / NT;
+  const int lo = min(P.n, tid * chunk), hi = min(P.n, lo + chunk);
+  int cnt = 0;
+  for (int b = lo; b < hi; ++b) cnt += P.need[P.env_idx ? P.env_idx[b] : b] != 0;
+  // block exclusive scan of cnt
+  const int lane = tid & 31, wid = tid >> 5;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_scan[wid] = incl;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int w = 0; w < NT / 32; ++w) { const int v = s_scan[w]; s_scan[w] = run; run += v; }
+    s_scan[NT / 32] = run;
+  }
+  __syncthreads();
+  const int excl = s_scan[wid] + incl - cnt;
+  const int total = s_scan[NT / 32];
+  const int r0 = c * group;
+  int m = total - r0;
+  if (m > group) m = group;
+  if (m > 0 && cnt > 0 && excl < r0 + m && excl + cnt > r0) {
+    int r = excl;
+    for (int b = lo; b < hi; ++b) {
+      const int e = P.env_idx ? P.env_idx[b] : b;
+      if (P.need[e] != 0) {
+        if (r >= r0 && r < r0 + m) s_env[r - r0] = e;
+        ++r;
+      }
+    }
+  }
+  __syncthreads();
+  return m > 0 ? m : 0;
+}
+
+__global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__ Params P, int group) {
   extern __shared__ __align__(16) float sm[];
   float* x_t = sm;                       // [D][TS]   tokens / encoder output h
-  float* y_t = x_t + D * TS;             // [D][TS]   attention output / residual sums / a_h', t_h'
-  float* z_t = y_t + D * TS;             // [D][TS]   scratch (cross contexts, ha / ht)
+  float* y_t = x_t + D * TS;             // [D][TS]   attention output / residual sums / ha
+  float* z_t = y_t + D * TS;             // [D][TS]   scratch (cross contexts, [a' | t'])
   float* big_t = z_t + D * TS;           // [3D][TS]  qkv or FF hidden; pair-head weight tiles
-  __shared__ int s_na, s_nt;
+  __shared__ int s_env[GLIST], s_na[GLIST], s_nt[GLIST], s_scan[NT / 32 + 1];
+  __shared__ Seg s_seg[GMAX];
+  __shared__ uint8_t s_seg_of[TS];
+  __shared__ int s_nseg, s_R, s_npairs, s_next;
   const int tid = threadIdx.x;
-  const int b = blockIdx.x;
-  if (b >= P.n) return;
-  const int e = P.env_idx ? P.env_idx[b] : b;
-  if (P.need && !P.need[e]) return;  // this environment does not replan now: its score rows stay as they are
   const int MT = P.max_tasks, MA = P.max_agents;
   const float* w = P.w;
   const muav_attpair_offsets& o = P.o;
-  const uint8_t* am = P.agent_mask + (size_t)e * MA;
-  const uint8_t* tm = P.task_mask + (size_t)e * MT;
-  if (tid == 0) {
+  const int m = pick_envs(P, group, s_env, s_scan);
+  if (m == 0) return;
+  if (tid < m) {
+    const int e = s_env[tid];
+    const uint8_t* am = P.agent_mask + (size_t)e * MA;
+    const uint8_t* tm = P.task_mask + (size_t)e * MT;
     int na = 0, nt = 0;
     while (na < MA && am[na] == 0) ++na;  // valid rows / columns are a prefix by construction of the token builders
     while (nt < MT && tm[nt] == 0) ++nt;
-    s_na = na;
-    s_nt = nt;
+    s_na[tid] = na;
+    s_nt[tid] = nt;
   }
+  if (tid == 0) s_next = 0;
   __syncthreads();
-  const int na = s_na, nt = s_nt;
-  const int R = na + nt;
-  float* sc = P.scores + (size_t)e * MA * MT;
-  for (int idx = tid; idx < MA * MT; idx += NT) sc[idx] = 0.0f;
-  if (na == 0 || nt == 0) return;
+  // scores of every picked environment start at zero (padded rows / columns, invalid edges)
+  for (int g = 0; g < m; ++g) {
+    float* sc = P.scores + (size_t)s_env[g] * MA * MT;
+    for (int idx = tid; idx < MA * MT; idx += NT) sc[idx] = 0.0f;
+  }
 
-  // ---- token embeddings: x = proj(feats) + type_embed  (PairCostHybrid.py:131-133)
-  // Linear layers act on each token independently and the register tiles are 4 tokens wide, so token
-  // columns beyond the valid range may hold anything: they never reach a valid output.
-  for (int idx = tid; idx < AF * na; idx += NT) {
-    const int r = idx / AF, k = idx - r * AF;
-    big_t[k * TS + r] = P.agent_feats[((size_t)e * MA + r) * AF + k];
-  }
-  for (int idx = tid; idx < TF * nt; idx += NT) {
-    const int r = idx / TF, k = idx - r * TF;
-    z_t[k * TS + r] = P.task_feats[((size_t)e * MT + r) * TF + k];
-  }
-  __syncthreads();
-  linear_t(big_t, na, AF, w + o.agent_proj_w, D, w + o.agent_proj_b, D, x_t, nullptr, false);  // agents -> x[:, :na]
-  linear_t(z_t, nt, TF, w + o.task_proj_w, D, w + o.task_proj_b, D, y_t, nullptr, false);       // tasks  -> y[:, :nt]
-  for (int idx = tid; idx < D * R; idx += NT) {
-    const int k = idx / R, r = idx - k * R;
-    if (r < na) x_t[k * TS + r] += w[o.type_embed + k];
-    else x_t[k * TS + r] = y_t[k * TS + (r - na)] + w[o.type_embed + D + k];
-  }
-  __syncthreads();
-
-  // ---- TransformerEncoderLayer (post-norm, relu, eval): x1 = LN1(x + SA(x)); x2 = LN2(x1 + FF(x1))
-  linear_t(x_t, R, D, w + o.enc_in_w, 3 * D, w + o.enc_in_b, 3 * D, big_t, nullptr, false);
-  attention_t(big_t, 0, R, 0, R, y_t);
-  linear_t(y_t, R, D, w + o.enc_out_w, D, w + o.enc_out_b, D, z_t, x_t, false);   // z = x + out_proj(attn)
-  layer_norm_t(z_t, R, w + o.enc_n1_w, w + o.enc_n1_b);                                    // z = x1
-  linear_t(z_t, R, D, w + o.enc_l1_w, FF, w + o.enc_l1_b, FF, big_t, nullptr, true);  // hidden
-  linear_t(big_t, R, FF, w + o.enc_l2_w, D, w + o.enc_l2_b, D, x_t, z_t, false);                 // x = x1 + FF(x1)
-  layer_norm_t(x_t, R, w + o.enc_n2_w, w + o.enc_n2_b);                                    // x = h (encoder output)
-
-  // ---- cross attention (both use the ORIGINAL h): a' = a + MHA_a2t(a, t, t); t' = t + MHA_t2a(t, a, a)
-  linear_t(x_t, R, D, w + o.a2t_in_w, 3 * D, w + o.a2t_in_b, 3 * D, big_t, nullptr, false);
-  attention_t(big_t, 0, na, na, R, y_t);
-  __syncthreads();
-  linear_t(y_t, na, D, w + o.a2t_out_w, D, w + o.a2t_out_b, D, z_t, x_t, false);  // z[:, :na] = a'
-  linear_t(x_t, R, D, w + o.t2a_in_w, 3 * D, w + o.t2a_in_b, 3 * D, big_t, nullptr, false);
-  attention_t(big_t, na, R, 0, na, y_t);
-  // out-projection of the task rows: the register tiles start at token 0, rows < na are recomputed garbage
-  // that is discarded (y_t rows < na still hold the a2t attention output; harmless)
-  linear_t(y_t, R, D, w + o.t2a_out_w, D, w + o.t2a_out_b, D, big_t, x_t, false);  // big[:, na:R] = t'
-  for (int idx = tid; idx < D * nt; idx += NT) {
-    const int k = idx / nt, r = idx - k * nt;
-    z_t[k * TS + na + r] = big_t[k * TS + na + r];
-  }
-  __syncthreads();
-  // z_t now holds [a' | t'] for tokens [0, R)
-
-  // ---- pair head: logits[i, j] = w3 . relu(W2 relu(Wat (a_i * t_j) + Wa a_i + Wt t_j + b1) + b2) + b3
-  // ha[o][i] (agents) and ht[o][j] (tasks, with bias) share one buffer y_t: columns [0,na) / [na,R)
-  linear_t(z_t, R, D, w + o.head1_w, D, nullptr, D, y_t, nullptr, false);             // Wa x for all tokens
-  linear_t(z_t, R, D, w + o.head1_w + D * D, D, w + o.head1_b, D, x_t, nullptr, false);   // Wt x + b1 for all tokens
-  // stage Wat [o][d] (row-major, stride WS) and W2^T [o][p]
-  float* wat = big_t;               // [64][WS]
-  float* w2t = big_t + 64 * WS;     // [64][36]
-  for (int idx = tid; idx < D * D; idx += NT) {
-    const int oo = idx >> 6, d = idx & 63;
-    wat[oo * WS + d] = w[o.head1_w + (size_t)(2 * D + d) * D + oo];
-  }
-  for (int idx = tid; idx < 32 * D; idx += NT) {
-    const int p = idx >> 6, oo = idx & 63;
-    w2t[oo * 36 + p] = w[o.head2_w + (size_t)oo * 32 + p];  // head2^T is [64][32]
-  }
-  __syncthreads();
-  const float* ev = P.edge_valid + (size_t)e * MA * MT;
-  // two lanes per pair: each owns half of the 64 product features (first layer) and half of the 32 hidden
-  // units (second layer); partial sums meet through a shuffle.  Keeps the register count low enough for
-  // three CTAs per SM.
-  const int npairs = na * nt;
-  const int hp = tid & 1;
-  const int d0 = hp * 32, p0 = hp * 16;
-  for (int base = 0; base < npairs; base += NT / 2) {
-    const int pair = base + (tid >> 1);
-    const bool valid = pair < npairs;
-    const int pc = valid ? pair : 0;
-    const int i = pc / nt, j = pc - i * nt;
-    float u[32];
-#pragma unroll
-    for (int d = 0; d < 32; ++d) u[d] = z_t[(d0 + d) * TS + i] * z_t[(d0 + d) * TS + na + j];
-    float h2[16];
-#pragma unroll
-    for (int p = 0; p < 16; ++p) h2[p] = w[o.head2_b + p0 + p];
-    for (int oo = 0; oo < D; ++oo) {
-      float acc = 0.0f;
-      const float4* wr = (const float4*)&wat[oo * WS + d0];
-#pragma unroll
-      for (int d4 = 0; d4 < 8; ++d4) {
-        const float4 ww = wr[d4];
-        acc = fmaf(ww.x, u[4 * d4], acc);
-        acc = fmaf(ww.y, u[4 * d4 + 1], acc);
-        acc = fmaf(ww.z, u[4 * d4 + 2], acc);
-        acc = fmaf(ww.w, u[4 * d4 + 3], acc);
+  for (;;) {
+    // ---- next pass: as many of the remaining environments as fit TS tokens (at most GMAX)
+    if (tid == 0) {
+      int g = s_next, ns = 0, tot = 0, pairs = 0;
+      while (g < m && ns < GMAX) {
+        const int na = s_na[g], nt = s_nt[g];
+        if (na == 0 || nt == 0) { ++g; continue; }
+        if (tot + na + nt > TS) break;
+        s_seg[ns].e = s_env[g];
+        s_seg[ns].base = tot;
+        s_seg[ns].na = na;
+        s_seg[ns].nt = nt;
+        s_seg[ns].poff = pairs;
+        for (int r = 0; r < na + nt; ++r) s_seg_of[tot + r] = (uint8_t)ns;
+        tot += na + nt;
+        pairs += na * nt;
+        ++ns;
+        ++g;
       }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc = fmaxf(acc + y_t[oo * TS + i] + x_t[oo * TS + na + j], 0.0f);
-      const float4* w2 = (const float4*)&w2t[oo * 36 + p0];
-#pragma unroll
-      for (int p4 = 0; p4 < 4; ++p4) {
-        const float4 ww = w2[p4];
-        h2[4 * p4] = fmaf(ww.x, acc, h2[4 * p4]);
-        h2[4 * p4 + 1] = fmaf(ww.y, acc, h2[4 * p4 + 1]);
-        h2[4 * p4 + 2] = fmaf(ww.z, acc, h2[4 * p4 + 2]);
-        h2[4 * p4 + 3] = fmaf(ww.w, acc, h2[4 * p4 + 3]);
+      s_next = g;
+      s_nseg = ns;
+      s_R = tot;
+      s_npairs = pairs;
+    }
+    __syncthreads();
+    const int nseg = s_nseg;
+    if (nseg == 0) break;
+    const int R = s_R;
+
+    // ---- token embeddings: x = proj(feats) + type_embed  (PairCostHybrid.py:131-133).  Agent and task tokens of the
+    // packed environments interleave, so both projections run over all tokens (K is 12 / 13) and each token keeps
+    // the one of its type.  Linear layers act on each token independently and the register tiles are 4 tokens wide:
+    // whatever a token column of the wrong type or beyond R holds never reaches a valid output.
+    for (int idx = tid; idx < (AF + TF) * R; idx += NT) {
+      const int r = idx % R, k = idx / R;
+      const Seg sg = s_seg[s_seg_of[r]];
+      const int l = r - sg.base;
+      if (k < AF) {
+        big_t[k * TS + r] = l < sg.na ? P.agent_feats[((size_t)sg.e * MA + l) * AF + k] : 0.0f;
+      } else {
+        const int kk = k - AF;
+        z_t[kk * TS + r] = l >= sg.na ? P.task_feats[((size_t)sg.e * MT + (l - sg.na)) * TF + kk] : 0.0f;
       }
     }
-    float logit = 0.0f;
+    __syncthreads();
+    linear_t(big_t, R, AF, w + o.agent_proj_w, D, w + o.agent_proj_b, D, x_t, nullptr, false);
+    linear_t(z_t, R, TF, w + o.task_proj_w, D, w + o.task_proj_b, D, y_t, nullptr, false);
+    for (int idx = tid; idx < D * R; idx += NT) {
+      const int k = idx / R, r = idx - k * R;
+      const Seg sg = s_seg[s_seg_of[r]];
+      if (r < sg.base + sg.na) x_t[k * TS + r] += w[o.type_embed + k];
+      else x_t[k * TS + r] = y_t[k * TS + r] + w[o.type_embed + D + k];
+    }
+    __syncthreads();
+
+    // ---- TransformerEncoderLayer (post-norm, relu, eval): x1 = LN1(x + SA(x)); x2 = LN2(x1 + FF(x1))
+    linear_t(x_t, R, D, w + o.enc_in_w, 3 * D, w + o.enc_in_b, 3 * D, big_t, nullptr, false);
+    attention_t(big_t, R, s_seg, s_seg_of, 0, y_t);
+    linear_t(y_t, R, D, w + o.enc_out_w, D, w + o.enc_out_b, D, z_t, x_t, false);   // z = x + out_proj(attn)
+    layer_norm_t(z_t, R, w + o.enc_n1_w, w + o.enc_n1_b);                                    // z = x1
+    linear_t(z_t, R, D, w + o.enc_l1_w, FF, w + o.enc_l1_b, FF, big_t, nullptr, true);  // hidden
+    linear_t(big_t, R, FF, w + o.enc_l2_w, D, w + o.enc_l2_b, D, x_t, z_t, false);                 // x = x1 + FF(x1)
+    layer_norm_t(x_t, R, w + o.enc_n2_w, w + o.enc_n2_b);                                    // x = h (encoder output)
+
+    // ---- cross attention (both use the ORIGINAL h): a' = a + MHA_a2t(a, t, t); t' = t + MHA_t2a(t, a, a).
+    // Out-projections run over all tokens; each token keeps the one of its type.
+    linear_t(x_t, R, D, w + o.a2t_in_w, 3 * D, w + o.a2t_in_b, 3 * D, big_t, nullptr, false);
+    attention_t(big_t, R, s_seg, s_seg_of, 1, y_t);
+    linear_t(y_t, R, D, w + o.a2t_out_w, D, w + o.a2t_out_b, D, z_t, x_t, false);   // z[:, agents] = a'
+    linear_t(x_t, R, D, w + o.t2a_in_w, 3 * D, w + o.t2a_in_b, 3 * D, big_t, nullptr, false);
+    attention_t(big_t, R, s_seg, s_seg_of, 2, y_t);
+    linear_t(y_t, R, D, w + o.t2a_out_w, D, w + o.t2a_out_b, D, big_t, x_t, false);  // big[:, tasks] = t'
+    for (int idx = tid; idx < D * R; idx += NT) {
+      const int k = idx / R, r = idx - k * R;
+      const Seg sg = s_seg[s_seg_of[r]];
+      if (r >= sg.base + sg.na) z_t[k * TS + r] = big_t[k * TS + r];
+    }
+    __syncthreads();
+    // z_t now holds a' (agent tokens) / t' (task tokens)
+
+    // ---- pair head: logits[i, j] = w3 . relu(W2 relu(Wat (a_i * t_j) + Wa a_i + Wt t_j + b1) + b2) + b3
+    linear_t(z_t, R, D, w + o.head1_w, D, nullptr, D, y_t, nullptr, false);                 // Wa x for all tokens
+    linear_t(z_t, R, D, w + o.head1_w + D * D, D, w + o.head1_b, D, x_t, nullptr, false);   // Wt x + b1 for all tokens
+    // stage Wat [o][d] (row-major, stride WS) and W2^T [o][p]
+    float* wat = big_t;               // [64][WS]
+    float* w2t = big_t + 64 * WS;     // [64][36]
+    for (int idx = tid; idx < D * D; idx += NT) {
+      const int oo = idx >> 6, d = idx & 63;
+      wat[oo * WS + d] = w[o.head1_w + (size_t)(2 * D + d) * D + oo];
+    }
+    for (int idx = tid; idx < 32 * D; idx += NT) {
+      const int p = idx >> 6, oo = idx & 63;
+      w2t[oo * 36 + p] = w[o.head2_w + (size_t)oo * 32 + p];  // head2^T is [64][32]
+    }
+    __syncthreads();
+    // two lanes per pair: each owns half of the 64 product features (first layer) and half of the 32 hidden
+    // units (second layer); partial sums meet through a shuffle.
+    const int npairs = s_npairs;
+    const int hp = tid & 1;
+    const int d0 = hp * 32, p0 = hp * 16;
+    for (int pbase = 0; pbase < npairs; pbase += NT / 2) {
+      const int pair = pbase + (tid >> 1);
+      const bool valid = pair < npairs;
+      const int pc = valid ? pair : 0;
+      int g = 0;
 #pragma unroll
-    for (int p = 0; p < 16; ++p) logit = fmaf(w[o.head3_w + p0 + p], fmaxf(h2[p], 0.0f), logit);
-    logit += __shfl_xor_sync(0xffffffffu, logit, 1);
-    logit += w[o.head3_b];
-    if (valid && hp == 0) sc[i * MT + j] = tanhf(logit) * P.clamp * ev[i * MT + j];
+      for (int q = 1; q < GMAX; ++q)
+        if (q < nseg && pc >= s_seg[q].poff) g = q;
+      const Seg sg = s_seg[g];
+      const int loc = pc - sg.poff;
+      const int i = loc / sg.nt, j = loc - i * sg.nt;
+      const int ta = sg.base + i, tt = sg.base + sg.na + j;
+      float u[32];
+#pragma unroll
+      for (int d = 0; d < 32; ++d) u[d] = z_t[(d0 + d) * TS + ta] * z_t[(d0 + d) * TS + tt];
+      float h2[16];
+#pragma unroll
+      for (int p = 0; p < 16; ++p) h2[p] = w[o.head2_b + p0 + p];
+      for (int oo = 0; oo < D; ++oo) {
+        float acc = 0.0f;
+        const float4* wr = (const float4*)&wat[oo * WS + d0];
+#pragma unroll
+        for (int d4 = 0; d4 < 8; ++d4) {
+          const float4 ww = wr[d4];
+          acc = fmaf(ww.x, u[4 * d4], acc);
+          acc = fmaf(ww.y, u[4 * d4 + 1], acc);
+          acc = fmaf(ww.z, u[4 * d4 + 2], acc);
+          acc = fmaf(ww.w, u[4 * d4 + 3], acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc = fmaxf(acc + y_t[oo * TS + ta] + x_t[oo * TS + tt], 0.0f);
+        const float4* w2 = (const float4*)&w2t[oo * 36 + p0];
+#pragma unroll
+        for (int p4 = 0; p4 < 4; ++p4) {
+          const float4 ww = w2[p4];
+          h2[4 * p4] = fmaf(ww.x, acc, h2[4 * p4]);
+          h2[4 * p4 + 1] = fmaf(ww.y, acc, h2[4 * p4 + 1]);
+          h2[4 * p4 + 2] = fmaf(ww.z, acc, h2[4 * p4 + 2]);
+          h2[4 * p4 + 3] = fmaf(ww.w, acc, h2[4 * p4 + 3]);
+        }
+      }
+      float logit = 0.0f;
+#pragma unroll
+      for (int p = 0; p < 16; ++p) logit = fmaf(w[o.head3_w + p0 + p], fmaxf(h2[p], 0.0f), logit);
+      logit += __shfl_xor_sync(0xffffffffu, logit, 1);
+      logit += w[o.head3_b];
+      if (valid && hp == 0) {
+        const size_t off = (size_t)sg.e * MA * MT + (size_t)i * MT + j;
+        P.scores[off] = tanhf(logit) * P.clamp * P.edge_valid[off];
+      }
+    }
+    __syncthreads();  // the next pass reuses every buffer
   }
 }
 
@@ -319,7 +439,13 @@ extern "C" int muav_att_pair_scores(const float* d_params, const muav_attpair_of
     if (e != cudaSuccess) return -1000 - (int)e;
     set = true;
   }
-  att_pair_kernel<<<n, NT, smem, (cudaStream_t)stream>>>(P);
+  // environments per CTA: three WPS_hard environments (~19 tokens each) fill the 64-token pass
+  int group = 3;
+  const char* ge = getenv("MUAV_SCORER_GROUP");
+  if (ge) group = atoi(ge);
+  if (group < 1) group = 1;
+  if (group > GLIST) group = GLIST;
+  att_pair_kernel<<<(n + group - 1) / group, NT, smem, (cudaStream_t)stream>>>(P, group);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -1000 - (int)e;
 }

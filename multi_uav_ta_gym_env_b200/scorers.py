@@ -325,8 +325,8 @@ class GraphedPairScorer:
 
 
 class FusedAttPairScorer:
-    """AttPairNet forward as one CUDA kernel (csrc/muav_scorer.cu, C ABI muav_att_pair_scores): one CTA per
-    environment, only live agents / valid task columns are tokens, scores are written straight into the
+    """AttPairNet forward as one CUDA kernel (csrc/muav_scorer.cu, C ABI muav_att_pair_scores): three environments
+    per CTA packed token by token, only live agents / valid task columns are tokens, scores are written straight into the
     [E, max_agents, max_tasks] tensor the allocator reads (no gather / scatter, no intermediates in HBM).
     Parameters are the module's own (packed once); arithmetic is fp32 like the module."""
 
