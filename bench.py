@@ -318,10 +318,7 @@ def run_gpu_arm(args):
         env.allocate(spec, edge_scores=scores, actions_out=d_act)
         h_act.copy_(d_act, non_blocking=True)
         torch.cuda.current_stream().synchronize()          # the caller now holds the allocator's decision
-        rc = env.lib.dll.muav_step_host(C.byref(env.cfg), env.records.data_ptr(), env.tapes.data_ptr(), h_act.data_ptr(),
-                                        None, env._tok_ref(), h_rew.data_ptr(), h_term.data_ptr(), h_trunc.data_ptr(), E, 1,
-                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
-        assert rc == 0
+        env.step_host(h_act, h_rew, h_term, h_trunc, 1, hint=spec)
         if t + 1 == EPISODE:
             episode_end()
     e1.record()

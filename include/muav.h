@@ -95,7 +95,9 @@ typedef struct muav_alloc_opts {
                                 agent locked for commit_horizon;
                               5 UrgencyPair.plan (PairCostHybrid.py:520-550): urgency_edge_scores (:68-86) on the valid
                                 edges of build_pair_tokens(score_cols = max_tasks, score_rows = max_agents), no locks */
-  int32_t reserved1;
+  int32_t order_hint_mode; /* mode == 0 only (actions come from the caller): the replan rule (1 / 2 / 3, with replan_interval,
+                              event_mask and planner as above) that the caller's allocator follows, used solely to fill
+                              muav_step_out.d_env_order_next; 0 = no hint */
   double commit_fraction;  /* UrgencyCommit(commit_fraction=0.35) */
   double max_coord;        /* HungarianAllocator(max_coord=...) */
   const void* d_edge_scores;   /* [E, score_rows, score_cols] float (or double when score_f64) or NULL;
@@ -119,6 +121,14 @@ typedef struct muav_step_out {
   int32_t* d_n_pairs;    /* [E] allocator output this step */
   int32_t* d_pairs;      /* [E, n_agents] (agent_id<<16) | task_id, in reference order */
   int32_t* d_n_open;     /* [E] len(env.last_tasks_info) after the step */
+  /* Scheduling hint, no effect on results.  The warps of a CTA walk the step phase by phase together, so a CTA is as
+   * slow as its slowest environment; environments that will run the allocator at the next step are therefore grouped
+   * into the same CTAs.  d_env_order (NULL = identity): permutation of [0, E) giving the environment of each launch
+   * slot.  d_env_order_next (NULL = none): int32 [E + 2], receives the permutation for the NEXT launch (replanning
+   * environments first); its two trailing counters must be zero on entry -- the kernel zeroes those of d_env_order,
+   * so two zero-initialised buffers used alternately need no further care. */
+  const int32_t* d_env_order;
+  int32_t* d_env_order_next;
 } muav_step_out;
 
 /* Optional pair-token emission fused at the end of each step (saves the separate muav_tokens_pair pass):
@@ -158,7 +168,8 @@ int muav_allocate(const muav_config* cfg, void* d_records, const muav_alloc_opts
 /* Same call with HOST action / output buffers: copies in, runs, copies out, synchronises. */
 int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* h_actions,
                    const muav_alloc_opts* opts, const muav_token_out* tok, double* h_reward, uint8_t* h_terminated,
-                   uint8_t* h_truncated, int n_envs, int n_steps, void* stream);
+                   uint8_t* h_truncated, int n_envs, int n_steps, void* stream, const int32_t* d_env_order,
+                   int32_t* d_env_order_next);
 
 /* K fused (plan -> allocate -> step) iterations with the state resident on chip: muav_step with a fused allocator and
  * no external actions (the episode loops of experiments/wps_eval.py:96-140 and escort_eval.py:85-200 without the

@@ -51,7 +51,7 @@ class MuavAllocOpts(C.Structure):
         ("mode", C.c_int32), ("replan_interval", C.c_int32), ("event_mask", C.c_int32),
         ("use_visibility", C.c_int32), ("pair_tokens", C.c_int32), ("score_rows", C.c_int32),
         ("score_cols", C.c_int32), ("score_f64", C.c_int32),
-        ("planner", C.c_int32), ("reserved1", C.c_int32),
+        ("planner", C.c_int32), ("order_hint_mode", C.c_int32),
         ("commit_fraction", C.c_double),
         ("max_coord", C.c_double),
         ("d_edge_scores", C.c_void_p), ("d_priorities", C.c_void_p), ("d_reserved", C.c_void_p),
@@ -65,6 +65,7 @@ class MuavStepOut(C.Structure):
         ("d_reward", C.c_void_p), ("d_terminated", C.c_void_p), ("d_truncated", C.c_void_p),
         ("d_n_events", C.c_void_p), ("d_events", C.c_void_p), ("d_n_pairs", C.c_void_p),
         ("d_pairs", C.c_void_p), ("d_n_open", C.c_void_p),
+        ("d_env_order", C.c_void_p), ("d_env_order_next", C.c_void_p),
     ]
 
 
@@ -177,7 +178,7 @@ class CudaLib(Lib):
                                     C.c_int, P]
         d.muav_step_host.restype = C.c_int
         d.muav_step_host.argtypes = [C.POINTER(MuavConfig), P, P, P, C.POINTER(MuavAllocOpts), C.POINTER(MuavTokenOut),
-                                     P, P, P, C.c_int, C.c_int, P]
+                                     P, P, P, C.c_int, C.c_int, P, P, P]
         d.muav_lsap.restype = C.c_int
         d.muav_lsap.argtypes = [P, P, P, C.c_int, C.c_int, P, C.c_int, P]
         d.muav_avoid_obstacles.restype = C.c_int

@@ -9,6 +9,7 @@ Reference semantics: MultiUAVEnv.reset/step (mUAV_TA/DroneEnv.py:522-762, 774-12
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -117,6 +118,10 @@ class BatchedMultiUAVEnv:
         self._out.d_n_pairs = self.n_pairs.data_ptr()
         self._out.d_pairs = self.pairs.data_ptr()
         self._out.d_n_open = self.n_open.data_ptr()
+        # launch-slot order (scheduling hint of muav_step_out): two buffers used alternately, see include/muav.h
+        self.group_replanners = os.environ.get("MUAV_ENV_ORDER", "1") != "0"
+        self._order = torch.zeros(2, E + 2, dtype=torch.int32, device=dev)
+        self._order_cur = -1  # index of the buffer holding the order for the next launch (-1: identity)
         self.scenarios = None
         self.agent_names = None
         self.launches = 0
@@ -192,6 +197,18 @@ class BatchedMultiUAVEnv:
         return C.byref(self._tok) if getattr(self, "_tok", None) is not None else None
 
     # ------------------------------------------------------------------ step
+    def _order_args(self):
+        """Point muav_step_out at the current / next launch-slot order and flip the buffers."""
+        if not self.group_replanners:
+            self._out.d_env_order = None
+            self._out.d_env_order_next = None
+            return
+        cur = self._order_cur
+        nxt = 0 if cur != 0 else 1
+        self._out.d_env_order = None if cur < 0 else self._order[cur].data_ptr()
+        self._out.d_env_order_next = self._order[nxt].data_ptr()
+        self._order_cur = nxt
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -208,12 +225,32 @@ class BatchedMultiUAVEnv:
             i_sorted = torch.gather(actions.to(torch.int32), 1, order)
             actions = torch.stack([a_sorted, i_sorted], dim=2)
         actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+        self._order_args()
         rc = self.lib.dll.muav_step(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(),
                                     actions.data_ptr(), None, C.byref(self._out), self._tok_ref(), self.n_envs, n_steps,
                                     self._stream())
         _lib.check(rc, "muav_step")
         self.launches += 1
         return self.reward, self.terminated, self.truncated
+
+    def step_host(self, h_actions, h_reward, h_terminated, h_truncated, n_steps: int = 1, hint: Optional[AllocSpec] = None):
+        """muav_step_host: ordered actions int32 [E, A, 2] in HOST memory in, reward f64 [E] / terminated u8 [E] /
+        truncated u8 [E] in HOST memory out (copies and the final synchronisation happen inside the call).
+        `hint`: the AllocSpec whose replan rule the caller's allocator follows (launch-slot grouping only)."""
+        ptr = lambda x: x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
+        O = None
+        if hint is not None:
+            O = _lib.MuavAllocOpts()
+            O.mode = 0
+            O.order_hint_mode = hint.mode
+            O.replan_interval, O.event_mask, O.planner = hint.replan_interval, hint.event_mask, hint.planner
+        self._order_args()
+        rc = self.lib.dll.muav_step_host(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(), ptr(h_actions),
+                                         None if O is None else C.byref(O), self._tok_ref(), ptr(h_reward),
+                                         ptr(h_terminated), ptr(h_truncated), self.n_envs, n_steps, self._stream(),
+                                         self._out.d_env_order, self._out.d_env_order_next)
+        _lib.check(rc, "muav_step_host")
+        self.launches += 1
 
     def _alloc_opts(self, spec, edge_scores, priorities, reserved, task_order=None, plan_pri=None, plan_commit=None):
         O = _lib.MuavAllocOpts()
@@ -264,6 +301,7 @@ class BatchedMultiUAVEnv:
                        plan_commit: Optional[torch.Tensor] = None):
         """n_steps fused (allocate -> step) iterations per environment, state resident in shared memory."""
         O, keep = self._alloc_opts(spec, edge_scores, priorities, reserved, task_order, plan_pri, plan_commit)
+        self._order_args()
         rc = self.lib.dll.muav_rollout(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(), C.byref(O),
                                        C.byref(self._out), self._tok_ref(), self.n_envs, n_steps, self._stream())
         _lib.check(rc, "muav_rollout")
@@ -278,6 +316,10 @@ class BatchedMultiUAVEnv:
         O, keep = self._alloc_opts(spec, edge_scores, priorities, reserved)
         if actions_out is None:
             actions_out = torch.empty(self.n_envs, self.n_agents, 2, dtype=torch.int32, device=self.device)
+        # read-only use of the current launch-slot order (the allocator kernel profits from the grouping too)
+        cur = self._order_cur
+        self._out.d_env_order = self._order[cur].data_ptr() if (self.group_replanners and cur >= 0) else None
+        self._out.d_env_order_next = None
         rc = self.lib.dll.muav_allocate(C.byref(self.cfg), self.records.data_ptr(), C.byref(O), C.byref(self._out),
                                         actions_out.data_ptr(), self.n_envs, self._stream())
         _lib.check(rc, "muav_allocate")

@@ -73,7 +73,7 @@ struct StepParams {
 
 // One warp per environment; a CTA holds `cta_warps` environments whose warps are phase-aligned with
 // CTA barriers (no data is shared between them).
-__global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS) muav_step_kernel(const __grid_constant__ StepParams P) {
+__global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(const __grid_constant__ StepParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar[MUAV_MAX_CTA_WARPS];
   __shared__ int16_t act_agent_s[MUAV_MAX_CTA_WARPS][MUAV_MAX_AGENTS];
@@ -82,8 +82,18 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS) muav_step_kernel(cons
   const int W = P.cta_warps;
   const int w = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int e = blockIdx.x * W + w;
-  const bool has_env = e < P.n_envs;
+  const int slot = blockIdx.x * W + w;
+  bool has_env = slot < P.n_envs;
+  int e = slot;
+  if (has_env && P.out.d_env_order) {
+    e = P.out.d_env_order[slot];
+    if (e < 0 || e >= P.n_envs) { has_env = false; e = 0; }
+  }
+  if (P.out.d_env_order && blockIdx.x == 0 && threadIdx.x == 0) {
+    // counters of the buffer that the next launch will fill
+    ((int32_t*)P.out.d_env_order)[P.n_envs] = 0;
+    ((int32_t*)P.out.d_env_order)[P.n_envs + 1] = 0;
+  }
   const int sync_mask = W > 1 ? P.sync_mask : 0;
   const Layout& L = P.L;
   const int slot_bytes = L.record_bytes + L.scratch_bytes;
@@ -235,6 +245,23 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS) muav_step_kernel(cons
     }
   }
 
+  // ---- launch slot of this environment in the next launch: replanning environments first
+  if (P.out.d_env_order_next && has_env && lane == 0 && !P.alloc_only) {
+    const muav_alloc_opts& O = P.opts;
+    bool will = false;
+    const int rule = O.mode != 0 ? O.mode : O.order_hint_mode;
+    if (!HIv(DONE) && rule != 0) {
+      const int t = HIv(T);
+      const int iv = O.replan_interval > 0 ? O.replan_interval : 1;
+      const bool ev_hit = (HIv(EV_TAGMASK) & O.event_mask) != 0;
+      if (rule == 1 && O.planner == 0) will = (t - HIv(LAST_PLAN_STEP)) >= iv || ev_hit;
+      else if (rule == 3) will = true;
+      else will = t == 0 || (t % iv) == 0 || ev_hit;
+    }
+    int32_t* nx = P.out.d_env_order_next;
+    const int pos = atomicAdd(&nx[P.n_envs + (will ? 0 : 1)], 1);
+    if (pos >= 0 && pos < P.n_envs) nx[will ? pos : P.n_envs - 1 - pos] = e;
+  }
 #if defined(MUAV_PHASE_TIMING)
   __syncthreads();
   if (lane == 0 && w == 0 && P.phase_out) {
@@ -496,7 +523,8 @@ int muav_snapshot(const muav_config* cfg, const void* d_records, int env_index, 
 
 int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* h_actions,
                    const muav_alloc_opts* opts, const muav_token_out* tok, double* h_reward, uint8_t* h_terminated,
-                   uint8_t* h_truncated, int n_envs, int n_steps, void* stream) {
+                   uint8_t* h_truncated, int n_envs, int n_steps, void* stream, const int32_t* d_env_order,
+                   int32_t* d_env_order_next) {
   int rc = check_cfg(cfg);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
@@ -523,6 +551,8 @@ int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_ta
   out.d_reward = (double*)(b + off_rew);
   out.d_terminated = (uint8_t*)(b + off_term);
   out.d_truncated = (uint8_t*)(b + off_trunc);
+  out.d_env_order = d_env_order;
+  out.d_env_order_next = d_env_order_next;
   rc = muav_step(cfg, d_records, d_tapes, h_actions ? (const int32_t*)b : nullptr, opts, &out, tok, n_envs, n_steps,
                  stream);
   if (rc) return rc;

@@ -262,9 +262,14 @@ def test_step_host_entry_point_matches_device_path():
         for e, ep in enumerate(eps):
             for i, (a, idx) in enumerate(ep["steps"][t]["actions"]):
                 act[e, i] = (a, idx)
-        rc = env.lib.dll.muav_step_host(C.byref(env.cfg), env.records.data_ptr(), env.tapes.data_ptr(), act.ctypes.data,
-                                        None, None, rew.ctypes.data, term.ctypes.data, trunc.ctypes.data, E, 1, None)
-        assert rc == 0
+        if t % 2 == 0:   # raw C ABI call, no launch-slot order
+            rc = env.lib.dll.muav_step_host(C.byref(env.cfg), env.records.data_ptr(), env.tapes.data_ptr(), act.ctypes.data,
+                                            None, None, rew.ctypes.data, term.ctypes.data, trunc.ctypes.data, E, 1, None,
+                                            None, None)
+            assert rc == 0
+        else:            # host wrapper: same call with the launch-slot order hint of a Local-Hungarian caller
+            from multi_uav_ta_gym_env_b200 import AllocSpec
+            env.step_host(act, rew, term, trunc, 1, hint=AllocSpec.local_hungarian(20))
         for e, ep in enumerate(eps):
             assert rew[e] == float.fromhex(ep["steps"][t]["reward"])
     recs = env.records.cpu().numpy()
