@@ -29,9 +29,9 @@ enum { EV_RESET = 0, EV_FAIL = 1, EV_THREAT = 2, EV_ESC_CREATED = 3, EV_ESC_RETI
 
 // Out of line on purpose: float64 sqrt / divide expand to ~25 SASS instructions each; the kernel is
 // instruction-fetch bound (profiles/r01_step_kernel_ncu.md), so all call sites share one copy.
-MUAV_HD MUAV_NOINLINE inline double norm2(double x, double y) { return sqrt(fma(y, y, x * x)); }
-MUAV_HD MUAV_NOINLINE inline double norm2_rows(double x, double y) { return sqrt(x * x + y * y); }
-MUAV_HD MUAV_NOINLINE inline double ddiv(double a, double b) { return a / b; }
+MUAV_HD MUAV_NOINLINE_LEAF inline double norm2(double x, double y) { return sqrt(fma(y, y, x * x)); }
+MUAV_HD MUAV_NOINLINE_LEAF inline double norm2_rows(double x, double y) { return sqrt(x * x + y * y); }
+MUAV_HD MUAV_NOINLINE_LEAF inline double ddiv(double a, double b) { return a / b; }
 MUAV_HD inline double dmax(double a, double b) { return a > b ? a : b; }
 MUAV_HD inline double dmin(double a, double b) { return a < b ? a : b; }
 MUAV_HD inline bool is_fighter(int ut) { return ut == UT_F1 || ut == UT_F2; }
@@ -905,7 +905,7 @@ struct Sim {
   }
 
   // core_sim::SimCore::avoid_obstacles (core_sim/src/sim_core.rs:24-59)
-  MUAV_HD MUAV_NOINLINE static void avoid_obstacles(const double* obst, int nobs, double px, double py, double mx, double my,
+  MUAV_HD MUAV_NOINLINE_LEAF static void avoid_obstacles(const double* obst, int nobs, double px, double py, double mx, double my,
                                                     double* ax, double* ay) {
     const double PI = 3.14159265358979323846;
     double sx = 0.0, sy = 0.0;

@@ -9,10 +9,23 @@
 
 #if defined(__CUDACC__)
 #define MUAV_HD __host__ __device__
+// MUAV_NOINLINE_LEAF: pure math helpers kept out of line (code size).  MUAV_NOINLINE: rarely executed member functions;
+// inlined on the device by default because an out-of-line member takes `this`, which forces the whole Sim object
+// (and with it the record base pointer) into local memory and turns every record access into a generic load.
+#if defined(MUAV_ALL_INLINE)
+#define MUAV_NOINLINE_LEAF
+#else
+#define MUAV_NOINLINE_LEAF __noinline__
+#endif
+#if defined(MUAV_MEMBERS_OUT_OF_LINE)
 #define MUAV_NOINLINE __noinline__
+#else
+#define MUAV_NOINLINE
+#endif
 #else
 #define MUAV_HD
 #define MUAV_NOINLINE __attribute__((noinline))
+#define MUAV_NOINLINE_LEAF __attribute__((noinline))
 #endif
 // tuning switches (see tools/kbench.py): out-of-line copies of the frequently used helpers / the allocator
 #if defined(MUAV_NI_HOT)
