@@ -240,7 +240,11 @@ def run_gpu_arm(args):
         scorer.score(tok, scores, use_need=True)
         launches["n"] += 1
 
+    err_acc = torch.zeros(1, dtype=torch.int32, device=dev)
+
     def episode_end():
+        # capacity / tape overflow bits are sticky per episode: collect them before the records are rewound
+        err_acc.copy_(torch.maximum(err_acc, env.error_flags().abs().max().to(torch.int32).reshape(1)))
         m = env.metrics()
         launches["n"] += 1
         vec = sharding.metric_vector(m, names)
@@ -289,7 +293,7 @@ def run_gpu_arm(args):
             episode_end()
     barrier()
     clocks = sampler.stop(first_sample)
-    err_flags = int(env.error_flags().abs().max().item())  # capacity / tape overflow bits: must stay 0
+    err_flags = max(int(env.error_flags().abs().max().item()), int(err_acc.item()))  # overflow bits: must stay 0
     step_ms = sum(a.elapsed_time(c) for a, b, c in ev)
     kern_ms = sum(b.elapsed_time(c) for a, b, c in ev)
     gpu_launches = launches["n"]
@@ -327,6 +331,7 @@ def run_gpu_arm(args):
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = world * E * Ke / (e2e_ms.item() / 1e3)
+    err_flags = max(err_flags, int(err_acc.item()), int(env.error_flags().abs().max().item()))
     act_bytes = E * A * 2 * 4
 
     if rank == 0:

@@ -219,7 +219,7 @@ def check(rc: int, what: str):
         raise RuntimeError(f"{what} failed with code {rc}" + (f" (cudaError {-1000 - rc})" if rc <= -1000 else ""))
 
 
-def build_config(opts, task_cap=None, queue_cap=8, event_cap=None, id_cap=None) -> MuavConfig:
+def build_config(opts, task_cap=None, queue_cap=16, event_cap=None, id_cap=None) -> MuavConfig:
     """agentEnvOptions -> muav_config.  Derived constants follow MultiUAVEnv.__init__
     (mUAV_TA/DroneEnv.py:73-323) and the entity constructors."""
     g = lambda n, d=None: getattr(opts, n, d)

@@ -83,7 +83,7 @@ class AllocSpec:
 
 
 class BatchedMultiUAVEnv:
-    def __init__(self, config, n_envs: int, device="cuda:0", task_cap=None, queue_cap=8, id_cap=None):
+    def __init__(self, config, n_envs: int, device="cuda:0", task_cap=None, queue_cap=16, id_cap=None):
         self.lib = _lib.cuda_lib()  # raises if the CUDA library is not built: no CPU fallback
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedMultiUAVEnv needs a CUDA device (B200); there is no CPU path")

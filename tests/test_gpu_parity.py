@@ -683,3 +683,41 @@ def test_learned_commit_pipeline_matches_oracle():
         for e, o in enumerate(oracles):
             assert refsnap.digest(env.codec.snapshot(recs[e])) == refsnap.digest(o.snapshot()), (t, e)
     assert locks > 0
+
+
+def test_full_batch_scored_episode_has_no_capacity_overflow():
+    """BASELINE config 2 as bench.py runs it (4096 environments, fused tokens -> fused Att-Pair scorer -> hybrid
+    Local-Hungarian, launch-slot grouping on): a whole episode must not set any capacity / tape error bit (an agent
+    queue deeper than 8 entries occurs at this batch size), and sampled environments must match the oracle driven
+    with the device's own scores."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+    from multi_uav_ta_gym_env_b200.scorers import AttPairNet, FusedAttPairScorer
+    from oracle.hungarian import OracleHungarian, apply_assign
+    from oracle import tokens as otok
+    from oracle.sim import OracleEnv
+
+    cfg = wps_config("WPS_hard")
+    E = 4096
+    env = make_env(cfg, list(range(E)))
+    torch.manual_seed(0)
+    net = AttPairNet().cuda().eval()
+    scorer = FusedAttPairScorer(net, torch.device("cuda"))
+    scores = torch.zeros(E, 16, 32, dtype=torch.float32, device="cuda")
+    tok = env.enable_fused_tokens(32, 16, 15, 0b111)
+    env.refresh_fused_tokens()
+    sample = [5, 1777, 3030, 4095]
+    oracles = [OracleEnv(cfg).reset(s) for s in sample]
+    hungs = [OracleHungarian(20, 1200.0) for _ in sample]
+    spec = AllocSpec.pair_hybrid(15)
+    for t in range(150):
+        scorer.score(tok, scores, use_need=True)
+        sc = scores[sample].cpu().numpy()
+        env.step_allocated(spec, 1, edge_scores=scores)
+        for i, o in enumerate(oracles):
+            pairs = otok.pair_plan(o, hungs[i], sc[i]) if otok.hybrid_should_replan(o, o.last_events, 15) else []
+            o.step(apply_assign(o, pairs))
+        if t % 25 == 24 or t == 149:
+            for i, e in enumerate(sample):
+                assert refsnap.digest(env.snapshot(e)) == refsnap.digest(oracles[i].snapshot()), (t, e)
+    flags = env.error_flags()
+    assert int(flags.abs().max().item()) == 0, (flags != 0).nonzero().flatten()[:8].tolist()
