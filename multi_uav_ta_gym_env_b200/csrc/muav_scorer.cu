@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
   __shared__ int s_env[GLIST], s_na[GLIST], s_nt[GLIST], s_scan[NT / 32 + 1];
   __shared__ Seg s_seg[GMAX];
   __shared__ uint8_t s_seg_of[TS];
-  __shared__ int s_nseg, s_R, s_npairs, s_next;
+  __shared__ int s_nseg, s_R, s_npairs, s_next, s_nvalid;
+  __shared__ uint16_t s_plist[1024];  // pairs of this pass whose edge is valid (the others keep their zero score)
   const int tid = threadIdx.x;
   const int MT = P.max_tasks, MA = P.max_agents;
   const float* w = P.w;
@@ -274,6 +275,7 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
       s_nseg = ns;
       s_R = tot;
       s_npairs = pairs;
+      s_nvalid = 0;
     }
     __syncthreads();
     const int nseg = s_nseg;
@@ -346,15 +348,27 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
       w2t[oo * 36 + p] = w[o.head2_w + (size_t)oo * 32 + p];  // head2^T is [64][32]
     }
     __syncthreads();
+    // only pairs with a valid edge are evaluated: scores = tanh(logit) * clamp * edge_valid is zero for the others
+    for (int pr = tid; pr < s_npairs; pr += NT) {
+      int g = 0;
+#pragma unroll
+      for (int q = 1; q < GMAX; ++q)
+        if (q < nseg && pr >= s_seg[q].poff) g = q;
+      const Seg sg = s_seg[g];
+      const int loc = pr - sg.poff;
+      const int i = loc / sg.nt, j = loc - i * sg.nt;
+      if (P.edge_valid[(size_t)sg.e * MA * MT + (size_t)i * MT + j] != 0.0f) s_plist[atomicAdd(&s_nvalid, 1)] = (uint16_t)pr;
+    }
+    __syncthreads();
     // two lanes per pair: each owns half of the 64 product features (first layer) and half of the 32 hidden
     // units (second layer); partial sums meet through a shuffle.
-    const int npairs = s_npairs;
+    const int npairs = s_nvalid;
     const int hp = tid & 1;
     const int d0 = hp * 32, p0 = hp * 16;
     for (int pbase = 0; pbase < npairs; pbase += NT / 2) {
       const int pair = pbase + (tid >> 1);
       const bool valid = pair < npairs;
-      const int pc = valid ? pair : 0;
+      const int pc = valid ? (int)s_plist[pair] : (int)s_plist[0];
       int g = 0;
 #pragma unroll
       for (int q = 1; q < GMAX; ++q)
