@@ -45,18 +45,33 @@ struct Params {
   float clamp;
 };
 
-// out_t[o][r] = act( sum_k in_t[k][r] * W[o][k] + b[o] (+ res_t[o][r]) ), r < R, o < O.
-// WT is the TRANSPOSED weight ([K][ldo] row-major, packed that way by the host), read through the
+// Weights of a linear layer.  With wb != NULL the tile picks A or B: A when (token tile is an agent tile) == (output
+// column < osplit), else B -- agent and task tokens use different matrices in the projections, the cross-attention
+// in-projections (q of one module, k / v of the other) and out-projections.
+struct LinW {
+  const float* wa;
+  const float* ba;
+  const float* wb;
+  const float* bb;
+  int split;   // first task token (multiple of 4)
+  int osplit;  // first output column of the second block
+};
+__device__ __forceinline__ LinW lin1(const float* w, const float* b) { return LinW{w, b, nullptr, nullptr, 0, 0}; }
+
+// out_t[o][r] = act( sum_k in_t[k][r] * W[o][k] + b[o] (+ res_t[o][r]) ), r_lo <= r < r_hi, o < O.
+// W is the TRANSPOSED weight ([K][ldo] row-major, packed that way by the host), read through the
 // read-only path (L1-resident: every CTA on the SM streams the same 330 KB of parameters).
 // Each thread owns a 4 (tokens) x 4 (outputs) register tile.
-__device__ void linear_t(const float* __restrict__ in_t, int R, int K, const float* __restrict__ WT, int ldo,
-                         const float* __restrict__ bg, int O, float* __restrict__ out_t,
-                         const float* __restrict__ res_t, bool relu) {
+__device__ void linear_t(const float* __restrict__ in_t, int r_lo, int r_hi, int K, const LinW W, int ldo, int O,
+                         float* __restrict__ out_t, const float* __restrict__ res_t, bool relu) {
   const int tid = threadIdx.x;
   const int og = tid & 15, rg = tid >> 4;
   const int r4 = rg * 4;
-  if (r4 < R) {
+  if (r4 >= r_lo && r4 < r_hi) {
     for (int o4 = og * 4; o4 < O; o4 += 64) {
+      const bool useA = !W.wb || ((r4 < W.split) == (o4 < W.osplit));
+      const float* __restrict__ WT = useA ? W.wa : W.wb;
+      const float* __restrict__ bg = useA ? W.ba : W.bb;
       float acc[4][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -110,44 +125,56 @@ __device__ void layer_norm_t(float* x_t, int R, const float* __restrict__ g, con
   __syncthreads();
 }
 
-// Segment table of the environments packed into one pass (shared memory)
+// Segment table of the environments packed into one pass (shared memory).  Token layout of a pass: the agents of
+// all segments first ([0, NA), padded to a multiple of 4 so that a register tile never mixes token types), then the
+// tasks of all segments.
 struct Seg {
-  int e;     // environment index
-  int base;  // first token: [base, base+na) agents, [base+na, base+na+nt) tasks
+  int e;      // environment index
+  int abase;  // first agent token
+  int tbase;  // first task token
   int na, nt;
-  int poff;  // first pair index
+  int poff;   // first pair index
 };
+#define SEG_NONE 0xFF  // padding token between the agent block and the task block
 
 // softmax(q k^T / sqrt(HD)) v, block-diagonal over the packed environments.
-// mode 0: every token attends to its environment's tokens; 1: agent tokens attend to their environment's task tokens;
-// 2: task tokens attend to their environment's agent tokens.  qkv_t rows: q 0..63, k 64..127, v 128..191.
-__device__ void attention_t(const float* __restrict__ qkv_t, int R, const Seg* __restrict__ seg,
-                            const uint8_t* __restrict__ seg_of, int mode, float* __restrict__ out_t) {
+// cross == false: every token attends to the agents and tasks of its environment (encoder self-attention);
+// cross == true: agent tokens attend to their environment's task tokens (cross_a2t) and task tokens to its agent tokens
+// (cross_t2a) in one pass -- the in-projection gave every token the q of its own module and the k / v of the other.
+// qkv_t rows: q 0..63, k 64..127, v 128..191.
+__device__ void attention_t(const float* __restrict__ qkv_t, int R, int split, const Seg* __restrict__ seg,
+                            const uint8_t* __restrict__ seg_of, bool cross, float* __restrict__ out_t) {
   const int h = threadIdx.x >> 6;
   const int i = threadIdx.x & 63;
-  if (i < R) {
+  if (i < R && seg_of[i] != SEG_NONE) {
     const Seg sg = seg[seg_of[i]];
-    const bool is_agent = i < sg.base + sg.na;
-    int k0 = sg.base, k1 = sg.base + sg.na + sg.nt;
-    bool active = true;
-    if (mode == 1) { active = is_agent; k0 = sg.base + sg.na; }
-    if (mode == 2) { active = !is_agent; k1 = sg.base + sg.na; }
-    if (active) {
-      float q[HD];
+    const bool is_agent = i < split;
+    // up to two key ranges
+    int k0[2] = {sg.abase, sg.tbase};
+    int k1[2] = {sg.abase + sg.na, sg.tbase + sg.nt};
+    if (cross) {
+      if (is_agent) k1[0] = k0[0];  // agents: tasks only
+      else k1[1] = k0[1];           // tasks: agents only
+    }
+    float q[HD];
 #pragma unroll
-      for (int d = 0; d < HD; ++d) q[d] = qkv_t[(h * HD + d) * TS + i] * 0.25f;
-      float m = -INFINITY;
-      for (int j = k0; j < k1; ++j) {
+    for (int d = 0; d < HD; ++d) q[d] = qkv_t[(h * HD + d) * TS + i] * 0.25f;
+    float m = -INFINITY;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+      for (int j = k0[rr]; j < k1[rr]; ++j) {
         float s = 0.0f;
 #pragma unroll
         for (int d = 0; d < HD; ++d) s = fmaf(q[d], qkv_t[(D + h * HD + d) * TS + j], s);
         m = fmaxf(m, s);
       }
-      float l = 0.0f;
-      float acc[HD];
+    float l = 0.0f;
+    float acc[HD];
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc[d] = 0.0f;
-      for (int j = k0; j < k1; ++j) {
+    for (int d = 0; d < HD; ++d) acc[d] = 0.0f;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+      for (int j = k0[rr]; j < k1[rr]; ++j) {
         float s = 0.0f;
 #pragma unroll
         for (int d = 0; d < HD; ++d) s = fmaf(q[d], qkv_t[(D + h * HD + d) * TS + j], s);
@@ -156,10 +183,9 @@ __device__ void attention_t(const float* __restrict__ qkv_t, int R, const Seg* _
 #pragma unroll
         for (int d = 0; d < HD; ++d) acc[d] = fmaf(p, qkv_t[(2 * D + h * HD + d) * TS + j], acc[d]);
       }
-      const float inv = 1.0f / l;
+    const float inv = 1.0f / l;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) out_t[(h * HD + d) * TS + i] = acc[d] * inv;
-    }
+    for (int d = 0; d < HD; ++d) out_t[(h * HD + d) * TS + i] = acc[d] * inv;
   }
   __syncthreads();
 }
@@ -226,7 +252,7 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
   __shared__ int s_env[GLIST], s_na[GLIST], s_nt[GLIST], s_scan[NT / 32 + 1];
   __shared__ Seg s_seg[GMAX];
   __shared__ uint8_t s_seg_of[TS];
-  __shared__ int s_nseg, s_R, s_npairs, s_next, s_nvalid;
+  __shared__ int s_nseg, s_R, s_split, s_npairs, s_next, s_nvalid;
   __shared__ uint16_t s_plist[1024];  // pairs of this pass whose edge is valid (the others keep their zero score)
   const int tid = threadIdx.x;
   const int MT = P.max_tasks, MA = P.max_agents;
@@ -255,25 +281,34 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
   for (;;) {
     // ---- next pass: as many of the remaining environments as fit TS tokens (at most GMAX)
     if (tid == 0) {
-      int g = s_next, ns = 0, tot = 0, pairs = 0;
+      int g = s_next, ns = 0, sa = 0, st = 0, pairs = 0;
       while (g < m && ns < GMAX) {
         const int na = s_na[g], nt = s_nt[g];
         if (na == 0 || nt == 0) { ++g; continue; }
-        if (tot + na + nt > TS) break;
+        if (((sa + na + 3) & ~3) + st + nt > TS) break;
         s_seg[ns].e = s_env[g];
-        s_seg[ns].base = tot;
+        s_seg[ns].abase = sa;
+        s_seg[ns].tbase = st;  // relative to the task block for now
         s_seg[ns].na = na;
         s_seg[ns].nt = nt;
         s_seg[ns].poff = pairs;
-        for (int r = 0; r < na + nt; ++r) s_seg_of[tot + r] = (uint8_t)ns;
-        tot += na + nt;
+        sa += na;
+        st += nt;
         pairs += na * nt;
         ++ns;
         ++g;
       }
+      const int split = (sa + 3) & ~3;
+      for (int q = 0; q < ns; ++q) {
+        s_seg[q].tbase += split;
+        for (int r = 0; r < s_seg[q].na; ++r) s_seg_of[s_seg[q].abase + r] = (uint8_t)q;
+        for (int r = 0; r < s_seg[q].nt; ++r) s_seg_of[s_seg[q].tbase + r] = (uint8_t)q;
+      }
+      for (int r = sa; r < split; ++r) s_seg_of[r] = SEG_NONE;
       s_next = g;
       s_nseg = ns;
-      s_R = tot;
+      s_split = split;
+      s_R = split + st;
       s_npairs = pairs;
       s_nvalid = 0;
     }
@@ -281,61 +316,57 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
     const int nseg = s_nseg;
     if (nseg == 0) break;
     const int R = s_R;
+    const int split = s_split;  // agent tokens [0, split), task tokens [split, R)
 
-    // ---- token embeddings: x = proj(feats) + type_embed  (PairCostHybrid.py:131-133).  Agent and task tokens of the
-    // packed environments interleave, so both projections run over all tokens (K is 12 / 13) and each token keeps
-    // the one of its type.  Linear layers act on each token independently and the register tiles are 4 tokens wide:
-    // whatever a token column of the wrong type or beyond R holds never reaches a valid output.
-    for (int idx = tid; idx < (AF + TF) * R; idx += NT) {
-      const int r = idx % R, k = idx / R;
-      const Seg sg = s_seg[s_seg_of[r]];
-      const int l = r - sg.base;
-      if (k < AF) {
-        big_t[k * TS + r] = l < sg.na ? P.agent_feats[((size_t)sg.e * MA + l) * AF + k] : 0.0f;
-      } else {
-        const int kk = k - AF;
-        z_t[kk * TS + r] = l >= sg.na ? P.task_feats[((size_t)sg.e * MT + (l - sg.na)) * TF + kk] : 0.0f;
+    // ---- token embeddings: x = proj(feats) + type_embed  (PairCostHybrid.py:131-133).
+    // Linear layers act on each token independently and the register tiles are 4 tokens wide: whatever a padding
+    // column holds never reaches a valid output.
+    for (int idx = tid; idx < AF * split; idx += NT) {
+      const int r = idx % split, k = idx / split;
+      float v = 0.0f;
+      if (s_seg_of[r] != SEG_NONE) {
+        const Seg sg = s_seg[s_seg_of[r]];
+        v = P.agent_feats[((size_t)sg.e * MA + (r - sg.abase)) * AF + k];
       }
+      big_t[k * TS + r] = v;
+    }
+    for (int idx = tid; idx < TF * (R - split); idx += NT) {
+      const int r = split + idx % (R - split), k = idx / (R - split);
+      const Seg sg = s_seg[s_seg_of[r]];
+      z_t[k * TS + r] = P.task_feats[((size_t)sg.e * MT + (r - sg.tbase)) * TF + k];
     }
     __syncthreads();
-    linear_t(big_t, R, AF, w + o.agent_proj_w, D, w + o.agent_proj_b, D, x_t, nullptr, false);
-    linear_t(z_t, R, TF, w + o.task_proj_w, D, w + o.task_proj_b, D, y_t, nullptr, false);
+    linear_t(big_t, 0, split, AF, lin1(w + o.agent_proj_w, w + o.agent_proj_b), D, D, x_t, nullptr, false);
+    linear_t(z_t, split, R, TF, lin1(w + o.task_proj_w, w + o.task_proj_b), D, D, x_t, nullptr, false);
     for (int idx = tid; idx < D * R; idx += NT) {
       const int k = idx / R, r = idx - k * R;
-      const Seg sg = s_seg[s_seg_of[r]];
-      if (r < sg.base + sg.na) x_t[k * TS + r] += w[o.type_embed + k];
-      else x_t[k * TS + r] = y_t[k * TS + r] + w[o.type_embed + D + k];
+      x_t[k * TS + r] += w[o.type_embed + (r < split ? 0 : D) + k];
     }
     __syncthreads();
 
     // ---- TransformerEncoderLayer (post-norm, relu, eval): x1 = LN1(x + SA(x)); x2 = LN2(x1 + FF(x1))
-    linear_t(x_t, R, D, w + o.enc_in_w, 3 * D, w + o.enc_in_b, 3 * D, big_t, nullptr, false);
-    attention_t(big_t, R, s_seg, s_seg_of, 0, y_t);
-    linear_t(y_t, R, D, w + o.enc_out_w, D, w + o.enc_out_b, D, z_t, x_t, false);   // z = x + out_proj(attn)
+    linear_t(x_t, 0, R, D, lin1(w + o.enc_in_w, w + o.enc_in_b), 3 * D, 3 * D, big_t, nullptr, false);
+    attention_t(big_t, R, split, s_seg, s_seg_of, false, y_t);
+    linear_t(y_t, 0, R, D, lin1(w + o.enc_out_w, w + o.enc_out_b), D, D, z_t, x_t, false);   // z = x + out_proj(attn)
     layer_norm_t(z_t, R, w + o.enc_n1_w, w + o.enc_n1_b);                                    // z = x1
-    linear_t(z_t, R, D, w + o.enc_l1_w, FF, w + o.enc_l1_b, FF, big_t, nullptr, true);  // hidden
-    linear_t(big_t, R, FF, w + o.enc_l2_w, D, w + o.enc_l2_b, D, x_t, z_t, false);                 // x = x1 + FF(x1)
+    linear_t(z_t, 0, R, D, lin1(w + o.enc_l1_w, w + o.enc_l1_b), FF, FF, big_t, nullptr, true);  // hidden
+    linear_t(big_t, 0, R, FF, lin1(w + o.enc_l2_w, w + o.enc_l2_b), D, D, x_t, z_t, false);      // x = x1 + FF(x1)
     layer_norm_t(x_t, R, w + o.enc_n2_w, w + o.enc_n2_b);                                    // x = h (encoder output)
 
-    // ---- cross attention (both use the ORIGINAL h): a' = a + MHA_a2t(a, t, t); t' = t + MHA_t2a(t, a, a).
-    // Out-projections run over all tokens; each token keeps the one of its type.
-    linear_t(x_t, R, D, w + o.a2t_in_w, 3 * D, w + o.a2t_in_b, 3 * D, big_t, nullptr, false);
-    attention_t(big_t, R, s_seg, s_seg_of, 1, y_t);
-    linear_t(y_t, R, D, w + o.a2t_out_w, D, w + o.a2t_out_b, D, z_t, x_t, false);   // z[:, agents] = a'
-    linear_t(x_t, R, D, w + o.t2a_in_w, 3 * D, w + o.t2a_in_b, 3 * D, big_t, nullptr, false);
-    attention_t(big_t, R, s_seg, s_seg_of, 2, y_t);
-    linear_t(y_t, R, D, w + o.t2a_out_w, D, w + o.t2a_out_b, D, big_t, x_t, false);  // big[:, tasks] = t'
-    for (int idx = tid; idx < D * R; idx += NT) {
-      const int k = idx / R, r = idx - k * R;
-      const Seg sg = s_seg[s_seg_of[r]];
-      if (r >= sg.base + sg.na) z_t[k * TS + r] = big_t[k * TS + r];
+    // ---- cross attention (both use the ORIGINAL h): a' = a + MHA_a2t(a, t, t); t' = t + MHA_t2a(t, a, a), merged:
+    // agent tiles take q from cross_a2t and k, v from cross_t2a (they are keys of the task queries); task tiles the
+    // other way round; one attention pass; out-projection by token type.
+    {
+      const LinW in_w{w + o.a2t_in_w, w + o.a2t_in_b, w + o.t2a_in_w, w + o.t2a_in_b, split, D};
+      linear_t(x_t, 0, R, D, in_w, 3 * D, 3 * D, big_t, nullptr, false);
+      attention_t(big_t, R, split, s_seg, s_seg_of, true, y_t);
+      const LinW out_w{w + o.a2t_out_w, w + o.a2t_out_b, w + o.t2a_out_w, w + o.t2a_out_b, split, 1 << 30};
+      linear_t(y_t, 0, R, D, out_w, D, D, z_t, x_t, false);   // z = a' (agent tokens) / t' (task tokens)
     }
-    __syncthreads();
-    // z_t now holds a' (agent tokens) / t' (task tokens)
 
     // ---- pair head: logits[i, j] = w3 . relu(W2 relu(Wat (a_i * t_j) + Wa a_i + Wt t_j + b1) + b2) + b3
-    linear_t(z_t, R, D, w + o.head1_w, D, nullptr, D, y_t, nullptr, false);                 // Wa x for all tokens
-    linear_t(z_t, R, D, w + o.head1_w + D * D, D, w + o.head1_b, D, x_t, nullptr, false);   // Wt x + b1 for all tokens
+    linear_t(z_t, 0, split, D, lin1(w + o.head1_w, nullptr), D, D, y_t, nullptr, false);               // Wa a
+    linear_t(z_t, split, R, D, lin1(w + o.head1_w + D * D, w + o.head1_b), D, D, x_t, nullptr, false);   // Wt t + b1
     // stage Wat [o][d] (row-major, stride WS) and W2^T [o][p]
     float* wat = big_t;               // [64][WS]
     float* w2t = big_t + 64 * WS;     // [64][36]
@@ -376,7 +407,7 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
       const Seg sg = s_seg[g];
       const int loc = pc - sg.poff;
       const int i = loc / sg.nt, j = loc - i * sg.nt;
-      const int ta = sg.base + i, tt = sg.base + sg.na + j;
+      const int ta = sg.abase + i, tt = sg.tbase + j;
       float u[32];
 #pragma unroll
       for (int d = 0; d < 32; ++d) u[d] = z_t[(d0 + d) * TS + ta] * z_t[(d0 + d) * TS + tt];
