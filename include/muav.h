@@ -129,6 +129,12 @@ typedef struct muav_step_out {
    * so two zero-initialised buffers used alternately need no further care. */
   const int32_t* d_env_order;
   int32_t* d_env_order_next;
+  /* Optional workspace int32 [E, n_agents, 2].  When given, a single-step call with a fused allocator (n_steps == 1,
+   * opts->mode != 0) runs as two kernels: the allocator for the environments whose replan rule fires (the others leave
+   * after reading their record header), then the step for all environments without the allocator's scratch, i.e.
+   * half as many environments again per SM.  Same results as the one-kernel form; on B200 the one-kernel form is
+   * faster (the allocator of a few environments hides among the others' steps), so callers normally leave this NULL. */
+  int32_t* d_actions_ws;
 } muav_step_out;
 
 /* Optional pair-token emission fused at the end of each step (saves the separate muav_tokens_pair pass):

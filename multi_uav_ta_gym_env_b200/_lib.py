@@ -65,7 +65,7 @@ class MuavStepOut(C.Structure):
         ("d_reward", C.c_void_p), ("d_terminated", C.c_void_p), ("d_truncated", C.c_void_p),
         ("d_n_events", C.c_void_p), ("d_events", C.c_void_p), ("d_n_pairs", C.c_void_p),
         ("d_pairs", C.c_void_p), ("d_n_open", C.c_void_p),
-        ("d_env_order", C.c_void_p), ("d_env_order_next", C.c_void_p),
+        ("d_env_order", C.c_void_p), ("d_env_order_next", C.c_void_p), ("d_actions_ws", C.c_void_p),
     ]
 
 

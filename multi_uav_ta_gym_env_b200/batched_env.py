@@ -122,6 +122,12 @@ class BatchedMultiUAVEnv:
         self.group_replanners = os.environ.get("MUAV_ENV_ORDER", "1") != "0"
         self._order = torch.zeros(2, E + 2, dtype=torch.int32, device=dev)
         self._order_cur = -1  # index of the buffer holding the order for the next launch (-1: identity)
+        # workspace that lets a single fused step run as allocator kernel + step kernel (muav_step_out.d_actions_ws)
+        # (measured slower than the one-kernel form on B200: off unless MUAV_SPLIT_STEP=1)
+        self._actions_ws = None
+        if os.environ.get("MUAV_SPLIT_STEP", "0") == "1":
+            self._actions_ws = torch.empty(E, A, 2, dtype=torch.int32, device=dev)
+            self._out.d_actions_ws = self._actions_ws.data_ptr()
         self.scenarios = None
         self.agent_names = None
         self.launches = 0

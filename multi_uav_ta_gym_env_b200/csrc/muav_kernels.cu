@@ -67,6 +67,8 @@ struct StepParams {
   int32_t* actions_out;  // allocate-only mode: ordered (agent, index) list per env
   long long* phase_out;  // MUAV_PHASE_TIMING builds: 16 cycle counters summed over warps
   int n_envs, n_steps, tape_stride, use_bulk, alloc_only, cta_warps, sync_mask;
+  int scratch_launch;   // per-environment scratch bytes of this launch (allocator work arrays or step temporaries)
+  int actions_are_ids;  // actions hold (agent, task id) instead of (agent, index into last_tasks_info)
 };
 
 #define MUAV_MAX_CTA_WARPS 16
@@ -96,12 +98,37 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
   }
   const int sync_mask = W > 1 ? P.sync_mask : 0;
   const Layout& L = P.L;
-  const int slot_bytes = L.record_bytes + L.scratch_bytes;
+  const int slot_bytes = L.record_bytes + P.scratch_launch;
   char* rec = (char*)smem + (size_t)w * slot_bytes;
   char* scratch = rec + L.record_bytes;
   char* grec = P.records + (size_t)(has_env ? e : 0) * L.record_bytes;
   int16_t* act_agent = act_agent_s[w];
   int16_t* act_tid = act_tid_s[w];
+
+  // ---- allocator-only launch: environments whose replan rule does not fire leave after a look at their header
+  if (P.alloc_only && has_env) {
+    int32_t* ghi = (int32_t*)(grec + L.o_hi);
+    int go = 0;
+    if (lane == 0) {
+      const muav_alloc_opts& O = P.opts;
+      if (!ghi[HI_DONE]) {
+        const int t = ghi[HI_T];
+        const int iv = O.replan_interval > 0 ? O.replan_interval : 1;
+        const bool ev_hit = (ghi[HI_EV_TAGMASK] & O.event_mask) != 0;
+        if (O.mode == 1 && O.planner == 0) go = (t - ghi[HI_LAST_PLAN_STEP]) >= iv || ev_hit;
+        else if (O.mode == 3) go = 1;
+        else go = t == 0 || (t % iv) == 0 || ev_hit;
+        // allocate_tasks counts every call, also those that return without replanning (HungarianAllocator.py:84)
+        if (!go && O.planner == 0 && O.mode != 0) ghi[HI_N_CALLS] += 1;
+      }
+      if (!go) {
+        if (P.out.d_n_pairs) P.out.d_n_pairs[e] = 0;
+        if (P.actions_out) P.actions_out[(size_t)e * L.D.A * 2] = -1;
+      }
+    }
+    go = __shfl_sync(0xffffffffu, go, 0);
+    if (!go) has_env = false;
+  }
 
   // ---- stage the record into shared memory
   if (has_env) {
@@ -168,7 +195,13 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
       int n_act = 0;
       for (int i = 0; i < np; ++i) {
         if (P.out.d_pairs) P.out.d_pairs[(size_t)e * A + i] = ((int)act_agent[i] << 16) | (int)act_tid[i];
-        if (P.actions_out && HIv(N_OPEN) > 0 && S.in_last_open(act_tid[i])) {
+        if (P.actions_out && P.actions_are_ids) {
+          if (HIv(N_OPEN) > 0 && S.in_last_open(act_tid[i])) {
+            P.actions_out[((size_t)e * A + n_act) * 2] = act_agent[i];
+            P.actions_out[((size_t)e * A + n_act) * 2 + 1] = act_tid[i];
+            ++n_act;
+          }
+        } else if (P.actions_out && HIv(N_OPEN) > 0 && S.in_last_open(act_tid[i])) {
           // index of the task inside last_tasks_info = number of open tasks with a smaller id
           int k = act_tid[i] - 1, idx = 0;
           for (int ww = 0; ww < (k >> 5); ++ww) idx += __popc(V.open_mask()[ww]);
@@ -213,7 +246,7 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
           int a = act[2 * i];
           if (a < 0) break;
           act_agent[n_act] = (int16_t)a;
-          act_tid[n_act] = (int16_t)S.open_task_at(act[2 * i + 1]);
+          act_tid[n_act] = (int16_t)(P.actions_are_ids ? act[2 * i + 1] : S.open_task_at(act[2 * i + 1]));
           ++n_act;
         }
       }
@@ -388,10 +421,42 @@ extern "C" {
 #include "muav_abi_common.inl"
 
 static int launch_step(StepParams& P, void* stream) {
-  const size_t slot = (size_t)P.L.record_bytes + (size_t)P.L.scratch_bytes;
-  // environments (warps) per CTA: two CTAs per SM (~113 KB of shared memory each); MUAV_CTA_WARPS overrides.
-  // Measured on B200, WPS_hard 4096 envs (tools/kbench.py): W=1 0.273 ms, 2 0.261, 4 0.231, 6 0.218, 12 0.218.
-  int W = (int)((113 * 1024) / slot);
+  // launches without the allocator need only the step's temporaries: more environments per SM
+  P.scratch_launch = (P.alloc_only || P.opts.mode != 0) ? P.L.scratch_bytes : P.L.step_scratch_bytes;
+  const size_t slot = (size_t)P.L.record_bytes + (size_t)P.scratch_launch;
+  // environments (warps) per CTA.  The warps of a CTA are phase-aligned with CTA barriers: they share instruction
+  // fetches, but a CTA is as slow as its slowest environment.  Measured on B200 (bench.py --workload ..., all widths
+  // 1..6, profiles/r01_cta_width.md): the number of resident environments per SM decides first; at equal residency the
+  // widest CTA that still leaves two CTAs per SM wins (WPS_hard 6 x 2, WPS_commit 4 x 2, burst x2 3 x 2); when only
+  // one-warp CTAs or a single wide CTA reach the maximum, the wide CTA wins from four environments up (WPS_escort
+  // 5 x 1) and one-warp CTAs below (burst x4 1 x 3).  MUAV_CTA_WARPS overrides.
+  int W = 1;
+  {
+    static size_t static_smem = 0;
+    if (!static_smem) {
+      cudaFuncAttributes fa;
+      static_smem = cudaFuncGetAttributes(&fa, muav_step_kernel) == cudaSuccess ? fa.sharedSizeBytes : 4608;
+    }
+    const size_t budget = 228 * 1024, per_cta = static_smem + 1024;  // B200: 228 KB per SM, 1 KB reserved per CTA
+    int envs[7] = {0, 0, 0, 0, 0, 0, 0}, ctas[7] = {0, 0, 0, 0, 0, 0, 0}, best = 0;
+    for (int w = 1; w <= 6; ++w) {
+      const size_t cta = slot * w + per_cta;
+      if (cta > 227 * 1024) break;
+      ctas[w] = (int)(budget / cta);
+      envs[w] = ctas[w] * w;
+      if (envs[w] > best) best = envs[w];
+    }
+    int pick = 0;
+    for (int w = 6; w >= 2 && !pick; --w)
+      if (envs[w] == best && ctas[w] >= 2) pick = w;
+    if (!pick) {
+      int wide = 0;
+      for (int w = 6; w >= 2 && !wide; --w)
+        if (envs[w] == best) wide = w;
+      pick = (wide && (best >= 4 || envs[1] < best)) ? wide : 1;
+    }
+    W = pick;
+  }
   const char* ev = getenv("MUAV_CTA_WARPS");
   if (ev) W = atoi(ev);
   if (W < 1) W = 1;
@@ -457,6 +522,26 @@ int muav_step(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, 
     }
   }
 #endif
+  if (n_steps == 1 && P.opts.mode != 0 && P.out.d_actions_ws) {
+    // two kernels: allocator for the environments that replan, then the step for everyone with the small scratch
+    StepParams Pa = P;
+    Pa.n_steps = 0;
+    Pa.alloc_only = 1;
+    Pa.actions_out = P.out.d_actions_ws;
+    Pa.actions_are_ids = 1;
+    Pa.out.d_env_order_next = nullptr;
+    memset(&Pa.tok, 0, sizeof(Pa.tok));
+    rc = launch_step(Pa, stream);
+    if (rc) return rc;
+    StepParams Ps = P;
+    Ps.actions = P.out.d_actions_ws;
+    Ps.actions_are_ids = 1;
+    Ps.opts.order_hint_mode = P.opts.mode;
+    Ps.opts.mode = 0;
+    Ps.out.d_n_pairs = nullptr;  // written by the allocator launch
+    Ps.out.d_pairs = nullptr;
+    return launch_step(Ps, stream);
+  }
   return launch_step(P, stream);
 }
 

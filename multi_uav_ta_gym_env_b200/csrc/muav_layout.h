@@ -173,6 +173,7 @@ struct Layout {
 #undef X
   int32_t record_bytes;
   int32_t scratch_bytes;
+  int32_t step_scratch_bytes;  // scratch of a launch that does not run the allocator
   Dims D;
 };
 
@@ -204,6 +205,10 @@ MUAV_HD inline Layout make_layout(const muav_config& c) {
   int32_t s2 = 8 * 4 * D.A + 2 * D.A + 16;
   if (s2 > s) s = s2;
   L.scratch_bytes = align_up(s, 16);
+  // launches that do not run the allocator only need the step's temporaries (+ the token builder's column list)
+  int32_t s3 = s2 + 2 * (D.TC + 4);
+  L.step_scratch_bytes = align_up(s3, 16);
+  if (L.step_scratch_bytes > L.scratch_bytes) L.step_scratch_bytes = L.scratch_bytes;
   return L;
 }
 
