@@ -71,11 +71,17 @@ def _cpu_worker(args):
             pairs = []
             if otok.hybrid_should_replan(env, env.last_events, HYBRID_INTERVAL):
                 tok = otok.build_pair_tokens(env, 32, 16)
-                with torch.no_grad():
-                    logits, _ = net(torch.from_numpy(tok["task_feats"])[None], torch.from_numpy(tok["task_mask"])[None],
-                                    torch.from_numpy(tok["agent_feats"])[None], torch.from_numpy(tok["agent_mask"])[None])
-                scores = (torch.tanh(logits[0]) * 0.35).numpy() * tok["edge_valid"]
-                pairs = otok.pair_plan(env, hung, scores)
+                if tok["agent_mask"].all() or tok["task_mask"].all():
+                    # nobody left to assign or nothing left to do: the allocator returns [] whatever the scores are
+                    # (and torch's padded-encoder fast path rejects a batch whose tokens are all padding)
+                    pairs = []
+                else:
+                    with torch.no_grad():
+                        logits, _ = net(torch.from_numpy(tok["task_feats"])[None], torch.from_numpy(tok["task_mask"])[None],
+                                        torch.from_numpy(tok["agent_feats"])[None],
+                                        torch.from_numpy(tok["agent_mask"])[None])
+                    scores = (torch.tanh(logits[0]) * 0.35).numpy() * tok["edge_valid"]
+                    pairs = otok.pair_plan(env, hung, scores)
             env.step(apply_assign(env, pairs))
             n += 1
         return n
