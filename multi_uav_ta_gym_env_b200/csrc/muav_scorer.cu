@@ -79,7 +79,7 @@ __device__ void linear_t(const float* __restrict__ in_t, int r_lo, int r_hi, int
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[j][i] = b;
       }
-#pragma unroll 4
+#pragma unroll 16
       for (int k = 0; k < K; ++k) {
         const float4 a = *(const float4*)&in_t[k * TS + r4];
         const float4 w = __ldg((const float4*)&WT[(size_t)k * ldo + o4]);
