@@ -220,7 +220,11 @@ def run_gpu_arm(args):
     else:
         raise SystemExit(f"unknown workload {wl}")
     E = args.envs
-    env = BatchedMultiUAVEnv(cfg, E, device=dev).reset(sharding.shard_range(E, rank))
+    # task slots per environment: the library default is the provable bound (every task that could ever be created, 48
+    # for WPS_hard).  With slot recycling at most 24 are alive at once over 4096 seeds x 150 steps; --task-cap 32 gives
+    # 15 instead of 12 environments per SM but no measurable gain in this bench, so the default stays the safe one.
+    task_cap = args.task_cap if args.task_cap > 0 else None
+    env = BatchedMultiUAVEnv(cfg, E, device=dev, task_cap=task_cap).reset(sharding.shard_range(E, rank))
     torch.manual_seed(0)
     scores = tok = scorer = None
     if use_scorer:
@@ -355,7 +359,7 @@ def run_gpu_arm(args):
             "config": {"workload": f"{case_name} ({A} agents), {E} envs per GPU, {desc}, seeds = env index",
                        "envs_per_gpu": E, "global_envs": world * E, "parallelism": f"env-shard x{world}",
                        "l2": f"flushed between timed steps (256 MB write); state {E * rb / 1e6:.0f} MB vs 126 MB L2",
-                       "record_bytes": rb, "agent_steps_per_s": value * A},
+                       "record_bytes": rb, "task_slots": int(env.task_cap), "agent_steps_per_s": value * A},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes,
                     "d2h_bytes_per_step": act_bytes + E * 10, "steps": Ke},
             "gpu_launches": gpu_launches,
@@ -456,6 +460,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
     ap.add_argument("--workload", default="hard_pair",
                     help="hard_pair (default, BASELINE config 2) | hard_local | commit_urgency | escort_coalition | burst_xK")
+    ap.add_argument("--task-cap", type=int, default=0, help="task slots per environment (0 = workload default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
