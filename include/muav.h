@@ -18,6 +18,7 @@
  *   muav_avoid_obstacles      -> core_sim.SimCore.avoid_obstacles  core_sim/src/sim_core.rs:24-59 (PyO3 export lib.rs:10-18)
  *   muav_tokens_pair          -> build_pair_tokens             TaskAllocation/Hybrid/PairCostHybrid.py:31-65
  *                                (build_att_tokens             TaskAllocation/Hybrid/AttentionRAH.py:50-173)
+ *   muav_tokens_context       -> build_context_pair_tokens     TaskAllocation/Hybrid/ContextPairHybrid.py:33-78
  *   muav_tokens_commit        -> enrich_commit_tokens          TaskAllocation/Hybrid/AttentionCommit.py:49-62
  *   muav_tokens_escort        -> build_escort_tokens           TaskAllocation/Hybrid/AttentionEscort.py:76-241
  *   muav_observe              -> _generate_observations/get_task_info  mUAV_TA/DroneEnv.py:365-492
@@ -212,6 +213,13 @@ int muav_metrics(const muav_config* cfg, const void* d_records, double* d_out, i
 int muav_tokens_pair(const muav_config* cfg, const void* d_records, int max_tasks, int max_agents,
                      float* d_task_feats, uint8_t* d_task_mask, float* d_agent_feats, uint8_t* d_agent_mask,
                      float* d_edge_valid, int32_t* d_task_ids, int n_envs, void* stream);
+
+/* Context-pair tokens = build_context_pair_tokens(env, raw) (ContextPairHybrid.py:33-78): the pair tokens plus the team /
+ * situation vector context [E, 8] f32.  raw != 0 selects the per-entity feature variant of build_att_tokens(raw=True)
+ * (AttentionRAH.py:86-97,140-146): task_feats [E,max_tasks,9], agent_feats [E,max_agents,11], context [E,1]. */
+int muav_tokens_context(const muav_config* cfg, const void* d_records, int max_tasks, int max_agents, int raw,
+                        float* d_task_feats, uint8_t* d_task_mask, float* d_agent_feats, uint8_t* d_agent_mask,
+                        float* d_edge_valid, int32_t* d_task_ids, float* d_context, int n_envs, void* stream);
 
 /* Commit tokens = enrich_commit_tokens(build_att_tokens(env)) (AttentionCommit.py:49-62, AttentionRAH.py:50-173):
  * as muav_tokens_pair but agent_feats is [E, max_agents, 13] (last column: remaining commit-lock fraction) and there is

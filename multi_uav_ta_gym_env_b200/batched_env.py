@@ -361,6 +361,25 @@ class BatchedMultiUAVEnv:
         return {"task_feats": tf, "task_mask": tm.bool(), "agent_feats": af, "agent_mask": am.bool(),
                 "edge_valid": ev, "task_ids": ids}
 
+    def tokens_context(self, max_tasks=32, max_agents=16, raw=False):
+        """build_context_pair_tokens(env, raw) for every environment (ContextPairHybrid.py:33-78): pair tokens (the
+        per-entity `raw` variant has 9 / 11 features) plus the context vector [E, 8] ([E, 1] when raw)."""
+        E, dev = self.n_envs, self.device
+        tf = torch.empty(E, max_tasks, 9 if raw else 13, dtype=torch.float32, device=dev)
+        tm = torch.empty(E, max_tasks, dtype=torch.uint8, device=dev)
+        af = torch.empty(E, max_agents, 11 if raw else 12, dtype=torch.float32, device=dev)
+        am = torch.empty(E, max_agents, dtype=torch.uint8, device=dev)
+        ev = torch.empty(E, max_agents, max_tasks, dtype=torch.float32, device=dev)
+        ids = torch.empty(E, max_tasks, dtype=torch.int32, device=dev)
+        ctx = torch.empty(E, 1 if raw else 8, dtype=torch.float32, device=dev)
+        rc = self.lib.dll.muav_tokens_context(C.byref(self.cfg), self.records.data_ptr(), max_tasks, max_agents, int(raw),
+                                              tf.data_ptr(), tm.data_ptr(), af.data_ptr(), am.data_ptr(), ev.data_ptr(),
+                                              ids.data_ptr(), ctx.data_ptr(), E, self._stream())
+        _lib.check(rc, "muav_tokens_context")
+        self.launches += 1
+        return {"task_feats": tf, "task_mask": tm.bool(), "agent_feats": af, "agent_mask": am.bool(),
+                "edge_valid": ev, "task_ids": ids, "context": ctx}
+
     def tokens_commit(self, max_tasks=32, max_agents=16):
         """enrich_commit_tokens(build_att_tokens(env)) for every environment (AttentionCommit.py:49-62)."""
         E, dev = self.n_envs, self.device

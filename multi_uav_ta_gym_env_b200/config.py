@@ -129,13 +129,49 @@ CASE_SPECS: Dict[str, Dict[str, Any]] = {
     "WPS_easy": _wps((2, 2, 2, 2), (4, 6), 0.05, (4, 3), 0.08, 250.0, 8, 40, False, 2, 25.0, 10.0),
     "WPS_hard": _wps((2, 2, 2, 2), (3, 5), 0.08, (5, 4), 0.12, 120.0, 15, 25, True, 3, 30.0, 12.0),
     "WPS_burst": _wps((2, 2, 2, 2), (2, 4), 0.1, (6, 4), 0.15, 150.0, 12, 20, True, 4, 35.0, 15.0),
-    "WPS_attn": _wps((4, 2, 4, 2), (4, 8), 0.08, (8, 6), 0.18, 90.0, 18, 22, True, 4),
+    "WPS_attn": _wps((4, 2, 4, 2), (4, 8), 0.08, (8, 6), 0.18, 90.0, 18, 22, True, 4, 30.0, 12.0, **_DUAL),
     "WPS_attn_XL": _wps((14, 6, 14, 6), (13, 26), 0.08, (26, 20), 0.18, 90.0, 18, 22, True, 4, 30.0, 12.0, **_DUAL),
     "WPS_commit": _wps((4, 2, 4, 2), (4, 8), 0.08, (8, 6), 0.18, 90.0, 18, 22, True, 4, 30.0, 12.0,
                        commit_horizon=25, reassign_penalty=2.0, **_DUAL),
     "WPS_escort": _wps((5, 3, 4, 2), (2, 6), 0.03, (4, 6), 0.15, 100.0, 15, 28, True, 3, 30.0, 12.0,
                        commit_horizon=20, reassign_penalty=2.0, **_DUAL, **_ESCORT),
 }
+
+
+def _attn_variant(**over):
+    s = copy.deepcopy(CASE_SPECS["WPS_attn"])
+    s.update(over)
+    return s
+
+
+def _static(agents, tasks, fail_rate=0.0, threats=(), arrival=0.0):
+    return {"agents": dict(zip(("F1", "F2", "R1", "R2"), agents)), "tasks": {"Att": tasks[0], "Rec": tasks[1], "Hold": 0},
+            "fail_rate": fail_rate, "threats_list": [(n, c) for n, c in zip(("T1", "T2"), threats)], "arrival_rate": arrival}
+
+
+# the remaining registered scenarios of experiments/paper_scenarios.py: common-operating-picture sweeps of WPS_attn
+# (:126-160, 274-300), its larger fleets (:161-215) and the legacy static / dynamic cases (:14-57)
+CASE_SPECS.update({
+    "WPS_attn_AWACS": _attn_variant(sense_radius=0.0, threat_delay=0, share_knowledge=True),
+    "WPS_attn_L": _attn_variant(agents={"F1": 10, "F2": 5, "R1": 10, "R2": 5}, tasks={"Att": 10, "Rec": 20, "Hold": 0},
+                                threats_list=[("T1", 20), ("T2", 15)]),
+    "WPS_attn_OS18": _attn_variant(agents={"F1": 6, "F2": 3, "R1": 6, "R2": 3}),
+    "WPS_attn_OS24": _attn_variant(agents={"F1": 8, "F2": 4, "R1": 8, "R2": 4}),
+    "static_strike": _static((0, 2, 0, 0), (15, 0)),
+    "scal_None": _static((0, 2, 0, 0), (15, 0)),
+    "recon_strike_mix": _static((2, 0, 4, 0), (6, 12)),
+    "train_mixed": _static((2, 0, 4, 0), (6, 12)),
+    "agent_scaling_mid": _static((3, 0, 6, 0), (6, 24)),
+    "scal_Agents_mid": _static((3, 0, 6, 0), (6, 24)),
+    "D1_attrition": _static((2, 0, 4, 0), (6, 12), fail_rate=0.1),
+    "D2_popup_threats": _static((2, 2, 2, 2), (4, 8), threats=(3, 2)),
+    "D3_combined": _static((2, 2, 2, 2), (4, 8), fail_rate=0.1, threats=(3, 2), arrival=0.02),
+})
+for _r in (60, 90, 150, 250):
+    CASE_SPECS[f"WPS_attn_COP_R{_r}"] = _attn_variant(sense_radius=float(_r), threat_delay=18, share_knowledge=False)
+for _d in (0, 6, 12, 18):
+    CASE_SPECS[f"WPS_attn_COP_d{_d}"] = _attn_variant(sense_radius=90.0, threat_delay=_d, share_knowledge=False)
+    CASE_SPECS[f"WPS_attn_COP_cue_d{_d}"] = _attn_variant(sense_radius=0.0, threat_delay=_d, share_knowledge=True)
 
 
 def burst_scaled_spec(k: int) -> Dict[str, Any]:

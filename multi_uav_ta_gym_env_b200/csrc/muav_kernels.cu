@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(128) muav_tokens_pair_kernel(const __grid_cons
                                                                const __grid_constant__ Layout L, const char* records,
                                                                int max_tasks, int max_agents, float* tf, uint8_t* tm,
                                                                float* af, uint8_t* am, float* ev, int32_t* ids, int n,
-                                                               int af_dim) {
+                                                               int af_dim, int raw, float* ctx) {
   __shared__ int16_t cols[4][MUAV_MAX_TASK_CAP + 2];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e = blockIdx.x * 4 + w;
@@ -371,10 +371,11 @@ __global__ void __launch_bounds__(128) muav_tokens_pair_kernel(const __grid_cons
   View V;
   V.base = (char*)records + (size_t)e * L.record_bytes;
   V.L = &L;
-  tokens_pair_env(V, cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * 13, tm + (size_t)e * max_tasks,
-                  af + (size_t)e * max_agents * af_dim, am + (size_t)e * max_agents,
+  const int TD = raw ? 9 : 13, AD = raw ? 11 : af_dim, CD = raw ? 1 : 8;
+  tokens_pair_env(V, cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * TD, tm + (size_t)e * max_tasks,
+                  af + (size_t)e * max_agents * AD, am + (size_t)e * max_agents,
                   ev ? ev + (size_t)e * max_agents * max_tasks : nullptr, ids + (size_t)e * max_tasks, cols[w], lane, 32,
-                  af_dim);
+                  af_dim, raw, ctx ? ctx + (size_t)e * CD : nullptr);
 }
 
 __global__ void __launch_bounds__(128) muav_tokens_escort_kernel(const __grid_constant__ muav_config cfg,
@@ -690,7 +691,23 @@ int muav_tokens_pair(const muav_config* cfg, const void* d_records, int max_task
   if (max_tasks > MUAV_MAX_TASK_CAP) return -22;
   muav_tokens_pair_kernel<<<(n_envs + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
       *cfg, L, (const char*)d_records, max_tasks, max_agents, d_task_feats, d_task_mask, d_agent_feats, d_agent_mask,
-      d_edge_valid, d_task_ids, n_envs, 12);
+      d_edge_valid, d_task_ids, n_envs, 12, 0, nullptr);
+  return cuda_rc(cudaGetLastError());
+}
+
+int muav_tokens_context(const muav_config* cfg, const void* d_records, int max_tasks, int max_agents, int raw,
+                        float* d_task_feats, uint8_t* d_task_mask, float* d_agent_feats, uint8_t* d_agent_mask,
+                        float* d_edge_valid, int32_t* d_task_ids, float* d_context, int n_envs, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (n_envs <= 0) return n_envs == 0 ? 0 : -22;
+  if (max_tasks < 1 || max_agents < 1 || max_tasks > MUAV_MAX_TASK_CAP) return -22;
+  if (!d_task_feats || !d_task_mask || !d_agent_feats || !d_agent_mask || !d_edge_valid || !d_task_ids || !d_context)
+    return -22;
+  Layout L = make_layout(*cfg);
+  muav_tokens_pair_kernel<<<(n_envs + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
+      *cfg, L, (const char*)d_records, max_tasks, max_agents, d_task_feats, d_task_mask, d_agent_feats, d_agent_mask,
+      d_edge_valid, d_task_ids, n_envs, 12, raw ? 1 : 0, d_context);
   return cuda_rc(cudaGetLastError());
 }
 
@@ -704,7 +721,7 @@ int muav_tokens_commit(const muav_config* cfg, const void* d_records, int max_ta
   Layout L = make_layout(*cfg);
   muav_tokens_pair_kernel<<<(n_envs + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
       *cfg, L, (const char*)d_records, max_tasks, max_agents, d_task_feats, d_task_mask, d_agent_feats13, d_agent_mask,
-      nullptr, d_task_ids, n_envs, 13);
+      nullptr, d_task_ids, n_envs, 13, 0, nullptr);
   return cuda_rc(cudaGetLastError());
 }
 

@@ -29,9 +29,13 @@ MUAV_HD inline bool view_known(const View& V, int a, int k) {
 // (int16 scratch, >= max_tasks entries + 2), then columns and agent rows are independent.
 // af_dim = 12 (Att-Pair / Att-RAH agent features) or 13: enrich_commit_tokens (AttentionCommit.py:49-62) appends the
 // remaining commit-lock fraction min(max(commit_until - t, 0) / max(commit_horizon or 25, 1), 1); ev may be null.
+// raw != 0: per-entity attributes only (build_att_tokens(raw=True), AttentionRAH.py:86-97,140-146): task_feats [.,9],
+// agent_feats [.,11].  ctx != NULL: build_context_summary (ContextPairHybrid.py:33-70), 8 floats (1 when raw).
 MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max_tasks, int max_agents, float* tf,
                                     uint8_t* tm, float* af, uint8_t* am, float* ev, int32_t* ids, int16_t* cols,
-                                    int lane, int nlanes, int af_dim = 12) {
+                                    int lane, int nlanes, int af_dim = 12, int raw = 0, float* ctx = nullptr) {
+  const int TD = raw ? 9 : 13;
+  if (raw) af_dim = 11;
   const int A = V.L->D.A, TC = V.L->D.TC;
   const int n = V.hi()[HI_N_TASKS];
   const int t = V.hi()[HI_T];
@@ -58,13 +62,43 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
   int n_live = 0;
   for (int a = 0; a < A; ++a) n_live += V.a_state()[a] != -1;
   const int n_agents = n_live > 1 ? n_live : 1;
+  // ---- context summary (ContextPairHybrid.py:33-70)
+  if (ctx && lane == 0) {
+    const double tfrac = (double)t / (double)horizon;
+    if (raw) {
+      ctx[0] = (float)tfrac;
+    } else {
+      int n_urgent = 0, left = 0, right = 0, free_a = 0, fighters = 0;
+      for (int j = 0; j < ncol; ++j) {
+        const int k = cols[j];
+        if (urgency_of(V, k, t) >= urgent_thr && V.k_deadline()[k] >= 0) ++n_urgent;
+        if (V.k_posx()[k] < mid_x) ++left;
+        else ++right;
+      }
+      for (int a = 0; a < A; ++a) {
+        if (V.a_state()[a] == -1) continue;
+        if (V.a_qlen()[a] == 0) ++free_a;
+        if (is_fighter(V.a_type()[a])) ++fighters;
+      }
+      const double nt = (double)(ncol > 1 ? ncol : 1), na = (double)n_agents;
+      const int diff = left > right ? left - right : right - left;
+      ctx[0] = (float)((double)n_urgent / nt);
+      ctx[1] = (float)(dmin((double)ncol / na, 4.0) / 4.0);
+      ctx[2] = (float)((double)free_a / na);
+      ctx[3] = (float)((double)fighters / na);
+      ctx[4] = (float)((double)left / nt);
+      ctx[5] = (float)((double)right / nt);
+      ctx[6] = (float)((double)diff / nt);
+      ctx[7] = (float)tfrac;
+    }
+  }
   // ---- task columns
   for (int j = lane; j < max_tasks; j += nlanes) {
-    float* f = tf + j * 13;
+    float* f = tf + j * TD;
     if (j >= ncol) {
       tm[j] = 1;
       ids[j] = 0;
-      for (int c = 0; c < 13; ++c) f[c] = 0.0f;
+      for (int c = 0; c < TD; ++c) f[c] = 0.0f;
       continue;
     }
     const int k = cols[j];
@@ -92,13 +126,22 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
     f[3] = ti == TT_ATT ? 1.0f : 0.0f;
     f[4] = ti == TT_REC ? 1.0f : 0.0f;
     f[5] = ti == TT_INT ? 1.0f : 0.0f;
-    f[6] = (float)urg;
-    f[7] = (float)scar;
-    f[8] = (float)dmin(rem / 4.0, 1.0);
-    f[9] = (float)is_dyn;
-    f[10] = (float)dmin(n_know / (double)n_agents, 1.0);
-    f[11] = (float)dmin(d_spec / mc, 1.0);
-    f[12] = V.k_posx()[k] < mid_x ? 0.0f : 1.0f;
+    if (raw) {
+      const int dl = V.k_deadline()[k];
+      int remt = dl - t;
+      if (remt < 0) remt = 0;
+      f[6] = dl < 0 ? 1.0f : (float)dmin((double)remt / (double)horizon, 1.0);
+      f[7] = (float)dmin(rem / 4.0, 1.0);
+      f[8] = (float)is_dyn;
+    } else {
+      f[6] = (float)urg;
+      f[7] = (float)scar;
+      f[8] = (float)dmin(rem / 4.0, 1.0);
+      f[9] = (float)is_dyn;
+      f[10] = (float)dmin(n_know / (double)n_agents, 1.0);
+      f[11] = (float)dmin(d_spec / mc, 1.0);
+      f[12] = V.k_posx()[k] < mid_x ? 0.0f : 1.0f;
+    }
     tm[j] = 0;
     ids[j] = k + 1;
   }
@@ -140,9 +183,13 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
     f[7] = (float)dmin(cap_rec / 2.0, 1.0);
     f[8] = (float)((double)V.a_state()[a] / 5.0);
     f[9] = (float)((double)t / (double)horizon);
-    f[10] = (float)dmin((double)n_known_urgent / (double)(n_open_all > 1 ? n_open_all : 1), 1.0);
-    f[11] = at == UT_F2 ? 1.0f : 0.0f;
-    if (af_dim > 12) {
+    if (raw) {
+      f[10] = at == UT_F2 ? 1.0f : 0.0f;
+    } else {
+      f[10] = (float)dmin((double)n_known_urgent / (double)(n_open_all > 1 ? n_open_all : 1), 1.0);
+      f[11] = at == UT_F2 ? 1.0f : 0.0f;
+    }
+    if (!raw && af_dim > 12) {
       const int hz = C.commit_horizon != 0 ? C.commit_horizon : 25;
       const double rem = dmax((double)V.a_commit()[a] - (double)t, 0.0);
       f[12] = (float)dmin(rem / (double)(hz > 1 ? hz : 1), 1.0);

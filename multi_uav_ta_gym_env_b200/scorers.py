@@ -84,6 +84,96 @@ class MLPPairNet(nn.Module):
         return logits, value
 
 
+CONTEXT_DIM = 8  # build_context_summary (ContextPairHybrid.py:23-31); 1 in raw mode
+
+
+class AttContextPairNet(nn.Module):
+    """AttContextPairNet (ContextPairHybrid.py:81-151): Att-Pair plus a context vector (projected summary + pooled encoder
+    output) appended to every pair."""
+
+    def __init__(self, max_tasks=32, max_agents=16, d_model=64, nhead=4, n_layers=2, dropout=0.1,
+                 task_feat_dim=TASK_FEAT_DIM, agent_feat_dim=AGENT_FEAT_DIM, context_dim=CONTEXT_DIM):
+        super().__init__()
+        self.max_tasks, self.max_agents, self.d_model = max_tasks, max_agents, d_model
+        self.task_proj = nn.Linear(task_feat_dim, d_model)
+        self.agent_proj = nn.Linear(agent_feat_dim, d_model)
+        self.ctx_proj = nn.Linear(context_dim, d_model)
+        self.type_embed = nn.Embedding(2, d_model)
+        layer = nn.TransformerEncoderLayer(d_model=d_model, nhead=nhead, dim_feedforward=d_model * 2,
+                                           batch_first=True, dropout=dropout)
+        self.self_encoder = nn.TransformerEncoder(layer, num_layers=max(1, n_layers - 1))
+        self.cross_a2t = nn.MultiheadAttention(d_model, nhead, dropout=dropout, batch_first=True)
+        self.cross_t2a = nn.MultiheadAttention(d_model, nhead, dropout=dropout, batch_first=True)
+        self.pair_head = nn.Sequential(nn.Linear(d_model * 4, d_model), nn.ReLU(), nn.Linear(d_model, d_model // 2),
+                                       nn.ReLU(), nn.Linear(d_model // 2, 1))
+        self.value_head = nn.Sequential(nn.Linear(d_model * 2, d_model), nn.ReLU(), nn.Linear(d_model, 1))
+
+    def forward(self, task_feats, task_mask, agent_feats, agent_mask, context):
+        t_emb = self.task_proj(task_feats) + self.type_embed.weight[1]
+        a_emb = self.agent_proj(agent_feats) + self.type_embed.weight[0]
+        tokens = torch.cat([a_emb, t_emb], dim=1)
+        pad_mask = torch.cat([agent_mask, task_mask], dim=1)
+        h = self.self_encoder(tokens, src_key_padding_mask=pad_mask)
+        a_h = h[:, : self.max_agents, :]
+        t_h = h[:, self.max_agents:, :]
+        a_ctx, _ = self.cross_a2t(a_h, t_h, t_h, key_padding_mask=task_mask, need_weights=False)
+        t_ctx, _ = self.cross_t2a(t_h, a_h, a_h, key_padding_mask=agent_mask, need_weights=False)
+        a_h = a_h + a_ctx
+        t_h = t_h + t_ctx
+        valid = (~pad_mask).unsqueeze(-1).float()
+        pooled = (h * valid).sum(dim=1) / valid.sum(dim=1).clamp(min=1.0)
+        ctx = self.ctx_proj(context) + pooled
+        ctx_exp = ctx.unsqueeze(1).unsqueeze(2).expand(-1, self.max_agents, self.max_tasks, -1)
+        a_exp = a_h.unsqueeze(2).expand(-1, -1, self.max_tasks, -1)
+        t_exp = t_h.unsqueeze(1).expand(-1, self.max_agents, -1, -1)
+        logits = self.pair_head(torch.cat([a_exp, t_exp, a_exp * t_exp, ctx_exp], dim=-1)).squeeze(-1)
+        logits = logits.masked_fill(agent_mask.unsqueeze(2), -1e9)
+        logits = logits.masked_fill(task_mask.unsqueeze(1), -1e9)
+        value = self.value_head(torch.cat([pooled, ctx], dim=-1)).squeeze(-1)
+        return logits, value
+
+
+class MLPContextPairNet(nn.Module):
+    """MLPContextPairNet (ContextPairHybrid.py:154-207): the matched control without attention."""
+
+    def __init__(self, max_tasks=32, max_agents=16, hidden=192, d_model=64, task_feat_dim=TASK_FEAT_DIM,
+                 agent_feat_dim=AGENT_FEAT_DIM, context_dim=CONTEXT_DIM, **_):
+        super().__init__()
+        self.max_tasks, self.max_agents = max_tasks, max_agents
+        in_pair = task_feat_dim + agent_feat_dim + task_feat_dim + agent_feat_dim + context_dim
+        self.ctx_mlp = nn.Sequential(nn.Linear(task_feat_dim + agent_feat_dim + context_dim, hidden), nn.ReLU(),
+                                     nn.Linear(hidden, hidden), nn.ReLU())
+        self.pair_mlp = nn.Sequential(nn.Linear(in_pair, hidden), nn.ReLU(), nn.Linear(hidden, hidden), nn.ReLU(),
+                                      nn.Linear(hidden, 1))
+        self.value_mlp = nn.Sequential(nn.Linear(hidden, hidden // 2), nn.ReLU(), nn.Linear(hidden // 2, 1))
+
+    def forward(self, task_feats, task_mask, agent_feats, agent_mask, context):
+        am = (~agent_mask).float().unsqueeze(-1)
+        tm = (~task_mask).float().unsqueeze(-1)
+        a_pool = (agent_feats * am).sum(1) / am.sum(1).clamp(min=1.0)
+        t_pool = (task_feats * tm).sum(1) / tm.sum(1).clamp(min=1.0)
+        ctx_h = self.ctx_mlp(torch.cat([a_pool, t_pool, context], dim=-1))
+        b, a, _ = agent_feats.shape
+        t = task_feats.size(1)
+        a_exp = agent_feats.unsqueeze(2).expand(-1, -1, t, -1)
+        t_exp = task_feats.unsqueeze(1).expand(-1, a, -1, -1)
+        a_p = a_pool.unsqueeze(1).unsqueeze(2).expand(-1, a, t, -1)
+        t_p = t_pool.unsqueeze(1).unsqueeze(2).expand(-1, a, t, -1)
+        c_exp = context.unsqueeze(1).unsqueeze(2).expand(-1, a, t, -1)
+        logits = self.pair_mlp(torch.cat([a_exp, t_exp, a_p, t_p, c_exp], dim=-1)).squeeze(-1)
+        logits = logits.masked_fill(agent_mask.unsqueeze(2), -1e9)
+        logits = logits.masked_fill(task_mask.unsqueeze(1), -1e9)
+        return logits, self.value_mlp(ctx_h).squeeze(-1)
+
+
+@torch.no_grad()
+def context_pair_scores(net: nn.Module, tok: dict, score_clamp: float = SCORE_CLAMP) -> torch.Tensor:
+    """tokens (BatchedMultiUAVEnv.tokens_context) -> edge scores f32 [B, max_agents, max_tasks]: ContextPairHybrid.act
+    without exploration (ContextPairHybrid.py:235-246); feed to AllocSpec.pair_hybrid()."""
+    logits, _ = net(tok["task_feats"], tok["task_mask"], tok["agent_feats"], tok["agent_mask"], tok["context"])
+    return torch.tanh(logits) * score_clamp * tok["edge_valid"]
+
+
 TASK_FEAT_DIM_E = 22   # build_escort_tokens task features (AttentionEscort.py:23)
 AGENT_FEAT_DIM_E = 16  # build_escort_tokens agent features (AttentionEscort.py:25)
 AGENT_FEAT_DIM_C = AGENT_FEAT_DIM + 1  # enrich_commit_tokens (AttentionCommit.py:65)

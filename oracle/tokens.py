@@ -7,6 +7,8 @@ Restates, over the oracle's flat state (oracle/sim.py):
   edge_score_dict + plan(scores=)  TaskAllocation/Hybrid/PairCostHybrid.py:280-291, 308-328
   hybrid replan cadence            experiments/wps_eval.py:64-73
   _generate_observations / get_task_info / _event_flag_vector   mUAV_TA/DroneEnv.py:365-492
+  build_att_tokens (raw=True), build_context_summary / build_context_pair_tokens
+                                   AttentionRAH.py:86-97,140-146, TaskAllocation/Hybrid/ContextPairHybrid.py:33-78
   _open_tasks_residual / _threat_stats / _task_priority_key / build_escort_tokens
                                    TaskAllocation/Hybrid/AttentionEscort.py:31-241
 """
@@ -30,7 +32,8 @@ def hybrid_should_replan(env, events, interval=15):
     return env.t == 0 or env.t % interval == 0 or any(ev[0] in (EV_RESET, EV_THREAT, EV_FAIL) for ev in events)
 
 
-def build_pair_tokens(env, max_tasks=32, max_agents=16):
+def build_pair_tokens(env, max_tasks=32, max_agents=16, raw=False):
+    """raw=True: per-entity attributes only (task 9 / agent 11 features, AttentionRAH.py:86-97,140-146)."""
     A = env.n_agents
     T = len(env.k_pos)
     max_coord = float(env.max_coord)
@@ -42,7 +45,7 @@ def build_pair_tokens(env, max_tasks=32, max_agents=16):
     specialists = [a for a in live if UAV_TYPES[env.a_type[a]] == "F2"]
     open_tasks = [k for k in range(T)
                   if env.k_status[k] != 2 and env.k_alloc[k][env.k_type[k]] < env.k_cur[k][env.k_type[k]]]
-    task_feats = np.zeros((max_tasks, 13), dtype=np.float32)
+    task_feats = np.zeros((max_tasks, 9 if raw else 13), dtype=np.float32)
     task_mask = np.ones(max_tasks, dtype=bool)
     task_ids = []
     thr = 1.0 - 12.0 / 40.0
@@ -64,15 +67,24 @@ def build_pair_tokens(env, max_tasks=32, max_agents=16):
         else:
             d_spec = max_coord
         region = 0.0 if float(tp[0]) < mid_x else 1.0
-        task_feats[i] = [
-            float(tp[0]) / max_coord, float(tp[1]) / max_coord, float(ti) / 8.0,
-            1.0 if ti == T_ATT else 0.0, 1.0 if ti == T_REC else 0.0, 1.0 if ti == T_INT else 0.0,
-            urg, scar, min(rem / 4.0, 1.0), is_dynamic, min(n_know / max(n_agents, 1), 1.0),
-            min(d_spec / max_coord, 1.0), region,
-        ]
+        if raw:
+            dl = env.k_deadline[k]
+            t_left = 1.0 if dl < 0 else min(max(dl - env.t, 0) / horizon, 1.0)
+            task_feats[i] = [
+                float(tp[0]) / max_coord, float(tp[1]) / max_coord, float(ti) / 8.0,
+                1.0 if ti == T_ATT else 0.0, 1.0 if ti == T_REC else 0.0, 1.0 if ti == T_INT else 0.0,
+                t_left, min(rem / 4.0, 1.0), is_dynamic,
+            ]
+        else:
+            task_feats[i] = [
+                float(tp[0]) / max_coord, float(tp[1]) / max_coord, float(ti) / 8.0,
+                1.0 if ti == T_ATT else 0.0, 1.0 if ti == T_REC else 0.0, 1.0 if ti == T_INT else 0.0,
+                urg, scar, min(rem / 4.0, 1.0), is_dynamic, min(n_know / max(n_agents, 1), 1.0),
+                min(d_spec / max_coord, 1.0), region,
+            ]
         task_mask[i] = False
         task_ids.append(k + 1)
-    agent_feats = np.zeros((max_agents, 12), dtype=np.float32)
+    agent_feats = np.zeros((max_agents, 11 if raw else 12), dtype=np.float32)
     agent_mask = np.ones(max_agents, dtype=bool)
     for i, a in enumerate(live[:max_agents]):
         caps = env.a_caps[a]
@@ -83,14 +95,17 @@ def build_pair_tokens(env, max_tasks=32, max_agents=16):
                 continue
             if urgency(env, k, env.t) >= thr and env.k_deadline[k] >= 0:
                 n_known_urgent += 1
-        agent_feats[i] = [
+        base = [
             float(env.a_pos[a][0]) / max_coord, float(env.a_pos[a][1]) / max_coord,
             1.0 if atype.startswith("F") else 0.0, 1.0 if atype.startswith("R") else 0.0,
             1.0 if not env.a_queue[a] else 0.0,
             min(float(caps[2]) / 2.0, 1.0), min(float(caps[3]) / 2.0, 1.0), min(float(caps[1]) / 2.0, 1.0),
             float(env.a_state[a]) / 5.0, float(env.t) / horizon,
-            min(n_known_urgent / max(len(open_tasks), 1), 1.0), 1.0 if atype == "F2" else 0.0,
         ]
+        if raw:
+            agent_feats[i] = base + [1.0 if atype == "F2" else 0.0]
+        else:
+            agent_feats[i] = base + [min(n_known_urgent / max(len(open_tasks), 1), 1.0), 1.0 if atype == "F2" else 0.0]
         agent_mask[i] = False
     kept = open_tasks[:max_tasks]
     edge_valid = np.zeros((max_agents, max_tasks), dtype=np.float32)
@@ -108,6 +123,35 @@ def build_pair_tokens(env, max_tasks=32, max_agents=16):
     ids[: len(task_ids)] = task_ids
     return {"task_feats": task_feats, "task_mask": task_mask, "agent_feats": agent_feats, "agent_mask": agent_mask,
             "edge_valid": edge_valid, "task_ids": ids, "open_tasks": [k + 1 for k in kept], "live": live, "vis": vis}
+
+
+def build_context_pair_tokens(env, max_tasks=32, max_agents=16, raw=False):
+    """build_context_pair_tokens (ContextPairHybrid.py:73-78): pair tokens + the team / situation vector of
+    build_context_summary (:33-70)."""
+    tok = build_pair_tokens(env, max_tasks, max_agents, raw=raw)
+    horizon = max(env.max_time_steps, 1)
+    if raw:
+        tok["context"] = np.asarray([float(env.t) / horizon], dtype=np.float32)
+        return tok
+    mid_x = float(env.area_width) * 0.5
+    live = tok["live"]
+    tasks = [tid - 1 for tid in tok["open_tasks"]]
+    n_agents = max(len(live), 1)
+    n_tasks = max(len(tasks), 1)
+    n_urgent = left = right = 0
+    for k in tasks:
+        if urgency(env, k, env.t) >= (1.0 - 12.0 / 40.0) and env.k_deadline[k] >= 0:
+            n_urgent += 1
+        if float(env.k_pos[k][0]) < mid_x:
+            left += 1
+        else:
+            right += 1
+    free = sum(1 for a in live if not env.a_queue[a])
+    fighters = sum(1 for a in live if UAV_TYPES[env.a_type[a]].startswith("F"))
+    tok["context"] = np.asarray([
+        n_urgent / n_tasks, min(len(tasks) / float(n_agents), 4.0) / 4.0, free / n_agents, fighters / n_agents,
+        left / n_tasks, right / n_tasks, abs(left - right) / n_tasks, float(env.t) / horizon], dtype=np.float32)
+    return tok
 
 
 def commit_tokens(env, max_tasks=32, max_agents=16):

@@ -19,6 +19,9 @@ Drivers (all restate the reference's own episode loops):
   urgency_commit    UrgencyCommit.plan (AttentionCommit.py:310-357) under the hybrid cadence wps_eval.py:64-73
   urgency_coalition UrgencyCoalition.plan (AttentionEscort.py:720-767) under escort_eval.py:52-58, interval 12
   urgency_pair      UrgencyPair.plan (PairCostHybrid.py:520-550) under the hybrid cadence wps_eval.py:64-73
+  context_injected  ContextPairHybrid.plan(scores=...) (ContextPairHybrid.py:210-233 over PairCostHybrid.plan) with injected edge
+                    scores; the reference's build_context_pair_tokens tensors (raw=False and raw=True) of every 4th plan
+                    are stored too
   att_commit_injected  AttentionCommit.plan (AttentionCommit.py:260-300) with the network replaced by injected
                     (priority, commit) vectors, hybrid cadence wps_eval.py:64-73
   att_escort_injected  AttentionEscort.plan (AttentionEscort.py:519-524: build_escort_tokens -> act -> _plan_from_scores)
@@ -96,6 +99,12 @@ def tok_dump(tok):
             for k in ("task_feats", "task_mask", "agent_feats", "agent_mask", "edge_valid", "task_ids") if k in tok}
 
 
+def ctx_dump(tok):
+    d = tok_dump(tok)
+    d["context"] = np.asarray(tok["context"]).astype(np.float64).tolist()
+    return d
+
+
 def hybrid_should_replan(env, events, interval=15):
     return (env.time_steps == 0 or env.time_steps % interval == 0
             or any(ev[0] in ("Reset_Allocation", "New_Threat", "Agent_Fail") for ev in events))
@@ -126,6 +135,9 @@ def run_episode(case, seed, driver, overrides=None):
     elif driver == "urgency_pair":
         from TaskAllocation.Hybrid.PairCostHybrid import UrgencyPair
         planner = UrgencyPair()
+    elif driver == "context_injected":
+        from TaskAllocation.Hybrid.ContextPairHybrid import ContextPairHybrid, build_context_pair_tokens
+        pair = ContextPairHybrid(use_attention=False, device="cpu")
     elif driver == "att_commit_injected":
         import torch
         from TaskAllocation.Hybrid.AttentionCommit import AttentionCommit
@@ -146,6 +158,7 @@ def run_episode(case, seed, driver, overrides=None):
         events = list(info.get("events") or []) if isinstance(info, dict) else []
         pairs = []
         tok_rec = None
+        ctx_rec = None
         if driver in ("local_hungarian", "coalition"):
             res = hung.allocate_tasks(env.get_live_agents(), ref_open_tasks(env), time_step=env.time_steps,
                                       events=events, agent_known_ids=env.agent_visibility_map())
@@ -168,6 +181,14 @@ def run_episode(case, seed, driver, overrides=None):
         elif driver == "urgency_pair":
             if hybrid_should_replan(env, events):
                 pairs = planner.plan(env, hung, events=events, force=True)[0]
+        elif driver == "context_injected":
+            if hybrid_should_replan(env, events):
+                sc = injected_scores(seed, env.time_steps, pair.max_agents, pair.max_tasks)
+                if n_plans % 4 == 0:
+                    ctx_rec = {"tok": ctx_dump(build_context_pair_tokens(env, 32, 16, raw=False)),
+                               "raw": ctx_dump(build_context_pair_tokens(env, 32, 16, raw=True))}
+                n_plans += 1
+                pairs = pair.plan(env, hung, events=events, explore=False, force=True, scores=sc)[0]
         elif driver == "att_commit_injected":
             if hybrid_should_replan(env, events):
                 pv, cv = injected_commit_vectors(seed, env.time_steps)
@@ -212,6 +233,9 @@ def run_episode(case, seed, driver, overrides=None):
         })
         if tok_rec is not None:
             ep["steps"][-1]["escort_tokens"] = tok_rec["tok"]
+        if ctx_rec is not None:
+            ep["steps"][-1]["context_tokens"] = ctx_rec["tok"]
+            ep["steps"][-1]["context_tokens_raw"] = ctx_rec["raw"]
         if all(term.values()) or all(trunc.values()):
             break
     m = info["metrics"]
@@ -238,6 +262,7 @@ PLAN = [
     ("wps_escort_urgency", "WPS_escort", "urgency_coalition", range(0, 6), None),
     ("wps_hard_obstacles", "WPS_hard", "local_hungarian", range(0, 4), {"num_obstacles": 4}),
     ("wps_hard_urgency_pair", "WPS_hard", "urgency_pair", range(0, 6), None),
+    ("wps_attn_context", "WPS_attn", "context_injected", range(0, 4), None),
     ("wps_commit_attcommit", "WPS_commit", "att_commit_injected", range(0, 6), None),
     ("wps_escort_attescort", "WPS_escort", "att_escort_injected", range(0, 6), None),
 ]

@@ -58,7 +58,22 @@ def escort_scores_from_logits(logits, edge_valid, agent_mask, task_mask):
     return scores.astype(np.float32)
 
 
+def assert_tokens_equal_reference(ref_tok, tok, e=None, what=""):
+    """ref_tok: token dump of the reference stored in a fixture; tok: dict of arrays ([E, ...] when e is given)."""
+    pick = (lambda v: v[e]) if e is not None else (lambda v: v)
+    for k in ("task_feats", "agent_feats", "edge_valid", "context"):
+        if k in ref_tok:
+            assert np.array_equal(np.asarray(ref_tok[k], np.float32), np.asarray(pick(tok[k]), np.float32)), (what, k)
+    for k in ("task_mask", "agent_mask"):
+        assert [int(x) for x in pick(tok[k])] == ref_tok[k], (what, k)
+    nk = len(ref_tok["task_ids"])
+    ids = pick(tok["task_ids"])
+    assert [int(x) for x in ids[:nk]] == ref_tok["task_ids"] and not np.asarray(ids[nk:]).any(), (what, "task_ids")
+
+
 def alloc_opts_for(driver):
+    if driver == "context_injected":
+        driver = "pair_injected"   # ContextPairHybrid plans exactly like PairCostHybrid (it only adds the context vector)
     O = _lib.MuavAllocOpts()
     O.max_coord = 1200.0
     if driver in ("local_hungarian", "coalition", "global_hungarian"):
@@ -107,6 +122,8 @@ class HostCheck:
         d.hostcheck_step.restype = C.c_int
         d.hostcheck_step.argtypes = [C.POINTER(_lib.MuavConfig), P, P, P, C.POINTER(_lib.MuavAllocOpts),
                                      C.POINTER(_lib.MuavStepOut), C.c_int, C.c_int]
+        d.hostcheck_tokens_context.restype = C.c_int
+        d.hostcheck_tokens_context.argtypes = [C.POINTER(_lib.MuavConfig), P, C.c_int, C.c_int, C.c_int, P, P, P, P, P, P, P, C.c_int]
         d.hostcheck_tokens_escort.restype = C.c_int
         d.hostcheck_tokens_escort.argtypes = [C.POINTER(_lib.MuavConfig), P, C.c_int, C.c_int, P, P, P, P, P, P, P, C.c_int]
         d.hostcheck_lsap.restype = C.c_int
@@ -173,6 +190,19 @@ class HostEnv:
         rc = self.lib.dll.hostcheck_step(C.byref(self.cfg), self.rec.ctypes.data, self.tapes.ctypes.data, None,
                                          C.byref(O), C.byref(self.out), self.E, n_steps)
         assert rc == 0
+
+    def tokens_context(self, max_tasks=32, max_agents=16, raw=False):
+        E = self.E
+        tok = {"task_feats": np.zeros((E, max_tasks, 9 if raw else 13), np.float32), "task_mask": np.zeros((E, max_tasks), np.uint8),
+               "agent_feats": np.zeros((E, max_agents, 11 if raw else 12), np.float32),
+               "agent_mask": np.zeros((E, max_agents), np.uint8), "edge_valid": np.zeros((E, max_agents, max_tasks), np.float32),
+               "task_ids": np.zeros((E, max_tasks), np.int32), "context": np.zeros((E, 1 if raw else 8), np.float32)}
+        rc = self.lib.dll.hostcheck_tokens_context(
+            C.byref(self.cfg), self.rec.ctypes.data, max_tasks, max_agents, int(raw), tok["task_feats"].ctypes.data,
+            tok["task_mask"].ctypes.data, tok["agent_feats"].ctypes.data, tok["agent_mask"].ctypes.data,
+            tok["edge_valid"].ctypes.data, tok["task_ids"].ctypes.data, tok["context"].ctypes.data, E)
+        assert rc == 0
+        return tok
 
     def tokens_escort(self, max_tasks=48, max_agents=16):
         E = self.E

@@ -140,6 +140,23 @@ int hostcheck_tokens_pair(const muav_config* cfg, const void* records, int max_t
   return 0;
 }
 
+int hostcheck_tokens_context(const muav_config* cfg, const void* records, int max_tasks, int max_agents, int raw, float* tf,
+                             uint8_t* tm, float* af, uint8_t* am, float* ev, int32_t* ids, float* ctx, int n_envs) {
+  Layout L = make_layout(*cfg);
+  int16_t* cols = (int16_t*)malloc(sizeof(int16_t) * (max_tasks + 2));
+  const int TD = raw ? 9 : 13, AD = raw ? 11 : 12, CD = raw ? 1 : 8;
+  for (int e = 0; e < n_envs; ++e) {
+    View V;
+    V.base = (char*)records + (size_t)e * L.record_bytes;
+    V.L = &L;
+    tokens_pair_env(V, *cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * TD, tm + (size_t)e * max_tasks,
+                    af + (size_t)e * max_agents * AD, am + (size_t)e * max_agents, ev + (size_t)e * max_agents * max_tasks,
+                    ids + (size_t)e * max_tasks, cols, 0, 1, 12, raw, ctx + (size_t)e * CD);
+  }
+  free(cols);
+  return 0;
+}
+
 int hostcheck_tokens_escort(const muav_config* cfg, const void* records, int max_tasks, int max_agents, float* tf,
                             uint8_t* tm, float* af, uint8_t* am, float* ev, int32_t* ids, int32_t* order, int n_envs) {
   Layout L = make_layout(*cfg);

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (escort_scores_from_logits, golden_config, injected_commit_vectors, injected_logits, injected_scores,
+from helpers import (assert_tokens_equal_reference, escort_scores_from_logits, golden_config, injected_commit_vectors, injected_logits, injected_scores,
                      load_golden)
 import refsnap
 
@@ -21,7 +21,7 @@ STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit
               "wps_attn_xl_local", "wps_hard_single_task"]
 # planner fixtures mutate commit_until between steps: they are replayed through the fused planner only
 ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
-    "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair"]
+    "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair", "wps_attn_context"]
 
 
 def make_env(cfg, seeds, **kw):
@@ -36,7 +36,7 @@ def spec_for(driver):
     return {"local_hungarian": AllocSpec.local_hungarian(20), "coalition": AllocSpec.coalition_hungarian(12),
             "global_hungarian": AllocSpec.global_hungarian(20), "pair_injected": AllocSpec.pair_hybrid(15),
             "urgency_commit": AllocSpec.urgency_commit(15), "urgency_coalition": AllocSpec.urgency_coalition(12),
-            "urgency_pair": AllocSpec.urgency_pair(15), "att_commit_injected": AllocSpec.att_commit(15), "att_escort_injected": AllocSpec.att_escort(12)}[driver]
+            "context_injected": AllocSpec.pair_hybrid(15), "urgency_pair": AllocSpec.urgency_pair(15), "att_commit_injected": AllocSpec.att_commit(15), "att_escort_injected": AllocSpec.att_escort(12)}[driver]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)
@@ -83,8 +83,15 @@ def test_cuda_fused_allocator_matches_reference_golden(name):
     spec = spec_for(drv)
     for t in range(len(eps[0]["steps"])):
         scores = None
-        if drv == "pair_injected":
+        if drv in ("pair_injected", "context_injected"):
             scores = torch.from_numpy(np.stack([injected_scores(ep["seed"], t, 16, 32) for ep in eps]))
+            if any("context_tokens" in ep["steps"][t] for ep in eps):
+                tok = {k: v.cpu().numpy() for k, v in env.tokens_context(32, 16, False).items()}
+                raw = {k: v.cpu().numpy() for k, v in env.tokens_context(32, 16, True).items()}
+                for e, ep in enumerate(eps):
+                    if "context_tokens" in ep["steps"][t]:   # the reference's build_context_pair_tokens at this step
+                        assert_tokens_equal_reference(ep["steps"][t]["context_tokens"], tok, e, (ep["seed"], t))
+                        assert_tokens_equal_reference(ep["steps"][t]["context_tokens_raw"], raw, e, (ep["seed"], t, "raw"))
         kw = {}
         if drv == "att_commit_injected":
             vec = [injected_commit_vectors(ep["seed"], t) for ep in eps]
@@ -721,3 +728,40 @@ def test_full_batch_scored_episode_has_no_capacity_overflow():
                 assert refsnap.digest(env.snapshot(e)) == refsnap.digest(oracles[i].snapshot()), (t, e)
     flags = env.error_flags()
     assert int(flags.abs().max().item()) == 0, (flags != 0).nonzero().flatten()[:8].tolist()
+
+
+def test_context_pair_pipeline_matches_oracle():
+    """The paper's primary method shape (WPS_attn, Att-ContextPair): tokens_context -> AttContextPairNet (random init) ->
+    context_pair_scores -> hybrid Local-Hungarian on the device, against the oracle fed with the same scores."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+    from multi_uav_ta_gym_env_b200.scorers import AttContextPairNet, context_pair_scores
+    from oracle.hungarian import OracleHungarian, apply_assign
+    from oracle import tokens as otok
+    from oracle.sim import OracleEnv
+
+    cfg = wps_config("WPS_attn")
+    seeds = [41, 42, 43]
+    env = make_env(cfg, seeds)
+    torch.manual_seed(0)
+    net = AttContextPairNet().cuda().eval()
+    oracles = [OracleEnv(cfg).reset(s) for s in seeds]
+    hungs = [OracleHungarian(20, 1200.0) for _ in seeds]
+    spec = AllocSpec.pair_hybrid(15)
+    for t in range(150):
+        tok = env.tokens_context(32, 16)
+        scores = context_pair_scores(net, tok)
+        host = {k: v.cpu().numpy() for k, v in tok.items()}
+        sc = scores.cpu().numpy()
+        for e, o in enumerate(oracles):
+            pairs = []
+            if otok.hybrid_should_replan(o, o.last_events, 15):
+                want = otok.build_context_pair_tokens(o, 32, 16)
+                for k in ("task_feats", "task_mask", "agent_feats", "agent_mask", "edge_valid", "task_ids", "context"):
+                    assert np.array_equal(host[k][e], want[k]), (t, e, k)
+                pairs = otok.pair_plan(o, hungs[e], sc[e])
+            o.step(apply_assign(o, pairs))
+        env.step_allocated(spec, 1, edge_scores=scores)
+        recs = env.records.cpu().numpy()
+        for e, o in enumerate(oracles):
+            assert refsnap.digest(env.codec.snapshot(recs[e])) == refsnap.digest(o.snapshot()), (t, e)
+    assert int(env.error_flags().abs().max().item()) == 0

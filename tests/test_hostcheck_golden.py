@@ -4,7 +4,7 @@ repeats these checks through the C ABI on the device."""
 import numpy as np
 import pytest
 
-from helpers import (alloc_opts_for, escort_scores_from_logits, golden_config, injected_commit_vectors, injected_logits,
+from helpers import (alloc_opts_for, assert_tokens_equal_reference, escort_scores_from_logits, golden_config, injected_commit_vectors, injected_logits,
                      injected_scores, load_golden)
 
 STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit_local", "wps_escort_coalition",
@@ -12,7 +12,7 @@ STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit
               "wps_attn_xl_local", "wps_hard_single_task", "wps_hard_obstacles"]
 # planner fixtures mutate commit_until between steps: they are replayed through the fused planner only
 ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
-    "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair"]
+    "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair", "wps_attn_context"]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)
@@ -40,9 +40,15 @@ def test_fused_allocator(hostcheck, name):
     env = hostcheck.make(golden_config(eps[0]), [ep["seed"] for ep in eps])
     O = alloc_opts_for(drv)
     for t in range(len(eps[0]["steps"])):
-        if drv == "pair_injected":
+        if drv in ("pair_injected", "context_injected"):
             sc = np.stack([injected_scores(ep["seed"], t, 16, 32) for ep in eps])
             O.d_edge_scores = sc.ctypes.data
+            if any("context_tokens" in ep["steps"][t] for ep in eps):
+                tok, raw = env.tokens_context(32, 16, False), env.tokens_context(32, 16, True)
+                for e, ep in enumerate(eps):
+                    if "context_tokens" in ep["steps"][t]:
+                        assert_tokens_equal_reference(ep["steps"][t]["context_tokens"], tok, e, (ep["seed"], t))
+                        assert_tokens_equal_reference(ep["steps"][t]["context_tokens_raw"], raw, e, (ep["seed"], t, "raw"))
         elif drv == "att_commit_injected":
             vec = [injected_commit_vectors(ep["seed"], t) for ep in eps]
             pv = np.stack([v[0] for v in vec])

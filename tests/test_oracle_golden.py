@@ -5,7 +5,7 @@ import pytest
 
 import numpy as np
 
-from helpers import (escort_scores_from_logits, injected_commit_vectors, injected_logits, injected_scores, load_golden,
+from helpers import (assert_tokens_equal_reference, escort_scores_from_logits, injected_commit_vectors, injected_logits, injected_scores, load_golden,
                      golden_config)
 import refsnap
 from oracle.hungarian import OracleHungarian, apply_assign, open_tasks
@@ -19,7 +19,7 @@ CASES = [
     ("wps_escort_coalition", 2), ("wps_hard_global", 2), ("wps_hard_pair", 3), ("wps_commit_pair", 1),
     ("wps_hard_random", 3), ("wps_escort_random", 1), ("wps_attn_xl_local", 1), ("wps_hard_single_task", 2),
     ("wps_commit_urgency", 3), ("wps_escort_urgency", 2), ("wps_hard_obstacles", 2),
-    ("wps_hard_urgency_pair", 3), ("wps_commit_attcommit", 3), ("wps_escort_attescort", 3),
+    ("wps_hard_urgency_pair", 3), ("wps_attn_context", 2), ("wps_commit_attcommit", 3), ("wps_escort_attescort", 3),
 ]
 
 
@@ -36,8 +36,12 @@ def replay(ep):
             pairs = hung.allocate(o, time_step=o.t, events=o.last_events, known=known)
             assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
             assert [list(a) for a in apply_assign(o, pairs)] == st["actions"], (ep["seed"], t)
-        elif drv == "pair_injected":
+        elif drv in ("pair_injected", "context_injected"):
             pairs = []
+            if "context_tokens" in st:   # build_context_pair_tokens of the reference at this step, both variants
+                assert_tokens_equal_reference(st["context_tokens"], otok.build_context_pair_tokens(o, 32, 16), None, (t, "ctx"))
+                assert_tokens_equal_reference(st["context_tokens_raw"], otok.build_context_pair_tokens(o, 32, 16, raw=True),
+                                              None, (t, "raw"))
             if otok.hybrid_should_replan(o, o.last_events, 15):
                 sc = injected_scores(ep["seed"], o.t, 16, 32)
                 pairs = otok.pair_plan(o, hung, sc)

@@ -14,6 +14,7 @@ pytestmark = pytest.mark.skipif(not refshim.reference_available(), reason="refer
 def _pairs():
     refshim.install()
     from TaskAllocation.Hybrid import AttentionCommit as RC
+    from TaskAllocation.Hybrid import ContextPairHybrid as RX
     from TaskAllocation.Hybrid import AttentionEscort as RE
     from TaskAllocation.Hybrid import PairCostHybrid as RP
     from multi_uav_ta_gym_env_b200 import scorers as S
@@ -25,10 +26,12 @@ def _pairs():
         ("mlp_commit", RC.MLPCommitNet, S.MLPCommitNet, (32, 13), (16, 13)),
         ("att_coalition", RE.AttCoalitionNet, S.AttCoalitionNet, (48, 22), (16, 16)),
         ("mlp_coalition", RE.MLPCoalitionNet, S.MLPCoalitionNet, (48, 22), (16, 16)),
+        ("att_context", RX.AttContextPairNet, S.AttContextPairNet, (32, 13), (16, 12)),
+        ("mlp_context", RX.MLPContextPairNet, S.MLPContextPairNet, (32, 13), (16, 12)),
     ]
 
 
-@pytest.mark.parametrize("idx", range(6))
+@pytest.mark.parametrize("idx", range(8))
 def test_same_seed_same_parameters_same_forward(idx):
     name, Ref, Mine, tshape, ashape = _pairs()[idx]
     torch.manual_seed(7)
@@ -48,9 +51,10 @@ def test_same_seed_same_parameters_same_forward(idx):
     for b in range(B):
         tm[b, 5 + 3 * b:] = True
         am[b, 6 + b:] = True
+    extra = (torch.rand(B, 8, generator=g),) if "context" in name else ()
     with torch.no_grad():
-        ro = ref(tf, tm, af, am)
-        mo = mine(tf, tm, af, am)
+        ro = ref(tf, tm, af, am, *extra)
+        mo = mine(tf, tm, af, am, *extra)
     for r, m in zip(ro, mo):
         assert torch.equal(r, m), name
 
@@ -73,3 +77,20 @@ def test_coalition_scores_follow_act():
     tt = {k: torch.as_tensor(v)[None] for k, v in tok.items()}
     got = S.coalition_scores(mine.eval(), tt)[0].numpy()
     assert np.allclose(got, want, atol=1e-6, rtol=0)
+
+
+def test_registered_scenarios_match_the_reference():
+    """config.CASE_SPECS / wps_config against experiments/paper_scenarios.CASE_SPECS + paper_eval.make_config."""
+    refshim.install()
+    from experiments.paper_scenarios import CASE_SPECS as REF
+    from multi_uav_ta_gym_env_b200 import config as mine
+
+    assert set(REF) <= set(mine.CASE_SPECS)
+    for case in REF:
+        want = {k: v for k, v in REF[case].items() if k != "label"}
+        got = {k: v for k, v in mine.CASE_SPECS[case].items() if k != "label"}
+        assert want == got, case
+        a, b = refshim.wps_config(case), mine.wps_config(case)
+        da = {k: v for k, v in vars(a).items() if not k.startswith("_")}
+        db = {k: v for k, v in vars(b).items() if not k.startswith("_")}
+        assert da == db, (case, {k: (da.get(k), db.get(k)) for k in set(da) | set(db) if da.get(k) != db.get(k)})
