@@ -765,3 +765,28 @@ def test_context_pair_pipeline_matches_oracle():
         for e, o in enumerate(oracles):
             assert refsnap.digest(env.codec.snapshot(recs[e])) == refsnap.digest(o.snapshot()), (t, e)
     assert int(env.error_flags().abs().max().item()) == 0
+
+
+@pytest.mark.parametrize("case", ["static_strike", "recon_strike_mix", "agent_scaling_mid", "D1_attrition", "D2_popup_threats",
+                                  "D3_combined", "WPS_attn_AWACS", "WPS_attn_COP_cue_d12", "WPS_attn_COP_d0",
+                                  "WPS_attn_COP_R60", "WPS_attn_OS24", "WPS_attn_L"])
+def test_other_registered_scenarios_match_the_oracle(case):
+    """Every other scenario family of experiments/paper_scenarios.py through the CUDA path (Local-Hungarian)."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+    from oracle.hungarian import OracleHungarian, apply_assign
+    from oracle.sim import OracleEnv
+
+    cfg = wps_config(case)
+    seeds = [0, 1]
+    env = make_env(cfg, seeds)
+    oracles = [OracleEnv(cfg).reset(s) for s in seeds]
+    hungs = [OracleHungarian(20, 1200.0) for _ in seeds]
+    spec = AllocSpec.local_hungarian(20)
+    for t in range(150):
+        env.step_allocated(spec, 1)
+        recs = env.records.cpu().numpy()
+        for e, o in enumerate(oracles):
+            pairs = hungs[e].allocate(o, time_step=o.t, events=o.last_events, known=o.visibility())
+            o.step(apply_assign(o, pairs))
+            assert refsnap.digest(env.codec.snapshot(recs[e])) == refsnap.digest(o.snapshot()), (case, seeds[e], t)
+    assert int(env.error_flags().abs().max().item()) == 0

@@ -91,3 +91,29 @@ def test_multi_step_launch_equals_single_steps(hostcheck):
     for _ in range(60):
         b.step_alloc(O)
     assert (a.rec == b.rec).all()
+
+
+@pytest.mark.parametrize("case", ["static_strike", "D1_attrition", "D3_combined", "WPS_attn_AWACS", "WPS_attn_COP_cue_d12",
+                                  "WPS_attn_OS24"])
+def test_other_registered_scenarios_match_the_oracle(hostcheck, case):
+    """Scenarios of experiments/paper_scenarios.py outside the WPS core set (legacy static / dynamic cases, the
+    common-operating-picture sweeps and larger fleets of WPS_attn): kernel core vs oracle, Local-Hungarian, every step.
+    (The oracle itself was cross-checked against the live reference on these cases, tests/golden/crosscheck.py.)"""
+    from multi_uav_ta_gym_env_b200 import wps_config
+    from oracle.hungarian import OracleHungarian, apply_assign
+    from oracle.sim import OracleEnv
+    import refsnap
+
+    cfg = wps_config(case)
+    seeds = [0, 1]
+    env = hostcheck.make(cfg, seeds, queue_cap=16)
+    O = alloc_opts_for("local_hungarian")
+    oracles = [OracleEnv(cfg).reset(s) for s in seeds]
+    hungs = [OracleHungarian(20, 1200.0) for _ in seeds]
+    for t in range(150):
+        env.step_alloc(O)
+        for e, o in enumerate(oracles):
+            pairs = hungs[e].allocate(o, time_step=o.t, events=o.last_events, known=o.visibility())
+            o.step(apply_assign(o, pairs))
+            assert env.err(e) == 0
+            assert refsnap.digest(env.snapshot(e)) == refsnap.digest(o.snapshot()), (case, seeds[e], t)
