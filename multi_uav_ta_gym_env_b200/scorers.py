@@ -166,11 +166,77 @@ class MLPContextPairNet(nn.Module):
         return logits, self.value_mlp(ctx_h).squeeze(-1)
 
 
+class BipartiteMPLayer(nn.Module):
+    """One agent <-> task message-passing step restricted to the valid edges (GNNPairHybrid.py:23-57)."""
+
+    def __init__(self, d_model=64, msg_hidden=96):
+        super().__init__()
+        self.msg_a2t = nn.Sequential(nn.Linear(d_model * 2, msg_hidden), nn.ReLU(), nn.Linear(msg_hidden, d_model))
+        self.msg_t2a = nn.Sequential(nn.Linear(d_model * 2, msg_hidden), nn.ReLU(), nn.Linear(msg_hidden, d_model))
+        self.norm_a = nn.LayerNorm(d_model)
+        self.norm_t = nn.LayerNorm(d_model)
+
+    def forward(self, a_h, t_h, edge_valid):
+        a_exp = a_h.unsqueeze(2).expand(-1, -1, t_h.size(1), -1)
+        t_exp = t_h.unsqueeze(1).expand(-1, a_h.size(1), -1, -1)
+        pair = torch.cat([a_exp, t_exp], dim=-1)
+        w = edge_valid.unsqueeze(-1)
+        msg_t = self.msg_a2t(pair) * w
+        t_h = self.norm_t(t_h + msg_t.sum(dim=1) / w.sum(dim=1).clamp(min=1e-6))
+        msg_a = self.msg_t2a(pair) * w
+        a_h = self.norm_a(a_h + msg_a.sum(dim=2) / w.sum(dim=2).clamp(min=1e-6))
+        return a_h, t_h
+
+
+class GNNContextPairNet(nn.Module):
+    """GNNContextPairNet (GNNPairHybrid.py:60-122): bipartite GNN edge scorer with the context-biased pair head."""
+
+    def __init__(self, max_tasks=32, max_agents=16, d_model=64, n_layers=2, task_feat_dim=TASK_FEAT_DIM,
+                 agent_feat_dim=AGENT_FEAT_DIM, context_dim=CONTEXT_DIM, **_):
+        super().__init__()
+        self.max_tasks, self.max_agents, self.d_model = max_tasks, max_agents, d_model
+        self.task_proj = nn.Linear(task_feat_dim, d_model)
+        self.agent_proj = nn.Linear(agent_feat_dim, d_model)
+        self.ctx_proj = nn.Linear(context_dim, d_model)
+        self.type_embed = nn.Embedding(2, d_model)
+        self.layers = nn.ModuleList([BipartiteMPLayer(d_model) for _ in range(max(1, n_layers))])
+        self.pair_head = nn.Sequential(nn.Linear(d_model * 4, d_model), nn.ReLU(), nn.Linear(d_model, d_model // 2),
+                                       nn.ReLU(), nn.Linear(d_model // 2, 1))
+        self.value_head = nn.Sequential(nn.Linear(d_model * 2, d_model), nn.ReLU(), nn.Linear(d_model, 1))
+
+    def forward(self, task_feats, task_mask, agent_feats, agent_mask, context, edge_valid=None):
+        a_h = self.agent_proj(agent_feats) + self.type_embed.weight[0]
+        t_h = self.task_proj(task_feats) + self.type_embed.weight[1]
+        pad = (~agent_mask).unsqueeze(2).float() * (~task_mask).unsqueeze(1).float()
+        edge_valid = pad if edge_valid is None else edge_valid.float() * pad
+        for layer in self.layers:
+            a_h, t_h = layer(a_h, t_h, edge_valid)
+        am = (~agent_mask).float().unsqueeze(-1)
+        tm = (~task_mask).float().unsqueeze(-1)
+        a_pool = (a_h * am).sum(1) / am.sum(1).clamp(min=1.0)
+        t_pool = (t_h * tm).sum(1) / tm.sum(1).clamp(min=1.0)
+        pooled = 0.5 * (a_pool + t_pool)
+        ctx = self.ctx_proj(context) + pooled
+        ctx_exp = ctx.unsqueeze(1).unsqueeze(2).expand(-1, self.max_agents, self.max_tasks, -1)
+        a_exp = a_h.unsqueeze(2).expand(-1, -1, self.max_tasks, -1)
+        t_exp = t_h.unsqueeze(1).expand(-1, self.max_agents, -1, -1)
+        logits = self.pair_head(torch.cat([a_exp, t_exp, a_exp * t_exp, ctx_exp], dim=-1)).squeeze(-1)
+        logits = logits.masked_fill(agent_mask.unsqueeze(2), -1e9)
+        logits = logits.masked_fill(task_mask.unsqueeze(1), -1e9)
+        logits = logits.masked_fill(edge_valid < 0.5, -1e9)
+        value = self.value_head(torch.cat([pooled, ctx], dim=-1)).squeeze(-1)
+        return logits, value
+
+
 @torch.no_grad()
 def context_pair_scores(net: nn.Module, tok: dict, score_clamp: float = SCORE_CLAMP) -> torch.Tensor:
-    """tokens (BatchedMultiUAVEnv.tokens_context) -> edge scores f32 [B, max_agents, max_tasks]: ContextPairHybrid.act
-    without exploration (ContextPairHybrid.py:235-246); feed to AllocSpec.pair_hybrid()."""
-    logits, _ = net(tok["task_feats"], tok["task_mask"], tok["agent_feats"], tok["agent_mask"], tok["context"])
+    """tokens (BatchedMultiUAVEnv.tokens_context) -> edge scores f32 [B, max_agents, max_tasks]: ContextPairHybrid.act /
+    GNNContextPairHybrid.act without exploration (ContextPairHybrid.py:235-246, GNNPairHybrid.py:160-171); feed to
+    AllocSpec.pair_hybrid().  The GNN network also takes the valid-edge mask."""
+    args = [tok["task_feats"], tok["task_mask"], tok["agent_feats"], tok["agent_mask"], tok["context"]]
+    if isinstance(net, GNNContextPairNet):
+        args.append(tok["edge_valid"])
+    logits, _ = net(*args)
     return torch.tanh(logits) * score_clamp * tok["edge_valid"]
 
 

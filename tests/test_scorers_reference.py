@@ -15,6 +15,7 @@ def _pairs():
     refshim.install()
     from TaskAllocation.Hybrid import AttentionCommit as RC
     from TaskAllocation.Hybrid import ContextPairHybrid as RX
+    from TaskAllocation.Hybrid import GNNPairHybrid as RG
     from TaskAllocation.Hybrid import AttentionEscort as RE
     from TaskAllocation.Hybrid import PairCostHybrid as RP
     from multi_uav_ta_gym_env_b200 import scorers as S
@@ -28,10 +29,11 @@ def _pairs():
         ("mlp_coalition", RE.MLPCoalitionNet, S.MLPCoalitionNet, (48, 22), (16, 16)),
         ("att_context", RX.AttContextPairNet, S.AttContextPairNet, (32, 13), (16, 12)),
         ("mlp_context", RX.MLPContextPairNet, S.MLPContextPairNet, (32, 13), (16, 12)),
+        ("gnn_context", RG.GNNContextPairNet, S.GNNContextPairNet, (32, 13), (16, 12)),
     ]
 
 
-@pytest.mark.parametrize("idx", range(8))
+@pytest.mark.parametrize("idx", range(9))
 def test_same_seed_same_parameters_same_forward(idx):
     name, Ref, Mine, tshape, ashape = _pairs()[idx]
     torch.manual_seed(7)
@@ -52,6 +54,8 @@ def test_same_seed_same_parameters_same_forward(idx):
         tm[b, 5 + 3 * b:] = True
         am[b, 6 + b:] = True
     extra = (torch.rand(B, 8, generator=g),) if "context" in name else ()
+    if name == "gnn_context":
+        extra += ((torch.rand(B, ashape[0], tshape[0], generator=g) > 0.4).float(),)
     with torch.no_grad():
         ro = ref(tf, tm, af, am, *extra)
         mo = mine(tf, tm, af, am, *extra)
