@@ -239,6 +239,14 @@ int muav_tokens_escort(const muav_config* cfg, const void* d_records, int max_ta
                        uint8_t* d_task_mask, float* d_agent_feats16, uint8_t* d_agent_mask, float* d_edge_valid,
                        int32_t* d_task_ids, int32_t* d_task_order, int n_envs, void* stream);
 
+/* Training masks over the pair-token grid: mask [E, max_agents, max_tasks] f32, 1 where the allocator output of this step
+ * (muav_step_out.d_pairs / d_n_pairs) pairs token row i (i-th live agent) with token column j (d_task_ids).
+ * require_valid != 0: only through valid edges = _expert_mask (experiments/train_pair_cost.py:53-70, imitation of the
+ * Global-Hungarian teacher); require_valid == 0: PairCostHybrid._selected_mask (PairCostHybrid.py:293-306). */
+int muav_pair_mask(const muav_config* cfg, const void* d_records, const int32_t* d_pairs, const int32_t* d_n_pairs,
+                   const int32_t* d_task_ids, const float* d_edge_valid, int max_tasks, int max_agents, int require_valid,
+                   float* d_mask, int n_envs, void* stream);
+
 /* Observation tensors (DroneEnv.py:365-492).  tasks_info [E, max_rows, 21] f64 per open task:
  * id, x/max_coord, y/max_coord, status, current_reqs[6], alloc_reqs[6], init_time, end_time, type_idx, unmet, age
  * (status = -1 marks padding rows); pad_mask [E,max_rows] u8 ("mask"); legal_mask [E, n_agents, max_rows] u8;

@@ -90,7 +90,7 @@ class MuavAttPairOffsets(C.Structure):
 ABI_SYMBOLS = [
     "muav_version", "muav_config_size", "muav_record_bytes", "muav_scratch_bytes", "muav_num_fields",
     "muav_field_info", "muav_header_index", "muav_step", "muav_allocate", "muav_step_host", "muav_lsap",
-    "muav_avoid_obstacles", "muav_metric_name", "muav_metrics", "muav_tokens_pair", "muav_tokens_commit", "muav_tokens_escort", "muav_tokens_context", "muav_observe",
+    "muav_avoid_obstacles", "muav_metric_name", "muav_metrics", "muav_tokens_pair", "muav_tokens_commit", "muav_tokens_escort", "muav_tokens_context", "muav_pair_mask", "muav_observe",
     "muav_att_pair_scores", "muav_rollout", "muav_state_bytes", "muav_tape_bytes", "muav_reset_upload", "muav_snapshot",
 ]
 
@@ -202,6 +202,8 @@ class CudaLib(Lib):
         d.muav_reset_upload.argtypes = [C.POINTER(MuavConfig), P, P, P, P, C.c_int, P]
         d.muav_snapshot.restype = C.c_int
         d.muav_snapshot.argtypes = [C.POINTER(MuavConfig), P, C.c_int, P, P]
+        d.muav_pair_mask.restype = C.c_int
+        d.muav_pair_mask.argtypes = [C.POINTER(MuavConfig), P, P, P, P, P, C.c_int, C.c_int, C.c_int, P, C.c_int, P]
         d.muav_tokens_context.restype = C.c_int
         d.muav_tokens_context.argtypes = [C.POINTER(MuavConfig), P, C.c_int, C.c_int, C.c_int, P, P, P, P, P, P, P, C.c_int, P]
         d.muav_tokens_escort.restype = C.c_int

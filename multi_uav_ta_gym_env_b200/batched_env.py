@@ -361,6 +361,20 @@ class BatchedMultiUAVEnv:
         return {"task_feats": tf, "task_mask": tm.bool(), "agent_feats": af, "agent_mask": am.bool(),
                 "edge_valid": ev, "task_ids": ids}
 
+    def pair_mask(self, tok: dict, require_valid: bool) -> torch.Tensor:
+        """Mask [E, max_agents, max_tasks] of the allocator pairs of the last allocate / step call over the token grid of
+        `tok`: the imitation target _expert_mask (require_valid=True, train_pair_cost.py:53-70) or PairCostHybrid's
+        _selected_mask (False).  Call before the state moves on (row = i-th live agent of the current state)."""
+        E = self.n_envs
+        MA, MT = tok["edge_valid"].shape[1], tok["edge_valid"].shape[2]
+        mask = torch.empty(E, MA, MT, dtype=torch.float32, device=self.device)
+        rc = self.lib.dll.muav_pair_mask(C.byref(self.cfg), self.records.data_ptr(), self.pairs.data_ptr(),
+                                         self.n_pairs.data_ptr(), tok["task_ids"].data_ptr(), tok["edge_valid"].data_ptr(),
+                                         MT, MA, int(require_valid), mask.data_ptr(), E, self._stream())
+        _lib.check(rc, "muav_pair_mask")
+        self.launches += 1
+        return mask
+
     def tokens_context(self, max_tasks=32, max_agents=16, raw=False):
         """build_context_pair_tokens(env, raw) for every environment (ContextPairHybrid.py:33-78): pair tokens (the
         per-entity `raw` variant has 9 / 11 features) plus the context vector [E, 8] ([E, 1] when raw)."""

@@ -396,6 +396,38 @@ __global__ void __launch_bounds__(128) muav_tokens_escort_kernel(const __grid_co
                     ids + (size_t)e * max_tasks, order ? order + (size_t)e * L.D.IC : nullptr, W, lane, 32);
 }
 
+// Pair mask of the trainers: mask[i, j] = 1 for every allocator pair (agent, task) whose agent is token row i (i-th live
+// agent) and whose task is token column j (task_ids[j]); require_valid keeps only pairs with edge_valid >= 0.5
+// (_expert_mask, experiments/train_pair_cost.py:53-70) -- without it this is PairCostHybrid._selected_mask (:293-306).
+__global__ void muav_pair_mask_kernel(const __grid_constant__ Layout L, const char* records, const int32_t* pairs,
+                                      const int32_t* n_pairs, const int32_t* task_ids, const float* edge_valid,
+                                      int max_tasks, int max_agents, int require_valid, float* mask, int n) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  View V;
+  V.base = (char*)records + (size_t)e * L.record_bytes;
+  V.L = &L;
+  const int A = L.D.A;
+  float* m = mask + (size_t)e * max_agents * max_tasks;
+  for (int i = 0; i < max_agents * max_tasks; ++i) m[i] = 0.0f;
+  const int32_t* ids = task_ids + (size_t)e * max_tasks;
+  const int np = n_pairs[e];
+  for (int p = 0; p < np && p < A; ++p) {
+    const int v = pairs[(size_t)e * A + p];
+    const int a = v >> 16, tid = v & 0xFFFF;
+    if (a < 0 || a >= A || V.a_state()[a] == -1) continue;
+    int row = 0;
+    for (int b = 0; b < a; ++b) row += V.a_state()[b] != -1;
+    if (row >= max_agents) continue;
+    int col = -1;
+    for (int j = 0; j < max_tasks; ++j)
+      if (ids[j] == tid && tid != 0) col = j;   // dict built in column order: the last duplicate would win (ids are unique)
+    if (col < 0) continue;
+    if (require_valid && !(edge_valid[((size_t)e * max_agents + row) * max_tasks + col] >= 0.5f)) continue;
+    m[row * max_tasks + col] = 1.0f;
+  }
+}
+
 __global__ void muav_observe_kernel(const __grid_constant__ muav_config cfg, const __grid_constant__ Layout L,
                                     const char* records, int max_rows, double* ti, uint8_t* pad, uint8_t* legal,
                                     double* ao, float* ef, int32_t* n_rows, int n) {
@@ -738,6 +770,21 @@ int muav_tokens_escort(const muav_config* cfg, const void* d_records, int max_ta
   muav_tokens_escort_kernel<<<(n_envs + 3) / 4, 128, (size_t)per_warp * 4, (cudaStream_t)stream>>>(
       *cfg, L, (const char*)d_records, max_tasks, max_agents, d_task_feats22, d_task_mask, d_agent_feats16, d_agent_mask,
       d_edge_valid, d_task_ids, d_task_order, n_envs, per_warp);
+  return cuda_rc(cudaGetLastError());
+}
+
+int muav_pair_mask(const muav_config* cfg, const void* d_records, const int32_t* d_pairs, const int32_t* d_n_pairs,
+                   const int32_t* d_task_ids, const float* d_edge_valid, int max_tasks, int max_agents, int require_valid,
+                   float* d_mask, int n_envs, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (n_envs <= 0) return n_envs == 0 ? 0 : -22;
+  if (!d_records || !d_pairs || !d_n_pairs || !d_task_ids || !d_mask || max_tasks < 1 || max_agents < 1) return -22;
+  if (require_valid && !d_edge_valid) return -22;
+  Layout L = make_layout(*cfg);
+  muav_pair_mask_kernel<<<(n_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      L, (const char*)d_records, d_pairs, d_n_pairs, d_task_ids, d_edge_valid, max_tasks, max_agents, require_valid, d_mask,
+      n_envs);
   return cuda_rc(cudaGetLastError());
 }
 

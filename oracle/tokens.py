@@ -9,6 +9,7 @@ Restates, over the oracle's flat state (oracle/sim.py):
   _generate_observations / get_task_info / _event_flag_vector   mUAV_TA/DroneEnv.py:365-492
   build_att_tokens (raw=True), build_context_summary / build_context_pair_tokens
                                    AttentionRAH.py:86-97,140-146, TaskAllocation/Hybrid/ContextPairHybrid.py:33-78
+  _expert_mask / _selected_mask    experiments/train_pair_cost.py:53-70, PairCostHybrid.py:293-306
   _open_tasks_residual / _threat_stats / _task_priority_key / build_escort_tokens
                                    TaskAllocation/Hybrid/AttentionEscort.py:31-241
 """
@@ -315,6 +316,21 @@ def build_escort_tokens(env, max_tasks=48, max_agents=16):
     ids[: len(kept)] = [k + 1 for k in kept]
     return {"task_feats": task_feats, "task_mask": task_mask, "agent_feats": agent_feats, "agent_mask": agent_mask,
             "edge_valid": edge_valid, "task_ids": ids, "open_tasks": [k + 1 for k in kept], "live": live, "vis": vis}
+
+
+def pair_mask(tok, pairs, require_valid):
+    """pairs: [(agent_id, task_id)] of the allocator.  require_valid: _expert_mask, else _selected_mask."""
+    mask = np.zeros(tok["edge_valid"].shape, dtype=np.float32)
+    row_of = {a: i for i, a in enumerate(tok["live"][: mask.shape[0]]) if not tok["agent_mask"][i]}
+    col_of = {int(tid): j for j, tid in enumerate(tok["open_tasks"])}
+    for a, tid in pairs:
+        i, j = row_of.get(a), col_of.get(int(tid))
+        if i is None or j is None:
+            continue
+        if require_valid and tok["edge_valid"][i, j] < 0.5:
+            continue
+        mask[i, j] = 1.0
+    return mask
 
 
 def pair_plan(env, hung, scores, max_tasks=32, max_agents=16):

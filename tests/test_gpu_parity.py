@@ -790,3 +790,64 @@ def test_other_registered_scenarios_match_the_oracle(case):
             o.step(apply_assign(o, pairs))
             assert refsnap.digest(env.codec.snapshot(recs[e])) == refsnap.digest(o.snapshot()), (case, seeds[e], t)
     assert int(env.error_flags().abs().max().item()) == 0
+
+
+def test_batched_collectors_match_the_oracle():
+    """collectors.ILCollector / RLCollector against the oracle restatement of run_il_episode /
+    run_rl_episode (experiments/train_pair_cost.py:96-159): tokens, expert / selected masks, planned flags, rewards."""
+    from multi_uav_ta_gym_env_b200 import wps_config
+    from multi_uav_ta_gym_env_b200.collectors import ILCollector, RLCollector
+    from oracle.hungarian import OracleHungarian, apply_assign, open_tasks
+    from oracle import tokens as otok
+    from oracle.sim import OracleEnv
+
+    cfg = wps_config("WPS_hard")
+    seeds = [3, 4, 5]
+    keys = ("task_feats", "task_mask", "agent_feats", "agent_mask", "edge_valid")
+    # ---- imitation: Global-Hungarian teacher
+    col = ILCollector(make_env(cfg, seeds))
+    oracles = [OracleEnv(cfg).reset(s) for s in seeds]
+    hungs = [OracleHungarian(20, 1200.0) for _ in seeds]
+    n_samples = 0
+    for t in range(150):
+        tokens, mask, planned = col.step()
+        host = {k: v.cpu().numpy() for k, v in tokens.items()}
+        hm, hp = mask.cpu().numpy(), planned.cpu().numpy()
+        for e, o in enumerate(oracles):
+            go = otok.hybrid_should_replan(o, o.last_events, 20)
+            assert bool(hp[e]) == go, (t, e)
+            pairs = []
+            if go:
+                pairs = hungs[e].allocate(o, agents=o.live_agents(), tasks=open_tasks(o), time_step=o.t, events=o.last_events,
+                                          force=True)
+                want = otok.build_pair_tokens(o, 32, 16)
+                for k in keys:
+                    assert np.array_equal(host[k][e], want[k]), (t, e, k)
+                wm = otok.pair_mask(want, pairs, True)
+                assert np.array_equal(hm[e], wm), (t, e)
+                n_samples += int(wm.sum() > 0)
+            o.step(apply_assign(o, pairs))
+    assert n_samples > 20
+    # ---- RL transitions with deterministic injected scores
+    col = RLCollector(make_env(cfg, seeds))
+    oracles = [OracleEnv(cfg).reset(s) for s in seeds]
+    hungs = [OracleHungarian(20, 1200.0) for _ in seeds]
+    for t in range(150):
+        sc_host = np.stack([injected_scores(s, t, 16, 32) for s in seeds])
+        tr = col.step(lambda tok: torch.from_numpy(sc_host).cuda())
+        sel, rew, hp = tr["selected"].cpu().numpy(), tr["reward"].cpu().numpy(), tr["planned"].cpu().numpy()
+        nxt = {k: v.cpu().numpy() for k, v in tr["next_tokens"].items()}
+        for e, o in enumerate(oracles):
+            s_prev = o.compute_s_wps()
+            go = otok.hybrid_should_replan(o, o.last_events, 20)
+            assert bool(hp[e]) == go, (t, e)
+            pairs = []
+            if go:
+                tok = otok.build_pair_tokens(o, 32, 16)
+                pairs = otok.pair_plan(o, hungs[e], sc_host[e])
+                assert np.array_equal(sel[e], otok.pair_mask(tok, pairs, False)), (t, e)
+            o.step(apply_assign(o, pairs))
+            assert rew[e] == (o.compute_s_wps() - s_prev) / 20.0, (t, e)
+            want = otok.build_pair_tokens(o, 32, 16)
+            for k in keys:
+                assert np.array_equal(nxt[k][e], want[k]), (t, e, k)

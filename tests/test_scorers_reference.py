@@ -98,3 +98,49 @@ def test_registered_scenarios_match_the_reference():
         da = {k: v for k, v in vars(a).items() if not k.startswith("_")}
         db = {k: v for k, v in vars(b).items() if not k.startswith("_")}
         assert da == db, (case, {k: (da.get(k), db.get(k)) for k in set(da) | set(db) if da.get(k) != db.get(k)})
+
+
+def test_training_masks_follow_the_reference_trainers():
+    """oracle.tokens.pair_mask (the checker of the batched collectors) against _expert_mask of
+    experiments/train_pair_cost.py:53-70 and PairCostHybrid._selected_mask (:293-306) on a live reference episode with
+    the Global-Hungarian teacher."""
+    import sys
+    import types
+
+    refshim.install()
+    for name in ("tianshou", "tianshou.data", "TaskAllocation.RL_Policies.Tianshou_Policy"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["tianshou"].__path__ = []
+    sys.modules["tianshou.data"].Batch = dict
+    sys.modules["TaskAllocation.RL_Policies.Tianshou_Policy"]._get_model = lambda *a, **k: None
+    import experiments.train_pair_cost as T
+    from mUAV_TA.DroneEnv import MultiUAVEnv as RefEnv
+    from TaskAllocation.Hybrid.PairCostHybrid import PairCostHybrid
+    from TaskAllocation.OptimizationBased.HungarianAllocator import HungarianAllocator as RefHung
+    from oracle import tokens as otok
+    from oracle.sim import OracleEnv
+
+    cfg = refshim.wps_config("WPS_hard")
+    ref = RefEnv(cfg)
+    obs, info = ref.reset(seed=9)
+    orc = OracleEnv(cfg).reset(9)
+    hung = RefHung(20, ref.max_coord)
+    pol = PairCostHybrid(use_attention=False, device="cpu")
+    n = 0
+    for t in range(150):
+        events = list(info.get("events") or []) if isinstance(info, dict) else []
+        actions = {}
+        if T._should_replan(ref, events):
+            expert = hung.allocate_tasks(ref.get_live_agents(), T._open_tasks(ref), time_step=ref.time_steps, events=events,
+                                         force=True)
+            tok = pol.build_tokens(ref)
+            otk = otok.build_pair_tokens(orc, 32, 16)
+            pairs = [(ref.agent_by_name[nm].id, task.id) for nm, task in expert]
+            assert np.array_equal(T._expert_mask(tok, expert), otok.pair_mask(otk, pairs, True)), t
+            assert np.array_equal(pol._selected_mask(tok, expert), otok.pair_mask(otk, pairs, False)), t
+            n += int(T._expert_mask(tok, expert).sum() > 0)
+            actions = T._apply_assign(ref, expert)
+        obs, _, _, _, info = ref.step(actions)
+        orc.step([(ref.agent_by_name[nm].id, i) for nm, i in actions.items()])
+    assert n > 5
