@@ -247,6 +247,10 @@ def build_config(opts, task_cap=None, queue_cap=16, event_cap=None, id_cap=None)
         id_cap = base + (320 if escort else 0)
         id_cap = (id_cap + 31) // 32 * 32
     # Task slots: open tasks plus closed ones that a queue / the escort map / a live threat still references.
+    if task_cap == "all":
+        # one slot per id plus the head-room below which the step starts recycling (agents + threats + 2 new tasks per
+        # step): nothing is ever recycled -- the full task history of env.tasks, for the E = 1 facade
+        task_cap = (id_cap + n_agents + n_threats + 2 + 15) // 16 * 16
     if task_cap is None:
         task_cap = base + (24 if escort else 0)
         task_cap = (task_cap + 15) // 16 * 16

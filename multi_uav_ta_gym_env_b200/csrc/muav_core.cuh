@@ -167,6 +167,13 @@ struct Sim {
     return c;
   }
 
+  // A closed task keeps whatever allocationDetails entries it had when it closed (removeAgentCap is a no-op once
+  // status == 2, DroneEnvComponents.py:282-285); only their number is observable (the replay's assigned_agents).
+  MUAV_HD void close_task(int k) {
+    if (V.k_status()[k] != 2) V.k_det_frozen()[k] = (int16_t)details_count(k + 1);  // some sites re-close every step
+    V.k_status()[k] = 2;
+  }
+
   // ------------------------------------------------------------------ Task.add/removeAgentCap
   // DroneEnvComponents.py:280-301.  `t0` is the time stored with the entry that was just removed.
   MUAV_HD MUAV_NI_H void remove_agent_cap(int k, int a, double t0) {
@@ -377,6 +384,7 @@ struct Sim {
     V.k_tbl_lo()[k] = 0;
     V.k_tbl_hi()[k] = 0;
     V.k_reached()[k] = 0;
+    V.k_det_frozen()[k] = 0;
     return k + 1;
   }
   // A closed task keeps its slot only while something still refers to it: an agent queue or last_task (the
@@ -470,7 +478,7 @@ struct Sim {
         for (int ut = 0; ut < MUAV_N_UAV_TYPES; ++ut)
           if (((avail >> ut) & 1u) && C().cap_table[ut][for_type] != 0.0) any = true;
         if (!any) {
-          V.k_status()[k] = 2;
+          close_task(k);
           if (!V.k_reached()[k]) {
             V.k_reached()[k] = 1;
             HIv(N_REACHED) += 1;
@@ -598,9 +606,11 @@ struct Sim {
     int n = fighters_near(mission, C().escort_intercept_radius, near_i(), near_d());
     if (n == 0) {
       V.h_target()[hid] = (int16_t)mission;
+      V.h_intercept()[hid] = -1;
       return;
     }
     V.h_target()[hid] = near_i()[0];
+    V.h_intercept()[hid] = near_i()[0];  // Threat.intercepting_agent: read only by the replay (DroneEnv.py:1775-1791)
   }
   // _release_escort_agents (DroneEnv.py:1919-1936)
   MUAV_HD MUAV_NOINLINE void release_escort_agents(int esc) {
@@ -622,7 +632,7 @@ struct Sim {
   MUAV_HD MUAV_NOINLINE void retire_escort(int esc, bool failed) {
     if (esc == 0 || V.k_status()[esc - 1] == 2) return;
     release_escort_agents(esc);
-    V.k_status()[esc - 1] = 2;
+    close_task(esc - 1);
     int recon = V.k_prot_agent()[esc - 1];
     if (recon >= 0) V.a_escort()[recon] = 0;
     if (failed) HIv(ESC_FAILED) += 1;
@@ -664,6 +674,7 @@ struct Sim {
       if (nd > 0) {
         primary = defenders[0];
         V.h_target()[hid] = (int16_t)primary;
+        V.h_intercept()[hid] = (int16_t)primary;
       }
     }
     if (primary < 0) return;
@@ -692,7 +703,7 @@ struct Sim {
     int k = tid - 1;
     if (rnd < prob) {
       V.h_status()[hid] = 2;
-      V.k_status()[k] = 2;
+      close_task(k);
       mark_outcome(k, true);
       HIv(INTERCEPTED) += 1;
       V.a_ammo()[primary] -= 1;
@@ -722,7 +733,7 @@ struct Sim {
       }
       if (V.h_ammo()[hid] <= 0) {
         V.h_status()[hid] = 0;
-        V.k_status()[k] = 2;
+        close_task(k);
         mark_outcome(k, false);
       } else {
         int tgt = closest_agent(V.h_posx()[hid], V.h_posy()[hid]);
@@ -766,7 +777,7 @@ struct Sim {
       V.k_posx()[k] = V.h_posx()[hid];
       V.k_posy()[k] = V.h_posy()[hid];
       if (V.h_posy()[hid] <= 0) {
-        V.k_status()[k] = 2;
+        close_task(k);
         mark_outcome(k, false);
       }
     }
@@ -1171,7 +1182,7 @@ struct Sim {
                 acc.quality_reward += V.k_org_ti()[k] * 2;
                 HFv(F_REWARD) += ddiv(V.k_org_ti()[k] * 1, HFv(NORM_FACTOR));
                 if (V.k_kind()[k] != 1) mark_outcome(k, true);
-                V.k_status()[k] = 2;
+                close_task(k);
                 if (ti == TT_REC && is_recon(V.a_type()[a])) {
                   HIv(PROT_REC_DONE) += 1;
                   retire_escort(V.a_escort()[a], false);
@@ -1311,7 +1322,7 @@ struct Sim {
 #endif
 
   MUAV_HD MUAV_NI_H void expire_one(int k) {
-    V.k_status()[k] = 2;
+    close_task(k);
     V.k_fq()[k] = 0;
     mark_outcome(k, false);
     mark_reached(k);

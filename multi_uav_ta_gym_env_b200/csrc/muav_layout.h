@@ -154,6 +154,7 @@ MUAV_HD inline Dims dims_of(const muav_config& c) {
   XS(k_counted, int16_t, D.TC)      \
   XS(k_fq, int16_t, D.TC)           \
   XS(k_reached, int16_t, D.TC)      \
+  XS(k_det_frozen, int16_t, D.TC)   \
   XS(k_threat, int16_t, D.TC)       \
   XS(k_prot_agent, int16_t, D.TC)   \
   X(h_task, int16_t, D.HC)          \
@@ -164,6 +165,7 @@ MUAV_HD inline Dims dims_of(const muav_config& c) {
   X(h_ammo, int16_t, D.HC)          \
   X(h_target, int16_t, D.HC)        \
   X(h_mission, int16_t, D.HC)       \
+  X(h_intercept, int16_t, D.HC)     \
   X(h_spawned, int16_t, D.HC)       \
   X(h_order, int16_t, D.HC)
 

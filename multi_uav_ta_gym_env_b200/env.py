@@ -89,6 +89,10 @@ class TaskProxy:
         self.protected_task = env._task(pt) if pt > 0 else None
         det = s["k_det_time"][k]
         self.allocationDetails = {int(a): (None, float(det[a])) for a in range(len(det)) if det[a] >= 0}
+        if self.status == 2:
+            # a closed task keeps the entries it had when it closed (removeAgentCap is a no-op then); the device keeps
+            # their number only -- the one thing the reference reads from them (the replay's assigned_agents)
+            self.allocationDetails = {f"stale{i}": (None, -1.0) for i in range(int(s["k_det_frozen"][k]))}
         self._wps_outcome_counted = bool(s["k_counted"][k])
 
     def __repr__(self):
@@ -156,6 +160,8 @@ class ThreatProxy:
         self.target_agent = env.agents_obj[tg] if tg >= 0 else None
         ms = int(s["h_mission"][h])
         self.mission_target_agent = env.agents_obj[ms] if ms >= 0 else None
+        ic = int(s["h_intercept"][h])
+        self.intercepting_agent = env.agents_obj[ic] if ic >= 0 else None
         tk = int(s["h_task"][h])
         self.relative_task = env._task(tk) if tk > 0 else None
 
@@ -183,7 +189,9 @@ class _AgentSelector:
 
 # --------------------------------------------------------------------------- CUDA backend (E = 1)
 class _CudaBackend:
-    def __init__(self, config, device, task_cap=None, queue_cap=16):
+    def __init__(self, config, device, task_cap="all", queue_cap=16):
+        # one slot per task id: the facade keeps the whole task history like env.tasks of the reference (closed tasks
+        # stay readable for the replay generator / the web UI); recycling slots only pays for large batches
         from .batched_env import BatchedMultiUAVEnv
 
         self.b = BatchedMultiUAVEnv(config, 1, device=device, task_cap=task_cap, queue_cap=queue_cap)

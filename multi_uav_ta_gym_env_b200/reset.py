@@ -231,6 +231,7 @@ def pack_records(lib, cfg, scenarios) -> tuple[np.ndarray, np.ndarray]:
         view("h_ammo")[:] = 4
         view("h_target")[:] = -1
         view("h_mission")[:] = -1
+        view("h_intercept")[:] = -1
     if cfg.n_obstacles > 0:
         view("obst")[:] = np.array([s.obstacles for s in scenarios], dtype=np.float64).reshape(E, -1)
 

@@ -120,9 +120,11 @@ class RecordCodec:
         tbl[~has] = 0
         s["k_tbl_mask"] = tbl.view(np.int64)
         s["k_reached"] = per_task("k_reached")
+        s["k_det_frozen"] = per_task("k_det_frozen")  # facade only: len(allocationDetails) of closed tasks
         s["k_has_slot"] = has.astype(np.int64)
         s["h_pos"] = np.stack([f("h_posx"), f("h_posy")], axis=1).astype(np.float64).reshape(HC, 2)
-        for n in ("h_status", "h_type", "h_group", "h_ammo", "h_target", "h_mission", "h_task", "h_det_task", "h_spawned"):
+        for n in ("h_status", "h_type", "h_group", "h_ammo", "h_target", "h_mission", "h_task", "h_det_task", "h_spawned",
+                  "h_intercept"):
             s[n] = i64(f(n))
         s["h_order"] = i64(f("h_order")[: s["n_thr_active"]])
         kn = f("known").reshape(KW, A)

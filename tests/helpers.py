@@ -241,13 +241,13 @@ class HostBackend:
 
     _hc = None
 
-    def __init__(self, opts, queue_cap=16):
+    def __init__(self, opts, queue_cap=16, task_cap="all"):
         if HostBackend._hc is None:
             HostBackend._hc = HostCheck()
         hc = HostBackend._hc
         self.lib = hc.lib
         self.opts = opts
-        self.cfg = _lib.build_config(opts, queue_cap=queue_cap)
+        self.cfg = _lib.build_config(opts, queue_cap=queue_cap, task_cap=task_cap)
         self.codec = state.RecordCodec(self.lib, self.cfg)
         d = self.lib.dll
         P = C.c_void_p

@@ -247,3 +247,62 @@ def test_oracle_tokens_and_observations_match_the_reference(case, seed):
         actions = apply_assign(ref, res)
         obs, _, _, _, info = ref.step(actions)
         orc.step([(ref.agent_by_name[n].id, i) for n, i in actions.items()])
+
+
+def _replay_stubs():
+    import sys
+    import types
+
+    refshim.install()
+    for name in ("tianshou", "tianshou.data", "TaskAllocation.RL_Policies.Tianshou_Policy"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["tianshou"].__path__ = []
+    sys.modules["tianshou.data"].Batch = dict
+    sys.modules["TaskAllocation.RL_Policies.Tianshou_Policy"]._get_model = lambda *a, **k: None
+    import experiments.generate_simulation_replay as G
+
+    return G
+
+
+@pytest.mark.parametrize("scenario", ["WPS_commit", "WPS_escort"])
+def test_replay_documents_are_identical(scenario, tmp_path):
+    """SURVEY 8(f) row 4.  (1) The reference's own replay generator (experiments/generate_simulation_replay.py), run
+    UNMODIFIED with the facade in place of MultiUAVEnv, writes the same document as on the reference environment --
+    every frame, task (closed ones included: the facade keeps the whole task history), threat, event and metric.
+    (2) multi_uav_ta_gym_env_b200.replay.record_replay produces that document too."""
+    from multi_uav_ta_gym_env_b200 import replay as myreplay
+    from multi_uav_ta_gym_env_b200.env import MultiUAVEnv
+
+    G = _replay_stubs()
+    want = G.generate(1, tmp_path / "ref.json", scenario=scenario)
+    RefEnv = G.MultiUAVEnv
+    G.MultiUAVEnv = lambda cfg: MultiUAVEnv(cfg, _test_backend_factory=lambda c: HostBackend(c))
+    try:
+        got = G.generate(1, tmp_path / "mine.json", scenario=scenario)
+    finally:
+        G.MultiUAVEnv = RefEnv
+    assert got == want
+    assert (tmp_path / "mine.json").read_bytes() == (tmp_path / "ref.json").read_bytes()
+
+    # the package's own emitter, driven by the reference planner on the facade
+    from TaskAllocation.Hybrid.AttentionCommit import UrgencyCommit
+    from TaskAllocation.Hybrid.AttentionEscort import UrgencyCoalition
+    from TaskAllocation.OptimizationBased.HungarianAllocator import HungarianAllocator as RefHung
+    from multi_uav_ta_gym_env_b200 import wps_config
+
+    cfg = wps_config(scenario)
+    env = MultiUAVEnv(cfg, _test_backend_factory=lambda c: HostBackend(c))
+    _, info = env.reset(seed=1)
+    hung = RefHung(10**9, env.max_coord)
+    if scenario == "WPS_escort":
+        planner = UrgencyCoalition()
+        plan = lambda e, ev: (planner.plan(e, hung, events=ev, force=True), [])
+    else:
+        planner = UrgencyCommit()
+
+        def plan(e, ev):
+            pairs, _, committed, _ = planner.plan(e, hung, events=ev, force=True)
+            return pairs, committed
+    doc = myreplay.record_replay(env, info, plan, cfg, scenario, 1)
+    assert doc == want

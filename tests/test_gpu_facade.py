@@ -57,3 +57,20 @@ def test_core_sim_shim():
         want = o._avoid(pos[0], pos[1], mv[0], mv[1])
         assert np.allclose(got, want, rtol=1e-9, atol=1e-12)
     assert core_sim.SimCore.avoid_obstacles([5.0, 5.0], [], [1.0, 0.0]) == [0.0, 0.0]
+
+
+@pytest.mark.parametrize("scenario,seed", [("WPS_commit", 2), ("WPS_escort", 3)])
+def test_replay_document_on_the_cuda_backend(scenario, seed):
+    """replay.record_replay (the reference web UI's replay file) from the facade on its CUDA backend:
+    same document as on the CPU build of the kernel core (tests/golden/replay_digests.json, made by
+    tests/golden/gen_replay_digests.py; the format itself is pinned against the reference generator in
+    tests/test_dropin_facade.py)."""
+    import json
+    import os
+
+    import gen_replay_digests as G
+
+    with open(os.path.join(os.path.dirname(G.__file__), "replay_digests.json")) as f:
+        want = json.load(f)[f"{scenario}:{seed}"]
+    got = G.replay_digest(scenario, seed)
+    assert got == want
