@@ -174,6 +174,43 @@ for _d in (0, 6, 12, 18):
     CASE_SPECS[f"WPS_attn_COP_cue_d{_d}"] = _attn_variant(sense_radius=0.0, threat_delay=_d, share_knowledge=True)
 
 
+# display names used by the result tables (experiments/paper_scenarios.py "label")
+CASE_LABELS = {'D1_attrition': 'Attrition (fail_rate=0.1)',
+ 'D2_popup_threats': 'Pop-up Threats',
+ 'D3_combined': 'Attrition+Threats',
+ 'WPS_attn': 'WPS Attn stress (multi-front)',
+ 'WPS_attn_AWACS': 'WPS Attn + full COP (AWACS/ground)',
+ 'WPS_attn_COP_R150': 'WPS Attn COP R=150 d=18',
+ 'WPS_attn_COP_R250': 'WPS Attn COP R=250 d=18',
+ 'WPS_attn_COP_R60': 'WPS Attn COP R=60 d=18',
+ 'WPS_attn_COP_R90': 'WPS Attn COP R=90 d=18',
+ 'WPS_attn_COP_cue_d0': 'WPS Attn COP cueing d=0 (share)',
+ 'WPS_attn_COP_cue_d12': 'WPS Attn COP cueing d=12 (share)',
+ 'WPS_attn_COP_cue_d18': 'WPS Attn COP cueing d=18 (share)',
+ 'WPS_attn_COP_cue_d6': 'WPS Attn COP cueing d=6 (share)',
+ 'WPS_attn_COP_d0': 'WPS Attn COP R=90 d=0',
+ 'WPS_attn_COP_d12': 'WPS Attn COP R=90 d=12',
+ 'WPS_attn_COP_d18': 'WPS Attn COP R=90 d=18',
+ 'WPS_attn_COP_d6': 'WPS Attn COP R=90 d=6',
+ 'WPS_attn_L': 'WPS Attn L (~30 agents)',
+ 'WPS_attn_OS18': 'WPS Attn oversized 18 agents (1.5x)',
+ 'WPS_attn_OS24': 'WPS Attn oversized 24 agents (2x)',
+ 'WPS_attn_XL': 'WPS Attn XL (~40 agents)',
+ 'WPS_burst': 'WPS Burst stress',
+ 'WPS_commit': 'WPS Commit (dual-front + rematch)',
+ 'WPS_easy': 'WPS Easy (windows+delay)',
+ 'WPS_escort': 'WPS Escort (coalition protect)',
+ 'WPS_hard': 'WPS Hard (tight+local+burst)',
+ 'agent_scaling_mid': 'Agent Scaling',
+ 'recon_strike_mix': 'Recon-Strike Mix',
+ 'scal_Agents_mid': 'Agent Scaling',
+ 'scal_None': 'Static Strike',
+ 'static_strike': 'Static Strike',
+ 'train_mixed': 'Recon-Strike Mix'}
+for _k, _v in CASE_LABELS.items():
+    CASE_SPECS[_k]["label"] = _v
+
+
 def burst_scaled_spec(k: int) -> Dict[str, Any]:
     """BASELINE config 5: WPS_burst with agents/tasks/threats scaled by k."""
     s = copy.deepcopy(CASE_SPECS["WPS_burst"])

@@ -851,3 +851,31 @@ def test_batched_collectors_match_the_oracle():
             want = otok.build_pair_tokens(o, 32, 16)
             for k in keys:
                 assert np.array_equal(nxt[k][e], want[k]), (t, e, k)
+
+
+def test_batched_evaluation_driver_reproduces_run_wps_episode():
+    """evaluate.run_episodes against the return dicts of the reference's run_wps_episode (experiments/wps_eval.py:76-290)
+    stored in tests/golden/wps_eval_scores.json (seeds 0-3): every score bit for bit.  algo_replans is compared for the
+    Hungarian allocators only -- the reference reuses one Urgency-* planner object across episodes, so its counter
+    accumulates over the seeds."""
+    import json
+
+    from multi_uav_ta_gym_env_b200 import evaluate
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wps_eval_scores.json")) as f:
+        golden = json.load(f)
+    for key, rows in golden.items():
+        case, algo = key.split("|")
+        got = evaluate.run_episodes(case, algo, len(rows))
+        for seed, want in enumerate(rows):
+            for k, v in want.items():
+                if k == "algo_replans" and algo.startswith("Urgency"):
+                    continue
+                w = float.fromhex(v)
+                assert got[seed][k] == w or (got[seed][k] != got[seed][k] and w != w), (key, seed, k, got[seed][k], w)
+    # row schemas of the reference CSVs
+    row = evaluate.summary_row("WPS", "WPS_hard", "Local-Hungarian", got, 1.0)
+    assert list(row)[:6] == ["exp", "case", "label", "algorithm", "episodes", "mean_S_WPS"] and "delta_on_time_ci_hi" in row
+    assert list(evaluate.episode_rows("WPS", "WPS_hard", "x", got)[0]) == [
+        "exp", "case", "algorithm", "seed", "S_WPS", "n_on_time", "n_missed_windows", "total_distance", "max_coord",
+        "on_time_rate", "reserve_idle_fraction"]
