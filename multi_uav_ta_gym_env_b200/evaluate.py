@@ -73,6 +73,7 @@ def run_episodes(case: str, algorithm: str, episodes: int, device="cuda:0", scor
         row["decision_ms_mean"] = float(ms)
         row["algo_replans"] = float(replans[e])
         row["max_coord"] = float(env.max_coord)
+        row["S_ESC"] = float(m[e, names.index("S_ESC")])  # escort_eval.py's score (not a wps_eval column)
         out.append(row)
     return out
 
