@@ -127,7 +127,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.idx), "-lms", os.environ.get("MUAV_SMI_PERIOD_MS", "100")], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -290,6 +290,7 @@ def run_gpu_arm(args):
            torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     launches["n"] = 0
     barrier()
+    t_enq = time.perf_counter()
     for k in range(K):
         t = k % EPISODE
         flush_buf.fill_(k & 0xFF)
@@ -301,7 +302,9 @@ def run_gpu_arm(args):
         ev[k][2].record()
         if t + 1 == EPISODE:
             episode_end()
+    enqueue_ms = (time.perf_counter() - t_enq) * 1e3 / K   # host time to enqueue one step (the GPU must not wait for it)
     barrier()
+    wall_ms = (time.perf_counter() - t_enq) * 1e3 / K      # wall clock per step including the L2 flush between steps
     clocks = sampler.stop(first_sample)
     err_flags = max(int(env.error_flags().abs().max().item()), int(err_acc.item()))  # overflow bits: must stay 0
     step_ms = sum(a.elapsed_time(c) for a, b, c in ev)
@@ -359,7 +362,8 @@ def run_gpu_arm(args):
             "config": {"workload": f"{case_name} ({A} agents), {E} envs per GPU, {desc}, seeds = env index",
                        "envs_per_gpu": E, "global_envs": world * E, "parallelism": f"env-shard x{world}",
                        "l2": f"flushed between timed steps (256 MB write); state {E * rb / 1e6:.0f} MB vs 126 MB L2",
-                       "record_bytes": rb, "task_slots": int(env.task_cap), "agent_steps_per_s": value * A},
+                       "record_bytes": rb, "task_slots": int(env.task_cap), "agent_steps_per_s": value * A,
+                       "host_enqueue_ms_per_step": enqueue_ms, "wall_ms_per_step_incl_flush": wall_ms},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes,
                     "d2h_bytes_per_step": act_bytes + E * 10, "steps": Ke},
             "gpu_launches": gpu_launches,
