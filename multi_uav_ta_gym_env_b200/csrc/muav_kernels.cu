@@ -53,7 +53,9 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// wait until the bulk stores have READ their shared-memory source (the CTA may then exit and free it); the global writes
+// themselves complete before the grid does
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 struct StepParams {
   muav_config cfg;
