@@ -185,7 +185,7 @@ def run_gpu_arm(args):
     import torch.distributed as dist
 
     from multi_uav_ta_gym_env_b200 import AllocSpec, BatchedMultiUAVEnv, sharding, wps_config
-    from multi_uav_ta_gym_env_b200.scorers import AttPairNet, FusedAttPairScorer
+    from multi_uav_ta_gym_env_b200.scorers import AttContextPairNet, AttPairNet, FusedAttPairScorer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -199,8 +199,12 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     # workload: the default is BASELINE config 2; the others are BASELINE configs 3-5 (extra lines for profiles/)
     wl = args.workload
-    use_scorer = wl == "hard_pair"
-    if wl == "hard_pair":
+    use_scorer = wl in ("hard_pair", "attn_context")
+    if wl == "attn_context":
+        # the paper's primary method: Att-ContextPair on WPS_attn (12 agents, dual-front bursts, private knowledge)
+        case_name, cfg, spec = "WPS_attn", wps_config("WPS_attn"), AllocSpec.pair_hybrid(HYBRID_INTERVAL)
+        desc = "Local-Hungarian + random-init Att-ContextPair edge scores, hybrid replan rule t%15/events"
+    elif wl == "hard_pair":
         case_name, cfg, spec = CASE, wps_config(CASE), AllocSpec.pair_hybrid(HYBRID_INTERVAL)
         desc = "Local-Hungarian + random-init Att-Pair edge scores, hybrid replan rule t%15/events"
     elif wl == "hard_local":
@@ -228,10 +232,11 @@ def run_gpu_arm(args):
     torch.manual_seed(0)
     scores = tok = scorer = None
     if use_scorer:
-        net = AttPairNet().to(dev).eval()
+        ctx = wl == "attn_context"
+        net = (AttContextPairNet() if ctx else AttPairNet()).to(dev).eval()
         scores = torch.zeros(E, 16, 32, dtype=torch.float32, device=dev)
         # the step kernel emits the pair tokens of every env that will replan before the next step
-        tok = env.enable_fused_tokens(32, 16, HYBRID_INTERVAL, 0b111)
+        tok = env.enable_fused_tokens(32, 16, HYBRID_INTERVAL, 0b111, context=ctx)
         scorer = FusedAttPairScorer(net, dev)   # hand-written fused forward (csrc/muav_scorer.cu)
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     metric_acc = torch.zeros(32, dtype=torch.float64, device=dev)
@@ -463,7 +468,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
     ap.add_argument("--workload", default="hard_pair",
-                    help="hard_pair (default, BASELINE config 2) | hard_local | commit_urgency | escort_coalition | burst_xK")
+                    help="hard_pair (default, BASELINE config 2) | hard_local | commit_urgency | escort_coalition | burst_xK "
+                         "| attn_context")
     ap.add_argument("--task-cap", type=int, default=0, help="task slots per environment (0 = workload default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

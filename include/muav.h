@@ -150,6 +150,7 @@ typedef struct muav_token_out {
   int32_t* d_task_ids;    /* [E, max_tasks] */
   uint8_t* d_need;        /* [E] */
   int32_t max_tasks, max_agents, interval, event_mask;
+  float* d_context;       /* optional [E, 8]: build_context_summary (ContextPairHybrid.py:33-70) of the same tokens */
 } muav_token_out;
 
 const char* muav_version(void);
@@ -270,11 +271,20 @@ typedef struct muav_attpair_offsets {
   int32_t enc_n1_w, enc_n1_b, enc_n2_w, enc_n2_b;
   int32_t a2t_in_w, a2t_in_b, a2t_out_w, a2t_out_b, t2a_in_w, t2a_in_b, t2a_out_w, t2a_out_b;
   int32_t head1_w, head1_b, head2_w, head2_b, head3_w, head3_b;
+  /* AttContextPairNet (ContextPairHybrid.py:81-151) only, else 0: ctx_proj [8 -> 64]; head1_w then has 256 input rows
+   * (agent, task, product, context) instead of 192 */
+  int32_t ctx_proj_w, ctx_proj_b, has_context;
 } muav_attpair_offsets;
 int muav_att_pair_scores(const float* d_params, const muav_attpair_offsets* offsets, const float* d_task_feats,
                          const uint8_t* d_task_mask, const float* d_agent_feats, const uint8_t* d_agent_mask,
                          const float* d_edge_valid, const int32_t* d_env_idx, const uint8_t* d_need, int n, int max_tasks,
                          int max_agents, float score_clamp, float* d_scores, void* stream);
+/* Same kernel for AttContextPairNet: d_context [E, 8] (offsets->has_context must be set). */
+int muav_att_context_pair_scores(const float* d_params, const muav_attpair_offsets* offsets, const float* d_task_feats,
+                                 const uint8_t* d_task_mask, const float* d_agent_feats, const uint8_t* d_agent_mask,
+                                 const float* d_edge_valid, const float* d_context, const int32_t* d_env_idx,
+                                 const uint8_t* d_need, int n, int max_tasks, int max_agents, float score_clamp,
+                                 float* d_scores, void* stream);
 
 #ifdef __cplusplus
 }

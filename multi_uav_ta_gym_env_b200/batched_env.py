@@ -162,7 +162,7 @@ class BatchedMultiUAVEnv:
         self.records.copy_(self._records0)
 
     # ------------------------------------------------------------------ fused token emission
-    def enable_fused_tokens(self, max_tasks=32, max_agents=16, interval=15, event_mask=HYBRID_EVENTS):
+    def enable_fused_tokens(self, max_tasks=32, max_agents=16, interval=15, event_mask=HYBRID_EVENTS, context=False):
         """Ask the step kernel to emit pair tokens for the environments that will replan before the next
         step (muav_token_out).  Returns the token dict (tensors are updated in place by every step) with
         `need` u8[E]."""
@@ -176,6 +176,8 @@ class BatchedMultiUAVEnv:
             "task_ids": torch.zeros(E, max_tasks, dtype=torch.int32, device=dev),
             "need": torch.zeros(E, dtype=torch.uint8, device=dev),
         }
+        if context:   # build_context_summary of the same tokens (ContextPairHybrid.py:33-70)
+            tok["context"] = torch.zeros(E, 8, dtype=torch.float32, device=dev)
         T = _lib.MuavTokenOut()
         T.d_task_feats = tok["task_feats"].data_ptr()
         T.d_task_mask = tok["task_mask_u8"].data_ptr()
@@ -184,6 +186,7 @@ class BatchedMultiUAVEnv:
         T.d_edge_valid = tok["edge_valid"].data_ptr()
         T.d_task_ids = tok["task_ids"].data_ptr()
         T.d_need = tok["need"].data_ptr()
+        T.d_context = tok["context"].data_ptr() if context else None
         T.max_tasks, T.max_agents, T.interval, T.event_mask = max_tasks, max_agents, interval, event_mask
         self._tok = T
         self.fused_tokens = tok
@@ -192,9 +195,14 @@ class BatchedMultiUAVEnv:
     def refresh_fused_tokens(self):
         """Fill the fused token tensors for ALL environments with the standalone kernel (after reset/restore)."""
         tok, T = self.fused_tokens, self._tok
-        rc = self.lib.dll.muav_tokens_pair(C.byref(self.cfg), self.records.data_ptr(), T.max_tasks, T.max_agents,
-                                           T.d_task_feats, T.d_task_mask, T.d_agent_feats, T.d_agent_mask,
-                                           T.d_edge_valid, T.d_task_ids, self.n_envs, self._stream())
+        if T.d_context:
+            rc = self.lib.dll.muav_tokens_context(C.byref(self.cfg), self.records.data_ptr(), T.max_tasks, T.max_agents, 0,
+                                                  T.d_task_feats, T.d_task_mask, T.d_agent_feats, T.d_agent_mask,
+                                                  T.d_edge_valid, T.d_task_ids, T.d_context, self.n_envs, self._stream())
+        else:
+            rc = self.lib.dll.muav_tokens_pair(C.byref(self.cfg), self.records.data_ptr(), T.max_tasks, T.max_agents,
+                                               T.d_task_feats, T.d_task_mask, T.d_agent_feats, T.d_agent_mask,
+                                               T.d_edge_valid, T.d_task_ids, self.n_envs, self._stream())
         _lib.check(rc, "muav_tokens_pair")
         tok["need"].fill_(1)
         self.launches += 1

@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
         tokens_pair_env(V, P.cfg, mt, ma, P.tok.d_task_feats + (size_t)e * mt * 13, P.tok.d_task_mask + (size_t)e * mt,
                         P.tok.d_agent_feats + (size_t)e * ma * 12, P.tok.d_agent_mask + (size_t)e * ma,
                         P.tok.d_edge_valid + (size_t)e * ma * mt, P.tok.d_task_ids + (size_t)e * mt, (int16_t*)scratch,
-                        lane, 32);
+                        lane, 32, 12, 0, P.tok.d_context ? P.tok.d_context + (size_t)e * 8 : nullptr);
       }
       __syncwarp();
     }

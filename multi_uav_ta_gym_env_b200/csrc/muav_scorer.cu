@@ -38,6 +38,7 @@ struct Params {
   const float* agent_feats;
   const uint8_t* agent_mask;
   const float* edge_valid;
+  const float* context;  // [E, 8] or NULL (AttContextPairNet)
   const int32_t* env_idx;
   const uint8_t* need;
   float* scores;
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
   __shared__ uint8_t s_seg_of[TS];
   __shared__ int s_nseg, s_R, s_split, s_npairs, s_next, s_nvalid;
   __shared__ uint16_t s_plist[1024];  // pairs of this pass whose edge is valid (the others keep their zero score)
+  __shared__ float s_ctx[GMAX][D];    // AttContextPairNet: ctx_proj(context) + pooled encoder output, then Wc ctx
   const int tid = threadIdx.x;
   const int MT = P.max_tasks, MA = P.max_agents;
   const float* w = P.w;
@@ -352,6 +354,22 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
     linear_t(z_t, 0, R, D, lin1(w + o.enc_l1_w, w + o.enc_l1_b), FF, FF, big_t, nullptr, true);  // hidden
     linear_t(big_t, 0, R, FF, lin1(w + o.enc_l2_w, w + o.enc_l2_b), D, D, x_t, z_t, false);      // x = x1 + FF(x1)
     layer_norm_t(x_t, R, w + o.enc_n2_w, w + o.enc_n2_b);                                    // x = h (encoder output)
+    if (o.has_context) {
+      // ctx = ctx_proj(context) + mean of h over the environment's tokens (ContextPairHybrid.py:140-142)
+      for (int idx = tid; idx < nseg * D; idx += NT) {
+        const int g = idx / D, k = idx - g * D;
+        const Seg sg = s_seg[g];
+        float sum = 0.0f;
+        for (int r = 0; r < sg.na; ++r) sum += x_t[k * TS + sg.abase + r];
+        for (int r = 0; r < sg.nt; ++r) sum += x_t[k * TS + sg.tbase + r];
+        float c = w[o.ctx_proj_b + k];
+        const float* cx = P.context + (size_t)sg.e * 8;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) c = fmaf(cx[q], w[o.ctx_proj_w + q * D + k], c);
+        s_ctx[g][k] = c + sum / (float)(sg.na + sg.nt);
+      }
+      __syncthreads();
+    }
 
     // ---- cross attention (both use the ORIGINAL h): a' = a + MHA_a2t(a, t, t); t' = t + MHA_t2a(t, a, a), merged:
     // agent tiles take q from cross_a2t and k, v from cross_t2a (they are keys of the task queries); task tiles the
@@ -379,6 +397,17 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
       w2t[oo * 36 + p] = w[o.head2_w + (size_t)oo * 32 + p];  // head2^T is [64][32]
     }
     __syncthreads();
+    if (o.has_context) {
+      // per-environment context term of the first head layer: hc[o] = sum_k Wc[o][k] ctx[k] (head1 rows 192..255),
+      // computed in place (a thread reads the whole ctx vector of its environment before it writes)
+      float hc = 0.0f;
+      const int g = tid / D, oo = tid - g * D;
+      if (g < nseg)
+        for (int k = 0; k < D; ++k) hc = fmaf(w[o.head1_w + (size_t)(3 * D + k) * D + oo], s_ctx[g][k], hc);
+      __syncthreads();
+      if (g < nseg) s_ctx[g][oo] = hc;
+      __syncthreads();
+    }
     // only pairs with a valid edge are evaluated: scores = tanh(logit) * clamp * edge_valid is zero for the others
     for (int pr = tid; pr < s_npairs; pr += NT) {
       int g = 0;
@@ -426,7 +455,7 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
           acc = fmaf(ww.w, u[4 * d4 + 3], acc);
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc = fmaxf(acc + y_t[oo * TS + ta] + x_t[oo * TS + tt], 0.0f);
+        acc = fmaxf(acc + y_t[oo * TS + ta] + x_t[oo * TS + tt] + (o.has_context ? s_ctx[g][oo] : 0.0f), 0.0f);
         const float4* w2 = (const float4*)&w2t[oo * 36 + p0];
 #pragma unroll
         for (int p4 = 0; p4 < 4; ++p4) {
@@ -453,11 +482,30 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
 
 }  // namespace muav_scorer
 
+extern "C" int muav_att_context_pair_scores(const float* d_params, const muav_attpair_offsets* offsets,
+                                            const float* d_task_feats, const uint8_t* d_task_mask,
+                                            const float* d_agent_feats, const uint8_t* d_agent_mask,
+                                            const float* d_edge_valid, const float* d_context, const int32_t* d_env_idx,
+                                            const uint8_t* d_need, int n, int max_tasks, int max_agents, float score_clamp,
+                                            float* d_scores, void* stream);
+
 extern "C" int muav_att_pair_scores(const float* d_params, const muav_attpair_offsets* offsets, const float* d_task_feats,
                                     const uint8_t* d_task_mask, const float* d_agent_feats, const uint8_t* d_agent_mask,
                                     const float* d_edge_valid, const int32_t* d_env_idx, const uint8_t* d_need, int n,
                                     int max_tasks, int max_agents, float score_clamp, float* d_scores, void* stream) {
+  if (offsets && offsets->has_context) return -22;
+  return muav_att_context_pair_scores(d_params, offsets, d_task_feats, d_task_mask, d_agent_feats, d_agent_mask, d_edge_valid,
+                                      nullptr, d_env_idx, d_need, n, max_tasks, max_agents, score_clamp, d_scores, stream);
+}
+
+extern "C" int muav_att_context_pair_scores(const float* d_params, const muav_attpair_offsets* offsets,
+                                            const float* d_task_feats, const uint8_t* d_task_mask,
+                                            const float* d_agent_feats, const uint8_t* d_agent_mask,
+                                            const float* d_edge_valid, const float* d_context, const int32_t* d_env_idx,
+                                            const uint8_t* d_need, int n, int max_tasks, int max_agents, float score_clamp,
+                                            float* d_scores, void* stream) {
   using namespace muav_scorer;
+  if (offsets && ((offsets->has_context != 0) != (d_context != nullptr))) return -22;
   if (!d_params || !offsets || !d_task_feats || !d_task_mask || !d_agent_feats || !d_agent_mask || !d_edge_valid || !d_scores)
     return -22;
   if (n < 0 || max_tasks < 1 || max_agents < 1 || max_agents + max_tasks > 48 || max_agents > 16) return -22;
@@ -470,6 +518,7 @@ extern "C" int muav_att_pair_scores(const float* d_params, const muav_attpair_of
   P.agent_feats = d_agent_feats;
   P.agent_mask = d_agent_mask;
   P.edge_valid = d_edge_valid;
+  P.context = d_context;
   P.env_idx = d_env_idx;
   P.need = d_need;
   P.scores = d_scores;

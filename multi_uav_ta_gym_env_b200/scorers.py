@@ -505,12 +505,14 @@ class FusedAttPairScorer:
         ("head2_b", "pair_head.2.bias"), ("head3_w", "pair_head.4.weight"), ("head3_b", "pair_head.4.bias"),
     ]
 
-    def __init__(self, net: AttPairNet, device, score_clamp: float = SCORE_CLAMP):
+    def __init__(self, net, device, score_clamp: float = SCORE_CLAMP):
+        """net: AttPairNet or AttContextPairNet (the context vector then comes from tok["context"])."""
         import ctypes as C
 
         from . import _lib
 
         sd = net.state_dict()
+        self.has_context = "ctx_proj.weight" in sd
         if len(net.self_encoder.layers) != 1 or sd["task_proj.weight"].shape != (64, TASK_FEAT_DIM) \
                 or sd["self_encoder.layers.0.linear1.weight"].shape != (128, 64) \
                 or net.cross_a2t.num_heads != 4:
@@ -518,7 +520,13 @@ class FusedAttPairScorer:
         self.lib = _lib.cuda_lib()
         self.offsets = _lib.MuavAttPairOffsets()
         chunks, pos = [], 0
-        for field, key in self._ORDER:
+        order = list(self._ORDER)
+        if self.has_context:
+            if sd["pair_head.0.weight"].shape != (64, 256) or sd["ctx_proj.weight"].shape != (64, 8):
+                raise ValueError("the fused kernel implements the default AttContextPairNet (context_dim 8)")
+            order += [("ctx_proj_w", "ctx_proj.weight"), ("ctx_proj_b", "ctx_proj.bias")]
+        self.offsets.has_context = int(self.has_context)
+        for field, key in order:
             t = sd[key].detach().to(torch.float32)
             if t.dim() == 2 and field != "type_embed":
                 t = t.t().contiguous()  # the kernel streams W^T ([in][out]) rows as float4
@@ -547,11 +555,12 @@ class FusedAttPairScorer:
             return
         if idx is not None and idx.dtype != torch.int32:
             idx = idx.to(torch.int32)
-        rc = self.lib.dll.muav_att_pair_scores(
+        rc = self.lib.dll.muav_att_context_pair_scores(
             self.params.data_ptr(), C.byref(self.offsets), tok["task_feats"].data_ptr(), tok["task_mask_u8"].data_ptr(),
             tok["agent_feats"].data_ptr(), tok["agent_mask_u8"].data_ptr(), tok["edge_valid"].data_ptr(),
+            tok["context"].data_ptr() if self.has_context else None,
             None if idx is None else idx.data_ptr(), tok["need"].data_ptr() if use_need else None, n, MT, MA,
             C.c_float(self.clamp), scores_out.data_ptr(),
             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         if rc != 0:
-            raise RuntimeError(f"muav_att_pair_scores failed: {rc}")
+            raise RuntimeError(f"muav_att_context_pair_scores failed: {rc}")

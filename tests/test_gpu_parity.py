@@ -879,3 +879,36 @@ def test_batched_evaluation_driver_reproduces_run_wps_episode():
     assert list(evaluate.episode_rows("WPS", "WPS_hard", "x", got)[0]) == [
         "exp", "case", "algorithm", "seed", "S_WPS", "n_on_time", "n_missed_windows", "total_distance", "max_coord",
         "on_time_rate", "reserve_idle_fraction"]
+
+
+def test_fused_context_scorer_kernel_and_fused_context_emission():
+    """The fused scorer kernel with AttContextPairNet weights (context term of the pair head, pooled encoder output)
+    against the PyTorch module on real WPS_attn tokens, and the context vector emitted by the step kernel against the
+    standalone token kernel."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+    from multi_uav_ta_gym_env_b200.scorers import AttContextPairNet, FusedAttPairScorer, context_pair_scores
+
+    cfg = wps_config("WPS_attn")
+    E = 120
+    env = make_env(cfg, list(range(E)))
+    tok = env.enable_fused_tokens(32, 16, 15, 0b111, context=True)
+    env.refresh_fused_tokens()
+    torch.manual_seed(2)
+    net = AttContextPairNet().cuda().eval()
+    fused = FusedAttPairScorer(net, torch.device("cuda"))
+    spec = AllocSpec.pair_hybrid(15)
+    scores = torch.zeros(E, 16, 32, dtype=torch.float32, device="cuda")
+    checked = 0
+    for t in range(75):
+        ref = env.tokens_context(32, 16)
+        need = tok["need"].bool()
+        if need.any():
+            for k, kf in (("task_feats", "task_feats"), ("agent_feats", "agent_feats"), ("edge_valid", "edge_valid"),
+                          ("context", "context")):
+                assert torch.equal(tok[kf][need], ref[k][need]), (t, k)
+            want = context_pair_scores(net, ref)
+            fused.score(tok, scores, use_need=True)
+            assert (scores[need] - want[need]).abs().max().item() < 2e-5, (t, (scores[need] - want[need]).abs().max().item())
+            checked += int(need.sum().item())
+        env.step_allocated(spec, 1, edge_scores=scores)
+    assert checked > 500 and int(env.error_flags().abs().max().item()) == 0

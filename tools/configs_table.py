@@ -7,6 +7,7 @@ rows = [("hard_pair (2: WPS_hard, Local-Hungarian + Att-Pair scores) — default
         ("hard_local (WPS_hard, plain Local-Hungarian: the north_star target shape)", "r01_bench_hard_local"),
         ("commit_urgency (3: WPS_commit, UrgencyCommit planner on device)", "r01_bench_commit_urgency"),
         ("escort_coalition (4: WPS_escort, Coalition-Hungarian 12)", "r01_bench_escort_coalition"),
+        ("attn_context (WPS_attn, Att-ContextPair: the paper's primary method; fused context scorer)", "r01_bench_attn_context"),
         ("burst_x2 (5)", "r01_bench_burst_x2"), ("burst_x4 (5)", "r01_bench_burst_x4"), ("burst_x8 (5)", "r01_bench_burst_x8")]
 print("| workload (BASELINE config) | agents | envs | env-steps/s | agent-steps/s | ms/step | e2e env-steps/s | record B | frac (B_alg) | record I/O GB/s | error_flags |")
 print("|---|---|---|---|---|---|---|---|---|---|---|")
