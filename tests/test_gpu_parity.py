@@ -912,3 +912,26 @@ def test_fused_context_scorer_kernel_and_fused_context_emission():
             checked += int(need.sum().item())
         env.step_allocated(spec, 1, edge_scores=scores)
     assert checked > 500 and int(env.error_flags().abs().max().item()) == 0
+
+
+def test_two_kernel_split_step_gives_the_same_states(monkeypatch):
+    """muav_step_out.d_actions_ws: a fused single step run as allocator kernel (environments that do not replan leave after
+    reading their header) + step-only kernel (small scratch) must equal the one-kernel form bit for bit."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+
+    cfg = wps_config("WPS_hard")
+    seeds = list(range(40))
+    one = make_env(cfg, seeds)
+    monkeypatch.setenv("MUAV_SPLIT_STEP", "1")
+    two = make_env(cfg, seeds)
+    assert two._actions_ws is not None and one._actions_ws is None
+    for spec in (AllocSpec.local_hungarian(20), AllocSpec.urgency_pair(15)):
+        one.restore()
+        two.restore()
+        for t in range(150):
+            one.step_allocated(spec, 1)
+            two.step_allocated(spec, 1)
+            if t % 10 == 9 or t == 149:
+                assert torch.equal(one.records, two.records), t
+                assert torch.equal(one.pairs[:, :1], two.pairs[:, :1]) and torch.equal(one.n_pairs, two.n_pairs)
+                assert torch.equal(one.reward, two.reward)
