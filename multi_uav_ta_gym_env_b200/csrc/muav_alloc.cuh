@@ -234,12 +234,23 @@ MUAV_HD MUAV_NI_A inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, in
       // open task list (+ residuals, + pair-token column of each task)
       int tok_j = 0;
       const int32_t* order = O.d_task_order ? O.d_task_order + (size_t)e * IC : nullptr;
-      for (int it = 0; it < (order ? IC : n_tasks); ++it) {
-        int k = it;
+      // without a caller-given order the candidates are the ids set in open_mask: the allocator runs at a step
+      // boundary, where the mask of the last scan is exact, so closed ids (most of them in WPS_escort) are never touched
+      const int KWn = (n_tasks + 31) >> 5;
+      int wd = 0;
+      uint32_t bits = order ? 0u : (KWn > 0 ? V.open_mask()[0] : 0u);
+      for (int it = 0;; ++it) {
+        int k;
         if (order) {
+          if (it >= IC) break;
           k = order[it];
           if (k < 0) break;
           if (k >= n_tasks) continue;
+        } else {
+          while (!bits && ++wd < KWn) bits = V.open_mask()[wd];
+          if (!bits) break;
+          k = (wd << 5) + ctz32(bits);
+          bits &= bits - 1;
         }
         if (V.k_status()[k] == 2) continue;
         int col = -1;

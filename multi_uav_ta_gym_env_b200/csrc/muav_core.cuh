@@ -29,6 +29,14 @@ enum { EV_RESET = 0, EV_FAIL = 1, EV_THREAT = 2, EV_ESC_CREATED = 3, EV_ESC_RETI
 
 // Out of line on purpose: float64 sqrt / divide expand to ~25 SASS instructions each; the kernel is
 // instruction-fetch bound (profiles/r01_step_kernel_ncu.md), so all call sites share one copy.
+// index of the lowest set bit (x != 0)
+MUAV_HD inline int ctz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x) - 1;
+#else
+  return __builtin_ctz(x);
+#endif
+}
 MUAV_HD MUAV_NOINLINE_LEAF inline double norm2(double x, double y) { return sqrt(fma(y, y, x * x)); }
 MUAV_HD MUAV_NOINLINE_LEAF inline double norm2_rows(double x, double y) { return sqrt(x * x + y * y); }
 MUAV_HD MUAV_NOINLINE_LEAF inline double ddiv(double a, double b) { return a / b; }
@@ -471,8 +479,11 @@ struct Sim {
         }
       }
     }
-    int n = HIv(N_TASKS);
-    for (int k = 0; k < n; ++k) {
+    // only the tasks that were open at the last scan can be open now (events are drained first thing in a step)
+    const int KWn = (HIv(N_TASKS) + 31) >> 5;
+    for (int wd = 0; wd < KWn; ++wd)
+    for (uint32_t bits = V.open_mask()[wd]; bits; bits &= bits - 1) {
+      const int k = (wd << 5) + ctz32(bits);
       if (V.k_status()[k] != 2 && V.k_type()[k] == for_type) {
         bool any = false;
         for (int ut = 0; ut < MUAV_N_UAV_TYPES; ++ut)
@@ -874,11 +885,26 @@ struct Sim {
     if (C().sense_radius <= 0) return;
     int n = HIv(N_TASKS);
     int Aa = A();
-    for (int idx = lane; idx < Aa * n; idx += nlanes) {
-      int a = idx / n, k = idx - a * n;
+    // candidates = tasks that are open and dynamic, compacted first (WPS_escort creates ~250 ids of which ~25 are open)
+    int16_t* cand = (int16_t*)(scratch + ((8 * 4 * Aa + 2 * Aa + 16 + 15) & ~15));
+    int m = 0;
+#if defined(__CUDA_ARCH__)
+    for (int base = 0; base < n; base += 32) {
+      const int k = base + lane;
+      const bool c = k < n && V.k_status()[k] != 2 && !(V.k_created()[k] <= 0 && V.k_deadline()[k] < 0);
+      const unsigned mk = __ballot_sync(0xffffffffu, c);
+      if (c) cand[m + __popc(mk & ((1u << lane) - 1u))] = (int16_t)k;
+      m += __popc(mk);
+    }
+    __syncwarp();
+#else
+    for (int k = 0; k < n; ++k)
+      if (V.k_status()[k] != 2 && !(V.k_created()[k] <= 0 && V.k_deadline()[k] < 0)) cand[m++] = (int16_t)k;
+#endif
+    for (int idx = lane; idx < Aa * m; idx += nlanes) {
+      int a = idx / m, k = cand[idx - a * m];
       if (V.a_state()[a] == -1) continue;
-      if (V.k_status()[k] == 2 || known_bit(a, k)) continue;
-      if (V.k_created()[k] <= 0 && V.k_deadline()[k] < 0) continue;
+      if (known_bit(a, k)) continue;
       double d = norm2(V.a_posx()[a] - V.k_posx()[k], V.a_posy()[a] - V.k_posy()[k]);
       if (d <= C().sense_radius) {
 #if defined(__CUDA_ARCH__)
