@@ -479,15 +479,17 @@ struct Sim {
         }
       }
     }
+    // can any remaining agent type still serve this task type?  (the same answer for every task of the type)
+    bool any = false;
+    if (for_type >= 0)
+      for (int ut = 0; ut < MUAV_N_UAV_TYPES; ++ut)
+        if (((avail >> ut) & 1u) && C().cap_table[ut][for_type] != 0.0) any = true;
     // only the tasks that were open at the last scan can be open now (events are drained first thing in a step)
     const int KWn = (HIv(N_TASKS) + 31) >> 5;
     for (int wd = 0; wd < KWn; ++wd)
     for (uint32_t bits = V.open_mask()[wd]; bits; bits &= bits - 1) {
       const int k = (wd << 5) + ctz32(bits);
       if (V.k_status()[k] != 2 && V.k_type()[k] == for_type) {
-        bool any = false;
-        for (int ut = 0; ut < MUAV_N_UAV_TYPES; ++ut)
-          if (((avail >> ut) & 1u) && C().cap_table[ut][for_type] != 0.0) any = true;
         if (!any) {
           close_task(k);
           if (!V.k_reached()[k]) {
