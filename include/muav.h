@@ -23,8 +23,16 @@
  *   muav_tokens_escort        -> build_escort_tokens           TaskAllocation/Hybrid/AttentionEscort.py:76-241
  *   muav_observe              -> _generate_observations/get_task_info  mUAV_TA/DroneEnv.py:365-492
  *   muav_metrics              -> calculate_metrics / compute_s_wps / compute_s_esc  DroneEnv.py:1231-1337,2002-2011
- *   muav_field_info / muav_record_bytes: layout of one environment record (host packing at reset,
- *                                snapshots for the object proxies); reset itself (DroneEnv.py:522-762) stays in Python.
+ *   muav_pair_mask            -> _expert_mask / _selected_mask experiments/train_pair_cost.py:53-70, PairCostHybrid.py:293-306
+ *   muav_att_pair_scores, muav_att_context_pair_scores
+ *                             -> AttPairNet / AttContextPairNet forward + act(explore=False)
+ *                                                              PairCostHybrid.py:89-151,266-278, ContextPairHybrid.py:81-151,235-246
+ *   muav_alloc_opts.planner   -> UrgencyPair / UrgencyCommit / UrgencyCoalition .plan, AttentionCommit / AttentionEscort
+ *                                ._plan_from_scores            PairCostHybrid.py:520-550, AttentionCommit.py:266-357,
+ *                                                              AttentionEscort.py:500-517,720-767
+ *   muav_reset_upload / muav_state_bytes / muav_tape_bytes / muav_snapshot / muav_field_info / muav_record_bytes:
+ *                                device-resident state that replaces the UAV / Task / Threat objects (host packing at
+ *                                reset, snapshots for the object proxies); reset itself (DroneEnv.py:522-762) stays in Python.
  */
 #ifndef MUAV_H_
 #define MUAV_H_
