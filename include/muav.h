@@ -103,7 +103,10 @@ typedef struct muav_alloc_opts {
                                 muav_tokens_escort layout over d_task_order, committed agents reserved, every assigned
                                 agent locked for commit_horizon;
                               5 UrgencyPair.plan (PairCostHybrid.py:520-550): urgency_edge_scores (:68-86) on the valid
-                                edges of build_pair_tokens(score_cols = max_tasks, score_rows = max_agents), no locks */
+                                edges of build_pair_tokens(score_cols = max_tasks, score_rows = max_agents), no locks;
+                              6 PerformanceImpact.allocate_tasks(max_tasks_per_agent=1) (MarketBased/PerformanceImpact.py:59-224,
+                                slots and eligibility from MarketBased/CBBA.py:27-65) instead of the Hungarian allocator:
+                                mode / replan_interval / event_mask / use_visibility / d_reserved as for planner 0 */
   int32_t order_hint_mode; /* mode == 0 only (actions come from the caller): the replan rule (1 / 2 / 3, with replan_interval,
                               event_mask and planner as above) that the caller's allocator follows, used solely to fill
                               muav_step_out.d_env_order_next; 0 = no hint */

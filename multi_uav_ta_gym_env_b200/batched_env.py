@@ -34,7 +34,8 @@ class AllocSpec:
     pair_tokens: bool = False
     max_coord: float = 1200.0
     planner: int = 0              # 1: UrgencyCommit.plan, 2: UrgencyCoalition.plan (device-side planners),
-                                  # 3: AttentionCommit._plan_from_scores, 4: AttentionEscort._plan_from_scores
+                                  # 3: AttentionCommit._plan_from_scores, 4: AttentionEscort._plan_from_scores,
+                                  # 5: UrgencyPair.plan, 6: PerformanceImpact.allocate_tasks(max_tasks_per_agent=1)
     commit_fraction: float = 0.35
     commit_threshold: float = 0.5
 
@@ -49,6 +50,12 @@ class AllocSpec:
     @staticmethod
     def coalition_hungarian(interval=12):
         return AllocSpec(1, interval, ALL_EVENTS, True, False)
+
+    @staticmethod
+    def performance_impact(interval=20):
+        """Local-PI / Local-PI-Coalition (MarketBased/PerformanceImpact.py:59-224 with max_tasks_per_agent=1) under its own
+        should_replan rule, as experiments/wps_eval.py:147-159 (interval 20) and escort_eval.py:162-174 (12) run it."""
+        return AllocSpec(1, interval, ALL_EVENTS, True, False, planner=6)
 
     @staticmethod
     def pair_hybrid(interval=15):

@@ -420,6 +420,213 @@ MUAV_HD MUAV_NI_A inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, in
   return n_pairs;
 }
 
+// ---- Performance-Impact market allocator (TaskAllocation/MarketBased/PerformanceImpact.py:59-224) --------------------
+// as the reference's drivers call it: max_tasks_per_agent = 1 (experiments/wps_eval.py:147-156, escort_eval.py:162-170).
+// With one task per agent every path has at most one slot, so
+//   IPI(agent, slot) = provisional RPI = RPI of the winner = _path_cost([slot])                       (:243-261,263-301)
+//                    = start [+ 200 + (start - deadline) if start > deadline] - 5 cap',   start = max(nft, t) + dist / speed
+// is a constant of the call: it is computed once per (agent, open task) over the lanes, and the inclusion loop (:106-165)
+// is a repeated lane-parallel arg-min of (IPI, agent id, slot key) under the steal rule (:132-140).  The consensus phase
+// (:168-205) cannot change anything in this case (each slot has one claimant and the deadline filter repeats the test the
+// inclusion phase already made).  Slot keys are compared as the reference compares them: as the STRINGS "<id>#c<k>" /
+// "<id>#r<k>" (CBBA.py:46-65), i.e. ids in lexicographic decimal order.
+
+// "<x>#" < "<y>#" as strings ('#' sorts before every digit)
+MUAV_HD inline bool slot_id_less(int x, int y) {
+  int nx = 1, ny = 1, px = 10, py = 10;
+  while (x >= px) { px *= 10; ++nx; }
+  while (y >= py) { py *= 10; ++ny; }
+  if (nx == ny) return x < y;
+  if (nx < ny) {
+    int sh = 1;
+    for (int i = nx; i < ny; ++i) sh *= 10;
+    return x <= y / sh;   // equal prefix: the shorter string is smaller
+  }
+  int sh = 1;
+  for (int i = ny; i < nx; ++i) sh *= 10;
+  return x / sh < y;
+}
+
+MUAV_HD MUAV_NI_A inline int pi_allocate(Sim& S, const muav_alloc_opts& O, int e, int16_t* out_agent, int16_t* out_tid, int lane,
+                               int nlanes) {
+  View& V = S.V;
+  const int A = V.L->D.A, TC = V.L->D.TC;
+  const int t = HIv(T);
+  AllocScratch W = carve_scratch(S.scratch, A, TC);
+  const int M = A > TC ? A : TC;
+  const int SMAX = 3 * M + TC;               // u, v, spc, resid reused as four int16 arrays of SMAX entries
+  int16_t* slot_q = (int16_t*)W.u;           // open-task column of the slot
+  int16_t* slot_rank = slot_q + SMAX;        // position of the slot key in string order
+  int16_t* slot_win = slot_rank + SMAX;      // live row of the current winner or -1
+  int16_t* slot_k = slot_win + SMAX;         // k of "<id>#?k"
+  int16_t* q_rank = W.round_tasks;           // string rank of the task id among the open tasks
+  int16_t* row_slot = W.col_of_row;          // slot held by a live row or -1
+  const uint8_t* reserved = O.d_reserved ? O.d_reserved + (size_t)e * A : nullptr;
+  enum { C_GO = 0, C_NFREE = 1, C_NOPEN = 2, C_NSLOT = 3, C_BEST = 4 };
+  if (lane == 0) {
+    HIv(N_CALLS) += 1;
+    const bool ev_hit = (HIv(EV_TAGMASK) & O.event_mask) != 0;
+    const int interval = O.replan_interval > 0 ? O.replan_interval : 1;
+    bool go;
+    if (O.mode == 1) go = (t - HIv(LAST_PLAN_STEP)) >= interval || ev_hit;
+    else if (O.mode == 2) go = t == 0 || (t % interval) == 0 || ev_hit;
+    else go = O.mode == 3;
+    int n_free = 0, n_open = 0, n_slot = 0;
+    if (go) {
+      // every call that passes the rule counts as a replan, also the empty ones (:80-93,222-223)
+      HIv(LAST_PLAN_STEP) = t;
+      HIv(N_REPLANS) += 1;
+      for (int a = 0; a < A; ++a)
+        if (V.a_state()[a] != -1 && !(reserved && reserved[a])) W.free_agents[n_free++] = (int16_t)a;
+      // _open_tasks (paper_eval.py:96-101) + expand_slot_keys (CBBA.py:46-65)
+      const int n_tasks = HIv(N_TASKS);
+      const int IC = V.L->D.IC;
+      const int32_t* order = O.d_task_order ? O.d_task_order + (size_t)e * IC : nullptr;   // the caller's `tasks` argument
+      const int KWn = (n_tasks + 31) >> 5;
+      int wd = 0;
+      uint32_t bits = order ? 0u : (KWn > 0 ? V.open_mask()[0] : 0u);
+      for (int it = 0;; ++it) {
+        int k;
+        if (order) {
+          if (it >= IC) break;
+          k = order[it];
+          if (k < 0) break;
+          if (k >= n_tasks) continue;
+        } else {
+          while (!bits && ++wd < KWn) bits = V.open_mask()[wd];
+          if (!bits) break;
+          k = (wd << 5) + ctz32(bits);
+          bits &= bits - 1;
+        }
+        if (V.k_status()[k] == 2) continue;
+        const double rem = residual_demand(S, k);
+        if (!(rem > 0) || n_open >= TC) continue;
+        int ns = is_coalition(S, k) ? (int)ceil(rem) : (int)ceil(dmin(rem, 4.0));
+        if (ns < 1) ns = 1;
+        if (ns > 10 || n_slot + ns > SMAX) {   // two-digit slot numbers / more slots than the scratch holds: not representable
+          HIv(ERRFLAGS) |= ERR_NO_SPACE;
+          ns = ns > 10 ? 10 : ns;
+          if (n_slot + ns > SMAX) break;
+        }
+        W.open_t[n_open] = (int16_t)k;
+        for (int j = 0; j < ns; ++j) {
+          slot_q[n_slot] = (int16_t)n_open;
+          slot_k[n_slot] = (int16_t)j;
+          slot_win[n_slot] = -1;
+          ++n_slot;
+        }
+        ++n_open;
+      }
+      if (n_free == 0 || n_slot == 0) go = false;
+    }
+    W.ctrl[C_GO] = go ? 1 : 0;
+    W.ctrl[C_NFREE] = n_free;
+    W.ctrl[C_NOPEN] = n_open;
+    W.ctrl[C_NSLOT] = n_slot;
+  }
+  MUAV_WARP_SYNC();
+  if (!W.ctrl[C_GO]) return 0;
+  const int nr = W.ctrl[C_NFREE], nq = W.ctrl[C_NOPEN], ns = W.ctrl[C_NSLOT];
+  // ---- string rank of every open task id, then of every slot (slots of one task are adjacent and ordered by k)
+  for (int q = lane; q < nq; q += nlanes) {
+    const int id = W.open_t[q] + 1;
+    int r = 0;
+    for (int p = 0; p < nq; ++p) r += (p != q && slot_id_less(W.open_t[p] + 1, id)) ? 1 : 0;
+    q_rank[q] = (int16_t)r;
+  }
+  for (int i = lane; i < nr; i += nlanes) row_slot[i] = -1;
+  MUAV_WARP_SYNC();
+  for (int s = lane; s < ns; s += nlanes) {
+    const int rq = q_rank[slot_q[s]];
+    int r = 0;
+    for (int p = 0; p < ns; ++p) r += q_rank[slot_q[p]] < rq ? 1 : 0;
+    slot_rank[s] = (int16_t)(r + slot_k[s]);
+  }
+  // ---- cost of (live row, open task): independent entries, spread over the lanes
+  for (int idx = lane; idx < nr * nq; idx += nlanes) {
+    const int i = idx / nq, q = idx - i * nq;
+    const int a = W.free_agents[i];
+    const int k = W.open_t[q];
+    const int at = V.a_type()[a];
+    const int ti = V.k_type()[k];
+    const int el = V.k_elig()[k];
+    const bool coal = is_coalition(S, k);
+    double c = INFINITY;
+    // agent_eligible (CBBA.py:27-43)
+    bool ok = !O.use_visibility || S.known_bit(a, k);
+    ok = ok && ((el == 0) || ((el >> at) & 1));
+    ok = ok && S.qfind(a, k + 1) < 0;
+    ok = ok && (coal || S.cap(a, ti) > 0);
+    if (ok) {
+      const double nft = V.a_nft()[a];
+      const double now = dmax(nft, (double)t);
+      const double speed = dmax(S.speed_of(a) != 0.0 ? S.speed_of(a) : 1.0, 1e-6);
+      const double start = now + ddiv(norm2(V.a_posx()[a] - V.k_posx()[k], V.a_posy()[a] - V.k_posy()[k]), speed);
+      const int dl = V.k_deadline()[k];
+      if (!(dl >= 0 && start > (double)dl + 1e-6)) {   // _best_inclusion_impact's deadline test (:276-283)
+        double cost = start;
+        if (dl >= 0 && start > (double)dl) {
+          const double late = 200.0 + (start - (double)dl);
+          cost = cost + late;
+        }
+        const double cp = S.cap(a, ti);
+        const double bonus = 5.0 * (coal ? dmax(cp, 0.5) : cp);
+        c = cost - bonus;
+      }
+    }
+    W.cost[idx] = c;
+  }
+  MUAV_WARP_SYNC();
+  // ---- inclusion loop (:106-165)
+  const int max_it = ns * (nr > 1 ? nr : 1);
+  for (int it = 0; it < max_it; ++it) {
+    double bc = INFINITY;
+    int bkey = 0x7fffffff, bidx = -1;
+    for (int idx = lane; idx < nr * ns; idx += nlanes) {
+      const int i = idx / ns, s = idx - i * ns;
+      if (row_slot[i] >= 0) continue;
+      const int q = slot_q[s];
+      const double c = W.cost[i * nq + q];
+      if (!(c < INFINITY)) continue;
+      const int a = W.free_agents[i];
+      const int w = slot_win[s];
+      if (w >= 0) {
+        const double cur = W.cost[w * nq + q];
+        if (c < cur - 1e-9) continue;
+        if (fabs(c - cur) <= 1e-9 && a >= W.free_agents[w]) continue;
+      }
+      const int key = (a << 16) | slot_rank[s];
+      if (c < bc || (c == bc && key < bkey)) { bc = c; bkey = key; bidx = idx; }
+    }
+    const double m = warp_min_f64(bc);
+    const int kmin = warp_min_i32((bidx >= 0 && bc == m) ? bkey : 0x7fffffff);
+    if (kmin == 0x7fffffff) break;
+    if (bidx >= 0 && bc == m && bkey == kmin) W.ctrl[C_BEST] = bidx;   // (agent, slot rank) is unique
+    MUAV_WARP_SYNC();
+    if (lane == 0) {
+      const int idx = W.ctrl[C_BEST];
+      const int i = idx / ns, s = idx - i * ns;
+      const int prev = slot_win[s];
+      if (prev >= 0 && prev != i) row_slot[prev] = -1;
+      row_slot[i] = (int16_t)s;
+      slot_win[s] = (int16_t)i;
+    }
+    MUAV_WARP_SYNC();
+  }
+  int n_pairs = 0;
+  for (int i = 0; i < nr; ++i) {
+    const int s = row_slot[i];
+    if (s < 0) continue;
+    if (lane == 0) {
+      out_agent[n_pairs] = W.free_agents[i];
+      out_tid[n_pairs] = (int16_t)(W.open_t[slot_q[s]] + 1);
+    }
+    ++n_pairs;
+  }
+  MUAV_WARP_SYNC();
+  return n_pairs;
+}
+
 // urgency (_urgency, AttentionRAH.py:29-34)
 MUAV_HD inline double task_urgency(const View& V, int k, int t) {
   int dl = V.k_deadline()[k];
@@ -468,6 +675,7 @@ MUAV_HD inline void apply_commit(Sim& S, int a, int horizon) {
 MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, int16_t* out_agent, int16_t* out_tid, int lane,
                                      int nlanes) {
   if (O.planner == 0) return allocate_tasks(S, O, e, out_agent, out_tid, lane, nlanes);
+  if (O.planner == 6) return pi_allocate(S, O, e, out_agent, out_tid, lane, nlanes);
   View& V = S.V;
   const muav_config& C = S.C();
   const int A = V.L->D.A, TC = V.L->D.TC;

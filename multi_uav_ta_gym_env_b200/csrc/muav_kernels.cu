@@ -117,11 +117,11 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
         const int t = ghi[HI_T];
         const int iv = O.replan_interval > 0 ? O.replan_interval : 1;
         const bool ev_hit = (ghi[HI_EV_TAGMASK] & O.event_mask) != 0;
-        if (O.mode == 1 && O.planner == 0) go = (t - ghi[HI_LAST_PLAN_STEP]) >= iv || ev_hit;
+        if (O.mode == 1 && (O.planner == 0 || O.planner == 6)) go = (t - ghi[HI_LAST_PLAN_STEP]) >= iv || ev_hit;
         else if (O.mode == 3) go = 1;
         else go = t == 0 || (t % iv) == 0 || ev_hit;
         // allocate_tasks counts every call, also those that return without replanning (HungarianAllocator.py:84)
-        if (!go && O.planner == 0 && O.mode != 0) ghi[HI_N_CALLS] += 1;
+        if (!go && (O.planner == 0 || O.planner == 6) && O.mode != 0) ghi[HI_N_CALLS] += 1;
       }
       if (!go) {
         if (P.out.d_n_pairs) P.out.d_n_pairs[e] = 0;
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
       const int t = HIv(T);
       const int iv = O.replan_interval > 0 ? O.replan_interval : 1;
       const bool ev_hit = (HIv(EV_TAGMASK) & O.event_mask) != 0;
-      if (rule == 1 && O.planner == 0) will = (t - HIv(LAST_PLAN_STEP)) >= iv || ev_hit;
+      if (rule == 1 && (O.planner == 0 || O.planner == 6)) will = (t - HIv(LAST_PLAN_STEP)) >= iv || ev_hit;
       else if (rule == 3) will = true;
       else will = t == 0 || (t % iv) == 0 || ev_hit;
     }

@@ -654,3 +654,69 @@ class HungarianAllocator:
         self.last_plan_step = time_step
         self.n_replans += 1
         return [(env.agents_obj[a].name, env._task(tid)) for a, tid in pairs]
+
+
+class PerformanceImpact:
+    """Same constructor, attributes and allocate_tasks signature as the reference's market baseline
+    (TaskAllocation/MarketBased/PerformanceImpact.py:27-224); the slot expansion, the IPI / RPI costs and the
+    inclusion loop run in the CUDA allocator (muav_allocate, muav_alloc_opts.planner = 6).  Returns
+    (agent_name, [task]) items like the reference.  Only max_tasks_per_agent = 1 -- what every reference driver
+    passes (experiments/wps_eval.py:147-156, escort_eval.py:162-170) -- is implemented; anything else raises."""
+
+    def __init__(self, max_coord: float = 1000.0, seed: int = 0, replan_interval: int = 12, max_iters: int = 40):
+        self.max_coord = float(max_coord)
+        self.seed = int(seed)
+        self.replan_interval = max(1, int(replan_interval))
+        self.max_iters = max(4, int(max_iters))
+        self.last_plan_step = -10**9
+        self.n_replans = 0
+        self.n_calls = 0
+
+    should_replan = HungarianAllocator.should_replan
+
+    def allocate_tasks(self, agents, tasks, time_step: int = 0, events=None, force: bool = False, agent_known_ids=None,
+                       reserved_agent_names=None, max_tasks_per_agent: int = 1):
+        from .batched_env import AllocSpec
+
+        if max_tasks_per_agent != 1:
+            raise NotImplementedError("the device PI allocator implements max_tasks_per_agent=1 (the reference drivers' setting)")
+        self.n_calls += 1
+        if not force and not self.should_replan(time_step, events):
+            return []
+        agents = list(agents)
+        tasks = list(tasks)
+        # every call that passes the rule counts as a replan, also the empty ones (PerformanceImpact.py:80-93,222-223)
+        self.last_plan_step = time_step
+        self.n_replans += 1
+        env = None
+        for obj in agents + tasks:
+            env = getattr(obj, "_env", None)
+            if env is not None:
+                break
+        if env is None or not agents or not tasks:
+            return []
+        if int(time_step) != int(env.time_steps):
+            raise ValueError("time_step must be env.time_steps (the device allocator reads the env clock)")
+        cfg = env._backend.cfg
+        A, TC = cfg.n_agents, max(cfg.id_cap, cfg.task_cap)
+        reserved_names = set(reserved_agent_names or [])
+        given = {a.id for a in agents}
+        reserved = np.zeros(A, dtype=np.uint8)
+        for a in env.agents_obj:
+            if a.id not in given or a.name in reserved_names:
+                reserved[a.id] = 1
+        order = np.full(TC, -1, dtype=np.int32)
+        n_ord = 0
+        for t in tasks:
+            if t.id != 0 and n_ord < TC:
+                order[n_ord] = t.id - 1
+                n_ord += 1
+        use_vis = agent_known_ids is not None
+        if use_vis:
+            own = env.agent_visibility_map() or {}
+            for name, ids in agent_known_ids.items():
+                if name in own and set(ids) != own[name]:
+                    raise NotImplementedError("agent_known_ids must be env.agent_visibility_map() (device-resident sets)")
+        spec = AllocSpec(3, self.replan_interval, 0, use_vis, False, float(self.max_coord), planner=6)
+        pairs = env._backend.allocate(spec, None, None, reserved, order)
+        return [(env.agents_obj[a].name, [env._task(tid)]) for a, tid in pairs]

@@ -27,6 +27,8 @@ Drivers (all restate the reference's own episode loops):
   att_escort_injected  AttentionEscort.plan (AttentionEscort.py:519-524: build_escort_tokens -> act -> _plan_from_scores)
                     with the network replaced by injected logits, cadence escort_eval.py:52-58 (interval 12);
                     the reference tokens of every 4th plan are stored too
+  local_pi / pi_coalition  PerformanceImpact.allocate_tasks(max_tasks_per_agent=1) (MarketBased/PerformanceImpact.py:59-224)
+                    under experiments/wps_eval.py:147-159 (interval 20) / escort_eval.py:162-174 (interval 12)
 """
 from __future__ import annotations
 
@@ -149,6 +151,9 @@ def run_episode(case, seed, driver, overrides=None):
         planner = AttentionEscort(use_attention=False, device="cpu", d_model=16)
         planner.net = _InjectedNet()
         hung = HungarianAllocator(replan_interval=10**9, max_coord=env.max_coord)
+    elif driver in ("local_pi", "pi_coalition"):
+        from TaskAllocation.MarketBased.PerformanceImpact import PerformanceImpact
+        planner = PerformanceImpact(max_coord=env.max_coord, seed=seed, replan_interval=20 if driver == "local_pi" else 12)
     n_plans = 0
     rnd = random.Random(seed * 7919 + 13)
     ep = {"case": case, "seed": seed, "driver": driver, "overrides": overrides or {},
@@ -166,6 +171,10 @@ def run_episode(case, seed, driver, overrides=None):
         elif driver == "global_hungarian":
             pairs = hung.allocate_tasks(env.get_live_agents(), ref_open_tasks(env), time_step=env.time_steps,
                                         events=events)
+        elif driver in ("local_pi", "pi_coalition"):
+            res = planner.allocate_tasks(env.get_live_agents(), ref_open_tasks(env), time_step=env.time_steps, events=events,
+                                         agent_known_ids=env.agent_visibility_map(), max_tasks_per_agent=1)
+            pairs = [(name, task) for name, tl in res for task in tl]   # _flatten_pairs (wps_eval.py:40-52)
         elif driver == "pair_injected":
             if hybrid_should_replan(env, events):
                 sc = injected_scores(seed, env.time_steps, pair.max_agents, pair.max_tasks)
@@ -240,7 +249,7 @@ def run_episode(case, seed, driver, overrides=None):
             break
     m = info["metrics"]
     ep["metrics"] = {k: (fhex(v) if isinstance(v, (float, np.floating)) else int(v)) for k, v in m.items()}
-    ep["n_replans"] = int(hung.n_replans)
+    ep["n_replans"] = int(planner.n_replans if driver in ("local_pi", "pi_coalition") else hung.n_replans)
     return ep
 
 
@@ -265,6 +274,9 @@ PLAN = [
     ("wps_attn_context", "WPS_attn", "context_injected", range(0, 4), None),
     ("wps_commit_attcommit", "WPS_commit", "att_commit_injected", range(0, 6), None),
     ("wps_escort_attescort", "WPS_escort", "att_escort_injected", range(0, 6), None),
+    ("wps_hard_pi", "WPS_hard", "local_pi", range(0, 8), None),
+    ("wps_commit_pi", "WPS_commit", "local_pi", range(0, 4), None),
+    ("wps_escort_pi", "WPS_escort", "pi_coalition", range(0, 4), None),
 ]
 
 

@@ -81,6 +81,9 @@ def alloc_opts_for(driver):
         O.replan_interval = 12 if driver == "coalition" else 20
         O.event_mask = 0x1F
         O.use_visibility = 0 if driver == "global_hungarian" else 1
+    elif driver in ("local_pi", "pi_coalition"):
+        O.mode, O.replan_interval, O.event_mask, O.use_visibility = 1, (12 if driver == "pi_coalition" else 20), 0x1F, 1
+        O.planner = 6
     elif driver == "pair_injected":
         O.mode = 2
         O.replan_interval = 15

@@ -107,6 +107,41 @@ def test_env_and_allocator_facade_follow_the_reference_loop(case, seed, interval
     assert ref.compute_s_wps() == mine.compute_s_wps() and ref.compute_s_esc() == mine.compute_s_esc()
 
 
+@pytest.mark.parametrize("case,seed,interval", [("WPS_hard", 5, 20), ("WPS_escort", 2, 12)])
+def test_performance_impact_facade_follows_the_reference_loop(case, seed, interval):
+    """Local-PI / Local-PI-Coalition loop (wps_eval.py:147-159, escort_eval.py:162-174): the reference PerformanceImpact on the
+    reference env vs the facade class (device allocator, planner 6) on the facade env, every step."""
+    refshim.install()
+    from TaskAllocation.MarketBased.PerformanceImpact import PerformanceImpact as RefPI
+    from multi_uav_ta_gym_env_b200.env import PerformanceImpact
+
+    ref, ro, ri, mine, mo, mi = make_pair(case, seed)
+    rp = RefPI(max_coord=ref.max_coord, seed=seed, replan_interval=interval)
+    mp = PerformanceImpact(max_coord=mine.max_coord, seed=seed, replan_interval=interval)
+    flat = lambda env, res: [(env.agent_by_name[n].id, t.id) for n, tl in res for t in tl]  # noqa: E731
+    n_plans = 0
+    for t in range(150):
+        revents = list(ri.get("events") or []) if isinstance(ri, dict) else []
+        mevents = list(mi.get("events") or []) if isinstance(mi, dict) else []
+        rres = rp.allocate_tasks(ref.get_live_agents(), ref_open_tasks(ref), time_step=ref.time_steps, events=revents,
+                                 agent_known_ids=ref.agent_visibility_map(), max_tasks_per_agent=1)
+        mres = mp.allocate_tasks(mine.get_live_agents(), ref_open_tasks(mine), time_step=mine.time_steps, events=mevents,
+                                 agent_known_ids=mine.agent_visibility_map(), max_tasks_per_agent=1)
+        assert flat(ref, rres) == flat(mine, mres), t
+        n_plans += bool(rres)
+        ract = apply_assign(ref, [(n, t_) for n, tl in rres for t_ in tl])
+        mact = apply_assign(mine, [(n, t_) for n, tl in mres for t_ in tl])
+        assert ract == mact
+        ro, rr, rterm, rtrunc, ri = ref.step(ract)
+        mo, mr, mterm, mtrunc, mi = mine.step(mact)
+        assert rr == mr and ri["events"] == mi["events"], t
+        assert refsnap.digest(refsnap.snapshot(ref)) == refsnap.digest(mine._snap), t
+    assert n_plans > 5
+    assert (rp.n_replans, rp.n_calls, rp.last_plan_step) == (mp.n_replans, mp.n_calls, mp.last_plan_step)
+    with pytest.raises(NotImplementedError):
+        mp.allocate_tasks(mine.get_live_agents(), ref_open_tasks(mine), time_step=mine.time_steps, force=True, max_tasks_per_agent=2)
+
+
 def _load_oracle_from_snapshot(orc, facade_env):
     """Minimal oracle view of the facade's current state (only what the token builders read)."""
     s = facade_env._snap

@@ -21,7 +21,8 @@ STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit
               "wps_attn_xl_local", "wps_hard_single_task"]
 # planner fixtures mutate commit_until between steps: they are replayed through the fused planner only
 ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
-    "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair", "wps_attn_context"]
+    "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair", "wps_attn_context",
+    "wps_hard_pi", "wps_commit_pi", "wps_escort_pi"]
 
 
 def make_env(cfg, seeds, **kw):
@@ -36,7 +37,8 @@ def spec_for(driver):
     return {"local_hungarian": AllocSpec.local_hungarian(20), "coalition": AllocSpec.coalition_hungarian(12),
             "global_hungarian": AllocSpec.global_hungarian(20), "pair_injected": AllocSpec.pair_hybrid(15),
             "urgency_commit": AllocSpec.urgency_commit(15), "urgency_coalition": AllocSpec.urgency_coalition(12),
-            "context_injected": AllocSpec.pair_hybrid(15), "urgency_pair": AllocSpec.urgency_pair(15), "att_commit_injected": AllocSpec.att_commit(15), "att_escort_injected": AllocSpec.att_escort(12)}[driver]
+            "context_injected": AllocSpec.pair_hybrid(15), "urgency_pair": AllocSpec.urgency_pair(15), "att_commit_injected": AllocSpec.att_commit(15), "att_escort_injected": AllocSpec.att_escort(12),
+            "local_pi": AllocSpec.performance_impact(20), "pi_coalition": AllocSpec.performance_impact(12)}[driver]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)
@@ -122,7 +124,7 @@ def test_cuda_fused_allocator_matches_reference_golden(name):
             assert env.pairs_of(e) == st["pairs"], (name, ep["seed"], t)
             assert rew[e] == float.fromhex(st["reward"]), (name, ep["seed"], t)
             assert str(refsnap.digest(env.codec.snapshot(recs[e]))) == st["digest"], (name, ep["seed"], t)
-    if drv in ("local_hungarian", "coalition", "global_hungarian"):
+    if drv in ("local_hungarian", "coalition", "global_hungarian", "local_pi", "pi_coalition"):
         nrep = env.header_int("N_REPLANS").cpu().numpy()
         for e, ep in enumerate(eps):
             assert int(nrep[e]) == ep["n_replans"]

@@ -12,7 +12,8 @@ STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit
               "wps_attn_xl_local", "wps_hard_single_task", "wps_hard_obstacles"]
 # planner fixtures mutate commit_until between steps: they are replayed through the fused planner only
 ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
-    "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair", "wps_attn_context"]
+    "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair", "wps_attn_context",
+    "wps_hard_pi", "wps_commit_pi", "wps_escort_pi"]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)
@@ -76,7 +77,7 @@ def test_fused_allocator(hostcheck, name):
             assert env.pairs_of(e) == st["pairs"], (name, ep["seed"], t)
             assert env.reward[e] == float.fromhex(st["reward"])
             assert str(env.digest(e)) == st["digest"], (name, ep["seed"], t)
-    if drv in ("local_hungarian", "coalition", "global_hungarian"):
+    if drv in ("local_hungarian", "coalition", "global_hungarian", "local_pi", "pi_coalition"):
         for e, ep in enumerate(eps):
             assert env.codec.header(env.rec[e], "N_REPLANS") == ep["n_replans"]
 
