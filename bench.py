@@ -210,6 +210,12 @@ def run_gpu_arm(args):
     elif wl == "hard_local":
         case_name, cfg, spec = CASE, wps_config(CASE), AllocSpec.local_hungarian(20)
         desc = "Local-Hungarian interval 20 (no scorer)"
+    elif wl == "hard_pi":
+        case_name, cfg, spec = CASE, wps_config(CASE), AllocSpec.performance_impact(20)
+        desc = "Local-PI market allocator (PerformanceImpact, max_tasks_per_agent=1) interval 20 (no scorer)"
+    elif wl == "escort_pi":
+        case_name, cfg, spec = "WPS_escort", wps_config("WPS_escort"), AllocSpec.performance_impact(12)
+        desc = "Local-PI-Coalition market allocator interval 12 with visibility map"
     elif wl == "commit_urgency":
         case_name, cfg, spec = "WPS_commit", wps_config("WPS_commit"), AllocSpec.urgency_commit(HYBRID_INTERVAL)
         desc = "UrgencyCommit planner on the device (commit locks, rematch penalty), hybrid replan rule"
@@ -400,7 +406,8 @@ def survey_b_alg(wl, A, env):
     configs (WPS_hard 14.4 KB, WPS_commit 21 KB, WPS_escort 25 KB), else the section's own formula
     B_alg = 2 S_env + O_env with agent 104 B, live task 100 + 8 A B, threat 32 B, known bitmask 4 A ceil(Tcap / 32) B,
     pending reveals 4 x 48 B, scalars 128 B, RNG tape 44 B per step, O_env = 4 A + 16 B."""
-    stated = {"hard_pair": 14400, "hard_local": 14400, "commit_urgency": 21000, "escort_coalition": 25000}
+    stated = {"hard_pair": 14400, "hard_local": 14400, "commit_urgency": 21000, "escort_coalition": 25000,
+              "hard_pi": 14400, "escort_pi": 25000}
     if wl in stated:
         return stated[wl], "SURVEY.md 8(d), stated figure"
     H = int(env.cfg.n_threats)
@@ -469,7 +476,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
     ap.add_argument("--workload", default="hard_pair",
                     help="hard_pair (default, BASELINE config 2) | hard_local | commit_urgency | escort_coalition | burst_xK "
-                         "| attn_context")
+                         "| attn_context | hard_pi | escort_pi")
     ap.add_argument("--task-cap", type=int, default=0, help="task slots per environment (0 = workload default)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

