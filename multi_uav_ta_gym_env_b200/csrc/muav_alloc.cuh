@@ -325,9 +325,9 @@ MUAV_HD MUAV_NI_A inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, in
         }
         if (base < 1e5 / 2) {
           double sc = 0.0;
-          if (O.planner == 2) {
+          if (MUAV_F_PLANNER(O.planner) == 2) {
             sc = coalition_edge_score(S, a, k, t);
-          } else if (O.planner == 5) {
+          } else if (MUAV_F_PLANNER(O.planner) == 5) {
             // urgency_edge_scores (PairCostHybrid.py:68-86) on the valid edges of the pair tokens; stored as float32
             const int col = W.tokcol[q];
             const int row = W.live_row[i];
@@ -674,7 +674,7 @@ MUAV_HD inline void apply_commit(Sim& S, int a, int horizon) {
 // Planner front ends (muav_alloc_opts.planner) + allocate_tasks.  Warp-collective.
 MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, int16_t* out_agent, int16_t* out_tid, int lane,
                                      int nlanes) {
-  if (O.planner == 0) return allocate_tasks(S, O, e, out_agent, out_tid, lane, nlanes);
+  if (MUAV_F_PLANNER(O.planner) == 0) return allocate_tasks(S, O, e, out_agent, out_tid, lane, nlanes);
   if (O.planner == 6) return pi_allocate(S, O, e, out_agent, out_tid, lane, nlanes);
   View& V = S.V;
   const muav_config& C = S.C();

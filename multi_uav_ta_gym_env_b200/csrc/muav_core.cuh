@@ -18,6 +18,20 @@
 #include <stdint.h>
 #include "muav_layout.h"
 
+// Lean instantiation of the step kernel (muav_kernels.cu compiles it a second time with MUAV_LEAN): the configuration of
+// most registered scenarios -- no escorts, no obstacles, the plain Hungarian allocator -- as compile-time constants, so the
+// escort life cycle, obstacle avoidance and the planner front ends drop out of the instruction stream of a kernel that is
+// bound by instruction supply.  The launcher picks it only when the configuration really has those values.
+#if defined(MUAV_LEAN)
+#define MUAV_F_ESCORT(x) false
+#define MUAV_F_NOBS(x) 0
+#define MUAV_F_PLANNER(x) 0
+#else
+#define MUAV_F_ESCORT(x) ((x) != 0)
+#define MUAV_F_NOBS(x) (x)
+#define MUAV_F_PLANNER(x) (x)
+#endif
+
 namespace muav {
 
 #define HIv(name) V.hi()[HI_##name]
@@ -654,7 +668,7 @@ struct Sim {
   }
   // _create_escort_for (DroneEnv.py:1888-1917)
   MUAV_HD MUAV_NOINLINE void create_escort_for(int a, int rec_tid) {
-    if (!C().escort_enabled) return;
+    if (!MUAV_F_ESCORT(C().escort_enabled)) return;
     if (V.a_escort()[a] != 0) return;
     int tid = new_task(V.a_posx()[a], V.a_posy()[a], TT_DEF);
     if (tid == 0) return;
@@ -682,7 +696,7 @@ struct Sim {
     int primary = V.h_target()[hid];
     int mission = V.h_mission()[hid] >= 0 ? V.h_mission()[hid] : primary;
     int16_t* defenders = near_i();
-    if (C().escort_enabled && mission >= 0 && is_recon(V.a_type()[mission])) {
+    if (MUAV_F_ESCORT(C().escort_enabled) && mission >= 0 && is_recon(V.a_type()[mission])) {
       nd = fighters_near(mission, C().mutual_support_radius, defenders, near_d());
       if (nd > 0) {
         primary = defenders[0];
@@ -774,7 +788,7 @@ struct Sim {
         V.h_posx()[hid] = hx;
         V.h_posy()[hid] = hy;
       } else {
-        if (C().escort_enabled) retarget_via_escort(hid);
+        if (MUAV_F_ESCORT(C().escort_enabled)) retarget_via_escort(hid);
         int tg = V.h_target()[hid];
         double dx = V.a_posx()[tg] - hx, dy = V.a_posy()[tg] - hy;
         double mag = norm2(dx, dy);
@@ -799,7 +813,7 @@ struct Sim {
   // random_position (DroneEnv.py:1371-1410) for mission-area draws of the target stream
   MUAV_HD bool random_position_area(int stream, int area, double* ox, double* oy) {
     const double* m = &V.hf()[HF_M0_X + 4 * area];
-    int nobs = V.L->D.NOBS;
+    int nobs = MUAV_F_NOBS(V.L->D.NOBS);
     for (int tries = 0; tries < 100; ++tries) {
       double x = rng_uniform(stream, m[0], m[0] + m[2]);
       double y = rng_uniform(stream, m[1], m[1] + m[3]);
@@ -1116,7 +1130,7 @@ struct Sim {
         }
         acc.distance_reward += ddiv(-1.0 * norm2(V.a_nfpx()[a] - rx, V.a_nfpy()[a] - ry), C().max_coord);
         if (V.a_state()[a] != 1 && V.a_state()[a] != -1) V.a_state()[a] = 1;
-        if (C().escort_enabled && ti == TT_REC && is_recon(V.a_type()[a]) && V.a_escort()[a] == 0) create_escort_for(a, tid);
+        if (MUAV_F_ESCORT(C().escort_enabled) && ti == TT_REC && is_recon(V.a_type()[a]) && V.a_escort()[a] == 0) create_escort_for(a, tid);
       }
     }
 
@@ -1136,7 +1150,7 @@ struct Sim {
     const int TC = V.L->D.TC;
     const int t = HIv(T);
     const double bx = C().base_x, by = C().base_y;
-    const int nobs = V.L->D.NOBS;
+    const int nobs = MUAV_F_NOBS(V.L->D.NOBS);
     {
       if (V.a_state()[a] == -1) return;
       if (V.a_fail_event()[a] == t) {
@@ -1286,7 +1300,7 @@ struct Sim {
   MUAV_HD void step_pre_d() {
     MUAV_TICK_START();
     inject_arrivals();
-    if (C().escort_enabled) sync_escorts();
+    if (MUAV_F_ESCORT(C().escort_enabled)) sync_escorts();
     MUAV_TICK(6);
   }
 
@@ -1405,6 +1419,7 @@ struct Sim {
     if (alive && lane == 0) step_pre_a(act_agent, act_tid, n_act);
     MUAV_WARP_SYNC();
     MUAV_CTA_SYNC(sync_mask & 2);
+#if !defined(MUAV_LEAN)   // tuning variant (a second inlined copy of the FSM); the lean kernel keeps the default path only
     if (sync_mask & 32) {
       // one alignment point per agent: the FSM body is the longest straight-line stretch of the step
       const int Aa = A();
@@ -1413,13 +1428,16 @@ struct Sim {
         MUAV_WARP_SYNC();
         MUAV_CTA_SYNC(1);
       }
-    } else {
+    } else
+#endif
+    {
       if (alive && lane == 0) step_pre_b();
       MUAV_WARP_SYNC();
       MUAV_CTA_SYNC(sync_mask & 4);
     }
     if (alive && lane == 0) step_pre_c();
     MUAV_WARP_SYNC();
+#if !defined(MUAV_LEAN)
     if (sync_mask & 64) {
       const int HCc = V.L->D.HC;
       for (int i = 0; i < HCc; ++i) {
@@ -1427,7 +1445,9 @@ struct Sim {
         MUAV_WARP_SYNC();
         MUAV_CTA_SYNC(1);
       }
-    } else {
+    } else
+#endif
+    {
       if (alive && lane == 0) update_threats();
       MUAV_WARP_SYNC();
     }

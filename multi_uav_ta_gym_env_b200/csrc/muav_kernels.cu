@@ -108,7 +108,11 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
   int16_t* act_tid = act_tid_s[w];
 
   // ---- allocator-only launch: environments whose replan rule does not fire leave after a look at their header
+#if defined(MUAV_LEAN)
+  if (false) {   // the lean kernel is never launched allocator-only (launch_step): no second copy of the allocator
+#else
   if (P.alloc_only && has_env) {
+#endif
     int32_t* ghi = (int32_t*)(grec + L.o_hi);
     int go = 0;
     if (lane == 0) {
@@ -190,7 +194,11 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
     }
   }
 
+#if defined(MUAV_LEAN)
+  if (false) {
+#else
   if (P.alloc_only && has_env) {
+#endif
     const int np = HIv(DONE) ? 0 : plan_and_allocate(S, P.opts, e, act_agent, act_tid, lane, 32);
     if (lane == 0) {
       if (P.out.d_n_pairs) P.out.d_n_pairs[e] = np;
@@ -322,6 +330,26 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
   }
 }
 
+#if defined(MUAV_STEP_ONLY)
+}  // namespace muav (renamed by the including translation unit)
+
+// launcher of this translation unit's instantiation of the step kernel (see muav_step_lean.cu)
+extern "C" int MUAV_STEP_LAUNCHER(const void* params, int grid, int threads, size_t smem, void* stream) {
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(muav::muav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -1000 - (int)e;
+    smem_set = smem;
+  }
+  muav::muav_step_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(*(const muav::StepParams*)params);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -1000 - (int)e;
+}
+extern "C" int MUAV_STEP_STATIC_SMEM(void) {
+  cudaFuncAttributes fa;
+  return cudaFuncGetAttributes(&fa, muav::muav_step_kernel) == cudaSuccess ? (int)fa.sharedSizeBytes : 4608;
+}
+#else
 // ------------------------------------------------------------------ standalone batched LSAP
 __global__ void __launch_bounds__(32) muav_lsap_kernel(const double* cost, const int32_t* nr_arr, const int32_t* nc_arr,
                                                        int nr_max, int nc_max, int32_t* col4row, int n) {
@@ -455,7 +483,12 @@ extern "C" {
 
 #include "muav_abi_common.inl"
 
+// lean instantiation of the step kernel (muav_step_lean.cu): no escorts, no obstacles, plain Hungarian allocator
+int muav_step_lean_launch(const void* params, int grid, int threads, size_t smem, void* stream);
+int muav_step_lean_static_smem(void);
+
 static int launch_step(StepParams& P, void* stream) {
+  const bool lean = P.cfg.escort_enabled == 0 && P.L.D.NOBS == 0 && P.opts.planner == 0 && !P.alloc_only && !getenv("MUAV_NO_LEAN");
   // launches without the allocator need only the step's temporaries: more environments per SM
   P.scratch_launch = (P.alloc_only || P.opts.mode != 0) ? P.L.scratch_bytes : P.L.step_scratch_bytes;
   const size_t slot = (size_t)P.L.record_bytes + (size_t)P.scratch_launch;
@@ -471,6 +504,8 @@ static int launch_step(StepParams& P, void* stream) {
     if (!static_smem) {
       cudaFuncAttributes fa;
       static_smem = cudaFuncGetAttributes(&fa, muav_step_kernel) == cudaSuccess ? fa.sharedSizeBytes : 4608;
+      const size_t sl = (size_t)muav_step_lean_static_smem();
+      if (sl > static_smem) static_smem = sl;
     }
     const size_t budget = 228 * 1024, per_cta = static_smem + 1024;  // B200: 228 KB per SM, 1 KB reserved per CTA
     int envs[7] = {0, 0, 0, 0, 0, 0, 0}, ctas[7] = {0, 0, 0, 0, 0, 0, 0}, best = 0;
@@ -504,6 +539,7 @@ static int launch_step(StepParams& P, void* stream) {
   const char* sm = getenv("MUAV_SYNC_MASK");
   if (sm) P.sync_mask = atoi(sm);
   const size_t smem = slot * W;
+  if (lean) return muav_step_lean_launch(&P, (P.n_envs + W - 1) / W, 32 * W, smem, stream);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(muav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -805,3 +841,5 @@ int muav_observe(const muav_config* cfg, const void* d_records, int max_rows, do
 }
 
 }  // extern "C"
+
+#endif  // !MUAV_STEP_ONLY
