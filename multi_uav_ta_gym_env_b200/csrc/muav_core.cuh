@@ -23,7 +23,11 @@
 // escort life cycle, obstacle avoidance and the planner front ends drop out of the instruction stream of a kernel that is
 // bound by instruction supply.  The launcher picks it only when the configuration really has those values.
 #if defined(MUAV_LEAN)
+#if defined(MUAV_LEAN_ESCORT)   // second lean instantiation: escorts always on (WPS_escort), otherwise the same
+#define MUAV_F_ESCORT(x) true
+#else
 #define MUAV_F_ESCORT(x) false
+#endif
 #define MUAV_F_NOBS(x) 0
 #define MUAV_F_PLANNER(x) 0
 #else
@@ -1419,7 +1423,8 @@ struct Sim {
     if (alive && lane == 0) step_pre_a(act_agent, act_tid, n_act);
     MUAV_WARP_SYNC();
     MUAV_CTA_SYNC(sync_mask & 2);
-#if !defined(MUAV_LEAN)   // tuning variant (a second inlined copy of the FSM); the lean kernel keeps the default path only
+#if defined(MUAV_TUNING_VARIANTS)   // a second inlined copy of the FSM: development builds only (the kernel is bound by
+                                    // instruction supply, dead copies cost time)
     if (sync_mask & 32) {
       // one alignment point per agent: the FSM body is the longest straight-line stretch of the step
       const int Aa = A();
@@ -1437,7 +1442,7 @@ struct Sim {
     }
     if (alive && lane == 0) step_pre_c();
     MUAV_WARP_SYNC();
-#if !defined(MUAV_LEAN)
+#if defined(MUAV_TUNING_VARIANTS)
     if (sync_mask & 64) {
       const int HCc = V.L->D.HC;
       for (int i = 0; i < HCc; ++i) {

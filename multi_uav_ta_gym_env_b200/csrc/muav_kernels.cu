@@ -486,9 +486,11 @@ extern "C" {
 // lean instantiation of the step kernel (muav_step_lean.cu): no escorts, no obstacles, plain Hungarian allocator
 int muav_step_lean_launch(const void* params, int grid, int threads, size_t smem, void* stream);
 int muav_step_lean_static_smem(void);
+int muav_step_lean_escort_launch(const void* params, int grid, int threads, size_t smem, void* stream);
+int muav_step_lean_escort_static_smem(void);
 
 static int launch_step(StepParams& P, void* stream) {
-  const bool lean = P.cfg.escort_enabled == 0 && P.L.D.NOBS == 0 && P.opts.planner == 0 && !P.alloc_only && !getenv("MUAV_NO_LEAN");
+  const bool lean = P.L.D.NOBS == 0 && P.opts.planner == 0 && !P.alloc_only && !getenv("MUAV_NO_LEAN");
   // launches without the allocator need only the step's temporaries: more environments per SM
   P.scratch_launch = (P.alloc_only || P.opts.mode != 0) ? P.L.scratch_bytes : P.L.step_scratch_bytes;
   const size_t slot = (size_t)P.L.record_bytes + (size_t)P.scratch_launch;
@@ -504,8 +506,9 @@ static int launch_step(StepParams& P, void* stream) {
     if (!static_smem) {
       cudaFuncAttributes fa;
       static_smem = cudaFuncGetAttributes(&fa, muav_step_kernel) == cudaSuccess ? fa.sharedSizeBytes : 4608;
-      const size_t sl = (size_t)muav_step_lean_static_smem();
+      const size_t sl = (size_t)muav_step_lean_static_smem(), se = (size_t)muav_step_lean_escort_static_smem();
       if (sl > static_smem) static_smem = sl;
+      if (se > static_smem) static_smem = se;
     }
     const size_t budget = 228 * 1024, per_cta = static_smem + 1024;  // B200: 228 KB per SM, 1 KB reserved per CTA
     int envs[7] = {0, 0, 0, 0, 0, 0, 0}, ctas[7] = {0, 0, 0, 0, 0, 0, 0}, best = 0;
@@ -539,7 +542,9 @@ static int launch_step(StepParams& P, void* stream) {
   const char* sm = getenv("MUAV_SYNC_MASK");
   if (sm) P.sync_mask = atoi(sm);
   const size_t smem = slot * W;
-  if (lean) return muav_step_lean_launch(&P, (P.n_envs + W - 1) / W, 32 * W, smem, stream);
+  if (lean)
+    return (P.cfg.escort_enabled ? muav_step_lean_escort_launch : muav_step_lean_launch)(&P, (P.n_envs + W - 1) / W, 32 * W,
+                                                                                         smem, stream);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(muav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

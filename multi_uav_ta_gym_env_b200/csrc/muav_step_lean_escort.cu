@@ -1,0 +1,9 @@
+// Third instantiation of muav_step_kernel: the lean feature set of muav_step_lean.cu with escorts compiled IN
+// (escort_enabled fixed to true; no obstacles, plain Hungarian / Coalition-Hungarian allocator) for the WPS_escort family.
+#define MUAV_LEAN 1
+#define MUAV_LEAN_ESCORT 1
+#define MUAV_STEP_ONLY 1
+#define MUAV_STEP_LAUNCHER muav_step_lean_escort_launch
+#define MUAV_STEP_STATIC_SMEM muav_step_lean_escort_static_smem
+#define muav muav_lean_escort
+#include "muav_kernels.cu"
