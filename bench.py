@@ -41,8 +41,8 @@ EPISODE = 150
 HYBRID_INTERVAL = 15
 METRIC = "WPS_hard env-steps/sec (batched, 1/2/4/8 B200) vs ref CPU; % HBM roofline"
 # dram__bytes_read.sum + dram__bytes_write.sum per muav_step_kernel launch (4096 WPS_hard envs), ncu --set full capture
-# gpurun_out/prof_step_r1_t.ncu-rep summarised in profiles/r01_step_kernel_ncu_v3.md: 62.0 MB read + 3.1 MB written
-NCU_TRAFFIC_BYTES = 65.1e6  # dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_step_kernel_ncu_v3.md
+# gpurun_out/prof_step_r1_lean.ncu-rep summarised in profiles/r01_step_kernel_ncu_v4.md: 62.3 MB read + 2.3 MB written
+NCU_TRAFFIC_BYTES = 64.6e6  # dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_step_kernel_ncu_v4.md
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
@@ -383,7 +383,7 @@ def run_gpu_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES if (wl == "hard_pair" and E == ENVS_PER_GPU) else None,
                          "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
-                                         "capture (profiles/r01_step_kernel_ncu_v3.md); the write-back of the records is "
+                                         "capture (profiles/r01_step_kernel_ncu_v4.md); the write-back of the records is "
                                          "still in L2 when the kernel ends, so it is below the algorithmic bytes",
                          "algorithmic_bytes_per_launch": E * b_alg,
                          "kernel": "muav_step_kernel", "bytes_per_env_step": b_alg, "bytes_per_env_step_source": b_alg_src,
