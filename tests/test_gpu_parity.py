@@ -938,3 +938,30 @@ def test_two_kernel_split_step_gives_the_same_states(monkeypatch):
                 assert torch.equal(one.records, two.records), t
                 assert torch.equal(one.pairs[:, :1], two.pairs[:, :1]) and torch.equal(one.n_pairs, two.n_pairs)
                 assert torch.equal(one.reward, two.reward)
+
+
+@pytest.mark.parametrize("case,interval", [("WPS_hard", 20), ("WPS_commit", 20), ("WPS_escort", 12), ("WPS_burst", 20)])
+def test_lean_and_general_step_kernels_agree(case, interval, monkeypatch):
+    """csrc/muav_step_lean*.cu (feature set fixed at compile time, picked by launch_step) against the general
+    instantiation of the same kernel (MUAV_NO_LEAN=1) on 192 fresh environments: records, rewards and allocator pairs
+    byte for byte, single-step launches and one resident 150-step launch."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+
+    cfg = wps_config(case)
+    seeds = list(range(2000, 2192))
+    spec = AllocSpec(1, interval, 0x1F, True, False)
+    lean, general = make_env(cfg, seeds), make_env(cfg, seeds)
+    for t in range(60):
+        monkeypatch.delenv("MUAV_NO_LEAN", raising=False)
+        lean.step_allocated(spec, 1)
+        monkeypatch.setenv("MUAV_NO_LEAN", "1")
+        general.step_allocated(spec, 1)
+        assert torch.equal(lean.records, general.records), (case, t)
+        assert torch.equal(lean.reward, general.reward), (case, t)
+        assert [lean.pairs_of(e) for e in (0, 57, 191)] == [general.pairs_of(e) for e in (0, 57, 191)]
+    monkeypatch.delenv("MUAV_NO_LEAN", raising=False)
+    lean.step_allocated(spec, 90)
+    monkeypatch.setenv("MUAV_NO_LEAN", "1")
+    general.step_allocated(spec, 90)
+    assert torch.equal(lean.records, general.records)
+    assert int(lean.error_flags().abs().max().item()) == 0
