@@ -110,18 +110,35 @@ __device__ void linear_t(const float* __restrict__ in_t, int r_lo, int r_hi, int
 
 // LayerNorm over the feature axis (eps 1e-5, biased variance), in place on x_t[D][TS]
 __device__ void layer_norm_t(float* x_t, int R, const float* __restrict__ g, const float* __restrict__ b) {
-  const int r = threadIdx.x;
-  if (r < R) {
-    float mean = 0.0f;
-    for (int k = 0; k < D; ++k) mean += x_t[k * TS + r];
-    mean *= (1.0f / D);
-    float var = 0.0f;
-    for (int k = 0; k < D; ++k) {
-      const float d = x_t[k * TS + r] - mean;
-      var = fmaf(d, d, var);
-    }
-    const float inv = rsqrtf(var * (1.0f / D) + 1e-5f);
-    for (int k = 0; k < D; ++k) x_t[k * TS + r] = (x_t[k * TS + r] - mean) * inv * g[k] + b[k];
+  // four threads per token: thread (part, r) owns features [16 part, 16 part + 16) of token r (a warp reads 32 consecutive
+  // tokens of one feature row: conflict-free); the partial sums meet in shared memory
+  __shared__ float s_red[2][4][TS];
+  const int part = threadIdx.x >> 6, r = threadIdx.x & 63;
+  const int k0 = part * (D / 4);
+  const bool on = r < R;
+  float v[D / 4];
+  float sum = 0.0f;
+#pragma unroll
+  for (int k = 0; k < D / 4; ++k) {
+    v[k] = on ? x_t[(k0 + k) * TS + r] : 0.0f;
+    sum += v[k];
+  }
+  s_red[0][part][r] = sum;
+  __syncthreads();
+  const float mean = (s_red[0][0][r] + s_red[0][1][r] + s_red[0][2][r] + s_red[0][3][r]) * (1.0f / D);
+  float var = 0.0f;
+#pragma unroll
+  for (int k = 0; k < D / 4; ++k) {
+    const float d = v[k] - mean;
+    var = fmaf(d, d, var);
+  }
+  s_red[1][part][r] = var;
+  __syncthreads();
+  var = s_red[1][0][r] + s_red[1][1][r] + s_red[1][2][r] + s_red[1][3][r];
+  const float inv = rsqrtf(var * (1.0f / D) + 1e-5f);
+  if (on) {
+#pragma unroll
+    for (int k = 0; k < D / 4; ++k) x_t[(k0 + k) * TS + r] = (v[k] - mean) * inv * g[k0 + k] + b[k0 + k];
   }
   __syncthreads();
 }
@@ -160,15 +177,8 @@ __device__ void attention_t(const float* __restrict__ qkv_t, int R, int split, c
     float q[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) q[d] = qkv_t[(h * HD + d) * TS + i] * 0.25f;
+    // one pass over the keys with a running maximum (online softmax): the keys are read once
     float m = -INFINITY;
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr)
-      for (int j = k0[rr]; j < k1[rr]; ++j) {
-        float s = 0.0f;
-#pragma unroll
-        for (int d = 0; d < HD; ++d) s = fmaf(q[d], qkv_t[(D + h * HD + d) * TS + j], s);
-        m = fmaxf(m, s);
-      }
     float l = 0.0f;
     float acc[HD];
 #pragma unroll
@@ -179,6 +189,13 @@ __device__ void attention_t(const float* __restrict__ qkv_t, int R, int split, c
         float s = 0.0f;
 #pragma unroll
         for (int d = 0; d < HD; ++d) s = fmaf(q[d], qkv_t[(D + h * HD + d) * TS + j], s);
+        if (s > m) {
+          const float c = __expf(m - s);   // 0 for the first key (m = -inf)
+          l *= c;
+#pragma unroll
+          for (int d = 0; d < HD; ++d) acc[d] *= c;
+          m = s;
+        }
         const float p = __expf(s - m);
         l += p;
 #pragma unroll
@@ -388,13 +405,14 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
     // stage Wat [o][d] (row-major, stride WS) and W2^T [o][p]
     float* wat = big_t;               // [64][WS]
     float* w2t = big_t + 64 * WS;     // [64][36]
+    // consecutive threads read consecutive global words (the transposition happens on the shared-memory side)
     for (int idx = tid; idx < D * D; idx += NT) {
-      const int oo = idx >> 6, d = idx & 63;
-      wat[oo * WS + d] = w[o.head1_w + (size_t)(2 * D + d) * D + oo];
+      const int d = idx >> 6, oo = idx & 63;
+      wat[oo * WS + d] = __ldg(&w[o.head1_w + (size_t)(2 * D + d) * D + oo]);
     }
     for (int idx = tid; idx < 32 * D; idx += NT) {
-      const int p = idx >> 6, oo = idx & 63;
-      w2t[oo * 36 + p] = w[o.head2_w + (size_t)oo * 32 + p];  // head2^T is [64][32]
+      const int oo = idx >> 5, p = idx & 31;
+      w2t[oo * 36 + p] = __ldg(&w[o.head2_w + (size_t)oo * 32 + p]);  // head2^T is [64][32]
     }
     __syncthreads();
     if (o.has_context) {
