@@ -216,4 +216,7 @@ int hostcheck_lsap(const double* cost, const int32_t* nr_arr, const int32_t* nc_
   return 0;
 }
 
+// "<x>#..." < "<y>#..." as the reference compares its slot keys (strings): muav_alloc.cuh slot_id_less
+int hostcheck_slot_id_less(int x, int y) { return slot_id_less(x, y) ? 1 : 0; }
+
 }  // extern "C"

@@ -66,3 +66,19 @@ def test_kernel_lsap_cpu_build_matches_scipy(hostcheck):
         want = np.full(14, -1)
         want[r] = cc
         assert list(got[b]) == list(want), b
+
+
+def test_performance_impact_slot_key_order_is_the_string_order(hostcheck):
+    """PerformanceImpact breaks ties between equal (IPI, agent) candidates by the slot key STRING "<id>#c<k>" / "<id>#r<k>"
+    (MarketBased/PerformanceImpact.py:141-143 compares tuples that end in the key; keys from CBBA.py:46-65): the device
+    allocator's integer rule must order task ids exactly like Python orders those strings."""
+    import ctypes as C
+
+    f = hostcheck.lib.dll.hostcheck_slot_id_less
+    f.restype, f.argtypes = C.c_int, [C.c_int, C.c_int]
+    ids = list(range(1, 130)) + [199, 200, 201, 999, 1000, 1001, 1099, 1100, 1999, 2000, 2047]
+    for x in ids:
+        for y in ids:
+            if x != y:
+                assert bool(f(x, y)) == (f"{x}#c0" < f"{y}#c0"), (x, y)
+                assert (f"{x}#c0" < f"{y}#r1") == (f"{x}#" < f"{y}#")   # the id part decides between different tasks
