@@ -30,6 +30,9 @@
  *   muav_alloc_opts.planner   -> UrgencyPair / UrgencyCommit / UrgencyCoalition .plan, AttentionCommit / AttentionEscort
  *                                ._plan_from_scores            PairCostHybrid.py:520-550, AttentionCommit.py:266-357,
  *                                                              AttentionEscort.py:500-517,720-767
+ *   muav_alloc_opts.planner = 6 -> PerformanceImpact.allocate_tasks(max_tasks_per_agent=1)
+ *                                                              TaskAllocation/MarketBased/PerformanceImpact.py:59-224
+ *                                (expand_slot_keys / agent_eligible: TaskAllocation/MarketBased/CBBA.py:27-65)
  *   muav_reset_upload / muav_state_bytes / muav_tape_bytes / muav_snapshot / muav_field_info / muav_record_bytes:
  *                                device-resident state that replaces the UAV / Task / Threat objects (host packing at
  *                                reset, snapshots for the object proxies); reset itself (DroneEnv.py:522-762) stays in Python.
