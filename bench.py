@@ -40,9 +40,38 @@ ENVS_PER_GPU = 4096
 EPISODE = 150
 HYBRID_INTERVAL = 15
 METRIC = "WPS_hard env-steps/sec (batched, 1/2/4/8 B200) vs ref CPU; % HBM roofline"
-# dram__bytes_read.sum + dram__bytes_write.sum per muav_step_kernel launch (4096 WPS_hard envs), ncu --set full capture
-# gpurun_out/prof_step_r1_lean.ncu-rep summarised in profiles/r01_step_kernel_ncu_v4.md: 62.3 MB read + 2.3 MB written
-NCU_TRAFFIC_BYTES = 64.6e6  # dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_step_kernel_ncu_v4.md
+# roofline.traffic comes from profiles/step_kernel_traffic.json, written by tools/ncu_summary.py from an `ncu --set full`
+# capture together with a hash of the kernel sources it was taken on; a stale capture (sources changed since) reads as null
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+# the unmodified reference (DroneEnv + HungarianAllocator incl. observation building) measured in
+# the survey container, env-steps/s per core on WPS_hard; the oracle port used here skips the observation dicts
+REFERENCE_PER_CORE_SURVEY = "920-1560 env-steps/s/core (BASELINE.md section 2, unmodified reference incl. observations)"
+
+
+def kernel_source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "multi_uav_ta_gym_env_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.startswith("muav_scorer"):
+            continue
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(workload, envs):
+    """(bytes per launch | None, note) for the step kernel of this workload from the committed ncu summary."""
+    try:
+        rec = json.load(open(TRAFFIC_FILE))
+    except Exception:
+        return None, "no ncu capture committed (profiles/step_kernel_traffic.json)"
+    ent = rec.get(f"{workload}:{envs}")
+    if not ent:
+        return None, f"no ncu capture for {workload} with {envs} environments"
+    if ent.get("source_hash") != kernel_source_hash():
+        return None, f"ncu capture {ent.get('report')} is from other kernel sources ({ent.get('source_hash')}): stale"
+    return float(ent["dram_bytes_per_launch"]), (f"dram__bytes_read.sum + dram__bytes_write.sum per launch, {ent.get('report')}"
+                                                  f" ({ent.get('note', '')})")
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port)
@@ -140,6 +169,12 @@ class ClockSampler:
     def mark(self):
         return len(self.samples)
 
+    def wait_for(self, n, keep_busy, timeout_s=3.0):
+        """Keep the GPU under the same load (keep_busy() enqueues a few more untimed steps) until n samples exist."""
+        t0 = time.perf_counter()
+        while self.proc is not None and len(self.samples) < n and time.perf_counter() - t0 < timeout_s:
+            keep_busy()
+
     def stop(self, first=0):
         """Summary of the samples taken from index `first` on (the timed region); when the region was too short for
         three samples, every sample since start() is used (the warm-up runs the same load)."""
@@ -195,6 +230,8 @@ def run_gpu_arm(args):
         cpu_base = run_cpu_arm(EPISODE, 30, min_seconds=args.cpu_seconds)  # before CUDA is initialised (fork)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    sampler = ClockSampler(local)   # started before any GPU work so that it is warm when the timed region begins
+    sampler.start()
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     # workload: the default is BASELINE config 2; the others are BASELINE configs 3-5 (extra lines for profiles/)
@@ -230,6 +267,13 @@ def run_gpu_arm(args):
     else:
         raise SystemExit(f"unknown workload {wl}")
     E = args.envs
+    scaling = "weak"
+    if args.global_envs > 0:
+        # strong scaling: a fixed total sharded by environment index (BASELINE configs 3-5)
+        if args.global_envs % world:
+            raise SystemExit("--global-envs must be a multiple of the number of GPUs")
+        E = args.global_envs // world
+        scaling = "strong"
     # task slots per environment: the library default is the provable bound (every task that could ever be created, 48
     # for WPS_hard).  With slot recycling at most 24 are alive at once over 4096 seeds x 150 steps; --task-cap 32 gives
     # 15 instead of 12 environments per SM but no measurable gain in this bench, so the default stays the safe one.
@@ -286,8 +330,6 @@ def run_gpu_arm(args):
         torch.cuda.synchronize(dev)
 
     # ---- warm-up (then rewind so that the timed region starts at an episode boundary)
-    sampler = ClockSampler(local)
-    sampler.start()
     for w in range(max(args.warmup, 3)):
         device_step(w % EPISODE)
     env.restore()
@@ -316,39 +358,82 @@ def run_gpu_arm(args):
     enqueue_ms = (time.perf_counter() - t_enq) * 1e3 / K   # host time to enqueue one step (the GPU must not wait for it)
     barrier()
     wall_ms = (time.perf_counter() - t_enq) * 1e3 / K      # wall clock per step including the L2 flush between steps
-    clocks = sampler.stop(first_sample)
+    gpu_launches = launches["n"]                           # our kernels launched inside the timed region
     err_flags = max(int(env.error_flags().abs().max().item()), int(err_acc.item()))  # overflow bits: must stay 0
+    if sampler.mark() - first_sample < 3:
+        # a 20-step timed region lasts a few milliseconds: continue the identical load, untimed, until the sampler has
+        # three readings taken under it
+        def more():
+            for t in range(15):
+                flush_buf.fill_(t)
+                score_step(1 + t)
+                env.step_allocated(spec, 1, edge_scores=scores)
+            torch.cuda.synchronize(dev)
+        sampler.wait_for(first_sample + 3, more)
+        env.restore()
+    clocks = sampler.stop(first_sample)
+    clocks["window"] = "timed region + identical untimed continuation until 3 samples"
     step_ms = sum(a.elapsed_time(c) for a, b, c in ev)
     kern_ms = sum(b.elapsed_time(c) for a, b, c in ev)
-    gpu_launches = launches["n"]
     t_all = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     step_ms, kern_ms = t_all.tolist()
     value = world * E * K / (step_ms / 1e3)
 
-    # ---- end-to-end through the host-buffer entry point
+    # ---- the episode end (metrics kernel + the path's only collective + rewind), timed on its own: a 20-step run never
+    # reaches it, so the collective is measured explicitly
+    env.restore()
+    vec_probe = sharding.metric_vector(env.metrics(), names)
+    for _ in range(3):
+        sharding.allreduce_metric_vector(vec_probe)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    NCOLL = 20
+    c0.record()
+    for _ in range(NCOLL):
+        sharding.allreduce_metric_vector(vec_probe)
+    c1.record()
+    barrier()
+    coll_us = torch.tensor([c0.elapsed_time(c1) * 1e3 / NCOLL], dtype=torch.float64, device=dev)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(5):
+        episode_end()
+    p1.record()
+    barrier()
+    ep_end_ms = torch.tensor([p0.elapsed_time(p1) / 5], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(coll_us, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ep_end_ms, op=dist.ReduceOp.MAX)
+    coll_us, ep_end_ms = coll_us.item(), ep_end_ms.item()
+    metric_acc_timed = metric_acc.clone()
+
+    # ---- end-to-end through the host-buffer entry points (muav_ctx_allocate_host / muav_ctx_step_host): the allocator's
+    # decision goes to pinned host memory, comes back as host actions, reward / terminated / truncated land in host memory
     env.restore()
     A = env.n_agents
     h_act = torch.empty(E, A, 2, dtype=torch.int32).pin_memory()
-    d_act = torch.empty(E, A, 2, dtype=torch.int32, device=dev)
     h_rew = torch.empty(E, dtype=torch.float64).pin_memory()
     h_term = torch.empty(E, dtype=torch.uint8).pin_memory()
     h_trunc = torch.empty(E, dtype=torch.uint8).pin_memory()
-    import ctypes as C
+
+    def host_step(t):
+        score_step(t)
+        env.allocate_host(spec, h_act, edge_scores=scores)   # kernel + D2H + sync: the caller holds the decision
+        env.step_host(h_act, h_rew, h_term, h_trunc, 1, hint=spec)   # H2D + step + packed D2H + sync
+        if t + 1 == EPISODE:
+            episode_end()
+
+    for w in range(max(args.warmup, 3)):   # warm the host-buffer path too (module load of the allocator-only kernel, ctx)
+        host_step(w % EPISODE)
+    env.restore()
     Ke = min(K, 2 * EPISODE)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(Ke):
-        t = k % EPISODE
-        score_step(t)
-        env.allocate(spec, edge_scores=scores, actions_out=d_act)
-        h_act.copy_(d_act, non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the caller now holds the allocator's decision
-        env.step_host(h_act, h_rew, h_term, h_trunc, 1, hint=spec)
-        if t + 1 == EPISODE:
-            episode_end()
+        host_step(k % EPISODE)
     e1.record()
     barrier()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -357,6 +442,7 @@ def run_gpu_arm(args):
     e2e_value = world * E * Ke / (e2e_ms.item() / 1e3)
     err_flags = max(err_flags, int(err_acc.item()), int(env.error_flags().abs().max().item()))
     act_bytes = E * A * 2 * 4
+    metric_acc = metric_acc_timed
 
     if rank == 0:
         rb = env.record_bytes
@@ -365,26 +451,30 @@ def run_gpu_arm(args):
         b_alg, b_alg_src = survey_b_alg(wl, A, env)
         peak, peak_src = hbm_peak()
         achieved = E * b_alg / (kern_ms / K / 1e3) / 1e9
+        traffic, traffic_note = ncu_traffic(wl, E)
+        ms_step = step_ms / K
         stats = sharding.summarize(metric_acc[: len(sharding.METRIC_VECTOR)].cpu())
         line = {
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
-            "warmup": max(args.warmup, 3), "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{case_name} ({A} agents), {E} envs per GPU, {desc}, seeds = env index",
                        "envs_per_gpu": E, "global_envs": world * E, "parallelism": f"env-shard x{world}",
                        "l2": f"flushed between timed steps (256 MB write); state {E * rb / 1e6:.0f} MB vs 126 MB L2",
                        "record_bytes": rb, "task_slots": int(env.task_cap), "agent_steps_per_s": value * A,
-                       "host_enqueue_ms_per_step": enqueue_ms, "wall_ms_per_step_incl_flush": wall_ms},
+                       "host_enqueue_ms_per_step": enqueue_ms, "wall_ms_per_step_incl_flush": wall_ms,
+                       "episode_end_ms": ep_end_ms,
+                       "env_steps_per_s_incl_episode_end": world * E * EPISODE / ((EPISODE * ms_step + ep_end_ms) / 1e3)},
+            "collective_us": coll_us,
+            "collective": f"end-of-episode all-reduce of the {len(sharding.METRIC_VECTOR)}-double metric vector, "
+                          f"{'NCCL over NVLink' if world > 1 else 'single rank (no-op)'}, mean of {NCOLL} after 3 warm-ups",
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": act_bytes,
                     "d2h_bytes_per_step": act_bytes + E * 10, "steps": Ke},
             "gpu_launches": gpu_launches,
             "error_flags": err_flags,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES if (wl == "hard_pair" and E == ENVS_PER_GPU) else None,
-                         "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
-                                         "capture (profiles/r01_step_kernel_ncu_v4.md); the write-back of the records is "
-                                         "still in L2 when the kernel ends, so it is below the algorithmic bytes",
+                         "traffic": traffic, "traffic_note": traffic_note,
                          "algorithmic_bytes_per_launch": E * b_alg,
                          "kernel": "muav_step_kernel", "bytes_per_env_step": b_alg, "bytes_per_env_step_source": b_alg_src,
                          "record_io_bytes_per_env_step": b_rec,
@@ -395,7 +485,7 @@ def run_gpu_arm(args):
                                                     "mean_n_missed_windows", "mean_on_time_rate", "mean_Kills")},
         }
         if cpu_base is not None:
-            line["cpu_baseline"] = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = cpu_baseline_record(cpu_base)
         emit_line(line)
     if world > 1:
         dist.destroy_process_group()
@@ -416,6 +506,13 @@ def survey_b_alg(wl, A, env):
     return 2 * s_env + 44 + 4 * A + 16, "SURVEY.md 8(d), formula"
 
 
+def cpu_baseline_record(res):
+    rec = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    rec["per_core"] = res["value"] / max(res["cores"], 1)
+    rec["reference_per_core_survey"] = REFERENCE_PER_CORE_SURVEY
+    return rec
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -429,7 +526,7 @@ def run_reference_arm(args):
         "config": {"workload": f"{CASE} (8 agents), one env process per host core, Local-Hungarian + random-init "
                                f"Att-Pair edge scores (reference algorithm restated in oracle/; the Python reference "
                                f"itself cannot travel to the GPU box)"},
-        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": cpu_baseline_record(res),
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit_line(line)
@@ -478,7 +575,10 @@ def main():
                     help="hard_pair (default, BASELINE config 2) | hard_local | commit_urgency | escort_coalition | burst_xK "
                          "| attn_context | hard_pi | escort_pi")
     ap.add_argument("--task-cap", type=int, default=0, help="task slots per environment (0 = workload default)")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--global-envs", type=int, default=0,
+                    help="strong scaling: total environments sharded across the GPUs (overrides --envs)")
+    ap.add_argument("--cpu-seconds", type=float, default=60.0,
+                    help="timed seconds of the CPU baseline per worker (BASELINE.md section 3: >= 60)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     with _QuietStdout() as q:

@@ -187,11 +187,30 @@ int muav_step(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, 
  * terminates) that muav_step accepts.  Per-env allocator state (last_plan_step, n_replans, n_calls) advances. */
 int muav_allocate(const muav_config* cfg, void* d_records, const muav_alloc_opts* opts, const muav_step_out* out,
                   int32_t* d_actions_out, int n_envs, void* stream);
-/* Same call with HOST action / output buffers: copies in, runs, copies out, synchronises. */
+/* Same call with HOST action / output buffers: copies in, runs, copies out, synchronises.  The staging block is a
+ * stream-ordered allocation of the call itself (thread-safe, any device); muav_ctx_step_host below avoids it. */
 int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* h_actions,
                    const muav_alloc_opts* opts, const muav_token_out* tok, double* h_reward, uint8_t* h_terminated,
                    uint8_t* h_truncated, int n_envs, int n_steps, void* stream, const int32_t* d_env_order,
                    int32_t* d_env_order_next);
+
+/* Host-buffer context.  The reference's env object owns its buffers (MultiUAVEnv instance state, mUAV_TA/DroneEnv.py:
+ * 73-323); here a caller-owned handle owns the device staging block and the pinned host image of the per-step outputs
+ * for n_envs environments of ONE device.  The library keeps no mutable process-wide state: calls on different handles
+ * are independent (one handle per thread / per device); a handle must not be used from two threads at once. */
+typedef struct muav_ctx muav_ctx;
+int muav_ctx_create(const muav_config* cfg, int n_envs, int device, muav_ctx** out);
+void muav_ctx_destroy(muav_ctx* ctx);
+/* muav_step_host on the handle's buffers: one H2D copy (actions), the step, ONE D2H copy (reward | terminated |
+ * truncated, packed), one synchronisation.  MultiUAVEnv.step with host actions in / host rewards out (DroneEnv.py:774). */
+int muav_ctx_step_host(muav_ctx* ctx, void* d_records, const uint32_t* d_tapes, const int32_t* h_actions,
+                       const muav_alloc_opts* opts, const muav_token_out* tok, double* h_reward, uint8_t* h_terminated,
+                       uint8_t* h_truncated, int n_steps, void* stream, const int32_t* d_env_order,
+                       int32_t* d_env_order_next);
+/* muav_allocate with the ordered action list delivered to HOST memory [E, n_agents, 2] (HungarianAllocator.allocate_tasks
+ * returning its dict to the caller, HungarianAllocator.py:72-208): allocator kernel, one D2H copy, one synchronisation. */
+int muav_ctx_allocate_host(muav_ctx* ctx, void* d_records, const muav_alloc_opts* opts, const muav_step_out* out,
+                           int32_t* h_actions_out, void* stream);
 
 /* K fused (plan -> allocate -> step) iterations with the state resident on chip: muav_step with a fused allocator and
  * no external actions (the episode loops of experiments/wps_eval.py:96-140 and escort_eval.py:85-200 without the

@@ -93,6 +93,7 @@ ABI_SYMBOLS = [
     "muav_field_info", "muav_header_index", "muav_step", "muav_allocate", "muav_step_host", "muav_lsap",
     "muav_avoid_obstacles", "muav_metric_name", "muav_metrics", "muav_tokens_pair", "muav_tokens_commit", "muav_tokens_escort", "muav_tokens_context", "muav_pair_mask", "muav_observe",
     "muav_att_pair_scores", "muav_att_context_pair_scores", "muav_rollout", "muav_state_bytes", "muav_tape_bytes", "muav_reset_upload", "muav_snapshot",
+    "muav_ctx_create", "muav_ctx_destroy", "muav_ctx_step_host", "muav_ctx_allocate_host",
 ]
 
 
@@ -180,6 +181,15 @@ class CudaLib(Lib):
         d.muav_step_host.restype = C.c_int
         d.muav_step_host.argtypes = [C.POINTER(MuavConfig), P, P, P, C.POINTER(MuavAllocOpts), C.POINTER(MuavTokenOut),
                                      P, P, P, C.c_int, C.c_int, P, P, P]
+        d.muav_ctx_create.restype = C.c_int
+        d.muav_ctx_create.argtypes = [C.POINTER(MuavConfig), C.c_int, C.c_int, C.POINTER(P)]
+        d.muav_ctx_destroy.restype = None
+        d.muav_ctx_destroy.argtypes = [P]
+        d.muav_ctx_step_host.restype = C.c_int
+        d.muav_ctx_step_host.argtypes = [P, P, P, P, C.POINTER(MuavAllocOpts), C.POINTER(MuavTokenOut), P, P, P, C.c_int, P,
+                                         P, P]
+        d.muav_ctx_allocate_host.restype = C.c_int
+        d.muav_ctx_allocate_host.argtypes = [P, P, C.POINTER(MuavAllocOpts), C.POINTER(MuavStepOut), P, P]
         d.muav_lsap.restype = C.c_int
         d.muav_lsap.argtypes = [P, P, P, C.c_int, C.c_int, P, C.c_int, P]
         d.muav_avoid_obstacles.restype = C.c_int

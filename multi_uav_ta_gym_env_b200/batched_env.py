@@ -138,6 +138,25 @@ class BatchedMultiUAVEnv:
         self.scenarios = None
         self.agent_names = None
         self.launches = 0
+        self._ctx = None  # muav_ctx handle of the host-buffer entry points (created on first use, owned by this object)
+
+    def __del__(self):
+        ctx, self._ctx = getattr(self, "_ctx", None), None
+        if ctx:
+            try:
+                self.lib.dll.muav_ctx_destroy(ctx)
+            except Exception:
+                pass
+
+    def _host_ctx(self):
+        """The caller-owned handle behind step_host / allocate_host (include/muav.h: muav_ctx): staging buffers for this
+        environment batch on this device."""
+        if self._ctx is None:
+            h = C.c_void_p()
+            idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            _lib.check(self.lib.dll.muav_ctx_create(C.byref(self.cfg), self.n_envs, int(idx), C.byref(h)), "muav_ctx_create")
+            self._ctx = h
+        return self._ctx
 
     # ------------------------------------------------------------------ reset
     def reset(self, seeds: Optional[Sequence[int]] = None):
@@ -161,7 +180,9 @@ class BatchedMultiUAVEnv:
         _lib.check(rc, "muav_reset_upload")
         torch.cuda.current_stream(self.device).synchronize()
         self._records0 = self.records.clone()
-        self.n_open.fill_(int(self.codec.header(rec[0], "N_OPEN")))
+        self.n_open.copy_(self.header_int("N_OPEN"))
+        self._order_cur = -1   # identity order for the first launch; both buffers start with zeroed fill counters
+        self._order.zero_()
         return self
 
     def restore(self):
@@ -219,16 +240,22 @@ class BatchedMultiUAVEnv:
 
     # ------------------------------------------------------------------ step
     def _order_args(self):
-        """Point muav_step_out at the current / next launch-slot order and flip the buffers."""
+        """Point muav_step_out at the current / next launch-slot order.  The buffers flip in _order_commit(), i.e. only
+        after a launch that really ran and filled the next order."""
         if not self.group_replanners:
             self._out.d_env_order = None
             self._out.d_env_order_next = None
+            self._order_next = -1
             return
         cur = self._order_cur
         nxt = 0 if cur != 0 else 1
         self._out.d_env_order = None if cur < 0 else self._order[cur].data_ptr()
         self._out.d_env_order_next = self._order[nxt].data_ptr()
-        self._order_cur = nxt
+        self._order_next = nxt
+
+    def _order_commit(self, rc, n_steps):
+        if rc == 0 and n_steps > 0 and self.n_envs > 0 and self.group_replanners:
+            self._order_cur = self._order_next
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -247,9 +274,11 @@ class BatchedMultiUAVEnv:
             actions = torch.stack([a_sorted, i_sorted], dim=2)
         actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
         self._order_args()
-        rc = self.lib.dll.muav_step(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(),
-                                    actions.data_ptr(), None, C.byref(self._out), self._tok_ref(), self.n_envs, n_steps,
-                                    self._stream())
+        with torch.cuda.device(self.device):
+            rc = self.lib.dll.muav_step(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(),
+                                        actions.data_ptr(), None, C.byref(self._out), self._tok_ref(), self.n_envs, n_steps,
+                                        self._stream())
+        self._order_commit(rc, n_steps)
         _lib.check(rc, "muav_step")
         self.launches += 1
         return self.reward, self.terminated, self.truncated
@@ -266,11 +295,28 @@ class BatchedMultiUAVEnv:
             O.order_hint_mode = hint.mode
             O.replan_interval, O.event_mask, O.planner = hint.replan_interval, hint.event_mask, hint.planner
         self._order_args()
-        rc = self.lib.dll.muav_step_host(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(), ptr(h_actions),
-                                         None if O is None else C.byref(O), self._tok_ref(), ptr(h_reward),
-                                         ptr(h_terminated), ptr(h_truncated), self.n_envs, n_steps, self._stream(),
-                                         self._out.d_env_order, self._out.d_env_order_next)
-        _lib.check(rc, "muav_step_host")
+        with torch.cuda.device(self.device):
+            rc = self.lib.dll.muav_ctx_step_host(self._host_ctx(), self.records.data_ptr(), self.tapes.data_ptr(),
+                                                 ptr(h_actions), None if O is None else C.byref(O), self._tok_ref(),
+                                                 ptr(h_reward), ptr(h_terminated), ptr(h_truncated), n_steps, self._stream(),
+                                                 self._out.d_env_order, self._out.d_env_order_next)
+        self._order_commit(rc, n_steps)
+        _lib.check(rc, "muav_ctx_step_host")
+        self.launches += 1
+
+    def allocate_host(self, spec: "AllocSpec", h_actions_out, edge_scores: Optional[torch.Tensor] = None,
+                      priorities: Optional[torch.Tensor] = None, reserved: Optional[torch.Tensor] = None):
+        """allocate() with the ordered action list delivered to HOST memory int32 [E, A, 2] (the allocator handing its
+        decision to the caller, HungarianAllocator.py:72-208): kernel, one D2H copy and the synchronisation in one call."""
+        ptr = lambda x: x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
+        O, keep = self._alloc_opts(spec, edge_scores, priorities, reserved)
+        cur = self._order_cur
+        self._out.d_env_order = self._order[cur].data_ptr() if (self.group_replanners and cur >= 0) else None
+        self._out.d_env_order_next = None
+        with torch.cuda.device(self.device):
+            rc = self.lib.dll.muav_ctx_allocate_host(self._host_ctx(), self.records.data_ptr(), C.byref(O),
+                                                     C.byref(self._out), ptr(h_actions_out), self._stream())
+        _lib.check(rc, "muav_ctx_allocate_host")
         self.launches += 1
 
     def _alloc_opts(self, spec, edge_scores, priorities, reserved, task_order=None, plan_pri=None, plan_commit=None):
@@ -323,8 +369,10 @@ class BatchedMultiUAVEnv:
         """n_steps fused (allocate -> step) iterations per environment, state resident in shared memory."""
         O, keep = self._alloc_opts(spec, edge_scores, priorities, reserved, task_order, plan_pri, plan_commit)
         self._order_args()
-        rc = self.lib.dll.muav_rollout(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(), C.byref(O),
-                                       C.byref(self._out), self._tok_ref(), self.n_envs, n_steps, self._stream())
+        with torch.cuda.device(self.device):
+            rc = self.lib.dll.muav_rollout(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(), C.byref(O),
+                                           C.byref(self._out), self._tok_ref(), self.n_envs, n_steps, self._stream())
+        self._order_commit(rc, n_steps)
         _lib.check(rc, "muav_rollout")
         self.launches += 1
         return self.reward, self.terminated, self.truncated
@@ -341,8 +389,9 @@ class BatchedMultiUAVEnv:
         cur = self._order_cur
         self._out.d_env_order = self._order[cur].data_ptr() if (self.group_replanners and cur >= 0) else None
         self._out.d_env_order_next = None
-        rc = self.lib.dll.muav_allocate(C.byref(self.cfg), self.records.data_ptr(), C.byref(O), C.byref(self._out),
-                                        actions_out.data_ptr(), self.n_envs, self._stream())
+        with torch.cuda.device(self.device):
+            rc = self.lib.dll.muav_allocate(C.byref(self.cfg), self.records.data_ptr(), C.byref(O), C.byref(self._out),
+                                            actions_out.data_ptr(), self.n_envs, self._stream())
         _lib.check(rc, "muav_allocate")
         self.launches += 1
         return actions_out

@@ -185,7 +185,7 @@ MUAV_HD inline double residual_demand(const Sim& S, int k) {
     return r > 0.0 ? r : 0.0;
   }
   int ti = S.V.k_type()[k];
-  int TC = S.V.L->D.TC;
+  int TC = S.V.lay().D.TC;
   double r = S.V.k_cur2(ti, k) - S.V.k_alloc2(ti, k);
   return r > 0.0 ? r : 0.0;
 }
@@ -199,12 +199,12 @@ MUAV_HD inline double coalition_edge_score(const Sim& S, int a, int k, int t);
 MUAV_HD MUAV_NI_A inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, int e, int16_t* out_agent, int16_t* out_tid, int lane,
                                   int nlanes, bool local_ptrs = false) {
   View& V = S.V;
-  const int A = V.L->D.A, TC = V.L->D.TC;
+  const int A = V.lay().D.A, TC = V.lay().D.TC;
   const int t = HIv(T);
   AllocScratch W = carve_scratch(S.scratch, A, TC);
   const size_t eo = local_ptrs ? 0 : (size_t)e;  // planner-produced arrays live in this env's scratch
   const uint8_t* reserved = O.d_reserved ? O.d_reserved + eo * A : nullptr;
-  const int IC = V.L->D.IC;
+  const int IC = V.lay().D.IC;
   const double* pri = O.d_priorities ? O.d_priorities + eo * IC : nullptr;
   const size_t sc_off = (size_t)e * O.score_rows * O.score_cols;
   const float* scores = (O.d_edge_scores && !O.score_f64) ? (const float*)O.d_edge_scores + sc_off : nullptr;
@@ -450,7 +450,7 @@ MUAV_HD inline bool slot_id_less(int x, int y) {
 MUAV_HD MUAV_NI_A inline int pi_allocate(Sim& S, const muav_alloc_opts& O, int e, int16_t* out_agent, int16_t* out_tid, int lane,
                                int nlanes) {
   View& V = S.V;
-  const int A = V.L->D.A, TC = V.L->D.TC;
+  const int A = V.lay().D.A, TC = V.lay().D.TC;
   const int t = HIv(T);
   AllocScratch W = carve_scratch(S.scratch, A, TC);
   const int M = A > TC ? A : TC;
@@ -480,7 +480,7 @@ MUAV_HD MUAV_NI_A inline int pi_allocate(Sim& S, const muav_alloc_opts& O, int e
         if (V.a_state()[a] != -1 && !(reserved && reserved[a])) W.free_agents[n_free++] = (int16_t)a;
       // _open_tasks (paper_eval.py:96-101) + expand_slot_keys (CBBA.py:46-65)
       const int n_tasks = HIv(N_TASKS);
-      const int IC = V.L->D.IC;
+      const int IC = V.lay().D.IC;
       const int32_t* order = O.d_task_order ? O.d_task_order + (size_t)e * IC : nullptr;   // the caller's `tasks` argument
       const int KWn = (n_tasks + 31) >> 5;
       int wd = 0;
@@ -678,9 +678,9 @@ MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, in
   if (O.planner == 6) return pi_allocate(S, O, e, out_agent, out_tid, lane, nlanes);
   View& V = S.V;
   const muav_config& C = S.C();
-  const int A = V.L->D.A, TC = V.L->D.TC;
+  const int A = V.lay().D.A, TC = V.lay().D.TC;
   const int t = HIv(T);
-  AllocScratch W = carve_scratch(S.scratch, A, TC, V.L->D.IC);
+  AllocScratch W = carve_scratch(S.scratch, A, TC, V.lay().D.IC);
   // the caller's cadence (wps_eval.py:64-73 / escort_eval.py:52-58), then plan(force=True)
   const int interval = O.replan_interval > 0 ? O.replan_interval : 1;
   const bool go = O.mode == 3 || t == 0 || (t % interval) == 0 || (HIv(EV_TAGMASK) & O.event_mask) != 0;
@@ -756,7 +756,7 @@ MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, in
   if (O.planner == 1 || O.planner == 3) {
     P.d_priorities = W.plan_pri;
     P.pair_tokens = 1;      // task list = build_att_tokens' open list (alloc < cur), not truncated
-    P.score_cols = V.L->D.IC;
+    P.score_cols = V.lay().D.IC;
     P.score_rows = 0;
     P.use_visibility = 1;
   } else if (O.planner == 5) {

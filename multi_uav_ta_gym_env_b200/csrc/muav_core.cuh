@@ -106,8 +106,8 @@ struct Sim {
   long long* phase_cycles;  // MUAV_PHASE_TIMING only: per-warp cycle sums by phase
 
   MUAV_HD const muav_config& C() const { return *Cp; }
-  MUAV_HD int A() const { return V.L->D.A; }
-  MUAV_HD int QC() const { return V.L->D.QC; }
+  MUAV_HD int A() const { return V.lay().D.A; }
+  MUAV_HD int QC() const { return V.lay().D.QC; }
 
   // ------------------------------------------------------------------ RNG (oracle/rng.py rules)
   MUAV_HD uint32_t rng_word(int stream) {
@@ -147,7 +147,7 @@ struct Sim {
   MUAV_HD int qhead(int a) const { return V.a_qlen()[a] > 0 ? V.a_queue()[a] : 0; }
   MUAV_HD int qfind(int a, int tid) const {
     int n = V.a_qlen()[a];
-    for (int s = 0; s < n; ++s)
+    _Pragma("unroll 1") for (int s = 0; s < n; ++s)
       if (V.a_queue()[s * A() + a] == tid) return s;
     return -1;
   }
@@ -157,7 +157,7 @@ struct Sim {
     double* qt = V.a_qtime();
     int Aa = A();
     double t0 = qt[slot * Aa + a];
-    for (int s = slot; s + 1 < n; ++s) {
+    _Pragma("unroll 1") for (int s = slot; s + 1 < n; ++s) {
       q[s * Aa + a] = q[(s + 1) * Aa + a];
       qt[s * Aa + a] = qt[(s + 1) * Aa + a];
     }
@@ -178,7 +178,7 @@ struct Sim {
   MUAV_HD void set_known(int a, int k) { V.known()[(k >> 5) * A() + a] |= (1u << (k & 31)); }
   MUAV_HD void push_event(int tag, int arg) {
     int n = HIv(N_EVENTS);
-    if (n >= V.L->D.EVC) {
+    if (n >= V.lay().D.EVC) {
       HIv(ERRFLAGS) |= ERR_EVENT_OVERFLOW;
       return;
     }
@@ -188,7 +188,7 @@ struct Sim {
   // allocationDetails[k] is represented by the agents whose queue holds task k+1
   MUAV_HD int details_count(int tid) const {
     int c = 0;
-    for (int a = 0; a < A(); ++a)
+    _Pragma("unroll 1") for (int a = 0; a < A(); ++a)
       if (qfind(a, tid) >= 0) ++c;
     return c;
   }
@@ -204,12 +204,12 @@ struct Sim {
   // DroneEnvComponents.py:280-301.  `t0` is the time stored with the entry that was just removed.
   MUAV_HD MUAV_NI_H void remove_agent_cap(int k, int a, double t0) {
     if (V.k_status()[k] == 2) return;
-    int TC = V.L->D.TC;
+    int TC = V.lay().D.TC;
     _Pragma("unroll 1") for (int c = 0; c < 6; ++c) V.k_alloc2(c, k) = V.k_alloc2(c, k) - cap(a, c);
     int tid = k + 1;
     int cnt = 0;
     double mn = 0.0, mx = 0.0;
-    for (int b = 0; b < A(); ++b) {
+    _Pragma("unroll 1") for (int b = 0; b < A(); ++b) {
       int s = qfind(b, tid);
       if (s >= 0) {
         double tm = V.a_qtime()[s * A() + b];
@@ -234,7 +234,7 @@ struct Sim {
   // DroneEnvComponents.py:306-326 (the queue entry itself is pushed by the caller)
   MUAV_HD MUAV_NI_H void add_agent_cap(int k, int a, double time_at) {
     if (V.k_status()[k] == 2) return;
-    int TC = V.L->D.TC;
+    int TC = V.lay().D.TC;
     double end = time_at + (double)C().duration[V.k_type()[k]];
     _Pragma("unroll 1") for (int c = 0; c < 6; ++c) V.k_alloc2(c, k) = V.k_alloc2(c, k) + cap(a, c);
     if (time_at < V.k_init()[k] || V.k_init()[k] == -1.0) {
@@ -284,7 +284,7 @@ struct Sim {
   // so only the entries at even positions are removed.
   MUAV_HD MUAV_NI_H void des_allocate_all(int a) {
     int i = 0;
-    while (i < qlen(a)) {
+    _Pragma("unroll 1") while (i < qlen(a)) {
       des_allocate(a, qat(a, i));
       ++i;
     }
@@ -346,7 +346,7 @@ struct Sim {
     int el = V.k_elig()[k];
     if (el != 0 && !((el >> V.a_type()[a]) & 1)) return false;
     int ti = V.k_type()[k];
-    int TC = V.L->D.TC;
+    int TC = V.lay().D.TC;
     if (C().capability_mask && cap(a, ti) <= 0) return false;
     if (C().saturate_mask && V.k_alloc2(ti, k) >= V.k_org_ti()[k]) return false;
     return true;
@@ -368,13 +368,13 @@ struct Sim {
   // Task ctor + env.tasks.append (DroneEnvComponents.py:224-263); returns task id or 0 on overflow
   MUAV_HD MUAV_NOINLINE int new_task(double px, double py, int ti) {
     int k = HIv(N_TASKS);
-    const int TC = V.L->D.TC, IC = V.L->D.IC;
+    const int TC = V.lay().D.TC, IC = V.lay().D.IC;
     if (k >= IC) {
       HIv(ERRFLAGS) |= ERR_TASK_OVERFLOW;
       return 0;
     }
     int slot = -1;
-    for (int sidx = 0; sidx < TC; ++sidx)
+    _Pragma("unroll 1") for (int sidx = 0; sidx < TC; ++sidx)
       if (V.s_used()[sidx] == 0) { slot = sidx; break; }
     if (slot < 0) {
       HIv(ERRFLAGS) |= ERR_TASK_OVERFLOW;
@@ -419,7 +419,7 @@ struct Sim {
   // Everything else about a closed task is dead data in the reference (closed tasks never reopen, :1460), so the
   // slot is recycled.  Spread over the lanes: lane <-> slot.
   MUAV_HD void free_dead_tasks(int lane, int nlanes) {
-    const int TC = V.L->D.TC, Aa = A();
+    const int TC = V.lay().D.TC, Aa = A();
     for (int sidx = lane; sidx < TC; sidx += nlanes) {
       const int tid = V.s_used()[sidx];
       if (tid == 0 || V.k_status()[tid - 1] != 2) continue;
@@ -487,7 +487,7 @@ struct Sim {
   MUAV_HD MUAV_NOINLINE void release_all(int for_type) {
     int col = for_type < 0 ? 6 + for_type : for_type;
     uint32_t avail = 0;
-    for (int a = 0; a < A(); ++a) {
+    _Pragma("unroll 1") for (int a = 0; a < A(); ++a) {
       if (cap(a, col) > 0) {
         if (V.a_state()[a] != -1) {
           V.a_re_eval()[a] = 1;
@@ -528,7 +528,7 @@ struct Sim {
   MUAV_HD MUAV_NI_H int closest_agent(double px, double py) const {
     double min_f = INFINITY, min_w = INFINITY;
     int cf = -1, cw = -1;
-    for (int a = 0; a < A(); ++a) {
+    _Pragma("unroll 1") for (int a = 0; a < A(); ++a) {
       int st = V.a_state()[a];
       if (st != -1 && st != 4) {
         double d = norm2(V.a_posx()[a] - px, V.a_posy()[a] - py);
@@ -545,7 +545,7 @@ struct Sim {
   // generate_threat + TaskFromThreat (DroneEnv.py:1601-1643,1861-1876)
   MUAV_HD MUAV_NI_H void generate_threat() {
     int t = HIv(T);
-    int TC = V.L->D.TC;
+    int TC = V.lay().D.TC;
     for (int g = 0; g < C().n_groups; ++g) {
       int* gnext = &V.hi()[HI_GROUP_NEXT0 + g];
       int gend = C().group_start[g + 1];
@@ -608,7 +608,7 @@ struct Sim {
     if (esc == 0 || V.k_status()[esc - 1] == 2) return 0;
     double px = V.a_posx()[prot], py = V.a_posy()[prot];
     int n = 0;
-    for (int a = 0; a < A(); ++a) {
+    _Pragma("unroll 1") for (int a = 0; a < A(); ++a) {
       if (V.a_state()[a] == -1 || !((C().escort_type_mask >> V.a_type()[a]) & 1)) continue;
       if (qlen(a) == 0 || qat(a, 0) != esc) continue;
       double d = norm2(V.a_posx()[a] - px, V.a_posy()[a] - py);
@@ -626,8 +626,24 @@ struct Sim {
     }
     return n;
   }
-  MUAV_HD double* near_d() const { return (double*)scratch + 3 * V.L->D.A; }
-  MUAV_HD int16_t* near_i() const { return (int16_t*)((double*)scratch + 4 * V.L->D.A); }
+  // first element of _escort_fighters_near's stable distance sort (DroneEnv.py:1746-1764), or -1 when the list is empty
+  MUAV_HD int nearest_escort_fighter(int prot, double radius) const {
+    if (prot < 0) return -1;
+    const int esc = V.a_escort()[prot];
+    if (esc == 0 || V.k_status()[esc - 1] == 2) return -1;
+    const double px = V.a_posx()[prot], py = V.a_posy()[prot];
+    int best = -1;
+    double bd = 0.0;
+    _Pragma("unroll 1") for (int a = 0; a < A(); ++a) {
+      if (V.a_state()[a] == -1 || !((C().escort_type_mask >> V.a_type()[a]) & 1)) continue;
+      if (qlen(a) == 0 || qat(a, 0) != esc) continue;
+      const double d = norm2(V.a_posx()[a] - px, V.a_posy()[a] - py);
+      if (d <= radius && (best < 0 || d < bd)) { best = a; bd = d; }
+    }
+    return best;
+  }
+  MUAV_HD double* near_d() const { return (double*)scratch + 3 * V.lay().D.A; }
+  MUAV_HD int16_t* near_i() const { return (int16_t*)((double*)scratch + 4 * V.lay().D.A); }
 
   // _retarget_threat_via_escort (DroneEnv.py:1766-1779)
   MUAV_HD void retarget_via_escort(int hid) {
@@ -645,7 +661,7 @@ struct Sim {
   }
   // _release_escort_agents (DroneEnv.py:1919-1936)
   MUAV_HD MUAV_NOINLINE void release_escort_agents(int esc) {
-    for (int a = 0; a < A(); ++a) {
+_Pragma("unroll 1") for (int a = 0; a < A(); ++a) {
       if (V.a_state()[a] == -1) continue;
       if (qfind(a, esc) >= 0) {
         des_allocate(a, esc);
@@ -677,7 +693,7 @@ struct Sim {
     int tid = new_task(V.a_posx()[a], V.a_posy()[a], TT_DEF);
     if (tid == 0) return;
     int k = tid - 1;
-    int TC = V.L->D.TC;
+    int TC = V.lay().D.TC;
     V.k_cur2(TT_DEF, k) = C().escort_requirement;
     V.k_org_ti()[k] = C().escort_requirement;
     V.k_kind()[k] = 1;
@@ -774,10 +790,148 @@ struct Sim {
     }
   }
 
-  // update_threats (DroneEnv.py:1725-1744)
+  // update_threats (DroneEnv.py:1725-1744), sequential form
   MUAV_HD void update_threats() {
     int n = HIv(N_ACTIVE);
     for (int i = 0; i < n; ++i) update_threat(i);
+  }
+
+  // ------------------------------------------------------------------ threat-per-lane pursuit
+  // One iteration of update_threats moves the threat (drift, or pursuit of its target agent) and copies the position to
+  // its task; only two things reach beyond the threat itself: an engagement (RNG draw, ammunition, kills, DroneEnv.py:
+  // 1781-1858) and the window outcome when it leaves the area at y <= 0.  threat_plan(i) computes the move without
+  // writing; the moves of all threats commit one per lane, the engagements / exits then run in spawn order on one lane
+  // (update_threat's own arithmetic: one norm2 + two divisions for the pursuit, one norm2 for the range test).
+  // Without escorts a move reads nothing an engagement writes (target, status and position are the threat's own, agents
+  // do not move in this phase), so one round covers all threats; with escorts _retarget_threat_via_escort reads agent
+  // and escort-task state, so the threats behind an engagement are planned again after it.
+#define MUAV_MAX_THREATS_HOST 512
+  struct ThreatPlan {
+    double hx, hy;
+    int hid, k;
+    int16_t target, intercept;
+    bool live, engage, exit_area, retarget;
+  };
+
+  MUAV_HD ThreatPlan threat_plan(int i, bool lane_on = true) {
+    ThreatPlan P;
+    P.live = P.engage = P.exit_area = P.retarget = false;
+    const int n = V.hi()[HI_N_ACTIVE];
+    const bool in_range = lane_on && i < n;
+    const int hid = in_range ? (int)V.h_order()[i] : 0;
+    P.hid = hid;
+    const bool live = in_range && V.h_status()[hid] != 2;
+    P.live = live;
+    const int ht = V.lay().D.HC > 0 ? (int)V.h_type()[hid] : UT_T1;
+    const double sp = C().speed[ht];
+    double hx = V.lay().D.HC > 0 ? V.h_posx()[hid] : 0.0, hy = V.lay().D.HC > 0 ? V.h_posy()[hid] : 0.0;
+    int tg = V.lay().D.HC > 0 ? (int)V.h_target()[hid] : -1;
+    P.target = (int16_t)tg;
+    P.intercept = V.lay().D.HC > 0 ? V.h_intercept()[hid] : (int16_t)-1;
+    const bool drift = !live || V.h_status()[hid] == 0 || tg < 0;
+    if (MUAV_F_ESCORT(C().escort_enabled) && live && !drift) {
+      // _retarget_threat_via_escort (DroneEnv.py:1766-1779) on a private copy of (target, intercepting agent)
+      const int mission = V.h_mission()[hid] >= 0 ? (int)V.h_mission()[hid] : tg;
+      if (mission >= 0 && V.a_state()[mission] != -1 && is_recon(V.a_type()[mission])) {
+        const int nf = nearest_escort_fighter(mission, C().escort_intercept_radius);
+        P.retarget = true;
+        if (nf < 0) { P.target = (int16_t)mission; P.intercept = -1; }
+        else { P.target = (int16_t)nf; P.intercept = (int16_t)nf; }
+        tg = P.target;
+      }
+    }
+    const int tga = (!drift && tg >= 0) ? tg : 0;
+    const double ax = V.a_posx()[tga], ay = V.a_posy()[tga];
+    const double dx = ax - hx, dy = ay - hy;
+    const double mag = norm2(dx, dy);
+    const bool mag_ok = !drift && mag != 0;
+    const double den = mag_ok ? mag : 1.0;
+    const double qx = ddiv(dx, den), qy = ddiv(dy, den);
+    double nx = mag_ok ? qx : 0.0, ny = mag_ok ? qy : 0.0;
+    if (drift) { nx = 0.0; ny = -1.0; }
+    hx = hx + sp * nx;
+    hy = hy + sp * ny;
+    const double dist = norm2(ax - hx, ay - hy);
+    P.hx = hx;
+    P.hy = hy;
+    P.engage = live && !drift && dist < C().engage[ht];
+    P.k = live ? V.h_task()[hid] - 1 : 0;
+    // leaving the area re-closes the task every step (DroneEnv.py:1741-1744); only the first time has any effect
+    P.exit_area = live && hy <= 0 &&
+                  !(V.k_status()[P.k] == 2 && (V.k_deadline()[P.k] < 0 || V.k_counted()[P.k] != 0));
+    return P;
+  }
+
+  MUAV_HD void threat_commit(const ThreatPlan& P) {
+    if (P.retarget) {
+      V.h_target()[P.hid] = P.target;
+      V.h_intercept()[P.hid] = P.intercept;
+    }
+    V.h_posx()[P.hid] = P.hx;
+    V.h_posy()[P.hid] = P.hy;
+    V.k_posx()[P.k] = P.hx;
+    V.k_posy()[P.k] = P.hy;
+  }
+  // the part of an update_threats iteration that reaches beyond the threat (after its move has been committed)
+  MUAV_HD void threat_effects(int hid, bool eng) {
+    if (eng) engage(hid);
+    if (V.h_posy()[hid] <= 0) {
+      const int k = V.h_task()[hid] - 1;
+      close_task(k);
+      mark_outcome(k, false);
+    }
+  }
+
+  MUAV_HD void update_threats_lanes(int lane, int nlanes, bool alive_env) {
+#if defined(__CUDA_ARCH__)
+    const int n = alive_env ? HIv(N_ACTIVE) : 0;   // warp-uniform: a warp steps one environment
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      int lo = base;
+      const int hi = base + 32 < n ? base + 32 : n;
+      while (lo < hi) {
+        const bool mine = i >= lo && i < hi;
+        const ThreatPlan P = threat_plan(mine ? i : 0, mine);
+        unsigned em = __ballot_sync(0xffffffffu, mine && (P.engage || P.exit_area));
+        unsigned gm = __ballot_sync(0xffffffffu, mine && P.engage);
+        // without escorts every move of the round commits; with escorts only up to the first engagement (see above)
+        const int fe = (MUAV_F_ESCORT(C().escort_enabled) && gm) ? base + (__ffs((int)gm) - 1) : hi - 1;
+        if (mine && i <= fe && P.live) threat_commit(P);
+        __syncwarp();
+        em &= fe - base >= 31 ? 0xffffffffu : ((2u << (fe - base)) - 1u);
+        if (em) {
+          if (lane == 0) {
+            while (em) {
+              const int b = __ffs((int)em) - 1;
+              em &= em - 1;
+              threat_effects(V.h_order()[base + b], (gm >> b) & 1u);
+            }
+          }
+          __syncwarp();
+        }
+        lo = fe + 1;
+      }
+    }
+#else
+    // the same rounds with the lanes emulated one after the other (all plans of a round before its commits)
+    (void)lane; (void)nlanes;
+    if (!alive_env) return;
+    const int n = HIv(N_ACTIVE);
+    int lo = 0;
+    while (lo < n) {
+      ThreatPlan P[MUAV_MAX_THREATS_HOST];
+      for (int i = lo; i < n; ++i) P[i] = threat_plan(i);
+      int fe = n - 1;
+      if (MUAV_F_ESCORT(C().escort_enabled))
+        for (int i = n - 1; i >= lo; --i)
+          if (P[i].engage) fe = i;
+      for (int i = lo; i <= fe; ++i)
+        if (P[i].live) threat_commit(P[i]);
+      for (int i = lo; i <= fe; ++i)
+        if (P[i].engage || P[i].exit_area) threat_effects(P[i].hid, P[i].engage);
+      lo = fe + 1;
+    }
+#endif
   }
   // one iteration of update_threats (i indexes env.threats, spawn order)
   MUAV_HD MUAV_NI_H void update_threat(int i) {
@@ -817,7 +971,7 @@ struct Sim {
   // random_position (DroneEnv.py:1371-1410) for mission-area draws of the target stream
   MUAV_HD bool random_position_area(int stream, int area, double* ox, double* oy) {
     const double* m = &V.hf()[HF_M0_X + 4 * area];
-    int nobs = MUAV_F_NOBS(V.L->D.NOBS);
+    int nobs = MUAV_F_NOBS(V.lay().D.NOBS);
     for (int tries = 0; tries < 100; ++tries) {
       double x = rng_uniform(stream, m[0], m[0] + m[2]);
       double y = rng_uniform(stream, m[1], m[1] + m[3]);
@@ -853,7 +1007,7 @@ struct Sim {
     int tid = new_task(x, y, ti);
     if (tid == 0) return;
     int k = tid - 1;
-    int TC = V.L->D.TC;
+    int TC = V.lay().D.TC;
     V.k_cur2(ti, k) = 1.0;
     V.k_org_ti()[k] = 1.0;
     V.k_created()[k] = (int16_t)HIv(T);
@@ -1009,7 +1163,7 @@ struct Sim {
     int n_open = V.hi()[HI_N_OPEN];
     if (idx < 0) idx += n_open;  // Python negative indexing
     if (idx < 0 || idx >= n_open) return 0;
-    int KW = V.L->D.KW;
+    int KW = V.lay().D.KW;
     for (int w = 0; w < KW; ++w) {
       uint32_t m = V.open_mask()[w];
       int c = 0;
@@ -1046,14 +1200,8 @@ struct Sim {
     step_reward = 0.0;
     MUAV_TICK_START();
     int Aa = A();
-    int TC = V.L->D.TC;
+    int TC = V.lay().D.TC;
     HIv(T) += 1;
-    double* prev_x = (double*)scratch;
-    double* prev_y = prev_x + Aa;
-    for (int a = 0; a < Aa; ++a) {
-      prev_x[a] = V.a_posx()[a];
-      prev_y[a] = V.a_posy()[a];
-    }
     // drain events (DroneEnv.py:800-805)
     int nev = HIv(N_EVENTS);
     int tagmask = 0;
@@ -1067,14 +1215,14 @@ struct Sim {
       tagmask |= 1 << tag;
     }
     HIv(EV_TAGMASK) = tagmask;
-    for (int i = 0; i < nev; ++i) {
+_Pragma("unroll 1") for (int i = 0; i < nev; ++i) {
       int ev = V.events()[i];
       if ((ev & 0xff) == EV_RESET) release_all((ev >> 8) - 1);
     }
 
     MUAV_TICK(1);
     // ---- actions (DroneEnv.py:810-933)
-    for (int i = 0; i < n_act; ++i) {
+    _Pragma("unroll 1") for (int i = 0; i < n_act; ++i) {
       int a = act_agent[i];
       if (a < 0 || a >= Aa) continue;
       if (V.a_state()[a] == -1) continue;
@@ -1141,20 +1289,182 @@ struct Sim {
     MUAV_TICK(2);
   }
 
-  // step part 1b: kinematics FSM (DroneEnv.py:965-1129)
-  MUAV_HD void step_pre_b() {
-    MUAV_TICK_START();
+  // ------------------------------------------------------------------ agent-per-lane kinematics
+  // The loop at DroneEnv.py:965-1129 visits the agents in index order, but almost every visit touches only the agent's
+  // own state: fly towards the task / the base, arrive, wait out the task duration, drop a closed task.  fsm_plan(a)
+  // evaluates one visit WITHOUT writing anything and classifies it:
+  //   simple  -- every write goes to agent a's own fields (state, position, task_start, re_eval / last_task, own queue):
+  //              fsm_commit(a, plan) applies it; simple visits of different agents commute, so they run one per lane;
+  //   complex -- the visit has cross-agent side effects (agent failure -> events, an Int engagement writing the threat's
+  //              target, a task completion -> task / counters / reward / escort retirement): it runs through the
+  //              sequential fsm_agent(a), after every earlier agent has committed and before any later agent is planned.
+  // The arithmetic of a simple visit is fsm_agent's, operation for operation (one norm2 of the measured vector, its two
+  // divisions, the second normalisation of move + avoid, DroneEnv.py:1014-1048,1116-1127); only the control flow is
+  // arranged so that all lanes call the out-of-line float64 helpers together.
+  struct FsmPlan {
+    double px, py;        // position after the visit
+    int state;            // agent state after the visit
+    int task_start;       // a_task_start after the visit
+    bool alive, complex, drop_closed;
+    int cur;
+  };
+
+  MUAV_HD FsmPlan fsm_plan(int a, bool lane_on = true) const {
+    FsmPlan P;
+    P.alive = P.complex = P.drop_closed = false;
+    P.cur = 0;
+    const int t = V.hi()[HI_T];
+    const double bx = C().base_x, by = C().base_y;
+    const int nobs = MUAV_F_NOBS(V.lay().D.NOBS);
+    int st = lane_on ? (int)V.a_state()[a] : -1;
+    const bool alive = st != -1;
+    if (!alive) a = 0;  // idle lanes run the arithmetic below on agent 0's data and discard it: the calls stay converged
+    P.alive = alive;
+    P.state = st;
+    P.task_start = V.a_task_start()[a];
+    double px = V.a_posx()[a], py = V.a_posy()[a];
+    P.px = px;
+    P.py = py;
+    const double speed = speed_of(a);
+    const bool re_eval = V.a_re_eval()[a] != 0;
+    const int ql = qlen(a);
+    const int cur = re_eval ? (int)V.a_last_task()[a] : (ql > 0 ? (int)V.a_queue()[a] : 0);
+    P.cur = cur;
+    const bool failing = alive && V.a_fail_event()[a] == t;
+    const bool closed = cur > 0 && V.k_status()[cur - 1] == 2;
+    const bool on_task = alive && cur > 0 && !closed;
+    const int k = on_task ? cur - 1 : -1;
+    const int ti = on_task ? (int)V.k_type()[k] : -1;
+    double tx = 0.0, ty = 0.0;
+    if (on_task) { tx = V.k_posx()[k]; ty = V.k_posy()[k]; }
+    // the one vector whose length this visit measures: towards the base (idle far-check, returning) or towards the task
+    const bool base_vec = alive && ((st == 0 && !re_eval && ql == 0) || st == 3);
+    const bool task_vec = on_task && (st == 1 || (st == 2 && ti == TT_INT));
+    double vx = 0.0, vy = 0.0;
+    if (base_vec) { vx = bx - px; vy = by - py; }      // norm2(P - B) == norm2(B - P) bit for bit (exact negation, squares)
+    else if (task_vec) { vx = tx - px; vy = ty - py; }
+    const double d = norm2(vx, vy);
+    const bool div_ok = (task_vec && st == 1) ? !(fabs(d) < 1e-12) : (base_vec ? d != 0 : false);
+    const double den = div_ok ? d : 1.0;
+    const double qx = ddiv(vx, den), qy = ddiv(vy, den);
+    const double nx = div_ok ? qx : 0.0, ny = div_ok ? qy : 0.0;
+
+    double mvx = 0.0, mvy = 0.0;
+    bool moving = false;
+    if (failing) P.complex = true;
+    if (alive && !failing) {
+      if (st == 0 && !re_eval && ql == 0 && d > speed + 5) st = 3;
+      if (closed) {
+        P.drop_closed = true;
+      } else if (on_task) {
+        if (st == 1) {
+          if (ti == TT_INT) {
+            if (d < engage_of(a)) P.complex = true;          // engagement start writes the threat's target
+            else { mvx = nx; mvy = ny; moving = true; }
+          } else if (d < speed) {
+            st = 2;
+            P.task_start = t;
+            px = tx;
+            py = ty;
+          } else { mvx = nx; mvy = ny; moving = true; }
+        } else if (st == 2) {
+          if (ti == TT_INT && d >= engage_of(a)) st = 1;
+          if (P.task_start == -1) {
+            P.task_start = t;
+            px = tx;
+            py = ty;
+          } else if ((t - P.task_start) >= C().duration[ti] && (ti == TT_REC || ti == TT_ATT)) {
+            P.complex = true;                                // task completion
+          }
+        }
+      }
+      if (st == 3) {
+        if (d < speed + 5) st = 0;
+        else { mvx = nx; mvy = ny; moving = true; }
+      }
+    }
+    double avx = 0.0, avy = 0.0;
+    if (nobs > 0 && moving && !P.complex) avoid_obstacles(V.obst(), nobs, px, py, mvx, mvy, &avx, &avy);
+    const double sx = mvx + avx, sy = mvy + avy;
+    const double mag = norm2(sx, sy);
+    const bool mag_ok = mag != 0;
+    const double mden = mag_ok ? mag : 1.0;
+    const double wx = ddiv(sx, mden), wy = ddiv(sy, mden);
+    const double ux = mag_ok ? wx : 0.0, uy = mag_ok ? wy : 0.0;
+    px = px + ux * speed;
+    py = py + uy * speed;
+    px = dmin(dmax(px, 0.0), C().area_w);
+    py = dmin(dmax(py, 0.0), C().area_h);
+    P.px = px;
+    P.py = py;
+    P.state = st;
+    return P;
+  }
+
+  MUAV_HD void fsm_commit(int a, const FsmPlan& P) {
+    if (P.drop_closed) {
+      des_allocate(a, P.cur);
+      V.a_re_eval()[a] = 0;
+      V.a_last_task()[a] = -1;
+    }
+    V.a_state()[a] = P.state;
+    V.a_task_start()[a] = P.task_start;
+    V.a_posx()[a] = P.px;
+    V.a_posy()[a] = P.py;
+  }
+
+  // step part 1b: kinematics FSM (DroneEnv.py:965-1129).  Warp: rounds of {plan every remaining agent on its own lane,
+  // commit the simple ones in front of the first complex visit, run that one sequentially}; a step without complex
+  // visits (about five in six) is a single round.  Host build: the same plan / commit / fsm_agent calls in agent order,
+  // which is what the golden replays of tests/test_hostcheck_golden.py exercise.
+  MUAV_HD void step_pre_b(int lane, int nlanes, bool alive_env) {
     const int Aa = A();
-    for (int a = 0; a < Aa; ++a) fsm_agent(a);
-    MUAV_TICK(3);
+#if defined(__CUDA_ARCH__)
+    if (!alive_env) return;   // warp-uniform; a warp without an environment has no staged record to read
+    for (int base = 0; base < Aa; base += 32) {
+      const int a = base + lane;
+      int lo = base;
+      const int hi = base + 32 < Aa ? base + 32 : Aa;
+      while (lo < hi) {   // warp-uniform
+        const bool mine = alive_env && a >= lo && a < hi;
+        const FsmPlan P = fsm_plan(mine ? a : 0, mine);
+        const unsigned cm = __ballot_sync(0xffffffffu, mine && P.complex);
+        const int fc = cm ? base + (__ffs((int)cm) - 1) : hi;
+        if (mine && a < fc && P.alive) fsm_commit(a, P);
+        __syncwarp();
+        if (fc < hi) {
+          if (lane == 0) fsm_agent(fc);
+          __syncwarp();
+        }
+        lo = fc + 1;
+      }
+    }
+#else
+    // the same rounds with the lanes emulated one after the other: every plan of a round is made BEFORE any commit of
+    // that round, exactly what the warp does
+    (void)lane; (void)nlanes;
+    if (!alive_env) return;
+    int lo = 0;
+    while (lo < Aa) {
+      FsmPlan P[MUAV_MAX_AGENTS];
+      int fc = Aa;
+      for (int a = lo; a < Aa; ++a) P[a] = fsm_plan(a);
+      for (int a = Aa - 1; a >= lo; --a)
+        if (P[a].complex) fc = a;
+      for (int a = lo; a < fc; ++a)
+        if (P[a].alive) fsm_commit(a, P[a]);
+      if (fc < Aa) fsm_agent(fc);
+      lo = fc + 1;
+    }
+#endif
   }
 
   // kinematics FSM of one agent (one iteration of the loop at DroneEnv.py:965-1129)
   MUAV_HD void fsm_agent(int a) {
-    const int TC = V.L->D.TC;
+    const int TC = V.lay().D.TC;
     const int t = HIv(T);
     const double bx = C().base_x, by = C().base_y;
-    const int nobs = MUAV_F_NOBS(V.L->D.NOBS);
+    const int nobs = MUAV_F_NOBS(V.lay().D.NOBS);
     {
       if (V.a_state()[a] == -1) return;
       if (V.a_fail_event()[a] == t) {
@@ -1268,20 +1578,35 @@ struct Sim {
 
   }
 
-  // step part 1c: travelled distance, threats, arrivals, escorts
+  // positions before the agents move (DroneEnv.py:796-797) / per-agent travelled distance (DroneEnv.py:1131-1137):
+  // independent per agent, one agent per lane
+  MUAV_HD void snapshot_positions(int lane, int nlanes) {
+    const int Aa = A();
+    double* prev_x = (double*)scratch;
+    double* prev_y = prev_x + Aa;
+    for (int a = lane; a < Aa; a += nlanes) {
+      prev_x[a] = V.a_posx()[a];
+      prev_y[a] = V.a_posy()[a];
+    }
+  }
+  MUAV_HD void travelled_distances(int lane, int nlanes) {
+    const int Aa = A();
+    double* prev_x = (double*)scratch;
+    double* prev_y = prev_x + Aa;
+    double* dists = prev_y + Aa;
+    for (int a = lane; a < Aa; a += nlanes) {
+      dists[a] = norm2_rows(V.a_posx()[a] - prev_x[a], V.a_posy()[a] - prev_y[a]);
+      V.a_dist()[a] += dists[a];
+    }
+  }
+
+  // step part 1c: total distance, time penalty, threat generation
   MUAV_HD void step_pre_c() {
     MUAV_TICK_START();
     const int Aa = A();
     const int t = HIv(T);
-    double* prev_x = (double*)scratch;
-    double* prev_y = prev_x + Aa;
-    double* dists = prev_y + Aa;
-    // ---- travelled distance (DroneEnv.py:1131-1138)
-    for (int a = 0; a < Aa; ++a) {
-      dists[a] = norm2_rows(V.a_posx()[a] - prev_x[a], V.a_posy()[a] - prev_y[a]);
-      V.a_dist()[a] += dists[a];
-    }
-    HFv(TOTAL_DIST) += np_sum(dists, Aa);
+    double* dists = (double*)scratch + 2 * Aa;
+    HFv(TOTAL_DIST) += np_sum(dists, Aa);   // np.sum's pairwise order (DroneEnv.py:1138)
 
     // time_penaulty / alloc_reward are evaluated here in the reference (DroneEnv.py:1140-1145)
     {
@@ -1348,7 +1673,7 @@ struct Sim {
   // last_tasks_info mask + _counts_for_mission_done over all tasks; results are warp-uniform
   __device__ void scan_open_warp(int lane, int* n_open_out, bool* all_done_out) {
     const int n = HIv(N_TASKS);
-    const int KW = V.L->D.KW;
+    const int KW = V.lay().D.KW;
     int n_open = 0;
     bool blocking = false;
     for (int w = 0; w < KW; ++w) {
@@ -1372,7 +1697,7 @@ struct Sim {
     V.k_fq()[k] = 0;
     mark_outcome(k, false);
     mark_reached(k);
-    for (int a = 0; a < A(); ++a)
+    _Pragma("unroll 1") for (int a = 0; a < A(); ++a)
       if (qlen(a) > 0 && qat(a, 0) == k + 1) des_allocate_all(a);
   }
 
@@ -1416,45 +1741,31 @@ struct Sim {
     return r;
   }
 
-  // whole step.  Sequential phases run on lane 0, the task/agent scans are spread over the warp.
-  // `alive` = this warp has an environment to step; `cta_sync` = align the CTA's warps between phases.
+  // whole step.  The ordered phases (events, actions, threat generation, arrivals, escorts, the rare cross-agent visits of
+  // the FSM / threat loops) run on lane 0; the per-agent, per-threat and per-task phases are spread over the warp.
+  // `alive` = this warp has an environment to step; `sync_mask` = align the CTA's warps between phases.
   MUAV_HD StepResult step(const int16_t* act_agent, const int16_t* act_tid, int n_act, int lane, int nlanes,
                           bool alive = true, int sync_mask = 0) {
+    if (alive) snapshot_positions(lane, nlanes);
     if (alive && lane == 0) step_pre_a(act_agent, act_tid, n_act);
     MUAV_WARP_SYNC();
     MUAV_CTA_SYNC(sync_mask & 2);
-#if defined(MUAV_TUNING_VARIANTS)   // a second inlined copy of the FSM: development builds only (the kernel is bound by
-                                    // instruction supply, dead copies cost time)
-    if (sync_mask & 32) {
-      // one alignment point per agent: the FSM body is the longest straight-line stretch of the step
-      const int Aa = A();
-      for (int a = 0; a < Aa; ++a) {
-        if (alive && lane == 0) fsm_agent(a);
-        MUAV_WARP_SYNC();
-        MUAV_CTA_SYNC(1);
-      }
-    } else
-#endif
     {
-      if (alive && lane == 0) step_pre_b();
+      MUAV_TICK_START();
+      step_pre_b(lane, nlanes, alive);
       MUAV_WARP_SYNC();
+      if (alive) travelled_distances(lane, nlanes);
+      MUAV_WARP_SYNC();
+      MUAV_TICK(3);
       MUAV_CTA_SYNC(sync_mask & 4);
     }
     if (alive && lane == 0) step_pre_c();
     MUAV_WARP_SYNC();
-#if defined(MUAV_TUNING_VARIANTS)
-    if (sync_mask & 64) {
-      const int HCc = V.L->D.HC;
-      for (int i = 0; i < HCc; ++i) {
-        if (alive && lane == 0 && i < HIv(N_ACTIVE)) update_threat(i);
-        MUAV_WARP_SYNC();
-        MUAV_CTA_SYNC(1);
-      }
-    } else
-#endif
     {
-      if (alive && lane == 0) update_threats();
+      MUAV_TICK_START();
+      update_threats_lanes(lane, nlanes, alive);
       MUAV_WARP_SYNC();
+      MUAV_TICK(5);
     }
     if (alive && lane == 0) step_pre_d();
     MUAV_WARP_SYNC();
@@ -1480,7 +1791,7 @@ struct Sim {
       expire_windows();
       {
         const int n = HIv(N_TASKS);
-        const int KW = V.L->D.KW;
+        const int KW = V.lay().D.KW;
         for (int w = 0; w < KW; ++w) V.open_mask()[w] = 0;
         for (int k = 0; k < n; ++k)
           if (V.k_status()[k] != 2) {
@@ -1494,7 +1805,7 @@ struct Sim {
       MUAV_WARP_SYNC();
       // recycle slots lazily: only when the next step could run out of them (new tasks per step <= threats in a
       // burst + one arrival + one escort per agent).  Dead tasks are dead data whether recycled or not.
-      if (HIv(N_SLOTS_USED) + A() + V.L->D.HC + 2 > V.L->D.TC) {
+      if (HIv(N_SLOTS_USED) + A() + V.lay().D.HC + 2 > V.lay().D.TC) {
         free_dead_tasks(lane, nlanes);
         MUAV_WARP_SYNC();
       }

@@ -74,6 +74,7 @@ struct StepParams {
 };
 
 #define MUAV_MAX_CTA_WARPS 16
+#define MUAV_MAX_DEVICES 64
 
 // One warp per environment; a CTA holds `cta_warps` environments whose warps are phase-aligned with
 // CTA barriers (no data is shared between them).
@@ -99,7 +100,11 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
     ((int32_t*)P.out.d_env_order)[P.n_envs + 1] = 0;
   }
   const int sync_mask = W > 1 ? P.sync_mask : 0;
+#if defined(MUAV_FIXED_SHAPE)
+  constexpr Layout L = make_layout_dims(fixed_dims());   // launch_step checked that the configuration has this shape
+#else
   const Layout& L = P.L;
+#endif
   const int slot_bytes = L.record_bytes + P.scratch_launch;
   char* rec = (char*)smem + (size_t)w * slot_bytes;
   char* scratch = rec + L.record_bytes;
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
 
   Sim S;
   S.V.base = rec;
-  S.V.L = &L;
+  S.V.set_layout(&L);
   S.Cp = &P.cfg;
   S.tape = P.tapes + (size_t)(has_env ? e : 0) * P.tape_stride;
   S.scratch = scratch;
@@ -335,11 +340,16 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
 
 // launcher of this translation unit's instantiation of the step kernel (see muav_step_lean.cu)
 extern "C" int MUAV_STEP_LAUNCHER(const void* params, int grid, int threads, size_t smem, void* stream) {
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  // the opt-in shared-memory size is a per-device attribute of the function: remembered per device, set again when a larger
+  // launch comes (a benign race between threads: both write a sufficient value)
+  static size_t smem_set[MUAV_MAX_DEVICES];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t* seen = &smem_set[(dev >= 0 && dev < MUAV_MAX_DEVICES) ? dev : 0];
+  if (smem > 48 * 1024 && (smem > *seen || dev >= MUAV_MAX_DEVICES)) {
     cudaError_t e = cudaFuncSetAttribute(muav::muav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -1000 - (int)e;
-    smem_set = smem;
+    *seen = smem;
   }
   muav::muav_step_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(*(const muav::StepParams*)params);
   cudaError_t e = cudaGetLastError();
@@ -349,6 +359,13 @@ extern "C" int MUAV_STEP_STATIC_SMEM(void) {
   cudaFuncAttributes fa;
   return cudaFuncGetAttributes(&fa, muav::muav_step_kernel) == cudaSuccess ? (int)fa.sharedSizeBytes : 4608;
 }
+#if defined(MUAV_FIXED_SHAPE)
+// the one record shape this instantiation was compiled for: A, TC, IC, HC, QC, EVC, NOBS
+extern "C" void MUAV_STEP_SHAPE(int* out) {
+  const int v[7] = {MUAV_FIXED_SHAPE};
+  for (int i = 0; i < 7; ++i) out[i] = v[i];
+}
+#endif
 #else
 // ------------------------------------------------------------------ standalone batched LSAP
 __global__ void __launch_bounds__(32) muav_lsap_kernel(const double* cost, const int32_t* nr_arr, const int32_t* nc_arr,
@@ -385,7 +402,7 @@ __global__ void muav_metrics_kernel(const __grid_constant__ muav_config cfg, con
   if (e >= n) return;
   View V;
   V.base = (char*)records + (size_t)e * L.record_bytes;
-  V.L = &L;
+  V.set_layout(&L);
   metrics_env(V, cfg, out + (size_t)e * MUAV_N_METRICS);
 }
 
@@ -400,7 +417,7 @@ __global__ void __launch_bounds__(128) muav_tokens_pair_kernel(const __grid_cons
   if (e >= n) return;
   View V;
   V.base = (char*)records + (size_t)e * L.record_bytes;
-  V.L = &L;
+  V.set_layout(&L);
   const int TD = raw ? 9 : 13, AD = raw ? 11 : af_dim, CD = raw ? 1 : 8;
   tokens_pair_env(V, cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * TD, tm + (size_t)e * max_tasks,
                   af + (size_t)e * max_agents * AD, am + (size_t)e * max_agents,
@@ -419,7 +436,7 @@ __global__ void __launch_bounds__(128) muav_tokens_escort_kernel(const __grid_co
   if (e >= n) return;
   View V;
   V.base = (char*)records + (size_t)e * L.record_bytes;
-  V.L = &L;
+  V.set_layout(&L);
   EscortTokScratch W = carve_escort_tok(esc_smem + (size_t)w * per_warp, L.D.TC, max_tasks);
   tokens_escort_env(V, cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * 22, tm + (size_t)e * max_tasks,
                     af + (size_t)e * max_agents * 16, am + (size_t)e * max_agents, ev + (size_t)e * max_agents * max_tasks,
@@ -436,7 +453,7 @@ __global__ void muav_pair_mask_kernel(const __grid_constant__ Layout L, const ch
   if (e >= n) return;
   View V;
   V.base = (char*)records + (size_t)e * L.record_bytes;
-  V.L = &L;
+  V.set_layout(&L);
   const int A = L.D.A;
   float* m = mask + (size_t)e * max_agents * max_tasks;
   for (int i = 0; i < max_agents * max_tasks; ++i) m[i] = 0.0f;
@@ -465,7 +482,7 @@ __global__ void muav_observe_kernel(const __grid_constant__ muav_config cfg, con
   if (e >= n) return;
   View V;
   V.base = (char*)records + (size_t)e * L.record_bytes;
-  V.L = &L;
+  V.set_layout(&L);
   int32_t nr = 0;
   observe_env(V, cfg, max_rows, ti + (size_t)e * max_rows * MUAV_OBS_TASK_DIM, pad + (size_t)e * max_rows,
               legal + (size_t)e * L.D.A * max_rows, ao + (size_t)e * L.D.A * MUAV_OBS_AGENT_DIM, ef + (size_t)e * 5, &nr);
@@ -483,14 +500,56 @@ extern "C" {
 
 #include "muav_abi_common.inl"
 
-// lean instantiation of the step kernel (muav_step_lean.cu): no escorts, no obstacles, plain Hungarian allocator
-int muav_step_lean_launch(const void* params, int grid, int threads, size_t smem, void* stream);
-int muav_step_lean_static_smem(void);
-int muav_step_lean_escort_launch(const void* params, int grid, int threads, size_t smem, void* stream);
-int muav_step_lean_escort_static_smem(void);
+// Instantiations of the step kernel in their own translation units (same source, namespaces of their own):
+//   lean / lean_escort (muav_step_lean*.cu): no obstacles, plain Hungarian allocator, escorts off / always on;
+//   fixed-shape ones (muav_step_hard.cu, ...): the lean feature set AND the record dimensions as compile-time constants.
+#define MUAV_DECL_INST(n)                                                                        \
+  int muav_step_##n##_launch(const void* params, int grid, int threads, size_t smem, void* stream); \
+  int muav_step_##n##_static_smem(void);
+#define MUAV_DECL_SHAPED(n) MUAV_DECL_INST(n) void muav_step_##n##_shape(int* out);
+MUAV_DECL_INST(lean)
+MUAV_DECL_INST(lean_escort)
+MUAV_DECL_SHAPED(hard)
+MUAV_DECL_SHAPED(hard32)
+
+struct StepInst {
+  int (*launch)(const void*, int, int, size_t, void*);
+  int (*static_smem)(void);
+  void (*shape)(int*);  // null: any shape
+  int escort;           // value of cfg.escort_enabled this instantiation was compiled for
+};
+static const StepInst kStepInst[] = {
+    {muav_step_hard_launch, muav_step_hard_static_smem, muav_step_hard_shape, 0},
+    {muav_step_hard32_launch, muav_step_hard32_static_smem, muav_step_hard32_shape, 0},
+    {muav_step_lean_launch, muav_step_lean_static_smem, nullptr, 0},
+    {muav_step_lean_escort_launch, muav_step_lean_escort_static_smem, nullptr, 1},
+};
+
+// the most specialised instantiation that covers this launch (null: the general kernel of this translation unit)
+static const StepInst* pick_inst(const StepParams& P) {
+  const bool lean = P.L.D.NOBS == 0 && P.opts.planner == 0 && !P.alloc_only && !getenv("MUAV_NO_LEAN");
+  if (!lean) return nullptr;
+  const bool no_fixed = getenv("MUAV_NO_FIXED_SHAPE") != nullptr;
+  const Dims& D = P.L.D;
+  const int have[7] = {D.A, D.TC, D.IC, D.HC, D.QC, D.EVC, D.NOBS};
+  for (const StepInst& I : kStepInst) {
+    if (I.escort != (P.cfg.escort_enabled ? 1 : 0)) continue;
+    if (I.shape) {
+      if (no_fixed) continue;
+      int want[7];
+      I.shape(want);
+      if (want[2] < want[1]) want[2] = want[1];
+      bool same = true;
+      for (int i = 0; i < 7; ++i) same = same && want[i] == have[i];
+      if (!same) continue;
+    }
+    return &I;
+  }
+  return nullptr;
+}
 
 static int launch_step(StepParams& P, void* stream) {
-  const bool lean = P.L.D.NOBS == 0 && P.opts.planner == 0 && !P.alloc_only && !getenv("MUAV_NO_LEAN");
+  const StepInst* inst = pick_inst(P);
   // launches without the allocator need only the step's temporaries: more environments per SM
   P.scratch_launch = (P.alloc_only || P.opts.mode != 0) ? P.L.scratch_bytes : P.L.step_scratch_bytes;
   const size_t slot = (size_t)P.L.record_bytes + (size_t)P.scratch_launch;
@@ -502,14 +561,16 @@ static int launch_step(StepParams& P, void* stream) {
   // 5 x 1) and one-warp CTAs below (burst x4 1 x 3).  MUAV_CTA_WARPS overrides.
   int W = 1;
   {
-    static size_t static_smem = 0;
-    if (!static_smem) {
+    // per-CTA static shared memory of the chosen instantiation (a property of the compiled kernel, the same on every
+    // device; cached after the first query -- concurrent first calls write the same value)
+    static int static_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int ci = inst ? 1 + (int)(inst - kStepInst) : 0;
+    if (!static_cache[ci]) {
       cudaFuncAttributes fa;
-      static_smem = cudaFuncGetAttributes(&fa, muav_step_kernel) == cudaSuccess ? fa.sharedSizeBytes : 4608;
-      const size_t sl = (size_t)muav_step_lean_static_smem(), se = (size_t)muav_step_lean_escort_static_smem();
-      if (sl > static_smem) static_smem = sl;
-      if (se > static_smem) static_smem = se;
+      static_cache[ci] = inst ? inst->static_smem()
+                              : (cudaFuncGetAttributes(&fa, muav_step_kernel) == cudaSuccess ? (int)fa.sharedSizeBytes : 4608);
     }
+    const size_t static_smem = (size_t)static_cache[ci];
     const size_t budget = 228 * 1024, per_cta = static_smem + 1024;  // B200: 228 KB per SM, 1 KB reserved per CTA
     int envs[7] = {0, 0, 0, 0, 0, 0, 0}, ctas[7] = {0, 0, 0, 0, 0, 0, 0}, best = 0;
     for (int w = 1; w <= 6; ++w) {
@@ -542,14 +603,15 @@ static int launch_step(StepParams& P, void* stream) {
   const char* sm = getenv("MUAV_SYNC_MASK");
   if (sm) P.sync_mask = atoi(sm);
   const size_t smem = slot * W;
-  if (lean)
-    return (P.cfg.escort_enabled ? muav_step_lean_escort_launch : muav_step_lean_launch)(&P, (P.n_envs + W - 1) / W, 32 * W,
-                                                                                         smem, stream);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  if (inst) return inst->launch(&P, (P.n_envs + W - 1) / W, 32 * W, smem, stream);
+  static size_t smem_set[MUAV_MAX_DEVICES];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t* seen = &smem_set[(dev >= 0 && dev < MUAV_MAX_DEVICES) ? dev : 0];
+  if (smem > 48 * 1024 && (smem > *seen || dev >= MUAV_MAX_DEVICES)) {
     cudaError_t e = cudaFuncSetAttribute(muav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_rc(e);
-    smem_set = smem;
+    *seen = smem;
   }
   const int grid = (P.n_envs + W - 1) / W;
   muav_step_kernel<<<grid, 32 * W, smem, (cudaStream_t)stream>>>(P);
@@ -682,27 +744,63 @@ int muav_snapshot(const muav_config* cfg, const void* d_records, int env_index, 
   return cuda_rc(cudaStreamSynchronize(s));
 }
 
-int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* h_actions,
-                   const muav_alloc_opts* opts, const muav_token_out* tok, double* h_reward, uint8_t* h_terminated,
-                   uint8_t* h_truncated, int n_envs, int n_steps, void* stream, const int32_t* d_env_order,
-                   int32_t* d_env_order_next) {
+// ---- host-buffer entry points.  All staging memory belongs to a caller-owned handle (muav_ctx): the library keeps no
+// mutable process-wide state, so two handles (two threads, two devices) never share anything.
+struct muav_ctx {
+  muav_config cfg;
+  int n_envs, device;
+  char* d_buf;       // [actions in | reward | terminated | truncated]
+  char* h_pin;       // pinned image of the three outputs: one device -> host copy per step
+  size_t off_rew, off_term, off_trunc, bytes;
+};
+
+static size_t ctx_layout(const muav_config* cfg, int n_envs, size_t* off_rew, size_t* off_term, size_t* off_trunc) {
+  const size_t act_bytes = (size_t)n_envs * cfg->n_agents * 2 * sizeof(int32_t);
+  *off_rew = (act_bytes + 15) / 16 * 16;
+  *off_term = *off_rew + (size_t)n_envs * 8;
+  *off_trunc = *off_term + (size_t)n_envs;
+  return (*off_trunc + (size_t)n_envs + 15) / 16 * 16;
+}
+
+int muav_ctx_create(const muav_config* cfg, int n_envs, int device, muav_ctx** out) {
   int rc = check_cfg(cfg);
   if (rc) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
-  static void* d_buf = nullptr;
-  static size_t d_cap = 0;
-  size_t act_bytes = h_actions ? (size_t)n_envs * cfg->n_agents * 2 * sizeof(int32_t) : 0;
-  size_t off_rew = (act_bytes + 15) / 16 * 16;
-  size_t off_term = off_rew + (size_t)n_envs * 8;
-  size_t off_trunc = off_term + (size_t)n_envs;
-  size_t need = off_trunc + (size_t)n_envs;
-  if (need > d_cap) {
-    if (d_buf) cudaFree(d_buf);
-    cudaError_t e = cudaMalloc(&d_buf, need);
-    if (e != cudaSuccess) { d_buf = nullptr; d_cap = 0; return cuda_rc(e); }
-    d_cap = need;
+  if (!out || n_envs < 1 || device < 0) return -22;
+  *out = nullptr;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cuda_rc(e);
+  muav_ctx* c = (muav_ctx*)calloc(1, sizeof(muav_ctx));
+  if (!c) { cudaSetDevice(prev); return -12; }
+  c->cfg = *cfg;
+  c->n_envs = n_envs;
+  c->device = device;
+  c->bytes = ctx_layout(cfg, n_envs, &c->off_rew, &c->off_term, &c->off_trunc);
+  e = cudaMalloc((void**)&c->d_buf, c->bytes);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_pin, c->bytes - c->off_rew);
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) {
+    muav_ctx_destroy(c);
+    return cuda_rc(e);
   }
-  char* b = (char*)d_buf;
+  *out = c;
+  return 0;
+}
+
+void muav_ctx_destroy(muav_ctx* c) {
+  if (!c) return;
+  if (c->d_buf) cudaFree(c->d_buf);
+  if (c->h_pin) cudaFreeHost(c->h_pin);
+  free(c);
+}
+
+// shared body: `b` = device staging block laid out by ctx_layout, `h_pin` = optional pinned image of the outputs
+static int step_host_impl(const muav_config* cfg, char* b, char* h_pin, size_t off_rew, size_t off_term, size_t off_trunc,
+                          void* d_records, const uint32_t* d_tapes, const int32_t* h_actions, const muav_alloc_opts* opts,
+                          const muav_token_out* tok, double* h_reward, uint8_t* h_terminated, uint8_t* h_truncated,
+                          int n_envs, int n_steps, cudaStream_t s, const int32_t* d_env_order, int32_t* d_env_order_next) {
+  const size_t act_bytes = (size_t)n_envs * cfg->n_agents * 2 * sizeof(int32_t);
   if (h_actions) {
     cudaError_t e = cudaMemcpyAsync(b, h_actions, act_bytes, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return cuda_rc(e);
@@ -714,13 +812,73 @@ int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_ta
   out.d_truncated = (uint8_t*)(b + off_trunc);
   out.d_env_order = d_env_order;
   out.d_env_order_next = d_env_order_next;
-  rc = muav_step(cfg, d_records, d_tapes, h_actions ? (const int32_t*)b : nullptr, opts, &out, tok, n_envs, n_steps,
-                 stream);
+  int rc = muav_step(cfg, d_records, d_tapes, h_actions ? (const int32_t*)b : nullptr, opts, &out, tok, n_envs, n_steps,
+                     (void*)s);
   if (rc) return rc;
-  if (h_reward) cudaMemcpyAsync(h_reward, out.d_reward, (size_t)n_envs * 8, cudaMemcpyDeviceToHost, s);
-  if (h_terminated) cudaMemcpyAsync(h_terminated, out.d_terminated, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
-  if (h_truncated) cudaMemcpyAsync(h_truncated, out.d_truncated, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaSuccess;
+  if (h_pin) {
+    if (h_reward || h_terminated || h_truncated) {
+      e = cudaMemcpyAsync(h_pin, b + off_rew, off_trunc + (size_t)n_envs - off_rew, cudaMemcpyDeviceToHost, s);
+      if (e != cudaSuccess) return cuda_rc(e);
+    }
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return cuda_rc(e);
+    if (h_reward) memcpy(h_reward, h_pin, (size_t)n_envs * 8);
+    if (h_terminated) memcpy(h_terminated, h_pin + (off_term - off_rew), (size_t)n_envs);
+    if (h_truncated) memcpy(h_truncated, h_pin + (off_trunc - off_rew), (size_t)n_envs);
+    return 0;
+  }
+  if (h_reward) e = cudaMemcpyAsync(h_reward, out.d_reward, (size_t)n_envs * 8, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && h_terminated)
+    e = cudaMemcpyAsync(h_terminated, out.d_terminated, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && h_truncated)
+    e = cudaMemcpyAsync(h_truncated, out.d_truncated, (size_t)n_envs, cudaMemcpyDeviceToHost, s);
+  if (e != cudaSuccess) return cuda_rc(e);
   return cuda_rc(cudaStreamSynchronize(s));
+}
+
+int muav_ctx_step_host(muav_ctx* c, void* d_records, const uint32_t* d_tapes, const int32_t* h_actions,
+                       const muav_alloc_opts* opts, const muav_token_out* tok, double* h_reward, uint8_t* h_terminated,
+                       uint8_t* h_truncated, int n_steps, void* stream, const int32_t* d_env_order,
+                       int32_t* d_env_order_next) {
+  if (!c || !d_records || n_steps < 0) return -22;
+  return step_host_impl(&c->cfg, c->d_buf, c->h_pin, c->off_rew, c->off_term, c->off_trunc, d_records, d_tapes, h_actions,
+                        opts, tok, h_reward, h_terminated, h_truncated, c->n_envs, n_steps, (cudaStream_t)stream, d_env_order,
+                        d_env_order_next);
+}
+
+int muav_ctx_allocate_host(muav_ctx* c, void* d_records, const muav_alloc_opts* opts, const muav_step_out* out,
+                           int32_t* h_actions_out, void* stream) {
+  if (!c || !d_records || !opts || !h_actions_out) return -22;
+  int rc = muav_allocate(&c->cfg, d_records, opts, out, (int32_t*)c->d_buf, c->n_envs, stream);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t act_bytes = (size_t)c->n_envs * c->cfg.n_agents * 2 * sizeof(int32_t);
+  cudaError_t e = cudaMemcpyAsync(h_actions_out, c->d_buf, act_bytes, cudaMemcpyDeviceToHost, s);
+  if (e != cudaSuccess) return cuda_rc(e);
+  return cuda_rc(cudaStreamSynchronize(s));
+}
+
+// Handle-free form: the staging block is a stream-ordered allocation of this call (cudaMallocAsync), so concurrent
+// callers and several devices are safe; muav_ctx_step_host avoids the allocation.
+int muav_step_host(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, const int32_t* h_actions,
+                   const muav_alloc_opts* opts, const muav_token_out* tok, double* h_reward, uint8_t* h_terminated,
+                   uint8_t* h_truncated, int n_envs, int n_steps, void* stream, const int32_t* d_env_order,
+                   int32_t* d_env_order_next) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (!d_records || n_envs < 0 || n_steps < 0) return -22;
+  if (n_envs == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t off_rew, off_term, off_trunc;
+  const size_t need = ctx_layout(cfg, n_envs, &off_rew, &off_term, &off_trunc);
+  void* buf = nullptr;
+  cudaError_t e = cudaMallocAsync(&buf, need, s);
+  if (e != cudaSuccess) return cuda_rc(e);
+  rc = step_host_impl(cfg, (char*)buf, nullptr, off_rew, off_term, off_trunc, d_records, d_tapes, h_actions, opts, tok,
+                      h_reward, h_terminated, h_truncated, n_envs, n_steps, s, d_env_order, d_env_order_next);
+  cudaFreeAsync(buf, s);
+  return rc;
 }
 
 int muav_lsap(const double* d_cost, const int32_t* d_nr, const int32_t* d_nc, int nr_max, int nc_max, int32_t* d_col4row,

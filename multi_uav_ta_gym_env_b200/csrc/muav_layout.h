@@ -86,7 +86,7 @@ struct Dims {
 };
 
 MUAV_HD inline Dims dims_of(const muav_config& c) {
-  Dims d;
+  Dims d{};
   d.A = c.n_agents;
   d.TC = c.task_cap;
   d.IC = c.id_cap > c.task_cap ? c.id_cap : c.task_cap;
@@ -179,10 +179,10 @@ struct Layout {
   Dims D;
 };
 
-MUAV_HD inline int32_t align_up(int32_t x, int32_t a) { return (x + a - 1) / a * a; }
+MUAV_HD constexpr inline int32_t align_up(int32_t x, int32_t a) { return (x + a - 1) / a * a; }
 
 // bytes of allocator scratch: cost[A*TC], u/v/spc[M], resid[TC] doubles + 6 M-sized and 2A+3TC int16 arrays
-MUAV_HD inline int32_t alloc_scratch_bytes(int A, int TC) {
+MUAV_HD constexpr inline int32_t alloc_scratch_bytes(int A, int TC) {
   int M = A > TC ? A : TC;
   int b = 8 * (A * TC + 3 * M + TC + 4);
   b += 2 * (6 * M + 3 * A + 3 * TC);
@@ -190,9 +190,10 @@ MUAV_HD inline int32_t alloc_scratch_bytes(int A, int TC) {
   return (b + 15) / 16 * 16;
 }
 
-MUAV_HD inline Layout make_layout(const muav_config& c) {
-  Layout L;
-  Dims D = dims_of(c);
+// layout of a record with the given dimensions (a constant expression when the dimensions are: fixed-shape
+// instantiations of the step kernel, MUAV_FIXED_SHAPE)
+MUAV_HD constexpr inline Layout make_layout_dims(const Dims D) {
+  Layout L{};
   L.D = D;
   int32_t off = 0;
 #define X(name, type, count)                 \
@@ -214,6 +215,21 @@ MUAV_HD inline Layout make_layout(const muav_config& c) {
   return L;
 }
 
+MUAV_HD inline Layout make_layout(const muav_config& c) { return make_layout_dims(dims_of(c)); }
+
+#if defined(MUAV_FIXED_SHAPE)
+// MUAV_FIXED_SHAPE = A, TC, IC, HC, QC, EVC, NOBS: a step-kernel instantiation for ONE record shape.  Every field offset and
+// loop bound is then a constant expression (a third of the general kernel's dynamic instructions are offset arithmetic on
+// the run-time layout, profiles/r02_step_kernel.md); the launcher uses it only for configurations of exactly this shape.
+MUAV_HD constexpr inline Dims fixed_dims() {
+  constexpr int v[7] = {MUAV_FIXED_SHAPE};
+  Dims d{};
+  d.A = v[0]; d.TC = v[1]; d.IC = v[2] > v[1] ? v[2] : v[1]; d.HC = v[3]; d.QC = v[4]; d.EVC = v[5]; d.NOBS = v[6];
+  d.KW = (d.IC + 31) / 32;
+  return d;
+}
+#endif
+
 // array of a slot-indexed task field, addressed by task index (id - 1)
 template <class T>
 struct SlotRef {
@@ -224,20 +240,30 @@ struct SlotRef {
 
 struct View {
   char* base;
+#if defined(MUAV_FIXED_SHAPE)
+  MUAV_HD inline void set_layout(const Layout*) {}
+  MUAV_HD inline Layout lay() const {
+    constexpr Layout k = make_layout_dims(fixed_dims());
+    return k;
+  }
+#else
   const Layout* L;
+  MUAV_HD inline void set_layout(const Layout* l) { L = l; }
+  MUAV_HD inline const Layout& lay() const { return *L; }
+#endif
 #define X(name, type, count) \
-  MUAV_HD inline type* name() const { return (type*)(base + L->o_##name); }
-#define XS(name, type, count)                                                                   \
-  MUAV_HD inline SlotRef<type> name() const {                                                   \
-    return SlotRef<type>{(type*)(base + L->o_##name), (const int16_t*)(base + L->o_k_slot)};    \
-  }                                                                                             \
-  MUAV_HD inline type* name##_raw() const { return (type*)(base + L->o_##name); }
+  MUAV_HD inline type* name() const { return (type*)(base + lay().o_##name); }
+#define XS(name, type, count)                                                                       \
+  MUAV_HD inline SlotRef<type> name() const {                                                       \
+    return SlotRef<type>{(type*)(base + lay().o_##name), (const int16_t*)(base + lay().o_k_slot)};  \
+  }                                                                                                 \
+  MUAV_HD inline type* name##_raw() const { return (type*)(base + lay().o_##name); }
   MUAV_FIELDS(X, XS)
 #undef X
 #undef XS
   // requirement vectors: component c of task index k
-  MUAV_HD inline double& k_cur2(int c, int k) const { return k_cur()[c * L->D.TC + k_slot()[k]]; }
-  MUAV_HD inline double& k_alloc2(int c, int k) const { return k_alloc()[c * L->D.TC + k_slot()[k]]; }
+  MUAV_HD inline double& k_cur2(int c, int k) const { return k_cur()[c * lay().D.TC + k_slot()[k]]; }
+  MUAV_HD inline double& k_alloc2(int c, int k) const { return k_alloc()[c * lay().D.TC + k_slot()[k]]; }
 };
 
 }  // namespace muav

@@ -545,11 +545,15 @@ extern "C" int muav_att_context_pair_scores(const float* d_params, const muav_at
   P.max_agents = max_agents;
   P.clamp = score_clamp;
   const size_t smem = sizeof(float) * (size_t)(3 * D * TS + 3 * D * TS);
-  static bool set = false;
-  if (!set) {
+  // opt-in shared-memory size: an attribute of the function PER DEVICE (remembered per device; concurrent first calls
+  // write the same value)
+  static bool set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(att_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -1000 - (int)e;
-    set = true;
+    if (dev >= 0 && dev < 64) set[dev] = true;
   }
   // environments per CTA: three WPS_hard environments (~19 tokens each) fill the 64-token pass
   int group = 3;

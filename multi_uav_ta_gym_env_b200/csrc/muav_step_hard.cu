@@ -1,0 +1,11 @@
+// Fixed-shape instantiation of muav_step_kernel for the WPS_hard / WPS_easy / WPS_burst record (8 agents, 9 threats): the lean
+// feature set of muav_step_lean.cu AND the record dimensions as compile-time constants (MUAV_FIXED_SHAPE, muav_layout.h),
+// so every field offset is an immediate and the loops over agents / threats / mask words have constant bounds.
+#define MUAV_LEAN 1
+#define MUAV_FIXED_SHAPE 8, 48, 64, 9, 16, 58, 0
+#define MUAV_STEP_ONLY 1
+#define MUAV_STEP_LAUNCHER muav_step_hard_launch
+#define MUAV_STEP_STATIC_SMEM muav_step_hard_static_smem
+#define MUAV_STEP_SHAPE muav_step_hard_shape
+#define muav muav_hard
+#include "muav_kernels.cu"

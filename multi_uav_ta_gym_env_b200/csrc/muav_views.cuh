@@ -20,7 +20,7 @@ MUAV_HD inline double urgency_of(const View& V, int k, int t) {
 }
 
 MUAV_HD inline bool view_known(const View& V, int a, int k) {
-  return (V.known()[(k >> 5) * V.L->D.A + a] >> (k & 31)) & 1u;
+  return (V.known()[(k >> 5) * V.lay().D.A + a] >> (k & 31)) & 1u;
 }
 
 // task_feats [max_tasks,13] f32, task_mask [max_tasks] u8 (1 = padding), agent_feats [max_agents,12] f32,
@@ -36,7 +36,7 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
                                     int lane, int nlanes, int af_dim = 12, int raw = 0, float* ctx = nullptr) {
   const int TD = raw ? 9 : 13;
   if (raw) af_dim = 11;
-  const int A = V.L->D.A, TC = V.L->D.TC;
+  const int A = V.lay().D.A, TC = V.lay().D.TC;
   const int n = V.hi()[HI_N_TASKS];
   const int t = V.hi()[HI_T];
   const double mc = C.max_coord;
@@ -44,6 +44,28 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
   const double mid_x = C.area_w * 0.5;
   const bool vis_none = !(C.sense_radius != 0.0) && !(C.threat_delay != 0);
   const double urgent_thr = 1.0 - 12.0 / 40.0;
+#if defined(__CUDA_ARCH__)
+  // ordered token-task list: lane <-> task id, compacted with ballots (the order is the id order either way)
+  {
+    int n_open_res = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int k = base + lane;
+      bool res = k < n && V.k_status()[k] != 2;
+      if (res) {
+        const int ti = V.k_type()[k];
+        res = V.k_alloc2(ti, k) < V.k_cur2(ti, k);  // AttentionRAH.py:67-71
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, res);
+      const int pos = n_open_res + __popc(m & ((1u << lane) - 1u));
+      if (res && pos < max_tasks) cols[pos] = (int16_t)k;
+      n_open_res += __popc(m);
+    }
+    if (lane == 0) {
+      cols[max_tasks] = (int16_t)(n_open_res < max_tasks ? n_open_res : max_tasks);
+      cols[max_tasks + 1] = (int16_t)n_open_res;
+    }
+  }
+#else
   if (lane == 0) {
     int n_open_all = 0, col = 0;
     for (int k = 0; k < n; ++k) {
@@ -56,6 +78,7 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
     cols[max_tasks] = (int16_t)col;
     cols[max_tasks + 1] = (int16_t)n_open_all;
   }
+#endif
   MUAV_WARP_SYNC();
   const int ncol = cols[max_tasks];
   const int n_open_all = cols[max_tasks + 1];
@@ -146,15 +169,57 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
     ids[j] = k + 1;
   }
   // ---- agent rows (row i = i-th live agent)
-  for (int i = lane; i < max_agents; i += nlanes) {
+#if defined(__CUDA_ARCH__)
+  const bool warp_rows = max_agents <= 32;   // the warp-cooperative forms below put row i on lane i
+#else
+  const bool warp_rows = false;
+#endif
+  for (int i = lane; i < (warp_rows ? 32 : max_agents); i += nlanes) {
     float* f = af + i * af_dim;
-    float* evr = ev ? ev + i * max_tasks : nullptr;
+    float* evr = (ev && !warp_rows) ? ev + i * max_tasks : nullptr;
     int a = -1, seen = 0;
     for (int b = 0; b < A; ++b) {
       if (V.a_state()[b] == -1) continue;
       if (seen == i) { a = b; break; }
       ++seen;
     }
+    int n_known_urgent = 0;
+#if defined(__CUDA_ARCH__)
+    if (warp_rows) {
+      // known urgent tasks per agent: the per-task predicate is evaluated once (lane <-> task), every row then counts
+      // the bits its agent knows; edge_valid is filled afterwards over (row, column) pairs with coalesced stores
+      const int words = (n + 31) >> 5;
+      for (int w = 0; w < words; ++w) {
+        const int k = (w << 5) + lane;
+        bool u = k < n && V.k_status()[k] != 2 && V.k_deadline()[k] >= 0;
+        if (u) {
+          const int ti = V.k_type()[k];
+          u = V.k_alloc2(ti, k) < V.k_cur2(ti, k) && urgency_of(V, k, t) >= urgent_thr;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, u);
+        if (a >= 0) n_known_urgent += __popc(vis_none ? m : (m & V.known()[w * A + a]));
+      }
+      const int at_l = a >= 0 ? (int)V.a_type()[a] : 0;
+      const int n_edges = ev ? max_agents * max_tasks : 0;
+      for (int base = 0; base < n_edges; base += 32) {   // warp-uniform trip count: the shuffles need every lane
+        const int idx = base + lane;
+        const bool in = idx < n_edges;
+        const int r = in ? idx / max_tasks : 0, j = idx - r * max_tasks;
+        const int ar = __shfl_sync(0xffffffffu, a, r);
+        const int atr = __shfl_sync(0xffffffffu, at_l, r);
+        float v = 0.0f;
+        if (in && ar >= 0 && j < ncol) {
+          const int k = cols[j];
+          const int el = V.k_elig()[k];
+          const bool ok = (vis_none || view_known(V, ar, k)) && (el == 0 || ((el >> atr) & 1)) &&
+                          V.a_caps()[V.k_type()[k] * A + ar] > 0;
+          v = ok ? 1.0f : 0.0f;
+        }
+        if (in) ev[idx] = v;
+      }
+      if (i >= max_agents) continue;
+    }
+#endif
     if (a < 0) {
       am[i] = 1;
       for (int c = 0; c < af_dim; ++c) f[c] = 0.0f;
@@ -164,14 +229,15 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
     }
     int at = V.a_type()[a];
     double cap_rec = V.a_caps()[1 * A + a], cap_att = V.a_caps()[2 * A + a], cap_def = V.a_caps()[3 * A + a];
-    int n_known_urgent = 0;
-    for (int k = 0; k < n; ++k) {
-      if (V.k_status()[k] == 2) continue;
-      if (V.k_deadline()[k] < 0) continue;
-      int ti = V.k_type()[k];
-      if (!(V.k_alloc2(ti, k) < V.k_cur2(ti, k))) continue;
-      if (!vis_none && !view_known(V, a, k)) continue;
-      if (urgency_of(V, k, t) >= urgent_thr) ++n_known_urgent;
+    if (!warp_rows) {
+      for (int k = 0; k < n; ++k) {
+        if (V.k_status()[k] == 2) continue;
+        if (V.k_deadline()[k] < 0) continue;
+        int ti = V.k_type()[k];
+        if (!(V.k_alloc2(ti, k) < V.k_cur2(ti, k))) continue;
+        if (!vis_none && !view_known(V, a, k)) continue;
+        if (urgency_of(V, k, t) >= urgent_thr) ++n_known_urgent;
+      }
     }
     f[0] = (float)(V.a_posx()[a] / mc);
     f[1] = (float)(V.a_posy()[a] / mc);
@@ -236,7 +302,7 @@ MUAV_HD inline EscortTokScratch carve_escort_tok(char* p, int TC, int max_tasks)
 }
 
 MUAV_HD inline bool view_in_queue(const View& V, int a, int tid) {
-  const int A = V.L->D.A;
+  const int A = V.lay().D.A;
   const int ql = V.a_qlen()[a];
   for (int q = 0; q < ql; ++q)
     if (V.a_queue()[q * A + a] == tid) return true;
@@ -268,7 +334,7 @@ MUAV_HD inline void view_threat_stats(const View& V, const muav_config& C, int k
 MUAV_HD inline void tokens_escort_env(const View& V, const muav_config& C, int max_tasks, int max_agents, float* tf,
                                       uint8_t* tm, float* af, uint8_t* am, float* ev, int32_t* ids, int32_t* order,
                                       EscortTokScratch W, int lane, int nlanes) {
-  const int A = V.L->D.A, TC = V.L->D.TC, IC = V.L->D.IC;
+  const int A = V.lay().D.A, TC = V.lay().D.TC, IC = V.lay().D.IC;
   const int n = V.hi()[HI_N_TASKS];
   const int t = V.hi()[HI_T];
   const double mc = C.max_coord;
@@ -503,7 +569,7 @@ MUAV_HD inline void tokens_escort_env(const View& V, const muav_config& C, int m
 // (status = -1 marks padding); pad_mask [max_rows]; legal_mask [A, max_rows]; agent_obs [A, 9]; event_flags [5] f32.
 MUAV_HD inline void observe_env(const View& V, const muav_config& C, int max_rows, double* ti_out, uint8_t* pad,
                                 uint8_t* legal, double* ao, float* ef, int32_t* n_rows_out) {
-  const int A = V.L->D.A, TC = V.L->D.TC;
+  const int A = V.lay().D.A, TC = V.lay().D.TC;
   const int n = V.hi()[HI_N_TASKS];
   const int t = V.hi()[HI_T];
   const double mc = C.max_coord;
@@ -597,7 +663,7 @@ MUAV_HD inline void observe_env(const View& V, const muav_config& C, int max_row
 // calculate_metrics / compute_s_wps / compute_s_esc (mUAV_TA/DroneEnv.py:1231-1337,2002-2011);
 // o[0..29] in the order of muav_metric_name()
 MUAV_HD inline void metrics_env(const View& V, const muav_config& cfg, double* o) {
-  const Layout& L = *V.L;
+  const Layout& L = V.lay();
   const int A = L.D.A;
   const int T = HIv(N_TASKS);
   double td = HFv(TOTAL_DIST);

@@ -37,7 +37,7 @@ int hostcheck_step(const muav_config* cfg, void* records, const uint32_t* tapes,
   for (int e = 0; e < n_envs; ++e) {
     Sim S;
     S.V.base = (char*)records + (size_t)e * L.record_bytes;
-    S.V.L = &L;
+    S.V.set_layout(&L);
     S.Cp = cfg;
     S.tape = tapes + (size_t)e * tape_stride;
     S.scratch = scratch;
@@ -98,7 +98,7 @@ int hostcheck_allocate(const muav_config* cfg, void* records, const muav_alloc_o
   for (int e = 0; e < n_envs; ++e) {
     Sim S;
     S.V.base = (char*)records + (size_t)e * L.record_bytes;
-    S.V.L = &L;
+    S.V.set_layout(&L);
     S.Cp = cfg;
     S.tape = nullptr;
     S.scratch = scratch;
@@ -131,7 +131,7 @@ int hostcheck_tokens_pair(const muav_config* cfg, const void* records, int max_t
   for (int e = 0; e < n_envs; ++e) {
     View V;
     V.base = (char*)records + (size_t)e * L.record_bytes;
-    V.L = &L;
+    V.set_layout(&L);
     tokens_pair_env(V, *cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * 13, tm + (size_t)e * max_tasks,
                     af + (size_t)e * max_agents * 12, am + (size_t)e * max_agents, ev + (size_t)e * max_agents * max_tasks,
                     ids + (size_t)e * max_tasks, cols, 0, 1);
@@ -148,7 +148,7 @@ int hostcheck_tokens_context(const muav_config* cfg, const void* records, int ma
   for (int e = 0; e < n_envs; ++e) {
     View V;
     V.base = (char*)records + (size_t)e * L.record_bytes;
-    V.L = &L;
+    V.set_layout(&L);
     tokens_pair_env(V, *cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * TD, tm + (size_t)e * max_tasks,
                     af + (size_t)e * max_agents * AD, am + (size_t)e * max_agents, ev + (size_t)e * max_agents * max_tasks,
                     ids + (size_t)e * max_tasks, cols, 0, 1, 12, raw, ctx + (size_t)e * CD);
@@ -165,7 +165,7 @@ int hostcheck_tokens_escort(const muav_config* cfg, const void* records, int max
   for (int e = 0; e < n_envs; ++e) {
     View V;
     V.base = (char*)records + (size_t)e * L.record_bytes;
-    V.L = &L;
+    V.set_layout(&L);
     tokens_escort_env(V, *cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * 22, tm + (size_t)e * max_tasks,
                       af + (size_t)e * max_agents * 16, am + (size_t)e * max_agents, ev + (size_t)e * max_agents * max_tasks,
                       ids + (size_t)e * max_tasks, order ? order + (size_t)e * L.D.IC : nullptr, W, 0, 1);
@@ -180,7 +180,7 @@ int hostcheck_observe(const muav_config* cfg, const void* records, int max_rows,
   for (int e = 0; e < n_envs; ++e) {
     View V;
     V.base = (char*)records + (size_t)e * L.record_bytes;
-    V.L = &L;
+    V.set_layout(&L);
     int32_t nr = 0;
     observe_env(V, *cfg, max_rows, ti + (size_t)e * max_rows * 21, pad + (size_t)e * max_rows,
                 legal + (size_t)e * L.D.A * max_rows, ao + (size_t)e * L.D.A * 9, ef + (size_t)e * 5, &nr);
@@ -194,7 +194,7 @@ int hostcheck_metrics(const muav_config* cfg, const void* records, double* out, 
   for (int e = 0; e < n_envs; ++e) {
     View V;
     V.base = (char*)records + (size_t)e * L.record_bytes;
-    V.L = &L;
+    V.set_layout(&L);
     metrics_env(V, *cfg, out + (size_t)e * 30);
   }
   return 0;
