@@ -278,7 +278,12 @@ def run_gpu_arm(args):
     # for WPS_hard).  With slot recycling at most 24 are alive at once over 4096 seeds x 150 steps; --task-cap 32 gives
     # 15 instead of 12 environments per SM but no measurable gain in this bench, so the default stays the safe one.
     task_cap = args.task_cap if args.task_cap > 0 else None
-    env = BatchedMultiUAVEnv(cfg, E, device=dev, task_cap=task_cap).reset(sharding.shard_range(E, rank))
+    seeds = list(sharding.shard_range(E, rank))
+    if args.unique_seeds > 0:
+        # big sweeps: scenario generation on the host is the slow part (10 ms per 64-agent environment), so the shard
+        # cycles through a bounded set of distinct seeds (stated in config.workload)
+        seeds = [s % args.unique_seeds for s in seeds]
+    env = BatchedMultiUAVEnv(cfg, E, device=dev, task_cap=task_cap).reset(seeds)
     torch.manual_seed(0)
     scores = tok = scorer = None
     if use_scorer:
@@ -458,7 +463,8 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{case_name} ({A} agents), {E} envs per GPU, {desc}, seeds = env index",
+            "config": {"workload": f"{case_name} ({A} agents), {E} envs per GPU, {desc}, seeds = env index"
+                                   + (f" mod {args.unique_seeds}" if args.unique_seeds > 0 else ""),
                        "envs_per_gpu": E, "global_envs": world * E, "parallelism": f"env-shard x{world}",
                        "l2": f"flushed between timed steps (256 MB write); state {E * rb / 1e6:.0f} MB vs 126 MB L2",
                        "record_bytes": rb, "task_slots": int(env.task_cap), "agent_steps_per_s": value * A,
@@ -575,6 +581,8 @@ def main():
                     help="hard_pair (default, BASELINE config 2) | hard_local | commit_urgency | escort_coalition | burst_xK "
                          "| attn_context | hard_pi | escort_pi")
     ap.add_argument("--task-cap", type=int, default=0, help="task slots per environment (0 = workload default)")
+    ap.add_argument("--unique-seeds", type=int, default=0,
+                    help="cycle through this many distinct scenario seeds (0 = one seed per environment)")
     ap.add_argument("--global-envs", type=int, default=0,
                     help="strong scaling: total environments sharded across the GPUs (overrides --envs)")
     ap.add_argument("--cpu-seconds", type=float, default=60.0,

@@ -171,6 +171,8 @@ const char* muav_version(void);
 size_t muav_config_size(void);
 size_t muav_record_bytes(const muav_config* cfg);
 size_t muav_scratch_bytes(const muav_config* cfg);
+/* bytes at the start of a record that the step kernel stages on chip (the rest is touched in place, see csrc/muav_layout.h) */
+size_t muav_hot_bytes(const muav_config* cfg);
 int muav_num_fields(void);
 /* name/offset/count/element size of field `idx` of the record for this config */
 int muav_field_info(const muav_config* cfg, int idx, const char** name, int64_t* offset, int64_t* count, int32_t* elem_size);

@@ -89,7 +89,7 @@ class MuavAttPairOffsets(C.Structure):
 
 # every symbol include/muav.h declares
 ABI_SYMBOLS = [
-    "muav_version", "muav_config_size", "muav_record_bytes", "muav_scratch_bytes", "muav_num_fields",
+    "muav_version", "muav_config_size", "muav_record_bytes", "muav_scratch_bytes", "muav_hot_bytes", "muav_num_fields",
     "muav_field_info", "muav_header_index", "muav_step", "muav_allocate", "muav_step_host", "muav_lsap",
     "muav_avoid_obstacles", "muav_metric_name", "muav_metrics", "muav_tokens_pair", "muav_tokens_commit", "muav_tokens_escort", "muav_tokens_context", "muav_pair_mask", "muav_observe",
     "muav_att_pair_scores", "muav_att_context_pair_scores", "muav_rollout", "muav_state_bytes", "muav_tape_bytes", "muav_reset_upload", "muav_snapshot",
@@ -112,6 +112,8 @@ class Lib:
         d.muav_record_bytes.argtypes = [C.POINTER(MuavConfig)]
         d.muav_scratch_bytes.restype = C.c_size_t
         d.muav_scratch_bytes.argtypes = [C.POINTER(MuavConfig)]
+        d.muav_hot_bytes.restype = C.c_size_t
+        d.muav_hot_bytes.argtypes = [C.POINTER(MuavConfig)]
         d.muav_num_fields.restype = C.c_int
         d.muav_field_info.restype = C.c_int
         d.muav_field_info.argtypes = [C.POINTER(MuavConfig), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64),
@@ -123,6 +125,9 @@ class Lib:
 
     def record_bytes(self, cfg: MuavConfig) -> int:
         return int(self.dll.muav_record_bytes(C.byref(cfg)))
+
+    def hot_bytes(self, cfg: MuavConfig) -> int:
+        return int(self.dll.muav_hot_bytes(C.byref(cfg)))
 
     def scratch_bytes(self, cfg: MuavConfig) -> int:
         return int(self.dll.muav_scratch_bytes(C.byref(cfg)))
@@ -258,7 +263,7 @@ def build_config(opts, task_cap=None, queue_cap=16, event_cap=None, id_cap=None)
     # every step a recon sits on a Rec (~250 tasks per WPS_escort episode).
     base = max(max_tasks - 1, sum(tasks.values()) + len(threats)) + n_threats
     if id_cap is None:
-        id_cap = base + (320 if escort else 0)
+        id_cap = base + (448 if escort else 0)   # 8192 WPS_escort seeds: up to ~390 ids in one episode
         id_cap = (id_cap + 31) // 32 * 32
     # Task slots: open tasks plus closed ones that a queue / the escort map / a live threat still references.
     if task_cap == "all":

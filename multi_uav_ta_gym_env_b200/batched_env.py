@@ -129,12 +129,11 @@ class BatchedMultiUAVEnv:
         self.group_replanners = os.environ.get("MUAV_ENV_ORDER", "1") != "0"
         self._order = torch.zeros(2, E + 2, dtype=torch.int32, device=dev)
         self._order_cur = -1  # index of the buffer holding the order for the next launch (-1: identity)
-        # workspace that lets a single fused step run as allocator kernel + step kernel (muav_step_out.d_actions_ws)
-        # (measured slower than the one-kernel form on B200: off unless MUAV_SPLIT_STEP=1)
-        self._actions_ws = None
-        if os.environ.get("MUAV_SPLIT_STEP", "0") == "1":
-            self._actions_ws = torch.empty(E, A, 2, dtype=torch.int32, device=dev)
-            self._out.d_actions_ws = self._actions_ws.data_ptr()
+        # workspace that lets a single fused step run as allocator kernel + step kernel (muav_step_out.d_actions_ws): the
+        # library takes that form when the step-only launch keeps >= 1.5 x as many environments resident per SM as the
+        # fused one (big shapes: WPS_escort, burst x4 / x8), see launch rule in csrc/muav_kernels.cu
+        self._actions_ws = torch.empty(E, A, 2, dtype=torch.int32, device=dev)
+        self._out.d_actions_ws = self._actions_ws.data_ptr()
         self.scenarios = None
         self.agent_names = None
         self.launches = 0
@@ -167,9 +166,17 @@ class BatchedMultiUAVEnv:
         if len(seeds) != self.n_envs:
             raise ValueError("need one seed per environment")
         tw = list(self.cfg.tape_words)
-        self.scenarios = [_reset.generate_scenario(self.config, int(s), tw) for s in seeds]
+        # scenario generation is host work (about a millisecond per 8-agent environment): repeated seeds are generated
+        # and packed once, then their rows are replicated
+        uniq = sorted(set(int(s) for s in seeds))
+        made = {s: _reset.generate_scenario(self.config, s, tw) for s in uniq}
+        self.scenarios = [made[int(s)] for s in seeds]
         self.agent_names = [sc.agent_names for sc in self.scenarios]
-        rec, tapes = _reset.pack_records(self.lib, self.cfg, self.scenarios)
+        rec, tapes = _reset.pack_records(self.lib, self.cfg, [made[s] for s in uniq])
+        if len(uniq) != len(seeds):
+            row = {s: i for i, s in enumerate(uniq)}
+            take = np.fromiter((row[int(s)] for s in seeds), dtype=np.int64, count=len(seeds))
+            rec, tapes = np.ascontiguousarray(rec[take]), np.ascontiguousarray(tapes[take])
         E = self.n_envs
         dll = self.lib.dll
         assert dll.muav_state_bytes(C.byref(self.cfg), E) == rec.nbytes and dll.muav_tape_bytes(C.byref(self.cfg), E) == tapes.nbytes

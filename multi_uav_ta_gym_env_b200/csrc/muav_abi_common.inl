@@ -5,11 +5,12 @@ const char* muav_version(void) { return "muav_b200 0.1 (sm_100a)"; }
 size_t muav_config_size(void) { return sizeof(muav_config); }
 size_t muav_record_bytes(const muav_config* cfg) { return (size_t)make_layout(*cfg).record_bytes; }
 size_t muav_scratch_bytes(const muav_config* cfg) { return (size_t)make_layout(*cfg).scratch_bytes; }
+size_t muav_hot_bytes(const muav_config* cfg) { return (size_t)make_layout(*cfg).hot_bytes; }
 
 int muav_num_fields(void) {
   int n = 0;
 #define X(name, type, count) ++n;
-  MUAV_FIELDS(X, X)
+  MUAV_FIELDS(X, X, X, X)
 #undef X
   return n;
 }
@@ -28,7 +29,7 @@ int muav_field_info(const muav_config* cfg, int idx, const char** name, int64_t*
     return 0;                           \
   }                                     \
   ++i;
-  MUAV_FIELDS(X, X)
+  MUAV_FIELDS(X, X, X, X)
 #undef X
   return -22;
 }

@@ -186,7 +186,7 @@ MUAV_HD inline double residual_demand(const Sim& S, int k) {
   }
   int ti = S.V.k_type()[k];
   int TC = S.V.lay().D.TC;
-  double r = S.V.k_cur2(ti, k) - S.V.k_alloc2(ti, k);
+  double r = S.V.k_cur_ti()[k] - S.V.k_alloc_ti()[k];
   return r > 0.0 ? r : 0.0;
 }
 
@@ -258,7 +258,7 @@ MUAV_HD MUAV_NI_A inline int allocate_tasks(Sim& S, const muav_alloc_opts& O, in
           col = it < O.score_cols ? it : -1;  // column = position in the escort token list
         } else if (O.pair_tokens) {
           int ti = V.k_type()[k];
-          if (!(V.k_alloc2(ti, k) < V.k_cur2(ti, k))) continue;  // AttentionRAH.py:67-71
+          if (!(V.k_alloc_ti()[k] < V.k_cur_ti()[k])) continue;  // AttentionRAH.py:67-71
           if (tok_j >= O.score_cols) break;                                    // open_tasks[:max_tasks]
           col = tok_j++;
         }
@@ -699,7 +699,7 @@ MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, in
         double c = -1.0;
         if (V.k_status()[k] != 2) {
           const int ti = V.k_type()[k];
-          if (V.k_alloc2(ti, k) < V.k_cur2(ti, k)) {
+          if (V.k_alloc_ti()[k] < V.k_cur_ti()[k]) {
             if (col < O.score_cols) c = (double)col;
             ++col;
           }
@@ -812,7 +812,7 @@ MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, in
         for (int k = 0; k < n; ++k) {
           if (V.k_status()[k] == 2 || V.k_deadline()[k] < 0) continue;
           int ti = V.k_type()[k];
-          if (!(V.k_alloc2(ti, k) < V.k_cur2(ti, k))) continue;
+          if (!(V.k_alloc_ti()[k] < V.k_cur_ti()[k])) continue;
           if (!vis_none && !S.known_bit(a, k)) continue;
           if (!(task_urgency(V, k, t) >= thr)) continue;
           double d = norm2(V.a_posx()[a] - V.k_posx()[k], V.a_posy()[a] - V.k_posy()[k]);

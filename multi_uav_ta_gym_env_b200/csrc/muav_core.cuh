@@ -200,12 +200,20 @@ struct Sim {
     V.k_status()[k] = 2;
   }
 
+  // hot copies of component [task type] of the requirement vectors (muav_layout.h): refreshed after every update
+  MUAV_HD void sync_req(int k) {
+    const int ti = V.k_type()[k];
+    V.k_cur_ti()[k] = V.k_cur2(ti, k);
+    V.k_alloc_ti()[k] = V.k_alloc2(ti, k);
+  }
+
   // ------------------------------------------------------------------ Task.add/removeAgentCap
   // DroneEnvComponents.py:280-301.  `t0` is the time stored with the entry that was just removed.
   MUAV_HD MUAV_NI_H void remove_agent_cap(int k, int a, double t0) {
     if (V.k_status()[k] == 2) return;
     int TC = V.lay().D.TC;
     _Pragma("unroll 1") for (int c = 0; c < 6; ++c) V.k_alloc2(c, k) = V.k_alloc2(c, k) - cap(a, c);
+    sync_req(k);
     int tid = k + 1;
     int cnt = 0;
     double mn = 0.0, mx = 0.0;
@@ -237,6 +245,7 @@ struct Sim {
     int TC = V.lay().D.TC;
     double end = time_at + (double)C().duration[V.k_type()[k]];
     _Pragma("unroll 1") for (int c = 0; c < 6; ++c) V.k_alloc2(c, k) = V.k_alloc2(c, k) + cap(a, c);
+    sync_req(k);
     if (time_at < V.k_init()[k] || V.k_init()[k] == -1.0) {
       V.k_init()[k] = time_at;
       if (V.k_dtime()[k] == -1.0) V.k_dtime()[k] = end;
@@ -348,7 +357,7 @@ struct Sim {
     int ti = V.k_type()[k];
     int TC = V.lay().D.TC;
     if (C().capability_mask && cap(a, ti) <= 0) return false;
-    if (C().saturate_mask && V.k_alloc2(ti, k) >= V.k_org_ti()[k]) return false;
+    if (C().saturate_mask && V.k_alloc_ti()[k] >= V.k_org_ti()[k]) return false;
     return true;
   }
 
@@ -392,6 +401,8 @@ struct Sim {
       V.k_cur2(c, k) = 0.0;
       V.k_alloc2(c, k) = 0.0;
     }
+    V.k_cur_ti()[k] = 0.0;
+    V.k_alloc_ti()[k] = 0.0;
     V.k_done_ti()[k] = 0.0;
     V.k_org_ti()[k] = 0.0;
     V.k_init()[k] = -1.0;
@@ -577,6 +588,7 @@ struct Sim {
             V.k_cur2(TT_INT, k) = 2.0;
             V.k_cur2(TT_ATT, k) = C().cap_table[ht][3] * 2;
             V.k_cur2(TT_DEF, k) = C().cap_table[ht][2] * 2;
+            sync_req(k);
             V.k_org_ti()[k] = 2.0;
             V.k_threat()[k] = (int16_t)hid;
             V.k_created()[k] = (int16_t)t;
@@ -590,6 +602,7 @@ struct Sim {
             HIv(N_ACTIVE) += 1;
             int dk = V.h_det_task()[hid] - 1;
             V.k_cur2(TT_DET, dk) = V.k_cur2(TT_DET, dk) - 1.0;
+            sync_req(dk);
             register_dynamic(tid);
             push_event(EV_THREAT, tid);
             push_event(EV_RESET, TT_INT);
@@ -695,6 +708,7 @@ _Pragma("unroll 1") for (int a = 0; a < A(); ++a) {
     int k = tid - 1;
     int TC = V.lay().D.TC;
     V.k_cur2(TT_DEF, k) = C().escort_requirement;
+    sync_req(k);
     V.k_org_ti()[k] = C().escort_requirement;
     V.k_kind()[k] = 1;
     V.k_prot_agent()[k] = (int16_t)a;
@@ -1009,6 +1023,7 @@ _Pragma("unroll 1") for (int a = 0; a < A(); ++a) {
     int k = tid - 1;
     int TC = V.lay().D.TC;
     V.k_cur2(ti, k) = 1.0;
+    sync_req(k);
     V.k_org_ti()[k] = 1.0;
     V.k_created()[k] = (int16_t)HIv(T);
     HIv(N_ARRIVALS) += 1;
@@ -1262,7 +1277,7 @@ _Pragma("unroll 1") for (int i = 0; i < nev; ++i) {
         else V.k_tbl_hi()[k] |= 1u << (a - 32);
         int ti = V.k_type()[k];
         double cp = cap(a, ti);
-        double missing = V.k_cur2(ti, k) - (V.k_alloc2(ti, k) - cp);
+        double missing = V.k_cur_ti()[k] - (V.k_alloc_ti()[k] - cp);
         missing = missing > 0 ? missing : 0.0;
         double rest = missing - cp;
         double added = missing - (rest > 0 ? rest : 0.0);
@@ -1527,6 +1542,7 @@ _Pragma("unroll 1") for (int i = 0; i < nev; ++i) {
             bool popped = task_done(a, cur, &t0);
             V.k_done_ti()[k] = V.k_done_ti()[k] + cap(a, ti);
             _Pragma("unroll 1") for (int c = 0; c < 6; ++c) V.k_cur2(c, k) = V.k_cur2(c, k) - cap(a, c);
+            sync_req(k);
             if (popped) {
               remove_agent_cap(k, a, t0);
             } else if (qfind(a, cur) >= 0) {

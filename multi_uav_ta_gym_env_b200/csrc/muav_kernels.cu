@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 
 #include "muav_alloc.cuh"
 #include "muav_views.cuh"
@@ -70,6 +71,7 @@ struct StepParams {
   long long* phase_out;  // MUAV_PHASE_TIMING builds: 16 cycle counters summed over warps
   int n_envs, n_steps, tape_stride, use_bulk, alloc_only, cta_warps, sync_mask;
   int scratch_launch;   // per-environment scratch bytes of this launch (allocator work arrays or step temporaries)
+  int stage_bytes;      // bytes of each record staged into shared memory: hot_bytes, or record_bytes (cold part too)
   int actions_are_ids;  // actions hold (agent, task id) instead of (agent, index into last_tasks_info)
 };
 
@@ -78,11 +80,16 @@ struct StepParams {
 
 // One warp per environment; a CTA holds `cta_warps` environments whose warps are phase-aligned with
 // CTA barriers (no data is shared between them).
-__global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(const __grid_constant__ StepParams P) {
+// Register budget: the general kernel may be launched with up to 16 warps per CTA (128 registers per thread, at most 16
+// resident warps per SM).  A fixed-shape instantiation knows its shared-memory slot and states its own bound
+// (MUAV_LB_THREADS threads per CTA at most, MUAV_LB_BLOCKS CTAs per SM): more resident environments per SM.
+#if !defined(MUAV_LB_THREADS)
+#define MUAV_LB_THREADS (32 * MUAV_MAX_CTA_WARPS)
+#define MUAV_LB_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(MUAV_LB_THREADS, MUAV_LB_BLOCKS) muav_step_kernel(const __grid_constant__ StepParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar[MUAV_MAX_CTA_WARPS];
-  __shared__ int16_t act_agent_s[MUAV_MAX_CTA_WARPS][MUAV_MAX_AGENTS];
-  __shared__ int16_t act_tid_s[MUAV_MAX_CTA_WARPS][MUAV_MAX_AGENTS];
   __shared__ int n_act_s[MUAV_MAX_CTA_WARPS];
   const int W = P.cta_warps;
   const int w = threadIdx.x >> 5;
@@ -105,12 +112,15 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
 #else
   const Layout& L = P.L;
 #endif
-  const int slot_bytes = L.record_bytes + P.scratch_launch;
+  // shared-memory slot of this warp's environment: [hot record | scratch | ordered action list]
+  // (a launch may stage the cold part as well, P.stage_bytes == record_bytes: small records, many allocator updates)
+  const int stage_bytes = P.stage_bytes;
+  const int slot_bytes = stage_bytes + P.scratch_launch + L.act_bytes;
   char* rec = (char*)smem + (size_t)w * slot_bytes;
-  char* scratch = rec + L.record_bytes;
+  char* scratch = rec + stage_bytes;
   char* grec = P.records + (size_t)(has_env ? e : 0) * L.record_bytes;
-  int16_t* act_agent = act_agent_s[w];
-  int16_t* act_tid = act_tid_s[w];
+  int16_t* act_agent = (int16_t*)(scratch + P.scratch_launch);
+  int16_t* act_tid = act_agent + L.D.A;
 
   // ---- allocator-only launch: environments whose replan rule does not fire leave after a look at their header
 #if defined(MUAV_LEAN)
@@ -150,20 +160,21 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
       }
       __syncwarp();
       if (lane == 0) {
-        mbar_expect_tx(&bar[w], (uint32_t)L.record_bytes);
-        bulk_g2s(rec, grec, (uint32_t)L.record_bytes, &bar[w]);
+        mbar_expect_tx(&bar[w], (uint32_t)stage_bytes);
+        bulk_g2s(rec, grec, (uint32_t)stage_bytes, &bar[w]);
       }
       mbar_wait(&bar[w], 0);
     } else {
       const uint4* src = (const uint4*)grec;
       uint4* dst = (uint4*)rec;
-      for (int i = lane; i < L.record_bytes / 16; i += 32) dst[i] = src[i];
+      for (int i = lane; i < stage_bytes / 16; i += 32) dst[i] = src[i];
     }
   }
   __syncwarp();
 
   Sim S;
-  S.V.base = rec;
+  S.V.base = rec;     // hot part: shared memory
+  S.V.cbase = stage_bytes > L.hot_bytes ? rec : grec;   // cold part: staged too, or in place in HBM (muav_layout.h)
   S.V.set_layout(&L);
   S.Cp = &P.cfg;
   S.tape = P.tapes + (size_t)(has_env ? e : 0) * P.tape_stride;
@@ -324,13 +335,13 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        bulk_s2g(grec, rec, (uint32_t)L.record_bytes);
+        bulk_s2g(grec, rec, (uint32_t)stage_bytes);
         bulk_wait_all();
       }
     } else {
       const uint4* src = (const uint4*)rec;
       uint4* dst = (uint4*)grec;
-      for (int i = lane; i < L.record_bytes / 16; i += 32) dst[i] = src[i];
+      for (int i = lane; i < stage_bytes / 16; i += 32) dst[i] = src[i];
     }
   }
 }
@@ -339,18 +350,29 @@ __global__ void __launch_bounds__(32 * MUAV_MAX_CTA_WARPS, 1) muav_step_kernel(c
 }  // namespace muav (renamed by the including translation unit)
 
 // launcher of this translation unit's instantiation of the step kernel (see muav_step_lean.cu)
-extern "C" int MUAV_STEP_LAUNCHER(const void* params, int grid, int threads, size_t smem, void* stream) {
-  // the opt-in shared-memory size is a per-device attribute of the function: remembered per device, set again when a larger
-  // launch comes (a benign race between threads: both write a sufficient value)
-  static size_t smem_set[MUAV_MAX_DEVICES];
+// The opt-in shared-memory size is a per-device attribute of the function: set to the device maximum once per device
+// (concurrent first calls write the same value).
+static int muav_inst_prepare() {
+  static bool done[MUAV_MAX_DEVICES];
   int dev = 0;
   cudaGetDevice(&dev);
-  size_t* seen = &smem_set[(dev >= 0 && dev < MUAV_MAX_DEVICES) ? dev : 0];
-  if (smem > 48 * 1024 && (smem > *seen || dev >= MUAV_MAX_DEVICES)) {
-    cudaError_t e = cudaFuncSetAttribute(muav::muav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return -1000 - (int)e;
-    *seen = smem;
-  }
+  if (dev >= 0 && dev < MUAV_MAX_DEVICES && done[dev]) return 0;
+  // the opt-in limit covers static + dynamic shared memory of a CTA
+  int optin = 0;
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, muav::muav_step_kernel);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(muav::muav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             optin - (int)fa.sharedSizeBytes);
+  if (e != cudaSuccess) return -1000 - (int)e;
+  if (dev >= 0 && dev < MUAV_MAX_DEVICES) done[dev] = true;
+  return 0;
+}
+extern "C" int MUAV_STEP_LAUNCHER(const void* params, int grid, int threads, size_t smem, void* stream) {
+  if (threads > MUAV_LB_THREADS) return -22;
+  const int rc = muav_inst_prepare();
+  if (rc) return rc;
   muav::muav_step_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(*(const muav::StepParams*)params);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -1000 - (int)e;
@@ -358,6 +380,14 @@ extern "C" int MUAV_STEP_LAUNCHER(const void* params, int grid, int threads, siz
 extern "C" int MUAV_STEP_STATIC_SMEM(void) {
   cudaFuncAttributes fa;
   return cudaFuncGetAttributes(&fa, muav::muav_step_kernel) == cudaSuccess ? (int)fa.sharedSizeBytes : 4608;
+}
+// resident CTAs per SM for a CTA of `threads` threads with `smem` bytes of dynamic shared memory (registers, shared
+// memory and warp slots taken into account); 0 when the instantiation cannot be launched that wide
+extern "C" int MUAV_STEP_OCC(int threads, size_t smem) {
+  if (threads > MUAV_LB_THREADS || muav_inst_prepare() != 0) return 0;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, muav::muav_step_kernel, threads, smem) != cudaSuccess) return 0;
+  return nb;
 }
 #if defined(MUAV_FIXED_SHAPE)
 // the one record shape this instantiation was compiled for: A, TC, IC, HC, QC, EVC, NOBS
@@ -401,7 +431,7 @@ __global__ void muav_metrics_kernel(const __grid_constant__ muav_config cfg, con
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   View V;
-  V.base = (char*)records + (size_t)e * L.record_bytes;
+  V.at((char*)records + (size_t)e * L.record_bytes);
   V.set_layout(&L);
   metrics_env(V, cfg, out + (size_t)e * MUAV_N_METRICS);
 }
@@ -416,7 +446,7 @@ __global__ void __launch_bounds__(128) muav_tokens_pair_kernel(const __grid_cons
   const int e = blockIdx.x * 4 + w;
   if (e >= n) return;
   View V;
-  V.base = (char*)records + (size_t)e * L.record_bytes;
+  V.at((char*)records + (size_t)e * L.record_bytes);
   V.set_layout(&L);
   const int TD = raw ? 9 : 13, AD = raw ? 11 : af_dim, CD = raw ? 1 : 8;
   tokens_pair_env(V, cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * TD, tm + (size_t)e * max_tasks,
@@ -435,7 +465,7 @@ __global__ void __launch_bounds__(128) muav_tokens_escort_kernel(const __grid_co
   const int e = blockIdx.x * 4 + w;
   if (e >= n) return;
   View V;
-  V.base = (char*)records + (size_t)e * L.record_bytes;
+  V.at((char*)records + (size_t)e * L.record_bytes);
   V.set_layout(&L);
   EscortTokScratch W = carve_escort_tok(esc_smem + (size_t)w * per_warp, L.D.TC, max_tasks);
   tokens_escort_env(V, cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * 22, tm + (size_t)e * max_tasks,
@@ -452,7 +482,7 @@ __global__ void muav_pair_mask_kernel(const __grid_constant__ Layout L, const ch
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   View V;
-  V.base = (char*)records + (size_t)e * L.record_bytes;
+  V.at((char*)records + (size_t)e * L.record_bytes);
   V.set_layout(&L);
   const int A = L.D.A;
   float* m = mask + (size_t)e * max_agents * max_tasks;
@@ -481,7 +511,7 @@ __global__ void muav_observe_kernel(const __grid_constant__ muav_config cfg, con
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   View V;
-  V.base = (char*)records + (size_t)e * L.record_bytes;
+  V.at((char*)records + (size_t)e * L.record_bytes);
   V.set_layout(&L);
   int32_t nr = 0;
   observe_env(V, cfg, max_rows, ti + (size_t)e * max_rows * MUAV_OBS_TASK_DIM, pad + (size_t)e * max_rows,
@@ -505,7 +535,8 @@ extern "C" {
 //   fixed-shape ones (muav_step_hard.cu, ...): the lean feature set AND the record dimensions as compile-time constants.
 #define MUAV_DECL_INST(n)                                                                        \
   int muav_step_##n##_launch(const void* params, int grid, int threads, size_t smem, void* stream); \
-  int muav_step_##n##_static_smem(void);
+  int muav_step_##n##_static_smem(void);                                                         \
+  int muav_step_##n##_occ(int threads, size_t smem);
 #define MUAV_DECL_SHAPED(n) MUAV_DECL_INST(n) void muav_step_##n##_shape(int* out);
 MUAV_DECL_INST(lean)
 MUAV_DECL_INST(lean_escort)
@@ -514,16 +545,39 @@ MUAV_DECL_SHAPED(hard32)
 
 struct StepInst {
   int (*launch)(const void*, int, int, size_t, void*);
-  int (*static_smem)(void);
+  int (*occ)(int, size_t);
   void (*shape)(int*);  // null: any shape
   int escort;           // value of cfg.escort_enabled this instantiation was compiled for
 };
 static const StepInst kStepInst[] = {
-    {muav_step_hard_launch, muav_step_hard_static_smem, muav_step_hard_shape, 0},
-    {muav_step_hard32_launch, muav_step_hard32_static_smem, muav_step_hard32_shape, 0},
-    {muav_step_lean_launch, muav_step_lean_static_smem, nullptr, 0},
-    {muav_step_lean_escort_launch, muav_step_lean_escort_static_smem, nullptr, 1},
+    {muav_step_hard_launch, muav_step_hard_occ, muav_step_hard_shape, 0},
+    {muav_step_hard32_launch, muav_step_hard32_occ, muav_step_hard32_shape, 0},
+    {muav_step_lean_launch, muav_step_lean_occ, nullptr, 0},
+    {muav_step_lean_escort_launch, muav_step_lean_escort_occ, nullptr, 1},
 };
+
+// general kernel of this translation unit: same two services
+static int general_prepare() {
+  static bool done[MUAV_MAX_DEVICES];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < MUAV_MAX_DEVICES && done[dev]) return 0;
+  int optin = 0;
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, muav_step_kernel);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(muav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+  if (e != cudaSuccess) return cuda_rc(e);
+  if (dev >= 0 && dev < MUAV_MAX_DEVICES) done[dev] = true;
+  return 0;
+}
+static int general_occ(int threads, size_t smem) {
+  if (general_prepare() != 0) return 0;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, muav_step_kernel, threads, smem) != cudaSuccess) return 0;
+  return nb;
+}
 
 // the most specialised instantiation that covers this launch (null: the general kernel of this translation unit)
 static const StepInst* pick_inst(const StepParams& P) {
@@ -548,49 +602,76 @@ static const StepInst* pick_inst(const StepParams& P) {
   return nullptr;
 }
 
+// shared memory per resident environment of this launch: [hot record | scratch | ordered action list]; the scratch holds
+// the allocator's work arrays (+ the planner front ends' arrays when one runs) or just the step's temporaries
+static size_t slot_bytes_of(StepParams& P) {
+  const bool with_alloc = P.alloc_only || P.opts.mode != 0;
+  const bool with_planner = P.opts.planner != 0 && P.opts.planner != 6;
+  P.scratch_launch = !with_alloc ? P.L.step_scratch_bytes : (with_planner ? P.L.scratch_bytes : P.L.plain_scratch_bytes);
+  return (size_t)P.stage_bytes + (size_t)P.scratch_launch + (size_t)P.L.act_bytes;
+}
+
+// Environments (warps) per CTA.  The warps of a CTA are phase-aligned with CTA barriers: they share instruction
+// fetches, but a CTA is as slow as its slowest environment.  Measured on B200 (profiles/r01_cta_width.md,
+// profiles/r02_step_kernel.md): the number of resident environments per SM decides first (registers, shared memory and
+// warp slots: asked from the occupancy calculator per instantiation); at equal residency the widest CTA that still
+// leaves two CTAs per SM wins; when only one-warp CTAs or a single wide CTA reach the maximum, the wide CTA wins from
+// four environments up and one-warp CTAs below.  Returns W, *envs_per_sm = resident environments per SM with it.
+static int choose_width(const StepInst* inst, size_t slot, int* envs_per_sm) {
+  // the answer depends on (instantiation, slot size) only: remembered in a small table (written under a lock)
+  struct Memo { const StepInst* inst; size_t slot; int W, envs; };
+  static Memo memo[32];
+  static int n_memo = 0;
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> g(mu);
+    for (int i = 0; i < n_memo; ++i)
+      if (memo[i].inst == inst && memo[i].slot == slot) {
+        if (envs_per_sm) *envs_per_sm = memo[i].envs;
+        return memo[i].W;
+      }
+  }
+  const int WMAX = 12;
+  int envs[WMAX + 1], ctas[WMAX + 1], best = 0;
+  for (int w = 0; w <= WMAX; ++w) envs[w] = ctas[w] = 0;
+  for (int w = 1; w <= WMAX; ++w) {
+    if (slot * w > 226 * 1024) break;
+    ctas[w] = inst ? inst->occ(32 * w, slot * w) : general_occ(32 * w, slot * w);
+    envs[w] = ctas[w] * w;
+    if (envs[w] > best) best = envs[w];
+  }
+  int pick = 0;
+  for (int w = WMAX; w >= 2 && !pick; --w)
+    if (envs[w] == best && ctas[w] >= 2) pick = w;
+  if (!pick) {
+    int wide = 0;
+    for (int w = WMAX; w >= 2 && !wide; --w)
+      if (envs[w] == best) wide = w;
+    pick = (wide && (best >= 4 || envs[1] < best)) ? wide : 1;
+  }
+  std::lock_guard<std::mutex> g(mu);
+  if (n_memo < 32) memo[n_memo++] = Memo{inst, slot, pick, envs[pick]};
+  if (envs_per_sm) *envs_per_sm = envs[pick];
+  return pick;
+}
+
 static int launch_step(StepParams& P, void* stream) {
   const StepInst* inst = pick_inst(P);
-  // launches without the allocator need only the step's temporaries: more environments per SM
-  P.scratch_launch = (P.alloc_only || P.opts.mode != 0) ? P.L.scratch_bytes : P.L.step_scratch_bytes;
-  const size_t slot = (size_t)P.L.record_bytes + (size_t)P.scratch_launch;
-  // environments (warps) per CTA.  The warps of a CTA are phase-aligned with CTA barriers: they share instruction
-  // fetches, but a CTA is as slow as its slowest environment.  Measured on B200 (bench.py --workload ..., all widths
-  // 1..6, profiles/r01_cta_width.md): the number of resident environments per SM decides first; at equal residency the
-  // widest CTA that still leaves two CTAs per SM wins (WPS_hard 6 x 2, WPS_commit 4 x 2, burst x2 3 x 2); when only
-  // one-warp CTAs or a single wide CTA reach the maximum, the wide CTA wins from four environments up (WPS_escort
-  // 5 x 1) and one-warp CTAs below (burst x4 1 x 3).  MUAV_CTA_WARPS overrides.
-  int W = 1;
+  // Hot part only, or the whole record?  Staging the cold part costs shared memory (fewer resident environments) but
+  // turns the allocator's / the action phase's updates of the requirement vectors and allocation times into
+  // shared-memory accesses.  Measured on B200 (profiles/r02_step_kernel.md): while the whole record still leaves >= 12
+  // environments per SM (WPS_easy / hard / burst) staging everything is ~15 % faster; for the larger records (WPS_commit,
+  // WPS_escort, the scaled bursts) the residency of the hot-only slot wins by 20-40 %.  MUAV_STAGE_COLD=0 / 1 forces it.
   {
-    // per-CTA static shared memory of the chosen instantiation (a property of the compiled kernel, the same on every
-    // device; cached after the first query -- concurrent first calls write the same value)
-    static int static_cache[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int ci = inst ? 1 + (int)(inst - kStepInst) : 0;
-    if (!static_cache[ci]) {
-      cudaFuncAttributes fa;
-      static_cache[ci] = inst ? inst->static_smem()
-                              : (cudaFuncGetAttributes(&fa, muav_step_kernel) == cudaSuccess ? (int)fa.sharedSizeBytes : 4608);
-    }
-    const size_t static_smem = (size_t)static_cache[ci];
-    const size_t budget = 228 * 1024, per_cta = static_smem + 1024;  // B200: 228 KB per SM, 1 KB reserved per CTA
-    int envs[7] = {0, 0, 0, 0, 0, 0, 0}, ctas[7] = {0, 0, 0, 0, 0, 0, 0}, best = 0;
-    for (int w = 1; w <= 6; ++w) {
-      const size_t cta = slot * w + per_cta;
-      if (cta > 227 * 1024) break;
-      ctas[w] = (int)(budget / cta);
-      envs[w] = ctas[w] * w;
-      if (envs[w] > best) best = envs[w];
-    }
-    int pick = 0;
-    for (int w = 6; w >= 2 && !pick; --w)
-      if (envs[w] == best && ctas[w] >= 2) pick = w;
-    if (!pick) {
-      int wide = 0;
-      for (int w = 6; w >= 2 && !wide; --w)
-        if (envs[w] == best) wide = w;
-      pick = (wide && (best >= 4 || envs[1] < best)) ? wide : 1;
-    }
-    W = pick;
+    P.stage_bytes = P.L.record_bytes;
+    int envs_full = 0;
+    choose_width(inst, slot_bytes_of(P), &envs_full);
+    const char* fc = getenv("MUAV_STAGE_COLD");
+    const bool stage_cold = fc ? atoi(fc) != 0 : envs_full >= 12;
+    if (!stage_cold) P.stage_bytes = P.L.hot_bytes;
   }
+  const size_t slot = slot_bytes_of(P);
+  int W = choose_width(inst, slot, nullptr);
   const char* ev = getenv("MUAV_CTA_WARPS");
   if (ev) W = atoi(ev);
   if (W < 1) W = 1;
@@ -604,14 +685,9 @@ static int launch_step(StepParams& P, void* stream) {
   if (sm) P.sync_mask = atoi(sm);
   const size_t smem = slot * W;
   if (inst) return inst->launch(&P, (P.n_envs + W - 1) / W, 32 * W, smem, stream);
-  static size_t smem_set[MUAV_MAX_DEVICES];
-  int dev = 0;
-  cudaGetDevice(&dev);
-  size_t* seen = &smem_set[(dev >= 0 && dev < MUAV_MAX_DEVICES) ? dev : 0];
-  if (smem > 48 * 1024 && (smem > *seen || dev >= MUAV_MAX_DEVICES)) {
-    cudaError_t e = cudaFuncSetAttribute(muav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_rc(e);
-    *seen = smem;
+  {
+    const int prc = general_prepare();
+    if (prc) return prc;
   }
   const int grid = (P.n_envs + W - 1) / W;
   muav_step_kernel<<<grid, 32 * W, smem, (cudaStream_t)stream>>>(P);
@@ -660,7 +736,26 @@ int muav_step(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, 
     }
   }
 #endif
+  bool split = false;
   if (n_steps == 1 && P.opts.mode != 0 && P.out.d_actions_ws) {
+    // One fused kernel, or the allocator for the environments that replan followed by the step for everyone?  The
+    // step-only launch needs no allocator scratch, so more environments fit an SM; measured on B200 the split pays
+    // when that residency is at least 1.5 x the fused one (WPS_escort, burst x4 / x8), and costs ~15 % when both fit
+    // equally (WPS_hard): profiles/r02_configs.md.  MUAV_SPLIT_STEP=0 / 1 forces the answer.
+    const char* fs = getenv("MUAV_SPLIT_STEP");
+    if (fs) {
+      split = atoi(fs) != 0;
+    } else {
+      StepParams Pf = P, Ps = P;
+      Pf.stage_bytes = Ps.stage_bytes = P.L.hot_bytes;
+      Ps.opts.mode = 0;
+      int envs_f = 0, envs_s = 0;
+      choose_width(pick_inst(Pf), slot_bytes_of(Pf), &envs_f);
+      choose_width(pick_inst(Ps), slot_bytes_of(Ps), &envs_s);
+      split = envs_f > 0 && 2 * envs_s >= 3 * envs_f;
+    }
+  }
+  if (split) {
     // two kernels: allocator for the environments that replan, then the step for everyone with the small scratch
     StepParams Pa = P;
     Pa.n_steps = 0;

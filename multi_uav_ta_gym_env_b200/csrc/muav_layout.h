@@ -98,10 +98,16 @@ MUAV_HD inline Dims dims_of(const muav_config& c) {
   return d;
 }
 
-// name, C type, element count.  Ordered by decreasing alignment (8, 4, 2 bytes).
+// name, C type, element count.
 // X  = plain array; XS = per-task array indexed by SLOT and accessed by task index through k_slot
 // (closed tasks that nothing references any more give their slot back, see Sim::free_dead_tasks).
-#define MUAV_FIELDS(X, XS)          \
+// XC / XCS = the same, COLD: fields the common step never touches (full requirement vectors, allocation times,
+// assignment table, pending events).  The record is [hot part | cold part]; the step kernel stages only the hot part
+// into shared memory and reaches the cold part in global memory (L2) on the rare events that need it, which is what lets
+// twice as many environments stay resident per SM.  Each part is ordered by decreasing alignment (8, 4, 2 bytes).
+// k_cur_ti / k_alloc_ti are hot copies of component [task type] of the cold requirement vectors (the only component
+// the allocator, the token builders and the validity checks read); Sim::sync_req keeps them equal after every update.
+#define MUAV_FIELDS(X, XS, XC, XCS)  \
   X(hf, double, HF_COUNT)           \
   X(a_posx, double, D.A)            \
   X(a_posy, double, D.A)            \
@@ -110,15 +116,12 @@ MUAV_HD inline Dims dims_of(const muav_config& c) {
   X(a_nft, double, D.A)             \
   X(a_dist, double, D.A)            \
   X(a_caps, double, 6 * D.A)        \
-  X(a_qtime, double, D.QC * D.A)    \
   XS(k_posx, double, D.TC)          \
   XS(k_posy, double, D.TC)          \
-  X(k_cur, double, 6 * D.TC)        \
-  X(k_alloc, double, 6 * D.TC)      \
+  XS(k_cur_ti, double, D.TC)        \
+  XS(k_alloc_ti, double, D.TC)      \
   XS(k_done_ti, double, D.TC)       \
   XS(k_org_ti, double, D.TC)        \
-  XS(k_init, double, D.TC)          \
-  XS(k_dtime, double, D.TC)         \
   X(h_posx, double, D.HC)           \
   X(h_posy, double, D.HC)           \
   X(obst, double, 3 * D.NOBS)       \
@@ -130,11 +133,8 @@ MUAV_HD inline Dims dims_of(const muav_config& c) {
   X(a_last_task, int32_t, D.A)      \
   X(a_commit, int32_t, D.A)         \
   X(a_escort, int32_t, D.A)         \
-  XS(k_tbl_lo, uint32_t, D.TC)      \
-  XS(k_tbl_hi, uint32_t, D.TC)      \
   X(known, uint32_t, D.KW * D.A)    \
   X(open_mask, uint32_t, D.KW)      \
-  X(events, int32_t, D.EVC)         \
   X(a_queue, int16_t, D.QC * D.A)   \
   X(a_type, int16_t, D.A)           \
   X(a_re_eval, int16_t, D.A)        \
@@ -167,26 +167,38 @@ MUAV_HD inline Dims dims_of(const muav_config& c) {
   X(h_mission, int16_t, D.HC)       \
   X(h_intercept, int16_t, D.HC)     \
   X(h_spawned, int16_t, D.HC)       \
-  X(h_order, int16_t, D.HC)
+  X(h_order, int16_t, D.HC)         \
+  XC(k_cur, double, 6 * D.TC)       \
+  XC(k_alloc, double, 6 * D.TC)     \
+  XC(a_qtime, double, D.QC * D.A)   \
+  XCS(k_init, double, D.TC)         \
+  XCS(k_dtime, double, D.TC)        \
+  XCS(k_tbl_lo, uint32_t, D.TC)     \
+  XCS(k_tbl_hi, uint32_t, D.TC)     \
+  XC(events, int32_t, D.EVC)
 
 struct Layout {
 #define X(name, type, count) int32_t o_##name;
-  MUAV_FIELDS(X, X)
+  MUAV_FIELDS(X, X, X, X)
 #undef X
   int32_t record_bytes;
+  int32_t hot_bytes;           // [0, hot_bytes) is staged into shared memory by the step kernel; the rest stays in HBM
   int32_t scratch_bytes;
   int32_t step_scratch_bytes;  // scratch of a launch that does not run the allocator
+  int32_t plain_scratch_bytes; // scratch of a launch with the plain Hungarian / PI allocator (no planner front end)
+  int32_t act_bytes;           // ordered action list of the step (agent ids + task ids), kept behind the scratch
   Dims D;
 };
 
 MUAV_HD constexpr inline int32_t align_up(int32_t x, int32_t a) { return (x + a - 1) / a * a; }
 
 // bytes of allocator scratch: cost[A*TC], u/v/spc[M], resid[TC] doubles + 6 M-sized and 2A+3TC int16 arrays
-MUAV_HD constexpr inline int32_t alloc_scratch_bytes(int A, int TC) {
+MUAV_HD constexpr inline int32_t alloc_scratch_bytes(int A, int TC, bool planner_block = true) {
   int M = A > TC ? A : TC;
   int b = 8 * (A * TC + 3 * M + TC + 4);
   b += 2 * (6 * M + 3 * A + 3 * TC);
-  b += 8 * TC + 8 * A + ((A + 7) / 8) * 8;  // planner priorities, lock scores, reserved mask
+  b = (b + 7) / 8 * 8;
+  if (planner_block) b += 8 * TC + 8 * A + ((A + 7) / 8) * 8;  // planner priorities, lock scores, reserved mask
   return (b + 15) / 16 * 16;
 }
 
@@ -196,12 +208,17 @@ MUAV_HD constexpr inline Layout make_layout_dims(const Dims D) {
   Layout L{};
   L.D = D;
   int32_t off = 0;
+  bool cold = false;
 #define X(name, type, count)                 \
   off = align_up(off, (int32_t)sizeof(type)); \
   L.o_##name = off;                          \
   off += (int32_t)sizeof(type) * (int32_t)(count);
-  MUAV_FIELDS(X, X)
+#define XCF(name, type, count)                                    \
+  if (!cold) { cold = true; off = align_up(off, 16); L.hot_bytes = off; } \
+  X(name, type, count)
+  MUAV_FIELDS(X, X, XCF, XCF)
 #undef X
+#undef XCF
   L.record_bytes = align_up(off, 16);
   // per-warp scratch: allocator work arrays (muav_alloc.cuh carve_scratch) or the step's temporaries
   int32_t s = alloc_scratch_bytes(D.A, D.TC) + 8 * (D.IC - D.TC);  // planner priorities are indexed by task id
@@ -212,6 +229,11 @@ MUAV_HD constexpr inline Layout make_layout_dims(const Dims D) {
   int32_t s3 = s2 + 2 * (D.TC + 4);
   L.step_scratch_bytes = align_up(s3, 16);
   if (L.step_scratch_bytes > L.scratch_bytes) L.step_scratch_bytes = L.scratch_bytes;
+  int32_t s4 = alloc_scratch_bytes(D.A, D.TC, false);
+  if (s2 > s4) s4 = s2;
+  L.plain_scratch_bytes = align_up(s4, 16);
+  if (L.plain_scratch_bytes < L.step_scratch_bytes) L.plain_scratch_bytes = L.step_scratch_bytes;
+  L.act_bytes = align_up(4 * D.A, 16);
   return L;
 }
 
@@ -239,7 +261,10 @@ struct SlotRef {
 };
 
 struct View {
-  char* base;
+  char* base;    // hot part of the record (shared memory inside the step kernel)
+  char* cbase;   // record start as far as the COLD fields are concerned: the record in HBM inside the step kernel, == base
+                 // wherever the whole record is addressed in place (standalone kernels, CPU build)
+  MUAV_HD inline void at(char* rec) { base = rec; cbase = rec; }
 #if defined(MUAV_FIXED_SHAPE)
   MUAV_HD inline void set_layout(const Layout*) {}
   MUAV_HD inline Layout lay() const {
@@ -258,10 +283,19 @@ struct View {
     return SlotRef<type>{(type*)(base + lay().o_##name), (const int16_t*)(base + lay().o_k_slot)};  \
   }                                                                                                 \
   MUAV_HD inline type* name##_raw() const { return (type*)(base + lay().o_##name); }
-  MUAV_FIELDS(X, XS)
+#define XC(name, type, count) \
+  MUAV_HD inline type* name() const { return (type*)(cbase + lay().o_##name); }
+#define XCS(name, type, count)                                                                       \
+  MUAV_HD inline SlotRef<type> name() const {                                                        \
+    return SlotRef<type>{(type*)(cbase + lay().o_##name), (const int16_t*)(base + lay().o_k_slot)};  \
+  }                                                                                                  \
+  MUAV_HD inline type* name##_raw() const { return (type*)(cbase + lay().o_##name); }
+  MUAV_FIELDS(X, XS, XC, XCS)
 #undef X
 #undef XS
-  // requirement vectors: component c of task index k
+#undef XC
+#undef XCS
+  // requirement vectors (cold): component c of task index k
   MUAV_HD inline double& k_cur2(int c, int k) const { return k_cur()[c * lay().D.TC + k_slot()[k]]; }
   MUAV_HD inline double& k_alloc2(int c, int k) const { return k_alloc()[c * lay().D.TC + k_slot()[k]]; }
 };

@@ -53,7 +53,7 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
       bool res = k < n && V.k_status()[k] != 2;
       if (res) {
         const int ti = V.k_type()[k];
-        res = V.k_alloc2(ti, k) < V.k_cur2(ti, k);  // AttentionRAH.py:67-71
+        res = V.k_alloc_ti()[k] < V.k_cur_ti()[k];  // AttentionRAH.py:67-71
       }
       const unsigned m = __ballot_sync(0xffffffffu, res);
       const int pos = n_open_res + __popc(m & ((1u << lane) - 1u));
@@ -71,7 +71,7 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
     for (int k = 0; k < n; ++k) {
       if (V.k_status()[k] == 2) continue;
       int ti = V.k_type()[k];
-      if (!(V.k_alloc2(ti, k) < V.k_cur2(ti, k))) continue;  // AttentionRAH.py:67-71
+      if (!(V.k_alloc_ti()[k] < V.k_cur_ti()[k])) continue;  // AttentionRAH.py:67-71
       ++n_open_all;
       if (col < max_tasks) cols[col++] = (int16_t)k;
     }
@@ -126,7 +126,7 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
     }
     const int k = cols[j];
     const int ti = V.k_type()[k];
-    const double cur = V.k_cur2(ti, k), al = V.k_alloc2(ti, k);
+    const double cur = V.k_cur_ti()[k], al = V.k_alloc_ti()[k];
     double urg = urgency_of(V, k, t);
     int n_know_i = 0;
     for (int a = 0; a < A; ++a) n_know_i += view_known(V, a, k) ? 1 : 0;
@@ -194,7 +194,7 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
         bool u = k < n && V.k_status()[k] != 2 && V.k_deadline()[k] >= 0;
         if (u) {
           const int ti = V.k_type()[k];
-          u = V.k_alloc2(ti, k) < V.k_cur2(ti, k) && urgency_of(V, k, t) >= urgent_thr;
+          u = V.k_alloc_ti()[k] < V.k_cur_ti()[k] && urgency_of(V, k, t) >= urgent_thr;
         }
         const unsigned m = __ballot_sync(0xffffffffu, u);
         if (a >= 0) n_known_urgent += __popc(vis_none ? m : (m & V.known()[w * A + a]));
@@ -234,7 +234,7 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
         if (V.k_status()[k] == 2) continue;
         if (V.k_deadline()[k] < 0) continue;
         int ti = V.k_type()[k];
-        if (!(V.k_alloc2(ti, k) < V.k_cur2(ti, k))) continue;
+        if (!(V.k_alloc_ti()[k] < V.k_cur_ti()[k])) continue;
         if (!vis_none && !view_known(V, a, k)) continue;
         if (urgency_of(V, k, t) >= urgent_thr) ++n_known_urgent;
       }
@@ -360,7 +360,7 @@ MUAV_HD inline void tokens_escort_env(const View& V, const muav_config& C, int m
       int cnt = 0;
       for (int a = 0; a < A; ++a) cnt += view_in_queue(V, a, k + 1) ? 1 : 0;
       if ((double)(ra != 0 ? ra : 1) - (double)cnt > 0.0) fl = 1;
-    } else if (V.k_alloc2(ti, k) < V.k_cur2(ti, k)) {
+    } else if (V.k_alloc_ti()[k] < V.k_cur_ti()[k]) {
       fl = 1;
     }
     double key = 0.0;
@@ -438,7 +438,7 @@ MUAV_HD inline void tokens_escort_env(const View& V, const muav_config& C, int m
       req_agents = (double)(ra != 0 ? ra : 1);
       rem = dmax(req_agents - (double)cnt, 0.0);
     } else {
-      rem = dmax(V.k_cur2(ti, k) - V.k_alloc2(ti, k), 0.0);
+      rem = dmax(V.k_cur_ti()[k] - V.k_alloc_ti()[k], 0.0);
       req_agents = 1.0;
     }
     double d_spec = mc;

@@ -210,6 +210,7 @@ def pack_records(lib, cfg, scenarios) -> tuple[np.ndarray, np.ndarray]:
     kcur = view("k_cur").reshape(E, 6, TC)
     ee, kk = np.meshgrid(np.arange(E), np.arange(n_tasks0), indexing="ij")
     kcur[ee, ttype, kk] = torg
+    view("k_cur_ti")[:, :n_tasks0] = torg   # hot copy of component [task type] of the requirement vector (muav_layout.h)
     view("k_init")[:] = -1.0
     view("k_dtime")[:] = -1.0
     view("k_deadline")[:] = -1

@@ -36,7 +36,7 @@ int hostcheck_step(const muav_config* cfg, void* records, const uint32_t* tapes,
   int16_t act_agent[MUAV_MAX_AGENTS], act_tid[MUAV_MAX_AGENTS];
   for (int e = 0; e < n_envs; ++e) {
     Sim S;
-    S.V.base = (char*)records + (size_t)e * L.record_bytes;
+    S.V.at((char*)records + (size_t)e * L.record_bytes);
     S.V.set_layout(&L);
     S.Cp = cfg;
     S.tape = tapes + (size_t)e * tape_stride;
@@ -97,7 +97,7 @@ int hostcheck_allocate(const muav_config* cfg, void* records, const muav_alloc_o
   int16_t act_agent[MUAV_MAX_AGENTS], act_tid[MUAV_MAX_AGENTS];
   for (int e = 0; e < n_envs; ++e) {
     Sim S;
-    S.V.base = (char*)records + (size_t)e * L.record_bytes;
+    S.V.at((char*)records + (size_t)e * L.record_bytes);
     S.V.set_layout(&L);
     S.Cp = cfg;
     S.tape = nullptr;
@@ -130,7 +130,7 @@ int hostcheck_tokens_pair(const muav_config* cfg, const void* records, int max_t
   int16_t* cols = (int16_t*)malloc(sizeof(int16_t) * (max_tasks + 2));
   for (int e = 0; e < n_envs; ++e) {
     View V;
-    V.base = (char*)records + (size_t)e * L.record_bytes;
+    V.at((char*)records + (size_t)e * L.record_bytes);
     V.set_layout(&L);
     tokens_pair_env(V, *cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * 13, tm + (size_t)e * max_tasks,
                     af + (size_t)e * max_agents * 12, am + (size_t)e * max_agents, ev + (size_t)e * max_agents * max_tasks,
@@ -147,7 +147,7 @@ int hostcheck_tokens_context(const muav_config* cfg, const void* records, int ma
   const int TD = raw ? 9 : 13, AD = raw ? 11 : 12, CD = raw ? 1 : 8;
   for (int e = 0; e < n_envs; ++e) {
     View V;
-    V.base = (char*)records + (size_t)e * L.record_bytes;
+    V.at((char*)records + (size_t)e * L.record_bytes);
     V.set_layout(&L);
     tokens_pair_env(V, *cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * TD, tm + (size_t)e * max_tasks,
                     af + (size_t)e * max_agents * AD, am + (size_t)e * max_agents, ev + (size_t)e * max_agents * max_tasks,
@@ -164,7 +164,7 @@ int hostcheck_tokens_escort(const muav_config* cfg, const void* records, int max
   EscortTokScratch W = carve_escort_tok(scratch, L.D.TC, max_tasks);
   for (int e = 0; e < n_envs; ++e) {
     View V;
-    V.base = (char*)records + (size_t)e * L.record_bytes;
+    V.at((char*)records + (size_t)e * L.record_bytes);
     V.set_layout(&L);
     tokens_escort_env(V, *cfg, max_tasks, max_agents, tf + (size_t)e * max_tasks * 22, tm + (size_t)e * max_tasks,
                       af + (size_t)e * max_agents * 16, am + (size_t)e * max_agents, ev + (size_t)e * max_agents * max_tasks,
@@ -179,7 +179,7 @@ int hostcheck_observe(const muav_config* cfg, const void* records, int max_rows,
   Layout L = make_layout(*cfg);
   for (int e = 0; e < n_envs; ++e) {
     View V;
-    V.base = (char*)records + (size_t)e * L.record_bytes;
+    V.at((char*)records + (size_t)e * L.record_bytes);
     V.set_layout(&L);
     int32_t nr = 0;
     observe_env(V, *cfg, max_rows, ti + (size_t)e * max_rows * 21, pad + (size_t)e * max_rows,
@@ -193,7 +193,7 @@ int hostcheck_metrics(const muav_config* cfg, const void* records, double* out, 
   Layout L = make_layout(*cfg);
   for (int e = 0; e < n_envs; ++e) {
     View V;
-    V.base = (char*)records + (size_t)e * L.record_bytes;
+    V.at((char*)records + (size_t)e * L.record_bytes);
     V.set_layout(&L);
     metrics_env(V, *cfg, out + (size_t)e * 30);
   }

@@ -400,38 +400,159 @@ def test_scaled_burst_matches_oracle(k):
         assert refsnap.digest(env.codec.snapshot(recs[e])) == refsnap.digest(o.snapshot()), (k, s)
 
 
-def test_obstacle_avoidance_in_the_step_kernel():
-    """core_sim avoid_obstacles inside the kernel (ln / atan2 are not bit-reproducible across libms):
-    positions must agree to 1e-9 while trajectories coincide; discrete outcomes may flip only at near-ties."""
+def test_obstacle_avoidance_in_the_step_kernel(hostcheck):
+    """core_sim avoid_obstacles inside the kernel.  ln / atan2 come from Rust's libm in the reference and from CUDA's
+    math library here (1-2 ulp functions, not bit-reproducible), so obstacle configurations are TOLERANCE parity:
+    while a trajectory coincides with the CPU build of the same source (tests/hostcheck, host libm) the positions agree to
+    1e-9 and every discrete field is identical; a last-bit difference can flip a near-tie (arrival test, rotation sign),
+    after which the episode is a different but valid one.  Every flip is logged (what differed first, when) and the
+    number of flipped episodes is bounded.  The wps_hard_obstacles golden (reference + Rust-equivalent Python shim) is
+    replayed the same way."""
+    import json
     from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
-    from oracle.hungarian import OracleHungarian, apply_assign
-    from oracle.sim import OracleEnv
+    from helpers import alloc_opts_for
 
+    report = []
+    DISCRETE = ("a_state", "a_qlen", "a_queue", "a_ammo", "a_task_start", "k_status", "k_type", "k_counted", "h_status",
+                "h_target", "h_ammo", "n_tasks", "events")
+
+    def lockstep(name, cfg, seeds, advance, n_steps):
+        env = make_env(cfg, seeds, queue_cap=8)
+        host = hostcheck.make(cfg, seeds, queue_cap=8)
+        same = [True] * len(seeds)
+        for t in range(n_steps):
+            advance(env, host, t)
+            recs = env.records.cpu().numpy()
+            for e in range(len(seeds)):
+                if not same[e]:
+                    continue
+                got, want = env.codec.snapshot(recs[e]), host.snapshot(e)
+                bad = [k for k in DISCRETE if k in got and not np.array_equal(got[k], want[k])]
+                if bad:
+                    same[e] = False   # a near-tie flipped: logged here, bounded below
+                    report.append({"case": name, "seed": int(seeds[e]), "step": t, "first_difference": bad})
+                    continue
+                assert np.allclose(got["a_pos"], want["a_pos"], rtol=1e-9, atol=1e-9), (name, e, t)
+                assert np.allclose(got["total_distance"], want["total_distance"], rtol=1e-9)
+        assert int(env.error_flags().abs().max().item()) == 0
+        return same
+
+    # (1) fused Local-Hungarian rollout with four obstacles, CUDA vs the CPU build of the same source
     cfg = wps_config("WPS_hard", num_obstacles=4)
-    seeds = list(range(6))
-    env = make_env(cfg, seeds)
     spec = AllocSpec.local_hungarian(20)
-    oracles = [OracleEnv(cfg).reset(s) for s in seeds]
-    hungs = [OracleHungarian(20, 1200.0) for _ in seeds]
-    assert all(len(o.obstacles) == 4 for o in oracles)
-    same = [True] * len(seeds)
-    moved_by_avoidance = 0
+    O = alloc_opts_for("local_hungarian")
+    # the reference's reset cannot place four obstacles for every seed (DroneEnv.py:1371-1410 raises): first 12 that work
+    from multi_uav_ta_gym_env_b200 import _lib, reset as _rst
+    tw = list(_lib.build_config(cfg).tape_words)
+    good = []
+    for sd in range(200):
+        try:
+            _rst.generate_scenario(cfg, sd, tw)
+            good.append(sd)
+        except ValueError:
+            pass
+        if len(good) == 12:
+            break
+    same1 = lockstep("WPS_hard+4obs local", cfg, good,
+                     lambda env, host, t: (env.step_allocated(spec, 1), host.step_alloc(O, 1)), 150)
+    # (2) the golden episodes recorded from the reference: same ordered actions on both sides
+    eps = load_golden("wps_hard_obstacles")
+    gcfg = golden_config(eps[0])
+    A = sum(gcfg.agents.values())
+
+    def replay(env, host, t):
+        act = np.full((len(eps), A, 2), -1, np.int32)
+        for e, ep in enumerate(eps):
+            for i, (a, idx) in enumerate(ep["steps"][t]["actions"]):
+                act[e, i] = (a, idx)
+        env.step_batched(torch.from_numpy(act))
+        host.step_actions([[tuple(a) for a in ep["steps"][t]["actions"]] for ep in eps])
+
+    same2 = lockstep("wps_hard_obstacles golden", gcfg, [ep["seed"] for ep in eps], replay, len(eps[0]["steps"]))
+    os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "obstacle_flips.json"), "w") as f:
+        json.dump({"episodes": len(same1) + len(same2), "flipped": report}, f, indent=1)
+    print("obstacle flips:", json.dumps(report))
+    # bound: at most a quarter of the episodes may leave the common trajectory (measured: profiles/r02_parity_gaps.md)
+    assert sum(same1) >= len(same1) - len(same1) // 4, report
+    assert sum(same2) >= len(same2) - max(1, len(same2) // 4), report
+
+
+def test_scorer_near_tie_flips_are_logged_and_bounded():
+    """north_star: "any flip caused by a near-tie is logged and bounded".  The fused Att-Pair kernel agrees with the
+    PyTorch module to 2e-5 on scores; scores enter the LSAP cost (HungarianAllocator.py:177), so a near-tie can flip an
+    assignment.  Two copies of a 4096-environment WPS_hard batch run in lock-step over a whole episode: one is scored
+    by csrc/muav_scorer.cu, the other by the reference's arithmetic (AttPairNet forward in torch on the CPU, fp32).
+    While two copies of an environment are still in the same state their replans are compared pair by pair."""
+    import json
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+    from multi_uav_ta_gym_env_b200.scorers import AttPairNet, FusedAttPairScorer, SCORE_CLAMP
+
+    E = int(os.environ.get("MUAV_FLIP_ENVS", "4096"))
+    cfg = wps_config("WPS_hard")
+    seeds = list(range(E))
+    env_k, env_t = make_env(cfg, seeds), make_env(cfg, seeds)
+    torch.manual_seed(0)
+    net_cpu = AttPairNet().eval()
+    net_gpu = AttPairNet().cuda().eval()
+    net_gpu.load_state_dict(net_cpu.state_dict())
+    fused = FusedAttPairScorer(net_gpu, torch.device("cuda"))
+    tok_k = env_k.enable_fused_tokens(32, 16, 15, 0b111)
+    tok_t = env_t.enable_fused_tokens(32, 16, 15, 0b111)
+    env_k.refresh_fused_tokens()
+    env_t.refresh_fused_tokens()
+    sc_k = torch.zeros(E, 16, 32, dtype=torch.float32, device="cuda")
+    sc_t = torch.zeros_like(sc_k)
+    spec = AllocSpec.pair_hybrid(15)
+    same = torch.ones(E, dtype=torch.bool, device="cuda")
+    replans = flips = 0
+    max_dscore = 0.0
+    first = []
     for t in range(150):
-        env.step_allocated(spec, 1)
-        recs = env.records.cpu().numpy()
-        for e, o in enumerate(oracles):
-            o.step(apply_assign(o, hungs[e].allocate(o, time_step=o.t, events=o.last_events, known=o.visibility())))
-            if not same[e]:
-                continue
-            got = env.codec.snapshot(recs[e])
-            want = o.snapshot()
-            if not (np.array_equal(got["a_state"], want["a_state"]) and np.array_equal(got["k_status"], want["k_status"])):
-                same[e] = False  # a near-tie flipped: logged, bounded below
-                continue
-            assert np.allclose(got["a_pos"], want["a_pos"], rtol=1e-9, atol=1e-9), (e, t)
-            assert np.allclose(got["total_distance"], want["total_distance"], rtol=1e-9)
-    assert sum(same) >= 4, same
-    assert int(env.error_flags().abs().max().item()) == 0
+        fused.score(tok_k, sc_k, use_need=True)
+        idx = tok_t["need"].nonzero().flatten()
+        if idx.numel():
+            tf, tm = tok_t["task_feats"][idx].cpu(), tok_t["task_mask_u8"][idx].bool().cpu()
+            af, am = tok_t["agent_feats"][idx].cpu(), tok_t["agent_mask_u8"][idx].bool().cpu()
+            ok = ~(tm.all(1) | am.all(1))     # the allocator returns [] for these whatever the scores are
+            out = torch.zeros(idx.numel(), 16, 32)
+            if ok.any():
+                with torch.no_grad():
+                    logits, _ = net_cpu(tf[ok], tm[ok], af[ok], am[ok])
+                out[ok] = torch.tanh(logits) * SCORE_CLAMP
+            sc_t[idx] = out.cuda() * tok_t["edge_valid"][idx]
+            both = same[idx] & tok_k["need"][idx].bool()
+            if both.any():
+                max_dscore = max(max_dscore, float((sc_t[idx][both] - sc_k[idx][both]).abs().max().item()))
+        env_k.step_allocated(spec, 1, edge_scores=sc_k)
+        env_t.step_allocated(spec, 1, edge_scores=sc_t)
+        planned = same & ((env_k.n_pairs > 0) | (env_t.n_pairs > 0))
+        differ = planned & ((env_k.n_pairs != env_t.n_pairs) | (env_k.pairs != env_t.pairs).any(1))
+        replans += int(planned.sum().item())
+        flips += int(differ.sum().item())
+        for e in differ.nonzero().flatten().tolist()[:4]:
+            if len(first) < 16:
+                first.append({"env": e, "step": t, "kernel": env_k.pairs_of(e), "torch_cpu": env_t.pairs_of(e)})
+        same &= (env_k.records == env_t.records).all(1)
+    mk, mt = env_k.metrics(), env_t.metrics()
+    names = env_k.lib.metric_names()
+    cols = [names.index(n) for n in ("n_on_time", "n_missed_windows", "Kills", "Losses", "n_task_switches")]
+    ep_diff = int((mk[:, cols] != mt[:, cols]).any(1).sum().item())
+    res = {"envs": E, "replans_compared": replans, "replans_with_different_pairs": flips,
+           "flip_rate_per_replan": flips / max(replans, 1), "episodes_with_different_terminal_counters": ep_diff,
+           "episodes_off_the_common_trajectory": int((~same).sum().item()), "max_abs_score_difference": max_dscore,
+           "first_flips": first}
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "scorer_flips.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    print("scorer flips:", json.dumps({k: v for k, v in res.items() if k != "first_flips"}))
+    # measured on B200 (profiles/r02_parity_gaps.md): 110 of 89 434 replans (0.12 %) and 10 of 4096 episodes (0.24 %), at
+    # score differences below 1e-7: exact ties between identical agents at the base decided by the last bit of a score
+    assert max_dscore < 5e-5
+    assert flips <= max(2, replans // 250), res           # bound: <= 0.4 % of the compared replans
+    assert ep_diff <= max(2, E // 100), res               # bound: <= 1 % of the episodes
+    assert int(env_k.error_flags().abs().max().item()) == 0 and int(env_t.error_flags().abs().max().item()) == 0
 
 
 def test_fused_scorer_kernel_matches_torch_module():
@@ -555,9 +676,11 @@ def test_largest_shape_burst_x8():
     assert refsnap.digest(env.snapshot(0)) == refsnap.digest(o.snapshot())
 
 
-@pytest.mark.parametrize("case,planner", [("WPS_hard", "local"), ("WPS_commit", "urgency_commit"), ("WPS_escort", "urgency_coalition")])
+@pytest.mark.parametrize("case,planner", [("WPS_hard", "local"), ("WPS_commit", "urgency_commit"), ("WPS_escort", "urgency_coalition"),
+                                          ("WPS_escort", "coalition")])
 def test_random_members_of_a_large_batch_match_the_oracle(case, planner):
-    """Full-size batches (2048 / 4096 envs, one 150-step launch); a random sample of members is re-run on the oracle."""
+    """BASELINE.json's full batch sizes (config 2: 4096 WPS_hard, config 3: 16 384 WPS_commit, config 4: 8192 WPS_escort
+    environments; one 150-step launch); a random sample of members is re-run on the oracle."""
     from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
     from oracle.hungarian import OracleHungarian, apply_assign
     from oracle import planners as oplan
@@ -565,20 +688,20 @@ def test_random_members_of_a_large_batch_match_the_oracle(case, planner):
     from oracle.sim import OracleEnv
 
     cfg = wps_config(case)
-    E = 4096 if case != "WPS_escort" else 2048
+    E = {"WPS_hard": 4096, "WPS_commit": 16384, "WPS_escort": 8192}[case]
     base = 50_000
     env = make_env(cfg, list(range(base, base + E)))
     spec = {"local": AllocSpec.local_hungarian(20), "urgency_commit": AllocSpec.urgency_commit(15),
-            "urgency_coalition": AllocSpec.urgency_coalition(12)}[planner]
+            "urgency_coalition": AllocSpec.urgency_coalition(12), "coalition": AllocSpec.coalition_hungarian(12)}[planner]
     env.step_allocated(spec, n_steps=150)
     assert int(env.error_flags().abs().max().item()) == 0
     rng = np.random.default_rng(7)
     for e in sorted(rng.choice(E, size=10, replace=False).tolist()):
         o = OracleEnv(cfg).reset(base + e)
-        h = OracleHungarian(10**9 if planner == "urgency_coalition" else 20, 1200.0)
+        h = OracleHungarian(10**9 if planner == "urgency_coalition" else (12 if planner == "coalition" else 20), 1200.0)
         for _ in range(150):
             pairs = []
-            if planner == "local":
+            if planner in ("local", "coalition"):
                 pairs = h.allocate(o, time_step=o.t, events=o.last_events, known=o.visibility())
             elif planner == "urgency_commit":
                 if otok.hybrid_should_replan(o, o.last_events, 15):
@@ -925,14 +1048,15 @@ def test_two_kernel_split_step_gives_the_same_states(monkeypatch):
     cfg = wps_config("WPS_hard")
     seeds = list(range(40))
     one = make_env(cfg, seeds)
-    monkeypatch.setenv("MUAV_SPLIT_STEP", "1")
     two = make_env(cfg, seeds)
-    assert two._actions_ws is not None and one._actions_ws is None
+    assert two._actions_ws is not None
     for spec in (AllocSpec.local_hungarian(20), AllocSpec.urgency_pair(15)):
         one.restore()
         two.restore()
         for t in range(150):
+            monkeypatch.setenv("MUAV_SPLIT_STEP", "0")   # the library reads the switch at every launch
             one.step_allocated(spec, 1)
+            monkeypatch.setenv("MUAV_SPLIT_STEP", "1")
             two.step_allocated(spec, 1)
             if t % 10 == 9 or t == 149:
                 assert torch.equal(one.records, two.records), t
