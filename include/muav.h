@@ -51,7 +51,7 @@ extern "C" {
 #define MUAV_N_TASK_TYPES 6 /* Hold Rec Att Def Int Det (MultiDroneEnvData.py:18) */
 #define MUAV_MAX_GROUPS 8
 #define MUAV_MAX_AGENTS 64
-#define MUAV_MAX_TASK_CAP 512 /* task slots (open or still referenced tasks) */
+#define MUAV_MAX_TASK_CAP 640 /* task slots (open or still referenced tasks) */
 #define MUAV_MAX_ID_CAP 2048  /* tasks ever created in one episode */
 #define MUAV_MAX_QUEUE 32
 
