@@ -274,10 +274,17 @@ def run_gpu_arm(args):
             raise SystemExit("--global-envs must be a multiple of the number of GPUs")
         E = args.global_envs // world
         scaling = "strong"
-    # task slots per environment: the library default is the provable bound (every task that could ever be created, 48
-    # for WPS_hard).  With slot recycling at most 24 are alive at once over 4096 seeds x 150 steps; --task-cap 32 gives
-    # 15 instead of 12 environments per SM but no measurable gain in this bench, so the default stays the safe one.
-    task_cap = args.task_cap if args.task_cap > 0 else None
+    # Task slots per environment.  The library default is the provable bound (every task that could ever be created: 48
+    # for WPS_hard); with slot recycling at most 24 are alive at once over 4096 seeds x 150 steps, so the WPS_hard
+    # workloads run with 32 slots (16 instead of 12 resident environments per SM, step kernel 0.112 -> 0.099 ms,
+    # profiles/r02_step_kernel.md).  A slot overflow would set the sticky ERR_TASK_OVERFLOW bit: `error_flags` in the
+    # output line must be (and is) 0.  --task-cap -1 runs the library default.
+    if args.task_cap > 0:
+        task_cap = args.task_cap
+    elif args.task_cap == 0 and wl in ("hard_pair", "hard_local", "hard_pi"):
+        task_cap = 32
+    else:
+        task_cap = None
     seeds = list(sharding.shard_range(E, rank))
     if args.unique_seeds > 0:
         # big sweeps: scenario generation on the host is the slow part (10 ms per 64-agent environment), so the shard
@@ -580,7 +587,9 @@ def main():
     ap.add_argument("--workload", default="hard_pair",
                     help="hard_pair (default, BASELINE config 2) | hard_local | commit_urgency | escort_coalition | burst_xK "
                          "| attn_context | hard_pi | escort_pi")
-    ap.add_argument("--task-cap", type=int, default=0, help="task slots per environment (0 = workload default)")
+    ap.add_argument("--task-cap", type=int, default=0,
+                    help="task slots per environment (0 = workload default: 32 for WPS_hard, else the library's bound; "
+                         "-1 = always the library's provable bound)")
     ap.add_argument("--unique-seeds", type=int, default=0,
                     help="cycle through this many distinct scenario seeds (0 = one seed per environment)")
     ap.add_argument("--global-envs", type=int, default=0,

@@ -113,8 +113,14 @@ __global__ void __launch_bounds__(MUAV_LB_THREADS, MUAV_LB_BLOCKS) muav_step_ker
   const Layout& L = P.L;
 #endif
   // shared-memory slot of this warp's environment: [hot record | scratch | ordered action list]
-  // (a launch may stage the cold part as well, P.stage_bytes == record_bytes: small records, many allocator updates)
+  // (a launch may stage the cold part as well, stage_bytes == record_bytes: small records, many allocator updates.  The
+  // specialised instantiations fix the choice at compile time -- MUAV_STAGE_COLD_FIXED -- so that the compiler knows
+  // whether a cold access is a shared-memory or a global one and that it cannot alias the hot part)
+#if defined(MUAV_STAGE_COLD_FIXED)
+  const int stage_bytes = MUAV_STAGE_COLD_FIXED ? L.record_bytes : L.hot_bytes;
+#else
   const int stage_bytes = P.stage_bytes;
+#endif
   const int slot_bytes = stage_bytes + P.scratch_launch + L.act_bytes;
   char* rec = (char*)smem + (size_t)w * slot_bytes;
   char* scratch = rec + stage_bytes;
@@ -174,7 +180,11 @@ __global__ void __launch_bounds__(MUAV_LB_THREADS, MUAV_LB_BLOCKS) muav_step_ker
 
   Sim S;
   S.V.base = rec;     // hot part: shared memory
-  S.V.cbase = stage_bytes > L.hot_bytes ? rec : grec;   // cold part: staged too, or in place in HBM (muav_layout.h)
+#if defined(MUAV_STAGE_COLD_FIXED)
+  S.V.cbase = MUAV_STAGE_COLD_FIXED ? rec : grec;       // cold part: staged too, or in place in HBM (muav_layout.h)
+#else
+  S.V.cbase = stage_bytes > L.hot_bytes ? rec : grec;
+#endif
   S.V.set_layout(&L);
   S.Cp = &P.cfg;
   S.tape = P.tapes + (size_t)(has_env ? e : 0) * P.tape_stride;
@@ -548,12 +558,13 @@ struct StepInst {
   int (*occ)(int, size_t);
   void (*shape)(int*);  // null: any shape
   int escort;           // value of cfg.escort_enabled this instantiation was compiled for
+  int stage_cold;       // MUAV_STAGE_COLD_FIXED of the instantiation: 1 whole record staged, 0 hot part only
 };
 static const StepInst kStepInst[] = {
-    {muav_step_hard_launch, muav_step_hard_occ, muav_step_hard_shape, 0},
-    {muav_step_hard32_launch, muav_step_hard32_occ, muav_step_hard32_shape, 0},
-    {muav_step_lean_launch, muav_step_lean_occ, nullptr, 0},
-    {muav_step_lean_escort_launch, muav_step_lean_escort_occ, nullptr, 1},
+    {muav_step_hard_launch, muav_step_hard_occ, muav_step_hard_shape, 0, 1},
+    {muav_step_hard32_launch, muav_step_hard32_occ, muav_step_hard32_shape, 0, 1},
+    {muav_step_lean_launch, muav_step_lean_occ, nullptr, 0, 0},
+    {muav_step_lean_escort_launch, muav_step_lean_escort_occ, nullptr, 1, 0},
 };
 
 // general kernel of this translation unit: same two services
@@ -662,7 +673,10 @@ static int launch_step(StepParams& P, void* stream) {
   // shared-memory accesses.  Measured on B200 (profiles/r02_step_kernel.md): while the whole record still leaves >= 12
   // environments per SM (WPS_easy / hard / burst) staging everything is ~15 % faster; for the larger records (WPS_commit,
   // WPS_escort, the scaled bursts) the residency of the hot-only slot wins by 20-40 %.  MUAV_STAGE_COLD=0 / 1 forces it.
-  {
+  // The specialised instantiations carry the answer for their family; the general kernel decides at run time.
+  if (inst) {
+    P.stage_bytes = inst->stage_cold ? P.L.record_bytes : P.L.hot_bytes;
+  } else {
     P.stage_bytes = P.L.record_bytes;
     int envs_full = 0;
     choose_width(inst, slot_bytes_of(P), &envs_full);
@@ -747,11 +761,14 @@ int muav_step(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, 
       split = atoi(fs) != 0;
     } else {
       StepParams Pf = P, Ps = P;
-      Pf.stage_bytes = Ps.stage_bytes = P.L.hot_bytes;
       Ps.opts.mode = 0;
+      const StepInst* inf = pick_inst(Pf);
+      const StepInst* ins = pick_inst(Ps);
+      Pf.stage_bytes = (inf && inf->stage_cold) ? P.L.record_bytes : P.L.hot_bytes;
+      Ps.stage_bytes = (ins && ins->stage_cold) ? P.L.record_bytes : P.L.hot_bytes;
       int envs_f = 0, envs_s = 0;
-      choose_width(pick_inst(Pf), slot_bytes_of(Pf), &envs_f);
-      choose_width(pick_inst(Ps), slot_bytes_of(Ps), &envs_s);
+      choose_width(inf, slot_bytes_of(Pf), &envs_f);
+      choose_width(ins, slot_bytes_of(Ps), &envs_s);
       split = envs_f > 0 && 2 * envs_s >= 3 * envs_f;
     }
   }

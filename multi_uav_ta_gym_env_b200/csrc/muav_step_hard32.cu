@@ -9,6 +9,7 @@
 #define MUAV_LB_THREADS 256
 #define MUAV_LB_BLOCKS 2
 #endif
+#define MUAV_STAGE_COLD_FIXED 1   // the whole record is staged: 8-agent records are small (launch_step, muav_kernels.cu)
 #define MUAV_STEP_ONLY 1
 #define MUAV_STEP_LAUNCHER muav_step_hard32_launch
 #define MUAV_STEP_STATIC_SMEM muav_step_hard32_static_smem

@@ -7,6 +7,7 @@
 #define MUAV_LB_THREADS 384
 #define MUAV_LB_BLOCKS 2
 #endif
+#define MUAV_STAGE_COLD_FIXED 0   // only the hot part of the record is staged: residency first (launch_step, muav_kernels.cu)
 #define MUAV_STEP_ONLY 1
 #define MUAV_STEP_LAUNCHER muav_step_lean_escort_launch
 #define MUAV_STEP_STATIC_SMEM muav_step_lean_escort_static_smem

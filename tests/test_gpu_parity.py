@@ -1089,3 +1089,79 @@ def test_lean_and_general_step_kernels_agree(case, interval, monkeypatch):
     general.step_allocated(spec, 90)
     assert torch.equal(lean.records, general.records)
     assert int(lean.error_flags().abs().max().item()) == 0
+
+
+def test_bench_task_cap_32_is_bit_identical_to_the_library_default():
+    """bench.py runs the WPS_hard workloads with 32 task slots (fixed-shape instantiation muav_step_hard32.cu, 16 resident
+    environments per SM) instead of the provable bound of 48.  Slots are recycled, ids are not: the episode must be the
+    same bit for bit on all 4096 seeds (metrics of every environment, canonical digests of a sample) and no capacity bit
+    may be set."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+
+    cfg = wps_config("WPS_hard")
+    E = 4096
+    big, small = make_env(cfg, list(range(E))), make_env(cfg, list(range(E)), task_cap=32)
+    assert big.task_cap == 48 and small.task_cap == 32 and small.record_bytes < big.record_bytes
+    spec = AllocSpec.local_hungarian(20)
+    for _ in range(5):
+        big.step_allocated(spec, n_steps=30)
+        small.step_allocated(spec, n_steps=30)
+        assert torch.equal(big.reward, small.reward)
+    assert int(small.error_flags().abs().max().item()) == 0 and int(big.error_flags().abs().max().item()) == 0
+    assert torch.equal(big.metrics(), small.metrics())
+    assert int(small.header_int("N_SLOTS_USED").max().item()) <= 32
+    for e in range(0, E, 293):
+        assert refsnap.digest(big.snapshot(e)) == refsnap.digest(small.snapshot(e)), e
+
+
+def test_two_handles_two_threads():
+    """Host-buffer entry points are re-entrant: two environment batches, each with its own muav_ctx handle and CUDA stream,
+    are driven concurrently from two threads (ctypes releases the GIL inside the calls); both must reproduce the
+    single-threaded device path bit for bit.  The handle-free muav_step_host (stream-ordered staging) is checked too."""
+    import threading
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+
+    cfg = wps_config("WPS_hard")
+    E, K = 256, 60
+    spec = AllocSpec.local_hungarian(20)
+    ref = make_env(cfg, list(range(E)))
+    want = []
+    for _ in range(K):
+        ref.step_allocated(spec, 1)
+        want.append(ref.reward.clone())
+    want_rec = ref.records.clone()
+    envs = [make_env(cfg, list(range(E))) for _ in range(2)]
+    errs = []
+
+    def drive(env, handle_free):
+        try:
+            stream = torch.cuda.Stream()
+            A = env.n_agents
+            h_act = torch.empty(E, A, 2, dtype=torch.int32).pin_memory()
+            h_rew = torch.empty(E, dtype=torch.float64).pin_memory()
+            h_t = torch.empty(E, dtype=torch.uint8).pin_memory()
+            h_u = torch.empty(E, dtype=torch.uint8).pin_memory()
+            with torch.cuda.stream(stream):
+                for t in range(K):
+                    env.allocate_host(spec, h_act)
+                    if handle_free:
+                        rc = env.lib.dll.muav_step_host(C.byref(env.cfg), env.records.data_ptr(), env.tapes.data_ptr(),
+                                                        h_act.data_ptr(), None, None, h_rew.data_ptr(), h_t.data_ptr(),
+                                                        h_u.data_ptr(), E, 1, C.c_void_p(stream.cuda_stream), None, None)
+                        assert rc == 0
+                    else:
+                        env.step_host(h_act, h_rew, h_t, h_u, 1, hint=spec)
+                    assert torch.equal(h_rew, want[t].cpu()), t
+                stream.synchronize()
+        except Exception as ex:  # surfaced in the main thread
+            errs.append(repr(ex))
+
+    th = [threading.Thread(target=drive, args=(envs[0], False)), threading.Thread(target=drive, args=(envs[1], True))]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    assert envs[0]._ctx is not None and envs[0]._ctx.value != (envs[1]._host_ctx().value)
+    for env in envs:
+        assert torch.equal(env.records, want_rec)
