@@ -78,3 +78,81 @@ class RLCollector(_Base):
         mt, ma = tokens["edge_valid"].shape[2], tokens["edge_valid"].shape[1]
         return {"tokens": tokens, "scores": scores, "selected": selected, "reward": reward, "planned": planned,
                 "next_tokens": env.tokens_pair(mt, ma), "done": done}
+
+
+def _planned_mask(env: BatchedMultiUAVEnv, interval: int, event_mask: int) -> torch.Tensor:
+    """`should` of the commit / escort trainers (train_att_commit.py:36-45, train_escort.py:35-50): t == 0, t % 12 == 0
+    or an event with one of the listed tags since the last step; evaluated for every environment on the device."""
+    t = env.header_int("T")
+    tags = env.header_int("EV_TAGMASK")
+    done = env.header_int("DONE")
+    return ((t == 0) | (t % interval == 0) | ((tags & event_mask) != 0)) & (done == 0)
+
+
+class CommitCollector:
+    """run_episode of experiments/train_att_commit.py:28-75 for a whole batch: tokens (enrich_commit_tokens), the
+    policy's (priorities, commits) drive AttentionCommit._plan_from_scores on the device (AllocSpec.att_commit, cadence 12),
+    reward (S_WPS' - S_WPS) / 20, next tokens, done.  Transitions are the rows with planned == 1."""
+
+    INTERVAL = 12
+
+    def __init__(self, env: BatchedMultiUAVEnv, max_tasks=32, max_agents=16):
+        self.env, self.mt, self.ma = env, max_tasks, max_agents
+        self._s_wps = env.lib.metric_names().index("S_WPS")
+        self.spec = AllocSpec.att_commit(self.INTERVAL)
+        self.reset()
+
+    def reset(self):
+        self.env.restore()
+
+    def score(self) -> torch.Tensor:
+        return self.env.metrics()[:, self._s_wps]
+
+    def step(self, act_fn):
+        """act_fn(tokens) -> (priorities f32 [E, max_tasks], commits f32 [E, max_agents]) (exploration is the caller's)."""
+        env = self.env
+        planned = _planned_mask(env, self.INTERVAL, HYBRID_EVENTS)
+        tokens = env.tokens_commit(self.mt, self.ma)
+        s_prev = self.score()
+        pri, com = act_fn(tokens)
+        env.step_allocated(self.spec, 1, plan_pri=pri, plan_commit=com)
+        reward = (self.score() - s_prev) / torch.full_like(s_prev, 20.0)
+        done = (env.terminated | env.truncated).clone()
+        return {"tokens": tokens, "pri": pri, "com": com, "reward": reward, "planned": planned.to(torch.uint8),
+                "next_tokens": env.tokens_commit(self.mt, self.ma), "done": done}
+
+
+class EscortCollector:
+    """run_episode of experiments/train_escort.py:28-82 for a whole batch: build_escort_tokens, the policy's edge scores
+    (sigmoid of noisy logits on valid edges, AttentionEscort.act :444-470) drive AttentionEscort._plan_from_scores on the
+    device (AllocSpec.att_escort, cadence 12, every event tag), reward (S_ESC' - S_ESC) / 20, selected-edge mask of the
+    plan, next tokens, done."""
+
+    INTERVAL = 12
+
+    def __init__(self, env: BatchedMultiUAVEnv, max_tasks=48, max_agents=16):
+        self.env, self.mt, self.ma = env, max_tasks, max_agents
+        self._s_esc = env.lib.metric_names().index("S_ESC")
+        self.spec = AllocSpec.att_escort(self.INTERVAL)
+        self.reset()
+
+    def reset(self):
+        self.env.restore()
+
+    def score(self) -> torch.Tensor:
+        return self.env.metrics()[:, self._s_esc]
+
+    def step(self, act_fn):
+        """act_fn(tokens) -> (scores [E, A, T], noise [E, A, T], logits [E, A, T])."""
+        env = self.env
+        planned = _planned_mask(env, self.INTERVAL, 0x1F)
+        tokens = env.tokens_escort(self.mt, self.ma)
+        s_prev = self.score()
+        scores, noise, logits = act_fn(tokens)
+        env.step_allocated(self.spec, 1, edge_scores=scores, task_order=tokens["task_order"])
+        selected = env.pair_mask(tokens, require_valid=False)   # AttentionEscort._selected_mask == PairCostHybrid's
+        reward = (self.score() - s_prev) / torch.full_like(s_prev, 20.0)
+        done = (env.terminated | env.truncated).clone()
+        return {"tokens": tokens, "scores": scores, "noise": noise, "logits": logits, "selected": selected,
+                "reward": reward, "planned": planned.to(torch.uint8), "next_tokens": env.tokens_escort(self.mt, self.ma),
+                "done": done}

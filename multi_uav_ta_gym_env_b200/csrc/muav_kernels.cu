@@ -722,7 +722,7 @@ int muav_step(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, 
   if (opts) P.opts = *opts;
   if (out) P.out = *out;
   if (tok) {
-    if (tok->max_tasks < 1 || tok->max_agents < 1 || tok->max_tasks > cfg->task_cap) return -22;
+    if (tok->max_tasks < 1 || tok->max_agents < 1 || tok->max_tasks > (cfg->task_cap > 64 ? cfg->task_cap : 64)) return -22;
     P.tok = *tok;
   }
   P.records = (char*)d_records;

@@ -226,7 +226,9 @@ MUAV_HD constexpr inline Layout make_layout_dims(const Dims D) {
   if (s2 > s) s = s2;
   L.scratch_bytes = align_up(s, 16);
   // launches that do not run the allocator only need the step's temporaries (+ the token builder's column list)
-  int32_t s3 = s2 + 2 * (D.TC + 4);
+  // (the fused token emission keeps its column list here: room for max(TC, 64) columns, so that the standalone and
+  // the fused builders accept the same max_tasks)
+  int32_t s3 = s2 + 2 * ((D.TC > 64 ? D.TC : 64) + 4);
   L.step_scratch_bytes = align_up(s3, 16);
   if (L.step_scratch_bytes > L.scratch_bytes) L.step_scratch_bytes = L.scratch_bytes;
   int32_t s4 = alloc_scratch_bytes(D.A, D.TC, false);

@@ -1165,3 +1165,92 @@ def test_two_handles_two_threads():
     assert envs[0]._ctx is not None and envs[0]._ctx.value != (envs[1]._host_ctx().value)
     for env in envs:
         assert torch.equal(env.records, want_rec)
+
+
+def test_commit_and_escort_collectors_match_the_oracle_and_trainers_run():
+    """collectors.CommitCollector / EscortCollector (run_episode of experiments/train_att_commit.py:28-75
+    and train_escort.py:28-82) in lock-step with the oracle: planned flags (cadence 12 + event tags), transitions' rewards
+    (delta S_WPS / 20, delta S_ESC / 20), the selected-edge mask, next tokens; then a few optimiser steps of every
+    trainer of multi_uav_ta_gym_env_b200.training on the batched environment (finite losses, parameters move)."""
+    from multi_uav_ta_gym_env_b200 import wps_config
+    from multi_uav_ta_gym_env_b200.collectors import CommitCollector, EscortCollector
+    from multi_uav_ta_gym_env_b200 import scorers as S, training as T
+    from oracle.hungarian import OracleHungarian, apply_assign
+    from oracle import planners as oplan
+    from oracle import tokens as otok
+    from oracle.sim import OracleEnv
+
+    def should(o, tags):
+        return o.t == 0 or o.t % 12 == 0 or any(ev[0] in tags for ev in o.last_events)
+
+    # ---- Att-Commit
+    cfg = wps_config("WPS_commit")
+    seeds = [41, 42]
+    col = CommitCollector(make_env(cfg, seeds))
+    torch.manual_seed(0)
+    net = S.AttCommitNet().cuda().eval()
+    oracles = [OracleEnv(cfg).reset(s) for s in seeds]
+    hungs = [OracleHungarian(10**9, 1200.0) for _ in seeds]
+    act = lambda tok: S.commit_vectors(net, tok)
+    for t in range(60):
+        tr = col.step(act)
+        hp, hc = tr["pri"].cpu().numpy(), tr["com"].cpu().numpy()
+        rew, pl = tr["reward"].cpu().numpy(), tr["planned"].cpu().numpy()
+        nxt = {k: v.cpu().numpy() for k, v in tr["next_tokens"].items()}
+        for e, o in enumerate(oracles):
+            s_prev = o.compute_s_wps()
+            go = should(o, ("Reset_Allocation", "New_Threat", "Agent_Fail"))
+            assert bool(pl[e]) == go, (t, e)
+            pairs = oplan.att_commit_plan_from_scores(o, hungs[e], hp[e], hc[e], 0.5) if go else []
+            o.step(apply_assign(o, pairs))
+            assert rew[e] == (o.compute_s_wps() - s_prev) / 20.0, (t, e)
+            want = otok.commit_tokens(o, 32, 16)
+            for k in ("task_feats", "task_mask", "agent_feats", "agent_mask"):
+                assert np.array_equal(nxt[k][e], want[k]), (t, e, k)
+    # ---- Att-Coalition
+    cfg = wps_config("WPS_escort")
+    col = EscortCollector(make_env(cfg, seeds))
+    torch.manual_seed(0)
+    enet = S.AttCoalitionNet().cuda().eval()
+    oracles = [OracleEnv(cfg).reset(s) for s in seeds]
+    hungs = [OracleHungarian(10**9, 1200.0) for _ in seeds]
+
+    def eact(tok):
+        sc = S.coalition_scores(enet, tok)
+        return sc, torch.zeros_like(sc), sc
+    for t in range(50):
+        tr = col.step(eact)
+        sc, rew, pl = tr["scores"].cpu().numpy(), tr["reward"].cpu().numpy(), tr["planned"].cpu().numpy()
+        sel = tr["selected"].cpu().numpy()
+        for e, o in enumerate(oracles):
+            s_prev = o.compute_s_esc()
+            go = should(o, ("Reset_Allocation", "New_Threat", "Agent_Fail", "Escort_Created", "Escort_Retired"))
+            assert bool(pl[e]) == go, (t, e)
+            pairs = []
+            if go:
+                tok = otok.build_escort_tokens(o, 48, 16)
+                pairs = oplan.att_escort_plan_from_scores(o, hungs[e], sc[e])
+                assert np.array_equal(sel[e], otok.pair_mask(tok, pairs, False)), (t, e)
+            o.step(apply_assign(o, pairs))
+            assert rew[e] == (o.compute_s_esc() - s_prev) / 20.0, (t, e)
+    # ---- the four trainers, a few updates each on a small batch
+    def moved(net0, net1):
+        return any(not torch.equal(a, b) for a, b in zip(net0.values(), net1.state_dict().values()))
+
+    hard = make_env(wps_config("WPS_hard"), list(range(64)))
+    hard.cfg.max_time_steps = 150
+    pnet = S.AttPairNet().cuda()
+    before = {k: v.clone() for k, v in pnet.state_dict().items()}
+    losses = T.train_pair_il(hard, pnet, episodes=1)
+    assert len(losses) > 5 and all(np.isfinite(losses)) and moved(before, pnet)
+    before = {k: v.clone() for k, v in pnet.state_dict().items()}
+    losses = T.train_pair_rl(make_env(wps_config("WPS_hard"), list(range(64))), pnet, episodes=1)
+    assert len(losses) > 5 and all(np.isfinite(losses)) and moved(before, pnet)
+    cnet = S.AttCommitNet().cuda()
+    before = {k: v.clone() for k, v in cnet.state_dict().items()}
+    losses = T.train_att_commit(make_env(wps_config("WPS_commit"), list(range(32))), cnet, episodes=1)
+    assert len(losses) > 5 and all(np.isfinite(losses)) and moved(before, cnet)
+    xnet = S.AttCoalitionNet().cuda()
+    before = {k: v.clone() for k, v in xnet.state_dict().items()}
+    losses = T.train_escort(make_env(wps_config("WPS_escort"), list(range(32))), xnet, episodes=1)
+    assert len(losses) > 5 and all(np.isfinite(losses)) and moved(before, xnet)
