@@ -1180,7 +1180,10 @@ def test_commit_and_escort_collectors_match_the_oracle_and_trainers_run():
     from oracle import tokens as otok
     from oracle.sim import OracleEnv
 
-    def should(o, tags):
+    TAG = {"Reset_Allocation": 0, "Agent_Fail": 1, "New_Threat": 2, "Escort_Created": 3, "Escort_Retired": 4}   # oracle tags
+
+    def should(o, names):
+        tags = [TAG[n] for n in names]
         return o.t == 0 or o.t % 12 == 0 or any(ev[0] in tags for ev in o.last_events)
 
     # ---- Att-Commit
