@@ -61,7 +61,7 @@ def main():
         if not cands:
             continue
         col = ix[cands[0]]
-        unit = rows[1][col].lower()
+        unit = rows[1][col].lower().split("/")[0]
         # the raw page states each column's unit: normalise to the unit the label promises
         to_base = {"nsecond": 1e-9, "ns": 1e-9, "usecond": 1e-6, "us": 1e-6, "msecond": 1e-3, "ms": 1e-3, "second": 1.0,
                    "s": 1.0, "byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
