@@ -154,6 +154,13 @@ def run_episode(case, seed, driver, overrides=None):
     elif driver in ("local_pi", "pi_coalition"):
         from TaskAllocation.MarketBased.PerformanceImpact import PerformanceImpact
         planner = PerformanceImpact(max_coord=env.max_coord, seed=seed, replan_interval=20 if driver == "local_pi" else 12)
+    elif driver in ("cbba_replan", "cbba_coalition"):
+        # Local-CBBA-Replan (wps_eval.py:105,134-146) / Local-CBBA-Coalition (escort_eval.py:108-112,149-161).  CBBA's
+        # auction order starts from a set of strings: reproducible only with the string hash pinned
+        assert os.environ.get("PYTHONHASHSEED") == "0", "generate the CBBA fixtures with PYTHONHASHSEED=0"
+        from TaskAllocation.MarketBased.CBBA_Replan import CBBAReplan
+        planner = CBBAReplan(env.agents_obj, env.tasks, env.max_coord, seed=seed,
+                             replan_interval=20 if driver == "cbba_replan" else 12)
     n_plans = 0
     rnd = random.Random(seed * 7919 + 13)
     ep = {"case": case, "seed": seed, "driver": driver, "overrides": overrides or {},
@@ -175,6 +182,10 @@ def run_episode(case, seed, driver, overrides=None):
             res = planner.allocate_tasks(env.get_live_agents(), ref_open_tasks(env), time_step=env.time_steps, events=events,
                                          agent_known_ids=env.agent_visibility_map(), max_tasks_per_agent=1)
             pairs = [(name, task) for name, tl in res for task in tl]   # _flatten_pairs (wps_eval.py:40-52)
+        elif driver in ("cbba_replan", "cbba_coalition"):
+            res = planner.allocate_tasks(env.get_live_agents(), ref_open_tasks(env), time_step=env.time_steps, events=events,
+                                         agent_known_ids=env.agent_visibility_map(), max_tasks_per_agent=1)
+            pairs = [(name, task) for name, tl in res for task in tl]
         elif driver == "pair_injected":
             if hybrid_should_replan(env, events):
                 sc = injected_scores(seed, env.time_steps, pair.max_agents, pair.max_tasks)
@@ -249,7 +260,8 @@ def run_episode(case, seed, driver, overrides=None):
             break
     m = info["metrics"]
     ep["metrics"] = {k: (fhex(v) if isinstance(v, (float, np.floating)) else int(v)) for k, v in m.items()}
-    ep["n_replans"] = int(planner.n_replans if driver in ("local_pi", "pi_coalition") else hung.n_replans)
+    ep["n_replans"] = int(planner.n_replans if driver in ("local_pi", "pi_coalition", "cbba_replan", "cbba_coalition")
+                          else hung.n_replans)
     return ep
 
 
@@ -277,6 +289,10 @@ PLAN = [
     ("wps_hard_pi", "WPS_hard", "local_pi", range(0, 8), None),
     ("wps_commit_pi", "WPS_commit", "local_pi", range(0, 4), None),
     ("wps_escort_pi", "WPS_escort", "pi_coalition", range(0, 4), None),
+    # CBBA: run this script with PYTHONHASHSEED=0 (set-of-strings iteration order, CBBA.py:116,128)
+    ("wps_hard_cbba", "WPS_hard", "cbba_replan", range(0, 6), None),
+    ("wps_commit_cbba", "WPS_commit", "cbba_replan", range(0, 3), None),
+    ("wps_escort_cbba", "WPS_escort", "cbba_coalition", range(0, 3), None),
 ]
 
 

@@ -12,6 +12,7 @@ from oracle.hungarian import OracleHungarian, apply_assign, open_tasks
 from oracle.sim import OracleEnv
 from oracle import tokens as otok
 from oracle import planners as oplan
+from oracle.cbba import OracleCBBAReplan
 from oracle.market import OraclePI
 
 # (fixture, max episodes replayed on CPU -- keeps the CPU suite short; the GPU suite replays all)
@@ -22,6 +23,7 @@ CASES = [
     ("wps_commit_urgency", 3), ("wps_escort_urgency", 2), ("wps_hard_obstacles", 2),
     ("wps_hard_urgency_pair", 3), ("wps_attn_context", 2), ("wps_commit_attcommit", 3), ("wps_escort_attescort", 3),
     ("wps_hard_pi", 4), ("wps_commit_pi", 2), ("wps_escort_pi", 2),
+    ("wps_hard_cbba", 6), ("wps_commit_cbba", 3), ("wps_escort_cbba", 3),
 ]
 
 
@@ -33,6 +35,7 @@ def replay(ep):
     interval = 12 if drv == "coalition" else (10**9 if drv in ("urgency_coalition", "att_escort_injected") else 20)
     hung = OracleHungarian(interval, o.max_coord)
     pi = OraclePI(o.max_coord, ep["seed"], 12 if drv == "pi_coalition" else 20)
+    cbba = OracleCBBAReplan(o.max_coord, ep["seed"], 12 if drv == "cbba_coalition" else 20)
     for t, st in enumerate(ep["steps"]):
         if drv in ("local_hungarian", "coalition", "global_hungarian"):
             known = None if drv == "global_hungarian" else o.visibility()
@@ -41,6 +44,10 @@ def replay(ep):
             assert [list(a) for a in apply_assign(o, pairs)] == st["actions"], (ep["seed"], t)
         elif drv in ("local_pi", "pi_coalition"):
             pairs = pi.allocate(o, time_step=o.t, events=o.last_events, known=o.visibility())
+            assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
+            assert [list(a) for a in apply_assign(o, pairs)] == st["actions"], (ep["seed"], t)
+        elif drv in ("cbba_replan", "cbba_coalition"):
+            pairs = cbba.allocate(o, time_step=o.t, events=o.last_events, known=o.visibility())
             assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
             assert [list(a) for a in apply_assign(o, pairs)] == st["actions"], (ep["seed"], t)
         elif drv in ("pair_injected", "context_injected"):
@@ -101,6 +108,8 @@ def replay(ep):
         assert m[k] == want or (m[k] != m[k] and want != want), k
     if drv in ("local_hungarian", "coalition", "global_hungarian"):
         assert hung.n_replans == ep["n_replans"]
+    if drv in ("cbba_replan", "cbba_coalition"):
+        assert cbba.n_replans == ep["n_replans"]
     if drv in ("local_pi", "pi_coalition"):
         assert pi.n_replans == ep["n_replans"]
 
