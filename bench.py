@@ -250,6 +250,12 @@ def run_gpu_arm(args):
     elif wl == "hard_pi":
         case_name, cfg, spec = CASE, wps_config(CASE), AllocSpec.performance_impact(20)
         desc = "Local-PI market allocator (PerformanceImpact, max_tasks_per_agent=1) interval 20 (no scorer)"
+    elif wl == "hard_cbba":
+        case_name, cfg, spec = CASE, wps_config(CASE), AllocSpec.cbba_replan(20)
+        desc = "Local-CBBA-Replan market allocator (CBBAReplan, max_tasks_per_agent=1) interval 20 (no scorer)"
+    elif wl == "escort_cbba":
+        case_name, cfg, spec = "WPS_escort", wps_config("WPS_escort"), AllocSpec.cbba_replan(12)
+        desc = "Local-CBBA-Coalition market allocator interval 12 with visibility map"
     elif wl == "escort_pi":
         case_name, cfg, spec = "WPS_escort", wps_config("WPS_escort"), AllocSpec.performance_impact(12)
         desc = "Local-PI-Coalition market allocator interval 12 with visibility map"
@@ -281,7 +287,7 @@ def run_gpu_arm(args):
     # output line must be (and is) 0.  --task-cap -1 runs the library default.
     if args.task_cap > 0:
         task_cap = args.task_cap
-    elif args.task_cap == 0 and wl in ("hard_pair", "hard_local", "hard_pi"):
+    elif args.task_cap == 0 and wl in ("hard_pair", "hard_local", "hard_pi", "hard_cbba"):
         task_cap = 32
     else:
         task_cap = None
@@ -510,7 +516,7 @@ def survey_b_alg(wl, A, env):
     B_alg = 2 S_env + O_env with agent 104 B, live task 100 + 8 A B, threat 32 B, known bitmask 4 A ceil(Tcap / 32) B,
     pending reveals 4 x 48 B, scalars 128 B, RNG tape 44 B per step, O_env = 4 A + 16 B."""
     stated = {"hard_pair": 14400, "hard_local": 14400, "commit_urgency": 21000, "escort_coalition": 25000,
-              "hard_pi": 14400, "escort_pi": 25000}
+              "hard_pi": 14400, "escort_pi": 25000, "hard_cbba": 14400, "escort_cbba": 25000}
     if wl in stated:
         return stated[wl], "SURVEY.md 8(d), stated figure"
     H = int(env.cfg.n_threats)
@@ -586,7 +592,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
     ap.add_argument("--workload", default="hard_pair",
                     help="hard_pair (default, BASELINE config 2) | hard_local | commit_urgency | escort_coalition | burst_xK "
-                         "| attn_context | hard_pi | escort_pi")
+                         "| attn_context | hard_pi | escort_pi | hard_cbba | escort_cbba")
     ap.add_argument("--task-cap", type=int, default=0,
                     help="task slots per environment (0 = workload default: 32 for WPS_hard, else the library's bound; "
                          "-1 = always the library's provable bound)")

@@ -109,7 +109,11 @@ typedef struct muav_alloc_opts {
                                 edges of build_pair_tokens(score_cols = max_tasks, score_rows = max_agents), no locks;
                               6 PerformanceImpact.allocate_tasks(max_tasks_per_agent=1) (MarketBased/PerformanceImpact.py:59-224,
                                 slots and eligibility from MarketBased/CBBA.py:27-65) instead of the Hungarian allocator:
-                                mode / replan_interval / event_mask / use_visibility / d_reserved as for planner 0 */
+                                mode / replan_interval / event_mask / use_visibility / d_reserved as for planner 0;
+                              7 CBBAReplan.allocate_tasks(max_tasks_per_agent=1) (MarketBased/CBBA_Replan.py:15-69 around
+                                MarketBased/CBBA.py:68-324; a fresh CBBA(seed + n_replans) per replan, seed = d_cbba_seed[env]):
+                                same options as planner 6.  Bit-exact with the reference run under PYTHONHASHSEED=0 (its
+                                auction order starts from a set of strings, see csrc/muav_cbba.cuh) */
   int32_t order_hint_mode; /* mode == 0 only (actions come from the caller): the replan rule (1 / 2 / 3, with replan_interval,
                               event_mask and planner as above) that the caller's allocator follows, used solely to fill
                               muav_step_out.d_env_order_next; 0 = no hint */
@@ -124,6 +128,7 @@ typedef struct muav_alloc_opts {
   const float* d_plan_pri;     /* planner 3: [E, score_cols] AttCommitNet priorities by token task column */
   const float* d_plan_commit;  /* planner 3: [E, score_rows] AttCommitNet commit gates by live-agent row */
   double commit_threshold;     /* planner 3: AttentionCommit(commit_threshold=0.5) */
+  const int32_t* d_cbba_seed;  /* planner 7: [E] the `seed` argument of CBBAReplan (the drivers pass the episode seed) or NULL = 0 */
 } muav_alloc_opts;
 
 /* Per-step outputs (any pointer may be NULL). */

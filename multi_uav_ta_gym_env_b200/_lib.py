@@ -57,6 +57,7 @@ class MuavAllocOpts(C.Structure):
         ("d_edge_scores", C.c_void_p), ("d_priorities", C.c_void_p), ("d_reserved", C.c_void_p),
         ("d_task_order", C.c_void_p),
         ("d_plan_pri", C.c_void_p), ("d_plan_commit", C.c_void_p), ("commit_threshold", C.c_double),
+        ("d_cbba_seed", C.c_void_p),
     ]
 
 

@@ -35,7 +35,8 @@ class AllocSpec:
     max_coord: float = 1200.0
     planner: int = 0              # 1: UrgencyCommit.plan, 2: UrgencyCoalition.plan (device-side planners),
                                   # 3: AttentionCommit._plan_from_scores, 4: AttentionEscort._plan_from_scores,
-                                  # 5: UrgencyPair.plan, 6: PerformanceImpact.allocate_tasks(max_tasks_per_agent=1)
+                                  # 5: UrgencyPair.plan, 6: PerformanceImpact.allocate_tasks(max_tasks_per_agent=1),
+                                  # 7: CBBAReplan.allocate_tasks(max_tasks_per_agent=1)
     commit_fraction: float = 0.35
     commit_threshold: float = 0.5
 
@@ -56,6 +57,14 @@ class AllocSpec:
         """Local-PI / Local-PI-Coalition (MarketBased/PerformanceImpact.py:59-224 with max_tasks_per_agent=1) under its own
         should_replan rule, as experiments/wps_eval.py:147-159 (interval 20) and escort_eval.py:162-174 (12) run it."""
         return AllocSpec(1, interval, ALL_EVENTS, True, False, planner=6)
+
+    @staticmethod
+    def cbba_replan(interval=20):
+        """Local-CBBA-Replan / Local-CBBA-Coalition (MarketBased/CBBA_Replan.py:15-69 around CBBA.py:68-324 with
+        max_tasks_per_agent=1, a fresh CBBA(seed + n_replans) per replan; seed = the environment's reset seed) as
+        experiments/wps_eval.py:134-146 (interval 20) and escort_eval.py:149-161 (12) run it.  Reproduces the reference
+        run under PYTHONHASHSEED=0 (csrc/muav_cbba.cuh)."""
+        return AllocSpec(1, interval, ALL_EVENTS, True, False, planner=7)
 
     @staticmethod
     def pair_hybrid(interval=15):
@@ -187,6 +196,7 @@ class BatchedMultiUAVEnv:
         _lib.check(rc, "muav_reset_upload")
         torch.cuda.current_stream(self.device).synchronize()
         self._records0 = self.records.clone()
+        self.seeds = torch.tensor([int(s) for s in seeds], dtype=torch.int32, device=self.device)   # CBBAReplan(seed=...)
         self.n_open.copy_(self.header_int("N_OPEN"))
         self._order_cur = -1   # identity order for the first launch; both buffers start with zeroed fill counters
         self._order.zero_()
@@ -357,6 +367,8 @@ class BatchedMultiUAVEnv:
             keep.append(to)
             O.d_task_order = to.data_ptr()
         O.commit_threshold = spec.commit_threshold
+        if spec.planner == 7:
+            O.d_cbba_seed = self.seeds.data_ptr()
         if spec.planner == 3:
             if plan_pri is None or plan_commit is None:
                 raise ValueError("planner 3 needs plan_pri [E, max_tasks] and plan_commit [E, max_agents]")

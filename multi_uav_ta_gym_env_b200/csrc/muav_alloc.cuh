@@ -672,10 +672,15 @@ MUAV_HD inline void apply_commit(Sim& S, int a, int horizon) {
 }
 
 // Planner front ends (muav_alloc_opts.planner) + allocate_tasks.  Warp-collective.
+}  // namespace muav
+#include "muav_cbba.cuh"
+namespace muav {
+
 MUAV_HD inline int plan_and_allocate(Sim& S, const muav_alloc_opts& O, int e, int16_t* out_agent, int16_t* out_tid, int lane,
                                      int nlanes) {
   if (MUAV_F_PLANNER(O.planner) == 0) return allocate_tasks(S, O, e, out_agent, out_tid, lane, nlanes);
   if (O.planner == 6) return pi_allocate(S, O, e, out_agent, out_tid, lane, nlanes);
+  if (O.planner == 7) return cbba_allocate(S, O, e, out_agent, out_tid, lane, nlanes);
   View& V = S.V;
   const muav_config& C = S.C();
   const int A = V.lay().D.A, TC = V.lay().D.TC;

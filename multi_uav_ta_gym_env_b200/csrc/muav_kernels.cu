@@ -142,11 +142,11 @@ __global__ void __launch_bounds__(MUAV_LB_THREADS, MUAV_LB_BLOCKS) muav_step_ker
         const int t = ghi[HI_T];
         const int iv = O.replan_interval > 0 ? O.replan_interval : 1;
         const bool ev_hit = (ghi[HI_EV_TAGMASK] & O.event_mask) != 0;
-        if (O.mode == 1 && (O.planner == 0 || O.planner == 6)) go = (t - ghi[HI_LAST_PLAN_STEP]) >= iv || ev_hit;
+        if (O.mode == 1 && (O.planner == 0 || O.planner == 6 || O.planner == 7)) go = (t - ghi[HI_LAST_PLAN_STEP]) >= iv || ev_hit;
         else if (O.mode == 3) go = 1;
         else go = t == 0 || (t % iv) == 0 || ev_hit;
         // allocate_tasks counts every call, also those that return without replanning (HungarianAllocator.py:84)
-        if (!go && (O.planner == 0 || O.planner == 6) && O.mode != 0) ghi[HI_N_CALLS] += 1;
+        if (!go && (O.planner == 0 || O.planner == 6 || O.planner == 7) && O.mode != 0) ghi[HI_N_CALLS] += 1;
       }
       if (!go) {
         if (P.out.d_n_pairs) P.out.d_n_pairs[e] = 0;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(MUAV_LB_THREADS, MUAV_LB_BLOCKS) muav_step_ker
       const int t = HIv(T);
       const int iv = O.replan_interval > 0 ? O.replan_interval : 1;
       const bool ev_hit = (HIv(EV_TAGMASK) & O.event_mask) != 0;
-      if (rule == 1 && (O.planner == 0 || O.planner == 6)) will = (t - HIv(LAST_PLAN_STEP)) >= iv || ev_hit;
+      if (rule == 1 && (O.planner == 0 || O.planner == 6 || O.planner == 7)) will = (t - HIv(LAST_PLAN_STEP)) >= iv || ev_hit;
       else if (rule == 3) will = true;
       else will = t == 0 || (t % iv) == 0 || ev_hit;
     }
@@ -619,6 +619,10 @@ static size_t slot_bytes_of(StepParams& P) {
   const bool with_alloc = P.alloc_only || P.opts.mode != 0;
   const bool with_planner = P.opts.planner != 0 && P.opts.planner != 6;
   P.scratch_launch = !with_alloc ? P.L.step_scratch_bytes : (with_planner ? P.L.scratch_bytes : P.L.plain_scratch_bytes);
+  if (with_alloc && P.opts.planner == 7) {   // CBBA keeps an MT19937 state, a set table and per-agent paths
+    const int cb = cbba_scratch_bytes(P.L.D.A);
+    if (cb > P.scratch_launch) P.scratch_launch = cb;
+  }
   return (size_t)P.stage_bytes + (size_t)P.scratch_launch + (size_t)P.L.act_bytes;
 }
 

@@ -213,11 +213,15 @@ class _CudaBackend:
         return (float(self.b.reward[0].item()), bool(self.b.terminated[0].item()), bool(self.b.truncated[0].item()),
                 self.b.events_of(0))
 
-    def allocate(self, spec, scores, priorities, reserved, order):
+    def allocate(self, spec, scores, priorities, reserved, order, cbba_seed=None):
         import torch
 
         O, keep = self.b._alloc_opts(spec, None, None if priorities is None else torch.from_numpy(priorities[None]),
                                      None if reserved is None else torch.from_numpy(reserved[None]))
+        if cbba_seed is not None:
+            sd = torch.tensor([int(cbba_seed)], dtype=torch.int32, device=self.b.device)
+            keep.append(sd)
+            O.d_cbba_seed = sd.data_ptr()
         if scores is not None:
             sc = torch.from_numpy(scores[None]).to(self.b.device)
             keep.append(sc)
@@ -719,4 +723,72 @@ class PerformanceImpact:
                     raise NotImplementedError("agent_known_ids must be env.agent_visibility_map() (device-resident sets)")
         spec = AllocSpec(3, self.replan_interval, 0, use_vis, False, float(self.max_coord), planner=6)
         pairs = env._backend.allocate(spec, None, None, reserved, order)
+        return [(env.agents_obj[a].name, [env._task(tid)]) for a, tid in pairs]
+
+
+class CBBAReplan:
+    """Same constructor, attributes and allocate_tasks signature as the reference's CBBA with periodic / event-triggered
+    replan (TaskAllocation/MarketBased/CBBA_Replan.py:15-69 around MarketBased/CBBA.py:68-324); the auction (slot
+    expansion, MT19937 shuffles, bids over insertion points, consensus) runs in the CUDA allocator
+    (muav_alloc_opts.planner = 7, csrc/muav_cbba.cuh).  The reference's auction order starts from a set of strings, so its
+    result depends on the interpreter's string hash: this class reproduces the reference run under PYTHONHASHSEED=0.
+    Only max_tasks_per_agent = 1 -- what every reference driver passes -- is implemented; anything else raises."""
+
+    def __init__(self, agents=None, tasks=None, max_coord: float = 1000.0, seed: int = 0, replan_interval: int = 20):
+        self.max_coord = max_coord
+        self.seed = int(seed)
+        self.replan_interval = max(1, int(replan_interval))
+        self.last_plan_step = -10**9
+        self.n_replans = 0
+        self.n_calls = 0
+
+    should_replan = HungarianAllocator.should_replan
+
+    def allocate_tasks(self, agents, tasks, time_step: int = 0, events=None, force: bool = False, agent_known_ids=None,
+                       reserved_agent_names=None, max_tasks_per_agent: int = 1):
+        from .batched_env import AllocSpec
+
+        if max_tasks_per_agent != 1:
+            raise NotImplementedError("the device CBBA implements max_tasks_per_agent=1 (the reference drivers' setting)")
+        self.n_calls += 1
+        if not force and not self.should_replan(time_step, events):
+            return []
+        agents = list(agents)
+        tasks = list(tasks)
+        self.last_plan_step = time_step
+        self.n_replans += 1
+        env = None
+        for obj in agents + tasks:
+            env = getattr(obj, "_env", None)
+            if env is not None:
+                break
+        if env is None or not agents or not tasks:
+            return []
+        if int(time_step) != int(env.time_steps):
+            raise ValueError("time_step must be env.time_steps (the device allocator reads the env clock)")
+        cfg = env._backend.cfg
+        A, TC = cfg.n_agents, max(cfg.id_cap, cfg.task_cap)
+        reserved_names = set(reserved_agent_names or [])
+        given = {a.id for a in agents}
+        reserved = np.zeros(A, dtype=np.uint8)
+        for a in env.agents_obj:
+            if a.id not in given or a.name in reserved_names:
+                reserved[a.id] = 1
+        order = np.full(TC, -1, dtype=np.int32)
+        n_ord = 0
+        for t in tasks:
+            if t.id != 0 and n_ord < TC:
+                order[n_ord] = t.id - 1
+                n_ord += 1
+        use_vis = agent_known_ids is not None
+        if use_vis:
+            own = env.agent_visibility_map() or {}
+            for name, ids in agent_known_ids.items():
+                if name in own and set(ids) != own[name]:
+                    raise NotImplementedError("agent_known_ids must be env.agent_visibility_map() (device-resident sets)")
+        spec = AllocSpec(3, self.replan_interval, 0, use_vis, False, float(self.max_coord), planner=7)
+        # the device seeds its generator with d_cbba_seed + N_REPLANS of the record (incremented by this call): hand it the
+        # difference so that the generator is Random(self.seed + self.n_replans), whatever else replanned on this record
+        n_dev = int(env._backend.codec.header(env._backend.record(), "N_REPLANS"))
+        pairs = env._backend.allocate(spec, None, None, reserved, order, cbba_seed=self.seed + self.n_replans - (n_dev + 1))
         return [(env.agents_obj[a].name, [env._task(tid)]) for a, tid in pairs]

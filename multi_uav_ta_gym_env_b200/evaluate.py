@@ -29,6 +29,8 @@ ESCORT_INTERVAL = 12   # experiments/escort_eval.py:52-58, 85-93
 DEVICE_ALGORITHMS: Dict[str, Callable[[], AllocSpec]] = {
     "Global-Hungarian": lambda: AllocSpec.global_hungarian(20),            # wps_eval.py:117-122
     "Local-Hungarian": lambda: AllocSpec.local_hungarian(20),              # wps_eval.py:123-133
+    "Local-CBBA-Replan": lambda: AllocSpec.cbba_replan(20),                # wps_eval.py:134-146 (reference under PYTHONHASHSEED=0)
+    "Local-CBBA-Coalition": lambda: AllocSpec.cbba_replan(ESCORT_INTERVAL),  # escort_eval.py:149-161
     "Local-PI": lambda: AllocSpec.performance_impact(20),                  # wps_eval.py:147-159
     "Local-PI-Coalition": lambda: AllocSpec.performance_impact(ESCORT_INTERVAL),   # escort_eval.py:162-174
     "Urgency-Pair": lambda: AllocSpec.urgency_pair(HYBRID_INTERVAL),       # wps_eval.py:232-236

@@ -84,6 +84,10 @@ def alloc_opts_for(driver):
     elif driver in ("local_pi", "pi_coalition"):
         O.mode, O.replan_interval, O.event_mask, O.use_visibility = 1, (12 if driver == "pi_coalition" else 20), 0x1F, 1
         O.planner = 6
+    elif driver in ("cbba_replan", "cbba_coalition"):
+        # CBBAReplan under the drivers of wps_eval.py:134-146 / escort_eval.py:149-161; the caller sets O.d_cbba_seed
+        O.mode, O.replan_interval, O.event_mask, O.use_visibility = 1, (12 if driver == "cbba_coalition" else 20), 0x1F, 1
+        O.planner = 7
     elif driver == "pair_injected":
         O.mode = 2
         O.replan_interval = 15
@@ -288,9 +292,12 @@ class HostBackend:
         assert rc == 0
         return float(rew[0]), bool(term[0]), bool(trunc[0]), state.decode_events(nev[0], evs[0])
 
-    def allocate(self, spec, scores, priorities, reserved, order):
+    def allocate(self, spec, scores, priorities, reserved, order, cbba_seed=None):
         A = self.cfg.n_agents
         O = _lib.MuavAllocOpts()
+        if cbba_seed is not None:
+            self._cbba_seed = np.array([int(cbba_seed)], np.int32)
+            O.d_cbba_seed = self._cbba_seed.ctypes.data
         O.mode, O.replan_interval, O.event_mask = spec.mode, spec.replan_interval, spec.event_mask
         O.use_visibility, O.pair_tokens, O.max_coord = int(spec.use_visibility), int(spec.pair_tokens), spec.max_coord
         O.planner, O.commit_fraction = spec.planner, spec.commit_fraction

@@ -30,7 +30,7 @@ int hostcheck_step(const muav_config* cfg, void* records, const uint32_t* tapes,
   muav_step_out Z;
   memset(&Z, 0, sizeof(Z));
   if (out) Z = *out;
-  char* scratch = (char*)malloc((size_t)L.scratch_bytes + 64);
+  char* scratch = (char*)malloc((size_t)L.scratch_bytes + (size_t)cbba_scratch_bytes(L.D.A) + 64);
   int tape_stride = cfg->tape_words[0] + cfg->tape_words[1] + cfg->tape_words[2];
   const int A = L.D.A;
   int16_t act_agent[MUAV_MAX_AGENTS], act_tid[MUAV_MAX_AGENTS];
@@ -92,7 +92,7 @@ int hostcheck_allocate(const muav_config* cfg, void* records, const muav_alloc_o
   muav_step_out Z;
   memset(&Z, 0, sizeof(Z));
   if (out) Z = *out;
-  char* scratch = (char*)malloc((size_t)L.scratch_bytes + 64);
+  char* scratch = (char*)malloc((size_t)L.scratch_bytes + (size_t)cbba_scratch_bytes(L.D.A) + 64);
   const int A = L.D.A;
   int16_t act_agent[MUAV_MAX_AGENTS], act_tid[MUAV_MAX_AGENTS];
   for (int e = 0; e < n_envs; ++e) {

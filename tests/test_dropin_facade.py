@@ -142,6 +142,35 @@ def test_performance_impact_facade_follows_the_reference_loop(case, seed, interv
         mp.allocate_tasks(mine.get_live_agents(), ref_open_tasks(mine), time_step=mine.time_steps, force=True, max_tasks_per_agent=2)
 
 
+@pytest.mark.parametrize("fixture,case,interval", [("wps_hard_cbba", "WPS_hard", 20), ("wps_escort_cbba", "WPS_escort", 12)])
+def test_cbba_replan_facade_reproduces_the_reference_under_hashseed_zero(fixture, case, interval):
+    """Local-CBBA-Replan / Local-CBBA-Coalition loop (wps_eval.py:134-146, escort_eval.py:149-161) with the facade's
+    CBBAReplan (device allocator, planner 7) on the facade env against the fixture recorded from the unmodified reference
+    class in an interpreter started with PYTHONHASHSEED=0 (CBBA's auction order depends on the string hash, so the
+    reference cannot be run side by side in this process)."""
+    from helpers import load_golden
+    from multi_uav_ta_gym_env_b200 import wps_config
+    from multi_uav_ta_gym_env_b200.env import CBBAReplan, MultiUAVEnv
+
+    for ep in load_golden(fixture)[:2]:
+        seed = ep["seed"]
+        mine = MultiUAVEnv(wps_config(case), _test_backend_factory=lambda c: HostBackend(c))
+        mo, mi = mine.reset(seed=seed)
+        cb = CBBAReplan(mine.agents_obj, mine.tasks, mine.max_coord, seed=seed, replan_interval=interval)
+        for t, st in enumerate(ep["steps"]):
+            events = list(mi.get("events") or []) if isinstance(mi, dict) else []
+            res = cb.allocate_tasks(mine.get_live_agents(), ref_open_tasks(mine), time_step=mine.time_steps, events=events,
+                                    agent_known_ids=mine.agent_visibility_map(), max_tasks_per_agent=1)
+            pairs = [[mine.agent_by_name[n].id, t_.id] for n, tl in res for t_ in tl]
+            assert pairs == st["pairs"], (seed, t)
+            mo, mr, mterm, mtrunc, mi = mine.step(apply_assign(mine, [(n, t_) for n, tl in res for t_ in tl]))
+            assert str(refsnap.digest(mine._snap)) == st["digest"], (seed, t)
+        assert cb.n_replans == ep["n_replans"]
+        with pytest.raises(NotImplementedError):
+            cb.allocate_tasks(mine.get_live_agents(), ref_open_tasks(mine), time_step=mine.time_steps, force=True,
+                              max_tasks_per_agent=2)
+
+
 def _load_oracle_from_snapshot(orc, facade_env):
     """Minimal oracle view of the facade's current state (only what the token builders read)."""
     s = facade_env._snap

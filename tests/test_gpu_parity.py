@@ -22,7 +22,7 @@ STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit
 # planner fixtures mutate commit_until between steps: they are replayed through the fused planner only
 ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
     "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair", "wps_attn_context",
-    "wps_hard_pi", "wps_commit_pi", "wps_escort_pi"]
+    "wps_hard_pi", "wps_commit_pi", "wps_escort_pi", "wps_hard_cbba", "wps_commit_cbba", "wps_escort_cbba"]
 
 
 def make_env(cfg, seeds, **kw):
@@ -38,7 +38,8 @@ def spec_for(driver):
             "global_hungarian": AllocSpec.global_hungarian(20), "pair_injected": AllocSpec.pair_hybrid(15),
             "urgency_commit": AllocSpec.urgency_commit(15), "urgency_coalition": AllocSpec.urgency_coalition(12),
             "context_injected": AllocSpec.pair_hybrid(15), "urgency_pair": AllocSpec.urgency_pair(15), "att_commit_injected": AllocSpec.att_commit(15), "att_escort_injected": AllocSpec.att_escort(12),
-            "local_pi": AllocSpec.performance_impact(20), "pi_coalition": AllocSpec.performance_impact(12)}[driver]
+            "local_pi": AllocSpec.performance_impact(20), "pi_coalition": AllocSpec.performance_impact(12),
+            "cbba_replan": AllocSpec.cbba_replan(20), "cbba_coalition": AllocSpec.cbba_replan(12)}[driver]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)

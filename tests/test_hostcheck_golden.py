@@ -13,7 +13,7 @@ STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit
 # planner fixtures mutate commit_until between steps: they are replayed through the fused planner only
 ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
     "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair", "wps_attn_context",
-    "wps_hard_pi", "wps_commit_pi", "wps_escort_pi"]
+    "wps_hard_pi", "wps_commit_pi", "wps_escort_pi", "wps_hard_cbba", "wps_commit_cbba", "wps_escort_cbba"]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)
@@ -40,6 +40,9 @@ def test_fused_allocator(hostcheck, name):
     drv = eps[0]["driver"]
     env = hostcheck.make(golden_config(eps[0]), [ep["seed"] for ep in eps])
     O = alloc_opts_for(drv)
+    if drv in ("cbba_replan", "cbba_coalition"):
+        cbba_seeds = np.array([ep["seed"] for ep in eps], np.int32)
+        O.d_cbba_seed = cbba_seeds.ctypes.data
     for t in range(len(eps[0]["steps"])):
         if drv in ("pair_injected", "context_injected"):
             sc = np.stack([injected_scores(ep["seed"], t, 16, 32) for ep in eps])
@@ -77,7 +80,7 @@ def test_fused_allocator(hostcheck, name):
             assert env.pairs_of(e) == st["pairs"], (name, ep["seed"], t)
             assert env.reward[e] == float.fromhex(st["reward"])
             assert str(env.digest(e)) == st["digest"], (name, ep["seed"], t)
-    if drv in ("local_hungarian", "coalition", "global_hungarian", "local_pi", "pi_coalition"):
+    if drv in ("local_hungarian", "coalition", "global_hungarian", "local_pi", "pi_coalition", "cbba_replan", "cbba_coalition"):
         for e, ep in enumerate(eps):
             assert env.codec.header(env.rec[e], "N_REPLANS") == ep["n_replans"]
 
