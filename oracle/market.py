@@ -5,10 +5,9 @@ Restates the Performance-Impact market allocator TaskAllocation/MarketBased/Perf
 state (oracle/sim.py).  Pinned by tests/golden/wps_{hard,commit,escort}_pi.json.gz, generated from the unmodified
 reference class under the episode loops of experiments/wps_eval.py:147-159 / escort_eval.py:162-174.
 
-The reference's other market baseline, CBBA / CBBAReplan (MarketBased/CBBA.py:68-324), is NOT restated: its auction
-order starts from `list(remaining)` of a *set of strings* (CBBA.py:116,128), i.e. from CPython's per-process salted
-string hash, so the reference itself gives different assignments from one interpreter start to the next unless
-PYTHONHASHSEED is pinned -- there is no reference result to be bit-exact with.
+The reference's other market baseline, CBBA / CBBAReplan (MarketBased/CBBA.py:68-324), is restated in oracle/cbba.py:
+its auction order starts from `list(remaining)` of a *set of strings* (CBBA.py:116,128), i.e. from CPython's string
+hash, so it is pinned for PYTHONHASHSEED=0 (oracle/pyset.py restates the hash and the set order).
 
 Arithmetic (float64, one rounding per operation):
     start = max(next_free_time, t) + ||pos - task_pos|| / max(speed, 1e-6)             (_schedule :227-241)
