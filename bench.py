@@ -237,6 +237,7 @@ def run_gpu_arm(args):
     # workload: the default is BASELINE config 2; the others are BASELINE configs 3-5 (extra lines for profiles/)
     wl = args.workload
     use_scorer = wl in ("hard_pair", "attn_context")
+    use_commit_net = wl == "commit_att"
     if wl == "attn_context":
         # the paper's primary method: Att-ContextPair on WPS_attn (12 agents, dual-front bursts, private knowledge)
         case_name, cfg, spec = "WPS_attn", wps_config("WPS_attn"), AllocSpec.pair_hybrid(HYBRID_INTERVAL)
@@ -262,6 +263,10 @@ def run_gpu_arm(args):
     elif wl == "commit_urgency":
         case_name, cfg, spec = "WPS_commit", wps_config("WPS_commit"), AllocSpec.urgency_commit(HYBRID_INTERVAL)
         desc = "UrgencyCommit planner on the device (commit locks, rematch penalty), hybrid replan rule"
+    elif wl == "commit_att":
+        case_name, cfg, spec = "WPS_commit", wps_config("WPS_commit"), AllocSpec.att_commit(HYBRID_INTERVAL)
+        desc = ("Att-Commit: random-init AttCommitNet (fused forward kernel on fused commit tokens) -> "
+                "AttentionCommit._plan_from_scores on the device, hybrid replan rule")
     elif wl == "escort_coalition":
         case_name, cfg, spec = "WPS_escort", wps_config("WPS_escort"), AllocSpec.coalition_hungarian(12)
         desc = "Coalition-Hungarian interval 12 with visibility map"
@@ -306,6 +311,14 @@ def run_gpu_arm(args):
         # the step kernel emits the pair tokens of every env that will replan before the next step
         tok = env.enable_fused_tokens(32, 16, HYBRID_INTERVAL, 0b111, context=ctx)
         scorer = FusedAttPairScorer(net, dev)   # hand-written fused forward (csrc/muav_scorer.cu)
+    plan_kw = {}
+    if use_commit_net:
+        from multi_uav_ta_gym_env_b200.scorers import AttCommitNet, FusedAttCommitScorer
+        cnet = AttCommitNet().to(dev).eval()
+        tok = env.enable_fused_tokens(32, 16, HYBRID_INTERVAL, 0b111, commit=True)
+        commit_scorer = FusedAttCommitScorer(cnet, dev)
+        plan_kw = {"plan_pri": torch.zeros(E, 32, dtype=torch.float32, device=dev),
+                   "plan_commit": torch.zeros(E, 16, dtype=torch.float32, device=dev)}
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     metric_acc = torch.zeros(32, dtype=torch.float64, device=dev)
     names = env.lib.metric_names()
@@ -313,6 +326,13 @@ def run_gpu_arm(args):
 
     def score_step(t):
         """Att-Pair scorer for the environments whose hybrid replan rule fires at time t (wps_eval.py:64-73)."""
+        if use_commit_net:
+            if t == 0:
+                env.refresh_fused_tokens()
+                launches["n"] += 1
+            commit_scorer.vectors(tok, plan_kw["plan_pri"], plan_kw["plan_commit"], use_need=True)
+            launches["n"] += 1
+            return
         if not use_scorer:
             return
         if t == 0:
@@ -337,7 +357,7 @@ def run_gpu_arm(args):
 
     def device_step(t):
         score_step(t)
-        env.step_allocated(spec, 1, edge_scores=scores)
+        env.step_allocated(spec, 1, edge_scores=scores, **plan_kw)
         launches["n"] += 1
         if t + 1 == EPISODE:
             episode_end()
@@ -368,7 +388,7 @@ def run_gpu_arm(args):
         ev[k][0].record()
         score_step(t)
         ev[k][1].record()
-        env.step_allocated(spec, 1, edge_scores=scores)
+        env.step_allocated(spec, 1, edge_scores=scores, **plan_kw)
         launches["n"] += 1
         ev[k][2].record()
         if t + 1 == EPISODE:
@@ -385,7 +405,7 @@ def run_gpu_arm(args):
             for t in range(15):
                 flush_buf.fill_(t)
                 score_step(1 + t)
-                env.step_allocated(spec, 1, edge_scores=scores)
+                env.step_allocated(spec, 1, edge_scores=scores, **plan_kw)
             torch.cuda.synchronize(dev)
         sampler.wait_for(first_sample + 3, more)
         env.restore()
@@ -438,7 +458,7 @@ def run_gpu_arm(args):
 
     def host_step(t):
         score_step(t)
-        env.allocate_host(spec, h_act, edge_scores=scores)   # kernel + D2H + sync: the caller holds the decision
+        env.allocate_host(spec, h_act, edge_scores=scores, **plan_kw)   # kernel + D2H + sync: the caller holds the decision
         env.step_host(h_act, h_rew, h_term, h_trunc, 1, hint=spec)   # H2D + step + packed D2H + sync
         if t + 1 == EPISODE:
             episode_end()
@@ -515,7 +535,7 @@ def survey_b_alg(wl, A, env):
     configs (WPS_hard 14.4 KB, WPS_commit 21 KB, WPS_escort 25 KB), else the section's own formula
     B_alg = 2 S_env + O_env with agent 104 B, live task 100 + 8 A B, threat 32 B, known bitmask 4 A ceil(Tcap / 32) B,
     pending reveals 4 x 48 B, scalars 128 B, RNG tape 44 B per step, O_env = 4 A + 16 B."""
-    stated = {"hard_pair": 14400, "hard_local": 14400, "commit_urgency": 21000, "escort_coalition": 25000,
+    stated = {"hard_pair": 14400, "hard_local": 14400, "commit_urgency": 21000, "commit_att": 21000, "escort_coalition": 25000,
               "hard_pi": 14400, "escort_pi": 25000, "hard_cbba": 14400, "escort_cbba": 25000}
     if wl in stated:
         return stated[wl], "SURVEY.md 8(d), stated figure"
@@ -592,7 +612,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
     ap.add_argument("--workload", default="hard_pair",
                     help="hard_pair (default, BASELINE config 2) | hard_local | commit_urgency | escort_coalition | burst_xK "
-                         "| attn_context | hard_pi | escort_pi | hard_cbba | escort_cbba")
+                         "| attn_context | hard_pi | escort_pi | hard_cbba | escort_cbba | commit_att")
     ap.add_argument("--task-cap", type=int, default=0,
                     help="task slots per environment (0 = workload default: 32 for WPS_hard, else the library's bound; "
                          "-1 = always the library's provable bound)")

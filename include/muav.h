@@ -170,6 +170,8 @@ typedef struct muav_token_out {
   uint8_t* d_need;        /* [E] */
   int32_t max_tasks, max_agents, interval, event_mask;
   float* d_context;       /* optional [E, 8]: build_context_summary (ContextPairHybrid.py:33-70) of the same tokens */
+  int32_t agent_feat_dim; /* 0 / 12: pair tokens; 13: commit tokens (enrich_commit_tokens, AttentionCommit.py:49-62):
+                             d_agent_feats is then [E, max_agents, 13] and d_edge_valid may be NULL */
 } muav_token_out;
 
 const char* muav_version(void);
@@ -325,6 +327,22 @@ int muav_att_context_pair_scores(const float* d_params, const muav_attpair_offse
                                  const float* d_edge_valid, const float* d_context, const int32_t* d_env_idx,
                                  const uint8_t* d_need, int n, int max_tasks, int max_agents, float score_clamp,
                                  float* d_scores, void* stream);
+
+/* Fused AttCommitNet forward (TaskAllocation/Hybrid/AttentionCommit.py:68-100; AttentionCommit.act without exploration,
+ * :167-175): commit tokens (muav_tokens_commit layout, agent features [.,13]) -> priorities f32 [E, max_tasks] and commit
+ * gates f32 [E, max_agents] (0 on padded columns / rows), the d_plan_pri / d_plan_commit inputs of planner 3.  d_model 64,
+ * 4 heads, 2 encoder layers, feed-forward 128 are fixed; weights packed like muav_attpair_offsets (transposed, offsets in
+ * floats).  d_env_idx / d_need as in muav_att_pair_scores. */
+typedef struct muav_attcommit_offsets {
+  int32_t agent_proj_w, agent_proj_b, task_proj_w, task_proj_b, type_embed;
+  int32_t enc_in_w[2], enc_in_b[2], enc_out_w[2], enc_out_b[2], enc_l1_w[2], enc_l1_b[2], enc_l2_w[2], enc_l2_b[2];
+  int32_t enc_n1_w[2], enc_n1_b[2], enc_n2_w[2], enc_n2_b[2];
+  int32_t priority_w, priority_b, commit_w, commit_b;
+} muav_attcommit_offsets;
+int muav_att_commit_vectors(const float* d_params, const muav_attcommit_offsets* offsets, const float* d_task_feats,
+                            const uint8_t* d_task_mask, const float* d_agent_feats13, const uint8_t* d_agent_mask,
+                            const int32_t* d_env_idx, const uint8_t* d_need, int n, int max_tasks, int max_agents,
+                            float* d_priorities, float* d_commits, void* stream);
 
 #ifdef __cplusplus
 }

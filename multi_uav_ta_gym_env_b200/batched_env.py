@@ -207,15 +207,16 @@ class BatchedMultiUAVEnv:
         self.records.copy_(self._records0)
 
     # ------------------------------------------------------------------ fused token emission
-    def enable_fused_tokens(self, max_tasks=32, max_agents=16, interval=15, event_mask=HYBRID_EVENTS, context=False):
+    def enable_fused_tokens(self, max_tasks=32, max_agents=16, interval=15, event_mask=HYBRID_EVENTS, context=False,
+                            commit=False):
         """Ask the step kernel to emit pair tokens for the environments that will replan before the next
         step (muav_token_out).  Returns the token dict (tensors are updated in place by every step) with
-        `need` u8[E]."""
+        `need` u8[E].  commit=True: commit tokens instead (agent features [., 13], enrich_commit_tokens)."""
         E, dev = self.n_envs, self.device
         tok = {
             "task_feats": torch.zeros(E, max_tasks, 13, dtype=torch.float32, device=dev),
             "task_mask_u8": torch.ones(E, max_tasks, dtype=torch.uint8, device=dev),
-            "agent_feats": torch.zeros(E, max_agents, 12, dtype=torch.float32, device=dev),
+            "agent_feats": torch.zeros(E, max_agents, 13 if commit else 12, dtype=torch.float32, device=dev),
             "agent_mask_u8": torch.ones(E, max_agents, dtype=torch.uint8, device=dev),
             "edge_valid": torch.zeros(E, max_agents, max_tasks, dtype=torch.float32, device=dev),
             "task_ids": torch.zeros(E, max_tasks, dtype=torch.int32, device=dev),
@@ -233,6 +234,7 @@ class BatchedMultiUAVEnv:
         T.d_need = tok["need"].data_ptr()
         T.d_context = tok["context"].data_ptr() if context else None
         T.max_tasks, T.max_agents, T.interval, T.event_mask = max_tasks, max_agents, interval, event_mask
+        T.agent_feat_dim = 13 if commit else 12
         self._tok = T
         self.fused_tokens = tok
         return tok
@@ -240,7 +242,11 @@ class BatchedMultiUAVEnv:
     def refresh_fused_tokens(self):
         """Fill the fused token tensors for ALL environments with the standalone kernel (after reset/restore)."""
         tok, T = self.fused_tokens, self._tok
-        if T.d_context:
+        if T.agent_feat_dim == 13:
+            rc = self.lib.dll.muav_tokens_commit(C.byref(self.cfg), self.records.data_ptr(), T.max_tasks, T.max_agents,
+                                                 T.d_task_feats, T.d_task_mask, T.d_agent_feats, T.d_agent_mask,
+                                                 T.d_task_ids, self.n_envs, self._stream())
+        elif T.d_context:
             rc = self.lib.dll.muav_tokens_context(C.byref(self.cfg), self.records.data_ptr(), T.max_tasks, T.max_agents, 0,
                                                   T.d_task_feats, T.d_task_mask, T.d_agent_feats, T.d_agent_mask,
                                                   T.d_edge_valid, T.d_task_ids, T.d_context, self.n_envs, self._stream())
@@ -322,11 +328,13 @@ class BatchedMultiUAVEnv:
         self.launches += 1
 
     def allocate_host(self, spec: "AllocSpec", h_actions_out, edge_scores: Optional[torch.Tensor] = None,
-                      priorities: Optional[torch.Tensor] = None, reserved: Optional[torch.Tensor] = None):
+                      priorities: Optional[torch.Tensor] = None, reserved: Optional[torch.Tensor] = None,
+                      task_order: Optional[torch.Tensor] = None, plan_pri: Optional[torch.Tensor] = None,
+                      plan_commit: Optional[torch.Tensor] = None):
         """allocate() with the ordered action list delivered to HOST memory int32 [E, A, 2] (the allocator handing its
         decision to the caller, HungarianAllocator.py:72-208): kernel, one D2H copy and the synchronisation in one call."""
         ptr = lambda x: x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
-        O, keep = self._alloc_opts(spec, edge_scores, priorities, reserved)
+        O, keep = self._alloc_opts(spec, edge_scores, priorities, reserved, task_order, plan_pri, plan_commit)
         cur = self._order_cur
         self._out.d_env_order = self._order[cur].data_ptr() if (self.group_replanners and cur >= 0) else None
         self._out.d_env_order_next = None

@@ -305,10 +305,12 @@ __global__ void __launch_bounds__(MUAV_LB_THREADS, MUAV_LB_BLOCKS) muav_step_ker
       if (lane == 0) P.tok.d_need[e] = need ? 1 : 0;
       if (need && P.tok.d_task_feats) {
         const int mt = P.tok.max_tasks, ma = P.tok.max_agents;
+        const int afd = P.tok.agent_feat_dim == 13 ? 13 : 12;   // 13: commit tokens (enrich_commit_tokens)
         tokens_pair_env(V, P.cfg, mt, ma, P.tok.d_task_feats + (size_t)e * mt * 13, P.tok.d_task_mask + (size_t)e * mt,
-                        P.tok.d_agent_feats + (size_t)e * ma * 12, P.tok.d_agent_mask + (size_t)e * ma,
-                        P.tok.d_edge_valid + (size_t)e * ma * mt, P.tok.d_task_ids + (size_t)e * mt, (int16_t*)scratch,
-                        lane, 32, 12, 0, P.tok.d_context ? P.tok.d_context + (size_t)e * 8 : nullptr);
+                        P.tok.d_agent_feats + (size_t)e * ma * afd, P.tok.d_agent_mask + (size_t)e * ma,
+                        P.tok.d_edge_valid ? P.tok.d_edge_valid + (size_t)e * ma * mt : nullptr,
+                        P.tok.d_task_ids + (size_t)e * mt, (int16_t*)scratch, lane, 32, afd, 0,
+                        P.tok.d_context ? P.tok.d_context + (size_t)e * 8 : nullptr);
       }
       __syncwarp();
     }

@@ -213,7 +213,12 @@ constexpr int GLIST = 8;  // environments per CTA (launch parameter `group` <= G
 
 // Which environments does this CTA score?  Launch slots b in [0, n) map to environments e = env_idx ? env_idx[b] : b;
 // a slot counts when need == NULL or need[e] != 0; CTA c takes the counted slots of rank [c*group, (c+1)*group).
-__device__ int pick_envs(const Params& P, int group, int* s_env, int* s_scan) {
+struct PickArgs {
+  const uint8_t* need;
+  const int32_t* env_idx;
+  int n;
+};
+__device__ int pick_envs(const PickArgs P, int group, int* s_env, int* s_scan) {
   const int tid = threadIdx.x;
   const int c = blockIdx.x;
   if (!P.need) {
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
   const int MT = P.max_tasks, MA = P.max_agents;
   const float* w = P.w;
   const muav_attpair_offsets& o = P.o;
-  const int m = pick_envs(P, group, s_env, s_scan);
+  const int m = pick_envs(PickArgs{P.need, P.env_idx, P.n}, group, s_env, s_scan);
   if (m == 0) return;
   if (tid < m) {
     const int e = s_env[tid];
@@ -498,7 +503,180 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// AttCommitNet forward (TaskAllocation/Hybrid/AttentionCommit.py:68-100): the same token embedding and post-norm encoder
+// layers (two of them, no cross attention), then priority = sigmoid(w_p . h_task + b_p), commit = sigmoid(w_c . h_agent
+// + b_c); padded rows / columns read 0 (masked_fill).  Same packing as the pair kernel: three environments per 64-token
+// pass, block-diagonal attention, only valid tokens.
+struct CommitParams {
+  const float* w;
+  muav_attcommit_offsets o;
+  const float* task_feats;
+  const uint8_t* task_mask;
+  const float* agent_feats;   // [E, max_agents, 13]
+  const uint8_t* agent_mask;
+  const int32_t* env_idx;
+  const uint8_t* need;
+  float* pri;   // [E, max_tasks]
+  float* com;   // [E, max_agents]
+  int n, max_tasks, max_agents;
+};
+constexpr int AFC = 13;
+
+__global__ void __launch_bounds__(NT, 2) att_commit_kernel(const __grid_constant__ CommitParams P, int group) {
+  extern __shared__ __align__(16) float sm[];
+  float* x_t = sm;
+  float* y_t = x_t + D * TS;
+  float* z_t = y_t + D * TS;
+  float* big_t = z_t + D * TS;
+  __shared__ int s_env[GLIST], s_na[GLIST], s_nt[GLIST], s_scan[NT / 32 + 1];
+  __shared__ Seg s_seg[GMAX];
+  __shared__ uint8_t s_seg_of[TS];
+  __shared__ int s_nseg, s_R, s_split, s_next;
+  const int tid = threadIdx.x;
+  const int MT = P.max_tasks, MA = P.max_agents;
+  const float* w = P.w;
+  const muav_attcommit_offsets& o = P.o;
+  const int m = pick_envs(PickArgs{P.need, P.env_idx, P.n}, group, s_env, s_scan);
+  if (m == 0) return;
+  if (tid < m) {
+    const int e = s_env[tid];
+    const uint8_t* am = P.agent_mask + (size_t)e * MA;
+    const uint8_t* tm = P.task_mask + (size_t)e * MT;
+    int na = 0, nt = 0;
+    while (na < MA && am[na] == 0) ++na;
+    while (nt < MT && tm[nt] == 0) ++nt;
+    s_na[tid] = na;
+    s_nt[tid] = nt;
+  }
+  if (tid == 0) s_next = 0;
+  __syncthreads();
+  for (int g = 0; g < m; ++g) {
+    for (int idx = tid; idx < MT; idx += NT) P.pri[(size_t)s_env[g] * MT + idx] = 0.0f;
+    for (int idx = tid; idx < MA; idx += NT) P.com[(size_t)s_env[g] * MA + idx] = 0.0f;
+  }
+  for (;;) {
+    if (tid == 0) {
+      int g = s_next, ns = 0, sa = 0, st = 0;
+      while (g < m && ns < GMAX) {
+        const int na = s_na[g], nt = s_nt[g];
+        if (na == 0 && nt == 0) { ++g; continue; }
+        if (((sa + na + 3) & ~3) + st + nt > TS) break;
+        s_seg[ns].e = s_env[g];
+        s_seg[ns].abase = sa;
+        s_seg[ns].tbase = st;
+        s_seg[ns].na = na;
+        s_seg[ns].nt = nt;
+        s_seg[ns].poff = 0;
+        sa += na;
+        st += nt;
+        ++ns;
+        ++g;
+      }
+      const int split = (sa + 3) & ~3;
+      for (int q = 0; q < ns; ++q) {
+        s_seg[q].tbase += split;
+        for (int r = 0; r < s_seg[q].na; ++r) s_seg_of[s_seg[q].abase + r] = (uint8_t)q;
+        for (int r = 0; r < s_seg[q].nt; ++r) s_seg_of[s_seg[q].tbase + r] = (uint8_t)q;
+      }
+      for (int r = sa; r < split; ++r) s_seg_of[r] = SEG_NONE;
+      s_next = g;
+      s_nseg = ns;
+      s_split = split;
+      s_R = split + st;
+    }
+    __syncthreads();
+    const int nseg = s_nseg;
+    if (nseg == 0) break;
+    const int R = s_R;
+    const int split = s_split;
+    for (int idx = tid; idx < AFC * split; idx += NT) {
+      const int r = idx % split, k = idx / split;
+      float v = 0.0f;
+      if (s_seg_of[r] != SEG_NONE) {
+        const Seg sg = s_seg[s_seg_of[r]];
+        v = P.agent_feats[((size_t)sg.e * MA + (r - sg.abase)) * AFC + k];
+      }
+      big_t[k * TS + r] = v;
+    }
+    for (int idx = tid; idx < TF * (R - split); idx += NT) {
+      const int r = split + idx % (R - split), k = idx / (R - split);
+      const Seg sg = s_seg[s_seg_of[r]];
+      z_t[k * TS + r] = P.task_feats[((size_t)sg.e * MT + (r - sg.tbase)) * TF + k];
+    }
+    __syncthreads();
+    linear_t(big_t, 0, split, AFC, lin1(w + o.agent_proj_w, w + o.agent_proj_b), D, D, x_t, nullptr, false);
+    linear_t(z_t, split, R, TF, lin1(w + o.task_proj_w, w + o.task_proj_b), D, D, x_t, nullptr, false);
+    for (int idx = tid; idx < D * R; idx += NT) {
+      const int k = idx / R, r = idx - k * R;
+      x_t[k * TS + r] += w[o.type_embed + (r < split ? 0 : D) + k];
+    }
+    __syncthreads();
+    for (int l = 0; l < 2; ++l) {
+      linear_t(x_t, 0, R, D, lin1(w + o.enc_in_w[l], w + o.enc_in_b[l]), 3 * D, 3 * D, big_t, nullptr, false);
+      attention_t(big_t, R, split, s_seg, s_seg_of, false, y_t);
+      linear_t(y_t, 0, R, D, lin1(w + o.enc_out_w[l], w + o.enc_out_b[l]), D, D, z_t, x_t, false);
+      layer_norm_t(z_t, R, w + o.enc_n1_w[l], w + o.enc_n1_b[l]);
+      linear_t(z_t, 0, R, D, lin1(w + o.enc_l1_w[l], w + o.enc_l1_b[l]), FF, FF, big_t, nullptr, true);
+      linear_t(big_t, 0, R, FF, lin1(w + o.enc_l2_w[l], w + o.enc_l2_b[l]), D, D, x_t, z_t, false);
+      layer_norm_t(x_t, R, w + o.enc_n2_w[l], w + o.enc_n2_b[l]);
+    }
+    // heads: one thread per token
+    if (tid < R && s_seg_of[tid] != SEG_NONE) {
+      const int r = tid;
+      const Seg sg = s_seg[s_seg_of[r]];
+      const bool is_agent = r < split;
+      const float* hw = w + (is_agent ? o.commit_w : o.priority_w);
+      float acc = w[is_agent ? o.commit_b : o.priority_b];
+#pragma unroll 8
+      for (int k = 0; k < D; ++k) acc = fmaf(hw[k], x_t[k * TS + r], acc);
+      const float v = 1.0f / (1.0f + expf(-acc));
+      if (is_agent) P.com[(size_t)sg.e * MA + (r - sg.abase)] = v;
+      else P.pri[(size_t)sg.e * MT + (r - sg.tbase)] = v;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace muav_scorer
+
+extern "C" int muav_att_commit_vectors(const float* d_params, const muav_attcommit_offsets* offsets, const float* d_task_feats,
+                                       const uint8_t* d_task_mask, const float* d_agent_feats13, const uint8_t* d_agent_mask,
+                                       const int32_t* d_env_idx, const uint8_t* d_need, int n, int max_tasks, int max_agents,
+                                       float* d_priorities, float* d_commits, void* stream) {
+  using namespace muav_scorer;
+  if (!d_params || !offsets || !d_task_feats || !d_task_mask || !d_agent_feats13 || !d_agent_mask || !d_priorities || !d_commits)
+    return -22;
+  if (n < 0 || max_tasks < 1 || max_agents < 1 || max_agents + max_tasks > 48 || max_agents > 16) return -22;
+  if (n == 0) return 0;
+  CommitParams P;
+  P.w = d_params;
+  P.o = *offsets;
+  P.task_feats = d_task_feats;
+  P.task_mask = d_task_mask;
+  P.agent_feats = d_agent_feats13;
+  P.agent_mask = d_agent_mask;
+  P.env_idx = d_env_idx;
+  P.need = d_need;
+  P.pri = d_priorities;
+  P.com = d_commits;
+  P.n = n;
+  P.max_tasks = max_tasks;
+  P.max_agents = max_agents;
+  const size_t smem = sizeof(float) * (size_t)(3 * D * TS + 3 * D * TS);
+  static bool set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(att_commit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -1000 - (int)e;
+    if (dev >= 0 && dev < 64) set[dev] = true;
+  }
+  const int group = 3;
+  att_commit_kernel<<<(n + group - 1) / group, NT, smem, (cudaStream_t)stream>>>(P, group);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -1000 - (int)e;
+}
 
 extern "C" int muav_att_context_pair_scores(const float* d_params, const muav_attpair_offsets* offsets,
                                             const float* d_task_feats, const uint8_t* d_task_mask,

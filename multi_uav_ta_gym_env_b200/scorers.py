@@ -564,3 +564,78 @@ class FusedAttPairScorer:
             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         if rc != 0:
             raise RuntimeError(f"muav_att_context_pair_scores failed: {rc}")
+
+
+class FusedAttCommitScorer:
+    """AttCommitNet forward as one CUDA kernel (csrc/muav_scorer.cu att_commit_kernel, C ABI muav_att_commit_vectors): the
+    pair kernel's packing (three environments per 64-token pass, only valid tokens) with two encoder layers and the
+    priority / commit heads.  Outputs feed AllocSpec.att_commit() (plan_pri / plan_commit)."""
+
+    def __init__(self, net, device):
+        import ctypes as C
+
+        from . import _lib
+
+        sd = net.state_dict()
+        if len(net.encoder.layers) != 2 or sd["task_proj.weight"].shape != (64, TASK_FEAT_DIM) \
+                or sd["agent_proj.weight"].shape != (64, 13) or sd["encoder.layers.0.linear1.weight"].shape != (128, 64):
+            raise ValueError("the fused kernel implements the default AttCommitNet (d_model 64, 4 heads, 2 layers)")
+        self.lib = _lib.cuda_lib()
+        self.offsets = _lib.MuavAttCommitOffsets()
+        chunks, pos = [], 0
+
+        def put(t, transpose):
+            nonlocal pos
+            t = t.detach().to(torch.float32)
+            if transpose:
+                t = t.t().contiguous()
+            t = t.reshape(-1)
+            pos = (pos + 3) // 4 * 4
+            at = pos
+            chunks.append((at, t))
+            pos += t.numel()
+            return at
+
+        o = self.offsets
+        o.agent_proj_w, o.agent_proj_b = put(sd["agent_proj.weight"], True), put(sd["agent_proj.bias"], False)
+        o.task_proj_w, o.task_proj_b = put(sd["task_proj.weight"], True), put(sd["task_proj.bias"], False)
+        o.type_embed = put(sd["type_embed.weight"], False)
+        for l in range(2):
+            pre = f"encoder.layers.{l}."
+            o.enc_in_w[l], o.enc_in_b[l] = put(sd[pre + "self_attn.in_proj_weight"], True), put(sd[pre + "self_attn.in_proj_bias"], False)
+            o.enc_out_w[l], o.enc_out_b[l] = put(sd[pre + "self_attn.out_proj.weight"], True), put(sd[pre + "self_attn.out_proj.bias"], False)
+            o.enc_l1_w[l], o.enc_l1_b[l] = put(sd[pre + "linear1.weight"], True), put(sd[pre + "linear1.bias"], False)
+            o.enc_l2_w[l], o.enc_l2_b[l] = put(sd[pre + "linear2.weight"], True), put(sd[pre + "linear2.bias"], False)
+            o.enc_n1_w[l], o.enc_n1_b[l] = put(sd[pre + "norm1.weight"], False), put(sd[pre + "norm1.bias"], False)
+            o.enc_n2_w[l], o.enc_n2_b[l] = put(sd[pre + "norm2.weight"], False), put(sd[pre + "norm2.bias"], False)
+        o.priority_w, o.priority_b = put(sd["priority_head.weight"], False), put(sd["priority_head.bias"], False)
+        o.commit_w, o.commit_b = put(sd["commit_head.weight"], False), put(sd["commit_head.bias"], False)
+        buf = torch.zeros(pos, dtype=torch.float32)
+        for p, t in chunks:
+            buf[p:p + t.numel()] = t.cpu()
+        self.params = buf.to(device)
+        self.device = device
+        self._C = C
+
+    @torch.no_grad()
+    def vectors(self, tok: dict, pri_out: torch.Tensor, com_out: torch.Tensor, idx: Optional[torch.Tensor] = None,
+                use_need: bool = False):
+        """tok: fused commit tokens (enable_fused_tokens(commit=True); masks uint8) or a tokens_commit() dict; rows of
+        environments that are not scored are left untouched."""
+        C = self._C
+        E, MT = pri_out.shape
+        MA = com_out.shape[1]
+        tm = tok["task_mask_u8"] if "task_mask_u8" in tok else tok["task_mask"].to(torch.uint8)
+        am = tok["agent_mask_u8"] if "agent_mask_u8" in tok else tok["agent_mask"].to(torch.uint8)
+        n = E if idx is None else int(idx.numel())
+        if n == 0:
+            return
+        if idx is not None and idx.dtype != torch.int32:
+            idx = idx.to(torch.int32)
+        rc = self.lib.dll.muav_att_commit_vectors(
+            self.params.data_ptr(), C.byref(self.offsets), tok["task_feats"].data_ptr(), tm.data_ptr(),
+            tok["agent_feats"].data_ptr(), am.data_ptr(), None if idx is None else idx.data_ptr(),
+            tok["need"].data_ptr() if use_need else None, n, MT, MA, pri_out.data_ptr(), com_out.data_ptr(),
+            C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"muav_att_commit_vectors failed: {rc}")

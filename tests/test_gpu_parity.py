@@ -1258,3 +1258,50 @@ def test_commit_and_escort_collectors_match_the_oracle_and_trainers_run():
     before = {k: v.clone() for k, v in xnet.state_dict().items()}
     losses = T.train_escort(make_env(wps_config("WPS_escort"), list(range(32))), xnet, episodes=1)
     assert len(losses) > 5 and all(np.isfinite(losses)) and moved(before, xnet)
+
+
+def test_fused_commit_scorer_kernel_and_fused_commit_tokens():
+    """csrc/muav_scorer.cu att_commit_kernel vs the PyTorch AttCommitNet forward on real commit tokens (fp32, 2e-5), the
+    commit tokens emitted by the step kernel (muav_token_out.agent_feat_dim = 13) vs the standalone muav_tokens_commit, and
+    the fused pipeline (tokens -> kernel -> AllocSpec.att_commit) against the PyTorch-scored pipeline."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+    from multi_uav_ta_gym_env_b200.scorers import AttCommitNet, FusedAttCommitScorer, commit_vectors
+
+    cfg = wps_config("WPS_commit")
+    E = 192
+    env = make_env(cfg, list(range(E)))
+    env.step_allocated(AllocSpec.urgency_commit(15), n_steps=40)
+    torch.manual_seed(2)
+    net = AttCommitNet().cuda().eval()
+    fused = FusedAttCommitScorer(net, torch.device("cuda"))
+    tok = env.tokens_commit(32, 16)
+    want_p, want_c = commit_vectors(net, tok)
+    got_p = torch.full_like(want_p, 7.0)
+    got_c = torch.full_like(want_c, 7.0)
+    fused.vectors(tok, got_p, got_c)
+    assert (got_p - want_p).abs().max().item() < 2e-5 and (got_c - want_c).abs().max().item() < 2e-5
+    assert want_p.max().item() > 0.1 and want_c.max().item() > 0.1
+    idx = torch.arange(5, 150, 3, device="cuda", dtype=torch.int32)
+    got_p2 = torch.full_like(want_p, 7.0)
+    got_c2 = torch.full_like(want_c, 7.0)
+    fused.vectors(tok, got_p2, got_c2, idx)
+    assert (got_p2[idx.long()] - want_p[idx.long()]).abs().max().item() < 2e-5 and bool((got_p2[0] == 7.0).all())
+    # fused emission of the commit tokens: after every step the rows with need == 1 equal the standalone builder's
+    ftok = env.enable_fused_tokens(32, 16, 15, 0b111, commit=True)
+    env.refresh_fused_tokens()
+    spec = AllocSpec.att_commit(15)
+    pri = torch.zeros(E, 32, device="cuda")
+    com = torch.zeros(E, 16, device="cuda")
+    seen = 0
+    for t in range(40):
+        fused.vectors(ftok, pri, com, use_need=True)
+        env.step_allocated(spec, 1, plan_pri=pri, plan_commit=com)
+        need = ftok["need"].bool()
+        ref = env.tokens_commit(32, 16)
+        for k, fk in (("task_feats", "task_feats"), ("agent_feats", "agent_feats"), ("task_ids", "task_ids")):
+            assert torch.equal(ftok[fk][need], ref[k][need]), (t, k)
+        assert torch.equal(ftok["task_mask_u8"][need].bool(), ref["task_mask"][need])
+        assert torch.equal(ftok["agent_mask_u8"][need].bool(), ref["agent_mask"][need])
+        seen += int(need.sum().item())
+    assert seen > E
+    assert int(env.error_flags().abs().max().item()) == 0
