@@ -1,0 +1,969 @@
+// Att-Pair scorer forward on the 5th-generation tensor cores (tcgen05 + TMEM), same function as att_pair_kernel in
+// muav_scorer.cu (AttPairNet, TaskAllocation/Hybrid/PairCostHybrid.py:89-151, scores = tanh(logits) * clamp * edge_valid,
+// :266-278).
+//
+// One CTA per SM owns all 512 TMEM columns.  A pass packs the live tokens of up to eight environments into the 128
+// rows of an M = 128 MMA (agents first, then tasks; row = TMEM lane).  Every linear layer is D[128 x N] = A[128 x K] *
+// W[N x K]^T with
+//   * A (the activations) in TMEM, written there by the previous layer's epilogue with tcgen05.st -- each worker thread
+//     owns one token row, so LayerNorm, residuals and ReLU are thread-local and activations never pass through shared
+//     memory;
+//   * W streamed from L2 into a four-slot shared-memory ring by a producer thread (cp.async.bulk, 1-D TMA), packed by
+//     muav_att_pair_tc_pack in the canonical K-major no-swizzle layout the MMA reads;
+//   * 3xTF32: x = hi + lo with hi = the upper 19 bits; hi*hi + hi*lo + lo*hi accumulate in fp32 (the dropped lo*lo term
+//     is 2^-22 relative), which keeps the 2e-5 score tolerance of the fp32 kernel.
+// Token-type specific layers (projections, cross-attention in/out, first pair-head layer) run both weight sets over all
+// rows into different TMEM columns; the epilogue of a row reads the columns of its type.
+// Attention reads q from TMEM and k / v from a token-major shared-memory tile; the pair head is two more MMAs over
+// tiles of 128 valid (agent, task) pairs.
+//
+// Roles: warps 0-7 workers (row = 32 * (warp & 3) + lane, warps w and w + 4 split the columns), warp 8 lane 0 issues the
+// MMAs, warp 9 lane 0 streams the weights.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "../../include/muav.h"
+
+namespace muav_tc {
+
+constexpr int D = 64;
+constexpr int HD = 16;
+constexpr int TF = 13, AF = 12;
+constexpr int ROWS = 128;
+constexpr int NWORK = 256;
+constexpr int NT = 320;
+constexpr int NSLOT = 4;
+constexpr int SLOT_BYTES = 32768;
+constexpr int KV_STRIDE = 132;  // floats per token row of the k | v tile (conflict-free float4 rows)
+constexpr int ZG_STRIDE = 68;   // floats per token row of the z and g tiles of the pair head
+constexpr int KVG_BYTES = (ROWS * KV_STRIDE > 2 * ROWS * ZG_STRIDE ? ROWS * KV_STRIDE : 2 * ROWS * ZG_STRIDE) * 4;
+constexpr int PLIST_MAX = 4096;
+constexpr int DYN_SMEM = NSLOT * SLOT_BYTES + KVG_BYTES + PLIST_MAX * 2;
+constexpr int GMAX = 8;    // environments per pass
+constexpr int GLIST = 16;  // environments per CTA
+
+// TMEM columns
+constexpr int A0_HI = 0, A0_LO = 64;        // layer input x (hi / lo), 64 features
+constexpr int F_HI = 256, F_LO = 272;       // raw features, K padded to 16
+constexpr int AO_HI = 320, AO_LO = 384;     // self-attention output
+constexpr int H_HI = 256, H_LO = 384;       // feed-forward hidden, 128 features
+constexpr int AO2_HI = 192, AO2_LO = 256;   // cross-attention output
+constexpr int U_HI = 256, U_LO = 320;       // pair tile: a*t products, then the first hidden layer
+
+// ---- weight chunks in consumption order (one ring slot each)
+struct ChunkDesc {
+  uint32_t off;   // float offset in the packed buffer
+  uint16_t nc, kc;
+  uint16_t a_hi, a_lo, d_col;
+  uint8_t acc, first, last;
+};
+constexpr int NCHUNK = 22;
+constexpr int CH_PAIR1 = 20, CH_PAIR2 = 21;
+#define CH(off, nc, kc, ahi, alo, d, acc, first, last) \
+  ChunkDesc { off, nc, kc, ahi, alo, d, acc, first, last }
+constexpr uint32_t C64 = 64 * 64 * 2, C16 = 64 * 16 * 2, C32 = 32 * 64 * 2;
+__constant__ ChunkDesc c_chunks[NCHUNK] = {
+    CH(0, 64, 16, F_HI, F_LO, 128, 0, 1, 0),                      // 0 agent_proj
+    CH(C16, 64, 16, F_HI, F_LO, 192, 0, 0, 1),                    // 1 task_proj
+    CH(2 * C16, 64, 64, A0_HI, A0_LO, 128, 0, 1, 0),              // 2 enc_in q
+    CH(2 * C16 + C64, 64, 64, A0_HI, A0_LO, 192, 0, 0, 0),        // 3 enc_in k
+    CH(2 * C16 + 2 * C64, 64, 64, A0_HI, A0_LO, 256, 0, 0, 1),    // 4 enc_in v
+    CH(2 * C16 + 3 * C64, 64, 64, AO_HI, AO_LO, 448, 0, 1, 1),    // 5 enc_out
+    CH(2 * C16 + 4 * C64, 64, 64, A0_HI, A0_LO, 128, 0, 1, 0),    // 6 linear1 [0, 64)
+    CH(2 * C16 + 5 * C64, 64, 64, A0_HI, A0_LO, 192, 0, 0, 1),    // 7 linear1 [64, 128)
+    CH(2 * C16 + 6 * C64, 64, 64, H_HI, H_LO, 128, 0, 1, 0),      // 8 linear2, k [0, 64)
+    CH(2 * C16 + 7 * C64, 64, 64, H_HI + 64, H_LO + 64, 128, 1, 0, 1),  // 9 linear2, k [64, 128)
+    CH(2 * C16 + 8 * C64, 64, 64, A0_HI, A0_LO, 128, 0, 1, 0),    // 10 cross_a2t in q
+    CH(2 * C16 + 9 * C64, 64, 64, A0_HI, A0_LO, 192, 0, 0, 0),    // 11 cross_a2t in k
+    CH(2 * C16 + 10 * C64, 64, 64, A0_HI, A0_LO, 256, 0, 0, 0),   // 12 cross_a2t in v
+    CH(2 * C16 + 11 * C64, 64, 64, A0_HI, A0_LO, 320, 0, 0, 0),   // 13 cross_t2a in q
+    CH(2 * C16 + 12 * C64, 64, 64, A0_HI, A0_LO, 384, 0, 0, 0),   // 14 cross_t2a in k
+    CH(2 * C16 + 13 * C64, 64, 64, A0_HI, A0_LO, 448, 0, 0, 1),   // 15 cross_t2a in v
+    CH(2 * C16 + 14 * C64, 64, 64, AO2_HI, AO2_LO, 384, 0, 1, 0), // 16 cross_a2t out
+    CH(2 * C16 + 15 * C64, 64, 64, AO2_HI, AO2_LO, 448, 0, 0, 1), // 17 cross_t2a out
+    CH(2 * C16 + 16 * C64, 64, 64, A0_HI, A0_LO, 128, 0, 1, 0),   // 18 head1, agent block
+    CH(2 * C16 + 17 * C64, 64, 64, A0_HI, A0_LO, 192, 0, 0, 1),   // 19 head1, task block
+    CH(2 * C16 + 18 * C64, 64, 64, U_HI, U_LO, 384, 0, 1, 1),     // 20 head1, product block (per pair tile)
+    CH(2 * C16 + 19 * C64, 32, 64, U_HI, U_LO, 448, 0, 1, 1),     // 21 head2 (per pair tile)
+};
+constexpr uint32_t TCW_FLOATS = 2 * C16 + 19 * C64 + C32;
+
+// ---- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// bounded wait: a protocol error traps (the launch fails) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(phase)
+        : "memory");
+    if (!done && clock64() - t0 > 4000000000LL) __trap();
+  } while (!done);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// 16 consecutive columns of this thread's TMEM lane (issue only; tc_wait_ld() before the values are used)
+__device__ __forceinline__ void tmem_ld16(uint32_t a, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(a)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t a, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(a),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+// x = hi + lo exactly; hi has the 10 mantissa bits TF32 keeps
+__device__ __forceinline__ void split16(const float* x, float* hi, float* lo) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    hi[i] = __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u);
+    lo[i] = x[i] - hi[i];
+  }
+}
+// store 16 features of this thread's row as an MMA A operand (hi and lo planes)
+__device__ __forceinline__ void st_operand16(uint32_t tl, int col_hi, int col_lo, int c, const float* x) {
+  float hi[16], lo[16];
+  split16(x, hi, lo);
+  tmem_st16(tl + col_hi + c, hi);
+  tmem_st16(tl + col_lo + c, lo);
+}
+// 16 accumulator columns of this thread's row from the column block of its token type.
+// wtype (warp-uniform): 0 = every row of the warp is an agent row, 1 = every row a task row, 2 = mixed
+__device__ __forceinline__ void ld_variant16(uint32_t tl, int col_agent, int col_task, int c, bool is_agent, int wtype, float* v) {
+  if (wtype == 0) {
+    tmem_ld16(tl + col_agent + c, v);
+  } else if (wtype == 1) {
+    tmem_ld16(tl + col_task + c, v);
+  } else {
+    float b[16];
+    tmem_ld16(tl + col_agent + c, v);
+    tmem_ld16(tl + col_task + c, b);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = is_agent ? v[i] : b[i];
+  }
+}
+
+// shared-memory matrix descriptor: no swizzle, K-major (validated by tools/tc_probe)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// instruction descriptor: fp32 accumulate, TF32 x TF32, both K-major
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, one K = 8 step
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// the MMAs of one weight chunk: hi*hi + hi*lo + lo*hi over K in steps of 8
+__device__ __forceinline__ void issue_chunk(uint32_t tm, const ChunkDesc& c, const unsigned char* slot) {
+  const uint32_t idesc = make_idesc(ROWS, c.nc);
+  const uint32_t lbo = (uint32_t)c.nc * 16u;
+  const uint32_t plane = (uint32_t)c.nc * c.kc * 4u;
+  const uint32_t b0 = smem_u32(slot);
+  uint32_t acc = c.acc;
+#pragma unroll 1
+  for (int term = 0; term < 3; ++term) {
+    const uint32_t a_col = term == 2 ? c.a_lo : c.a_hi;
+    const uint32_t b_base = b0 + (term == 1 ? plane : 0u);
+#pragma unroll 1
+    for (int k8 = 0; k8 < c.kc / 8; ++k8) {
+      mma_ts(tm + c.d_col, tm + a_col + k8 * 8, make_desc(b_base + k8 * 2 * lbo, lbo, 128), idesc, acc);
+      acc = 1;
+    }
+  }
+}
+
+struct Params {
+  const float* w;
+  muav_attpair_offsets o;
+  const float* tcw;
+  const float* task_feats;
+  const uint8_t* task_mask;
+  const float* agent_feats;
+  const uint8_t* agent_mask;
+  const float* edge_valid;
+  const int32_t* env_idx;
+  const uint8_t* need;
+  float* scores;
+  int n, max_tasks, max_agents;
+  float clamp;
+  float* dbg;   // development: [stage][128][64] dump of the layer inputs of CTA 0's first pass, or NULL
+};
+
+struct Seg {
+  int e, abase, tbase, na, nt;
+};
+#define SEG_NONE 0xFF
+
+struct PickArgs {
+  const uint8_t* need;
+  const int32_t* env_idx;
+  int n;
+};
+// CTA c takes the counted launch slots of rank [c * group, (c + 1) * group) (same rule as muav_scorer.cu)
+__device__ int pick_envs(const PickArgs P, int group, int* s_env, int* s_scan) {
+  const int tid = threadIdx.x;
+  const int c = blockIdx.x;
+  if (!P.need) {
+    const int m = min(group, P.n - c * group);
+    if (tid < m) s_env[tid] = P.env_idx ? P.env_idx[c * group + tid] : c * group + tid;
+    __syncthreads();
+    return m > 0 ? m : 0;
+  }
+  const int chunk = (P.n + NT - 1) / NT;
+  const int lo = min(P.n, tid * chunk), hi = min(P.n, lo + chunk);
+  int cnt = 0;
+  for (int b = lo; b < hi; ++b) cnt += P.need[P.env_idx ? P.env_idx[b] : b] != 0;
+  const int lane = tid & 31, wid = tid >> 5;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_scan[wid] = incl;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int w = 0; w < NT / 32; ++w) { const int v = s_scan[w]; s_scan[w] = run; run += v; }
+    s_scan[NT / 32] = run;
+  }
+  __syncthreads();
+  const int excl = s_scan[wid] + incl - cnt;
+  const int total = s_scan[NT / 32];
+  const int r0 = c * group;
+  int m = total - r0;
+  if (m > group) m = group;
+  if (m > 0 && cnt > 0 && excl < r0 + m && excl + cnt > r0) {
+    int r = excl;
+    for (int b = lo; b < hi; ++b) {
+      const int e = P.env_idx ? P.env_idx[b] : b;
+      if (P.need[e] != 0) {
+        if (r >= r0 && r < r0 + m) s_env[r - r0] = e;
+        ++r;
+      }
+    }
+  }
+  __syncthreads();
+  return m > 0 ? m : 0;
+}
+
+// development dump of this thread's 32 columns of x (A0 planes)
+__device__ __forceinline__ void dump_a0(const Params& P, int stage, uint32_t tl, int row, int half) {
+  if (!P.dbg || blockIdx.x != 0) return;
+  for (int g = 0; g < 2; ++g) {
+    const int c = half * 32 + g * 16;
+    float h[16], l[16];
+    tmem_ld16(tl + A0_HI + c, h);
+    tmem_ld16(tl + A0_LO + c, l);
+    for (int i = 0; i < 16; ++i) P.dbg[((size_t)stage * ROWS + row) * D + c + i] = h[i] + l[i];
+  }
+}
+
+// softmax(q k^T / 4) v for the two heads of this thread, keys = the task / agent tokens of the row's environment
+// (cross: agents attend tasks, tasks attend agents).  q from TMEM, k | v from the shared tile, output to TMEM as the
+// A operand of the out-projection.
+__device__ __forceinline__ void attention(uint32_t tl, const float* __restrict__ kv, int half, bool on, const Seg sg,
+                                          bool cross, bool is_agent, int wtype, int qcol_agent, int qcol_task,
+                                          const float* __restrict__ qb_agent, const float* __restrict__ qb_task, int ao_hi,
+                                          int ao_lo) {
+  int k0[2] = {sg.abase, sg.tbase};
+  int k1[2] = {sg.abase + sg.na, sg.tbase + sg.nt};
+  if (cross) {
+    if (is_agent) k1[0] = k0[0];
+    else k1[1] = k0[1];
+  }
+  const float* qb = is_agent ? qb_agent : qb_task;
+#pragma unroll 1
+  for (int hh = 0; hh < 2; ++hh) {
+    const int h = half * 2 + hh;
+    float q[HD];
+    ld_variant16(tl, qcol_agent, qcol_task, h * HD, is_agent, wtype, q);
+#pragma unroll
+    for (int d = 0; d < HD; ++d) q[d] = (q[d] + __ldg(&qb[h * HD + d])) * 0.25f;
+    float acc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = 0.0f;
+    if (on) {
+      float m = -INFINITY, l = 0.0f;
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+        for (int j = k0[rr]; j < k1[rr]; ++j) {
+          const float4* kr = (const float4*)&kv[j * KV_STRIDE + h * HD];
+          const float4* vr = (const float4*)&kv[j * KV_STRIDE + D + h * HD];
+          float s = 0.0f;
+#pragma unroll
+          for (int d4 = 0; d4 < HD / 4; ++d4) {
+            const float4 kk = kr[d4];
+            s = fmaf(q[4 * d4], kk.x, s);
+            s = fmaf(q[4 * d4 + 1], kk.y, s);
+            s = fmaf(q[4 * d4 + 2], kk.z, s);
+            s = fmaf(q[4 * d4 + 3], kk.w, s);
+          }
+          if (s > m) {
+            const float c = __expf(m - s);
+            l *= c;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) acc[d] *= c;
+            m = s;
+          }
+          const float p = __expf(s - m);
+          l += p;
+#pragma unroll
+          for (int d4 = 0; d4 < HD / 4; ++d4) {
+            const float4 vv = vr[d4];
+            acc[4 * d4] = fmaf(p, vv.x, acc[4 * d4]);
+            acc[4 * d4 + 1] = fmaf(p, vv.y, acc[4 * d4 + 1]);
+            acc[4 * d4 + 2] = fmaf(p, vv.z, acc[4 * d4 + 2]);
+            acc[4 * d4 + 3] = fmaf(p, vv.w, acc[4 * d4 + 3]);
+          }
+        }
+      const float inv = 1.0f / l;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc[d] *= inv;
+    }
+    __syncwarp();
+    st_operand16(tl, ao_hi, ao_lo, h * HD, acc);
+  }
+}
+
+// k | v columns of the in-projection (+ bias) into the shared token-major tile: the thread with half 0 moves k, half 1 v
+__device__ __forceinline__ void kv_epilogue(uint32_t tl, float* __restrict__ kv, int row, int half, bool is_agent, int wtype,
+                                            int col_agent, int col_task, const float* __restrict__ b_agent,
+                                            const float* __restrict__ b_task) {
+  const float* bias = (is_agent ? b_agent : b_task) + D + half * D;
+#pragma unroll 1
+  for (int g = 0; g < 4; ++g) {
+    float v[16];
+    ld_variant16(tl, col_agent + D + half * D, col_task + D + half * D, g * 16, is_agent, wtype, v);
+    float4* dst = (float4*)&kv[row * KV_STRIDE + half * D + g * 16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      dst[i] = make_float4(v[4 * i] + __ldg(&bias[g * 16 + 4 * i]), v[4 * i + 1] + __ldg(&bias[g * 16 + 4 * i + 1]),
+                           v[4 * i + 2] + __ldg(&bias[g * 16 + 4 * i + 2]), v[4 * i + 3] + __ldg(&bias[g * 16 + 4 * i + 3]));
+  }
+}
+
+// x <- LayerNorm(x + acc + bias) (eps 1e-5, biased variance) on this thread's row; the two threads of a row own 32
+// columns each and exchange partial sums through shared memory
+__device__ __forceinline__ void ln_epilogue(uint32_t tl, int row, int half, int d_col, const float* __restrict__ bias,
+                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                            float (*s_part)[2][ROWS]) {
+  float z[32];
+  float sum = 0.0f;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int c = half * 32 + g * 16;
+    float v[16], h[16], l[16];
+    tmem_ld16(tl + d_col + c, v);
+    tmem_ld16(tl + A0_HI + c, h);
+    tmem_ld16(tl + A0_LO + c, l);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      z[g * 16 + i] = (h[i] + l[i]) + (v[i] + __ldg(&bias[c + i]));
+      sum += z[g * 16 + i];
+    }
+  }
+  s_part[0][half][row] = sum;
+  worker_sync();
+  const float mean = (s_part[0][0][row] + s_part[0][1][row]) * (1.0f / D);
+  float var = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float d = z[i] - mean;
+    var = fmaf(d, d, var);
+  }
+  s_part[1][half][row] = var;
+  worker_sync();
+  var = s_part[1][0][row] + s_part[1][1][row];
+  const float inv = rsqrtf(var * (1.0f / D) + 1e-5f);
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int c = half * 32 + g * 16;
+    float y[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y[i] = (z[g * 16 + i] - mean) * inv * __ldg(&gamma[c + i]) + __ldg(&beta[c + i]);
+    st_operand16(tl, A0_HI, A0_LO, c, y);
+  }
+}
+
+__global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constant__ Params P, int group) {
+  extern __shared__ __align__(1024) unsigned char dsm[];
+  unsigned char* ring = dsm;
+  float* kvg = (float*)(dsm + NSLOT * SLOT_BYTES);
+  uint16_t* plist = (uint16_t*)(dsm + NSLOT * SLOT_BYTES + KVG_BYTES);
+  __shared__ __align__(8) uint64_t s_full[NSLOT], s_empty[NSLOT], s_a_ready, s_d_ready;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_env[GLIST], s_na[GLIST], s_nt[GLIST], s_scan[NT / 32 + 1];
+  __shared__ Seg s_seg[GMAX];
+  __shared__ uint8_t s_seg_of[ROWS];
+  __shared__ int s_nseg, s_R, s_split, s_next, s_nvalid;
+  __shared__ float s_part[2][2][ROWS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int MT = P.max_tasks, MA = P.max_agents;
+  const float* w = P.w;
+  const muav_attpair_offsets& o = P.o;
+
+  const int m = pick_envs(PickArgs{P.need, P.env_idx, P.n}, group, s_env, s_scan);
+  if (m == 0) return;
+  if (tid < m) {
+    const int e = s_env[tid];
+    const uint8_t* am = P.agent_mask + (size_t)e * MA;
+    const uint8_t* tmk = P.task_mask + (size_t)e * MT;
+    int na = 0, nt = 0;
+    while (na < MA && am[na] == 0) ++na;
+    while (nt < MT && tmk[nt] == 0) ++nt;
+    s_na[tid] = na;
+    s_nt[tid] = nt;
+  }
+  if (tid == 0) {
+    s_next = 0;
+    for (int i = 0; i < NSLOT; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 1);
+    }
+    mbar_init(&s_a_ready, NWORK);
+    mbar_init(&s_d_ready, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = s_tmem;
+  // scores of every picked environment start at zero (padded rows / columns, invalid edges)
+  for (int g = 0; g < m; ++g) {
+    float* sc = P.scores + (size_t)s_env[g] * MA * MT;
+    for (int idx = tid; idx < MA * MT; idx += NT) sc[idx] = 0.0f;
+  }
+
+  uint32_t seq = 0;  // weight chunks consumed / produced so far (MMA and producer threads)
+  uint32_t pa = 0;   // parity of s_a_ready (MMA thread)
+  uint32_t pd = 0;   // parity of s_d_ready (workers)
+  bool first_pass = true;
+  for (;;) {
+    // ---- next pass: as many of the remaining environments as fit 128 rows (at most GMAX)
+    if (tid == 0) {
+      int g = s_next, ns = 0, sa = 0, st = 0;
+      while (g < m && ns < GMAX) {
+        const int na = s_na[g], nt = s_nt[g];
+        if (na == 0 || nt == 0) { ++g; continue; }
+        if (((sa + na + 3) & ~3) + st + nt > ROWS) break;
+        s_seg[ns].e = s_env[g];
+        s_seg[ns].abase = sa;
+        s_seg[ns].tbase = st;
+        s_seg[ns].na = na;
+        s_seg[ns].nt = nt;
+        sa += na;
+        st += nt;
+        ++ns;
+        ++g;
+      }
+      const int split = (sa + 3) & ~3;
+      for (int r = 0; r < ROWS; ++r) s_seg_of[r] = SEG_NONE;
+      for (int q = 0; q < ns; ++q) {
+        s_seg[q].tbase += split;
+        for (int r = 0; r < s_seg[q].na; ++r) s_seg_of[s_seg[q].abase + r] = (uint8_t)q;
+        for (int r = 0; r < s_seg[q].nt; ++r) s_seg_of[s_seg[q].tbase + r] = (uint8_t)q;
+      }
+      s_next = g;
+      s_nseg = ns;
+      s_split = split;
+      s_R = split + st;
+      s_nvalid = 0;
+    }
+    __syncthreads();
+    const int nseg = s_nseg;
+    if (nseg == 0) break;
+    const int split = s_split;
+
+    if (warp == 9) {
+      // ================= producer: weight chunks through the ring
+      if (lane == 0) {
+        for (int c = 0; c < NCHUNK; ++c, ++seq) {
+          const int slot = seq & (NSLOT - 1);
+          const uint32_t use = seq / NSLOT;
+          if (use > 0) mbar_wait(&s_empty[slot], (use - 1) & 1);
+          const ChunkDesc cd = c_chunks[c];
+          const uint32_t bytes = (uint32_t)cd.nc * cd.kc * 8u;
+          mbar_expect_tx(&s_full[slot], bytes);
+          bulk_g2s(ring + slot * SLOT_BYTES, P.tcw + cd.off, bytes, &s_full[slot]);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 8) {
+      // ================= MMA issuer
+      if (lane == 0) {
+        int c = 0;
+        while (c < CH_PAIR1) {
+          mbar_wait(&s_a_ready, pa);
+          pa ^= 1;
+          tc_fence_after();
+          for (;;) {
+            const ChunkDesc cd = c_chunks[c];
+            const int slot = seq & (NSLOT - 1);
+            mbar_wait(&s_full[slot], (seq / NSLOT) & 1);
+            tc_fence_after();
+            issue_chunk(tm, cd, ring + slot * SLOT_BYTES);
+            tc_commit(&s_empty[slot]);
+            ++seq;
+            ++c;
+            if (cd.last) break;
+          }
+          tc_commit(&s_d_ready);
+        }
+        // pair head: the two weight chunks stay in their slots for every tile of the pass
+        mbar_wait(&s_a_ready, pa);
+        pa ^= 1;
+        const int nvalid = *(volatile int*)&s_nvalid;
+        const int ntiles = (nvalid + ROWS - 1) / ROWS;
+        const int slot1 = seq & (NSLOT - 1);
+        mbar_wait(&s_full[slot1], (seq / NSLOT) & 1);
+        ++seq;
+        const int slot2 = seq & (NSLOT - 1);
+        mbar_wait(&s_full[slot2], (seq / NSLOT) & 1);
+        ++seq;
+        for (int t = 0; t < ntiles; ++t) {
+          mbar_wait(&s_a_ready, pa);
+          pa ^= 1;
+          tc_fence_after();
+          issue_chunk(tm, c_chunks[CH_PAIR1], ring + slot1 * SLOT_BYTES);
+          tc_commit(&s_d_ready);
+          mbar_wait(&s_a_ready, pa);
+          pa ^= 1;
+          tc_fence_after();
+          issue_chunk(tm, c_chunks[CH_PAIR2], ring + slot2 * SLOT_BYTES);
+          tc_commit(&s_d_ready);
+        }
+        tc_commit(&s_empty[slot1]);
+        tc_commit(&s_empty[slot2]);
+      }
+      __syncwarp();
+    } else {
+      // ================= workers
+      const int q = warp & 3, half = warp >> 2;
+      const int row = q * 32 + lane;
+      const uint32_t tl = tm + ((uint32_t)(q * 32) << 16);
+      const int R = s_R;
+      const bool is_agent = row < split;
+      const int wtype = (q * 32 + 32 <= split) ? 0 : (q * 32 >= split ? 1 : 2);
+      const uint8_t sid = s_seg_of[row];
+      const bool on = sid != SEG_NONE;
+      Seg sg = s_seg[on ? sid : 0];
+      (void)R;
+
+      // ---- raw features as the A operand of the projections (K padded to 16)
+      if (half == 0) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = 0.0f;
+        if (on) {
+          if (is_agent) {
+            const float* src = P.agent_feats + ((size_t)sg.e * MA + (row - sg.abase)) * AF;
+#pragma unroll
+            for (int i = 0; i < AF; ++i) f[i] = src[i];
+          } else {
+            const float* src = P.task_feats + ((size_t)sg.e * MT + (row - sg.tbase)) * TF;
+#pragma unroll
+            for (int i = 0; i < TF; ++i) f[i] = src[i];
+          }
+        }
+        __syncwarp();
+        st_operand16(tl, F_HI, F_LO, 0, f);
+        tc_wait_st();
+      }
+      tc_fence_before();
+      mbar_arrive(&s_a_ready);
+
+      // ---- x = proj(feats) + type_embed
+      mbar_wait(&s_d_ready, pd);
+      pd ^= 1;
+      tc_fence_after();
+      {
+        const float* b = w + (is_agent ? o.agent_proj_b : o.task_proj_b);
+        const float* te = w + o.type_embed + (is_agent ? 0 : D);
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          const int c = half * 32 + g * 16;
+          float v[16];
+          ld_variant16(tl, 128, 192, c, is_agent, wtype, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = v[i] + __ldg(&b[c + i]) + __ldg(&te[c + i]);
+          st_operand16(tl, A0_HI, A0_LO, c, v);
+        }
+        tc_wait_st();
+        if (first_pass) dump_a0(P, 0, tl, row, half);
+      }
+      tc_fence_before();
+      mbar_arrive(&s_a_ready);
+
+      // ---- encoder self-attention
+      mbar_wait(&s_d_ready, pd);
+      pd ^= 1;
+      tc_fence_after();
+      kv_epilogue(tl, kvg, row, half, is_agent, 0, 128, 128, w + o.enc_in_b, w + o.enc_in_b);
+      worker_sync();
+      attention(tl, kvg, half, on, sg, false, is_agent, 0, 128, 128, w + o.enc_in_b, w + o.enc_in_b, AO_HI, AO_LO);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&s_a_ready);
+
+      // ---- x1 = LN1(x + out_proj(attn))
+      mbar_wait(&s_d_ready, pd);
+      pd ^= 1;
+      tc_fence_after();
+      ln_epilogue(tl, row, half, 448, w + o.enc_out_b, w + o.enc_n1_w, w + o.enc_n1_b, s_part);
+      tc_wait_st();
+      if (first_pass) dump_a0(P, 1, tl, row, half);
+      tc_fence_before();
+      mbar_arrive(&s_a_ready);
+
+      // ---- hidden = relu(linear1(x1))
+      mbar_wait(&s_d_ready, pd);
+      pd ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        const int c = half * 64 + g * 16;
+        float v[16];
+        tmem_ld16(tl + 128 + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(&w[o.enc_l1_b + c + i]), 0.0f);
+        st_operand16(tl, H_HI, H_LO, c, v);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&s_a_ready);
+
+      // ---- h = LN2(x1 + linear2(hidden))
+      mbar_wait(&s_d_ready, pd);
+      pd ^= 1;
+      tc_fence_after();
+      ln_epilogue(tl, row, half, 128, w + o.enc_l2_b, w + o.enc_n2_w, w + o.enc_n2_b, s_part);
+      tc_wait_st();
+      if (first_pass) dump_a0(P, 2, tl, row, half);
+      tc_fence_before();
+      mbar_arrive(&s_a_ready);
+
+      // ---- cross attention: agent rows take q from cross_a2t (columns 128..) and serve as k / v of cross_t2a
+      // (columns 320 + 64..); task rows the other way round
+      mbar_wait(&s_d_ready, pd);
+      pd ^= 1;
+      tc_fence_after();
+      kv_epilogue(tl, kvg, row, half, is_agent, wtype, 320, 128, w + o.t2a_in_b, w + o.a2t_in_b);
+      worker_sync();
+      attention(tl, kvg, half, on, sg, true, is_agent, wtype, 128, 320, w + o.a2t_in_b, w + o.t2a_in_b, AO2_HI, AO2_LO);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&s_a_ready);
+
+      // ---- z = h + out_proj(ctx) (a' / t'): the A operand of the first pair-head layer and, in shared memory, the
+      // source of the pair products
+      float* zt = kvg;
+      float* gt = kvg + ROWS * ZG_STRIDE;
+      mbar_wait(&s_d_ready, pd);
+      pd ^= 1;
+      tc_fence_after();
+      {
+        const float* b = w + (is_agent ? o.a2t_out_b : o.t2a_out_b);
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          const int c = half * 32 + g * 16;
+          float v[16], h[16], l[16];
+          ld_variant16(tl, 384, 448, c, is_agent, wtype, v);
+          tmem_ld16(tl + A0_HI + c, h);
+          tmem_ld16(tl + A0_LO + c, l);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = (h[i] + l[i]) + (v[i] + __ldg(&b[c + i]));
+          st_operand16(tl, A0_HI, A0_LO, c, v);
+          float4* dst = (float4*)&zt[row * ZG_STRIDE + c];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        tc_wait_st();
+        if (first_pass) dump_a0(P, 3, tl, row, half);
+      }
+      tc_fence_before();
+      mbar_arrive(&s_a_ready);
+
+      // ---- g = Wa a' (agent rows) / Wt t' + b1 (task rows); list of the pairs with a valid edge
+      mbar_wait(&s_d_ready, pd);
+      pd ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int g = 0; g < 2; ++g) {
+        const int c = half * 32 + g * 16;
+        float v[16];
+        ld_variant16(tl, 128, 192, c, is_agent, wtype, v);
+        if (!is_agent) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += __ldg(&w[o.head1_b + c + i]);
+        }
+        float4* dst = (float4*)&gt[row * ZG_STRIDE + c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+      for (int s = 0; s < nseg; ++s) {
+        const Seg ps = s_seg[s];
+        const float* ev = P.edge_valid + (size_t)ps.e * MA * MT;
+        for (int idx = tid; idx < ps.na * ps.nt; idx += NWORK) {
+          const int i = idx / ps.nt, j = idx - i * ps.nt;
+          if (ev[(size_t)i * MT + j] != 0.0f) plist[atomicAdd(&s_nvalid, 1)] = (uint16_t)(((ps.abase + i) << 7) | (ps.tbase + j));
+        }
+      }
+      worker_sync();
+      const int nvalid = s_nvalid;
+      tc_fence_before();
+      mbar_arrive(&s_a_ready);
+
+      // ---- pair tiles: logits = w3 . relu(W2 relu(Wat (a' * t') + g_a + g_t) + b2) + b3
+      const int ntiles = (nvalid + ROWS - 1) / ROWS;
+#pragma unroll 1
+      for (int t = 0; t < ntiles; ++t) {
+        const int p = t * ROWS + row;
+        const bool valid = p < nvalid;
+        const int pc = plist[valid ? p : 0];
+        const int ta = pc >> 7, tt = pc & 127;
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          const int c = half * 32 + g * 16;
+          const float4* za = (const float4*)&zt[ta * ZG_STRIDE + c];
+          const float4* zb = (const float4*)&zt[tt * ZG_STRIDE + c];
+          float u[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 a = za[i], b = zb[i];
+            u[4 * i] = a.x * b.x;
+            u[4 * i + 1] = a.y * b.y;
+            u[4 * i + 2] = a.z * b.z;
+            u[4 * i + 3] = a.w * b.w;
+          }
+          st_operand16(tl, U_HI, U_LO, c, u);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&s_a_ready);
+
+        mbar_wait(&s_d_ready, pd);
+        pd ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          const int c = half * 32 + g * 16;
+          const float4* ga = (const float4*)&gt[ta * ZG_STRIDE + c];
+          const float4* gb = (const float4*)&gt[tt * ZG_STRIDE + c];
+          float v[16];
+          tmem_ld16(tl + 384 + c, v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 a = ga[i], b = gb[i];
+            v[4 * i] = fmaxf(v[4 * i] + a.x + b.x, 0.0f);
+            v[4 * i + 1] = fmaxf(v[4 * i + 1] + a.y + b.y, 0.0f);
+            v[4 * i + 2] = fmaxf(v[4 * i + 2] + a.z + b.z, 0.0f);
+            v[4 * i + 3] = fmaxf(v[4 * i + 3] + a.w + b.w, 0.0f);
+          }
+          st_operand16(tl, U_HI, U_LO, c, v);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&s_a_ready);
+
+        mbar_wait(&s_d_ready, pd);
+        pd ^= 1;
+        tc_fence_after();
+        if (half == 0) {
+          float logit = __ldg(&w[o.head3_b]);
+#pragma unroll 1
+          for (int g = 0; g < 2; ++g) {
+            float v[16];
+            tmem_ld16(tl + 448 + g * 16, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              logit = fmaf(__ldg(&w[o.head3_w + g * 16 + i]), fmaxf(v[i] + __ldg(&w[o.head2_b + g * 16 + i]), 0.0f), logit);
+          }
+          if (valid) {
+            const Seg ps = s_seg[s_seg_of[ta]];
+            const size_t off = (size_t)ps.e * MA * MT + (size_t)(ta - ps.abase) * MT + (tt - ps.tbase);
+            P.scores[off] = tanhf(logit) * P.clamp * P.edge_valid[off];
+          }
+        }
+        // the next tile's products overwrite the operand columns: every read of this tile is complete (wait::ld above)
+        tc_fence_before();
+      }
+    }
+    first_pass = false;
+    __syncthreads();  // the next pass reuses the segment table and every buffer
+  }
+  // the two resident slots are released by commits that may still be in flight: wait for them before the CTA ends
+  if (warp == 8 && lane == 0 && seq >= 2) {
+    const uint32_t s1 = seq - 2, s2 = seq - 1;
+    mbar_wait(&s_empty[s1 & (NSLOT - 1)], (s1 / NSLOT) & 1);
+    mbar_wait(&s_empty[s2 & (NSLOT - 1)], (s2 / NSLOT) & 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512));
+}
+
+// ---- packing of the weights: every chunk as hi plane then lo plane, each [K/4][N][4] (K-major core matrices of 8 x 16 B)
+struct PackSrc {
+  int src[NCHUNK];   // float offset of W^T ([in][out], as packed by the host for the fp32 kernel) in the parameter buffer
+  int ldo[NCHUNK];   // row stride of W^T
+  int n0[NCHUNK], k0[NCHUNK], kreal[NCHUNK];
+};
+__global__ void tc_pack_kernel(const float* __restrict__ w, const __grid_constant__ PackSrc S, float* __restrict__ out) {
+  const int c = blockIdx.y;
+  const ChunkDesc cd = c_chunks[c];
+  const int total = cd.nc * cd.kc;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int n = idx / cd.kc, k = idx - n * cd.kc;
+    float x = 0.0f;
+    if (k < S.kreal[c]) x = w[S.src[c] + (size_t)(S.k0[c] + k) * S.ldo[c] + S.n0[c] + n];
+    const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    const int pos = ((k >> 2) * cd.nc + n) * 4 + (k & 3);
+    out[cd.off + pos] = hi;
+    out[cd.off + total + pos] = x - hi;
+  }
+}
+
+static float* g_dbg = nullptr;
+
+}  // namespace muav_tc
+
+extern "C" void muav_tc_debug_buffer_(float* d_dbg) { muav_tc::g_dbg = d_dbg; }
+
+extern "C" int64_t muav_att_pair_tc_floats(void) { return (int64_t)muav_tc::TCW_FLOATS; }
+
+extern "C" int muav_att_pair_tc_pack(const float* d_params, const muav_attpair_offsets* offsets, float* d_tc_weights,
+                                     void* stream) {
+  using namespace muav_tc;
+  if (!d_params || !offsets || !d_tc_weights) return -22;
+  if (offsets->has_context) return -22;
+  const muav_attpair_offsets& o = *offsets;
+  PackSrc S;
+  auto set = [&](int c, int src, int ldo, int n0, int k0, int kreal) {
+    S.src[c] = src; S.ldo[c] = ldo; S.n0[c] = n0; S.k0[c] = k0; S.kreal[c] = kreal;
+  };
+  set(0, o.agent_proj_w, D, 0, 0, AF);
+  set(1, o.task_proj_w, D, 0, 0, TF);
+  for (int i = 0; i < 3; ++i) set(2 + i, o.enc_in_w, 3 * D, i * D, 0, D);
+  set(5, o.enc_out_w, D, 0, 0, D);
+  set(6, o.enc_l1_w, 2 * D, 0, 0, D);
+  set(7, o.enc_l1_w, 2 * D, D, 0, D);
+  set(8, o.enc_l2_w, D, 0, 0, D);
+  set(9, o.enc_l2_w, D, 0, D, D);
+  for (int i = 0; i < 3; ++i) set(10 + i, o.a2t_in_w, 3 * D, i * D, 0, D);
+  for (int i = 0; i < 3; ++i) set(13 + i, o.t2a_in_w, 3 * D, i * D, 0, D);
+  set(16, o.a2t_out_w, D, 0, 0, D);
+  set(17, o.t2a_out_w, D, 0, 0, D);
+  set(18, o.head1_w, D, 0, 0, D);        // Wa: input features [0, 64) of pair_head.0
+  set(19, o.head1_w, D, 0, D, D);        // Wt: [64, 128)
+  set(20, o.head1_w, D, 0, 2 * D, D);    // Wat: [128, 192)
+  set(21, o.head2_w, D / 2, 0, 0, D);
+  tc_pack_kernel<<<dim3(8, NCHUNK), 256, 0, (cudaStream_t)stream>>>(d_params, S, d_tc_weights);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -1000 - (int)e;
+}
+
+extern "C" int muav_att_pair_scores_tc(const float* d_params, const muav_attpair_offsets* offsets, const float* d_tc_weights,
+                                       const float* d_task_feats, const uint8_t* d_task_mask, const float* d_agent_feats,
+                                       const uint8_t* d_agent_mask, const float* d_edge_valid, const int32_t* d_env_idx,
+                                       const uint8_t* d_need, int n, int max_tasks, int max_agents, float score_clamp,
+                                       float* d_scores, void* stream) {
+  using namespace muav_tc;
+  if (!d_params || !offsets || !d_tc_weights || !d_task_feats || !d_task_mask || !d_agent_feats || !d_agent_mask ||
+      !d_edge_valid || !d_scores)
+    return -22;
+  if (offsets->has_context) return -22;
+  if (n < 0 || max_tasks < 1 || max_agents < 1 || max_agents + max_tasks > 48 || max_agents > 16) return -22;
+  if (n == 0) return 0;
+  Params P;
+  P.w = d_params;
+  P.o = *offsets;
+  P.tcw = d_tc_weights;
+  P.task_feats = d_task_feats;
+  P.task_mask = d_task_mask;
+  P.agent_feats = d_agent_feats;
+  P.agent_mask = d_agent_mask;
+  P.edge_valid = d_edge_valid;
+  P.env_idx = d_env_idx;
+  P.need = d_need;
+  P.scores = d_scores;
+  P.n = n;
+  P.max_tasks = max_tasks;
+  P.max_agents = max_agents;
+  P.clamp = score_clamp;
+  P.dbg = g_dbg;
+  static bool set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(att_pair_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM);
+    if (e != cudaSuccess) return -1000 - (int)e;
+    if (dev >= 0 && dev < 64) set[dev] = true;
+  }
+  int group = 6;
+  const char* ge = getenv("MUAV_SCORER_TC_GROUP");
+  if (ge) group = atoi(ge);
+  if (group < 1) group = 1;
+  if (group > GLIST) group = GLIST;
+  att_pair_tc_kernel<<<(n + group - 1) / group, NT, DYN_SMEM, (cudaStream_t)stream>>>(P, group);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -1000 - (int)e;
+}

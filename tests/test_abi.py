@@ -16,7 +16,7 @@ def test_library_exports_header_symbols():
     ge.build_cuda()
     lib = _lib.cuda_lib()
     hdr = open(os.path.join(ROOT, "include", "muav.h")).read()
-    declared = set(re.findall(r"^(?:int|void|size_t|const char\*)\s+(muav_[a-z_]+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|void|size_t|const char\*)\s+(muav_[a-z_]+)\s*\(", hdr, flags=re.M))
     assert declared == set(_lib.ABI_SYMBOLS)
     for sym in declared:
         assert hasattr(lib.dll, sym), sym
