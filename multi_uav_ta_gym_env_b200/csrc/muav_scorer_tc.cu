@@ -253,20 +253,25 @@ struct PickArgs {
   const int32_t* env_idx;
   int n;
 };
-// CTA c takes the counted launch slots of rank [c * group, (c + 1) * group) (same rule as muav_scorer.cu)
-__device__ int pick_envs(const PickArgs P, int group, int* s_env, int* s_scan) {
+// Launch slots b in [0, n) map to environments e = env_idx ? env_idx[b] : b; a slot counts when need == NULL or
+// need[e] != 0 (same rule as muav_scorer.cu).  scan_envs: every thread counts its chunk of slots once; select_envs
+// writes the environments of rank [r0, r0 + m) to s_env.
+struct EnvScan {
+  int lo, hi, cnt, excl, total;
+};
+__device__ EnvScan scan_envs(const PickArgs P, int* s_scan) {
   const int tid = threadIdx.x;
-  const int c = blockIdx.x;
+  EnvScan S;
   if (!P.need) {
-    const int m = min(group, P.n - c * group);
-    if (tid < m) s_env[tid] = P.env_idx ? P.env_idx[c * group + tid] : c * group + tid;
-    __syncthreads();
-    return m > 0 ? m : 0;
+    S.lo = S.hi = S.cnt = S.excl = 0;
+    S.total = P.n;
+    return S;
   }
   const int chunk = (P.n + NT - 1) / NT;
-  const int lo = min(P.n, tid * chunk), hi = min(P.n, lo + chunk);
+  S.lo = min(P.n, tid * chunk);
+  S.hi = min(P.n, S.lo + chunk);
   int cnt = 0;
-  for (int b = lo; b < hi; ++b) cnt += P.need[P.env_idx ? P.env_idx[b] : b] != 0;
+  for (int b = S.lo; b < S.hi; ++b) cnt += P.need[P.env_idx ? P.env_idx[b] : b] != 0;
   const int lane = tid & 31, wid = tid >> 5;
   int incl = cnt;
 #pragma unroll
@@ -282,14 +287,20 @@ __device__ int pick_envs(const PickArgs P, int group, int* s_env, int* s_scan) {
     s_scan[NT / 32] = run;
   }
   __syncthreads();
-  const int excl = s_scan[wid] + incl - cnt;
-  const int total = s_scan[NT / 32];
-  const int r0 = c * group;
-  int m = total - r0;
-  if (m > group) m = group;
-  if (m > 0 && cnt > 0 && excl < r0 + m && excl + cnt > r0) {
-    int r = excl;
-    for (int b = lo; b < hi; ++b) {
+  S.cnt = cnt;
+  S.excl = s_scan[wid] + incl - cnt;
+  S.total = s_scan[NT / 32];
+  return S;
+}
+__device__ void select_envs(const PickArgs P, const EnvScan S, int r0, int m, int* s_env) {
+  const int tid = threadIdx.x;
+  if (!P.need) {
+    if (tid < m) s_env[tid] = P.env_idx ? P.env_idx[r0 + tid] : r0 + tid;
+    return;
+  }
+  if (S.cnt > 0 && S.excl < r0 + m && S.excl + S.cnt > r0) {
+    int r = S.excl;
+    for (int b = S.lo; b < S.hi; ++b) {
       const int e = P.env_idx ? P.env_idx[b] : b;
       if (P.need[e] != 0) {
         if (r >= r0 && r < r0 + m) s_env[r - r0] = e;
@@ -297,8 +308,6 @@ __device__ int pick_envs(const PickArgs P, int group, int* s_env, int* s_scan) {
       }
     }
   }
-  __syncthreads();
-  return m > 0 ? m : 0;
 }
 
 // development dump of this thread's 32 columns of x (A0 planes)
@@ -450,27 +459,22 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
   __shared__ int s_env[GLIST], s_na[GLIST], s_nt[GLIST], s_scan[NT / 32 + 1];
   __shared__ Seg s_seg[GMAX];
   __shared__ uint8_t s_seg_of[ROWS];
-  __shared__ int s_nseg, s_R, s_split, s_next, s_nvalid;
+  __shared__ int s_nseg, s_R, s_split, s_next, s_nvalid, s_done;
   __shared__ float s_part[2][2][ROWS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int MT = P.max_tasks, MA = P.max_agents;
   const float* w = P.w;
   const muav_attpair_offsets& o = P.o;
 
-  const int m = pick_envs(PickArgs{P.need, P.env_idx, P.n}, group, s_env, s_scan);
-  if (m == 0) return;
-  if (tid < m) {
-    const int e = s_env[tid];
-    const uint8_t* am = P.agent_mask + (size_t)e * MA;
-    const uint8_t* tmk = P.task_mask + (size_t)e * MT;
-    int na = 0, nt = 0;
-    while (na < MA && am[na] == 0) ++na;
-    while (nt < MT && tmk[nt] == 0) ++nt;
-    s_na[tid] = na;
-    s_nt[tid] = nt;
-  }
+  // work split: CTA b of the persistent (one per SM) grid takes the counted environments of rank [b * per, (b + 1) * per)
+  // and streams them through its passes (group > 0: `group` environments per CTA instead, A/B runs)
+  const PickArgs PA{P.need, P.env_idx, P.n};
+  const EnvScan ES = scan_envs(PA, s_scan);
+  const int T = ES.total;
+  const int per = group > 0 ? group : (T + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int stride = group > 0 ? (int)gridDim.x * per : T;   // group > 0: the grid strides over the groups
+  if ((int)blockIdx.x * per >= T) return;
   if (tid == 0) {
-    s_next = 0;
     for (int i = 0; i < NSLOT; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 1);
@@ -487,24 +491,51 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = s_tmem;
-  // scores of every picked environment start at zero (padded rows / columns, invalid edges)
-  for (int g = 0; g < m; ++g) {
-    float* sc = P.scores + (size_t)s_env[g] * MA * MT;
-    for (int idx = tid; idx < MA * MT; idx += NT) sc[idx] = 0.0f;
-  }
 
   uint32_t seq = 0;  // weight chunks consumed / produced so far (MMA and producer threads)
   uint32_t pa = 0;   // parity of s_a_ready (MMA thread)
   uint32_t pd = 0;   // parity of s_d_ready (workers)
   bool first_pass = true;
+  for (int r_lo = blockIdx.x * per; r_lo < T; r_lo += stride) {
+  const int r_hi = min(T, r_lo + per);
+  int cursor = r_lo;
+  while (cursor < r_hi) {
+  // the next (at most GLIST) environments of the range; a pass that the list leaves half empty is deferred to the next
+  // list when the range holds more environments
+  const int m = min(GLIST, r_hi - cursor);
+  const bool more = cursor + m < r_hi;
+  select_envs(PA, ES, cursor, m, s_env);
+  __syncthreads();
+  if (tid < m) {
+    const int e = s_env[tid];
+    const uint8_t* am = P.agent_mask + (size_t)e * MA;
+    const uint8_t* tmk = P.task_mask + (size_t)e * MT;
+    int na = 0, nt = 0;
+    while (na < MA && am[na] == 0) ++na;
+    while (nt < MT && tmk[nt] == 0) ++nt;
+    s_na[tid] = na;
+    s_nt[tid] = nt;
+  }
+  if (tid == 0) {
+    s_next = 0;
+    s_done = m;
+  }
+  // scores of every listed environment start at zero (padded rows / columns, invalid edges)
+  for (int g = 0; g < m; ++g) {
+    float* sc = P.scores + (size_t)s_env[g] * MA * MT;
+    for (int idx = tid; idx < MA * MT; idx += NT) sc[idx] = 0.0f;
+  }
+  __syncthreads();
   for (;;) {
     // ---- next pass: as many of the remaining environments as fit 128 rows (at most GMAX)
     if (tid == 0) {
+      const int g_first = s_next;
       int g = s_next, ns = 0, sa = 0, st = 0;
+      bool full = false;
       while (g < m && ns < GMAX) {
         const int na = s_na[g], nt = s_nt[g];
         if (na == 0 || nt == 0) { ++g; continue; }
-        if (((sa + na + 3) & ~3) + st + nt > ROWS) break;
+        if (((sa + na + 3) & ~3) + st + nt > ROWS) { full = true; break; }
         s_seg[ns].e = s_env[g];
         s_seg[ns].abase = sa;
         s_seg[ns].tbase = st;
@@ -514,6 +545,14 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
         st += nt;
         ++ns;
         ++g;
+      }
+      if (ns == GMAX) full = true;
+      if (!full && more && ns > 0 && g_first > 0) {
+        // the list ran out before the pass was full: take these environments up again with the next list
+        s_done = g_first;
+        ns = 0;
+        sa = st = 0;
+        g = m;
       }
       const int split = (sa + 3) & ~3;
       for (int r = 0; r < ROWS; ++r) s_seg_of[r] = SEG_NONE;
@@ -850,6 +889,10 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
     first_pass = false;
     __syncthreads();  // the next pass reuses the segment table and every buffer
   }
+  cursor += s_done;
+  __syncthreads();
+  }
+  }
   // the two resident slots are released by commits that may still be in flight: wait for them before the CTA ends
   if (warp == 8 && lane == 0 && seq >= 2) {
     const uint32_t s1 = seq - 2, s2 = seq - 1;
@@ -958,12 +1001,21 @@ extern "C" int muav_att_pair_scores_tc(const float* d_params, const muav_attpair
     if (e != cudaSuccess) return -1000 - (int)e;
     if (dev >= 0 && dev < 64) set[dev] = true;
   }
-  int group = 6;
+  // persistent grid, one CTA per SM (MUAV_SCORER_TC_GROUP = g > 0: g environments per CTA, grid-strided: A/B runs)
+  static int n_sm[64];
+  if (dev < 0 || dev >= 64 || n_sm[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev < 0 ? 0 : dev);
+    if (v < 1) v = 1;
+    if (dev >= 0 && dev < 64) n_sm[dev] = v;
+  }
+  const int sms = (dev >= 0 && dev < 64) ? n_sm[dev] : 148;
+  int group = 0;
   const char* ge = getenv("MUAV_SCORER_TC_GROUP");
   if (ge) group = atoi(ge);
-  if (group < 1) group = 1;
-  if (group > GLIST) group = GLIST;
-  att_pair_tc_kernel<<<(n + group - 1) / group, NT, DYN_SMEM, (cudaStream_t)stream>>>(P, group);
+  if (group < 0) group = 0;
+  int grid = n < sms ? n : sms;
+  att_pair_tc_kernel<<<grid, NT, DYN_SMEM, (cudaStream_t)stream>>>(P, group);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -1000 - (int)e;
 }
