@@ -51,43 +51,50 @@ constexpr int H_HI = 256, H_LO = 384;       // feed-forward hidden, 128 features
 constexpr int AO2_HI = 192, AO2_LO = 256;   // cross-attention output
 constexpr int U_HI = 256, U_LO = 320;       // pair tile: a*t products, then the first hidden layer
 
-// ---- weight chunks in consumption order (one ring slot each)
+// ---- weight chunks in consumption order (one ring slot each).  A chunk holds all N output features of its layer for a
+// slice of K (so that one MMA covers the whole N: fewer, larger instructions); token-type specific layers that share
+// their A operand are one layer with the two weight matrices stacked along N.
 struct ChunkDesc {
   uint32_t off;   // float offset in the packed buffer
   uint16_t nc, kc;
   uint16_t a_hi, a_lo, d_col;
-  uint8_t acc, first, last;
+  uint8_t acc, last;
 };
-constexpr int NCHUNK = 22;
-constexpr int CH_PAIR1 = 20, CH_PAIR2 = 21;
-#define CH(off, nc, kc, ahi, alo, d, acc, first, last) \
-  ChunkDesc { off, nc, kc, ahi, alo, d, acc, first, last }
-constexpr uint32_t C64 = 64 * 64 * 2, C16 = 64 * 16 * 2, C32 = 32 * 64 * 2;
+constexpr int NCHUNK = 24;
+constexpr int CH_PAIR1 = 22, CH_PAIR2 = 23;
+#define CH(off, nc, kc, ahi, alo, d, acc, last) \
+  ChunkDesc { off, nc, kc, ahi, alo, d, acc, last }
+constexpr uint32_t S_PROJ = 128 * 16 * 2, S_IN = 192 * 16 * 2, S_64 = 64 * 64 * 2, S_128 = 128 * 32 * 2, S_H2 = 32 * 64 * 2;
+constexpr uint32_t O_IN = S_PROJ, O_OUT = O_IN + 4 * S_IN, O_L1 = O_OUT + S_64, O_L2 = O_L1 + 2 * S_128, O_XA = O_L2 + 2 * S_64,
+                   O_XB = O_XA + 4 * S_IN, O_XO = O_XB + 4 * S_IN, O_H1 = O_XO + 2 * S_128, O_P1 = O_H1 + 2 * S_128,
+                   O_P2 = O_P1 + S_64;
 __constant__ ChunkDesc c_chunks[NCHUNK] = {
-    CH(0, 64, 16, F_HI, F_LO, 128, 0, 1, 0),                      // 0 agent_proj
-    CH(C16, 64, 16, F_HI, F_LO, 192, 0, 0, 1),                    // 1 task_proj
-    CH(2 * C16, 64, 64, A0_HI, A0_LO, 128, 0, 1, 0),              // 2 enc_in q
-    CH(2 * C16 + C64, 64, 64, A0_HI, A0_LO, 192, 0, 0, 0),        // 3 enc_in k
-    CH(2 * C16 + 2 * C64, 64, 64, A0_HI, A0_LO, 256, 0, 0, 1),    // 4 enc_in v
-    CH(2 * C16 + 3 * C64, 64, 64, AO_HI, AO_LO, 448, 0, 1, 1),    // 5 enc_out
-    CH(2 * C16 + 4 * C64, 64, 64, A0_HI, A0_LO, 128, 0, 1, 0),    // 6 linear1 [0, 64)
-    CH(2 * C16 + 5 * C64, 64, 64, A0_HI, A0_LO, 192, 0, 0, 1),    // 7 linear1 [64, 128)
-    CH(2 * C16 + 6 * C64, 64, 64, H_HI, H_LO, 128, 0, 1, 0),      // 8 linear2, k [0, 64)
-    CH(2 * C16 + 7 * C64, 64, 64, H_HI + 64, H_LO + 64, 128, 1, 0, 1),  // 9 linear2, k [64, 128)
-    CH(2 * C16 + 8 * C64, 64, 64, A0_HI, A0_LO, 128, 0, 1, 0),    // 10 cross_a2t in q
-    CH(2 * C16 + 9 * C64, 64, 64, A0_HI, A0_LO, 192, 0, 0, 0),    // 11 cross_a2t in k
-    CH(2 * C16 + 10 * C64, 64, 64, A0_HI, A0_LO, 256, 0, 0, 0),   // 12 cross_a2t in v
-    CH(2 * C16 + 11 * C64, 64, 64, A0_HI, A0_LO, 320, 0, 0, 0),   // 13 cross_t2a in q
-    CH(2 * C16 + 12 * C64, 64, 64, A0_HI, A0_LO, 384, 0, 0, 0),   // 14 cross_t2a in k
-    CH(2 * C16 + 13 * C64, 64, 64, A0_HI, A0_LO, 448, 0, 0, 1),   // 15 cross_t2a in v
-    CH(2 * C16 + 14 * C64, 64, 64, AO2_HI, AO2_LO, 384, 0, 1, 0), // 16 cross_a2t out
-    CH(2 * C16 + 15 * C64, 64, 64, AO2_HI, AO2_LO, 448, 0, 0, 1), // 17 cross_t2a out
-    CH(2 * C16 + 16 * C64, 64, 64, A0_HI, A0_LO, 128, 0, 1, 0),   // 18 head1, agent block
-    CH(2 * C16 + 17 * C64, 64, 64, A0_HI, A0_LO, 192, 0, 0, 1),   // 19 head1, task block
-    CH(2 * C16 + 18 * C64, 64, 64, U_HI, U_LO, 384, 0, 1, 1),     // 20 head1, product block (per pair tile)
-    CH(2 * C16 + 19 * C64, 32, 64, U_HI, U_LO, 448, 0, 1, 1),     // 21 head2 (per pair tile)
+    CH(0, 128, 16, F_HI, F_LO, 128, 0, 1),                              // 0 agent_proj | task_proj
+    CH(O_IN, 192, 16, A0_HI, A0_LO, 128, 0, 0),                         // 1-4 encoder in_proj (q | k | v), K slices of 16
+    CH(O_IN + S_IN, 192, 16, A0_HI + 16, A0_LO + 16, 128, 1, 0),
+    CH(O_IN + 2 * S_IN, 192, 16, A0_HI + 32, A0_LO + 32, 128, 1, 0),
+    CH(O_IN + 3 * S_IN, 192, 16, A0_HI + 48, A0_LO + 48, 128, 1, 1),
+    CH(O_OUT, 64, 64, AO_HI, AO_LO, 448, 0, 1),                         // 5 encoder out_proj
+    CH(O_L1, 128, 32, A0_HI, A0_LO, 128, 0, 0),                         // 6-7 linear1, K slices of 32
+    CH(O_L1 + S_128, 128, 32, A0_HI + 32, A0_LO + 32, 128, 1, 1),
+    CH(O_L2, 64, 64, H_HI, H_LO, 128, 0, 0),                            // 8-9 linear2, K slices of 64
+    CH(O_L2 + S_64, 64, 64, H_HI + 64, H_LO + 64, 128, 1, 1),
+    CH(O_XA, 192, 16, A0_HI, A0_LO, 128, 0, 0),                         // 10-13 cross_a2t in_proj
+    CH(O_XA + S_IN, 192, 16, A0_HI + 16, A0_LO + 16, 128, 1, 0),
+    CH(O_XA + 2 * S_IN, 192, 16, A0_HI + 32, A0_LO + 32, 128, 1, 0),
+    CH(O_XA + 3 * S_IN, 192, 16, A0_HI + 48, A0_LO + 48, 128, 1, 0),
+    CH(O_XB, 192, 16, A0_HI, A0_LO, 320, 0, 0),                         // 14-17 cross_t2a in_proj
+    CH(O_XB + S_IN, 192, 16, A0_HI + 16, A0_LO + 16, 320, 1, 0),
+    CH(O_XB + 2 * S_IN, 192, 16, A0_HI + 32, A0_LO + 32, 320, 1, 0),
+    CH(O_XB + 3 * S_IN, 192, 16, A0_HI + 48, A0_LO + 48, 320, 1, 1),
+    CH(O_XO, 128, 32, AO2_HI, AO2_LO, 384, 0, 0),                       // 18-19 cross_a2t | cross_t2a out_proj
+    CH(O_XO + S_128, 128, 32, AO2_HI + 32, AO2_LO + 32, 384, 1, 1),
+    CH(O_H1, 128, 32, A0_HI, A0_LO, 128, 0, 0),                         // 20-21 head1 agent block | task block
+    CH(O_H1 + S_128, 128, 32, A0_HI + 32, A0_LO + 32, 128, 1, 1),
+    CH(O_P1, 64, 64, U_HI, U_LO, 384, 0, 1),                            // 22 head1 product block (per pair tile)
+    CH(O_P2, 32, 64, U_HI, U_LO, 448, 0, 1),                            // 23 head2 (per pair tile)
 };
-constexpr uint32_t TCW_FLOATS = 2 * C16 + 19 * C64 + C32;
+constexpr uint32_t TCW_FLOATS = O_P2 + S_H2;
 
 // ---- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -123,6 +130,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
     if (!done && clock64() - t0 > 4000000000LL) __trap();
   } while (!done);
 }
+// the same with a back-off between polls (waiters that must not steal issue slots from the MMA thread)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t phase) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(phase)
+        : "memory");
+    if (done) break;
+    __nanosleep(40);
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -130,6 +157,13 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// workers: one lane polls the accumulator barrier, the warp follows
+__device__ __forceinline__ void wait_d(uint64_t* bar, uint32_t& phase, int lane) {
+  if (lane == 0) mbar_wait_relaxed(bar, phase);
+  __syncwarp();
+  phase ^= 1;
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // 16 consecutive columns of this thread's TMEM lane (issue only; tc_wait_ld() before the values are used)
@@ -208,22 +242,31 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
 }
 
 // the MMAs of one weight chunk: hi*hi + hi*lo + lo*hi over K in steps of 8
-__device__ __forceinline__ void issue_chunk(uint32_t tm, const ChunkDesc& c, const unsigned char* slot) {
+template <int KC>
+__device__ __forceinline__ void issue_chunk_k(uint32_t tm, const ChunkDesc& c, uint32_t b0) {
   const uint32_t idesc = make_idesc(ROWS, c.nc);
   const uint32_t lbo = (uint32_t)c.nc * 16u;
-  const uint32_t plane = (uint32_t)c.nc * c.kc * 4u;
-  const uint32_t b0 = smem_u32(slot);
+  const uint32_t plane16 = ((uint32_t)c.nc * KC * 4u) >> 4;   // lo plane, in 16-byte units
+  const uint32_t step16 = (2u * lbo) >> 4;                    // one K = 8 step
+  const uint64_t desc0 = make_desc(b0, lbo, 128);
+  const uint32_t d = tm + c.d_col;
   uint32_t acc = c.acc;
-#pragma unroll 1
+#pragma unroll
   for (int term = 0; term < 3; ++term) {
-    const uint32_t a_col = term == 2 ? c.a_lo : c.a_hi;
-    const uint32_t b_base = b0 + (term == 1 ? plane : 0u);
-#pragma unroll 1
-    for (int k8 = 0; k8 < c.kc / 8; ++k8) {
-      mma_ts(tm + c.d_col, tm + a_col + k8 * 8, make_desc(b_base + k8 * 2 * lbo, lbo, 128), idesc, acc);
+    const uint32_t a = tm + (term == 2 ? c.a_lo : c.a_hi);
+    const uint64_t db = desc0 + (term == 1 ? plane16 : 0u);
+#pragma unroll
+    for (int k8 = 0; k8 < KC / 8; ++k8) {
+      mma_ts(d, a + k8 * 8, db + (uint64_t)(k8 * step16), idesc, acc);
       acc = 1;
     }
   }
+}
+__device__ __forceinline__ void issue_chunk(uint32_t tm, const ChunkDesc& c, const unsigned char* slot) {
+  const uint32_t b0 = smem_u32(slot);
+  if (c.kc == 16) issue_chunk_k<16>(tm, c, b0);
+  else if (c.kc == 32) issue_chunk_k<32>(tm, c, b0);
+  else issue_chunk_k<64>(tm, c, b0);
 }
 
 struct Params {
@@ -578,7 +621,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
         for (int c = 0; c < NCHUNK; ++c, ++seq) {
           const int slot = seq & (NSLOT - 1);
           const uint32_t use = seq / NSLOT;
-          if (use > 0) mbar_wait(&s_empty[slot], (use - 1) & 1);
+          if (use > 0) mbar_wait_relaxed(&s_empty[slot], (use - 1) & 1);
           const ChunkDesc cd = c_chunks[c];
           const uint32_t bytes = (uint32_t)cd.nc * cd.kc * 8u;
           mbar_expect_tx(&s_full[slot], bytes);
@@ -671,9 +714,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       mbar_arrive(&s_a_ready);
 
       // ---- x = proj(feats) + type_embed
-      mbar_wait(&s_d_ready, pd);
-      pd ^= 1;
-      tc_fence_after();
+      wait_d(&s_d_ready, pd, lane);
       {
         const float* b = w + (is_agent ? o.agent_proj_b : o.task_proj_b);
         const float* te = w + o.type_embed + (is_agent ? 0 : D);
@@ -693,9 +734,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       mbar_arrive(&s_a_ready);
 
       // ---- encoder self-attention
-      mbar_wait(&s_d_ready, pd);
-      pd ^= 1;
-      tc_fence_after();
+      wait_d(&s_d_ready, pd, lane);
       kv_epilogue(tl, kvg, row, half, is_agent, 0, 128, 128, w + o.enc_in_b, w + o.enc_in_b);
       worker_sync();
       attention(tl, kvg, half, on, sg, false, is_agent, 0, 128, 128, w + o.enc_in_b, w + o.enc_in_b, AO_HI, AO_LO);
@@ -704,9 +743,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       mbar_arrive(&s_a_ready);
 
       // ---- x1 = LN1(x + out_proj(attn))
-      mbar_wait(&s_d_ready, pd);
-      pd ^= 1;
-      tc_fence_after();
+      wait_d(&s_d_ready, pd, lane);
       ln_epilogue(tl, row, half, 448, w + o.enc_out_b, w + o.enc_n1_w, w + o.enc_n1_b, s_part);
       tc_wait_st();
       if (first_pass) dump_a0(P, 1, tl, row, half);
@@ -714,9 +751,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       mbar_arrive(&s_a_ready);
 
       // ---- hidden = relu(linear1(x1))
-      mbar_wait(&s_d_ready, pd);
-      pd ^= 1;
-      tc_fence_after();
+      wait_d(&s_d_ready, pd, lane);
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
         const int c = half * 64 + g * 16;
@@ -731,9 +766,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       mbar_arrive(&s_a_ready);
 
       // ---- h = LN2(x1 + linear2(hidden))
-      mbar_wait(&s_d_ready, pd);
-      pd ^= 1;
-      tc_fence_after();
+      wait_d(&s_d_ready, pd, lane);
       ln_epilogue(tl, row, half, 128, w + o.enc_l2_b, w + o.enc_n2_w, w + o.enc_n2_b, s_part);
       tc_wait_st();
       if (first_pass) dump_a0(P, 2, tl, row, half);
@@ -742,9 +775,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
 
       // ---- cross attention: agent rows take q from cross_a2t (columns 128..) and serve as k / v of cross_t2a
       // (columns 320 + 64..); task rows the other way round
-      mbar_wait(&s_d_ready, pd);
-      pd ^= 1;
-      tc_fence_after();
+      wait_d(&s_d_ready, pd, lane);
       kv_epilogue(tl, kvg, row, half, is_agent, wtype, 320, 128, w + o.t2a_in_b, w + o.a2t_in_b);
       worker_sync();
       attention(tl, kvg, half, on, sg, true, is_agent, wtype, 128, 320, w + o.a2t_in_b, w + o.t2a_in_b, AO2_HI, AO2_LO);
@@ -756,9 +787,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       // source of the pair products
       float* zt = kvg;
       float* gt = kvg + ROWS * ZG_STRIDE;
-      mbar_wait(&s_d_ready, pd);
-      pd ^= 1;
-      tc_fence_after();
+      wait_d(&s_d_ready, pd, lane);
       {
         const float* b = w + (is_agent ? o.a2t_out_b : o.t2a_out_b);
 #pragma unroll 1
@@ -782,9 +811,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       mbar_arrive(&s_a_ready);
 
       // ---- g = Wa a' (agent rows) / Wt t' + b1 (task rows); list of the pairs with a valid edge
-      mbar_wait(&s_d_ready, pd);
-      pd ^= 1;
-      tc_fence_after();
+      wait_d(&s_d_ready, pd, lane);
 #pragma unroll 1
       for (int g = 0; g < 2; ++g) {
         const int c = half * 32 + g * 16;
@@ -839,9 +866,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
         tc_fence_before();
         mbar_arrive(&s_a_ready);
 
-        mbar_wait(&s_d_ready, pd);
-        pd ^= 1;
-        tc_fence_after();
+        wait_d(&s_d_ready, pd, lane);
 #pragma unroll 1
         for (int g = 0; g < 2; ++g) {
           const int c = half * 32 + g * 16;
@@ -863,9 +888,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
         tc_fence_before();
         mbar_arrive(&s_a_ready);
 
-        mbar_wait(&s_d_ready, pd);
-        pd ^= 1;
-        tc_fence_after();
+        wait_d(&s_d_ready, pd, lane);
         if (half == 0) {
           float logit = __ldg(&w[o.head3_b]);
 #pragma unroll 1
@@ -906,9 +929,10 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
 
 // ---- packing of the weights: every chunk as hi plane then lo plane, each [K/4][N][4] (K-major core matrices of 8 x 16 B)
 struct PackSrc {
-  int src[NCHUNK];   // float offset of W^T ([in][out], as packed by the host for the fp32 kernel) in the parameter buffer
-  int ldo[NCHUNK];   // row stride of W^T
-  int n0[NCHUNK], k0[NCHUNK], kreal[NCHUNK];
+  // output feature n of chunk c comes from matrix 0 (n < nsplit) or matrix 1 (n - nsplit); src: float offset of W^T
+  // ([in][out], as packed by the host for the fp32 kernel) in the parameter buffer, ldo its row stride
+  int src[NCHUNK][2], ldo[NCHUNK][2], n0[NCHUNK][2], kreal[NCHUNK][2];
+  int nsplit[NCHUNK], k0[NCHUNK];
 };
 __global__ void tc_pack_kernel(const float* __restrict__ w, const __grid_constant__ PackSrc S, float* __restrict__ out) {
   const int c = blockIdx.y;
@@ -916,8 +940,11 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, const __grid_constan
   const int total = cd.nc * cd.kc;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int n = idx / cd.kc, k = idx - n * cd.kc;
+    const int v = n < S.nsplit[c] ? 0 : 1;
+    const int nn = v ? n - S.nsplit[c] : n;
+    const int kk = S.k0[c] + k;
     float x = 0.0f;
-    if (k < S.kreal[c]) x = w[S.src[c] + (size_t)(S.k0[c] + k) * S.ldo[c] + S.n0[c] + n];
+    if (kk < S.kreal[c][v]) x = w[S.src[c][v] + (size_t)kk * S.ldo[c][v] + S.n0[c][v] + nn];
     const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
     const int pos = ((k >> 2) * cd.nc + n) * 4 + (k & 3);
     out[cd.off + pos] = hi;
@@ -940,25 +967,27 @@ extern "C" int muav_att_pair_tc_pack(const float* d_params, const muav_attpair_o
   if (offsets->has_context) return -22;
   const muav_attpair_offsets& o = *offsets;
   PackSrc S;
-  auto set = [&](int c, int src, int ldo, int n0, int k0, int kreal) {
-    S.src[c] = src; S.ldo[c] = ldo; S.n0[c] = n0; S.k0[c] = k0; S.kreal[c] = kreal;
+  // one matrix: every output feature from (src, ldo, n0); K slice [k0, k0 + kc) of kreal input features
+  auto one = [&](int c, int src, int ldo, int n0, int k0, int kreal) {
+    S.src[c][0] = S.src[c][1] = src; S.ldo[c][0] = S.ldo[c][1] = ldo; S.n0[c][0] = S.n0[c][1] = n0;
+    S.kreal[c][0] = S.kreal[c][1] = kreal; S.nsplit[c] = 1 << 20; S.k0[c] = k0;
   };
-  set(0, o.agent_proj_w, D, 0, 0, AF);
-  set(1, o.task_proj_w, D, 0, 0, TF);
-  for (int i = 0; i < 3; ++i) set(2 + i, o.enc_in_w, 3 * D, i * D, 0, D);
-  set(5, o.enc_out_w, D, 0, 0, D);
-  set(6, o.enc_l1_w, 2 * D, 0, 0, D);
-  set(7, o.enc_l1_w, 2 * D, D, 0, D);
-  set(8, o.enc_l2_w, D, 0, 0, D);
-  set(9, o.enc_l2_w, D, 0, D, D);
-  for (int i = 0; i < 3; ++i) set(10 + i, o.a2t_in_w, 3 * D, i * D, 0, D);
-  for (int i = 0; i < 3; ++i) set(13 + i, o.t2a_in_w, 3 * D, i * D, 0, D);
-  set(16, o.a2t_out_w, D, 0, 0, D);
-  set(17, o.t2a_out_w, D, 0, 0, D);
-  set(18, o.head1_w, D, 0, 0, D);        // Wa: input features [0, 64) of pair_head.0
-  set(19, o.head1_w, D, 0, D, D);        // Wt: [64, 128)
-  set(20, o.head1_w, D, 0, 2 * D, D);    // Wat: [128, 192)
-  set(21, o.head2_w, D / 2, 0, 0, D);
+  auto two = [&](int c, int srcA, int kA, int srcB, int kB, int ldo, int k0) {   // [A; B] stacked along N, 64 rows each
+    S.src[c][0] = srcA; S.src[c][1] = srcB; S.ldo[c][0] = S.ldo[c][1] = ldo; S.n0[c][0] = S.n0[c][1] = 0;
+    S.kreal[c][0] = kA; S.kreal[c][1] = kB; S.nsplit[c] = D; S.k0[c] = k0;
+  };
+  two(0, o.agent_proj_w, AF, o.task_proj_w, TF, D, 0);
+  for (int i = 0; i < 4; ++i) one(1 + i, o.enc_in_w, 3 * D, 0, 16 * i, D);
+  one(5, o.enc_out_w, D, 0, 0, D);
+  for (int i = 0; i < 2; ++i) one(6 + i, o.enc_l1_w, 2 * D, 0, 32 * i, D);
+  for (int i = 0; i < 2; ++i) one(8 + i, o.enc_l2_w, D, 0, 64 * i, 2 * D);
+  for (int i = 0; i < 4; ++i) one(10 + i, o.a2t_in_w, 3 * D, 0, 16 * i, D);
+  for (int i = 0; i < 4; ++i) one(14 + i, o.t2a_in_w, 3 * D, 0, 16 * i, D);
+  for (int i = 0; i < 2; ++i) two(18 + i, o.a2t_out_w, D, o.t2a_out_w, D, D, 32 * i);
+  // pair_head.0: input features [0, 64) agent block, [64, 128) task block, [128, 192) product block
+  for (int i = 0; i < 2; ++i) two(20 + i, o.head1_w, D, o.head1_w + D * D, D, D, 32 * i);
+  one(22, o.head1_w + 2 * D * D, D, 0, 0, D);
+  one(23, o.head2_w, D / 2, 0, 0, D);
   tc_pack_kernel<<<dim3(8, NCHUNK), 256, 0, (cudaStream_t)stream>>>(d_params, S, d_tc_weights);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -1000 - (int)e;

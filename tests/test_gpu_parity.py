@@ -556,12 +556,15 @@ def test_scorer_near_tie_flips_are_logged_and_bounded():
     assert int(env_k.error_flags().abs().max().item()) == 0 and int(env_t.error_flags().abs().max().item()) == 0
 
 
-def test_fused_scorer_kernel_matches_torch_module():
-    """csrc/muav_scorer.cu vs the PyTorch AttPairNet forward on real tokens (fp32, tolerance 2e-5 on scores)."""
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_fused_scorer_kernel_matches_torch_module(tc, monkeypatch):
+    """csrc/muav_scorer_tc.cu (tcgen05, the default) and csrc/muav_scorer.cu (FP32 pipe, MUAV_SCORER_TC=0) vs the PyTorch
+    AttPairNet forward on real tokens (fp32, tolerance 2e-5 on scores)."""
     from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
     from multi_uav_ta_gym_env_b200.scorers import AttPairNet, FusedAttPairScorer, pair_scores
 
-    for case, steps in (("WPS_hard", 60), ("WPS_commit", 75), ("WPS_hard", 0)):
+    monkeypatch.setenv("MUAV_SCORER_TC", tc)
+    for case, steps in (("WPS_hard", 60), ("WPS_commit", 75), ("WPS_hard", 0), ("WPS_burst", 40)):
         cfg = wps_config(case)
         E = 200
         env = make_env(cfg, list(range(E)))
@@ -576,6 +579,7 @@ def test_fused_scorer_kernel_matches_torch_module():
                      "edge_valid": tok["edge_valid"]}
         want = pair_scores(net, eager_tok)
         fused = FusedAttPairScorer(net, torch.device("cuda"))
+        assert (fused.tcw is not None) == (tc == "1")
         got = torch.full_like(want, 7.0)
         fused.score(tok, got)
         assert (got - want).abs().max().item() < 2e-5, (case, (got - want).abs().max().item())
