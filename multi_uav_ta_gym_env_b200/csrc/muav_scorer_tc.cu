@@ -50,6 +50,9 @@ constexpr int AO_HI = 320, AO_LO = 384;     // self-attention output
 constexpr int H_HI = 256, H_LO = 384;       // feed-forward hidden, 128 features
 constexpr int AO2_HI = 192, AO2_LO = 256;   // cross-attention output
 constexpr int U_HI = 256, U_LO = 320;       // pair tile: a*t products, then the first hidden layer
+constexpr int P1_D = 384, P2_D = 448;       // pair tile accumulators
+constexpr int U2_HI = 0, U2_LO = 64;        // second pair tile of a round (x and the head1 accumulators are dead by then)
+constexpr int P1B_D = 128, P2B_D = 192;
 
 // ---- weight chunks in consumption order (one ring slot each).  A chunk holds all N output features of its layer for a
 // slice of K (so that one MMA covers the whole N: fewer, larger instructions); token-type specific layers that share
@@ -146,7 +149,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t phase)
         : "r"(addr), "r"(phase)
         : "memory");
     if (done) break;
-    __nanosleep(40);
+    __nanosleep(20);
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
@@ -385,7 +388,7 @@ __device__ __forceinline__ void attention(uint32_t tl, const float* __restrict__
     float q[HD];
     ld_variant16(tl, qcol_agent, qcol_task, h * HD, is_agent, wtype, q);
 #pragma unroll
-    for (int d = 0; d < HD; ++d) q[d] = (q[d] + __ldg(&qb[h * HD + d])) * 0.25f;
+    for (int d = 0; d < HD; ++d) q[d] = (q[d] + __ldg(&qb[h * HD + d])) * (0.25f * 1.44269504088896340736f);   // scores in log2 units
     float acc[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) acc[d] = 0.0f;
@@ -406,13 +409,13 @@ __device__ __forceinline__ void attention(uint32_t tl, const float* __restrict__
             s = fmaf(q[4 * d4 + 3], kk.w, s);
           }
           if (s > m) {
-            const float c = __expf(m - s);
+            const float c = exp2f(m - s);
             l *= c;
 #pragma unroll
             for (int d = 0; d < HD; ++d) acc[d] *= c;
             m = s;
           }
-          const float p = __expf(s - m);
+          const float p = exp2f(s - m);
           l += p;
 #pragma unroll
           for (int d4 = 0; d4 < HD / 4; ++d4) {
@@ -539,6 +542,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
   uint32_t pa = 0;   // parity of s_a_ready (MMA thread)
   uint32_t pd = 0;   // parity of s_d_ready (workers)
   bool first_pass = true;
+  int n_ts = 0;
   for (int r_lo = blockIdx.x * per; r_lo < T; r_lo += stride) {
   const int r_hi = min(T, r_lo + per);
   int cursor = r_lo;
@@ -549,15 +553,26 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
   const bool more = cursor + m < r_hi;
   select_envs(PA, ES, cursor, m, s_env);
   __syncthreads();
-  if (tid < m) {
-    const int e = s_env[tid];
-    const uint8_t* am = P.agent_mask + (size_t)e * MA;
-    const uint8_t* tmk = P.task_mask + (size_t)e * MT;
+  // valid rows / columns are a prefix by construction of the token builders: one warp per environment counts them
+  for (int g = warp; g < m; g += NT / 32) {
+    const int e = s_env[g];
     int na = 0, nt = 0;
-    while (na < MA && am[na] == 0) ++na;
-    while (nt < MT && tmk[nt] == 0) ++nt;
-    s_na[tid] = na;
-    s_nt[tid] = nt;
+    for (int base = 0; base < MA; base += 32) {
+      const unsigned bal = __ballot_sync(0xffffffffu, base + lane < MA && P.agent_mask[(size_t)e * MA + base + lane] == 0);
+      if (bal == 0xffffffffu) { na += 32; continue; }
+      na += __ffs(~bal) - 1;
+      break;
+    }
+    for (int base = 0; base < MT; base += 32) {
+      const unsigned bal = __ballot_sync(0xffffffffu, base + lane < MT && P.task_mask[(size_t)e * MT + base + lane] == 0);
+      if (bal == 0xffffffffu) { nt += 32; continue; }
+      nt += __ffs(~bal) - 1;
+      break;
+    }
+    if (lane == 0) {
+      s_na[g] = na;
+      s_nt[g] = nt;
+    }
   }
   if (tid == 0) {
     s_next = 0;
@@ -598,12 +613,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
         g = m;
       }
       const int split = (sa + 3) & ~3;
-      for (int r = 0; r < ROWS; ++r) s_seg_of[r] = SEG_NONE;
-      for (int q = 0; q < ns; ++q) {
-        s_seg[q].tbase += split;
-        for (int r = 0; r < s_seg[q].na; ++r) s_seg_of[s_seg[q].abase + r] = (uint8_t)q;
-        for (int r = 0; r < s_seg[q].nt; ++r) s_seg_of[s_seg[q].tbase + r] = (uint8_t)q;
-      }
+      for (int q = 0; q < ns; ++q) s_seg[q].tbase += split;
       s_next = g;
       s_nseg = ns;
       s_split = split;
@@ -661,16 +671,23 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
         const int slot2 = seq & (NSLOT - 1);
         mbar_wait(&s_full[slot2], (seq / NSLOT) & 1);
         ++seq;
-        for (int t = 0; t < ntiles; ++t) {
+        ChunkDesc p1b = c_chunks[CH_PAIR1], p2b = c_chunks[CH_PAIR2];   // the second tile of a round
+        p1b.a_hi = p2b.a_hi = U2_HI;
+        p1b.a_lo = p2b.a_lo = U2_LO;
+        p1b.d_col = P1B_D;
+        p2b.d_col = P2B_D;
+        for (int t = 0; t < ntiles; t += 2) {
           mbar_wait(&s_a_ready, pa);
           pa ^= 1;
           tc_fence_after();
           issue_chunk(tm, c_chunks[CH_PAIR1], ring + slot1 * SLOT_BYTES);
+          if (t + 1 < ntiles) issue_chunk(tm, p1b, ring + slot1 * SLOT_BYTES);
           tc_commit(&s_d_ready);
           mbar_wait(&s_a_ready, pa);
           pa ^= 1;
           tc_fence_after();
           issue_chunk(tm, c_chunks[CH_PAIR2], ring + slot2 * SLOT_BYTES);
+          if (t + 1 < ntiles) issue_chunk(tm, p2b, ring + slot2 * SLOT_BYTES);
           tc_commit(&s_d_ready);
         }
         tc_commit(&s_empty[slot1]);
@@ -685,11 +702,24 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       const int R = s_R;
       const bool is_agent = row < split;
       const int wtype = (q * 32 + 32 <= split) ? 0 : (q * 32 >= split ? 1 : 2);
-      const uint8_t sid = s_seg_of[row];
+      // the segment (environment) of this thread's row
+      int sid = SEG_NONE;
+      for (int q2 = 0; q2 < nseg; ++q2) {
+        const Seg t = s_seg[q2];
+        if ((row >= t.abase && row < t.abase + t.na) || (row >= t.tbase && row < t.tbase + t.nt)) sid = q2;
+      }
       const bool on = sid != SEG_NONE;
       Seg sg = s_seg[on ? sid : 0];
+      if (half == 0) s_seg_of[row] = (uint8_t)sid;   // read by the pair tiles (several worker barriers later)
       (void)R;
 
+      // development: stage timestamps of CTA 0 / thread 0 behind the activation dumps
+      long long* ts = (P.dbg && blockIdx.x == 0 && tid == 0) ? (long long*)(P.dbg + 4 * ROWS * D) : nullptr;
+#define TS_MARK()                               \
+  do {                                          \
+    if (ts && n_ts < 250) ts[1 + n_ts++] = clock64(); \
+  } while (0)
+      TS_MARK();
       // ---- raw features as the A operand of the projections (K padded to 16)
       if (half == 0) {
         float f[16];
@@ -712,9 +742,44 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       }
       tc_fence_before();
       mbar_arrive(&s_a_ready);
+      TS_MARK();
+
+      // ---- list of the pairs with a valid edge (needs only the tokens: built while the first MMAs run)
+      {
+        int poff[GMAX + 1];
+        poff[0] = 0;
+#pragma unroll
+        for (int q2 = 0; q2 < GMAX; ++q2) poff[q2 + 1] = poff[q2] + (q2 < nseg ? s_seg[q2].na * s_seg[q2].nt : 0);
+        const int np = poff[GMAX];
+        for (int base = 0; base < np; base += NWORK) {
+          const int idx = base + tid;
+          bool v = false;
+          int code = 0;
+          if (idx < np) {
+            int q2 = 0;
+#pragma unroll
+            for (int k = 1; k < GMAX; ++k)
+              if (idx >= poff[k]) q2 = k;
+            const Seg ps = s_seg[q2];
+            const int loc = idx - poff[q2];
+            const int i = loc / ps.nt, j = loc - i * ps.nt;
+            v = P.edge_valid[(size_t)ps.e * MA * MT + (size_t)i * MT + j] != 0.0f;
+            code = ((ps.abase + i) << 7) | (ps.tbase + j);
+          }
+          // one shared-memory atomic per warp
+          const unsigned bal = __ballot_sync(0xffffffffu, v);
+          if (bal) {
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(&s_nvalid, __popc(bal));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (v) plist[pos + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)code;
+          }
+        }
+      }
 
       // ---- x = proj(feats) + type_embed
       wait_d(&s_d_ready, pd, lane);
+      TS_MARK();
       {
         const float* b = w + (is_agent ? o.agent_proj_b : o.task_proj_b);
         const float* te = w + o.type_embed + (is_agent ? 0 : D);
@@ -732,26 +797,32 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       }
       tc_fence_before();
       mbar_arrive(&s_a_ready);
+      TS_MARK();
 
       // ---- encoder self-attention
       wait_d(&s_d_ready, pd, lane);
+      TS_MARK();
       kv_epilogue(tl, kvg, row, half, is_agent, 0, 128, 128, w + o.enc_in_b, w + o.enc_in_b);
       worker_sync();
       attention(tl, kvg, half, on, sg, false, is_agent, 0, 128, 128, w + o.enc_in_b, w + o.enc_in_b, AO_HI, AO_LO);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&s_a_ready);
+      TS_MARK();
 
       // ---- x1 = LN1(x + out_proj(attn))
       wait_d(&s_d_ready, pd, lane);
+      TS_MARK();
       ln_epilogue(tl, row, half, 448, w + o.enc_out_b, w + o.enc_n1_w, w + o.enc_n1_b, s_part);
       tc_wait_st();
       if (first_pass) dump_a0(P, 1, tl, row, half);
       tc_fence_before();
       mbar_arrive(&s_a_ready);
+      TS_MARK();
 
       // ---- hidden = relu(linear1(x1))
       wait_d(&s_d_ready, pd, lane);
+      TS_MARK();
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
         const int c = half * 64 + g * 16;
@@ -764,30 +835,36 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&s_a_ready);
+      TS_MARK();
 
       // ---- h = LN2(x1 + linear2(hidden))
       wait_d(&s_d_ready, pd, lane);
+      TS_MARK();
       ln_epilogue(tl, row, half, 128, w + o.enc_l2_b, w + o.enc_n2_w, w + o.enc_n2_b, s_part);
       tc_wait_st();
       if (first_pass) dump_a0(P, 2, tl, row, half);
       tc_fence_before();
       mbar_arrive(&s_a_ready);
+      TS_MARK();
 
       // ---- cross attention: agent rows take q from cross_a2t (columns 128..) and serve as k / v of cross_t2a
       // (columns 320 + 64..); task rows the other way round
       wait_d(&s_d_ready, pd, lane);
+      TS_MARK();
       kv_epilogue(tl, kvg, row, half, is_agent, wtype, 320, 128, w + o.t2a_in_b, w + o.a2t_in_b);
       worker_sync();
       attention(tl, kvg, half, on, sg, true, is_agent, wtype, 128, 320, w + o.a2t_in_b, w + o.t2a_in_b, AO2_HI, AO2_LO);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&s_a_ready);
+      TS_MARK();
 
       // ---- z = h + out_proj(ctx) (a' / t'): the A operand of the first pair-head layer and, in shared memory, the
       // source of the pair products
       float* zt = kvg;
       float* gt = kvg + ROWS * ZG_STRIDE;
       wait_d(&s_d_ready, pd, lane);
+      TS_MARK();
       {
         const float* b = w + (is_agent ? o.a2t_out_b : o.t2a_out_b);
 #pragma unroll 1
@@ -809,9 +886,11 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       }
       tc_fence_before();
       mbar_arrive(&s_a_ready);
+      TS_MARK();
 
       // ---- g = Wa a' (agent rows) / Wt t' + b1 (task rows); list of the pairs with a valid edge
       wait_d(&s_d_ready, pd, lane);
+      TS_MARK();
 #pragma unroll 1
       for (int g = 0; g < 2; ++g) {
         const int c = half * 32 + g * 16;
@@ -825,89 +904,107 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
 #pragma unroll
         for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
-      for (int s = 0; s < nseg; ++s) {
-        const Seg ps = s_seg[s];
-        const float* ev = P.edge_valid + (size_t)ps.e * MA * MT;
-        for (int idx = tid; idx < ps.na * ps.nt; idx += NWORK) {
-          const int i = idx / ps.nt, j = idx - i * ps.nt;
-          if (ev[(size_t)i * MT + j] != 0.0f) plist[atomicAdd(&s_nvalid, 1)] = (uint16_t)(((ps.abase + i) << 7) | (ps.tbase + j));
-        }
-      }
       worker_sync();
       const int nvalid = s_nvalid;
       tc_fence_before();
       mbar_arrive(&s_a_ready);
+      TS_MARK();
 
-      // ---- pair tiles: logits = w3 . relu(W2 relu(Wat (a' * t') + g_a + g_t) + b2) + b3
+      // ---- pair tiles: logits = w3 . relu(W2 relu(Wat (a' * t') + g_a + g_t) + b2) + b3, two tiles of 128 pairs per
+      // round (the second one in the columns the encoder no longer needs): half the hand-offs with the MMA thread
       const int ntiles = (nvalid + ROWS - 1) / ROWS;
 #pragma unroll 1
-      for (int t = 0; t < ntiles; ++t) {
-        const int p = t * ROWS + row;
-        const bool valid = p < nvalid;
-        const int pc = plist[valid ? p : 0];
-        const int ta = pc >> 7, tt = pc & 127;
-#pragma unroll 1
-        for (int g = 0; g < 2; ++g) {
-          const int c = half * 32 + g * 16;
-          const float4* za = (const float4*)&zt[ta * ZG_STRIDE + c];
-          const float4* zb = (const float4*)&zt[tt * ZG_STRIDE + c];
-          float u[16];
+      for (int t = 0; t < ntiles; t += 2) {
+        const int nt2 = min(2, ntiles - t);
+        int ta[2], tt[2];
+        bool valid[2];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 a = za[i], b = zb[i];
-            u[4 * i] = a.x * b.x;
-            u[4 * i + 1] = a.y * b.y;
-            u[4 * i + 2] = a.z * b.z;
-            u[4 * i + 3] = a.w * b.w;
+        for (int u2 = 0; u2 < 2; ++u2) {
+          const int p = (t + u2) * ROWS + row;
+          valid[u2] = p < nvalid;
+          const int pc = plist[valid[u2] ? p : 0];
+          ta[u2] = pc >> 7;
+          tt[u2] = pc & 127;
+        }
+#pragma unroll
+        for (int u2 = 0; u2 < 2; ++u2) {
+          if (u2 < nt2) {
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {
+              const int c = half * 32 + g * 16;
+              const float4* za = (const float4*)&zt[ta[u2] * ZG_STRIDE + c];
+              const float4* zb = (const float4*)&zt[tt[u2] * ZG_STRIDE + c];
+              float u[16];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 a = za[i], b = zb[i];
+                u[4 * i] = a.x * b.x;
+                u[4 * i + 1] = a.y * b.y;
+                u[4 * i + 2] = a.z * b.z;
+                u[4 * i + 3] = a.w * b.w;
+              }
+              st_operand16(tl, u2 ? U2_HI : U_HI, u2 ? U2_LO : U_LO, c, u);
+            }
           }
-          st_operand16(tl, U_HI, U_LO, c, u);
         }
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(&s_a_ready);
+      TS_MARK();
 
         wait_d(&s_d_ready, pd, lane);
-#pragma unroll 1
-        for (int g = 0; g < 2; ++g) {
-          const int c = half * 32 + g * 16;
-          const float4* ga = (const float4*)&gt[ta * ZG_STRIDE + c];
-          const float4* gb = (const float4*)&gt[tt * ZG_STRIDE + c];
-          float v[16];
-          tmem_ld16(tl + 384 + c, v);
+      TS_MARK();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 a = ga[i], b = gb[i];
-            v[4 * i] = fmaxf(v[4 * i] + a.x + b.x, 0.0f);
-            v[4 * i + 1] = fmaxf(v[4 * i + 1] + a.y + b.y, 0.0f);
-            v[4 * i + 2] = fmaxf(v[4 * i + 2] + a.z + b.z, 0.0f);
-            v[4 * i + 3] = fmaxf(v[4 * i + 3] + a.w + b.w, 0.0f);
+        for (int u2 = 0; u2 < 2; ++u2) {
+          if (u2 < nt2) {
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {
+              const int c = half * 32 + g * 16;
+              const float4* ga = (const float4*)&gt[ta[u2] * ZG_STRIDE + c];
+              const float4* gb = (const float4*)&gt[tt[u2] * ZG_STRIDE + c];
+              float v[16];
+              tmem_ld16(tl + (u2 ? P1B_D : P1_D) + c, v);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 a = ga[i], b = gb[i];
+                v[4 * i] = fmaxf(v[4 * i] + a.x + b.x, 0.0f);
+                v[4 * i + 1] = fmaxf(v[4 * i + 1] + a.y + b.y, 0.0f);
+                v[4 * i + 2] = fmaxf(v[4 * i + 2] + a.z + b.z, 0.0f);
+                v[4 * i + 3] = fmaxf(v[4 * i + 3] + a.w + b.w, 0.0f);
+              }
+              st_operand16(tl, u2 ? U2_HI : U_HI, u2 ? U2_LO : U_LO, c, v);
+            }
           }
-          st_operand16(tl, U_HI, U_LO, c, v);
         }
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(&s_a_ready);
+      TS_MARK();
 
         wait_d(&s_d_ready, pd, lane);
-        if (half == 0) {
+      TS_MARK();
+        // the two threads of a row take one tile each
+        if (half < nt2) {
           float logit = __ldg(&w[o.head3_b]);
 #pragma unroll 1
           for (int g = 0; g < 2; ++g) {
             float v[16];
-            tmem_ld16(tl + 448 + g * 16, v);
+            tmem_ld16(tl + (half ? P2B_D : P2_D) + g * 16, v);
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               logit = fmaf(__ldg(&w[o.head3_w + g * 16 + i]), fmaxf(v[i] + __ldg(&w[o.head2_b + g * 16 + i]), 0.0f), logit);
           }
-          if (valid) {
-            const Seg ps = s_seg[s_seg_of[ta]];
-            const size_t off = (size_t)ps.e * MA * MT + (size_t)(ta - ps.abase) * MT + (tt - ps.tbase);
+          if (valid[half]) {
+            const int a_row = ta[half], t_row = tt[half];
+            const Seg ps = s_seg[s_seg_of[a_row]];
+            const size_t off = (size_t)ps.e * MA * MT + (size_t)(a_row - ps.abase) * MT + (t_row - ps.tbase);
             P.scores[off] = tanhf(logit) * P.clamp * P.edge_valid[off];
           }
         }
-        // the next tile's products overwrite the operand columns: every read of this tile is complete (wait::ld above)
+        // the next round's products overwrite the operand columns: every read of this round is complete (wait::ld above)
         tc_fence_before();
       }
+      if (ts) ts[0] = n_ts;
     }
     first_pass = false;
     __syncthreads();  // the next pass reuses the segment table and every buffer

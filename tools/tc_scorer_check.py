@@ -79,12 +79,19 @@ def main():
     torch.cuda.synchronize()
     print("fp32 kernel vs torch: max err %.3e" % (got32 - want).abs().max().item(), flush=True)
 
-    dbg = torch.full((4, 128, 64), float("nan"), device=dev)
-    tc.lib.dll.muav_tc_debug_buffer_(C.c_void_p(dbg.data_ptr()))
+    dbg_all = torch.zeros(4 * 128 * 64 + 1024, device=dev)
+    dbg = dbg_all[:4 * 128 * 64].view(4, 128, 64)
+    dbg.fill_(float("nan"))
+    tc.lib.dll.muav_tc_debug_buffer_(C.c_void_p(dbg_all.data_ptr()))
     got = torch.full_like(want, 7.0)
     tc.score(tok, got)
     torch.cuda.synchronize()
     tc.lib.dll.muav_tc_debug_buffer_(None)
+    ts = dbg_all[4 * 128 * 64:].view(torch.int64).cpu().tolist()
+    n_ts = ts[0]
+    marks = ts[1:1 + n_ts]
+    print("stage timestamps of CTA 0 (worker thread 0), cycles since the first: wait_d marks follow arrive marks")
+    print(" ".join(str(m - marks[0]) for m in marks), flush=True)
     err = (got - want).abs()
     print("tc kernel vs torch:   max err %.3e   (vs fp32 kernel %.3e)  untouched %d" %
           (err.max().item(), (got - got32).abs().max().item(), int((got == 7.0).sum().item())), flush=True)
