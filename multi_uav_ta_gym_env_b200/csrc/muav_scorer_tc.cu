@@ -382,57 +382,63 @@ __device__ __forceinline__ void attention(uint32_t tl, const float* __restrict__
     else k1[1] = k0[1];
   }
   const float* qb = is_agent ? qb_agent : qb_task;
-#pragma unroll 1
-  for (int hh = 0; hh < 2; ++hh) {
-    const int h = half * 2 + hh;
-    float q[HD];
-    ld_variant16(tl, qcol_agent, qcol_task, h * HD, is_agent, wtype, q);
+  // the thread's two heads (features [32 half, 32 half + 32)) run side by side: two independent softmax chains, and
+  // the 16-term dot products as four partial sums each
+  float q[2 * HD], acc[2 * HD];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) q[d] = (q[d] + __ldg(&qb[h * HD + d])) * (0.25f * 1.44269504088896340736f);   // scores in log2 units
-    float acc[HD];
+  for (int hh = 0; hh < 2; ++hh) ld_variant16(tl, qcol_agent, qcol_task, (half * 2 + hh) * HD, is_agent, wtype, q + hh * HD);
 #pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] = 0.0f;
-    if (on) {
-      float m = -INFINITY, l = 0.0f;
+  for (int d = 0; d < 2 * HD; ++d) {
+    q[d] = (q[d] + __ldg(&qb[half * 2 * HD + d])) * (0.25f * 1.44269504088896340736f);   // scores in log2 units
+    acc[d] = 0.0f;
+  }
+  if (on) {
+    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.0f, 0.0f};
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr)
-        for (int j = k0[rr]; j < k1[rr]; ++j) {
-          const float4* kr = (const float4*)&kv[j * KV_STRIDE + h * HD];
-          const float4* vr = (const float4*)&kv[j * KV_STRIDE + D + h * HD];
-          float s = 0.0f;
+    for (int rr = 0; rr < 2; ++rr)
+      for (int j = k0[rr]; j < k1[rr]; ++j) {
+        const float4* kr = (const float4*)&kv[j * KV_STRIDE + half * 2 * HD];
+        const float4* vr = (const float4*)&kv[j * KV_STRIDE + D + half * 2 * HD];
+        float s[2];
 #pragma unroll
-          for (int d4 = 0; d4 < HD / 4; ++d4) {
-            const float4 kk = kr[d4];
-            s = fmaf(q[4 * d4], kk.x, s);
-            s = fmaf(q[4 * d4 + 1], kk.y, s);
-            s = fmaf(q[4 * d4 + 2], kk.z, s);
-            s = fmaf(q[4 * d4 + 3], kk.w, s);
-          }
-          if (s > m) {
-            const float c = exp2f(m - s);
-            l *= c;
-#pragma unroll
-            for (int d = 0; d < HD; ++d) acc[d] *= c;
-            m = s;
-          }
-          const float p = exp2f(s - m);
-          l += p;
+        for (int hh = 0; hh < 2; ++hh) {
+          float part[4];
 #pragma unroll
           for (int d4 = 0; d4 < HD / 4; ++d4) {
-            const float4 vv = vr[d4];
-            acc[4 * d4] = fmaf(p, vv.x, acc[4 * d4]);
-            acc[4 * d4 + 1] = fmaf(p, vv.y, acc[4 * d4 + 1]);
-            acc[4 * d4 + 2] = fmaf(p, vv.z, acc[4 * d4 + 2]);
-            acc[4 * d4 + 3] = fmaf(p, vv.w, acc[4 * d4 + 3]);
+            const float4 kk = kr[hh * 4 + d4];
+            const float* qq = q + hh * HD + 4 * d4;
+            part[d4] = fmaf(qq[3], kk.w, fmaf(qq[2], kk.z, fmaf(qq[1], kk.y, qq[0] * kk.x)));
+          }
+          s[hh] = (part[0] + part[1]) + (part[2] + part[3]);
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const float mn = fmaxf(m[hh], s[hh]);
+          const float c = exp2f(m[hh] - mn);   // 1 when the maximum stays, 0 for the first key (m = -inf)
+          const float p = exp2f(s[hh] - mn);
+          m[hh] = mn;
+          l[hh] = fmaf(l[hh], c, p);
+#pragma unroll
+          for (int d4 = 0; d4 < HD / 4; ++d4) {
+            const float4 vv = vr[hh * 4 + d4];
+            float* aa = acc + hh * HD + 4 * d4;
+            aa[0] = fmaf(aa[0], c, p * vv.x);
+            aa[1] = fmaf(aa[1], c, p * vv.y);
+            aa[2] = fmaf(aa[2], c, p * vv.z);
+            aa[3] = fmaf(aa[3], c, p * vv.w);
           }
         }
-      const float inv = 1.0f / l;
+      }
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc[d] *= inv;
+    for (int hh = 0; hh < 2; ++hh) {
+      const float inv = 1.0f / l[hh];
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc[hh * HD + d] *= inv;
     }
-    __syncwarp();
-    st_operand16(tl, ao_hi, ao_lo, h * HD, acc);
   }
+  __syncwarp();
+  st_operand16(tl, ao_hi, ao_lo, half * 2 * HD, acc);
+  st_operand16(tl, ao_hi, ao_lo, half * 2 * HD + HD, acc + HD);
 }
 
 // k | v columns of the in-projection (+ bias) into the shared token-major tile: the thread with half 0 moves k, half 1 v
