@@ -328,17 +328,17 @@ int muav_att_context_pair_scores(const float* d_params, const muav_attpair_offse
                                  const uint8_t* d_need, int n, int max_tasks, int max_agents, float score_clamp,
                                  float* d_scores, void* stream);
 
-/* The same Att-Pair forward on the tensor cores (tcgen05.mma kind::tf32 in 3xTF32, accumulators and activations in
- * TMEM; csrc/muav_scorer_tc.cu).  Same function, arguments and tolerance as muav_att_pair_scores (AttPairNet only:
- * offsets->has_context must be 0); d_tc_weights: muav_att_pair_tc_floats() floats written once per parameter set by
+/* The same Att-Pair / Att-ContextPair forward on the tensor cores (tcgen05.mma kind::tf32 in 3xTF32, accumulators and
+ * activations in TMEM; csrc/muav_scorer_tc.cu).  Same function, arguments and tolerance as muav_att_context_pair_scores
+ * (d_context NULL for AttPairNet); d_tc_weights: muav_att_pair_tc_floats() floats written once per parameter set by
  * muav_att_pair_tc_pack (the linear layers' weights split into TF32 hi / lo planes in the MMA's shared-memory layout). */
 int64_t muav_att_pair_tc_floats(void);
 int muav_att_pair_tc_pack(const float* d_params, const muav_attpair_offsets* offsets, float* d_tc_weights, void* stream);
 int muav_att_pair_scores_tc(const float* d_params, const muav_attpair_offsets* offsets, const float* d_tc_weights,
                             const float* d_task_feats, const uint8_t* d_task_mask, const float* d_agent_feats,
-                            const uint8_t* d_agent_mask, const float* d_edge_valid, const int32_t* d_env_idx,
-                            const uint8_t* d_need, int n, int max_tasks, int max_agents, float score_clamp, float* d_scores,
-                            void* stream);
+                            const uint8_t* d_agent_mask, const float* d_edge_valid, const float* d_context,
+                            const int32_t* d_env_idx, const uint8_t* d_need, int n, int max_tasks, int max_agents,
+                            float score_clamp, float* d_scores, void* stream);
 
 /* Fused AttCommitNet forward (TaskAllocation/Hybrid/AttentionCommit.py:68-100; AttentionCommit.act without exploration,
  * :167-175): commit tokens (muav_tokens_commit layout, agent features [.,13]) -> priorities f32 [E, max_tasks] and commit

@@ -244,7 +244,7 @@ class CudaLib(Lib):
         d.muav_att_pair_tc_pack.restype = C.c_int
         d.muav_att_pair_tc_pack.argtypes = [P, C.POINTER(MuavAttPairOffsets), P, P]
         d.muav_att_pair_scores_tc.restype = C.c_int
-        d.muav_att_pair_scores_tc.argtypes = [P, C.POINTER(MuavAttPairOffsets), P, P, P, P, P, P, P, P, C.c_int, C.c_int,
+        d.muav_att_pair_scores_tc.argtypes = [P, C.POINTER(MuavAttPairOffsets), P, P, P, P, P, P, P, P, P, C.c_int, C.c_int,
                                               C.c_int, C.c_float, P, P]
         d.muav_att_commit_vectors.restype = C.c_int
         d.muav_att_commit_vectors.argtypes = [P, C.POINTER(MuavAttCommitOffsets), P, P, P, P, P, P, C.c_int, C.c_int, C.c_int,

@@ -281,6 +281,7 @@ struct Params {
   const float* agent_feats;
   const uint8_t* agent_mask;
   const float* edge_valid;
+  const float* context;  // [E, 8] (AttContextPairNet) or NULL
   const int32_t* env_idx;
   const uint8_t* need;
   float* scores;
@@ -462,7 +463,7 @@ __device__ __forceinline__ void kv_epilogue(uint32_t tl, float* __restrict__ kv,
 // columns each and exchange partial sums through shared memory
 __device__ __forceinline__ void ln_epilogue(uint32_t tl, int row, int half, int d_col, const float* __restrict__ bias,
                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                            float (*s_part)[2][ROWS]) {
+                                            float (*s_part)[2][ROWS], float* __restrict__ tile = nullptr) {
   float z[32];
   float sum = 0.0f;
 #pragma unroll
@@ -498,6 +499,11 @@ __device__ __forceinline__ void ln_epilogue(uint32_t tl, int row, int half, int 
 #pragma unroll
     for (int i = 0; i < 16; ++i) y[i] = (z[g * 16 + i] - mean) * inv * __ldg(&gamma[c + i]) + __ldg(&beta[c + i]);
     st_operand16(tl, A0_HI, A0_LO, c, y);
+    if (tile) {   // a float32 copy of the row for the context pooling
+      float4* dst = (float4*)&tile[row * ZG_STRIDE + c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+    }
   }
 }
 
@@ -513,6 +519,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
   __shared__ uint8_t s_seg_of[ROWS];
   __shared__ int s_nseg, s_R, s_split, s_next, s_nvalid, s_done;
   __shared__ float s_part[2][2][ROWS];
+  __shared__ float s_ctx[GMAX][D], s_hc[GMAX][D];   // AttContextPairNet: context vector, its pair-head term
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int MT = P.max_tasks, MA = P.max_agents;
   const float* w = P.w;
@@ -846,12 +853,36 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       // ---- h = LN2(x1 + linear2(hidden))
       wait_d(&s_d_ready, pd, lane);
       TS_MARK();
-      ln_epilogue(tl, row, half, 128, w + o.enc_l2_b, w + o.enc_n2_w, w + o.enc_n2_b, s_part);
+      ln_epilogue(tl, row, half, 128, w + o.enc_l2_b, w + o.enc_n2_w, w + o.enc_n2_b, s_part, o.has_context ? kvg : nullptr);
       tc_wait_st();
       if (first_pass) dump_a0(P, 2, tl, row, half);
       tc_fence_before();
       mbar_arrive(&s_a_ready);
       TS_MARK();
+      if (o.has_context) {
+        // ctx = ctx_proj(context) + mean of h over the environment's tokens (ContextPairHybrid.py:140-142), then its
+        // term of the first pair-head layer hc = Wc ctx (head1 input rows 192..255); runs under the cross in-projection MMAs
+        worker_sync();
+        for (int idx = tid; idx < nseg * D; idx += NWORK) {
+          const int g = idx / D, k = idx - g * D;
+          const Seg ps = s_seg[g];
+          float sum = 0.0f;
+          for (int r = 0; r < ps.na; ++r) sum += kvg[(ps.abase + r) * ZG_STRIDE + k];
+          for (int r = 0; r < ps.nt; ++r) sum += kvg[(ps.tbase + r) * ZG_STRIDE + k];
+          float c = w[o.ctx_proj_b + k];
+          const float* cx = P.context + (size_t)ps.e * 8;
+#pragma unroll
+          for (int q2 = 0; q2 < 8; ++q2) c = fmaf(cx[q2], w[o.ctx_proj_w + q2 * D + k], c);
+          s_ctx[g][k] = c + sum / (float)(ps.na + ps.nt);
+        }
+        worker_sync();
+        for (int idx = tid; idx < nseg * D; idx += NWORK) {
+          const int g = idx / D, oo = idx - g * D;
+          float hc = 0.0f;
+          for (int k = 0; k < D; ++k) hc = fmaf(w[o.head1_w + (size_t)(3 * D + k) * D + oo], s_ctx[g][k], hc);
+          s_hc[g][oo] = hc;
+        }
+      }
 
       // ---- cross attention: agent rows take q from cross_a2t (columns 128..) and serve as k / v of cross_t2a
       // (columns 320 + 64..); task rows the other way round
@@ -971,6 +1002,12 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
               float v[16];
               tmem_ld16(tl + (u2 ? P1B_D : P1_D) + c, v);
 #pragma unroll
+              if (o.has_context) {
+                const float* hc = &s_hc[s_seg_of[ta[u2]]][c];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += hc[i];
+              }
+#pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float4 a = ga[i], b = gb[i];
                 v[4 * i] = fmaxf(v[4 * i] + a.x + b.x, 0.0f);
@@ -1067,7 +1104,6 @@ extern "C" int muav_att_pair_tc_pack(const float* d_params, const muav_attpair_o
                                      void* stream) {
   using namespace muav_tc;
   if (!d_params || !offsets || !d_tc_weights) return -22;
-  if (offsets->has_context) return -22;
   const muav_attpair_offsets& o = *offsets;
   PackSrc S;
   // one matrix: every output feature from (src, ldo, n0); K slice [k0, k0 + kc) of kreal input features
@@ -1098,14 +1134,14 @@ extern "C" int muav_att_pair_tc_pack(const float* d_params, const muav_attpair_o
 
 extern "C" int muav_att_pair_scores_tc(const float* d_params, const muav_attpair_offsets* offsets, const float* d_tc_weights,
                                        const float* d_task_feats, const uint8_t* d_task_mask, const float* d_agent_feats,
-                                       const uint8_t* d_agent_mask, const float* d_edge_valid, const int32_t* d_env_idx,
-                                       const uint8_t* d_need, int n, int max_tasks, int max_agents, float score_clamp,
-                                       float* d_scores, void* stream) {
+                                       const uint8_t* d_agent_mask, const float* d_edge_valid, const float* d_context,
+                                       const int32_t* d_env_idx, const uint8_t* d_need, int n, int max_tasks, int max_agents,
+                                       float score_clamp, float* d_scores, void* stream) {
   using namespace muav_tc;
   if (!d_params || !offsets || !d_tc_weights || !d_task_feats || !d_task_mask || !d_agent_feats || !d_agent_mask ||
       !d_edge_valid || !d_scores)
     return -22;
-  if (offsets->has_context) return -22;
+  if ((offsets->has_context != 0) != (d_context != nullptr)) return -22;
   if (n < 0 || max_tasks < 1 || max_agents < 1 || max_agents + max_tasks > 48 || max_agents > 16) return -22;
   if (n == 0) return 0;
   Params P;
@@ -1117,6 +1153,7 @@ extern "C" int muav_att_pair_scores_tc(const float* d_params, const muav_attpair
   P.agent_feats = d_agent_feats;
   P.agent_mask = d_agent_mask;
   P.edge_valid = d_edge_valid;
+  P.context = d_context;
   P.env_idx = d_env_idx;
   P.need = d_need;
   P.scores = d_scores;

@@ -544,10 +544,10 @@ class FusedAttPairScorer:
         self.device = device
         self.clamp = float(score_clamp)
         self._C = C
-        # tensor-core path (csrc/muav_scorer_tc.cu, AttPairNet only): the linear layers' weights re-packed once as TF32
+        # tensor-core path (csrc/muav_scorer_tc.cu): the linear layers' weights re-packed once as TF32
         # hi / lo planes in the MMA's shared-memory layout.  MUAV_SCORER_TC=0 selects the FP32-pipe kernel (A/B runs).
         self.tcw = None
-        if not self.has_context and os.environ.get("MUAV_SCORER_TC", "1") != "0":
+        if os.environ.get("MUAV_SCORER_TC", "1") != "0":
             with torch.cuda.device(device):
                 self.tcw = torch.empty(int(self.lib.dll.muav_att_pair_tc_floats()), dtype=torch.float32, device=device)
                 rc = self.lib.dll.muav_att_pair_tc_pack(self.params.data_ptr(), C.byref(self.offsets), self.tcw.data_ptr(),
@@ -571,7 +571,8 @@ class FusedAttPairScorer:
             rc = self.lib.dll.muav_att_pair_scores_tc(
                 self.params.data_ptr(), C.byref(self.offsets), self.tcw.data_ptr(), tok["task_feats"].data_ptr(),
                 tok["task_mask_u8"].data_ptr(), tok["agent_feats"].data_ptr(), tok["agent_mask_u8"].data_ptr(),
-                tok["edge_valid"].data_ptr(), None if idx is None else idx.data_ptr(),
+                tok["edge_valid"].data_ptr(), tok["context"].data_ptr() if self.has_context else None,
+                None if idx is None else idx.data_ptr(),
                 tok["need"].data_ptr() if use_need else None, n, MT, MA, C.c_float(self.clamp), scores_out.data_ptr(),
                 C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
             if rc != 0:

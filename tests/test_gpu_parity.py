@@ -1012,13 +1012,15 @@ def test_batched_evaluation_driver_reproduces_run_wps_episode():
         "on_time_rate", "reserve_idle_fraction"]
 
 
-def test_fused_context_scorer_kernel_and_fused_context_emission():
-    """The fused scorer kernel with AttContextPairNet weights (context term of the pair head, pooled encoder output)
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_fused_context_scorer_kernel_and_fused_context_emission(tc, monkeypatch):
+    """The fused scorer kernels (tcgen05 and FP32 pipe) with AttContextPairNet weights (context term of the pair head, pooled encoder output)
     against the PyTorch module on real WPS_attn tokens, and the context vector emitted by the step kernel against the
     standalone token kernel."""
     from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
     from multi_uav_ta_gym_env_b200.scorers import AttContextPairNet, FusedAttPairScorer, context_pair_scores
 
+    monkeypatch.setenv("MUAV_SCORER_TC", tc)
     cfg = wps_config("WPS_attn")
     E = 120
     env = make_env(cfg, list(range(E)))
@@ -1027,6 +1029,7 @@ def test_fused_context_scorer_kernel_and_fused_context_emission():
     torch.manual_seed(2)
     net = AttContextPairNet().cuda().eval()
     fused = FusedAttPairScorer(net, torch.device("cuda"))
+    assert (fused.tcw is not None) == (tc == "1")
     spec = AllocSpec.pair_hybrid(15)
     scores = torch.zeros(E, 16, 32, dtype=torch.float32, device="cuda")
     checked = 0
