@@ -238,6 +238,7 @@ def run_gpu_arm(args):
     wl = args.workload
     use_scorer = wl in ("hard_pair", "attn_context")
     use_commit_net = wl == "commit_att"
+    use_coal_net = wl == "escort_att"
     if wl == "attn_context":
         # the paper's primary method: Att-ContextPair on WPS_attn (12 agents, dual-front bursts, private knowledge)
         case_name, cfg, spec = "WPS_attn", wps_config("WPS_attn"), AllocSpec.pair_hybrid(HYBRID_INTERVAL)
@@ -267,6 +268,10 @@ def run_gpu_arm(args):
         case_name, cfg, spec = "WPS_commit", wps_config("WPS_commit"), AllocSpec.att_commit(HYBRID_INTERVAL)
         desc = ("Att-Commit: random-init AttCommitNet (fused forward kernel on fused commit tokens) -> "
                 "AttentionCommit._plan_from_scores on the device, hybrid replan rule")
+    elif wl == "escort_att":
+        case_name, cfg, spec = "WPS_escort", wps_config("WPS_escort"), AllocSpec.att_escort(12)
+        desc = ("Att-Coalition: random-init AttCoalitionNet (fused forward kernel on fused escort tokens) -> "
+                "AttentionEscort._plan_from_scores on the device, replan rule t%12/any event")
     elif wl == "escort_coalition":
         case_name, cfg, spec = "WPS_escort", wps_config("WPS_escort"), AllocSpec.coalition_hungarian(12)
         desc = "Coalition-Hungarian interval 12 with visibility map"
@@ -319,6 +324,12 @@ def run_gpu_arm(args):
         commit_scorer = FusedAttCommitScorer(cnet, dev)
         plan_kw = {"plan_pri": torch.zeros(E, 32, dtype=torch.float32, device=dev),
                    "plan_commit": torch.zeros(E, 16, dtype=torch.float32, device=dev)}
+    if use_coal_net:
+        from multi_uav_ta_gym_env_b200.scorers import AttCoalitionNet, FusedAttCoalitionScorer
+        tok = env.enable_fused_tokens(48, 16, 12, 0x1F, escort=True)
+        coal_scorer = FusedAttCoalitionScorer(AttCoalitionNet().to(dev).eval(), dev)
+        scores = torch.zeros(E, 16, 48, dtype=torch.float32, device=dev)
+        plan_kw = {"task_order": tok["task_order"]}
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     metric_acc = torch.zeros(32, dtype=torch.float64, device=dev)
     names = env.lib.metric_names()
@@ -331,6 +342,13 @@ def run_gpu_arm(args):
                 env.refresh_fused_tokens()
                 launches["n"] += 1
             commit_scorer.vectors(tok, plan_kw["plan_pri"], plan_kw["plan_commit"], use_need=True)
+            launches["n"] += 1
+            return
+        if use_coal_net:
+            if t == 0:
+                env.refresh_fused_tokens()
+                launches["n"] += 1
+            coal_scorer.score(tok, scores, use_need=True)
             launches["n"] += 1
             return
         if not use_scorer:
@@ -535,7 +553,7 @@ def survey_b_alg(wl, A, env):
     configs (WPS_hard 14.4 KB, WPS_commit 21 KB, WPS_escort 25 KB), else the section's own formula
     B_alg = 2 S_env + O_env with agent 104 B, live task 100 + 8 A B, threat 32 B, known bitmask 4 A ceil(Tcap / 32) B,
     pending reveals 4 x 48 B, scalars 128 B, RNG tape 44 B per step, O_env = 4 A + 16 B."""
-    stated = {"hard_pair": 14400, "hard_local": 14400, "commit_urgency": 21000, "commit_att": 21000, "escort_coalition": 25000,
+    stated = {"hard_pair": 14400, "hard_local": 14400, "commit_urgency": 21000, "commit_att": 21000, "escort_coalition": 25000, "escort_att": 25000,
               "hard_pi": 14400, "escort_pi": 25000, "hard_cbba": 14400, "escort_cbba": 25000}
     if wl in stated:
         return stated[wl], "SURVEY.md 8(d), stated figure"
@@ -612,7 +630,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="environments per GPU")
     ap.add_argument("--workload", default="hard_pair",
                     help="hard_pair (default, BASELINE config 2) | hard_local | commit_urgency | escort_coalition | burst_xK "
-                         "| attn_context | hard_pi | escort_pi | hard_cbba | escort_cbba | commit_att")
+                         "| attn_context | hard_pi | escort_pi | hard_cbba | escort_cbba | commit_att | escort_att")
     ap.add_argument("--task-cap", type=int, default=0,
                     help="task slots per environment (0 = workload default: 32 for WPS_hard, else the library's bound; "
                          "-1 = always the library's provable bound)")

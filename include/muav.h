@@ -171,7 +171,11 @@ typedef struct muav_token_out {
   int32_t max_tasks, max_agents, interval, event_mask;
   float* d_context;       /* optional [E, 8]: build_context_summary (ContextPairHybrid.py:33-70) of the same tokens */
   int32_t agent_feat_dim; /* 0 / 12: pair tokens; 13: commit tokens (enrich_commit_tokens, AttentionCommit.py:49-62):
-                             d_agent_feats is then [E, max_agents, 13] and d_edge_valid may be NULL */
+                             d_agent_feats is then [E, max_agents, 13] and d_edge_valid may be NULL; 16: escort tokens
+                             (build_escort_tokens, AttentionEscort.py:76-241; escort_enabled configurations): d_task_feats
+                             [E, max_tasks, 22], d_agent_feats [E, max_agents, 16], d_edge_valid required */
+  int32_t* d_task_order;  /* escort tokens only, optional [E, id_cap]: the muav_tokens_escort d_task_order output (rank of
+                             each task id in the token order, the d_task_order input of planner 4) */
 } muav_token_out;
 
 const char* muav_version(void);
@@ -327,6 +331,23 @@ int muav_att_context_pair_scores(const float* d_params, const muav_attpair_offse
                                  const float* d_edge_valid, const float* d_context, const int32_t* d_env_idx,
                                  const uint8_t* d_need, int n, int max_tasks, int max_agents, float score_clamp,
                                  float* d_scores, void* stream);
+
+/* Fused AttCoalitionNet forward (TaskAllocation/Hybrid/AttentionEscort.py:244-330: the Att-Pair architecture at d_model
+ * 128, 4 heads, 2 encoder layers, feed-forward 512) on escort tokens (muav_tokens_escort layout: task features [., 22],
+ * agent features [., 16]): scores = sigmoid(clip(logits, -20, 20)) * edge_valid (AttentionEscort.act without exploration,
+ * :449-466), 0 on padded rows / columns; the d_edge_scores input of planner 4.  Weights packed like muav_attpair_offsets
+ * (transposed, offsets in floats).  max_agents <= 16, max_agents + max_tasks <= 64. */
+typedef struct muav_attcoal_offsets {
+  int32_t agent_proj_w, agent_proj_b, task_proj_w, task_proj_b, type_embed;
+  int32_t enc_in_w[2], enc_in_b[2], enc_out_w[2], enc_out_b[2], enc_l1_w[2], enc_l1_b[2], enc_l2_w[2], enc_l2_b[2];
+  int32_t enc_n1_w[2], enc_n1_b[2], enc_n2_w[2], enc_n2_b[2];
+  int32_t a2t_in_w, a2t_in_b, a2t_out_w, a2t_out_b, t2a_in_w, t2a_in_b, t2a_out_w, t2a_out_b;
+  int32_t head1_w, head1_b, head2_w, head2_b, head3_w, head3_b;
+} muav_attcoal_offsets;
+int muav_att_coalition_scores(const float* d_params, const muav_attcoal_offsets* offsets, const float* d_task_feats,
+                              const uint8_t* d_task_mask, const float* d_agent_feats, const uint8_t* d_agent_mask,
+                              const float* d_edge_valid, const int32_t* d_env_idx, const uint8_t* d_need, int n,
+                              int max_tasks, int max_agents, float* d_scores, void* stream);
 
 /* The same Att-Pair / Att-ContextPair forward on the tensor cores (tcgen05.mma kind::tf32 in 3xTF32, accumulators and
  * activations in TMEM; csrc/muav_scorer_tc.cu).  Same function, arguments and tolerance as muav_att_context_pair_scores

@@ -75,7 +75,7 @@ class MuavTokenOut(C.Structure):
         ("d_task_feats", C.c_void_p), ("d_task_mask", C.c_void_p), ("d_agent_feats", C.c_void_p),
         ("d_agent_mask", C.c_void_p), ("d_edge_valid", C.c_void_p), ("d_task_ids", C.c_void_p), ("d_need", C.c_void_p),
         ("max_tasks", C.c_int32), ("max_agents", C.c_int32), ("interval", C.c_int32), ("event_mask", C.c_int32),
-        ("d_context", C.c_void_p), ("agent_feat_dim", C.c_int32),
+        ("d_context", C.c_void_p), ("agent_feat_dim", C.c_int32), ("d_task_order", C.c_void_p),
     ]
 
 
@@ -95,6 +95,15 @@ class MuavAttCommitOffsets(C.Structure):
                 + [(n, C.c_int32) for n in ("priority_w", "priority_b", "commit_w", "commit_b")])
 
 
+class MuavAttCoalOffsets(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("agent_proj_w", "agent_proj_b", "task_proj_w", "task_proj_b", "type_embed")]
+                + [(n, C.c_int32 * 2) for n in ("enc_in_w", "enc_in_b", "enc_out_w", "enc_out_b", "enc_l1_w", "enc_l1_b",
+                                                "enc_l2_w", "enc_l2_b", "enc_n1_w", "enc_n1_b", "enc_n2_w", "enc_n2_b")]
+                + [(n, C.c_int32) for n in ("a2t_in_w", "a2t_in_b", "a2t_out_w", "a2t_out_b", "t2a_in_w", "t2a_in_b",
+                                            "t2a_out_w", "t2a_out_b", "head1_w", "head1_b", "head2_w", "head2_b", "head3_w",
+                                            "head3_b")])
+
+
 # every symbol include/muav.h declares
 ABI_SYMBOLS = [
     "muav_version", "muav_config_size", "muav_record_bytes", "muav_scratch_bytes", "muav_hot_bytes", "muav_num_fields",
@@ -102,7 +111,7 @@ ABI_SYMBOLS = [
     "muav_avoid_obstacles", "muav_metric_name", "muav_metrics", "muav_tokens_pair", "muav_tokens_commit", "muav_tokens_escort", "muav_tokens_context", "muav_pair_mask", "muav_observe",
     "muav_att_pair_scores", "muav_att_context_pair_scores", "muav_rollout", "muav_state_bytes", "muav_tape_bytes", "muav_reset_upload", "muav_snapshot",
     "muav_ctx_create", "muav_ctx_destroy", "muav_ctx_step_host", "muav_ctx_allocate_host", "muav_att_commit_vectors",
-    "muav_att_pair_tc_floats", "muav_att_pair_tc_pack", "muav_att_pair_scores_tc",
+    "muav_att_pair_tc_floats", "muav_att_pair_tc_pack", "muav_att_pair_scores_tc", "muav_att_coalition_scores",
 ]
 
 
@@ -246,6 +255,9 @@ class CudaLib(Lib):
         d.muav_att_pair_scores_tc.restype = C.c_int
         d.muav_att_pair_scores_tc.argtypes = [P, C.POINTER(MuavAttPairOffsets), P, P, P, P, P, P, P, P, P, C.c_int, C.c_int,
                                               C.c_int, C.c_float, P, P]
+        d.muav_att_coalition_scores.restype = C.c_int
+        d.muav_att_coalition_scores.argtypes = [P, C.POINTER(MuavAttCoalOffsets), P, P, P, P, P, P, P, C.c_int, C.c_int,
+                                                C.c_int, P, P]
         d.muav_att_commit_vectors.restype = C.c_int
         d.muav_att_commit_vectors.argtypes = [P, C.POINTER(MuavAttCommitOffsets), P, P, P, P, P, P, C.c_int, C.c_int, C.c_int,
                                               P, P, P]

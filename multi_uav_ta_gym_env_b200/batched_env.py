@@ -208,15 +208,19 @@ class BatchedMultiUAVEnv:
 
     # ------------------------------------------------------------------ fused token emission
     def enable_fused_tokens(self, max_tasks=32, max_agents=16, interval=15, event_mask=HYBRID_EVENTS, context=False,
-                            commit=False):
+                            commit=False, escort=False):
         """Ask the step kernel to emit pair tokens for the environments that will replan before the next
         step (muav_token_out).  Returns the token dict (tensors are updated in place by every step) with
-        `need` u8[E].  commit=True: commit tokens instead (agent features [., 13], enrich_commit_tokens)."""
+        `need` u8[E].  commit=True: commit tokens instead (agent features [., 13], enrich_commit_tokens).
+        escort=True: escort tokens (build_escort_tokens: task features [., 22], agent features [., 16]) plus
+        `task_order` [E, id_cap] for AllocSpec.att_escort(); pass the escort replan rule (interval 12, every event)."""
         E, dev = self.n_envs, self.device
+        tfd = 22 if escort else 13
+        afd = 16 if escort else (13 if commit else 12)
         tok = {
-            "task_feats": torch.zeros(E, max_tasks, 13, dtype=torch.float32, device=dev),
+            "task_feats": torch.zeros(E, max_tasks, tfd, dtype=torch.float32, device=dev),
             "task_mask_u8": torch.ones(E, max_tasks, dtype=torch.uint8, device=dev),
-            "agent_feats": torch.zeros(E, max_agents, 13 if commit else 12, dtype=torch.float32, device=dev),
+            "agent_feats": torch.zeros(E, max_agents, afd, dtype=torch.float32, device=dev),
             "agent_mask_u8": torch.ones(E, max_agents, dtype=torch.uint8, device=dev),
             "edge_valid": torch.zeros(E, max_agents, max_tasks, dtype=torch.float32, device=dev),
             "task_ids": torch.zeros(E, max_tasks, dtype=torch.int32, device=dev),
@@ -224,6 +228,8 @@ class BatchedMultiUAVEnv:
         }
         if context:   # build_context_summary of the same tokens (ContextPairHybrid.py:33-70)
             tok["context"] = torch.zeros(E, 8, dtype=torch.float32, device=dev)
+        if escort:
+            tok["task_order"] = torch.zeros(E, max(self.cfg.id_cap, self.cfg.task_cap), dtype=torch.int32, device=dev)
         T = _lib.MuavTokenOut()
         T.d_task_feats = tok["task_feats"].data_ptr()
         T.d_task_mask = tok["task_mask_u8"].data_ptr()
@@ -233,8 +239,9 @@ class BatchedMultiUAVEnv:
         T.d_task_ids = tok["task_ids"].data_ptr()
         T.d_need = tok["need"].data_ptr()
         T.d_context = tok["context"].data_ptr() if context else None
+        T.d_task_order = tok["task_order"].data_ptr() if escort else None
         T.max_tasks, T.max_agents, T.interval, T.event_mask = max_tasks, max_agents, interval, event_mask
-        T.agent_feat_dim = 13 if commit else 12
+        T.agent_feat_dim = afd
         self._tok = T
         self.fused_tokens = tok
         return tok
@@ -242,7 +249,11 @@ class BatchedMultiUAVEnv:
     def refresh_fused_tokens(self):
         """Fill the fused token tensors for ALL environments with the standalone kernel (after reset/restore)."""
         tok, T = self.fused_tokens, self._tok
-        if T.agent_feat_dim == 13:
+        if T.agent_feat_dim == 16:
+            rc = self.lib.dll.muav_tokens_escort(C.byref(self.cfg), self.records.data_ptr(), T.max_tasks, T.max_agents,
+                                                 T.d_task_feats, T.d_task_mask, T.d_agent_feats, T.d_agent_mask,
+                                                 T.d_edge_valid, T.d_task_ids, T.d_task_order, self.n_envs, self._stream())
+        elif T.agent_feat_dim == 13:
             rc = self.lib.dll.muav_tokens_commit(C.byref(self.cfg), self.records.data_ptr(), T.max_tasks, T.max_agents,
                                                  T.d_task_feats, T.d_task_mask, T.d_agent_feats, T.d_agent_mask,
                                                  T.d_task_ids, self.n_envs, self._stream())

@@ -303,7 +303,15 @@ __global__ void __launch_bounds__(MUAV_LB_THREADS, MUAV_LB_BLOCKS) muav_step_ker
       const int iv = P.tok.interval > 0 ? P.tok.interval : 1;
       const bool need = !HIv(DONE) && ((HIv(T) % iv) == 0 || (HIv(EV_TAGMASK) & P.tok.event_mask) != 0);
       if (lane == 0) P.tok.d_need[e] = need ? 1 : 0;
-      if (need && P.tok.d_task_feats) {
+      if (need && P.tok.d_task_feats && MUAV_F_ESCORT(P.cfg.escort_enabled) && P.tok.agent_feat_dim == 16) {
+        // escort tokens (build_escort_tokens, AttentionEscort.py:76-241): task features [., 22], agent features [., 16]
+        const int mt = P.tok.max_tasks, ma = P.tok.max_agents;
+        EscortTokScratch W = carve_escort_tok((char*)scratch, V.lay().D.TC, mt);
+        tokens_escort_env(V, P.cfg, mt, ma, P.tok.d_task_feats + (size_t)e * mt * 22, P.tok.d_task_mask + (size_t)e * mt,
+                          P.tok.d_agent_feats + (size_t)e * ma * 16, P.tok.d_agent_mask + (size_t)e * ma,
+                          P.tok.d_edge_valid + (size_t)e * ma * mt, P.tok.d_task_ids + (size_t)e * mt,
+                          P.tok.d_task_order ? P.tok.d_task_order + (size_t)e * V.lay().D.IC : nullptr, W, lane, 32);
+      } else if (need && P.tok.d_task_feats) {
         const int mt = P.tok.max_tasks, ma = P.tok.max_agents;
         const int afd = P.tok.agent_feat_dim == 13 ? 13 : 12;   // 13: commit tokens (enrich_commit_tokens)
         tokens_pair_env(V, P.cfg, mt, ma, P.tok.d_task_feats + (size_t)e * mt * 13, P.tok.d_task_mask + (size_t)e * mt,
@@ -625,6 +633,10 @@ static size_t slot_bytes_of(StepParams& P) {
     const int cb = cbba_scratch_bytes(P.L.D.A);
     if (cb > P.scratch_launch) P.scratch_launch = cb;
   }
+  if (P.tok.d_need && P.tok.d_task_feats && P.tok.agent_feat_dim == 16) {   // escort tokens sort their candidates
+    const int eb = (int)escort_tok_scratch_bytes(P.L.D.TC, P.tok.max_tasks);
+    if (eb > P.scratch_launch) P.scratch_launch = eb;
+  }
   return (size_t)P.stage_bytes + (size_t)P.scratch_launch + (size_t)P.L.act_bytes;
 }
 
@@ -729,6 +741,7 @@ int muav_step(const muav_config* cfg, void* d_records, const uint32_t* d_tapes, 
   if (out) P.out = *out;
   if (tok) {
     if (tok->max_tasks < 1 || tok->max_agents < 1 || tok->max_tasks > (cfg->task_cap > 64 ? cfg->task_cap : 64)) return -22;
+    if (tok->agent_feat_dim == 16 && tok->d_task_feats && (!cfg->escort_enabled || !tok->d_edge_valid)) return -22;
     P.tok = *tok;
   }
   P.records = (char*)d_records;

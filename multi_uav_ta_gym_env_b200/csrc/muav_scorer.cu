@@ -21,18 +21,41 @@
 
 namespace muav_scorer {
 
-constexpr int D = 64;      // d_model
 constexpr int NH = 4;      // heads
-constexpr int HD = 16;     // head dim
-constexpr int FF = 128;    // dim_feedforward
 constexpr int TS = 64;     // token stride of transposed activations [feature][token]: tokens of one pass
-constexpr int WS = 68;     // row stride of the staged transposed weight tile [k][o]
 constexpr int NT = 256;    // threads per CTA
-constexpr int TF = 13, AF = 12;
+// Network shape: AttPairNet / AttContextPairNet / AttCommitNet (d_model 64, feed-forward 128, 13 / 12 or 13 features) and
+// AttCoalitionNet (AttentionEscort.py:244-330: d_model 128, feed-forward 512 processed in slices of 256, 22 / 16 features)
+template <int D_, int FF_, int FFS_, int TF_, int AF_>
+struct Shape {
+  static constexpr int D = D_, HD = D_ / NH, FF = FF_, FFS = FFS_, TF = TF_, AF = AF_;
+  static constexpr int WS = D_ + 4;       // row stride of the staged pair-head tile Wat [o][d]
+  static constexpr int W2S = D_ / 2 + 4;  // row stride of the staged W2^T [o][p]
+  static constexpr int BIG = (3 * D_ * TS > D_ * WS + D_ * W2S ? 3 * D_ * TS : D_ * WS + D_ * W2S) > FFS_ * TS
+                                 ? (3 * D_ * TS > D_ * WS + D_ * W2S ? 3 * D_ * TS : D_ * WS + D_ * W2S)
+                                 : FFS_ * TS;   // floats of the big buffer: q|k|v, a feed-forward slice, or the pair-head tiles
+  static constexpr size_t SMEM = sizeof(float) * (size_t)(3 * D_ * TS + BIG);
+};
+using PairShape = Shape<64, 128, 128, 13, 12>;
+using CommitShape = Shape<64, 128, 128, 13, 13>;
+using CoalShape = Shape<128, 512, 256, 22, 16>;
+constexpr int MAX_ENC = 2;
+// parameter offsets of the pair-scoring networks in one form (muav_attpair_offsets: one encoder layer;
+// muav_attcoal_offsets: two)
+struct NetOffsets {
+  int32_t agent_proj_w, agent_proj_b, task_proj_w, task_proj_b, type_embed;
+  int32_t n_enc;
+  int32_t enc_in_w[MAX_ENC], enc_in_b[MAX_ENC], enc_out_w[MAX_ENC], enc_out_b[MAX_ENC], enc_l1_w[MAX_ENC], enc_l1_b[MAX_ENC],
+      enc_l2_w[MAX_ENC], enc_l2_b[MAX_ENC], enc_n1_w[MAX_ENC], enc_n1_b[MAX_ENC], enc_n2_w[MAX_ENC], enc_n2_b[MAX_ENC];
+  int32_t a2t_in_w, a2t_in_b, a2t_out_w, a2t_out_b, t2a_in_w, t2a_in_b, t2a_out_w, t2a_out_b;
+  int32_t head1_w, head1_b, head2_w, head2_b, head3_w, head3_b;
+  int32_t ctx_proj_w, ctx_proj_b, has_context;
+  int32_t sigmoid_out;   // 0: tanh(logit) * clamp * edge_valid (Att-Pair); 1: sigmoid(clip(logit, +-20)) * edge_valid (Att-Coalition)
+};
 
 struct Params {
   const float* w;  // packed parameters
-  muav_attpair_offsets o;
+  NetOffsets o;
   const float* task_feats;
   const uint8_t* task_mask;
   const float* agent_feats;
@@ -109,6 +132,7 @@ __device__ void linear_t(const float* __restrict__ in_t, int r_lo, int r_hi, int
 }
 
 // LayerNorm over the feature axis (eps 1e-5, biased variance), in place on x_t[D][TS]
+template <int D>
 __device__ void layer_norm_t(float* x_t, int R, const float* __restrict__ g, const float* __restrict__ b) {
   // four threads per token: thread (part, r) owns features [16 part, 16 part + 16) of token r (a warp reads 32 consecutive
   // tokens of one feature row: conflict-free); the partial sums meet in shared memory
@@ -160,8 +184,11 @@ struct Seg {
 // cross == true: agent tokens attend to their environment's task tokens (cross_a2t) and task tokens to its agent tokens
 // (cross_t2a) in one pass -- the in-projection gave every token the q of its own module and the k / v of the other.
 // qkv_t rows: q 0..63, k 64..127, v 128..191.
+template <int D>
 __device__ void attention_t(const float* __restrict__ qkv_t, int R, int split, const Seg* __restrict__ seg,
                             const uint8_t* __restrict__ seg_of, bool cross, float* __restrict__ out_t) {
+  constexpr int HD = D / NH;
+  constexpr float qscale = HD == 16 ? 0.25f : 0.17677669529663689f;   // 1 / sqrt(head dim)
   const int h = threadIdx.x >> 6;
   const int i = threadIdx.x & 63;
   if (i < R && seg_of[i] != SEG_NONE) {
@@ -176,7 +203,7 @@ __device__ void attention_t(const float* __restrict__ qkv_t, int R, int split, c
     }
     float q[HD];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) q[d] = qkv_t[(h * HD + d) * TS + i] * 0.25f;
+    for (int d = 0; d < HD; ++d) q[d] = qkv_t[(h * HD + d) * TS + i] * qscale;
     // one pass over the keys with a running maximum (online softmax): the keys are read once
     float m = -INFINITY;
     float l = 0.0f;
@@ -266,7 +293,9 @@ __device__ int pick_envs(const PickArgs P, int group, int* s_env, int* s_scan) {
   return m > 0 ? m : 0;
 }
 
-__global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__ Params P, int group) {
+template <class S>
+__global__ void __launch_bounds__(NT, S::D == 64 ? 2 : 1) att_pair_kernel(const __grid_constant__ Params P, int group) {
+  constexpr int D = S::D, FF = S::FF, FFS = S::FFS, TF = S::TF, AF = S::AF, WS = S::WS, W2S = S::W2S;
   extern __shared__ __align__(16) float sm[];
   float* x_t = sm;                       // [D][TS]   tokens / encoder output h
   float* y_t = x_t + D * TS;             // [D][TS]   attention output / residual sums / ha
@@ -281,7 +310,7 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
   const int tid = threadIdx.x;
   const int MT = P.max_tasks, MA = P.max_agents;
   const float* w = P.w;
-  const muav_attpair_offsets& o = P.o;
+  const NetOffsets& o = P.o;
   const int m = pick_envs(PickArgs{P.need, P.env_idx, P.n}, group, s_env, s_scan);
   if (m == 0) return;
   if (tid < m) {
@@ -368,14 +397,20 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
     }
     __syncthreads();
 
-    // ---- TransformerEncoderLayer (post-norm, relu, eval): x1 = LN1(x + SA(x)); x2 = LN2(x1 + FF(x1))
-    linear_t(x_t, 0, R, D, lin1(w + o.enc_in_w, w + o.enc_in_b), 3 * D, 3 * D, big_t, nullptr, false);
-    attention_t(big_t, R, split, s_seg, s_seg_of, false, y_t);
-    linear_t(y_t, 0, R, D, lin1(w + o.enc_out_w, w + o.enc_out_b), D, D, z_t, x_t, false);   // z = x + out_proj(attn)
-    layer_norm_t(z_t, R, w + o.enc_n1_w, w + o.enc_n1_b);                                    // z = x1
-    linear_t(z_t, 0, R, D, lin1(w + o.enc_l1_w, w + o.enc_l1_b), FF, FF, big_t, nullptr, true);  // hidden
-    linear_t(big_t, 0, R, FF, lin1(w + o.enc_l2_w, w + o.enc_l2_b), D, D, x_t, z_t, false);      // x = x1 + FF(x1)
-    layer_norm_t(x_t, R, w + o.enc_n2_w, w + o.enc_n2_b);                                    // x = h (encoder output)
+    // ---- TransformerEncoderLayer(s) (post-norm, relu, eval): x1 = LN1(x + SA(x)); x2 = LN2(x1 + FF(x1)); the feed-forward
+    // hidden layer goes through the big buffer in slices of FFS features, linear2 accumulating over the slices
+    for (int l = 0; l < o.n_enc; ++l) {
+      linear_t(x_t, 0, R, D, lin1(w + o.enc_in_w[l], w + o.enc_in_b[l]), 3 * D, 3 * D, big_t, nullptr, false);
+      attention_t<D>(big_t, R, split, s_seg, s_seg_of, false, y_t);
+      linear_t(y_t, 0, R, D, lin1(w + o.enc_out_w[l], w + o.enc_out_b[l]), D, D, z_t, x_t, false);   // z = x + out_proj(attn)
+      layer_norm_t<D>(z_t, R, w + o.enc_n1_w[l], w + o.enc_n1_b[l]);                                  // z = x1
+      for (int fs = 0; fs < FF; fs += FFS) {
+        linear_t(z_t, 0, R, D, lin1(w + o.enc_l1_w[l] + fs, w + o.enc_l1_b[l] + fs), FF, FFS, big_t, nullptr, true);   // hidden slice
+        linear_t(big_t, 0, R, FFS, lin1(w + o.enc_l2_w[l] + (size_t)fs * D, fs == 0 ? w + o.enc_l2_b[l] : nullptr), D, D, x_t,
+                 fs == 0 ? z_t : x_t, false);                                                          // x = x1 + FF(x1)
+      }
+      layer_norm_t<D>(x_t, R, w + o.enc_n2_w[l], w + o.enc_n2_b[l]);                                  // x = h (encoder output)
+    }
     if (o.has_context) {
       // ctx = ctx_proj(context) + mean of h over the environment's tokens (ContextPairHybrid.py:140-142)
       for (int idx = tid; idx < nseg * D; idx += NT) {
@@ -399,7 +434,7 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
     {
       const LinW in_w{w + o.a2t_in_w, w + o.a2t_in_b, w + o.t2a_in_w, w + o.t2a_in_b, split, D};
       linear_t(x_t, 0, R, D, in_w, 3 * D, 3 * D, big_t, nullptr, false);
-      attention_t(big_t, R, split, s_seg, s_seg_of, true, y_t);
+      attention_t<D>(big_t, R, split, s_seg, s_seg_of, true, y_t);
       const LinW out_w{w + o.a2t_out_w, w + o.a2t_out_b, w + o.t2a_out_w, w + o.t2a_out_b, split, 1 << 30};
       linear_t(y_t, 0, R, D, out_w, D, D, z_t, x_t, false);   // z = a' (agent tokens) / t' (task tokens)
     }
@@ -408,16 +443,16 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
     linear_t(z_t, 0, split, D, lin1(w + o.head1_w, nullptr), D, D, y_t, nullptr, false);               // Wa a
     linear_t(z_t, split, R, D, lin1(w + o.head1_w + D * D, w + o.head1_b), D, D, x_t, nullptr, false);   // Wt t + b1
     // stage Wat [o][d] (row-major, stride WS) and W2^T [o][p]
-    float* wat = big_t;               // [64][WS]
-    float* w2t = big_t + 64 * WS;     // [64][36]
+    float* wat = big_t;               // [D][WS]
+    float* w2t = big_t + D * WS;      // [D][W2S]
     // consecutive threads read consecutive global words (the transposition happens on the shared-memory side)
     for (int idx = tid; idx < D * D; idx += NT) {
-      const int d = idx >> 6, oo = idx & 63;
+      const int d = idx / D, oo = idx - d * D;
       wat[oo * WS + d] = __ldg(&w[o.head1_w + (size_t)(2 * D + d) * D + oo]);
     }
-    for (int idx = tid; idx < 32 * D; idx += NT) {
-      const int oo = idx >> 5, p = idx & 31;
-      w2t[oo * 36 + p] = __ldg(&w[o.head2_w + (size_t)oo * 32 + p]);  // head2^T is [64][32]
+    for (int idx = tid; idx < (D / 2) * D; idx += NT) {
+      const int oo = idx / (D / 2), p = idx - oo * (D / 2);
+      w2t[oo * W2S + p] = __ldg(&w[o.head2_w + (size_t)oo * (D / 2) + p]);  // head2^T is [D][D / 2]
     }
     __syncthreads();
     if (o.has_context) {
@@ -426,7 +461,7 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
       float hc = 0.0f;
       const int g = tid / D, oo = tid - g * D;
       if (g < nseg)
-        for (int k = 0; k < D; ++k) hc = fmaf(w[o.head1_w + (size_t)(3 * D + k) * D + oo], s_ctx[g][k], hc);
+        for (int kk = 0; kk < D; ++kk) hc = fmaf(w[o.head1_w + (size_t)(3 * D + kk) * D + oo], s_ctx[g][kk], hc);
       __syncthreads();
       if (g < nseg) s_ctx[g][oo] = hc;
       __syncthreads();
@@ -443,11 +478,12 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
       if (P.edge_valid[(size_t)sg.e * MA * MT + (size_t)i * MT + j] != 0.0f) s_plist[atomicAdd(&s_nvalid, 1)] = (uint16_t)pr;
     }
     __syncthreads();
-    // two lanes per pair: each owns half of the 64 product features (first layer) and half of the 32 hidden
+    // two lanes per pair: each owns half of the D product features (first layer) and half of the D / 2 hidden
     // units (second layer); partial sums meet through a shuffle.
     const int npairs = s_nvalid;
     const int hp = tid & 1;
-    const int d0 = hp * 32, p0 = hp * 16;
+    constexpr int DH = D / 2, PH = D / 4;
+    const int d0 = hp * DH, p0 = hp * PH;
     for (int pbase = 0; pbase < npairs; pbase += NT / 2) {
       const int pair = pbase + (tid >> 1);
       const bool valid = pair < npairs;
@@ -460,17 +496,17 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
       const int loc = pc - sg.poff;
       const int i = loc / sg.nt, j = loc - i * sg.nt;
       const int ta = sg.abase + i, tt = sg.tbase + j;
-      float u[32];
+      float u[DH];
 #pragma unroll
-      for (int d = 0; d < 32; ++d) u[d] = z_t[(d0 + d) * TS + ta] * z_t[(d0 + d) * TS + tt];
-      float h2[16];
+      for (int d = 0; d < DH; ++d) u[d] = z_t[(d0 + d) * TS + ta] * z_t[(d0 + d) * TS + tt];
+      float h2[PH];
 #pragma unroll
-      for (int p = 0; p < 16; ++p) h2[p] = w[o.head2_b + p0 + p];
+      for (int p = 0; p < PH; ++p) h2[p] = w[o.head2_b + p0 + p];
       for (int oo = 0; oo < D; ++oo) {
         float acc = 0.0f;
         const float4* wr = (const float4*)&wat[oo * WS + d0];
 #pragma unroll
-        for (int d4 = 0; d4 < 8; ++d4) {
+        for (int d4 = 0; d4 < DH / 4; ++d4) {
           const float4 ww = wr[d4];
           acc = fmaf(ww.x, u[4 * d4], acc);
           acc = fmaf(ww.y, u[4 * d4 + 1], acc);
@@ -479,9 +515,9 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc = fmaxf(acc + y_t[oo * TS + ta] + x_t[oo * TS + tt] + (o.has_context ? s_ctx[g][oo] : 0.0f), 0.0f);
-        const float4* w2 = (const float4*)&w2t[oo * 36 + p0];
+        const float4* w2 = (const float4*)&w2t[oo * W2S + p0];
 #pragma unroll
-        for (int p4 = 0; p4 < 4; ++p4) {
+        for (int p4 = 0; p4 < PH / 4; ++p4) {
           const float4 ww = w2[p4];
           h2[4 * p4] = fmaf(ww.x, acc, h2[4 * p4]);
           h2[4 * p4 + 1] = fmaf(ww.y, acc, h2[4 * p4 + 1]);
@@ -491,12 +527,13 @@ __global__ void __launch_bounds__(NT, 2) att_pair_kernel(const __grid_constant__
       }
       float logit = 0.0f;
 #pragma unroll
-      for (int p = 0; p < 16; ++p) logit = fmaf(w[o.head3_w + p0 + p], fmaxf(h2[p], 0.0f), logit);
+      for (int p = 0; p < PH; ++p) logit = fmaf(w[o.head3_w + p0 + p], fmaxf(h2[p], 0.0f), logit);
       logit += __shfl_xor_sync(0xffffffffu, logit, 1);
       logit += w[o.head3_b];
       if (valid && hp == 0) {
         const size_t off = (size_t)sg.e * MA * MT + (size_t)i * MT + j;
-        P.scores[off] = tanhf(logit) * P.clamp * P.edge_valid[off];
+        const float act = o.sigmoid_out ? 1.0f / (1.0f + expf(-fminf(fmaxf(logit, -20.0f), 20.0f))) : tanhf(logit) * P.clamp;
+        P.scores[off] = act * P.edge_valid[off];
       }
     }
     __syncthreads();  // the next pass reuses every buffer
@@ -524,6 +561,7 @@ struct CommitParams {
 constexpr int AFC = 13;
 
 __global__ void __launch_bounds__(NT, 2) att_commit_kernel(const __grid_constant__ CommitParams P, int group) {
+  constexpr int D = CommitShape::D, FF = CommitShape::FF, TF = CommitShape::TF;
   extern __shared__ __align__(16) float sm[];
   float* x_t = sm;
   float* y_t = x_t + D * TS;
@@ -614,12 +652,12 @@ __global__ void __launch_bounds__(NT, 2) att_commit_kernel(const __grid_constant
     __syncthreads();
     for (int l = 0; l < 2; ++l) {
       linear_t(x_t, 0, R, D, lin1(w + o.enc_in_w[l], w + o.enc_in_b[l]), 3 * D, 3 * D, big_t, nullptr, false);
-      attention_t(big_t, R, split, s_seg, s_seg_of, false, y_t);
+      attention_t<D>(big_t, R, split, s_seg, s_seg_of, false, y_t);
       linear_t(y_t, 0, R, D, lin1(w + o.enc_out_w[l], w + o.enc_out_b[l]), D, D, z_t, x_t, false);
-      layer_norm_t(z_t, R, w + o.enc_n1_w[l], w + o.enc_n1_b[l]);
+      layer_norm_t<D>(z_t, R, w + o.enc_n1_w[l], w + o.enc_n1_b[l]);
       linear_t(z_t, 0, R, D, lin1(w + o.enc_l1_w[l], w + o.enc_l1_b[l]), FF, FF, big_t, nullptr, true);
       linear_t(big_t, 0, R, FF, lin1(w + o.enc_l2_w[l], w + o.enc_l2_b[l]), D, D, x_t, z_t, false);
-      layer_norm_t(x_t, R, w + o.enc_n2_w[l], w + o.enc_n2_b[l]);
+      layer_norm_t<D>(x_t, R, w + o.enc_n2_w[l], w + o.enc_n2_b[l]);
     }
     // heads: one thread per token
     if (tid < R && s_seg_of[tid] != SEG_NONE) {
@@ -663,7 +701,7 @@ extern "C" int muav_att_commit_vectors(const float* d_params, const muav_attcomm
   P.n = n;
   P.max_tasks = max_tasks;
   P.max_agents = max_agents;
-  const size_t smem = sizeof(float) * (size_t)(3 * D * TS + 3 * D * TS);
+  const size_t smem = CommitShape::SMEM;
   static bool set[64];
   int dev = 0;
   cudaGetDevice(&dev);
@@ -694,21 +732,16 @@ extern "C" int muav_att_pair_scores(const float* d_params, const muav_attpair_of
                                       nullptr, d_env_idx, d_need, n, max_tasks, max_agents, score_clamp, d_scores, stream);
 }
 
-extern "C" int muav_att_context_pair_scores(const float* d_params, const muav_attpair_offsets* offsets,
-                                            const float* d_task_feats, const uint8_t* d_task_mask,
-                                            const float* d_agent_feats, const uint8_t* d_agent_mask,
-                                            const float* d_edge_valid, const float* d_context, const int32_t* d_env_idx,
-                                            const uint8_t* d_need, int n, int max_tasks, int max_agents, float score_clamp,
-                                            float* d_scores, void* stream) {
-  using namespace muav_scorer;
-  if (offsets && ((offsets->has_context != 0) != (d_context != nullptr))) return -22;
-  if (!d_params || !offsets || !d_task_feats || !d_task_mask || !d_agent_feats || !d_agent_mask || !d_edge_valid || !d_scores)
-    return -22;
-  if (n < 0 || max_tasks < 1 || max_agents < 1 || max_agents + max_tasks > 48 || max_agents > 16) return -22;
-  if (n == 0) return 0;
+namespace muav_scorer {
+
+template <class S>
+static int launch_pair(const float* d_params, const NetOffsets& o, const float* d_task_feats, const uint8_t* d_task_mask,
+                       const float* d_agent_feats, const uint8_t* d_agent_mask, const float* d_edge_valid,
+                       const float* d_context, const int32_t* d_env_idx, const uint8_t* d_need, int n, int max_tasks,
+                       int max_agents, float score_clamp, float* d_scores, int group, void* stream) {
   Params P;
   P.w = d_params;
-  P.o = *offsets;
+  P.o = o;
   P.task_feats = d_task_feats;
   P.task_mask = d_task_mask;
   P.agent_feats = d_agent_feats;
@@ -722,24 +755,83 @@ extern "C" int muav_att_context_pair_scores(const float* d_params, const muav_at
   P.max_tasks = max_tasks;
   P.max_agents = max_agents;
   P.clamp = score_clamp;
-  const size_t smem = sizeof(float) * (size_t)(3 * D * TS + 3 * D * TS);
   // opt-in shared-memory size: an attribute of the function PER DEVICE (remembered per device; concurrent first calls
   // write the same value)
   static bool set[64];
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(att_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(att_pair_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM);
     if (e != cudaSuccess) return -1000 - (int)e;
     if (dev >= 0 && dev < 64) set[dev] = true;
   }
+  att_pair_kernel<S><<<(n + group - 1) / group, NT, S::SMEM, (cudaStream_t)stream>>>(P, group);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -1000 - (int)e;
+}
+
+}  // namespace muav_scorer
+
+extern "C" int muav_att_context_pair_scores(const float* d_params, const muav_attpair_offsets* offsets,
+                                            const float* d_task_feats, const uint8_t* d_task_mask,
+                                            const float* d_agent_feats, const uint8_t* d_agent_mask,
+                                            const float* d_edge_valid, const float* d_context, const int32_t* d_env_idx,
+                                            const uint8_t* d_need, int n, int max_tasks, int max_agents, float score_clamp,
+                                            float* d_scores, void* stream) {
+  using namespace muav_scorer;
+  if (offsets && ((offsets->has_context != 0) != (d_context != nullptr))) return -22;
+  if (!d_params || !offsets || !d_task_feats || !d_task_mask || !d_agent_feats || !d_agent_mask || !d_edge_valid || !d_scores)
+    return -22;
+  if (n < 0 || max_tasks < 1 || max_agents < 1 || max_agents + max_tasks > 48 || max_agents > 16) return -22;
+  if (n == 0) return 0;
+  const muav_attpair_offsets& a = *offsets;
+  NetOffsets o{};
+  o.agent_proj_w = a.agent_proj_w; o.agent_proj_b = a.agent_proj_b; o.task_proj_w = a.task_proj_w;
+  o.task_proj_b = a.task_proj_b; o.type_embed = a.type_embed;
+  o.n_enc = 1;
+  o.enc_in_w[0] = a.enc_in_w; o.enc_in_b[0] = a.enc_in_b; o.enc_out_w[0] = a.enc_out_w; o.enc_out_b[0] = a.enc_out_b;
+  o.enc_l1_w[0] = a.enc_l1_w; o.enc_l1_b[0] = a.enc_l1_b; o.enc_l2_w[0] = a.enc_l2_w; o.enc_l2_b[0] = a.enc_l2_b;
+  o.enc_n1_w[0] = a.enc_n1_w; o.enc_n1_b[0] = a.enc_n1_b; o.enc_n2_w[0] = a.enc_n2_w; o.enc_n2_b[0] = a.enc_n2_b;
+  o.a2t_in_w = a.a2t_in_w; o.a2t_in_b = a.a2t_in_b; o.a2t_out_w = a.a2t_out_w; o.a2t_out_b = a.a2t_out_b;
+  o.t2a_in_w = a.t2a_in_w; o.t2a_in_b = a.t2a_in_b; o.t2a_out_w = a.t2a_out_w; o.t2a_out_b = a.t2a_out_b;
+  o.head1_w = a.head1_w; o.head1_b = a.head1_b; o.head2_w = a.head2_w; o.head2_b = a.head2_b; o.head3_w = a.head3_w;
+  o.head3_b = a.head3_b; o.ctx_proj_w = a.ctx_proj_w; o.ctx_proj_b = a.ctx_proj_b; o.has_context = a.has_context;
+  o.sigmoid_out = 0;
   // environments per CTA: three WPS_hard environments (~19 tokens each) fill the 64-token pass
   int group = 3;
   const char* ge = getenv("MUAV_SCORER_GROUP");
   if (ge) group = atoi(ge);
   if (group < 1) group = 1;
   if (group > GLIST) group = GLIST;
-  att_pair_kernel<<<(n + group - 1) / group, NT, smem, (cudaStream_t)stream>>>(P, group);
-  cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? 0 : -1000 - (int)e;
+  return launch_pair<PairShape>(d_params, o, d_task_feats, d_task_mask, d_agent_feats, d_agent_mask, d_edge_valid, d_context,
+                                d_env_idx, d_need, n, max_tasks, max_agents, score_clamp, d_scores, group, stream);
+}
+
+extern "C" int muav_att_coalition_scores(const float* d_params, const muav_attcoal_offsets* offsets, const float* d_task_feats,
+                                         const uint8_t* d_task_mask, const float* d_agent_feats, const uint8_t* d_agent_mask,
+                                         const float* d_edge_valid, const int32_t* d_env_idx, const uint8_t* d_need, int n,
+                                         int max_tasks, int max_agents, float* d_scores, void* stream) {
+  using namespace muav_scorer;
+  if (!d_params || !offsets || !d_task_feats || !d_task_mask || !d_agent_feats || !d_agent_mask || !d_edge_valid || !d_scores)
+    return -22;
+  if (n < 0 || max_tasks < 1 || max_agents < 1 || max_agents + max_tasks > 64 || max_agents > 16) return -22;
+  if (n == 0) return 0;
+  const muav_attcoal_offsets& a = *offsets;
+  NetOffsets o{};
+  o.agent_proj_w = a.agent_proj_w; o.agent_proj_b = a.agent_proj_b; o.task_proj_w = a.task_proj_w;
+  o.task_proj_b = a.task_proj_b; o.type_embed = a.type_embed;
+  o.n_enc = 2;
+  for (int l = 0; l < 2; ++l) {
+    o.enc_in_w[l] = a.enc_in_w[l]; o.enc_in_b[l] = a.enc_in_b[l]; o.enc_out_w[l] = a.enc_out_w[l]; o.enc_out_b[l] = a.enc_out_b[l];
+    o.enc_l1_w[l] = a.enc_l1_w[l]; o.enc_l1_b[l] = a.enc_l1_b[l]; o.enc_l2_w[l] = a.enc_l2_w[l]; o.enc_l2_b[l] = a.enc_l2_b[l];
+    o.enc_n1_w[l] = a.enc_n1_w[l]; o.enc_n1_b[l] = a.enc_n1_b[l]; o.enc_n2_w[l] = a.enc_n2_w[l]; o.enc_n2_b[l] = a.enc_n2_b[l];
+  }
+  o.a2t_in_w = a.a2t_in_w; o.a2t_in_b = a.a2t_in_b; o.a2t_out_w = a.a2t_out_w; o.a2t_out_b = a.a2t_out_b;
+  o.t2a_in_w = a.t2a_in_w; o.t2a_in_b = a.t2a_in_b; o.t2a_out_w = a.t2a_out_w; o.t2a_out_b = a.t2a_out_b;
+  o.head1_w = a.head1_w; o.head1_b = a.head1_b; o.head2_w = a.head2_w; o.head2_b = a.head2_b; o.head3_w = a.head3_w;
+  o.head3_b = a.head3_b;
+  o.sigmoid_out = 1;
+  // one WPS_escort environment (14 agents + up to 48 task tokens) fills the 64-token pass; lighter ones share it
+  return launch_pair<CoalShape>(d_params, o, d_task_feats, d_task_mask, d_agent_feats, d_agent_mask, d_edge_valid, nullptr,
+                                d_env_idx, d_need, n, max_tasks, max_agents, 0.0f, d_scores, 2, stream);
 }

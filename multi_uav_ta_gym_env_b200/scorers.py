@@ -662,3 +662,83 @@ class FusedAttCommitScorer:
             C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         if rc != 0:
             raise RuntimeError(f"muav_att_commit_vectors failed: {rc}")
+
+
+class FusedAttCoalitionScorer:
+    """AttCoalitionNet forward as one CUDA kernel (csrc/muav_scorer.cu, att_pair_kernel at d_model 128 / two encoder layers /
+    feed-forward 512; C ABI muav_att_coalition_scores): escort tokens -> sigmoid(clip(logits)) * edge_valid, the edge scores
+    of AllocSpec.att_escort().  Same packing rules as the pair kernel (only live agents / valid task columns are tokens)."""
+
+    def __init__(self, net, device):
+        import ctypes as C
+
+        from . import _lib
+
+        sd = net.state_dict()
+        if len(net.self_encoder.layers) != 2 or sd["task_proj.weight"].shape != (128, TASK_FEAT_DIM_E) \
+                or sd["agent_proj.weight"].shape != (128, AGENT_FEAT_DIM_E) \
+                or sd["self_encoder.layers.0.linear1.weight"].shape != (512, 128) or net.cross_a2t.num_heads != 4:
+            raise ValueError("the fused kernel implements the default AttCoalitionNet (d_model 128, 4 heads, 3 layers)")
+        self.lib = _lib.cuda_lib()
+        self.offsets = _lib.MuavAttCoalOffsets()
+        chunks, pos = [], 0
+
+        def put(t, transpose):
+            nonlocal pos
+            t = t.detach().to(torch.float32)
+            if transpose:
+                t = t.t().contiguous()
+            t = t.reshape(-1)
+            pos = (pos + 3) // 4 * 4
+            at = pos
+            chunks.append((at, t))
+            pos += t.numel()
+            return at
+
+        o = self.offsets
+        o.agent_proj_w, o.agent_proj_b = put(sd["agent_proj.weight"], True), put(sd["agent_proj.bias"], False)
+        o.task_proj_w, o.task_proj_b = put(sd["task_proj.weight"], True), put(sd["task_proj.bias"], False)
+        o.type_embed = put(sd["type_embed.weight"], False)
+        for l in range(2):
+            pre = f"self_encoder.layers.{l}."
+            o.enc_in_w[l], o.enc_in_b[l] = put(sd[pre + "self_attn.in_proj_weight"], True), put(sd[pre + "self_attn.in_proj_bias"], False)
+            o.enc_out_w[l], o.enc_out_b[l] = put(sd[pre + "self_attn.out_proj.weight"], True), put(sd[pre + "self_attn.out_proj.bias"], False)
+            o.enc_l1_w[l], o.enc_l1_b[l] = put(sd[pre + "linear1.weight"], True), put(sd[pre + "linear1.bias"], False)
+            o.enc_l2_w[l], o.enc_l2_b[l] = put(sd[pre + "linear2.weight"], True), put(sd[pre + "linear2.bias"], False)
+            o.enc_n1_w[l], o.enc_n1_b[l] = put(sd[pre + "norm1.weight"], False), put(sd[pre + "norm1.bias"], False)
+            o.enc_n2_w[l], o.enc_n2_b[l] = put(sd[pre + "norm2.weight"], False), put(sd[pre + "norm2.bias"], False)
+        for name, pre in (("a2t", "cross_a2t."), ("t2a", "cross_t2a.")):
+            setattr(o, name + "_in_w", put(sd[pre + "in_proj_weight"], True))
+            setattr(o, name + "_in_b", put(sd[pre + "in_proj_bias"], False))
+            setattr(o, name + "_out_w", put(sd[pre + "out_proj.weight"], True))
+            setattr(o, name + "_out_b", put(sd[pre + "out_proj.bias"], False))
+        o.head1_w, o.head1_b = put(sd["pair_head.0.weight"], True), put(sd["pair_head.0.bias"], False)
+        o.head2_w, o.head2_b = put(sd["pair_head.2.weight"], True), put(sd["pair_head.2.bias"], False)
+        o.head3_w, o.head3_b = put(sd["pair_head.4.weight"], True), put(sd["pair_head.4.bias"], False)
+        buf = torch.zeros(pos, dtype=torch.float32)
+        for p, t in chunks:
+            buf[p:p + t.numel()] = t.cpu()
+        self.params = buf.to(device)
+        self.device = device
+        self._C = C
+
+    @torch.no_grad()
+    def score(self, tok: dict, scores_out: torch.Tensor, idx: Optional[torch.Tensor] = None, use_need: bool = False):
+        """tok: escort tokens (tokens_escort() dict or the fused escort token tensors); rows of environments that are not
+        scored are left untouched."""
+        C = self._C
+        E, MA, MT = scores_out.shape
+        tm = tok["task_mask_u8"] if "task_mask_u8" in tok else tok["task_mask"].to(torch.uint8)
+        am = tok["agent_mask_u8"] if "agent_mask_u8" in tok else tok["agent_mask"].to(torch.uint8)
+        n = E if idx is None else int(idx.numel())
+        if n == 0:
+            return
+        if idx is not None and idx.dtype != torch.int32:
+            idx = idx.to(torch.int32)
+        rc = self.lib.dll.muav_att_coalition_scores(
+            self.params.data_ptr(), C.byref(self.offsets), tok["task_feats"].data_ptr(), tm.data_ptr(),
+            tok["agent_feats"].data_ptr(), am.data_ptr(), tok["edge_valid"].data_ptr(),
+            None if idx is None else idx.data_ptr(), tok["need"].data_ptr() if use_need else None, n, MT, MA,
+            scores_out.data_ptr(), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"muav_att_coalition_scores failed: {rc}")

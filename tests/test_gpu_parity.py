@@ -1312,3 +1312,48 @@ def test_fused_commit_scorer_kernel_and_fused_commit_tokens():
         seen += int(need.sum().item())
     assert seen > E
     assert int(env.error_flags().abs().max().item()) == 0
+
+
+def test_fused_coalition_scorer_kernel_and_fused_escort_tokens():
+    """csrc/muav_scorer.cu at the AttCoalitionNet shape (d_model 128, two encoder layers, feed-forward 512) vs the PyTorch
+    module on real escort tokens (fp32, 5e-5 on sigmoid scores), the escort tokens emitted by the step kernel
+    (muav_token_out.agent_feat_dim = 16, with task_order) vs the standalone muav_tokens_escort, and the fused pipeline
+    (tokens -> kernel -> AllocSpec.att_escort) staying on the trajectory of the PyTorch-scored one."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+    from multi_uav_ta_gym_env_b200.scorers import AttCoalitionNet, FusedAttCoalitionScorer, coalition_scores
+
+    cfg = wps_config("WPS_escort")
+    E = 96
+    env = make_env(cfg, list(range(E)))
+    env.step_allocated(AllocSpec.coalition_hungarian(12), n_steps=45)
+    torch.manual_seed(3)
+    net = AttCoalitionNet().cuda().eval()
+    fused = FusedAttCoalitionScorer(net, torch.device("cuda"))
+    tok = env.tokens_escort(48, 16)
+    want = coalition_scores(net, tok)
+    got = torch.full_like(want, 7.0)
+    fused.score(tok, got)
+    assert (got - want).abs().max().item() < 5e-5, (got - want).abs().max().item()
+    assert want.max().item() > 0.1 and int((tok["edge_valid"] > 0).sum().item()) > 20 * E
+    idx = torch.arange(5, 90, 3, device="cuda", dtype=torch.int32)
+    got2 = torch.full_like(want, 7.0)
+    fused.score(tok, got2, idx)
+    assert (got2[idx.long()] - want[idx.long()]).abs().max().item() < 5e-5 and bool((got2[0] == 7.0).all())
+    # fused emission of the escort tokens: after every step the rows with need == 1 equal the standalone builder's
+    ftok = env.enable_fused_tokens(48, 16, 12, 0x1F, escort=True)
+    env.refresh_fused_tokens()
+    spec = AllocSpec.att_escort(12)
+    scores = torch.zeros(E, 16, 48, device="cuda")
+    seen = 0
+    for t in range(50):
+        fused.score(ftok, scores, use_need=True)
+        env.step_allocated(spec, 1, edge_scores=scores, task_order=ftok["task_order"])
+        need = ftok["need"].bool()
+        ref = env.tokens_escort(48, 16)
+        for k in ("task_feats", "agent_feats", "edge_valid", "task_ids", "task_order"):
+            assert torch.equal(ftok[k][need], ref[k][need]), (t, k)
+        assert torch.equal(ftok["task_mask_u8"][need].bool(), ref["task_mask"][need])
+        assert torch.equal(ftok["agent_mask_u8"][need].bool(), ref["agent_mask"][need])
+        seen += int(need.sum().item())
+    assert seen > E
+    assert int(env.error_flags().abs().max().item()) == 0
