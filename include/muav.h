@@ -376,6 +376,14 @@ int muav_att_commit_vectors(const float* d_params, const muav_attcommit_offsets*
                             const uint8_t* d_task_mask, const float* d_agent_feats13, const uint8_t* d_agent_mask,
                             const int32_t* d_env_idx, const uint8_t* d_need, int n, int max_tasks, int max_agents,
                             float* d_priorities, float* d_commits, void* stream);
+/* AttCommitNet forward on the tensor cores (same machinery as muav_att_pair_scores_tc: two encoder layers with
+ * activations in TMEM, then the two sigmoid heads); same function, arguments and tolerance as muav_att_commit_vectors. */
+int64_t muav_att_commit_tc_floats(void);
+int muav_att_commit_tc_pack(const float* d_params, const muav_attcommit_offsets* offsets, float* d_tc_weights, void* stream);
+int muav_att_commit_vectors_tc(const float* d_params, const muav_attcommit_offsets* offsets, const float* d_tc_weights,
+                               const float* d_task_feats, const uint8_t* d_task_mask, const float* d_agent_feats13,
+                               const uint8_t* d_agent_mask, const int32_t* d_env_idx, const uint8_t* d_need, int n,
+                               int max_tasks, int max_agents, float* d_priorities, float* d_commits, void* stream);
 
 #ifdef __cplusplus
 }

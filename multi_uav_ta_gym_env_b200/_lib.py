@@ -112,6 +112,7 @@ ABI_SYMBOLS = [
     "muav_att_pair_scores", "muav_att_context_pair_scores", "muav_rollout", "muav_state_bytes", "muav_tape_bytes", "muav_reset_upload", "muav_snapshot",
     "muav_ctx_create", "muav_ctx_destroy", "muav_ctx_step_host", "muav_ctx_allocate_host", "muav_att_commit_vectors",
     "muav_att_pair_tc_floats", "muav_att_pair_tc_pack", "muav_att_pair_scores_tc", "muav_att_coalition_scores",
+    "muav_att_commit_tc_floats", "muav_att_commit_tc_pack", "muav_att_commit_vectors_tc",
 ]
 
 
@@ -255,6 +256,13 @@ class CudaLib(Lib):
         d.muav_att_pair_scores_tc.restype = C.c_int
         d.muav_att_pair_scores_tc.argtypes = [P, C.POINTER(MuavAttPairOffsets), P, P, P, P, P, P, P, P, P, C.c_int, C.c_int,
                                               C.c_int, C.c_float, P, P]
+        d.muav_att_commit_tc_floats.restype = C.c_int64
+        d.muav_att_commit_tc_floats.argtypes = []
+        d.muav_att_commit_tc_pack.restype = C.c_int
+        d.muav_att_commit_tc_pack.argtypes = [P, C.POINTER(MuavAttCommitOffsets), P, P]
+        d.muav_att_commit_vectors_tc.restype = C.c_int
+        d.muav_att_commit_vectors_tc.argtypes = [P, C.POINTER(MuavAttCommitOffsets), P, P, P, P, P, P, P, C.c_int, C.c_int,
+                                                 C.c_int, P, P, P]
         d.muav_att_coalition_scores.restype = C.c_int
         d.muav_att_coalition_scores.argtypes = [P, C.POINTER(MuavAttCoalOffsets), P, P, P, P, P, P, P, C.c_int, C.c_int,
                                                 C.c_int, P, P]

@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "../../include/muav.h"
 
@@ -98,6 +99,30 @@ __constant__ ChunkDesc c_chunks[NCHUNK] = {
     CH(O_P2, 32, 64, U_HI, U_LO, 448, 0, 1),                            // 23 head2 (per pair tile)
 };
 constexpr uint32_t TCW_FLOATS = O_P2 + S_H2;
+
+// AttCommitNet (AttentionCommit.py:68-100): the projections and two encoder layers, no cross attention / pair head
+constexpr int NCHUNK_COMMIT = 19;
+constexpr uint32_t S_ENC = 4 * S_IN + S_64 + 2 * S_128 + 2 * S_64;   // one encoder layer
+#define ENC_CHUNKS(o)                                                         \
+  CH((o), 192, 16, A0_HI, A0_LO, 128, 0, 0),                                  \
+  CH((o) + S_IN, 192, 16, A0_HI + 16, A0_LO + 16, 128, 1, 0),                 \
+  CH((o) + 2 * S_IN, 192, 16, A0_HI + 32, A0_LO + 32, 128, 1, 0),             \
+  CH((o) + 3 * S_IN, 192, 16, A0_HI + 48, A0_LO + 48, 128, 1, 1),             \
+  CH((o) + 4 * S_IN, 64, 64, AO_HI, AO_LO, 448, 0, 1),                        \
+  CH((o) + 4 * S_IN + S_64, 128, 32, A0_HI, A0_LO, 128, 0, 0),                \
+  CH((o) + 4 * S_IN + S_64 + S_128, 128, 32, A0_HI + 32, A0_LO + 32, 128, 1, 1), \
+  CH((o) + 4 * S_IN + S_64 + 2 * S_128, 64, 64, H_HI, H_LO, 128, 0, 0),       \
+  CH((o) + 4 * S_IN + 2 * S_64 + 2 * S_128, 64, 64, H_HI + 64, H_LO + 64, 128, 1, 1)
+__constant__ ChunkDesc c_chunks_commit[NCHUNK_COMMIT] = {
+    CH(0, 128, 16, F_HI, F_LO, 128, 0, 1),   // agent_proj | task_proj
+    ENC_CHUNKS(S_PROJ),
+    ENC_CHUNKS(S_PROJ + S_ENC),
+};
+constexpr uint32_t TCW_FLOATS_COMMIT = S_PROJ + 2 * S_ENC;
+template <bool COMMIT>
+__device__ __forceinline__ const ChunkDesc* chunk_table() {
+  return COMMIT ? c_chunks_commit : c_chunks;
+}
 
 // ---- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -272,9 +297,20 @@ __device__ __forceinline__ void issue_chunk(uint32_t tm, const ChunkDesc& c, con
   else issue_chunk_k<64>(tm, c, b0);
 }
 
+constexpr int MAX_ENC = 2;
+// parameter offsets of both networks in one form (filled from muav_attpair_offsets / muav_attcommit_offsets)
+struct TcOffsets {
+  int32_t agent_proj_w, agent_proj_b, task_proj_w, task_proj_b, type_embed;
+  int32_t enc_in_w[MAX_ENC], enc_in_b[MAX_ENC], enc_out_w[MAX_ENC], enc_out_b[MAX_ENC], enc_l1_w[MAX_ENC], enc_l1_b[MAX_ENC],
+      enc_l2_w[MAX_ENC], enc_l2_b[MAX_ENC], enc_n1_w[MAX_ENC], enc_n1_b[MAX_ENC], enc_n2_w[MAX_ENC], enc_n2_b[MAX_ENC];
+  int32_t a2t_in_w, a2t_in_b, a2t_out_w, a2t_out_b, t2a_in_w, t2a_in_b, t2a_out_w, t2a_out_b;
+  int32_t head1_w, head1_b, head2_w, head2_b, head3_w, head3_b;
+  int32_t ctx_proj_w, ctx_proj_b, has_context;
+  int32_t priority_w, priority_b, commit_w, commit_b;   // AttCommitNet heads
+};
 struct Params {
   const float* w;
-  muav_attpair_offsets o;
+  TcOffsets o;
   const float* tcw;
   const float* task_feats;
   const uint8_t* task_mask;
@@ -285,6 +321,8 @@ struct Params {
   const int32_t* env_idx;
   const uint8_t* need;
   float* scores;
+  float* pri;   // AttCommitNet: priorities [E, max_tasks], commit gates [E, max_agents]
+  float* com;
   int n, max_tasks, max_agents;
   float clamp;
   float* dbg;   // development: [stage][128][64] dump of the layer inputs of CTA 0's first pass, or NULL
@@ -461,9 +499,12 @@ __device__ __forceinline__ void kv_epilogue(uint32_t tl, float* __restrict__ kv,
 
 // x <- LayerNorm(x + acc + bias) (eps 1e-5, biased variance) on this thread's row; the two threads of a row own 32
 // columns each and exchange partial sums through shared memory
-__device__ __forceinline__ void ln_epilogue(uint32_t tl, int row, int half, int d_col, const float* __restrict__ bias,
-                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                            float (*s_part)[2][ROWS], float* __restrict__ tile = nullptr) {
+// (returns the dot product of this thread's 32 output columns with dot_w, if given: the AttCommitNet heads)
+__device__ __forceinline__ float ln_epilogue(uint32_t tl, int row, int half, int d_col, const float* __restrict__ bias,
+                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                             float (*s_part)[2][ROWS], float* __restrict__ tile = nullptr,
+                                             const float* __restrict__ dot_w = nullptr) {
+  float dot = 0.0f;
   float z[32];
   float sum = 0.0f;
 #pragma unroll
@@ -504,10 +545,20 @@ __device__ __forceinline__ void ln_epilogue(uint32_t tl, int row, int half, int 
 #pragma unroll
       for (int i = 0; i < 4; ++i) dst[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
     }
+    if (dot_w) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dot = fmaf(__ldg(&dot_w[c + i]), y[i], dot);
+    }
   }
+  return dot;
 }
 
-__global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constant__ Params P, int group) {
+template <bool COMMIT>
+__global__ void __launch_bounds__(NT, 1) att_tc_kernel(const __grid_constant__ Params P, int group) {
+  const ChunkDesc* const chunks = chunk_table<COMMIT>();
+  constexpr int N_CHUNKS = COMMIT ? NCHUNK_COMMIT : NCHUNK;            // streamed per pass
+  constexpr int N_LAYER_CHUNKS = COMMIT ? NCHUNK_COMMIT : CH_PAIR1;    // consumed by the layer loop of the MMA thread
+  constexpr int AFD = COMMIT ? 13 : AF;                                // agent features per token
   extern __shared__ __align__(1024) unsigned char dsm[];
   unsigned char* ring = dsm;
   float* kvg = (float*)(dsm + NSLOT * SLOT_BYTES);
@@ -523,7 +574,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int MT = P.max_tasks, MA = P.max_agents;
   const float* w = P.w;
-  const muav_attpair_offsets& o = P.o;
+  const TcOffsets& o = P.o;
 
   // work split: CTA b of the persistent (one per SM) grid takes the counted environments of rank [b * per, (b + 1) * per)
   // and streams them through its passes (group > 0: `group` environments per CTA instead, A/B runs)
@@ -591,10 +642,15 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
     s_next = 0;
     s_done = m;
   }
-  // scores of every listed environment start at zero (padded rows / columns, invalid edges)
+  // outputs of every listed environment start at zero (padded rows / columns, invalid edges)
   for (int g = 0; g < m; ++g) {
-    float* sc = P.scores + (size_t)s_env[g] * MA * MT;
-    for (int idx = tid; idx < MA * MT; idx += NT) sc[idx] = 0.0f;
+    if (COMMIT) {
+      for (int idx = tid; idx < MT; idx += NT) P.pri[(size_t)s_env[g] * MT + idx] = 0.0f;
+      for (int idx = tid; idx < MA; idx += NT) P.com[(size_t)s_env[g] * MA + idx] = 0.0f;
+    } else {
+      float* sc = P.scores + (size_t)s_env[g] * MA * MT;
+      for (int idx = tid; idx < MA * MT; idx += NT) sc[idx] = 0.0f;
+    }
   }
   __syncthreads();
   for (;;) {
@@ -605,7 +661,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       bool full = false;
       while (g < m && ns < GMAX) {
         const int na = s_na[g], nt = s_nt[g];
-        if (na == 0 || nt == 0) { ++g; continue; }
+        if (COMMIT ? (na == 0 && nt == 0) : (na == 0 || nt == 0)) { ++g; continue; }
         if (((sa + na + 3) & ~3) + st + nt > ROWS) { full = true; break; }
         s_seg[ns].e = s_env[g];
         s_seg[ns].abase = sa;
@@ -641,11 +697,11 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
     if (warp == 9) {
       // ================= producer: weight chunks through the ring
       if (lane == 0) {
-        for (int c = 0; c < NCHUNK; ++c, ++seq) {
+        for (int c = 0; c < N_CHUNKS; ++c, ++seq) {
           const int slot = seq & (NSLOT - 1);
           const uint32_t use = seq / NSLOT;
           if (use > 0) mbar_wait_relaxed(&s_empty[slot], (use - 1) & 1);
-          const ChunkDesc cd = c_chunks[c];
+          const ChunkDesc cd = chunks[c];
           const uint32_t bytes = (uint32_t)cd.nc * cd.kc * 8u;
           mbar_expect_tx(&s_full[slot], bytes);
           bulk_g2s(ring + slot * SLOT_BYTES, P.tcw + cd.off, bytes, &s_full[slot]);
@@ -656,12 +712,12 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       // ================= MMA issuer
       if (lane == 0) {
         int c = 0;
-        while (c < CH_PAIR1) {
+        while (c < N_LAYER_CHUNKS) {
           mbar_wait(&s_a_ready, pa);
           pa ^= 1;
           tc_fence_after();
           for (;;) {
-            const ChunkDesc cd = c_chunks[c];
+            const ChunkDesc cd = chunks[c];
             const int slot = seq & (NSLOT - 1);
             mbar_wait(&s_full[slot], (seq / NSLOT) & 1);
             tc_fence_after();
@@ -673,6 +729,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
           }
           tc_commit(&s_d_ready);
         }
+        if constexpr (!COMMIT) {
         // pair head: the two weight chunks stay in their slots for every tile of the pass
         mbar_wait(&s_a_ready, pa);
         pa ^= 1;
@@ -705,6 +762,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
         }
         tc_commit(&s_empty[slot1]);
         tc_commit(&s_empty[slot2]);
+        }
       }
       __syncwarp();
     } else {
@@ -740,9 +798,9 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
         for (int i = 0; i < 16; ++i) f[i] = 0.0f;
         if (on) {
           if (is_agent) {
-            const float* src = P.agent_feats + ((size_t)sg.e * MA + (row - sg.abase)) * AF;
+            const float* src = P.agent_feats + ((size_t)sg.e * MA + (row - sg.abase)) * AFD;
 #pragma unroll
-            for (int i = 0; i < AF; ++i) f[i] = src[i];
+            for (int i = 0; i < AFD; ++i) f[i] = src[i];
           } else {
             const float* src = P.task_feats + ((size_t)sg.e * MT + (row - sg.tbase)) * TF;
 #pragma unroll
@@ -758,7 +816,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       TS_MARK();
 
       // ---- list of the pairs with a valid edge (needs only the tokens: built while the first MMAs run)
-      {
+      if constexpr (!COMMIT) {
         int poff[GMAX + 1];
         poff[0] = 0;
 #pragma unroll
@@ -812,12 +870,59 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       mbar_arrive(&s_a_ready);
       TS_MARK();
 
+      if constexpr (COMMIT) {
+        // ---- AttCommitNet: two encoder layers, then priority = sigmoid(w_p . h + b_p) on task rows and commit =
+        // sigmoid(w_c . h + b_c) on agent rows (AttentionCommit.py:90-100)
+        float dot = 0.0f;
+#pragma unroll 1
+        for (int l = 0; l < 2; ++l) {
+          wait_d(&s_d_ready, pd, lane);
+          kv_epilogue(tl, kvg, row, half, is_agent, 0, 128, 128, w + o.enc_in_b[l], w + o.enc_in_b[l]);
+          worker_sync();
+          attention(tl, kvg, half, on, sg, false, is_agent, 0, 128, 128, w + o.enc_in_b[l], w + o.enc_in_b[l], AO_HI, AO_LO);
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&s_a_ready);
+          wait_d(&s_d_ready, pd, lane);
+          ln_epilogue(tl, row, half, 448, w + o.enc_out_b[l], w + o.enc_n1_w[l], w + o.enc_n1_b[l], s_part);
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&s_a_ready);
+          wait_d(&s_d_ready, pd, lane);
+#pragma unroll 1
+          for (int g = 0; g < 4; ++g) {
+            const int c = half * 64 + g * 16;
+            float v[16];
+            tmem_ld16(tl + 128 + c, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(&w[o.enc_l1_b[l] + c + i]), 0.0f);
+            st_operand16(tl, H_HI, H_LO, c, v);
+          }
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&s_a_ready);
+          wait_d(&s_d_ready, pd, lane);
+          dot = ln_epilogue(tl, row, half, 128, w + o.enc_l2_b[l], w + o.enc_n2_w[l], w + o.enc_n2_b[l], s_part, nullptr,
+                            l == 1 ? w + (is_agent ? o.commit_w : o.priority_w) : nullptr);
+          tc_wait_st();
+          tc_fence_before();
+          if (l == 0) mbar_arrive(&s_a_ready);
+        }
+        s_part[0][half][row] = dot;
+        worker_sync();
+        if (half == 0 && on) {
+          const float acc = s_part[0][0][row] + s_part[0][1][row] + w[is_agent ? o.commit_b : o.priority_b];
+          const float v = 1.0f / (1.0f + expf(-acc));
+          if (is_agent) P.com[(size_t)sg.e * MA + (row - sg.abase)] = v;
+          else P.pri[(size_t)sg.e * MT + (row - sg.tbase)] = v;
+        }
+      } else {
       // ---- encoder self-attention
       wait_d(&s_d_ready, pd, lane);
       TS_MARK();
-      kv_epilogue(tl, kvg, row, half, is_agent, 0, 128, 128, w + o.enc_in_b, w + o.enc_in_b);
+      kv_epilogue(tl, kvg, row, half, is_agent, 0, 128, 128, w + o.enc_in_b[0], w + o.enc_in_b[0]);
       worker_sync();
-      attention(tl, kvg, half, on, sg, false, is_agent, 0, 128, 128, w + o.enc_in_b, w + o.enc_in_b, AO_HI, AO_LO);
+      attention(tl, kvg, half, on, sg, false, is_agent, 0, 128, 128, w + o.enc_in_b[0], w + o.enc_in_b[0], AO_HI, AO_LO);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&s_a_ready);
@@ -826,7 +931,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       // ---- x1 = LN1(x + out_proj(attn))
       wait_d(&s_d_ready, pd, lane);
       TS_MARK();
-      ln_epilogue(tl, row, half, 448, w + o.enc_out_b, w + o.enc_n1_w, w + o.enc_n1_b, s_part);
+      ln_epilogue(tl, row, half, 448, w + o.enc_out_b[0], w + o.enc_n1_w[0], w + o.enc_n1_b[0], s_part);
       tc_wait_st();
       if (first_pass) dump_a0(P, 1, tl, row, half);
       tc_fence_before();
@@ -842,7 +947,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
         float v[16];
         tmem_ld16(tl + 128 + c, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(&w[o.enc_l1_b + c + i]), 0.0f);
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(&w[o.enc_l1_b[0] + c + i]), 0.0f);
         st_operand16(tl, H_HI, H_LO, c, v);
       }
       tc_wait_st();
@@ -853,7 +958,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
       // ---- h = LN2(x1 + linear2(hidden))
       wait_d(&s_d_ready, pd, lane);
       TS_MARK();
-      ln_epilogue(tl, row, half, 128, w + o.enc_l2_b, w + o.enc_n2_w, w + o.enc_n2_b, s_part, o.has_context ? kvg : nullptr);
+      ln_epilogue(tl, row, half, 128, w + o.enc_l2_b[0], w + o.enc_n2_w[0], w + o.enc_n2_b[0], s_part, o.has_context ? kvg : nullptr);
       tc_wait_st();
       if (first_pass) dump_a0(P, 2, tl, row, half);
       tc_fence_before();
@@ -1001,7 +1106,6 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
               const float4* gb = (const float4*)&gt[tt[u2] * ZG_STRIDE + c];
               float v[16];
               tmem_ld16(tl + (u2 ? P1B_D : P1_D) + c, v);
-#pragma unroll
               if (o.has_context) {
                 const float* hc = &s_hc[s_seg_of[ta[u2]]][c];
 #pragma unroll
@@ -1047,6 +1151,7 @@ __global__ void __launch_bounds__(NT, 1) att_pair_tc_kernel(const __grid_constan
         // the next round's products overwrite the operand columns: every read of this round is complete (wait::ld above)
         tc_fence_before();
       }
+      }   // !COMMIT
       if (ts) ts[0] = n_ts;
     }
     first_pass = false;
@@ -1074,9 +1179,10 @@ struct PackSrc {
   int src[NCHUNK][2], ldo[NCHUNK][2], n0[NCHUNK][2], kreal[NCHUNK][2];
   int nsplit[NCHUNK], k0[NCHUNK];
 };
+template <bool COMMIT>
 __global__ void tc_pack_kernel(const float* __restrict__ w, const __grid_constant__ PackSrc S, float* __restrict__ out) {
   const int c = blockIdx.y;
-  const ChunkDesc cd = c_chunks[c];
+  const ChunkDesc cd = chunk_table<COMMIT>()[c];
   const int total = cd.nc * cd.kc;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int n = idx / cd.kc, k = idx - n * cd.kc;
@@ -1127,7 +1233,7 @@ extern "C" int muav_att_pair_tc_pack(const float* d_params, const muav_attpair_o
   for (int i = 0; i < 2; ++i) two(20 + i, o.head1_w, D, o.head1_w + D * D, D, D, 32 * i);
   one(22, o.head1_w + 2 * D * D, D, 0, 0, D);
   one(23, o.head2_w, D / 2, 0, 0, D);
-  tc_pack_kernel<<<dim3(8, NCHUNK), 256, 0, (cudaStream_t)stream>>>(d_params, S, d_tc_weights);
+  tc_pack_kernel<false><<<dim3(8, NCHUNK), 256, 0, (cudaStream_t)stream>>>(d_params, S, d_tc_weights);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -1000 - (int)e;
 }
@@ -1145,8 +1251,21 @@ extern "C" int muav_att_pair_scores_tc(const float* d_params, const muav_attpair
   if (n < 0 || max_tasks < 1 || max_agents < 1 || max_agents + max_tasks > 48 || max_agents > 16) return -22;
   if (n == 0) return 0;
   Params P;
+  memset(&P, 0, sizeof(P));
   P.w = d_params;
-  P.o = *offsets;
+  {
+    const muav_attpair_offsets& a = *offsets;
+    TcOffsets& o = P.o;
+    o.agent_proj_w = a.agent_proj_w; o.agent_proj_b = a.agent_proj_b; o.task_proj_w = a.task_proj_w;
+    o.task_proj_b = a.task_proj_b; o.type_embed = a.type_embed;
+    o.enc_in_w[0] = a.enc_in_w; o.enc_in_b[0] = a.enc_in_b; o.enc_out_w[0] = a.enc_out_w; o.enc_out_b[0] = a.enc_out_b;
+    o.enc_l1_w[0] = a.enc_l1_w; o.enc_l1_b[0] = a.enc_l1_b; o.enc_l2_w[0] = a.enc_l2_w; o.enc_l2_b[0] = a.enc_l2_b;
+    o.enc_n1_w[0] = a.enc_n1_w; o.enc_n1_b[0] = a.enc_n1_b; o.enc_n2_w[0] = a.enc_n2_w; o.enc_n2_b[0] = a.enc_n2_b;
+    o.a2t_in_w = a.a2t_in_w; o.a2t_in_b = a.a2t_in_b; o.a2t_out_w = a.a2t_out_w; o.a2t_out_b = a.a2t_out_b;
+    o.t2a_in_w = a.t2a_in_w; o.t2a_in_b = a.t2a_in_b; o.t2a_out_w = a.t2a_out_w; o.t2a_out_b = a.t2a_out_b;
+    o.head1_w = a.head1_w; o.head1_b = a.head1_b; o.head2_w = a.head2_w; o.head2_b = a.head2_b; o.head3_w = a.head3_w;
+    o.head3_b = a.head3_b; o.ctx_proj_w = a.ctx_proj_w; o.ctx_proj_b = a.ctx_proj_b; o.has_context = a.has_context;
+  }
   P.tcw = d_tc_weights;
   P.task_feats = d_task_feats;
   P.task_mask = d_task_mask;
@@ -1166,7 +1285,7 @@ extern "C" int muav_att_pair_scores_tc(const float* d_params, const muav_attpair
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(att_pair_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(att_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM);
     if (e != cudaSuccess) return -1000 - (int)e;
     if (dev >= 0 && dev < 64) set[dev] = true;
   }
@@ -1184,7 +1303,93 @@ extern "C" int muav_att_pair_scores_tc(const float* d_params, const muav_attpair
   if (ge) group = atoi(ge);
   if (group < 0) group = 0;
   int grid = n < sms ? n : sms;
-  att_pair_tc_kernel<<<grid, NT, DYN_SMEM, (cudaStream_t)stream>>>(P, group);
+  att_tc_kernel<false><<<grid, NT, DYN_SMEM, (cudaStream_t)stream>>>(P, group);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -1000 - (int)e;
+}
+
+extern "C" int64_t muav_att_commit_tc_floats(void) { return (int64_t)muav_tc::TCW_FLOATS_COMMIT; }
+
+extern "C" int muav_att_commit_tc_pack(const float* d_params, const muav_attcommit_offsets* offsets, float* d_tc_weights,
+                                       void* stream) {
+  using namespace muav_tc;
+  if (!d_params || !offsets || !d_tc_weights) return -22;
+  const muav_attcommit_offsets& o = *offsets;
+  PackSrc S;
+  memset(&S, 0, sizeof(S));
+  auto one = [&](int c, int src, int ldo, int n0, int k0, int kreal) {
+    S.src[c][0] = S.src[c][1] = src; S.ldo[c][0] = S.ldo[c][1] = ldo; S.n0[c][0] = S.n0[c][1] = n0;
+    S.kreal[c][0] = S.kreal[c][1] = kreal; S.nsplit[c] = 1 << 20; S.k0[c] = k0;
+  };
+  S.src[0][0] = o.agent_proj_w; S.src[0][1] = o.task_proj_w; S.ldo[0][0] = S.ldo[0][1] = D;
+  S.kreal[0][0] = 13; S.kreal[0][1] = TF; S.nsplit[0] = D; S.k0[0] = 0;
+  for (int l = 0; l < 2; ++l) {
+    const int b = 1 + 9 * l;
+    for (int i = 0; i < 4; ++i) one(b + i, o.enc_in_w[l], 3 * D, 0, 16 * i, D);
+    one(b + 4, o.enc_out_w[l], D, 0, 0, D);
+    for (int i = 0; i < 2; ++i) one(b + 5 + i, o.enc_l1_w[l], 2 * D, 0, 32 * i, D);
+    for (int i = 0; i < 2; ++i) one(b + 7 + i, o.enc_l2_w[l], D, 0, 64 * i, 2 * D);
+  }
+  tc_pack_kernel<true><<<dim3(8, NCHUNK_COMMIT), 256, 0, (cudaStream_t)stream>>>(d_params, S, d_tc_weights);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -1000 - (int)e;
+}
+
+extern "C" int muav_att_commit_vectors_tc(const float* d_params, const muav_attcommit_offsets* offsets,
+                                          const float* d_tc_weights, const float* d_task_feats, const uint8_t* d_task_mask,
+                                          const float* d_agent_feats13, const uint8_t* d_agent_mask, const int32_t* d_env_idx,
+                                          const uint8_t* d_need, int n, int max_tasks, int max_agents, float* d_priorities,
+                                          float* d_commits, void* stream) {
+  using namespace muav_tc;
+  if (!d_params || !offsets || !d_tc_weights || !d_task_feats || !d_task_mask || !d_agent_feats13 || !d_agent_mask ||
+      !d_priorities || !d_commits)
+    return -22;
+  if (n < 0 || max_tasks < 1 || max_agents < 1 || max_agents + max_tasks > 48 || max_agents > 16) return -22;
+  if (n == 0) return 0;
+  Params P;
+  memset(&P, 0, sizeof(P));
+  P.w = d_params;
+  {
+    const muav_attcommit_offsets& a = *offsets;
+    TcOffsets& o = P.o;
+    o.agent_proj_w = a.agent_proj_w; o.agent_proj_b = a.agent_proj_b; o.task_proj_w = a.task_proj_w;
+    o.task_proj_b = a.task_proj_b; o.type_embed = a.type_embed;
+    for (int l = 0; l < 2; ++l) {
+      o.enc_in_w[l] = a.enc_in_w[l]; o.enc_in_b[l] = a.enc_in_b[l]; o.enc_out_w[l] = a.enc_out_w[l];
+      o.enc_out_b[l] = a.enc_out_b[l]; o.enc_l1_w[l] = a.enc_l1_w[l]; o.enc_l1_b[l] = a.enc_l1_b[l];
+      o.enc_l2_w[l] = a.enc_l2_w[l]; o.enc_l2_b[l] = a.enc_l2_b[l]; o.enc_n1_w[l] = a.enc_n1_w[l];
+      o.enc_n1_b[l] = a.enc_n1_b[l]; o.enc_n2_w[l] = a.enc_n2_w[l]; o.enc_n2_b[l] = a.enc_n2_b[l];
+    }
+    o.priority_w = a.priority_w; o.priority_b = a.priority_b; o.commit_w = a.commit_w; o.commit_b = a.commit_b;
+  }
+  P.tcw = d_tc_weights;
+  P.task_feats = d_task_feats;
+  P.task_mask = d_task_mask;
+  P.agent_feats = d_agent_feats13;
+  P.agent_mask = d_agent_mask;
+  P.env_idx = d_env_idx;
+  P.need = d_need;
+  P.pri = d_priorities;
+  P.com = d_commits;
+  P.n = n;
+  P.max_tasks = max_tasks;
+  P.max_agents = max_agents;
+  static bool set[64];
+  static int n_sm[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(att_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_SMEM);
+    if (e != cudaSuccess) return -1000 - (int)e;
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev < 0 ? 0 : dev);
+    if (dev >= 0 && dev < 64) {
+      n_sm[dev] = v < 1 ? 1 : v;
+      set[dev] = true;
+    }
+  }
+  const int sms = (dev >= 0 && dev < 64 && n_sm[dev] > 0) ? n_sm[dev] : 148;
+  att_tc_kernel<true><<<n < sms ? n : sms, NT, DYN_SMEM, (cudaStream_t)stream>>>(P, 0);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -1000 - (int)e;
 }

@@ -639,6 +639,15 @@ class FusedAttCommitScorer:
         self.params = buf.to(device)
         self.device = device
         self._C = C
+        # tensor-core path (csrc/muav_scorer_tc.cu); MUAV_SCORER_TC=0 selects the FP32-pipe kernel (A/B runs)
+        self.tcw = None
+        if os.environ.get("MUAV_SCORER_TC", "1") != "0":
+            with torch.cuda.device(device):
+                self.tcw = torch.empty(int(self.lib.dll.muav_att_commit_tc_floats()), dtype=torch.float32, device=device)
+                rc = self.lib.dll.muav_att_commit_tc_pack(self.params.data_ptr(), C.byref(self.offsets), self.tcw.data_ptr(),
+                                                          C.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+            if rc != 0:
+                raise RuntimeError(f"muav_att_commit_tc_pack failed: {rc}")
 
     @torch.no_grad()
     def vectors(self, tok: dict, pri_out: torch.Tensor, com_out: torch.Tensor, idx: Optional[torch.Tensor] = None,
@@ -655,6 +664,15 @@ class FusedAttCommitScorer:
             return
         if idx is not None and idx.dtype != torch.int32:
             idx = idx.to(torch.int32)
+        if self.tcw is not None:
+            rc = self.lib.dll.muav_att_commit_vectors_tc(
+                self.params.data_ptr(), C.byref(self.offsets), self.tcw.data_ptr(), tok["task_feats"].data_ptr(),
+                tm.data_ptr(), tok["agent_feats"].data_ptr(), am.data_ptr(), None if idx is None else idx.data_ptr(),
+                tok["need"].data_ptr() if use_need else None, n, MT, MA, pri_out.data_ptr(), com_out.data_ptr(),
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+            if rc != 0:
+                raise RuntimeError(f"muav_att_commit_vectors_tc failed: {rc}")
+            return
         rc = self.lib.dll.muav_att_commit_vectors(
             self.params.data_ptr(), C.byref(self.offsets), tok["task_feats"].data_ptr(), tm.data_ptr(),
             tok["agent_feats"].data_ptr(), am.data_ptr(), None if idx is None else idx.data_ptr(),

@@ -1267,13 +1267,15 @@ def test_commit_and_escort_collectors_match_the_oracle_and_trainers_run():
     assert len(losses) > 5 and all(np.isfinite(losses)) and moved(before, xnet)
 
 
-def test_fused_commit_scorer_kernel_and_fused_commit_tokens():
-    """csrc/muav_scorer.cu att_commit_kernel vs the PyTorch AttCommitNet forward on real commit tokens (fp32, 2e-5), the
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_fused_commit_scorer_kernel_and_fused_commit_tokens(tc, monkeypatch):
+    """csrc/muav_scorer_tc.cu (tcgen05, default) / csrc/muav_scorer.cu att_commit_kernel (MUAV_SCORER_TC=0) vs the PyTorch AttCommitNet forward on real commit tokens (fp32, 2e-5), the
     commit tokens emitted by the step kernel (muav_token_out.agent_feat_dim = 13) vs the standalone muav_tokens_commit, and
     the fused pipeline (tokens -> kernel -> AllocSpec.att_commit) against the PyTorch-scored pipeline."""
     from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
     from multi_uav_ta_gym_env_b200.scorers import AttCommitNet, FusedAttCommitScorer, commit_vectors
 
+    monkeypatch.setenv("MUAV_SCORER_TC", tc)
     cfg = wps_config("WPS_commit")
     E = 192
     env = make_env(cfg, list(range(E)))
@@ -1281,6 +1283,7 @@ def test_fused_commit_scorer_kernel_and_fused_commit_tokens():
     torch.manual_seed(2)
     net = AttCommitNet().cuda().eval()
     fused = FusedAttCommitScorer(net, torch.device("cuda"))
+    assert (fused.tcw is not None) == (tc == "1")
     tok = env.tokens_commit(32, 16)
     want_p, want_c = commit_vectors(net, tok)
     got_p = torch.full_like(want_p, 7.0)
