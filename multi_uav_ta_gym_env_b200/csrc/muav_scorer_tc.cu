@@ -395,8 +395,11 @@ __device__ void select_envs(const PickArgs P, const EnvScan S, int r0, int m, in
   }
 }
 
-// development dump of this thread's 32 columns of x (A0 planes)
+// development dump of this thread's 32 columns of x (A0 planes); compiled in only with -DMUAV_TC_DEBUG (tools/tc_scorer_check.py)
 __device__ __forceinline__ void dump_a0(const Params& P, int stage, uint32_t tl, int row, int half) {
+#if !defined(MUAV_TC_DEBUG)
+  return;
+#endif
   if (!P.dbg || blockIdx.x != 0) return;
   for (int g = 0; g < 2; ++g) {
     const int c = half * 32 + g * 16;
@@ -785,11 +788,16 @@ __global__ void __launch_bounds__(NT, 1) att_tc_kernel(const __grid_constant__ P
       (void)R;
 
       // development: stage timestamps of CTA 0 / thread 0 behind the activation dumps
+#if defined(MUAV_TC_DEBUG)
       long long* ts = (P.dbg && blockIdx.x == 0 && tid == 0) ? (long long*)(P.dbg + 4 * ROWS * D) : nullptr;
 #define TS_MARK()                               \
   do {                                          \
     if (ts && n_ts < 250) ts[1 + n_ts++] = clock64(); \
   } while (0)
+#else
+      long long* const ts = nullptr;
+#define TS_MARK() ((void)0)
+#endif
       TS_MARK();
       // ---- raw features as the A operand of the projections (K padded to 16)
       if (half == 0) {
@@ -1198,11 +1206,15 @@ __global__ void tc_pack_kernel(const float* __restrict__ w, const __grid_constan
   }
 }
 
-static float* g_dbg = nullptr;
+#if defined(MUAV_TC_DEBUG)
+static float* g_dbg = nullptr;   // development builds only: where the next launch dumps its first pass
+#endif
 
 }  // namespace muav_tc
 
+#if defined(MUAV_TC_DEBUG)
 extern "C" void muav_tc_debug_buffer_(float* d_dbg) { muav_tc::g_dbg = d_dbg; }
+#endif
 
 extern "C" int64_t muav_att_pair_tc_floats(void) { return (int64_t)muav_tc::TCW_FLOATS; }
 
@@ -1280,7 +1292,9 @@ extern "C" int muav_att_pair_scores_tc(const float* d_params, const muav_attpair
   P.max_tasks = max_tasks;
   P.max_agents = max_agents;
   P.clamp = score_clamp;
+#if defined(MUAV_TC_DEBUG)
   P.dbg = g_dbg;
+#endif
   static bool set[64];
   int dev = 0;
   cudaGetDevice(&dev);

@@ -79,14 +79,34 @@ def main():
     torch.cuda.synchronize()
     print("fp32 kernel vs torch: max err %.3e" % (got32 - want).abs().max().item(), flush=True)
 
+    # the activation dumps / stage timestamps exist only in a -DMUAV_TC_DEBUG build of the scorer: compile one next to the
+    # product library and point the scorer object at it
+    import subprocess
+    dbg_so = os.path.join(ROOT, "build", "libmuav_tc_debug.so")
+    os.makedirs(os.path.dirname(dbg_so), exist_ok=True)
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+                    "-DMUAV_TC_DEBUG", "-shared", "-o", dbg_so,
+                    os.path.join(ROOT, "multi_uav_ta_gym_env_b200", "csrc", "muav_scorer_tc.cu")], check=True)
+    dbg_dll = C.CDLL(dbg_so)
+    dbg_dll.muav_att_pair_scores_tc.restype = C.c_int
+    dbg_dll.muav_att_pair_scores_tc.argtypes = tc.lib.dll.muav_att_pair_scores_tc.argtypes
+
+    class _Lib:
+        dll = dbg_dll
+    prod_lib, tc.lib = tc.lib, _Lib
     dbg_all = torch.zeros(4 * 128 * 64 + 1024, device=dev)
     dbg = dbg_all[:4 * 128 * 64].view(4, 128, 64)
     dbg.fill_(float("nan"))
-    tc.lib.dll.muav_tc_debug_buffer_(C.c_void_p(dbg_all.data_ptr()))
+    dbg_dll.muav_tc_debug_buffer_(C.c_void_p(dbg_all.data_ptr()))
     got = torch.full_like(want, 7.0)
     tc.score(tok, got)
     torch.cuda.synchronize()
-    tc.lib.dll.muav_tc_debug_buffer_(None)
+    dbg_dll.muav_tc_debug_buffer_(None)
+    tc.lib = prod_lib   # everything below runs the product library
+    got_prod = torch.full_like(want, 7.0)
+    tc.score(tok, got_prod)
+    torch.cuda.synchronize()
+    assert torch.equal(got_prod, got), "debug and product builds disagree"
     ts = dbg_all[4 * 128 * 64:].view(torch.int64).cpu().tolist()
     n_ts = ts[0]
     marks = ts[1:1 + n_ts]
