@@ -39,14 +39,59 @@ DEVICE_ALGORITHMS: Dict[str, Callable[[], AllocSpec]] = {
     "Global-Coalition": lambda: AllocSpec(1, ESCORT_INTERVAL, 0x1F, False, False),   # escort_eval.py:124-136
     "Urgency-Coalition": lambda: AllocSpec.urgency_coalition(ESCORT_INTERVAL),       # escort_eval.py:175-179
 }
+# learned hybrids with a fused forward kernel and in-step token emission: algorithm -> (tokens, planner spec)
+LEARNED_ALGORITHMS = {
+    "Att-Pair": ("pair", lambda: AllocSpec.pair_hybrid(HYBRID_INTERVAL)),               # wps_eval.py:239-255
+    "Att-ContextPair": ("context", lambda: AllocSpec.pair_hybrid(HYBRID_INTERVAL)),     # wps_eval.py:256-272
+    "Att-Commit": ("commit", lambda: AllocSpec.att_commit(HYBRID_INTERVAL)),            # wps_eval.py:222-238
+    "Att-Coalition": ("escort", lambda: AllocSpec.att_escort(ESCORT_INTERVAL)),         # escort_eval.py:180-196
+}
 SCORE_KEYS = ("F_Reward", "S_WPS", "on_time_rate", "n_missed_windows", "n_on_time", "n_windowed_tasks",
               "reserve_idle_fraction", "makespan", "total_distance", "n_task_switches")
 
 
+def _run_learned(env, algorithm: str, net, n_steps: int):
+    """A learned hybrid end to end on the device: the step kernel emits the tokens of the environments that replan next,
+    the fused forward kernel scores exactly those (need flags, no host synchronisation), the planner half runs inside the
+    next step's kernel."""
+    from . import scorers
+
+    kind, make_spec = LEARNED_ALGORITHMS[algorithm]
+    spec = make_spec()
+    E, dev = env.n_envs, env.device
+    if kind in ("pair", "context"):
+        tok = env.enable_fused_tokens(32, 16, HYBRID_INTERVAL, 0b111, context=kind == "context")
+        fused = scorers.FusedAttPairScorer(net, dev)
+        scores = torch.zeros(E, 16, 32, dtype=torch.float32, device=dev)
+        env.refresh_fused_tokens()
+        for _ in range(n_steps):
+            fused.score(tok, scores, use_need=True)
+            env.step_allocated(spec, 1, edge_scores=scores)
+    elif kind == "commit":
+        tok = env.enable_fused_tokens(32, 16, HYBRID_INTERVAL, 0b111, commit=True)
+        fused = scorers.FusedAttCommitScorer(net, dev)
+        pri = torch.zeros(E, 32, dtype=torch.float32, device=dev)
+        com = torch.zeros(E, 16, dtype=torch.float32, device=dev)
+        env.refresh_fused_tokens()
+        for _ in range(n_steps):
+            fused.vectors(tok, pri, com, use_need=True)
+            env.step_allocated(spec, 1, plan_pri=pri, plan_commit=com)
+    else:
+        tok = env.enable_fused_tokens(48, 16, ESCORT_INTERVAL, 0x1F, escort=True)
+        fused = scorers.FusedAttCoalitionScorer(net, dev)
+        scores = torch.zeros(E, 16, 48, dtype=torch.float32, device=dev)
+        env.refresh_fused_tokens()
+        for _ in range(n_steps):
+            fused.score(tok, scores, use_need=True)
+            env.step_allocated(spec, 1, edge_scores=scores, task_order=tok["task_order"])
+
+
 def run_episodes(case: str, algorithm: str, episodes: int, device="cuda:0", score_fn: Optional[Callable] = None,
-                 tokens: str = "pair") -> List[dict]:
+                 tokens: str = "pair", net=None) -> List[dict]:
     """Scores of seeds 0..episodes-1, one dict per seed with run_wps_episode's keys (decision_ms_mean is the device time
-    of the whole batch per step divided by the batch size)."""
+    of the whole batch per step divided by the batch size).  Learned hybrids (LEARNED_ALGORITHMS): pass the network as
+    `net` (AttPairNet / AttContextPairNet / AttCommitNet / AttCoalitionNet with the default shapes) to run them on the
+    fused forward kernels, or any `score_fn(tokens) -> scores` for the pair hybrids in PyTorch."""
     cfg = wps_config(case)
     env = BatchedMultiUAVEnv(cfg, episodes, device=device).reset(range(episodes))
     n_steps = int(cfg.max_time_steps)
@@ -55,6 +100,8 @@ def run_episodes(case: str, algorithm: str, episodes: int, device="cuda:0", scor
     t0.record()
     if algorithm in DEVICE_ALGORITHMS:
         env.step_allocated(DEVICE_ALGORITHMS[algorithm](), n_steps)
+    elif algorithm in LEARNED_ALGORITHMS and net is not None:
+        _run_learned(env, algorithm, net, n_steps)
     else:
         if score_fn is None:
             raise ValueError(f"{algorithm}: pass score_fn(tokens) -> scores (a learned pair scorer)")

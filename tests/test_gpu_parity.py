@@ -1360,3 +1360,30 @@ def test_fused_coalition_scorer_kernel_and_fused_escort_tokens():
         seen += int(need.sum().item())
     assert seen > E
     assert int(env.error_flags().abs().max().item()) == 0
+
+
+def test_evaluation_driver_runs_the_learned_hybrids_on_the_fused_kernels():
+    """evaluate.run_episodes(..., net=...) (in-step tokens -> fused forward -> planner in the step kernel) against the same
+    algorithm scored by the PyTorch module through score_fn / the token kernels: the episodes' scores agree except where a
+    float32 near-tie flips an assignment (bounded: at most 10 % of the episodes), and every learned hybrid runs end to end."""
+    from multi_uav_ta_gym_env_b200 import evaluate
+    from multi_uav_ta_gym_env_b200.scorers import (AttCoalitionNet, AttCommitNet, AttContextPairNet, AttPairNet,
+                                                   context_pair_scores, pair_scores)
+
+    n = 48
+    torch.manual_seed(5)
+    net = AttPairNet().cuda().eval()
+    fused = evaluate.run_episodes("WPS_hard", "Att-Pair", n, net=net)
+    eager = evaluate.run_episodes("WPS_hard", "Att-Pair", n, score_fn=lambda tok: pair_scores(net, tok))
+    same = sum(1 for a, b in zip(fused, eager) if a["S_WPS"] == b["S_WPS"] and a["total_distance"] == b["total_distance"])
+    assert same >= int(0.9 * n), same
+    cnet = AttContextPairNet().cuda().eval()
+    fused = evaluate.run_episodes("WPS_attn", "Att-ContextPair", n, net=cnet)
+    eager = evaluate.run_episodes("WPS_attn", "Att-ContextPair", n, score_fn=lambda tok: context_pair_scores(cnet, tok),
+                                  tokens="context")
+    same = sum(1 for a, b in zip(fused, eager) if a["S_WPS"] == b["S_WPS"] and a["total_distance"] == b["total_distance"])
+    assert same >= int(0.9 * n), same
+    rows = evaluate.run_episodes("WPS_commit", "Att-Commit", 24, net=AttCommitNet().cuda().eval())
+    assert len(rows) == 24 and all(np.isfinite(r["S_WPS"]) for r in rows)
+    rows = evaluate.run_episodes("WPS_escort", "Att-Coalition", 12, net=AttCoalitionNet().cuda().eval())
+    assert len(rows) == 12 and all(np.isfinite(r["S_ESC"]) for r in rows)
