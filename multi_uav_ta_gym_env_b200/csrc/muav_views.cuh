@@ -201,10 +201,13 @@ MUAV_HD inline void tokens_pair_env(const View& V, const muav_config& C, int max
       }
       const int at_l = a >= 0 ? (int)V.a_type()[a] : 0;
       const int n_edges = ev ? max_agents * max_tasks : 0;
+      int er = lane / max_tasks, ej = lane - er * max_tasks;   // (row, column) of this lane's edge, advanced without dividing
       for (int base = 0; base < n_edges; base += 32) {   // warp-uniform trip count: the shuffles need every lane
         const int idx = base + lane;
         const bool in = idx < n_edges;
-        const int r = in ? idx / max_tasks : 0, j = idx - r * max_tasks;
+        const int r = in ? er : 0, j = in ? ej : 0;
+        ej += 32;
+        while (ej >= max_tasks) { ej -= max_tasks; ++er; }
         const int ar = __shfl_sync(0xffffffffu, a, r);
         const int atr = __shfl_sync(0xffffffffu, at_l, r);
         float v = 0.0f;
