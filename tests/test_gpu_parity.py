@@ -1387,3 +1387,40 @@ def test_evaluation_driver_runs_the_learned_hybrids_on_the_fused_kernels():
     assert len(rows) == 24 and all(np.isfinite(r["S_WPS"]) for r in rows)
     rows = evaluate.run_episodes("WPS_escort", "Att-Coalition", 12, net=AttCoalitionNet().cuda().eval())
     assert len(rows) == 12 and all(np.isfinite(r["S_ESC"]) for r in rows)
+
+
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_fused_scorer_kernels_on_ragged_shapes(tc, monkeypatch):
+    """Both Att-Pair kernels on shapes away from the 16 x 32 default: narrow / wide token tensors, one environment, a launch
+    where nothing needs a score, environments without agents or without tasks (their scores stay 0)."""
+    from multi_uav_ta_gym_env_b200 import AllocSpec, wps_config
+    from multi_uav_ta_gym_env_b200.scorers import AttPairNet, FusedAttPairScorer, pair_scores
+
+    monkeypatch.setenv("MUAV_SCORER_TC", tc)
+    cfg = wps_config("WPS_hard")
+    for E, ma, mt, steps in ((1, 16, 32, 10), (3, 8, 40, 30), (37, 4, 12, 50), (150, 16, 24, 149)):
+        env = make_env(cfg, list(range(E)))
+        env.step_allocated(AllocSpec.local_hungarian(20), n_steps=steps)
+        tok = env.tokens_pair(mt, ma)
+        torch.manual_seed(4)
+        net = AttPairNet(max_tasks=mt, max_agents=ma).cuda().eval()
+        want = pair_scores(net, tok)
+        fused = FusedAttPairScorer(net, torch.device("cuda"))
+        ftok = {"task_feats": tok["task_feats"], "task_mask_u8": tok["task_mask"].to(torch.uint8),
+                "agent_feats": tok["agent_feats"], "agent_mask_u8": tok["agent_mask"].to(torch.uint8),
+                "edge_valid": tok["edge_valid"], "need": torch.zeros(E, dtype=torch.uint8, device="cuda")}
+        got = torch.full_like(want, 7.0)
+        fused.score(ftok, got)
+        assert (got - want).abs().max().item() < 2e-5, (E, ma, mt, (got - want).abs().max().item())
+        # nothing to do: the launch leaves every row alone
+        got2 = torch.full_like(want, 7.0)
+        fused.score(ftok, got2, use_need=True)
+        assert bool((got2 == 7.0).all())
+        # an environment without live agents and one without valid tasks
+        if E >= 3:
+            ftok["agent_mask_u8"][0] = 1
+            ftok["task_mask_u8"][1] = 1
+            got3 = torch.full_like(want, 7.0)
+            fused.score(ftok, got3)
+            assert bool((got3[0] == 0).all()) and bool((got3[1] == 0).all())
+            assert (got3[2:] - want[2:]).abs().max().item() < 2e-5
