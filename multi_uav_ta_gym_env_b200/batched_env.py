@@ -98,6 +98,17 @@ class AllocSpec:
         return AllocSpec(2, interval, ALL_EVENTS, True, False, planner=4)
 
 
+class _NoCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_CTX = _NoCtx()
+
+
 class BatchedMultiUAVEnv:
     def __init__(self, config, n_envs: int, device="cuda:0", task_cap=None, queue_cap=16, id_cap=None):
         self.lib = _lib.cuda_lib()  # raises if the CUDA library is not built: no CPU fallback
@@ -294,6 +305,12 @@ class BatchedMultiUAVEnv:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _dev_ctx(self):
+        """Make the environment's device current for a native call; nothing to do (and nothing to pay per step) when it
+        already is."""
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        return _NO_CTX if torch.cuda.current_device() == idx else torch.cuda.device(self.device)
+
     def step_batched(self, actions: torch.Tensor, n_steps: int = 1):
         """actions: int32 [E, A, 2] ordered (agent_id, index into last_tasks_info) pairs, agent_id = -1
         terminates an env's list; or int32 [E, A] with one index per agent id (-1 = no action), applied
@@ -308,7 +325,7 @@ class BatchedMultiUAVEnv:
             actions = torch.stack([a_sorted, i_sorted], dim=2)
         actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
         self._order_args()
-        with torch.cuda.device(self.device):
+        with self._dev_ctx():
             rc = self.lib.dll.muav_step(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(),
                                         actions.data_ptr(), None, C.byref(self._out), self._tok_ref(), self.n_envs, n_steps,
                                         self._stream())
@@ -329,7 +346,7 @@ class BatchedMultiUAVEnv:
             O.order_hint_mode = hint.mode
             O.replan_interval, O.event_mask, O.planner = hint.replan_interval, hint.event_mask, hint.planner
         self._order_args()
-        with torch.cuda.device(self.device):
+        with self._dev_ctx():
             rc = self.lib.dll.muav_ctx_step_host(self._host_ctx(), self.records.data_ptr(), self.tapes.data_ptr(),
                                                  ptr(h_actions), None if O is None else C.byref(O), self._tok_ref(),
                                                  ptr(h_reward), ptr(h_terminated), ptr(h_truncated), n_steps, self._stream(),
@@ -349,13 +366,28 @@ class BatchedMultiUAVEnv:
         cur = self._order_cur
         self._out.d_env_order = self._order[cur].data_ptr() if (self.group_replanners and cur >= 0) else None
         self._out.d_env_order_next = None
-        with torch.cuda.device(self.device):
+        with self._dev_ctx():
             rc = self.lib.dll.muav_ctx_allocate_host(self._host_ctx(), self.records.data_ptr(), C.byref(O),
                                                      C.byref(self._out), ptr(h_actions_out), self._stream())
         _lib.check(rc, "muav_ctx_allocate_host")
         self.launches += 1
 
     def _alloc_opts(self, spec, edge_scores, priorities, reserved, task_order=None, plan_pri=None, plan_commit=None):
+        # the same spec over the same tensors every step (a rollout loop): reuse the filled struct
+        key = (id(spec), spec.mode, spec.replan_interval, spec.event_mask, spec.planner, spec.commit_fraction,
+               spec.commit_threshold, spec.use_visibility, spec.pair_tokens, spec.max_coord) + tuple(
+            (x.data_ptr(), x.dtype, tuple(x.shape), x.device.index, x.is_contiguous()) if isinstance(x, torch.Tensor) else None
+            for x in (edge_scores, priorities, reserved, task_order, plan_pri, plan_commit))
+        cached = getattr(self, "_opts_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1], cached[2]
+        O, keep = self._alloc_opts_build(spec, edge_scores, priorities, reserved, task_order, plan_pri, plan_commit)
+        # the cache holds the argument tensors themselves too, so that the data pointers in the key cannot be reused
+        self._opts_cache = (key, O, keep + [x for x in (edge_scores, priorities, reserved, task_order, plan_pri, plan_commit)
+                                            if isinstance(x, torch.Tensor)])
+        return O, keep
+
+    def _alloc_opts_build(self, spec, edge_scores, priorities, reserved, task_order=None, plan_pri=None, plan_commit=None):
         O = _lib.MuavAllocOpts()
         O.mode = spec.mode
         O.replan_interval = spec.replan_interval
@@ -407,7 +439,7 @@ class BatchedMultiUAVEnv:
         """n_steps fused (allocate -> step) iterations per environment, state resident in shared memory."""
         O, keep = self._alloc_opts(spec, edge_scores, priorities, reserved, task_order, plan_pri, plan_commit)
         self._order_args()
-        with torch.cuda.device(self.device):
+        with self._dev_ctx():
             rc = self.lib.dll.muav_rollout(C.byref(self.cfg), self.records.data_ptr(), self.tapes.data_ptr(), C.byref(O),
                                            C.byref(self._out), self._tok_ref(), self.n_envs, n_steps, self._stream())
         self._order_commit(rc, n_steps)
@@ -427,7 +459,7 @@ class BatchedMultiUAVEnv:
         cur = self._order_cur
         self._out.d_env_order = self._order[cur].data_ptr() if (self.group_replanners and cur >= 0) else None
         self._out.d_env_order_next = None
-        with torch.cuda.device(self.device):
+        with self._dev_ctx():
             rc = self.lib.dll.muav_allocate(C.byref(self.cfg), self.records.data_ptr(), C.byref(O), C.byref(self._out),
                                             actions_out.data_ptr(), self.n_envs, self._stream())
         _lib.check(rc, "muav_allocate")
