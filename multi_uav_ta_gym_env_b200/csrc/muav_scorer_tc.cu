@@ -140,7 +140,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// bounded wait: a protocol error traps (the launch fails) instead of hanging the device
+// bounded wait (~10 s of SM clocks): a protocol error traps (the launch fails) instead of hanging the device
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
   uint32_t done = 0;
   const uint32_t addr = smem_u32(bar);
@@ -155,7 +155,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
         : "=r"(done)
         : "r"(addr), "r"(phase)
         : "memory");
-    if (!done && clock64() - t0 > 4000000000LL) __trap();
+    if (!done && clock64() - t0 > 20000000000LL) __trap();
   } while (!done);
 }
 // the same with a back-off between polls (waiters that must not steal issue slots from the MMA thread)
@@ -175,7 +175,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t phase)
         : "memory");
     if (done) break;
     __nanosleep(20);
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (clock64() - t0 > 20000000000LL) __trap();
   }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
