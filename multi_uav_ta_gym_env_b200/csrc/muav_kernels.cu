@@ -562,6 +562,8 @@ MUAV_DECL_INST(lean)
 MUAV_DECL_INST(lean_escort)
 MUAV_DECL_SHAPED(hard)
 MUAV_DECL_SHAPED(hard32)
+MUAV_DECL_SHAPED(commit)
+MUAV_DECL_SHAPED(escort)
 
 struct StepInst {
   int (*launch)(const void*, int, int, size_t, void*);
@@ -573,6 +575,8 @@ struct StepInst {
 static const StepInst kStepInst[] = {
     {muav_step_hard_launch, muav_step_hard_occ, muav_step_hard_shape, 0, 1},
     {muav_step_hard32_launch, muav_step_hard32_occ, muav_step_hard32_shape, 0, 1},
+    {muav_step_commit_launch, muav_step_commit_occ, muav_step_commit_shape, 0, 0},
+    {muav_step_escort_launch, muav_step_escort_occ, muav_step_escort_shape, 1, 0},
     {muav_step_lean_launch, muav_step_lean_occ, nullptr, 0, 0},
     {muav_step_lean_escort_launch, muav_step_lean_escort_occ, nullptr, 1, 0},
 };
