@@ -29,7 +29,11 @@
 #define MUAV_F_ESCORT(x) false
 #endif
 #define MUAV_F_NOBS(x) 0
+#if defined(MUAV_LEAN_PLANNER)   // lean instantiations that keep the planner front ends and the market allocators
+#define MUAV_F_PLANNER(x) (x)
+#else
 #define MUAV_F_PLANNER(x) 0
+#endif
 #else
 #define MUAV_F_ESCORT(x) ((x) != 0)
 #define MUAV_F_NOBS(x) (x)

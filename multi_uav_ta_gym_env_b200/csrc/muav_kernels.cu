@@ -564,6 +564,12 @@ MUAV_DECL_SHAPED(hard)
 MUAV_DECL_SHAPED(hard32)
 MUAV_DECL_SHAPED(commit)
 MUAV_DECL_SHAPED(escort)
+MUAV_DECL_SHAPED(commit_planner)
+MUAV_DECL_SHAPED(escort_planner)
+MUAV_DECL_SHAPED(hard32_planner)
+MUAV_DECL_SHAPED(burst2)
+MUAV_DECL_SHAPED(burst4)
+MUAV_DECL_SHAPED(burst8)
 
 struct StepInst {
   int (*launch)(const void*, int, int, size_t, void*);
@@ -571,14 +577,21 @@ struct StepInst {
   void (*shape)(int*);  // null: any shape
   int escort;           // value of cfg.escort_enabled this instantiation was compiled for
   int stage_cold;       // MUAV_STAGE_COLD_FIXED of the instantiation: 1 whole record staged, 0 hot part only
+  int planners;         // 1: compiled with the planner front ends / market allocators (any muav_alloc_opts.planner)
 };
 static const StepInst kStepInst[] = {
-    {muav_step_hard_launch, muav_step_hard_occ, muav_step_hard_shape, 0, 1},
-    {muav_step_hard32_launch, muav_step_hard32_occ, muav_step_hard32_shape, 0, 1},
-    {muav_step_commit_launch, muav_step_commit_occ, muav_step_commit_shape, 0, 0},
-    {muav_step_escort_launch, muav_step_escort_occ, muav_step_escort_shape, 1, 0},
-    {muav_step_lean_launch, muav_step_lean_occ, nullptr, 0, 0},
-    {muav_step_lean_escort_launch, muav_step_lean_escort_occ, nullptr, 1, 0},
+    {muav_step_hard_launch, muav_step_hard_occ, muav_step_hard_shape, 0, 1, 0},
+    {muav_step_hard32_launch, muav_step_hard32_occ, muav_step_hard32_shape, 0, 1, 0},
+    {muav_step_commit_launch, muav_step_commit_occ, muav_step_commit_shape, 0, 0, 0},
+    {muav_step_escort_launch, muav_step_escort_occ, muav_step_escort_shape, 1, 0, 0},
+    {muav_step_burst2_launch, muav_step_burst2_occ, muav_step_burst2_shape, 0, 0, 0},
+    {muav_step_burst4_launch, muav_step_burst4_occ, muav_step_burst4_shape, 0, 0, 0},
+    {muav_step_burst8_launch, muav_step_burst8_occ, muav_step_burst8_shape, 0, 0, 0},
+    {muav_step_lean_launch, muav_step_lean_occ, nullptr, 0, 0, 0},
+    {muav_step_lean_escort_launch, muav_step_lean_escort_occ, nullptr, 1, 0, 0},
+    {muav_step_hard32_planner_launch, muav_step_hard32_planner_occ, muav_step_hard32_planner_shape, 0, 1, 1},
+    {muav_step_commit_planner_launch, muav_step_commit_planner_occ, muav_step_commit_planner_shape, 0, 0, 1},
+    {muav_step_escort_planner_launch, muav_step_escort_planner_occ, muav_step_escort_planner_shape, 1, 0, 1},
 };
 
 // general kernel of this translation unit: same two services
@@ -606,13 +619,14 @@ static int general_occ(int threads, size_t smem) {
 
 // the most specialised instantiation that covers this launch (null: the general kernel of this translation unit)
 static const StepInst* pick_inst(const StepParams& P) {
-  const bool lean = P.L.D.NOBS == 0 && P.opts.planner == 0 && !P.alloc_only && !getenv("MUAV_NO_LEAN");
+  const bool lean = P.L.D.NOBS == 0 && !P.alloc_only && !getenv("MUAV_NO_LEAN");
   if (!lean) return nullptr;
   const bool no_fixed = getenv("MUAV_NO_FIXED_SHAPE") != nullptr;
   const Dims& D = P.L.D;
   const int have[7] = {D.A, D.TC, D.IC, D.HC, D.QC, D.EVC, D.NOBS};
   for (const StepInst& I : kStepInst) {
     if (I.escort != (P.cfg.escort_enabled ? 1 : 0)) continue;
+    if (P.opts.planner != 0 && !I.planners) continue;
     if (I.shape) {
       if (no_fixed) continue;
       int want[7];
