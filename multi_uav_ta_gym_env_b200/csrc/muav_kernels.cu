@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(MUAV_LB_THREADS, MUAV_LB_BLOCKS) muav_step_ker
   int16_t* act_tid = act_agent + L.D.A;
 
   // ---- allocator-only launch: environments whose replan rule does not fire leave after a look at their header
-#if defined(MUAV_LEAN)
-  if (false) {   // the lean kernel is never launched allocator-only (launch_step): no second copy of the allocator
+#if defined(MUAV_LEAN) && !defined(MUAV_LEAN_PLANNER)
+  if (false) {   // the plain lean kernels are never launched allocator-only (launch_step): no second copy of the allocator
 #else
   if (P.alloc_only && has_env) {
 #endif
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(MUAV_LB_THREADS, MUAV_LB_BLOCKS) muav_step_ker
     }
   }
 
-#if defined(MUAV_LEAN)
+#if defined(MUAV_LEAN) && !defined(MUAV_LEAN_PLANNER)
   if (false) {
 #else
   if (P.alloc_only && has_env) {
@@ -577,7 +577,8 @@ struct StepInst {
   void (*shape)(int*);  // null: any shape
   int escort;           // value of cfg.escort_enabled this instantiation was compiled for
   int stage_cold;       // MUAV_STAGE_COLD_FIXED of the instantiation: 1 whole record staged, 0 hot part only
-  int planners;         // 1: compiled with the planner front ends / market allocators (any muav_alloc_opts.planner)
+  int planners;         // 1: compiled with the planner front ends / market allocators (any muav_alloc_opts.planner) and
+                        //    the allocator-only launch (muav_allocate, the split allocator -> step path)
 };
 static const StepInst kStepInst[] = {
     {muav_step_hard_launch, muav_step_hard_occ, muav_step_hard_shape, 0, 1, 0},
@@ -619,14 +620,14 @@ static int general_occ(int threads, size_t smem) {
 
 // the most specialised instantiation that covers this launch (null: the general kernel of this translation unit)
 static const StepInst* pick_inst(const StepParams& P) {
-  const bool lean = P.L.D.NOBS == 0 && !P.alloc_only && !getenv("MUAV_NO_LEAN");
+  const bool lean = P.L.D.NOBS == 0 && !getenv("MUAV_NO_LEAN");
   if (!lean) return nullptr;
   const bool no_fixed = getenv("MUAV_NO_FIXED_SHAPE") != nullptr;
   const Dims& D = P.L.D;
   const int have[7] = {D.A, D.TC, D.IC, D.HC, D.QC, D.EVC, D.NOBS};
   for (const StepInst& I : kStepInst) {
     if (I.escort != (P.cfg.escort_enabled ? 1 : 0)) continue;
-    if (P.opts.planner != 0 && !I.planners) continue;
+    if ((P.opts.planner != 0 || P.alloc_only) && !I.planners) continue;   // front ends / the allocator-only service
     if (I.shape) {
       if (no_fixed) continue;
       int want[7];
