@@ -1416,6 +1416,19 @@ def test_fused_scorer_kernels_on_ragged_shapes(tc, monkeypatch):
         got2 = torch.full_like(want, 7.0)
         fused.score(ftok, got2, use_need=True)
         assert bool((got2 == 7.0).all())
+        # an index list together with the need flags: only listed environments whose flag is set are scored
+        if E >= 37:
+            idx = torch.arange(1, E, 2, device="cuda", dtype=torch.int32)
+            ftok["need"].zero_()
+            ftok["need"][torch.arange(0, E, 3, device="cuda")] = 1
+            got4 = torch.full_like(want, 7.0)
+            fused.score(ftok, got4, idx, use_need=True)
+            sel = torch.zeros(E, dtype=torch.bool, device="cuda")
+            sel[idx.long()] = True
+            sel &= ftok["need"].bool()
+            assert int(sel.sum().item()) > 3
+            assert (got4[sel] - want[sel]).abs().max().item() < 2e-5 and bool((got4[~sel] == 7.0).all())
+            ftok["need"].zero_()
         # an environment without live agents and one without valid tasks
         if E >= 3:
             ftok["agent_mask_u8"][0] = 1
