@@ -730,8 +730,11 @@ static int launch_step(StepParams& P, void* stream) {
   while (W > 1 && slot * W > 200 * 1024) --W;
   if (slot > 226 * 1024) return -12;
   P.cta_warps = W;
-  // phase-alignment barriers (bit 0: before the step, 1..3: after its three sequential parts, 4: end of step)
-  P.sync_mask = 31;
+  // phase-alignment barriers (bit 0: before the step, 1..3: after its three sequential parts, 4: end of step).
+  // Re-measured on the final kernels (profiles/r02_step_kernel.md): the barriers before the step and after the second and
+  // third part pay for themselves (shared instruction fetch), the ones after the first part and at the end of the step
+  // only add waiting: 13 beats 31 by 1.6-5.8 % on every BASELINE shape
+  P.sync_mask = 13;
   const char* sm = getenv("MUAV_SYNC_MASK");
   if (sm) P.sync_mask = atoi(sm);
   const size_t smem = slot * W;
