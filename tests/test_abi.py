@@ -62,3 +62,44 @@ def test_product_has_no_cpu_fallback():
 
     with pytest.raises(RuntimeError):
         BatchedMultiUAVEnv(config.wps_config("WPS_hard"), 2)
+
+
+def _header_structs():
+    """typedef struct NAME { ... } NAME; blocks of include/muav.h -> {name: [(field, array length or 0, is pointer)]}"""
+    hdr = open(os.path.join(ROOT, "include", "muav.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    out = {}
+    for m in re.finditer(r"typedef struct (\w+) \{(.*?)\} \1;", hdr, flags=re.S):
+        fields = []
+        for decl in m.group(2).split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            head, *rest = decl.split(",")
+            head = re.sub(r"\[[^\]]*\]", "[]", head)   # array extents may be expressions
+            toks = head.replace("*", " * ").split()
+            ptr = "*" in toks
+            names = [toks[-1]] + [re.sub(r"\[[^\]]*\]", "[]", r).replace("*", " ").strip() for r in rest]
+            for n in names:
+                fields.append((n.split("[")[0], 1 if "[" in n else 0, ptr))
+        out[m.group(1)] = fields
+    return out
+
+
+def test_ctypes_mirrors_follow_the_header_structs():
+    """Field names and order of every ctypes mirror in _lib.py equal the struct in include/muav.h (pointers are c_void_p,
+    arrays are ctypes arrays): a field added on one side only would silently shift everything behind it."""
+    structs = _header_structs()
+    mirrors = {"muav_token_out": _lib.MuavTokenOut, "muav_attpair_offsets": _lib.MuavAttPairOffsets,
+               "muav_attcommit_offsets": _lib.MuavAttCommitOffsets, "muav_attcoal_offsets": _lib.MuavAttCoalOffsets,
+               "muav_alloc_opts": _lib.MuavAllocOpts, "muav_step_out": _lib.MuavStepOut, "muav_config": _lib.MuavConfig}
+    for name, cls in mirrors.items():
+        assert name in structs, name
+        want = structs[name]
+        got = list(cls._fields_)
+        assert [f[0] for f in got] == [w[0] for w in want], (name, [f[0] for f in got], [w[0] for w in want])
+        for (fname, ftype), (_, alen, ptr) in zip(got, want):
+            if ptr:
+                assert ftype is C.c_void_p, (name, fname)
+            if alen:
+                assert issubclass(ftype, C.Array), (name, fname)
