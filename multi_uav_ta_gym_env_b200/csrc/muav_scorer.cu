@@ -2,7 +2,10 @@
 // scores = tanh(logits) * clamp * edge_valid, :266-278) as ONE kernel: each CTA packs up to four environments
 // (their tokens side by side, 64 per pass, attention block-diagonal) so that the 4 x 4 register tiles of the linear
 // layers are full and the 330 KB of weights are streamed from L2 once per pass instead of once per environment;
-// every activation stays in shared memory.
+// every activation stays in shared memory.  This is the FP32-pipe version: the tcgen05 kernels of muav_scorer_tc.cu
+// are the default for AttPairNet / AttContextPairNet / AttCommitNet; this file still serves AttCoalitionNet (the same
+// kernel template at d_model 128, two encoder layers, feed-forward 512 in two slices: muav_att_coalition_scores) and
+// the MUAV_SCORER_TC=0 baseline.
 //
 // Weight matrices are packed TRANSPOSED ([in][out]) by the host (scorers.FusedAttPairScorer).
 // Same function and parameters as the PyTorch module (fp32, FMA allowed like cuBLAS); differences are

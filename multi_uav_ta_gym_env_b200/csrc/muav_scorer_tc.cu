@@ -1,6 +1,8 @@
 // Att-Pair scorer forward on the 5th-generation tensor cores (tcgen05 + TMEM), same function as att_pair_kernel in
 // muav_scorer.cu (AttPairNet, TaskAllocation/Hybrid/PairCostHybrid.py:89-151, scores = tanh(logits) * clamp * edge_valid,
-// :266-278).
+// :266-278), with the context term of AttContextPairNet (ContextPairHybrid.py:81-151) when the parameters have one;
+// att_tc_kernel<true> is the AttCommitNet forward (AttentionCommit.py:68-100: the projections, two encoder layers, the
+// priority / commit sigmoid heads) on the same machinery.
 //
 // One CTA per SM owns all 512 TMEM columns.  A pass packs the live tokens of up to eight environments into the 128
 // rows of an M = 128 MMA (agents first, then tasks; row = TMEM lane).  Every linear layer is D[128 x N] = A[128 x K] *
