@@ -151,9 +151,10 @@ def run_episode(case, seed, driver, overrides=None):
         planner = AttentionEscort(use_attention=False, device="cpu", d_model=16)
         planner.net = _InjectedNet()
         hung = HungarianAllocator(replan_interval=10**9, max_coord=env.max_coord)
-    elif driver in ("local_pi", "pi_coalition"):
+    elif driver in ("local_pi", "pi_coalition", "local_pi2", "pi2_coalition"):
         from TaskAllocation.MarketBased.PerformanceImpact import PerformanceImpact
-        planner = PerformanceImpact(max_coord=env.max_coord, seed=seed, replan_interval=20 if driver == "local_pi" else 12)
+        planner = PerformanceImpact(max_coord=env.max_coord, seed=seed,
+                                    replan_interval=20 if driver in ("local_pi", "local_pi2") else 12)
     elif driver in ("cbba_replan", "cbba_coalition"):
         # Local-CBBA-Replan (wps_eval.py:105,134-146) / Local-CBBA-Coalition (escort_eval.py:108-112,149-161).  CBBA's
         # auction order starts from a set of strings: reproducible only with the string hash pinned
@@ -178,9 +179,12 @@ def run_episode(case, seed, driver, overrides=None):
         elif driver == "global_hungarian":
             pairs = hung.allocate_tasks(env.get_live_agents(), ref_open_tasks(env), time_step=env.time_steps,
                                         events=events)
-        elif driver in ("local_pi", "pi_coalition"):
+        elif driver in ("local_pi", "pi_coalition", "local_pi2", "pi2_coalition"):
+            # the *2 drivers: bundles of two tasks per agent (max_tasks_per_agent=2, PerformanceImpact.py:59-224 in full);
+            # _apply_assign keeps the first task of every agent's path (wps_eval.py:55-61)
             res = planner.allocate_tasks(env.get_live_agents(), ref_open_tasks(env), time_step=env.time_steps, events=events,
-                                         agent_known_ids=env.agent_visibility_map(), max_tasks_per_agent=1)
+                                         agent_known_ids=env.agent_visibility_map(),
+                                         max_tasks_per_agent=2 if driver.endswith(("pi2", "pi2_coalition")) else 1)
             pairs = [(name, task) for name, tl in res for task in tl]   # _flatten_pairs (wps_eval.py:40-52)
         elif driver in ("cbba_replan", "cbba_coalition"):
             res = planner.allocate_tasks(env.get_live_agents(), ref_open_tasks(env), time_step=env.time_steps, events=events,
@@ -260,7 +264,8 @@ def run_episode(case, seed, driver, overrides=None):
             break
     m = info["metrics"]
     ep["metrics"] = {k: (fhex(v) if isinstance(v, (float, np.floating)) else int(v)) for k, v in m.items()}
-    ep["n_replans"] = int(planner.n_replans if driver in ("local_pi", "pi_coalition", "cbba_replan", "cbba_coalition")
+    ep["n_replans"] = int(planner.n_replans if driver in ("local_pi", "pi_coalition", "local_pi2", "pi2_coalition",
+                                                          "cbba_replan", "cbba_coalition")
                           else hung.n_replans)
     return ep
 
@@ -289,6 +294,9 @@ PLAN = [
     ("wps_hard_pi", "WPS_hard", "local_pi", range(0, 8), None),
     ("wps_commit_pi", "WPS_commit", "local_pi", range(0, 4), None),
     ("wps_escort_pi", "WPS_escort", "pi_coalition", range(0, 4), None),
+    ("wps_hard_pi2", "WPS_hard", "local_pi2", range(0, 6), None),
+    ("wps_commit_pi2", "WPS_commit", "local_pi2", range(0, 3), None),
+    ("wps_escort_pi2", "WPS_escort", "pi2_coalition", range(0, 3), None),
     # CBBA: run this script with PYTHONHASHSEED=0 (set-of-strings iteration order, CBBA.py:116,128)
     ("wps_hard_cbba", "WPS_hard", "cbba_replan", range(0, 6), None),
     ("wps_commit_cbba", "WPS_commit", "cbba_replan", range(0, 3), None),

@@ -24,6 +24,7 @@ CASES = [
     ("wps_hard_urgency_pair", 3), ("wps_attn_context", 2), ("wps_commit_attcommit", 3), ("wps_escort_attescort", 3),
     ("wps_hard_pi", 4), ("wps_commit_pi", 2), ("wps_escort_pi", 2),
     ("wps_hard_cbba", 6), ("wps_commit_cbba", 3), ("wps_escort_cbba", 3),
+    ("wps_hard_pi2", 6), ("wps_commit_pi2", 3), ("wps_escort_pi2", 3),
 ]
 
 
@@ -34,7 +35,7 @@ def replay(ep):
     drv = ep["driver"]
     interval = 12 if drv == "coalition" else (10**9 if drv in ("urgency_coalition", "att_escort_injected") else 20)
     hung = OracleHungarian(interval, o.max_coord)
-    pi = OraclePI(o.max_coord, ep["seed"], 12 if drv == "pi_coalition" else 20)
+    pi = OraclePI(o.max_coord, ep["seed"], 12 if drv in ("pi_coalition", "pi2_coalition") else 20)
     cbba = OracleCBBAReplan(o.max_coord, ep["seed"], 12 if drv == "cbba_coalition" else 20)
     for t, st in enumerate(ep["steps"]):
         if drv in ("local_hungarian", "coalition", "global_hungarian"):
@@ -42,8 +43,9 @@ def replay(ep):
             pairs = hung.allocate(o, time_step=o.t, events=o.last_events, known=known)
             assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
             assert [list(a) for a in apply_assign(o, pairs)] == st["actions"], (ep["seed"], t)
-        elif drv in ("local_pi", "pi_coalition"):
-            pairs = pi.allocate(o, time_step=o.t, events=o.last_events, known=o.visibility())
+        elif drv in ("local_pi", "pi_coalition", "local_pi2", "pi2_coalition"):
+            pairs = pi.allocate(o, time_step=o.t, events=o.last_events, known=o.visibility(),
+                                max_tasks_per_agent=2 if drv.endswith(("pi2", "pi2_coalition")) else 1)
             assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
             assert [list(a) for a in apply_assign(o, pairs)] == st["actions"], (ep["seed"], t)
         elif drv in ("cbba_replan", "cbba_coalition"):
@@ -110,7 +112,7 @@ def replay(ep):
         assert hung.n_replans == ep["n_replans"]
     if drv in ("cbba_replan", "cbba_coalition"):
         assert cbba.n_replans == ep["n_replans"]
-    if drv in ("local_pi", "pi_coalition"):
+    if drv in ("local_pi", "pi_coalition", "local_pi2", "pi2_coalition"):
         assert pi.n_replans == ep["n_replans"]
 
 
