@@ -58,6 +58,8 @@ class MuavAllocOpts(C.Structure):
         ("d_task_order", C.c_void_p),
         ("d_plan_pri", C.c_void_p), ("d_plan_commit", C.c_void_p), ("commit_threshold", C.c_double),
         ("d_cbba_seed", C.c_void_p),
+        ("max_tasks_per_agent", C.c_int32), ("reserved0", C.c_int32),
+        ("d_bundle_pairs", C.c_void_p), ("d_n_bundle_pairs", C.c_void_p),
     ]
 
 

@@ -447,6 +447,187 @@ MUAV_HD inline bool slot_id_less(int x, int y) {
   return x / sh < y;
 }
 
+// ---- bundles (max_tasks_per_agent > 1): the inclusion phase over agent PATHS (PerformanceImpact.py:106-165).
+// A path is a list of slots in visiting order; _schedule / _path_cost (:227-261) walk it: start = now + dist / speed,
+// now = start + duration[type].  IPI of (agent, slot) = min over the feasible insertion points of cost(path + slot) -
+// cost(path) (_best_inclusion_impact :263-283, first minimum within 1e-9); its provisional RPI (:285-301) is the same two
+// costs subtracted the same way, i.e. the same number.
+constexpr int PI_MAX_BUNDLE = 4;
+
+// cost of the path p[0..n) of agent a; *first_bad = index of the first entry that starts later than its deadline + 1e-6
+// (n when every entry is feasible: _filter_feasible :303-311)
+MUAV_HD inline double pi_path_cost(Sim& S, const int16_t* open_t, const int16_t* slot_q, int a, const int16_t* p, int n, int t,
+                                   int* first_bad) {
+  View& V = S.V;
+  double px = V.a_posx()[a], py = V.a_posy()[a];
+  double now = dmax(V.a_nft()[a], (double)t);
+  const double speed = dmax(S.speed_of(a) != 0.0 ? S.speed_of(a) : 1.0, 1e-6);
+  double cost = 0.0;
+  int bad = n;
+  for (int j = 0; j < n; ++j) {
+    const int k = open_t[slot_q[p[j]]];
+    const double tx = V.k_posx()[k], ty = V.k_posy()[k];
+    const double start = now + ddiv(norm2(px - tx, py - ty), speed);
+    const int dl = V.k_deadline()[k];
+    if (bad == n && dl >= 0 && start > (double)dl + 1e-6) bad = j;
+    cost = cost + start;
+    if (dl >= 0 && start > (double)dl) {
+      const double late = 200.0 + (start - (double)dl);
+      cost = cost + late;
+    }
+    const int ti = V.k_type()[k];
+    const double cp = S.cap(a, ti);
+    const double bonus = 5.0 * (is_coalition(S, k) ? dmax(cp, 0.5) : cp);
+    cost = cost - bonus;
+    px = tx;
+    py = ty;
+    now = start + (double)S.C().duration[ti];
+  }
+  *first_bad = bad;
+  return cost;
+}
+
+// paths: [live row][PI_MAX_BUNDLE] slots, plen: [live row]; slot_rpi: RPI of the slot's winner when it won the slot
+MUAV_HD inline int pi_bundles(Sim& S, const muav_alloc_opts& O, int e, const AllocScratch& W, int nr, int nq, int ns,
+                              const int16_t* slot_q, const int16_t* slot_rank, int16_t* slot_win, int16_t* out_agent,
+                              int16_t* out_tid, int lane, int nlanes) {
+  View& V = S.V;
+  const int A = V.lay().D.A;
+  const int t = HIv(T);
+  int MB = O.max_tasks_per_agent;
+  if (MB > PI_MAX_BUNDLE) MB = PI_MAX_BUNDLE;
+  int16_t* paths = W.path;         // the six LSAP index arrays are contiguous: room for nr * PI_MAX_BUNDLE entries
+  int16_t* plen = W.live_row;
+  double* slot_rpi = W.cost;       // the cost matrix is not used by this form
+  enum { C_BEST = 4, C_AT = 5 };
+  if (A * V.lay().D.TC < ns) {   // the RPI array lives in the cost matrix: tiny fleets only
+    if (lane == 0) HIv(ERRFLAGS) |= ERR_NO_SPACE;
+    MUAV_WARP_SYNC();
+    return 0;
+  }
+  for (int i = lane; i < nr; i += nlanes) plen[i] = 0;
+  MUAV_WARP_SYNC();
+  const int max_it = ns * (nr > 1 ? nr : 1);
+  for (int it = 0; it < max_it; ++it) {
+    double bc = INFINITY;
+    int bkey = 0x7fffffff, bidx = -1, bat = 0;
+    for (int idx = lane; idx < nr * ns; idx += nlanes) {
+      const int i = idx / ns, s = idx - i * ns;
+      const int n = plen[i];
+      if (n >= MB) continue;
+      const int w = slot_win[s];
+      if (w == i) continue;
+      const int q = slot_q[s];
+      const int16_t* path = paths + i * PI_MAX_BUNDLE;
+      bool owned = false;
+      for (int j = 0; j < n; ++j) owned = owned || slot_q[path[j]] == q;
+      if (owned) continue;
+      const int a = W.free_agents[i];
+      const int k = W.open_t[q];
+      {   // agent_eligible (CBBA.py:27-43)
+        const int el = V.k_elig()[k];
+        bool ok = !O.use_visibility || S.known_bit(a, k);
+        ok = ok && ((el == 0) || ((el >> V.a_type()[a]) & 1));
+        ok = ok && S.qfind(a, k + 1) < 0;
+        ok = ok && (is_coalition(S, k) || S.cap(a, V.k_type()[k]) > 0);
+        if (!ok) continue;
+      }
+      int bad = 0;
+      const double base = pi_path_cost(S, W.open_t, slot_q, a, path, n, t, &bad);
+      double best = INFINITY;
+      int at = 0;
+      for (int pos = 0; pos <= n; ++pos) {
+        int16_t mapped[PI_MAX_BUNDLE + 1];
+        for (int j = 0; j < pos; ++j) mapped[j] = path[j];
+        mapped[pos] = (int16_t)s;
+        for (int j = pos; j < n; ++j) mapped[j + 1] = path[j];
+        const double c = pi_path_cost(S, W.open_t, slot_q, a, mapped, n + 1, t, &bad);
+        if (bad != n + 1) continue;
+        const double ipi = c - base;
+        if (ipi < best - 1e-9) { best = ipi; at = pos; }
+      }
+      if (!(best < INFINITY) || !(best > -INFINITY)) continue;
+      if (w >= 0) {
+        const double cur = slot_rpi[s];
+        if (best < cur - 1e-9) continue;
+        if (fabs(best - cur) <= 1e-9 && a >= W.free_agents[w]) continue;
+      }
+      const int key = (a << 16) | slot_rank[s];
+      if (best < bc || (best == bc && key < bkey)) { bc = best; bkey = key; bidx = idx; bat = at; }
+    }
+    const double m = warp_min_f64(bc);
+    const int kmin = warp_min_i32((bidx >= 0 && bc == m) ? bkey : 0x7fffffff);
+    if (kmin == 0x7fffffff) break;
+    if (bidx >= 0 && bc == m && bkey == kmin) { W.ctrl[C_BEST] = bidx; W.ctrl[C_AT] = bat; }   // (agent, slot rank) is unique
+    MUAV_WARP_SYNC();
+    if (lane == 0) {
+      const int idx = W.ctrl[C_BEST], at = W.ctrl[C_AT];
+      const int i = idx / ns, s = idx - i * ns;
+      const int prev = slot_win[s];
+      if (prev >= 0 && prev != i) {
+        int16_t* pp = paths + prev * PI_MAX_BUNDLE;
+        int n2 = 0;
+        for (int j = 0; j < plen[prev]; ++j)
+          if (pp[j] != s) pp[n2++] = pp[j];
+        plen[prev] = (int16_t)n2;
+      }
+      int16_t* path = paths + i * PI_MAX_BUNDLE;
+      const int n = plen[i];
+      for (int j = n; j > at; --j) path[j] = path[j - 1];
+      path[at] = (int16_t)s;
+      plen[i] = (int16_t)(n + 1);
+      slot_win[s] = (int16_t)i;
+      // _removal_impact of the slot in its new path (:285-301)
+      int16_t rest[PI_MAX_BUNDLE];
+      int n2 = 0, bad = 0;
+      for (int j = 0; j <= n; ++j)
+        if (j != at) rest[n2++] = path[j];
+      const int a = W.free_agents[i];
+      slot_rpi[s] = pi_path_cost(S, W.open_t, slot_q, a, path, n + 1, t, &bad) - pi_path_cost(S, W.open_t, slot_q, a, rest, n2, t, &bad);
+    }
+    MUAV_WARP_SYNC();
+  }
+  // consensus clean-up (:168-205): every slot has one claimant here (a stolen slot leaves its loser's path at once), so
+  // the only thing left to do is to cut paths back to their feasible prefix until nothing changes
+  if (lane == 0) {
+    for (int it = 0; it < 40; ++it) {
+      bool changed = false;
+      for (int i = 0; i < nr; ++i) {
+        int bad = 0;
+        pi_path_cost(S, W.open_t, slot_q, W.free_agents[i], paths + i * PI_MAX_BUNDLE, plen[i], t, &bad);
+        if (bad < plen[i]) {
+          for (int j = bad; j < plen[i]; ++j)
+            if (slot_win[paths[i * PI_MAX_BUNDLE + j]] == i) slot_win[paths[i * PI_MAX_BUNDLE + j]] = -1;
+          plen[i] = (int16_t)bad;
+          changed = true;
+        }
+      }
+      if (!changed) break;
+    }
+    int nb = 0;
+    int32_t* bp = O.d_bundle_pairs ? O.d_bundle_pairs + (size_t)e * A * O.max_tasks_per_agent : nullptr;
+    for (int i = 0; i < nr; ++i)
+      for (int j = 0; j < plen[i]; ++j) {
+        if (bp) bp[nb] = ((int)W.free_agents[i] << 16) | (W.open_t[slot_q[paths[i * PI_MAX_BUNDLE + j]]] + 1);
+        ++nb;
+      }
+    if (O.d_n_bundle_pairs) O.d_n_bundle_pairs[e] = nb;
+  }
+  MUAV_WARP_SYNC();
+  // the step's pairs: the first task of every path (_apply_assign keeps the first pair of an agent)
+  int n_pairs = 0;
+  for (int i = 0; i < nr; ++i) {
+    if (plen[i] == 0) continue;
+    if (lane == 0) {
+      out_agent[n_pairs] = W.free_agents[i];
+      out_tid[n_pairs] = (int16_t)(W.open_t[slot_q[paths[i * PI_MAX_BUNDLE]]] + 1);
+    }
+    ++n_pairs;
+  }
+  MUAV_WARP_SYNC();
+  return n_pairs;
+}
+
 MUAV_HD MUAV_NI_A inline int pi_allocate(Sim& S, const muav_alloc_opts& O, int e, int16_t* out_agent, int16_t* out_tid, int lane,
                                int nlanes) {
   View& V = S.V;
@@ -523,6 +704,7 @@ MUAV_HD MUAV_NI_A inline int pi_allocate(Sim& S, const muav_alloc_opts& O, int e
     W.ctrl[C_NFREE] = n_free;
     W.ctrl[C_NOPEN] = n_open;
     W.ctrl[C_NSLOT] = n_slot;
+    if (O.d_n_bundle_pairs) O.d_n_bundle_pairs[e] = 0;
   }
   MUAV_WARP_SYNC();
   if (!W.ctrl[C_GO]) return 0;
@@ -541,6 +723,10 @@ MUAV_HD MUAV_NI_A inline int pi_allocate(Sim& S, const muav_alloc_opts& O, int e
     int r = 0;
     for (int p = 0; p < ns; ++p) r += q_rank[slot_q[p]] < rq ? 1 : 0;
     slot_rank[s] = (int16_t)(r + slot_k[s]);
+  }
+  if (O.max_tasks_per_agent > 1) {
+    MUAV_WARP_SYNC();
+    return pi_bundles(S, O, e, W, nr, nq, ns, slot_q, slot_rank, slot_win, out_agent, out_tid, lane, nlanes);
   }
   // ---- cost of (live row, open task): independent entries, spread over the lanes
   for (int idx = lane; idx < nr * nq; idx += nlanes) {

@@ -81,9 +81,10 @@ def alloc_opts_for(driver):
         O.replan_interval = 12 if driver == "coalition" else 20
         O.event_mask = 0x1F
         O.use_visibility = 0 if driver == "global_hungarian" else 1
-    elif driver in ("local_pi", "pi_coalition"):
-        O.mode, O.replan_interval, O.event_mask, O.use_visibility = 1, (12 if driver == "pi_coalition" else 20), 0x1F, 1
+    elif driver in ("local_pi", "pi_coalition", "local_pi2", "pi2_coalition"):
+        O.mode, O.replan_interval, O.event_mask, O.use_visibility = 1, (12 if "coalition" in driver else 20), 0x1F, 1
         O.planner = 6
+        O.max_tasks_per_agent = 2 if "pi2" in driver else 1   # the caller points d_bundle_pairs / d_n_bundle_pairs somewhere
     elif driver in ("cbba_replan", "cbba_coalition"):
         # CBBAReplan under the drivers of wps_eval.py:134-146 / escort_eval.py:149-161; the caller sets O.d_cbba_seed
         O.mode, O.replan_interval, O.event_mask, O.use_visibility = 1, (12 if driver == "cbba_coalition" else 20), 0x1F, 1

@@ -13,7 +13,8 @@ STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit
 # planner fixtures mutate commit_until between steps: they are replayed through the fused planner only
 ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
     "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair", "wps_attn_context",
-    "wps_hard_pi", "wps_commit_pi", "wps_escort_pi", "wps_hard_cbba", "wps_commit_cbba", "wps_escort_cbba"]
+    "wps_hard_pi", "wps_commit_pi", "wps_escort_pi", "wps_hard_cbba", "wps_commit_cbba", "wps_escort_cbba",
+    "wps_hard_pi2", "wps_commit_pi2", "wps_escort_pi2"]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)
@@ -43,6 +44,12 @@ def test_fused_allocator(hostcheck, name):
     if drv in ("cbba_replan", "cbba_coalition"):
         cbba_seeds = np.array([ep["seed"] for ep in eps], np.int32)
         O.d_cbba_seed = cbba_seeds.ctypes.data
+    bundles = drv in ("local_pi2", "pi2_coalition")
+    if bundles:   # the whole plan (every path entry) next to the step's first-task pairs
+        A = len(eps[0]["agent_names"])
+        bp = np.zeros((len(eps), A * 2), np.int32)
+        nbp = np.zeros(len(eps), np.int32)
+        O.d_bundle_pairs, O.d_n_bundle_pairs = bp.ctypes.data, nbp.ctypes.data
     for t in range(len(eps[0]["steps"])):
         if drv in ("pair_injected", "context_injected"):
             sc = np.stack([injected_scores(ep["seed"], t, 16, 32) for ep in eps])
@@ -77,10 +84,20 @@ def test_fused_allocator(hostcheck, name):
         env.step_alloc(O)
         for e, ep in enumerate(eps):
             st = ep["steps"][t]
-            assert env.pairs_of(e) == st["pairs"], (name, ep["seed"], t)
+            if bundles:
+                got = [[int(v) >> 16, int(v) & 0xFFFF] for v in bp[e, : nbp[e]]]
+                assert got == st["pairs"], (name, ep["seed"], t, got, st["pairs"])
+                first = []
+                for a, k in st["pairs"]:
+                    if a not in [p[0] for p in first]:
+                        first.append([a, k])
+                assert env.pairs_of(e) == first, (name, ep["seed"], t)
+            else:
+                assert env.pairs_of(e) == st["pairs"], (name, ep["seed"], t)
             assert env.reward[e] == float.fromhex(st["reward"])
             assert str(env.digest(e)) == st["digest"], (name, ep["seed"], t)
-    if drv in ("local_hungarian", "coalition", "global_hungarian", "local_pi", "pi_coalition", "cbba_replan", "cbba_coalition"):
+    if drv in ("local_hungarian", "coalition", "global_hungarian", "local_pi", "pi_coalition", "cbba_replan", "cbba_coalition",
+               "local_pi2", "pi2_coalition"):
         for e, ep in enumerate(eps):
             assert env.codec.header(env.rec[e], "N_REPLANS") == ep["n_replans"]
 
