@@ -39,6 +39,7 @@ class AllocSpec:
                                   # 7: CBBAReplan.allocate_tasks(max_tasks_per_agent=1)
     commit_fraction: float = 0.35
     commit_threshold: float = 0.5
+    max_tasks_per_agent: int = 1  # planner 6: bundles of up to 4 tasks per agent (the step takes the first of each path)
 
     @staticmethod
     def local_hungarian(interval=20):
@@ -53,10 +54,12 @@ class AllocSpec:
         return AllocSpec(1, interval, ALL_EVENTS, True, False)
 
     @staticmethod
-    def performance_impact(interval=20):
-        """Local-PI / Local-PI-Coalition (MarketBased/PerformanceImpact.py:59-224 with max_tasks_per_agent=1) under its own
-        should_replan rule, as experiments/wps_eval.py:147-159 (interval 20) and escort_eval.py:162-174 (12) run it."""
-        return AllocSpec(1, interval, ALL_EVENTS, True, False, planner=6)
+    def performance_impact(interval=20, max_tasks_per_agent=1):
+        """Local-PI / Local-PI-Coalition (MarketBased/PerformanceImpact.py:59-224) under its own should_replan rule, as
+        experiments/wps_eval.py:147-159 (interval 20) and escort_eval.py:162-174 (12) run it (max_tasks_per_agent=1 there).
+        With max_tasks_per_agent 2..4 the allocator builds bundles; the step takes the first task of every path and the
+        whole plan is in env.bundle_pairs_of(e)."""
+        return AllocSpec(1, interval, ALL_EVENTS, True, False, planner=6, max_tasks_per_agent=int(max_tasks_per_agent))
 
     @staticmethod
     def cbba_replan(interval=20):
@@ -375,17 +378,19 @@ class BatchedMultiUAVEnv:
     def _alloc_opts(self, spec, edge_scores, priorities, reserved, task_order=None, plan_pri=None, plan_commit=None):
         # the same spec over the same tensors every step (a rollout loop): reuse the filled struct
         key = (id(spec), spec.mode, spec.replan_interval, spec.event_mask, spec.planner, spec.commit_fraction,
-               spec.commit_threshold, spec.use_visibility, spec.pair_tokens, spec.max_coord) + tuple(
+               spec.commit_threshold, spec.use_visibility, spec.pair_tokens, spec.max_coord, spec.max_tasks_per_agent) + tuple(
             (x.data_ptr(), x.dtype, tuple(x.shape), x.device.index, x.is_contiguous()) if isinstance(x, torch.Tensor) else None
             for x in (edge_scores, priorities, reserved, task_order, plan_pri, plan_commit))
         cached = getattr(self, "_opts_cache", None)
         if cached is not None and cached[0] == key:
-            return cached[1], cached[2]
+            # a copy: callers may fill further fields (the facade backend does) without touching the cached struct
+            return _lib.MuavAllocOpts.from_buffer_copy(cached[1]), list(cached[2])
         O, keep = self._alloc_opts_build(spec, edge_scores, priorities, reserved, task_order, plan_pri, plan_commit)
         # the cache holds the argument tensors themselves too, so that the data pointers in the key cannot be reused
-        self._opts_cache = (key, O, keep + [x for x in (edge_scores, priorities, reserved, task_order, plan_pri, plan_commit)
-                                            if isinstance(x, torch.Tensor)])
-        return O, keep
+        keep = keep + [x for x in (edge_scores, priorities, reserved, task_order, plan_pri, plan_commit)
+                       if isinstance(x, torch.Tensor)]
+        self._opts_cache = (key, _lib.MuavAllocOpts.from_buffer_copy(O), keep)
+        return O, list(keep)
 
     def _alloc_opts_build(self, spec, edge_scores, priorities, reserved, task_order=None, plan_pri=None, plan_commit=None):
         O = _lib.MuavAllocOpts()
@@ -418,6 +423,16 @@ class BatchedMultiUAVEnv:
             keep.append(to)
             O.d_task_order = to.data_ptr()
         O.commit_threshold = spec.commit_threshold
+        if spec.planner == 6 and spec.max_tasks_per_agent > 1:
+            if spec.max_tasks_per_agent > 4:
+                raise ValueError("the device PI allocator builds bundles of at most 4 tasks per agent")
+            O.max_tasks_per_agent = spec.max_tasks_per_agent
+            need = self.n_agents * spec.max_tasks_per_agent
+            bp = getattr(self, "bundle_pairs", None)
+            if bp is None or bp.shape[1] != need:
+                self.bundle_pairs = torch.zeros(self.n_envs, need, dtype=torch.int32, device=self.device)
+                self.n_bundle_pairs = torch.zeros(self.n_envs, dtype=torch.int32, device=self.device)
+            O.d_bundle_pairs, O.d_n_bundle_pairs = self.bundle_pairs.data_ptr(), self.n_bundle_pairs.data_ptr()
         if spec.planner == 7:
             O.d_cbba_seed = self.seeds.data_ptr()
         if spec.planner == 3:
@@ -601,6 +616,13 @@ class BatchedMultiUAVEnv:
 
     def events_of(self, e: int) -> list:
         return _state.decode_events(int(self.n_events[e].item()), self.events[e].cpu().numpy())
+
+    def bundle_pairs_of(self, e: int) -> list:
+        """The whole plan of the last Performance-Impact launch with bundles: [agent id, task id] of every path entry in the
+        order allocate_tasks returns them (pairs_of(e) holds the first task of every path, what the step used)."""
+        n = int(self.n_bundle_pairs[e].item())
+        p = self.bundle_pairs[e, :n].cpu().numpy()
+        return [[int(x) >> 16, int(x) & 0xFFFF] for x in p]
 
     def pairs_of(self, e: int) -> list:
         n = int(self.n_pairs[e].item())

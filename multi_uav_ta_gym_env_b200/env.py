@@ -236,6 +236,9 @@ class _CudaBackend:
         _lib.check(rc, "muav_allocate")
         return self.b.pairs_of(0)
 
+    def bundle_pairs(self):
+        return self.b.bundle_pairs_of(0)
+
     def observe(self, max_rows):
         return {k: v[0].cpu().numpy() for k, v in self.b.observe(max_rows).items()}
 
@@ -664,8 +667,9 @@ class PerformanceImpact:
     """Same constructor, attributes and allocate_tasks signature as the reference's market baseline
     (TaskAllocation/MarketBased/PerformanceImpact.py:27-224); the slot expansion, the IPI / RPI costs and the
     inclusion loop run in the CUDA allocator (muav_allocate, muav_alloc_opts.planner = 6).  Returns
-    (agent_name, [task]) items like the reference.  Only max_tasks_per_agent = 1 -- what every reference driver
-    passes (experiments/wps_eval.py:147-156, escort_eval.py:162-170) -- is implemented; anything else raises."""
+    (agent_name, [tasks in path order]) items like the reference.  max_tasks_per_agent = 1 is what every reference driver
+    passes (experiments/wps_eval.py:147-156, escort_eval.py:162-170); bundles of up to 4 tasks per agent are built by the
+    same allocator (pi_bundles, csrc/muav_alloc.cuh); larger values raise."""
 
     def __init__(self, max_coord: float = 1000.0, seed: int = 0, replan_interval: int = 12, max_iters: int = 40):
         self.max_coord = float(max_coord)
@@ -682,8 +686,8 @@ class PerformanceImpact:
                        reserved_agent_names=None, max_tasks_per_agent: int = 1):
         from .batched_env import AllocSpec
 
-        if max_tasks_per_agent != 1:
-            raise NotImplementedError("the device PI allocator implements max_tasks_per_agent=1 (the reference drivers' setting)")
+        if not 1 <= int(max_tasks_per_agent) <= 4:
+            raise NotImplementedError("the device PI allocator builds bundles of 1..4 tasks per agent")
         self.n_calls += 1
         if not force and not self.should_replan(time_step, events):
             return []
@@ -721,8 +725,17 @@ class PerformanceImpact:
             for name, ids in agent_known_ids.items():
                 if name in own and set(ids) != own[name]:
                     raise NotImplementedError("agent_known_ids must be env.agent_visibility_map() (device-resident sets)")
-        spec = AllocSpec(3, self.replan_interval, 0, use_vis, False, float(self.max_coord), planner=6)
+        spec = AllocSpec(3, self.replan_interval, 0, use_vis, False, float(self.max_coord), planner=6,
+                         max_tasks_per_agent=int(max_tasks_per_agent))
         pairs = env._backend.allocate(spec, None, None, reserved, order)
+        if max_tasks_per_agent > 1:   # (name, [tasks in path order]) like the reference (PerformanceImpact.py:207-220)
+            out = []
+            for a, tid in env._backend.bundle_pairs():
+                if out and out[-1][0] == env.agents_obj[a].name:
+                    out[-1][1].append(env._task(tid))
+                else:
+                    out.append((env.agents_obj[a].name, [env._task(tid)]))
+            return out
         return [(env.agents_obj[a].name, [env._task(tid)]) for a, tid in pairs]
 
 

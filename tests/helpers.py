@@ -319,6 +319,12 @@ class HostBackend:
             od = np.ascontiguousarray(order, dtype=np.int32)
             keep.append(od)
             O.d_task_order = od.ctypes.data
+        mb = int(getattr(spec, "max_tasks_per_agent", 1))
+        self._bundle = np.zeros((1, A * max(mb, 1)), np.int32)
+        self._n_bundle = np.zeros(1, np.int32)
+        if spec.planner == 6 and mb > 1:
+            O.max_tasks_per_agent = mb
+            O.d_bundle_pairs, O.d_n_bundle_pairs = self._bundle.ctypes.data, self._n_bundle.ctypes.data
         npairs = np.zeros(1, np.int32)
         pairs = np.zeros((1, A), np.int32)
         out = _lib.MuavStepOut()
@@ -326,6 +332,9 @@ class HostBackend:
         rc = self.lib.dll.hostcheck_allocate(C.byref(self.cfg), self.rec.ctypes.data, C.byref(O), C.byref(out), None, 1)
         assert rc == 0
         return [[int(p) >> 16, int(p) & 0xFFFF] for p in pairs[0, : npairs[0]]]
+
+    def bundle_pairs(self):
+        return [[int(p) >> 16, int(p) & 0xFFFF] for p in self._bundle[0, : self._n_bundle[0]]]
 
     def observe(self, max_rows):
         A = self.cfg.n_agents

@@ -107,10 +107,12 @@ def test_env_and_allocator_facade_follow_the_reference_loop(case, seed, interval
     assert ref.compute_s_wps() == mine.compute_s_wps() and ref.compute_s_esc() == mine.compute_s_esc()
 
 
-@pytest.mark.parametrize("case,seed,interval", [("WPS_hard", 5, 20), ("WPS_escort", 2, 12)])
-def test_performance_impact_facade_follows_the_reference_loop(case, seed, interval):
+@pytest.mark.parametrize("case,seed,interval,bundle", [("WPS_hard", 5, 20, 1), ("WPS_escort", 2, 12, 1), ("WPS_hard", 7, 20, 2),
+                                                       ("WPS_commit", 3, 20, 3), ("WPS_escort", 4, 12, 2)])
+def test_performance_impact_facade_follows_the_reference_loop(case, seed, interval, bundle):
     """Local-PI / Local-PI-Coalition loop (wps_eval.py:147-159, escort_eval.py:162-174): the reference PerformanceImpact on the
-    reference env vs the facade class (device allocator, planner 6) on the facade env, every step."""
+    reference env vs the facade class (device allocator, planner 6) on the facade env, every step; also with bundles of two
+    and three tasks per agent (max_tasks_per_agent, the full inclusion phase of PerformanceImpact.py:106-205)."""
     refshim.install()
     from TaskAllocation.MarketBased.PerformanceImpact import PerformanceImpact as RefPI
     from multi_uav_ta_gym_env_b200.env import PerformanceImpact
@@ -124,9 +126,10 @@ def test_performance_impact_facade_follows_the_reference_loop(case, seed, interv
         revents = list(ri.get("events") or []) if isinstance(ri, dict) else []
         mevents = list(mi.get("events") or []) if isinstance(mi, dict) else []
         rres = rp.allocate_tasks(ref.get_live_agents(), ref_open_tasks(ref), time_step=ref.time_steps, events=revents,
-                                 agent_known_ids=ref.agent_visibility_map(), max_tasks_per_agent=1)
+                                 agent_known_ids=ref.agent_visibility_map(), max_tasks_per_agent=bundle)
         mres = mp.allocate_tasks(mine.get_live_agents(), ref_open_tasks(mine), time_step=mine.time_steps, events=mevents,
-                                 agent_known_ids=mine.agent_visibility_map(), max_tasks_per_agent=1)
+                                 agent_known_ids=mine.agent_visibility_map(), max_tasks_per_agent=bundle)
+        assert [(n, len(tl)) for n, tl in rres] == [(n, len(tl)) for n, tl in mres], t
         assert flat(ref, rres) == flat(mine, mres), t
         n_plans += bool(rres)
         ract = apply_assign(ref, [(n, t_) for n, tl in rres for t_ in tl])
@@ -139,7 +142,7 @@ def test_performance_impact_facade_follows_the_reference_loop(case, seed, interv
     assert n_plans > 5
     assert (rp.n_replans, rp.n_calls, rp.last_plan_step) == (mp.n_replans, mp.n_calls, mp.last_plan_step)
     with pytest.raises(NotImplementedError):
-        mp.allocate_tasks(mine.get_live_agents(), ref_open_tasks(mine), time_step=mine.time_steps, force=True, max_tasks_per_agent=2)
+        mp.allocate_tasks(mine.get_live_agents(), ref_open_tasks(mine), time_step=mine.time_steps, force=True, max_tasks_per_agent=5)
 
 
 @pytest.mark.parametrize("fixture,case,interval", [("wps_hard_cbba", "WPS_hard", 20), ("wps_escort_cbba", "WPS_escort", 12)])

@@ -22,7 +22,8 @@ STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit
 # planner fixtures mutate commit_until between steps: they are replayed through the fused planner only
 ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
     "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair", "wps_attn_context",
-    "wps_hard_pi", "wps_commit_pi", "wps_escort_pi", "wps_hard_cbba", "wps_commit_cbba", "wps_escort_cbba"]
+    "wps_hard_pi", "wps_commit_pi", "wps_escort_pi", "wps_hard_cbba", "wps_commit_cbba", "wps_escort_cbba",
+    "wps_hard_pi2", "wps_commit_pi2", "wps_escort_pi2"]
 
 
 def make_env(cfg, seeds, **kw):
@@ -39,6 +40,7 @@ def spec_for(driver):
             "urgency_commit": AllocSpec.urgency_commit(15), "urgency_coalition": AllocSpec.urgency_coalition(12),
             "context_injected": AllocSpec.pair_hybrid(15), "urgency_pair": AllocSpec.urgency_pair(15), "att_commit_injected": AllocSpec.att_commit(15), "att_escort_injected": AllocSpec.att_escort(12),
             "local_pi": AllocSpec.performance_impact(20), "pi_coalition": AllocSpec.performance_impact(12),
+            "local_pi2": AllocSpec.performance_impact(20, 2), "pi2_coalition": AllocSpec.performance_impact(12, 2),
             "cbba_replan": AllocSpec.cbba_replan(20), "cbba_coalition": AllocSpec.cbba_replan(12)}[driver]
 
 
@@ -122,10 +124,19 @@ def test_cuda_fused_allocator_matches_reference_golden(name):
         recs = env.records.cpu().numpy()
         for e, ep in enumerate(eps):
             st = ep["steps"][t]
-            assert env.pairs_of(e) == st["pairs"], (name, ep["seed"], t)
+            if drv in ("local_pi2", "pi2_coalition"):
+                # bundles: the whole plan equals the reference's (name, [tasks]) list; the step used the first task per agent
+                assert env.bundle_pairs_of(e) == st["pairs"], (name, ep["seed"], t)
+                first = []
+                for a, k in st["pairs"]:
+                    if a not in [p[0] for p in first]:
+                        first.append([a, k])
+                assert env.pairs_of(e) == first, (name, ep["seed"], t)
+            else:
+                assert env.pairs_of(e) == st["pairs"], (name, ep["seed"], t)
             assert rew[e] == float.fromhex(st["reward"]), (name, ep["seed"], t)
             assert str(refsnap.digest(env.codec.snapshot(recs[e]))) == st["digest"], (name, ep["seed"], t)
-    if drv in ("local_hungarian", "coalition", "global_hungarian", "local_pi", "pi_coalition"):
+    if drv in ("local_hungarian", "coalition", "global_hungarian", "local_pi", "pi_coalition", "local_pi2", "pi2_coalition"):
         nrep = env.header_int("N_REPLANS").cpu().numpy()
         for e, ep in enumerate(eps):
             assert int(nrep[e]) == ep["n_replans"]
