@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(MUAV_LB_THREADS, MUAV_LB_BLOCKS) muav_step_ker
       }
       if (!go) {
         if (P.out.d_n_pairs) P.out.d_n_pairs[e] = 0;
+        if (P.opts.d_n_bundle_pairs) P.opts.d_n_bundle_pairs[e] = 0;
         if (P.actions_out) P.actions_out[(size_t)e * L.D.A * 2] = -1;
       }
     }
