@@ -35,7 +35,7 @@ class AllocSpec:
     max_coord: float = 1200.0
     planner: int = 0              # 1: UrgencyCommit.plan, 2: UrgencyCoalition.plan (device-side planners),
                                   # 3: AttentionCommit._plan_from_scores, 4: AttentionEscort._plan_from_scores,
-                                  # 5: UrgencyPair.plan, 6: PerformanceImpact.allocate_tasks(max_tasks_per_agent=1),
+                                  # 5: UrgencyPair.plan, 6: PerformanceImpact.allocate_tasks (max_tasks_per_agent below),
                                   # 7: CBBAReplan.allocate_tasks(max_tasks_per_agent=1)
     commit_fraction: float = 0.35
     commit_threshold: float = 0.5

@@ -2,7 +2,8 @@
 
 Restates the Performance-Impact market allocator TaskAllocation/MarketBased/PerformanceImpact.py:27-311
 (with the slot expansion and eligibility test it imports from MarketBased/CBBA.py:10-65) over the oracle's flat
-state (oracle/sim.py).  Pinned by tests/golden/wps_{hard,commit,escort}_pi.json.gz, generated from the unmodified
+state (oracle/sim.py).  Pinned by tests/golden/wps_{hard,commit,escort}_pi.json.gz (max_tasks_per_agent=1) and
+wps_{hard,commit,escort}_pi2.json.gz (bundles of two), generated from the unmodified
 reference class under the episode loops of experiments/wps_eval.py:147-159 / escort_eval.py:162-174.
 
 The reference's other market baseline, CBBA / CBBAReplan (MarketBased/CBBA.py:68-324), is restated in oracle/cbba.py:
