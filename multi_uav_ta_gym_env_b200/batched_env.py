@@ -36,10 +36,10 @@ class AllocSpec:
     planner: int = 0              # 1: UrgencyCommit.plan, 2: UrgencyCoalition.plan (device-side planners),
                                   # 3: AttentionCommit._plan_from_scores, 4: AttentionEscort._plan_from_scores,
                                   # 5: UrgencyPair.plan, 6: PerformanceImpact.allocate_tasks (max_tasks_per_agent below),
-                                  # 7: CBBAReplan.allocate_tasks(max_tasks_per_agent=1)
+                                  # 7: CBBAReplan.allocate_tasks (max_tasks_per_agent below)
     commit_fraction: float = 0.35
     commit_threshold: float = 0.5
-    max_tasks_per_agent: int = 1  # planner 6: bundles of up to 4 tasks per agent (the step takes the first of each path)
+    max_tasks_per_agent: int = 1  # planners 6 / 7: bundles of up to 4 tasks per agent (the step takes the first of each)
 
     @staticmethod
     def local_hungarian(interval=20):
@@ -62,12 +62,12 @@ class AllocSpec:
         return AllocSpec(1, interval, ALL_EVENTS, True, False, planner=6, max_tasks_per_agent=int(max_tasks_per_agent))
 
     @staticmethod
-    def cbba_replan(interval=20):
+    def cbba_replan(interval=20, max_tasks_per_agent=1):
         """Local-CBBA-Replan / Local-CBBA-Coalition (MarketBased/CBBA_Replan.py:15-69 around CBBA.py:68-324 with
         max_tasks_per_agent=1, a fresh CBBA(seed + n_replans) per replan; seed = the environment's reset seed) as
         experiments/wps_eval.py:134-146 (interval 20) and escort_eval.py:149-161 (12) run it.  Reproduces the reference
-        run under PYTHONHASHSEED=0 (csrc/muav_cbba.cuh)."""
-        return AllocSpec(1, interval, ALL_EVENTS, True, False, planner=7)
+        run under PYTHONHASHSEED=0 (csrc/muav_cbba.cuh).  max_tasks_per_agent 2..4: bundles, as for performance_impact()."""
+        return AllocSpec(1, interval, ALL_EVENTS, True, False, planner=7, max_tasks_per_agent=int(max_tasks_per_agent))
 
     @staticmethod
     def pair_hybrid(interval=15):
@@ -423,9 +423,9 @@ class BatchedMultiUAVEnv:
             keep.append(to)
             O.d_task_order = to.data_ptr()
         O.commit_threshold = spec.commit_threshold
-        if spec.planner == 6 and spec.max_tasks_per_agent > 1:
+        if spec.planner in (6, 7) and spec.max_tasks_per_agent > 1:
             if spec.max_tasks_per_agent > 4:
-                raise ValueError("the device PI allocator builds bundles of at most 4 tasks per agent")
+                raise ValueError("the device market allocators build bundles of at most 4 tasks per agent")
             O.max_tasks_per_agent = spec.max_tasks_per_agent
             need = self.n_agents * spec.max_tasks_per_agent
             bp = getattr(self, "bundle_pairs", None)

@@ -23,6 +23,7 @@ namespace muav {
 constexpr int CBBA_MAX_SLOTS = 128;   // auction slots per call (ERR_NO_SPACE beyond)
 constexpr int CBBA_TABLE = 512;       // set table entries (enough for 306 keys)
 constexpr int CBBA_PATH = 32;         // slots on one agent's path at a time (ERR_NO_SPACE beyond)
+constexpr int CBBA_MAX_BUNDLE = 4;    // max_tasks_per_agent (muav_alloc_opts.max_tasks_per_agent, 1 when 0)
 
 struct CbbaScratch {
   uint32_t* mt;        // [624] MT19937 state
@@ -34,13 +35,14 @@ struct CbbaScratch {
   int16_t* table;      // [CBBA_TABLE] set of remaining slots: slot index, -1 empty, -2 dummy
   int16_t* ordered;    // [CBBA_MAX_SLOTS]
   int16_t* live;       // [A] live agent ids, then [A] shuffled copy
-  int16_t* bundle;     // [A] slot held by the agent or -1 (max_tasks_per_agent = 1)
+  int16_t* bundle;     // [A][CBBA_MAX_BUNDLE] slots held by the agent, in the order they were won
+  int16_t* blen;       // [A]
   int16_t* plen;       // [A]
   int16_t* path;       // [A][CBBA_PATH] slot indices
 };
 
 MUAV_HD constexpr inline int32_t cbba_scratch_bytes(int A) {
-  int b = 624 * 4 + CBBA_MAX_SLOTS * (8 + 8 + 2 + 2 + 2 + 2) + CBBA_TABLE * 2 + A * 2 * (2 + 1 + 1 + CBBA_PATH) + 64;
+  int b = 624 * 4 + CBBA_MAX_SLOTS * (8 + 8 + 2 + 2 + 2 + 2) + CBBA_TABLE * 2 + A * 2 * (2 + CBBA_MAX_BUNDLE + 1 + 1 + CBBA_PATH) + 64;
   return (b + 15) / 16 * 16;
 }
 
@@ -55,7 +57,8 @@ MUAV_HD inline CbbaScratch carve_cbba(char* p, int A) {
   W.ordered = (int16_t*)p; p += 2 * CBBA_MAX_SLOTS;
   W.table = (int16_t*)p; p += 2 * CBBA_TABLE;
   W.live = (int16_t*)p; p += 2 * 2 * A;
-  W.bundle = (int16_t*)p; p += 2 * A;
+  W.bundle = (int16_t*)p; p += 2 * A * CBBA_MAX_BUNDLE;
+  W.blen = (int16_t*)p; p += 2 * A;
   W.plen = (int16_t*)p; p += 2 * A;
   W.path = (int16_t*)p;
   return W;
@@ -317,6 +320,7 @@ MUAV_HD MUAV_NI_A inline int cbba_allocate(Sim& S, const muav_alloc_opts& O, int
   if (lane == 0) {
     int n_pairs = 0;
     HIv(N_CALLS) += 1;
+    if (O.d_n_bundle_pairs) O.d_n_bundle_pairs[e] = 0;
     const bool ev_hit = (HIv(EV_TAGMASK) & O.event_mask) != 0;
     const int interval = O.replan_interval > 0 ? O.replan_interval : 1;
     bool go;
@@ -382,7 +386,13 @@ MUAV_HD MUAV_NI_A inline int cbba_allocate(Sim& S, const muav_alloc_opts& O, int
         R.overflow = false;
         R.clear_table(8);
         for (int s = 0; s < n_slot; ++s) R.add(s);
-        for (int i = 0; i < n_live; ++i) { W.bundle[i] = -1; W.plen[i] = 0; }
+        for (int i = 0; i < n_live; ++i) { W.blen[i] = 0; W.plen[i] = 0; }
+        int MB = O.max_tasks_per_agent > 1 ? O.max_tasks_per_agent : 1;
+        if (MB > CBBA_MAX_BUNDLE) MB = CBBA_MAX_BUNDLE;
+        // bundle helpers: position of slot s / of a slot of task tid in the bundle of a row, removal keeps the order
+        auto b_find = [&](int row, int s2) { for (int j = 0; j < W.blen[row]; ++j) if (W.bundle[row * CBBA_MAX_BUNDLE + j] == s2) return j; return -1; };
+        auto b_owns = [&](int row, int tid2) { for (int j = 0; j < W.blen[row]; ++j) if (W.s_tid[W.bundle[row * CBBA_MAX_BUNDLE + j]] == tid2) return true; return false; };
+        auto b_remove = [&](int row, int s2) { const int j0 = b_find(row, s2); if (j0 < 0) return; for (int j = j0; j + 1 < W.blen[row]; ++j) W.bundle[row * CBBA_MAX_BUNDLE + j] = W.bundle[row * CBBA_MAX_BUNDLE + j + 1]; W.blen[row] -= 1; };
         CbbaRng G;
         G.mt = W.mt;
         const uint32_t seed0 = O.d_cbba_seed ? (uint32_t)O.d_cbba_seed[e] : 0u;
@@ -411,9 +421,8 @@ MUAV_HD MUAV_NI_A inline int cbba_allocate(Sim& S, const muav_alloc_opts& O, int
               if (el != 0 && !((el >> V.a_type()[a]) & 1)) continue;
               if (S.qfind(a, tid) >= 0) continue;
               if (!coal && !(S.cap(a, V.k_type()[k]) > 0)) continue;
-              const int b = W.bundle[row];
-              if (b >= 0 && W.s_tid[b] == tid) continue;   // task.id in owned_tasks[agent]
-              if (b >= 0) continue;                        // bundle full (max_tasks_per_agent = 1), this slot or not
+              if (b_owns(row, tid)) continue;              // task.id in owned_tasks[agent] (also: this slot is in the bundle)
+              if (W.blen[row] >= MB) continue;             // bundle full
               // calculate_bid (CBBA.py:216-225)
               double best = -INFINITY;
               const int n = W.plen[row];
@@ -430,7 +439,7 @@ MUAV_HD MUAV_NI_A inline int cbba_allocate(Sim& S, const muav_alloc_opts& O, int
                 for (int i = 0; i < n_live; ++i)
                   if (W.live[i] == prev) prow = i;
                 X.path_remove(prow, s);
-                if (W.bundle[prow] == s) W.bundle[prow] = -1;   // (owned_tasks == the bundle's task when bundles hold one slot)
+                b_remove(prow, s);   // owned_tasks is the set of the bundle's tasks
               }
               W.win[s] = (int16_t)a;
               W.bid[s] = bid;
@@ -458,20 +467,20 @@ MUAV_HD MUAV_NI_A inline int cbba_allocate(Sim& S, const muav_alloc_opts& O, int
             int wrow = 0;
             for (int i = 0; i < n_live; ++i) {
               if (W.live[i] == winner) { wrow = i; continue; }
-              if (W.bundle[i] == s) {
-                W.bundle[i] = -1;
+              if (b_find(i, s) >= 0) {
+                b_remove(i, s);
                 X.path_remove(i, s);
               }
             }
-            if (W.bundle[wrow] != s) {
-              const int b = W.bundle[wrow];
-              if (b >= 0) {   // another slot of the task already owned, or the bundle is full: drop this bid
+            if (b_find(wrow, s) < 0) {
+              if (b_owns(wrow, tid) || W.blen[wrow] >= MB) {   // another slot of the task already owned, or the bundle is full
                 W.win[s] = -1;
                 W.bid[s] = -INFINITY;
                 X.path_remove(wrow, s);
                 continue;
               }
-              W.bundle[wrow] = (int16_t)s;
+              W.bundle[wrow * CBBA_MAX_BUNDLE + W.blen[wrow]] = (int16_t)s;
+              W.blen[wrow] += 1;
               R.discard(s);
             }
           }
@@ -483,12 +492,22 @@ MUAV_HD MUAV_NI_A inline int cbba_allocate(Sim& S, const muav_alloc_opts& O, int
           X.makespan = mk;
         }
         if (R.overflow) HIv(ERRFLAGS) |= ERR_NO_SPACE;
-        for (int i = 0; i < n_live; ++i)
-          if (W.bundle[i] >= 0) {
+        // the step's pairs: the first task of every bundle (_apply_assign keeps an agent's first pair); with bundles the
+        // whole plan goes to d_bundle_pairs in the order allocate_tasks returns it (CBBA.py:192-204)
+        int nb = 0;
+        int32_t* bp = (MB > 1 && O.d_bundle_pairs) ? O.d_bundle_pairs + (size_t)e * A * O.max_tasks_per_agent : nullptr;
+        for (int i = 0; i < n_live; ++i) {
+          if (W.blen[i] > 0) {
             out_agent[n_pairs] = W.live[i];
-            out_tid[n_pairs] = W.s_tid[W.bundle[i]];
+            out_tid[n_pairs] = W.s_tid[W.bundle[i * CBBA_MAX_BUNDLE]];
             ++n_pairs;
           }
+          for (int j = 0; j < W.blen[i]; ++j) {
+            if (bp) bp[nb] = ((int)W.live[i] << 16) | (int)W.s_tid[W.bundle[i * CBBA_MAX_BUNDLE + j]];
+            ++nb;
+          }
+        }
+        if (MB > 1 && O.d_n_bundle_pairs) O.d_n_bundle_pairs[e] = nb;
       }
     }
     ctrl[0] = n_pairs;

@@ -745,7 +745,8 @@ class CBBAReplan:
     expansion, MT19937 shuffles, bids over insertion points, consensus) runs in the CUDA allocator
     (muav_alloc_opts.planner = 7, csrc/muav_cbba.cuh).  The reference's auction order starts from a set of strings, so its
     result depends on the interpreter's string hash: this class reproduces the reference run under PYTHONHASHSEED=0.
-    Only max_tasks_per_agent = 1 -- what every reference driver passes -- is implemented; anything else raises."""
+    max_tasks_per_agent = 1 is what every reference driver passes; bundles of up to 4 tasks per agent are built by the same
+    auction (CBBA.py:128-147 with a longer bundle); larger values raise."""
 
     def __init__(self, agents=None, tasks=None, max_coord: float = 1000.0, seed: int = 0, replan_interval: int = 20):
         self.max_coord = max_coord
@@ -761,8 +762,8 @@ class CBBAReplan:
                        reserved_agent_names=None, max_tasks_per_agent: int = 1):
         from .batched_env import AllocSpec
 
-        if max_tasks_per_agent != 1:
-            raise NotImplementedError("the device CBBA implements max_tasks_per_agent=1 (the reference drivers' setting)")
+        if not 1 <= int(max_tasks_per_agent) <= 4:
+            raise NotImplementedError("the device CBBA allocator builds bundles of 1..4 tasks per agent")
         self.n_calls += 1
         if not force and not self.should_replan(time_step, events):
             return []
@@ -799,9 +800,18 @@ class CBBAReplan:
             for name, ids in agent_known_ids.items():
                 if name in own and set(ids) != own[name]:
                     raise NotImplementedError("agent_known_ids must be env.agent_visibility_map() (device-resident sets)")
-        spec = AllocSpec(3, self.replan_interval, 0, use_vis, False, float(self.max_coord), planner=7)
+        spec = AllocSpec(3, self.replan_interval, 0, use_vis, False, float(self.max_coord), planner=7,
+                         max_tasks_per_agent=int(max_tasks_per_agent))
         # the device seeds its generator with d_cbba_seed + N_REPLANS of the record (incremented by this call): hand it the
         # difference so that the generator is Random(self.seed + self.n_replans), whatever else replanned on this record
         n_dev = int(env._backend.codec.header(env._backend.record(), "N_REPLANS"))
         pairs = env._backend.allocate(spec, None, None, reserved, order, cbba_seed=self.seed + self.n_replans - (n_dev + 1))
+        if max_tasks_per_agent > 1:   # (name, [tasks in the order they were won]) like the reference (CBBA.py:192-204)
+            out = []
+            for a, tid in env._backend.bundle_pairs():
+                if out and out[-1][0] == env.agents_obj[a].name:
+                    out[-1][1].append(env._task(tid))
+                else:
+                    out.append((env.agents_obj[a].name, [env._task(tid)]))
+            return out
         return [(env.agents_obj[a].name, [env._task(tid)]) for a, tid in pairs]

@@ -112,6 +112,9 @@ def hybrid_should_replan(env, events, interval=15):
             or any(ev[0] in ("Reset_Allocation", "New_Threat", "Agent_Fail") for ev in events))
 
 
+CBBA_DRIVERS = ("cbba_replan", "cbba_coalition", "cbba2_replan", "cbba2_coalition", "cbba3_replan")   # cbba<N>: bundles of N
+
+
 def run_episode(case, seed, driver, overrides=None):
     refshim.install()
     from mUAV_TA.DroneEnv import MultiUAVEnv
@@ -155,13 +158,13 @@ def run_episode(case, seed, driver, overrides=None):
         from TaskAllocation.MarketBased.PerformanceImpact import PerformanceImpact
         planner = PerformanceImpact(max_coord=env.max_coord, seed=seed,
                                     replan_interval=20 if driver in ("local_pi", "local_pi2") else 12)
-    elif driver in ("cbba_replan", "cbba_coalition"):
+    elif driver in CBBA_DRIVERS:
         # Local-CBBA-Replan (wps_eval.py:105,134-146) / Local-CBBA-Coalition (escort_eval.py:108-112,149-161).  CBBA's
         # auction order starts from a set of strings: reproducible only with the string hash pinned
         assert os.environ.get("PYTHONHASHSEED") == "0", "generate the CBBA fixtures with PYTHONHASHSEED=0"
         from TaskAllocation.MarketBased.CBBA_Replan import CBBAReplan
         planner = CBBAReplan(env.agents_obj, env.tasks, env.max_coord, seed=seed,
-                             replan_interval=20 if driver == "cbba_replan" else 12)
+                             replan_interval=12 if driver.endswith("coalition") else 20)
     n_plans = 0
     rnd = random.Random(seed * 7919 + 13)
     ep = {"case": case, "seed": seed, "driver": driver, "overrides": overrides or {},
@@ -186,9 +189,10 @@ def run_episode(case, seed, driver, overrides=None):
                                          agent_known_ids=env.agent_visibility_map(),
                                          max_tasks_per_agent=2 if driver.endswith(("pi2", "pi2_coalition")) else 1)
             pairs = [(name, task) for name, tl in res for task in tl]   # _flatten_pairs (wps_eval.py:40-52)
-        elif driver in ("cbba_replan", "cbba_coalition"):
+        elif driver in CBBA_DRIVERS:
             res = planner.allocate_tasks(env.get_live_agents(), ref_open_tasks(env), time_step=env.time_steps, events=events,
-                                         agent_known_ids=env.agent_visibility_map(), max_tasks_per_agent=1)
+                                         agent_known_ids=env.agent_visibility_map(),
+                                         max_tasks_per_agent=int(driver[4]) if driver[4].isdigit() else 1)
             pairs = [(name, task) for name, tl in res for task in tl]
         elif driver == "pair_injected":
             if hybrid_should_replan(env, events):
@@ -265,7 +269,7 @@ def run_episode(case, seed, driver, overrides=None):
     m = info["metrics"]
     ep["metrics"] = {k: (fhex(v) if isinstance(v, (float, np.floating)) else int(v)) for k, v in m.items()}
     ep["n_replans"] = int(planner.n_replans if driver in ("local_pi", "pi_coalition", "local_pi2", "pi2_coalition",
-                                                          "cbba_replan", "cbba_coalition")
+                                                          ) + CBBA_DRIVERS
                           else hung.n_replans)
     return ep
 
@@ -301,6 +305,10 @@ PLAN = [
     ("wps_hard_cbba", "WPS_hard", "cbba_replan", range(0, 6), None),
     ("wps_commit_cbba", "WPS_commit", "cbba_replan", range(0, 3), None),
     ("wps_escort_cbba", "WPS_escort", "cbba_coalition", range(0, 3), None),
+    ("wps_hard_cbba2", "WPS_hard", "cbba2_replan", range(0, 4), None),
+    ("wps_commit_cbba2", "WPS_commit", "cbba2_replan", range(0, 2), None),
+    ("wps_escort_cbba2", "WPS_escort", "cbba2_coalition", range(0, 2), None),
+    ("wps_hard_cbba3", "WPS_hard", "cbba3_replan", range(4, 6), None),
 ]
 
 

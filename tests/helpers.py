@@ -71,6 +71,18 @@ def assert_tokens_equal_reference(ref_tok, tok, e=None, what=""):
     assert [int(x) for x in ids[:nk]] == ref_tok["task_ids"] and not np.asarray(ids[nk:]).any(), (what, "task_ids")
 
 
+CBBA_DRIVERS = ("cbba_replan", "cbba_coalition", "cbba2_replan", "cbba2_coalition", "cbba3_replan")
+BUNDLE_DRIVERS = ("local_pi2", "pi2_coalition", "cbba2_replan", "cbba2_coalition", "cbba3_replan")
+
+
+def bundle_of(driver):
+    """max_tasks_per_agent of a golden driver name: local_pi2 / pi2_coalition / cbba<N>_* build bundles of N tasks."""
+    for c in driver:
+        if c.isdigit():
+            return int(c)
+    return 1
+
+
 def alloc_opts_for(driver):
     if driver == "context_injected":
         driver = "pair_injected"   # ContextPairHybrid plans exactly like PairCostHybrid (it only adds the context vector)
@@ -85,10 +97,11 @@ def alloc_opts_for(driver):
         O.mode, O.replan_interval, O.event_mask, O.use_visibility = 1, (12 if "coalition" in driver else 20), 0x1F, 1
         O.planner = 6
         O.max_tasks_per_agent = 2 if "pi2" in driver else 1   # the caller points d_bundle_pairs / d_n_bundle_pairs somewhere
-    elif driver in ("cbba_replan", "cbba_coalition"):
+    elif driver in CBBA_DRIVERS:
         # CBBAReplan under the drivers of wps_eval.py:134-146 / escort_eval.py:149-161; the caller sets O.d_cbba_seed
-        O.mode, O.replan_interval, O.event_mask, O.use_visibility = 1, (12 if driver == "cbba_coalition" else 20), 0x1F, 1
+        O.mode, O.replan_interval, O.event_mask, O.use_visibility = 1, (12 if "coalition" in driver else 20), 0x1F, 1
         O.planner = 7
+        O.max_tasks_per_agent = bundle_of(driver)
     elif driver == "pair_injected":
         O.mode = 2
         O.replan_interval = 15
@@ -322,7 +335,7 @@ class HostBackend:
         mb = int(getattr(spec, "max_tasks_per_agent", 1))
         self._bundle = np.zeros((1, A * max(mb, 1)), np.int32)
         self._n_bundle = np.zeros(1, np.int32)
-        if spec.planner == 6 and mb > 1:
+        if spec.planner in (6, 7) and mb > 1:
             O.max_tasks_per_agent = mb
             O.d_bundle_pairs, O.d_n_bundle_pairs = self._bundle.ctypes.data, self._n_bundle.ctypes.data
         npairs = np.zeros(1, np.int32)

@@ -145,8 +145,9 @@ def test_performance_impact_facade_follows_the_reference_loop(case, seed, interv
         mp.allocate_tasks(mine.get_live_agents(), ref_open_tasks(mine), time_step=mine.time_steps, force=True, max_tasks_per_agent=5)
 
 
-@pytest.mark.parametrize("fixture,case,interval", [("wps_hard_cbba", "WPS_hard", 20), ("wps_escort_cbba", "WPS_escort", 12)])
-def test_cbba_replan_facade_reproduces_the_reference_under_hashseed_zero(fixture, case, interval):
+@pytest.mark.parametrize("fixture,case,interval,bundle", [("wps_hard_cbba", "WPS_hard", 20, 1), ("wps_escort_cbba", "WPS_escort", 12, 1),
+                                                          ("wps_hard_cbba2", "WPS_hard", 20, 2), ("wps_escort_cbba2", "WPS_escort", 12, 2)])
+def test_cbba_replan_facade_reproduces_the_reference_under_hashseed_zero(fixture, case, interval, bundle):
     """Local-CBBA-Replan / Local-CBBA-Coalition loop (wps_eval.py:134-146, escort_eval.py:149-161) with the facade's
     CBBAReplan (device allocator, planner 7) on the facade env against the fixture recorded from the unmodified reference
     class in an interpreter started with PYTHONHASHSEED=0 (CBBA's auction order depends on the string hash, so the
@@ -163,7 +164,7 @@ def test_cbba_replan_facade_reproduces_the_reference_under_hashseed_zero(fixture
         for t, st in enumerate(ep["steps"]):
             events = list(mi.get("events") or []) if isinstance(mi, dict) else []
             res = cb.allocate_tasks(mine.get_live_agents(), ref_open_tasks(mine), time_step=mine.time_steps, events=events,
-                                    agent_known_ids=mine.agent_visibility_map(), max_tasks_per_agent=1)
+                                    agent_known_ids=mine.agent_visibility_map(), max_tasks_per_agent=bundle)
             pairs = [[mine.agent_by_name[n].id, t_.id] for n, tl in res for t_ in tl]
             assert pairs == st["pairs"], (seed, t)
             mo, mr, mterm, mtrunc, mi = mine.step(apply_assign(mine, [(n, t_) for n, tl in res for t_ in tl]))
@@ -171,7 +172,7 @@ def test_cbba_replan_facade_reproduces_the_reference_under_hashseed_zero(fixture
         assert cb.n_replans == ep["n_replans"]
         with pytest.raises(NotImplementedError):
             cb.allocate_tasks(mine.get_live_agents(), ref_open_tasks(mine), time_step=mine.time_steps, force=True,
-                              max_tasks_per_agent=2)
+                              max_tasks_per_agent=5)
 
 
 def _load_oracle_from_snapshot(orc, facade_env):

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (assert_tokens_equal_reference, escort_scores_from_logits, golden_config, injected_commit_vectors, injected_logits, injected_scores,
+from helpers import (BUNDLE_DRIVERS, CBBA_DRIVERS, bundle_of, assert_tokens_equal_reference, escort_scores_from_logits, golden_config, injected_commit_vectors, injected_logits, injected_scores,
                      load_golden)
 import refsnap
 
@@ -23,7 +23,7 @@ STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit
 ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
     "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair", "wps_attn_context",
     "wps_hard_pi", "wps_commit_pi", "wps_escort_pi", "wps_hard_cbba", "wps_commit_cbba", "wps_escort_cbba",
-    "wps_hard_pi2", "wps_commit_pi2", "wps_escort_pi2"]
+    "wps_hard_pi2", "wps_commit_pi2", "wps_escort_pi2", "wps_hard_cbba2", "wps_commit_cbba2", "wps_escort_cbba2", "wps_hard_cbba3"]
 
 
 def make_env(cfg, seeds, **kw):
@@ -41,7 +41,9 @@ def spec_for(driver):
             "context_injected": AllocSpec.pair_hybrid(15), "urgency_pair": AllocSpec.urgency_pair(15), "att_commit_injected": AllocSpec.att_commit(15), "att_escort_injected": AllocSpec.att_escort(12),
             "local_pi": AllocSpec.performance_impact(20), "pi_coalition": AllocSpec.performance_impact(12),
             "local_pi2": AllocSpec.performance_impact(20, 2), "pi2_coalition": AllocSpec.performance_impact(12, 2),
-            "cbba_replan": AllocSpec.cbba_replan(20), "cbba_coalition": AllocSpec.cbba_replan(12)}[driver]
+            "cbba_replan": AllocSpec.cbba_replan(20), "cbba_coalition": AllocSpec.cbba_replan(12),
+            "cbba2_replan": AllocSpec.cbba_replan(20, 2), "cbba2_coalition": AllocSpec.cbba_replan(12, 2),
+            "cbba3_replan": AllocSpec.cbba_replan(20, 3)}[driver]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)
@@ -124,7 +126,7 @@ def test_cuda_fused_allocator_matches_reference_golden(name):
         recs = env.records.cpu().numpy()
         for e, ep in enumerate(eps):
             st = ep["steps"][t]
-            if drv in ("local_pi2", "pi2_coalition"):
+            if drv in BUNDLE_DRIVERS:
                 # bundles: the whole plan equals the reference's (name, [tasks]) list; the step used the first task per agent
                 assert env.bundle_pairs_of(e) == st["pairs"], (name, ep["seed"], t)
                 first = []
@@ -136,7 +138,7 @@ def test_cuda_fused_allocator_matches_reference_golden(name):
                 assert env.pairs_of(e) == st["pairs"], (name, ep["seed"], t)
             assert rew[e] == float.fromhex(st["reward"]), (name, ep["seed"], t)
             assert str(refsnap.digest(env.codec.snapshot(recs[e]))) == st["digest"], (name, ep["seed"], t)
-    if drv in ("local_hungarian", "coalition", "global_hungarian", "local_pi", "pi_coalition", "local_pi2", "pi2_coalition"):
+    if drv in ("local_hungarian", "coalition", "global_hungarian", "local_pi", "pi_coalition", "local_pi2", "pi2_coalition") + CBBA_DRIVERS:
         nrep = env.header_int("N_REPLANS").cpu().numpy()
         for e, ep in enumerate(eps):
             assert int(nrep[e]) == ep["n_replans"]

@@ -4,7 +4,7 @@ repeats these checks through the C ABI on the device."""
 import numpy as np
 import pytest
 
-from helpers import (alloc_opts_for, assert_tokens_equal_reference, escort_scores_from_logits, golden_config, injected_commit_vectors, injected_logits,
+from helpers import (BUNDLE_DRIVERS, CBBA_DRIVERS, bundle_of, alloc_opts_for, assert_tokens_equal_reference, escort_scores_from_logits, golden_config, injected_commit_vectors, injected_logits,
                      injected_scores, load_golden)
 
 STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit_local", "wps_escort_coalition",
@@ -14,7 +14,7 @@ STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit
 ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
     "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair", "wps_attn_context",
     "wps_hard_pi", "wps_commit_pi", "wps_escort_pi", "wps_hard_cbba", "wps_commit_cbba", "wps_escort_cbba",
-    "wps_hard_pi2", "wps_commit_pi2", "wps_escort_pi2"]
+    "wps_hard_pi2", "wps_commit_pi2", "wps_escort_pi2", "wps_hard_cbba2", "wps_commit_cbba2", "wps_escort_cbba2", "wps_hard_cbba3"]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)
@@ -41,13 +41,13 @@ def test_fused_allocator(hostcheck, name):
     drv = eps[0]["driver"]
     env = hostcheck.make(golden_config(eps[0]), [ep["seed"] for ep in eps])
     O = alloc_opts_for(drv)
-    if drv in ("cbba_replan", "cbba_coalition"):
+    if drv in CBBA_DRIVERS:
         cbba_seeds = np.array([ep["seed"] for ep in eps], np.int32)
         O.d_cbba_seed = cbba_seeds.ctypes.data
-    bundles = drv in ("local_pi2", "pi2_coalition")
+    bundles = drv in BUNDLE_DRIVERS
     if bundles:   # the whole plan (every path entry) next to the step's first-task pairs
         A = len(eps[0]["agent_names"])
-        bp = np.zeros((len(eps), A * 2), np.int32)
+        bp = np.zeros((len(eps), A * bundle_of(drv)), np.int32)
         nbp = np.zeros(len(eps), np.int32)
         O.d_bundle_pairs, O.d_n_bundle_pairs = bp.ctypes.data, nbp.ctypes.data
     for t in range(len(eps[0]["steps"])):
@@ -97,7 +97,7 @@ def test_fused_allocator(hostcheck, name):
             assert env.reward[e] == float.fromhex(st["reward"])
             assert str(env.digest(e)) == st["digest"], (name, ep["seed"], t)
     if drv in ("local_hungarian", "coalition", "global_hungarian", "local_pi", "pi_coalition", "cbba_replan", "cbba_coalition",
-               "local_pi2", "pi2_coalition"):
+               "local_pi2", "pi2_coalition") + CBBA_DRIVERS:
         for e, ep in enumerate(eps):
             assert env.codec.header(env.rec[e], "N_REPLANS") == ep["n_replans"]
 

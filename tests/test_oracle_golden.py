@@ -5,7 +5,7 @@ import pytest
 
 import numpy as np
 
-from helpers import (assert_tokens_equal_reference, escort_scores_from_logits, injected_commit_vectors, injected_logits, injected_scores, load_golden,
+from helpers import (BUNDLE_DRIVERS, CBBA_DRIVERS, bundle_of, assert_tokens_equal_reference, escort_scores_from_logits, injected_commit_vectors, injected_logits, injected_scores, load_golden,
                      golden_config)
 import refsnap
 from oracle.hungarian import OracleHungarian, apply_assign, open_tasks
@@ -25,6 +25,7 @@ CASES = [
     ("wps_hard_pi", 4), ("wps_commit_pi", 2), ("wps_escort_pi", 2),
     ("wps_hard_cbba", 6), ("wps_commit_cbba", 3), ("wps_escort_cbba", 3),
     ("wps_hard_pi2", 6), ("wps_commit_pi2", 3), ("wps_escort_pi2", 3),
+    ("wps_hard_cbba2", 4), ("wps_commit_cbba2", 2), ("wps_escort_cbba2", 2), ("wps_hard_cbba3", 2),
 ]
 
 
@@ -36,7 +37,7 @@ def replay(ep):
     interval = 12 if drv == "coalition" else (10**9 if drv in ("urgency_coalition", "att_escort_injected") else 20)
     hung = OracleHungarian(interval, o.max_coord)
     pi = OraclePI(o.max_coord, ep["seed"], 12 if drv in ("pi_coalition", "pi2_coalition") else 20)
-    cbba = OracleCBBAReplan(o.max_coord, ep["seed"], 12 if drv == "cbba_coalition" else 20)
+    cbba = OracleCBBAReplan(o.max_coord, ep["seed"], 12 if drv.endswith("coalition") else 20)
     for t, st in enumerate(ep["steps"]):
         if drv in ("local_hungarian", "coalition", "global_hungarian"):
             known = None if drv == "global_hungarian" else o.visibility()
@@ -48,8 +49,9 @@ def replay(ep):
                                 max_tasks_per_agent=2 if drv.endswith(("pi2", "pi2_coalition")) else 1)
             assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
             assert [list(a) for a in apply_assign(o, pairs)] == st["actions"], (ep["seed"], t)
-        elif drv in ("cbba_replan", "cbba_coalition"):
-            pairs = cbba.allocate(o, time_step=o.t, events=o.last_events, known=o.visibility())
+        elif drv in CBBA_DRIVERS:
+            pairs = cbba.allocate(o, time_step=o.t, events=o.last_events, known=o.visibility(),
+                                  max_tasks_per_agent=bundle_of(drv))
             assert [list(p) for p in pairs] == st["pairs"], (ep["seed"], t)
             assert [list(a) for a in apply_assign(o, pairs)] == st["actions"], (ep["seed"], t)
         elif drv in ("pair_injected", "context_injected"):
@@ -110,7 +112,7 @@ def replay(ep):
         assert m[k] == want or (m[k] != m[k] and want != want), k
     if drv in ("local_hungarian", "coalition", "global_hungarian"):
         assert hung.n_replans == ep["n_replans"]
-    if drv in ("cbba_replan", "cbba_coalition"):
+    if drv in CBBA_DRIVERS:
         assert cbba.n_replans == ep["n_replans"]
     if drv in ("local_pi", "pi_coalition", "local_pi2", "pi2_coalition"):
         assert pi.n_replans == ep["n_replans"]
