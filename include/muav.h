@@ -110,7 +110,7 @@ typedef struct muav_alloc_opts {
                               6 PerformanceImpact.allocate_tasks (max_tasks_per_agent below) (MarketBased/PerformanceImpact.py:59-224,
                                 slots and eligibility from MarketBased/CBBA.py:27-65) instead of the Hungarian allocator:
                                 mode / replan_interval / event_mask / use_visibility / d_reserved as for planner 0;
-                              7 CBBAReplan.allocate_tasks(max_tasks_per_agent=1) (MarketBased/CBBA_Replan.py:15-69 around
+                              7 CBBAReplan.allocate_tasks (max_tasks_per_agent below) (MarketBased/CBBA_Replan.py:15-69 around
                                 MarketBased/CBBA.py:68-324; a fresh CBBA(seed + n_replans) per replan, seed = d_cbba_seed[env]):
                                 same options as planner 6.  Bit-exact with the reference run under PYTHONHASHSEED=0 (its
                                 auction order starts from a set of strings, see csrc/muav_cbba.cuh) */
@@ -129,14 +129,15 @@ typedef struct muav_alloc_opts {
   const float* d_plan_commit;  /* planner 3: [E, score_rows] AttCommitNet commit gates by live-agent row */
   double commit_threshold;     /* planner 3: AttentionCommit(commit_threshold=0.5) */
   const int32_t* d_cbba_seed;  /* planner 7: [E] the `seed` argument of CBBAReplan (the drivers pass the episode seed) or NULL = 0 */
-  int32_t max_tasks_per_agent; /* planner 6: 0 / 1 = one task per agent (what the reference drivers pass); 2..4 = bundles
-                                  (the full inclusion phase of PerformanceImpact.py:106-165 over agent paths with insertion
-                                  points, consensus clean-up :168-205).  The step takes the FIRST task of every path
+  int32_t max_tasks_per_agent; /* planners 6 and 7: 0 / 1 = one task per agent (what the reference drivers pass); 2..4 = bundles
+                                  (planner 6: the full inclusion phase of PerformanceImpact.py:106-165 over agent paths with insertion
+                                  points, consensus clean-up :168-205; planner 7: CBBA.py:128-190 with bundles of that
+                                  length, listed in the order the slots were won).  The step takes the FIRST task of every path
                                   (_apply_assign, wps_eval.py:55-61); the whole plan goes to d_bundle_pairs */
   int32_t reserved0;
-  int32_t* d_bundle_pairs;     /* planner 6 with bundles, optional: [E, n_agents * max_tasks_per_agent] (agent id << 16) | task
-                                  id of every path entry in the order allocate_tasks returns them (agents ascending, path
-                                  order) */
+  int32_t* d_bundle_pairs;     /* planners 6 / 7 with bundles, optional: [E, n_agents * max_tasks_per_agent] (agent id << 16) | task
+                                  id of every path / bundle entry in the order allocate_tasks returns them (planner 6: agents
+                                  ascending, path order; planner 7: live-agent order, bundle order, CBBA.py:192-204) */
   int32_t* d_n_bundle_pairs;   /* [E] number of entries written to d_bundle_pairs (0 when the call did not replan) */
 } muav_alloc_opts;
 
