@@ -258,7 +258,7 @@ class _CudaBackend:
 class MultiUAVEnv:
     metadata = {"render_modes": ["human"], "name": "multi_agent_env_v0"}
 
-    def __init__(self, config=None, device="cuda:0", _test_backend_factory=None):
+    def __init__(self, config=None, device="cuda:0"):
         self.config = config if config is not None else agentEnvOptions()
         cfg = self.config
         g = lambda n, d=None: getattr(cfg, n, d)
@@ -312,14 +312,17 @@ class MultiUAVEnv:
         self.event_list = []
         self._tasks_by_id = {}
         self._obs_cache = None
-        if _test_backend_factory is not None:
-            self._backend = _test_backend_factory(cfg)
-        else:
-            self._backend = _CudaBackend(cfg, device)  # raises without the CUDA library / a GPU: no CPU fallback
+        self._backend = self._make_backend(cfg, device)
         self.rewards = {a: 0 for a in self.possible_agents}
         self.terminations = {a: False for a in self.possible_agents}
         self.truncations = {a: False for a in self.possible_agents}
         self.infos = {a: {} for a in self.possible_agents}
+
+    def _make_backend(self, cfg, device):
+        """The state holder behind the facade: the CUDA library on `device`.  Raises without libmuav_b200.so or a GPU --
+        there is no CPU fallback in the product (tests/helpers.py subclasses the facade over the CPU build of the kernel
+        sources to run the unmodified reference planners side by side in the GPU-less container)."""
+        return _CudaBackend(cfg, device)
 
     # ---- spaces (the reference's declared spaces do not match its emitted observations; kept as shapes)
     def observation_space(self, agent):

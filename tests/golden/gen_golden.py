@@ -112,7 +112,7 @@ def hybrid_should_replan(env, events, interval=15):
             or any(ev[0] in ("Reset_Allocation", "New_Threat", "Agent_Fail") for ev in events))
 
 
-CBBA_DRIVERS = ("cbba_replan", "cbba_coalition", "cbba2_replan", "cbba2_coalition", "cbba3_replan")   # cbba<N>: bundles of N
+CBBA_DRIVERS = ("cbba_replan", "cbba_coalition", "cbba2_replan", "cbba2_coalition", "cbba3_replan", "cbba4_replan")   # cbba<N>: bundles of N
 
 
 def run_episode(case, seed, driver, overrides=None):
@@ -309,6 +309,7 @@ PLAN = [
     ("wps_commit_cbba2", "WPS_commit", "cbba2_replan", range(0, 2), None),
     ("wps_escort_cbba2", "WPS_escort", "cbba2_coalition", range(0, 2), None),
     ("wps_hard_cbba3", "WPS_hard", "cbba3_replan", range(4, 6), None),
+    ("wps_commit_cbba4", "WPS_commit", "cbba4_replan", range(2, 3), None),
 ]
 
 

@@ -16,12 +16,12 @@ sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
 
-def replay_digest(scenario, seed, backend_factory=None):
+def replay_digest(scenario, seed, env_factory=None):
     from multi_uav_ta_gym_env_b200 import replay, wps_config
     from multi_uav_ta_gym_env_b200.env import HungarianAllocator, MultiUAVEnv
 
     cfg = wps_config(scenario)
-    env = MultiUAVEnv(cfg, _test_backend_factory=backend_factory) if backend_factory else MultiUAVEnv(cfg)
+    env = env_factory(cfg) if env_factory else MultiUAVEnv(cfg)
     _, info = env.reset(seed=seed)
     hung = HungarianAllocator(10**9, env.max_coord)
 
@@ -46,9 +46,9 @@ def _residual(t):
 CASES = [("WPS_commit", 2), ("WPS_escort", 3)]
 
 if __name__ == "__main__":
-    from helpers import HostBackend
+    from helpers import host_facade
 
-    out = {f"{s}:{seed}": replay_digest(s, seed, lambda c: HostBackend(c)) for s, seed in CASES}
+    out = {f"{s}:{seed}": replay_digest(s, seed, host_facade) for s, seed in CASES}
     with open(os.path.join(HERE, "replay_digests.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(out)

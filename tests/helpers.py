@@ -71,8 +71,8 @@ def assert_tokens_equal_reference(ref_tok, tok, e=None, what=""):
     assert [int(x) for x in ids[:nk]] == ref_tok["task_ids"] and not np.asarray(ids[nk:]).any(), (what, "task_ids")
 
 
-CBBA_DRIVERS = ("cbba_replan", "cbba_coalition", "cbba2_replan", "cbba2_coalition", "cbba3_replan")
-BUNDLE_DRIVERS = ("local_pi2", "pi2_coalition", "cbba2_replan", "cbba2_coalition", "cbba3_replan")
+CBBA_DRIVERS = ("cbba_replan", "cbba_coalition", "cbba2_replan", "cbba2_coalition", "cbba3_replan", "cbba4_replan")
+BUNDLE_DRIVERS = ("local_pi2", "pi2_coalition", "cbba2_replan", "cbba2_coalition", "cbba3_replan", "cbba4_replan")
 
 
 def bundle_of(driver):
@@ -385,3 +385,15 @@ class HostBackend:
 
     def patch_field(self, name, index, value):
         self.codec.field(self.rec[0], name)[index] = value
+
+
+def host_facade(cfg, **kw):
+    """multi_uav_ta_gym_env_b200.env.MultiUAVEnv over the CPU build of the kernel sources (HostBackend): a test-side
+    subclass overriding the facade's backend hook; the product class itself only ever builds the CUDA backend."""
+    from multi_uav_ta_gym_env_b200.env import MultiUAVEnv
+
+    class HostMultiUAVEnv(MultiUAVEnv):
+        def _make_backend(self, c, device):
+            return HostBackend(c, **kw)
+
+    return HostMultiUAVEnv(cfg)

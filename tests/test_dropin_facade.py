@@ -10,7 +10,7 @@ import pytest
 
 import refshim
 import refsnap
-from helpers import HostBackend, injected_scores
+from helpers import host_facade, injected_scores
 
 pytestmark = pytest.mark.skipif(not refshim.reference_available(), reason="reference tree not present")
 
@@ -27,7 +27,7 @@ def make_pair(case, seed, **over):
     ref_obs, ref_info = ref.reset(seed=seed)
     from multi_uav_ta_gym_env_b200 import wps_config
 
-    mine = MultiUAVEnv(wps_config(case, **over), _test_backend_factory=lambda c: HostBackend(c))
+    mine = host_facade(wps_config(case, **over))
     my_obs, my_info = mine.reset(seed=seed)
     return ref, ref_obs, ref_info, mine, my_obs, my_info
 
@@ -108,7 +108,7 @@ def test_env_and_allocator_facade_follow_the_reference_loop(case, seed, interval
 
 
 @pytest.mark.parametrize("case,seed,interval,bundle", [("WPS_hard", 5, 20, 1), ("WPS_escort", 2, 12, 1), ("WPS_hard", 7, 20, 2),
-                                                       ("WPS_commit", 3, 20, 3), ("WPS_escort", 4, 12, 2)])
+                                                       ("WPS_commit", 3, 20, 3), ("WPS_escort", 4, 12, 2), ("WPS_commit", 1, 20, 4)])
 def test_performance_impact_facade_follows_the_reference_loop(case, seed, interval, bundle):
     """Local-PI / Local-PI-Coalition loop (wps_eval.py:147-159, escort_eval.py:162-174): the reference PerformanceImpact on the
     reference env vs the facade class (device allocator, planner 6) on the facade env, every step; also with bundles of two
@@ -146,7 +146,8 @@ def test_performance_impact_facade_follows_the_reference_loop(case, seed, interv
 
 
 @pytest.mark.parametrize("fixture,case,interval,bundle", [("wps_hard_cbba", "WPS_hard", 20, 1), ("wps_escort_cbba", "WPS_escort", 12, 1),
-                                                          ("wps_hard_cbba2", "WPS_hard", 20, 2), ("wps_escort_cbba2", "WPS_escort", 12, 2)])
+                                                          ("wps_hard_cbba2", "WPS_hard", 20, 2), ("wps_escort_cbba2", "WPS_escort", 12, 2),
+                                                          ("wps_hard_cbba3", "WPS_hard", 20, 3), ("wps_commit_cbba4", "WPS_commit", 20, 4)])
 def test_cbba_replan_facade_reproduces_the_reference_under_hashseed_zero(fixture, case, interval, bundle):
     """Local-CBBA-Replan / Local-CBBA-Coalition loop (wps_eval.py:134-146, escort_eval.py:149-161) with the facade's
     CBBAReplan (device allocator, planner 7) on the facade env against the fixture recorded from the unmodified reference
@@ -158,7 +159,7 @@ def test_cbba_replan_facade_reproduces_the_reference_under_hashseed_zero(fixture
 
     for ep in load_golden(fixture)[:2]:
         seed = ep["seed"]
-        mine = MultiUAVEnv(wps_config(case), _test_backend_factory=lambda c: HostBackend(c))
+        mine = host_facade(wps_config(case))
         mo, mi = mine.reset(seed=seed)
         cb = CBBAReplan(mine.agents_obj, mine.tasks, mine.max_coord, seed=seed, replan_interval=interval)
         for t, st in enumerate(ep["steps"]):
@@ -345,7 +346,7 @@ def test_replay_documents_are_identical(scenario, tmp_path):
     G = _replay_stubs()
     want = G.generate(1, tmp_path / "ref.json", scenario=scenario)
     RefEnv = G.MultiUAVEnv
-    G.MultiUAVEnv = lambda cfg: MultiUAVEnv(cfg, _test_backend_factory=lambda c: HostBackend(c))
+    G.MultiUAVEnv = host_facade
     try:
         got = G.generate(1, tmp_path / "mine.json", scenario=scenario)
     finally:
@@ -360,7 +361,7 @@ def test_replay_documents_are_identical(scenario, tmp_path):
     from multi_uav_ta_gym_env_b200 import wps_config
 
     cfg = wps_config(scenario)
-    env = MultiUAVEnv(cfg, _test_backend_factory=lambda c: HostBackend(c))
+    env = host_facade(cfg)
     _, info = env.reset(seed=1)
     hung = RefHung(10**9, env.max_coord)
     if scenario == "WPS_escort":

@@ -23,7 +23,7 @@ STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit
 ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
     "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair", "wps_attn_context",
     "wps_hard_pi", "wps_commit_pi", "wps_escort_pi", "wps_hard_cbba", "wps_commit_cbba", "wps_escort_cbba",
-    "wps_hard_pi2", "wps_commit_pi2", "wps_escort_pi2", "wps_hard_cbba2", "wps_commit_cbba2", "wps_escort_cbba2", "wps_hard_cbba3"]
+    "wps_hard_pi2", "wps_commit_pi2", "wps_escort_pi2", "wps_hard_cbba2", "wps_commit_cbba2", "wps_escort_cbba2", "wps_hard_cbba3", "wps_commit_cbba4"]
 
 
 def make_env(cfg, seeds, **kw):
@@ -43,7 +43,7 @@ def spec_for(driver):
             "local_pi2": AllocSpec.performance_impact(20, 2), "pi2_coalition": AllocSpec.performance_impact(12, 2),
             "cbba_replan": AllocSpec.cbba_replan(20), "cbba_coalition": AllocSpec.cbba_replan(12),
             "cbba2_replan": AllocSpec.cbba_replan(20, 2), "cbba2_coalition": AllocSpec.cbba_replan(12, 2),
-            "cbba3_replan": AllocSpec.cbba_replan(20, 3)}[driver]
+            "cbba3_replan": AllocSpec.cbba_replan(20, 3), "cbba4_replan": AllocSpec.cbba_replan(20, 4)}[driver]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)

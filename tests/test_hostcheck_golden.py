@@ -14,7 +14,7 @@ STEP_CASES = ["wps_easy_local", "wps_hard_local", "wps_burst_local", "wps_commit
 ALLOC_CASES = [c for c in STEP_CASES if "random" not in c and "obstacles" not in c] + [
     "wps_commit_urgency", "wps_escort_urgency", "wps_commit_attcommit", "wps_escort_attescort", "wps_hard_urgency_pair", "wps_attn_context",
     "wps_hard_pi", "wps_commit_pi", "wps_escort_pi", "wps_hard_cbba", "wps_commit_cbba", "wps_escort_cbba",
-    "wps_hard_pi2", "wps_commit_pi2", "wps_escort_pi2", "wps_hard_cbba2", "wps_commit_cbba2", "wps_escort_cbba2", "wps_hard_cbba3"]
+    "wps_hard_pi2", "wps_commit_pi2", "wps_escort_pi2", "wps_hard_cbba2", "wps_commit_cbba2", "wps_escort_cbba2", "wps_hard_cbba3", "wps_commit_cbba4"]
 
 
 @pytest.mark.parametrize("name", STEP_CASES)

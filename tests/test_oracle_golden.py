@@ -25,7 +25,7 @@ CASES = [
     ("wps_hard_pi", 4), ("wps_commit_pi", 2), ("wps_escort_pi", 2),
     ("wps_hard_cbba", 6), ("wps_commit_cbba", 3), ("wps_escort_cbba", 3),
     ("wps_hard_pi2", 6), ("wps_commit_pi2", 3), ("wps_escort_pi2", 3),
-    ("wps_hard_cbba2", 4), ("wps_commit_cbba2", 2), ("wps_escort_cbba2", 2), ("wps_hard_cbba3", 2),
+    ("wps_hard_cbba2", 4), ("wps_commit_cbba2", 2), ("wps_escort_cbba2", 2), ("wps_hard_cbba3", 2), ("wps_commit_cbba4", 1),
 ]
 
 
