@@ -12,6 +12,7 @@ reference (experiments/wps_eval.py:55-61).
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import random
 import sys
@@ -583,6 +584,36 @@ def raw_env(config=None):
 
 
 # --------------------------------------------------------------------------- allocator
+@contextlib.contextmanager
+def _known_override(env, agent_known_ids):
+    """`agent_known_ids` of an allocator call (HungarianAllocator.py:125-147, CBBA.py:115-134, PerformanceImpact.py:94-123:
+    agent name -> set of task ids, a name missing from the map knows nothing).  The device allocator filters by the
+    known-task bitmask of the record; when the caller's map is not the environment's own (env.agent_visibility_map()),
+    the differing mask words are written into the record for the duration of the call and put back afterwards."""
+    own = env.agent_visibility_map() or {}
+    if agent_known_ids is None or all(set(agent_known_ids.get(n, ())) == ids for n, ids in own.items()):
+        yield
+        return
+    be = env._backend
+    n_agents = len(env.agents_obj)
+    old = np.array(be.codec.field(be.record(), "known"), dtype=np.uint32)
+    n_words = old.size // n_agents          # layout [word, agent], bit k of word k >> 5 = task id k + 1
+    new = np.zeros_like(old)
+    for a in env.agents_obj:
+        for tid in agent_known_ids.get(a.name, ()):
+            k = int(tid) - 1
+            if 0 <= k < 32 * n_words:
+                new[(k >> 5) * n_agents + a.id] |= np.uint32(1 << (k & 31))
+    changed = [i for i in range(old.size) if new[i] != old[i]]
+    for i in changed:
+        be.patch_field("known", i, int(new[i]))
+    try:
+        yield
+    finally:
+        for i in changed:
+            be.patch_field("known", i, int(old[i]))
+
+
 class HungarianAllocator:
     """Same constructor, attributes and allocate_tasks signature as the reference class; the cost matrix,
     the LSAP rounds and the acceptance rule run in the CUDA allocator (muav_allocate)."""
@@ -637,11 +668,6 @@ class HungarianAllocator:
                 order[n_ord] = t.id - 1
                 n_ord += 1
         use_vis = agent_known_ids is not None
-        if use_vis:
-            own = env.agent_visibility_map() or {}
-            for name, ids in agent_known_ids.items():
-                if name in own and set(ids) != own[name]:
-                    raise NotImplementedError("agent_known_ids must be env.agent_visibility_map() (device-resident sets)")
         pri = None
         if task_priorities:
             pri = np.zeros(TC, dtype=np.float64)
@@ -657,7 +683,8 @@ class HungarianAllocator:
                     scores[by_name[name].id, int(tid) - 1] = float(v)
         spec = AllocSpec(3, self.replan_interval, 0, use_vis, False, float(self.max_coord))
         before = env._backend.codec.header(env._backend.record(), "N_REPLANS")
-        pairs = env._backend.allocate(spec, scores, pri, reserved, order)
+        with _known_override(env, agent_known_ids):
+            pairs = env._backend.allocate(spec, scores, pri, reserved, order)
         after = env._backend.codec.header(env._backend.record(), "N_REPLANS")
         if after == before:
             return []  # no live agent or no open task: the reference returns before touching its counters
@@ -723,14 +750,10 @@ class PerformanceImpact:
                 order[n_ord] = t.id - 1
                 n_ord += 1
         use_vis = agent_known_ids is not None
-        if use_vis:
-            own = env.agent_visibility_map() or {}
-            for name, ids in agent_known_ids.items():
-                if name in own and set(ids) != own[name]:
-                    raise NotImplementedError("agent_known_ids must be env.agent_visibility_map() (device-resident sets)")
         spec = AllocSpec(3, self.replan_interval, 0, use_vis, False, float(self.max_coord), planner=6,
                          max_tasks_per_agent=int(max_tasks_per_agent))
-        pairs = env._backend.allocate(spec, None, None, reserved, order)
+        with _known_override(env, agent_known_ids):
+            pairs = env._backend.allocate(spec, None, None, reserved, order)
         if max_tasks_per_agent > 1:   # (name, [tasks in path order]) like the reference (PerformanceImpact.py:207-220)
             out = []
             for a, tid in env._backend.bundle_pairs():
@@ -798,17 +821,13 @@ class CBBAReplan:
                 order[n_ord] = t.id - 1
                 n_ord += 1
         use_vis = agent_known_ids is not None
-        if use_vis:
-            own = env.agent_visibility_map() or {}
-            for name, ids in agent_known_ids.items():
-                if name in own and set(ids) != own[name]:
-                    raise NotImplementedError("agent_known_ids must be env.agent_visibility_map() (device-resident sets)")
         spec = AllocSpec(3, self.replan_interval, 0, use_vis, False, float(self.max_coord), planner=7,
                          max_tasks_per_agent=int(max_tasks_per_agent))
         # the device seeds its generator with d_cbba_seed + N_REPLANS of the record (incremented by this call): hand it the
         # difference so that the generator is Random(self.seed + self.n_replans), whatever else replanned on this record
         n_dev = int(env._backend.codec.header(env._backend.record(), "N_REPLANS"))
-        pairs = env._backend.allocate(spec, None, None, reserved, order, cbba_seed=self.seed + self.n_replans - (n_dev + 1))
+        with _known_override(env, agent_known_ids):
+            pairs = env._backend.allocate(spec, None, None, reserved, order, cbba_seed=self.seed + self.n_replans - (n_dev + 1))
         if max_tasks_per_agent > 1:   # (name, [tasks in the order they were won]) like the reference (CBBA.py:192-204)
             out = []
             for a, tid in env._backend.bundle_pairs():

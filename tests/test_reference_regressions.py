@@ -166,6 +166,21 @@ def scenario_coalition_two_slot_and_legacy(env, info, classes):
     log["single"] = [(n, t.id) for n, t in single]
 
     def on_step(phase, result, events):
+        if phase == "step" and "synthetic" not in log:
+            # test_escort.py:90-105: three fighters offered one escort with edge scores 1.0 -> at least two assignments;
+            # here additionally with a caller-made visibility map in which the third fighter does not know the escort
+            escorts = [t for t in env.tasks if getattr(t, "kind", None) == "Escort" and t.status != 2 and t.required_agents >= 2]
+            fighters = [a for a in env.get_live_agents() if a.type in ("F1", "F2")][:3]
+            if escorts and len(fighters) == 3:
+                escort = escorts[0]
+                hung = classes[0](replan_interval=1, max_coord=env.max_coord)
+                scores = {(f.name, escort.id): 1.0 for f in fighters}
+                both = hung.allocate_tasks(fighters, [escort], time_step=env.time_steps, force=True, edge_scores=scores)
+                two = hung.allocate_tasks(fighters, [escort], time_step=env.time_steps, force=True, edge_scores=scores,
+                                          agent_known_ids={f.name: {escort.id} for f in fighters[:2]})
+                assert len(both) >= 2, f"expected >=2 escort assigns, got {both}"
+                assert all(n != fighters[2].name for n, _ in two)
+                log["synthetic"] = (env.time_steps, [(n, t.id) for n, t in both], [(n, t.id) for n, t in two])
         if phase != "plan" or not result:
             return
         log["plans"] += 1
@@ -184,6 +199,7 @@ def scenario_coalition_two_slot_and_legacy(env, info, classes):
 
     coalition_rollout(env, info, classes, on_step=on_step)
     assert log["two_slot_calls"] >= 1, "expected an escort taken by >= 2 fighters in one call"
+    assert "synthetic" in log
     return log
 
 
@@ -210,7 +226,7 @@ def scenario_threat_diversion_inputs(env, info, classes):
     return log
 
 
-def market_rollout(env, info, planner, steps, log):
+def market_rollout(env, info, planner, steps, log, make_probe):
     """Local-PI-Coalition / Local-CBBA-Coalition loop (experiments/escort_eval.py:149-174) with the reference test's
     assertions on every plan: visibility, eligibility, the recon never escorts, one task per agent."""
     for _ in range(steps):
@@ -232,6 +248,23 @@ def market_rollout(env, info, planner, steps, log):
         if assigned:
             log["plans"].append([(n, t.id) for n, t in assigned])
             assert to_actions(env, assigned), "expected convertible actions"
+        if "restricted" not in log:
+            # test_escort.py:160-176: only the first two fighters know the escort -> nobody else may be assigned to it
+            # (a caller-made agent_known_ids map, not the environment's own; a name missing from the map knows nothing)
+            escorts = [t for t in env.tasks if getattr(t, "kind", None) == "Escort" and t.status != 2]
+            fighters = [a for a in env.get_live_agents() if a.type in ("F1", "F2")]
+            if escorts and len(fighters) >= 3:
+                escort = escorts[0]
+                only = {f.name: set() for f in fighters[1:]}
+                only[fighters[1].name].add(escort.id)
+                only[fighters[2].name].add(escort.id)
+                probe = make_probe()
+                res = probe.allocate_tasks(fighters, [escort], time_step=env.time_steps, force=True, agent_known_ids=only,
+                                           max_tasks_per_agent=1)
+                got = [(n, t.id) for n, ts in res for t in ts]
+                assert all(n in (fighters[1].name, fighters[2].name) and tid == escort.id for n, tid in got), got
+                log["restricted"] = (env.time_steps, escort.id, sorted(got))
+                assert env.agent_visibility_map() == known   # the environment's own sets are back in place
         _, _, done, trunc, info = env.step(to_actions(env, assigned))
         if all(done.values()) or all(trunc.values()):
             break
@@ -242,7 +275,8 @@ def scenario_pi_coalition_eligibility_visibility(env, info, classes):
     """test_cbba_pi_coalition_eligibility_visibility (test_escort.py:141-241), Performance-Impact half."""
     pi = classes[1](max_coord=env.max_coord, seed=3, replan_interval=12)
     log = {"escort_assigns": 0, "plans": []}
-    market_rollout(env, info, pi, 100, log)
+    market_rollout(env, info, pi, 100, log, lambda: classes[1](max_coord=env.max_coord, seed=3, replan_interval=1))
+    assert len(log["restricted"][2]) >= 1
     assert log["escort_assigns"] >= 2
     assert pi.should_replan(10, [["Escort_Created", 7]]) and pi.should_replan(10, [["Escort_Retired", 7]])
     return log
@@ -253,7 +287,8 @@ def scenario_cbba_coalition_eligibility_visibility(env, info, classes):
     the interpreter's string hash in the reference (CBBA.py:116,128), so only the properties are compared."""
     rp = classes[2](env.agents_obj, env.tasks, env.max_coord, seed=0, replan_interval=12)
     log = {"escort_assigns": 0, "plans": []}
-    market_rollout(env, info, rp, 60, log)
+    market_rollout(env, info, rp, 60, log, lambda: classes[2](env.agents_obj, env.tasks, env.max_coord, seed=1, replan_interval=1))
+    assert len(log["restricted"][2]) >= 1
     assert log["escort_assigns"] >= 2
     far = classes[2](env.agents_obj, env.tasks, env.max_coord, seed=0, replan_interval=1000)
     far.last_plan_step = 0
