@@ -138,3 +138,49 @@ def test_other_registered_scenarios_match_the_oracle(hostcheck, case):
             o.step(apply_assign(o, pairs))
             assert env.err(e) == 0
             assert refsnap.digest(env.snapshot(e)) == refsnap.digest(o.snapshot()), (case, seeds[e], t)
+
+
+@pytest.mark.parametrize("case,market,bundle,interval", [
+    ("WPS_hard", "pi", 3, 20), ("WPS_commit", "pi", 4, 20), ("WPS_escort", "pi", 4, 12),
+    ("WPS_hard", "cbba", 4, 20), ("WPS_commit", "cbba", 3, 20), ("WPS_escort", "cbba", 3, 12), ("WPS_escort", "cbba", 4, 12)])
+def test_market_bundles_match_the_oracle_on_fresh_seeds(hostcheck, case, market, bundle, interval):
+    """Bundles of three and four tasks per agent (the goldens hold twelve PI episodes with two and eleven CBBA episodes
+    with two to four) on seeds outside the fixtures: kernel core vs the oracle that the goldens pin, whole plan (every
+    bundle entry in the order allocate_tasks returns it) and state digest at every step."""
+    from multi_uav_ta_gym_env_b200 import wps_config
+    from oracle.cbba import OracleCBBAReplan
+    from oracle.hungarian import apply_assign
+    from oracle.market import OraclePI
+    from oracle.sim import OracleEnv
+    import refsnap
+
+    cfg = wps_config(case)
+    seeds = [2000 + 7 * bundle, 2001 + 7 * bundle, 2002 + 7 * bundle]
+    env = hostcheck.make(cfg, seeds)
+    O = alloc_opts_for("cbba_replan" if market == "cbba" else "local_pi")
+    O.replan_interval = interval
+    O.max_tasks_per_agent = bundle
+    cbba_seeds = np.array(seeds, np.int32)
+    O.d_cbba_seed = cbba_seeds.ctypes.data
+    A = sum(cfg.agents.values())
+    bp = np.zeros((len(seeds), A * bundle), np.int32)
+    nbp = np.zeros(len(seeds), np.int32)
+    O.d_bundle_pairs, O.d_n_bundle_pairs = bp.ctypes.data, nbp.ctypes.data
+    oracles = [OracleEnv(cfg).reset(s) for s in seeds]
+    planners = [OracleCBBAReplan(o.max_coord, s, interval) if market == "cbba" else OraclePI(o.max_coord, s, interval)
+                for o, s in zip(oracles, seeds)]
+    longest = 0
+    for t in range(150):
+        env.step_alloc(O)
+        for e, o in enumerate(oracles):
+            pairs = planners[e].allocate(o, time_step=o.t, events=o.last_events, known=o.visibility(), max_tasks_per_agent=bundle)
+            got = [[int(v) >> 16, int(v) & 0xFFFF] for v in bp[e, : nbp[e]]]
+            assert got == [list(p) for p in pairs], (case, market, seeds[e], t)
+            for a in {p[0] for p in pairs}:
+                longest = max(longest, sum(1 for p in pairs if p[0] == a))
+            o.step(apply_assign(o, pairs))
+            assert env.err(e) == 0
+            assert refsnap.digest(env.snapshot(e)) == refsnap.digest(o.snapshot()), (case, market, seeds[e], t)
+    assert longest >= 3   # the long bundles really occur
+    for e in range(len(seeds)):
+        assert env.codec.header(env.rec[e], "N_REPLANS") == planners[e].n_replans
