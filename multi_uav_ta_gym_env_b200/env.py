@@ -693,6 +693,14 @@ class HungarianAllocator:
         return [(env.agents_obj[a].name, env._task(tid)) for a, tid in pairs]
 
 
+def _in_caller_order(result, agents):
+    """The market allocators list their plan agent by agent in the order of the `agents` argument
+    (PerformanceImpact.py:205-218, CBBA.py:88-108,199-211); the device lists it in agent-id order, which is the same thing
+    for env.get_live_agents() -- every reference driver's argument -- and is re-ordered here for any other list."""
+    pos = {a.name: i for i, a in enumerate(agents)}
+    return sorted(result, key=lambda item: pos.get(item[0], len(pos)))
+
+
 class PerformanceImpact:
     """Same constructor, attributes and allocate_tasks signature as the reference's market baseline
     (TaskAllocation/MarketBased/PerformanceImpact.py:27-224); the slot expansion, the IPI / RPI costs and the
@@ -761,8 +769,8 @@ class PerformanceImpact:
                     out[-1][1].append(env._task(tid))
                 else:
                     out.append((env.agents_obj[a].name, [env._task(tid)]))
-            return out
-        return [(env.agents_obj[a].name, [env._task(tid)]) for a, tid in pairs]
+            return _in_caller_order(out, agents)
+        return _in_caller_order([(env.agents_obj[a].name, [env._task(tid)]) for a, tid in pairs], agents)
 
 
 class CBBAReplan:
@@ -835,5 +843,5 @@ class CBBAReplan:
                     out[-1][1].append(env._task(tid))
                 else:
                     out.append((env.agents_obj[a].name, [env._task(tid)]))
-            return out
-        return [(env.agents_obj[a].name, [env._task(tid)]) for a, tid in pairs]
+            return _in_caller_order(out, agents)
+        return _in_caller_order([(env.agents_obj[a].name, [env._task(tid)]) for a, tid in pairs], agents)

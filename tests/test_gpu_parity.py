@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (BUNDLE_DRIVERS, CBBA_DRIVERS, bundle_of, assert_tokens_equal_reference, escort_scores_from_logits, golden_config, injected_commit_vectors, injected_logits, injected_scores,
+from helpers import (BUNDLE_DRIVERS, CBBA_DRIVERS, assert_tokens_equal_reference, escort_scores_from_logits, golden_config, injected_commit_vectors, injected_logits, injected_scores,
                      load_golden)
 import refsnap
 

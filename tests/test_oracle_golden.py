@@ -5,7 +5,7 @@ import pytest
 
 import numpy as np
 
-from helpers import (BUNDLE_DRIVERS, CBBA_DRIVERS, bundle_of, assert_tokens_equal_reference, escort_scores_from_logits, injected_commit_vectors, injected_logits, injected_scores, load_golden,
+from helpers import (CBBA_DRIVERS, bundle_of, assert_tokens_equal_reference, escort_scores_from_logits, injected_commit_vectors, injected_logits, injected_scores, load_golden,
                      golden_config)
 import refsnap
 from oracle.hungarian import OracleHungarian, apply_assign, open_tasks

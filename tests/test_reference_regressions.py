@@ -297,38 +297,49 @@ def scenario_cbba_coalition_eligibility_visibility(env, info, classes):
     return log
 
 
+def place(env, agent, xy):
+    """`agent.position = xy` of the reference tests: on the facade the two position fields of the record are written
+    and the proxies refreshed."""
+    if hasattr(env, "_backend"):
+        env._backend.patch_field("a_posx", agent.id, float(xy[0]))
+        env._backend.patch_field("a_posy", agent.id, float(xy[1]))
+        env._sync()
+    else:
+        agent.position = np.array([float(xy[0]), float(xy[1])])
+
+
 def scenario_pi_prefers_nearer(env, info, classes):
-    """test_pi_schedule_impact_prefers_nearer (test_escort.py:244-276): offered one escort slot and two idle fighters, PI
-    takes the nearer one.  Reached without moving objects by hand: at every step with an open escort, PI is asked (without
-    stepping on its result) to choose between the two idle fighters nearest to and farthest from it."""
-    hung_info = {"info": info}
-    log = {"checks": 0, "choices": []}
-
-    def on_step(phase, result, events):
-        if phase != "step":
-            return
-        known = env.agent_visibility_map()
-        for escort in [t for t in env.tasks if getattr(t, "kind", None) == "Escort" and t.status != 2]:
-            idle = [a for a in env.get_live_agents() if a.type in ("F1", "F2") and a.tasks[0].id == 0
-                    and escort.id in known[a.name]]
-            if len(idle) < 2:
-                continue
-            idle.sort(key=lambda a: float(np.linalg.norm(a.position - escort.position)))
-            near, far = idle[0], idle[-1]
-            d_near = float(np.linalg.norm(near.position - escort.position))
-            d_far = float(np.linalg.norm(far.position - escort.position))
-            if d_far - d_near < 100.0 or near.max_speed != far.max_speed:
-                continue
-            pi = classes[1](max_coord=env.max_coord, seed=0, replan_interval=1)
-            out = pi.allocate_tasks([near, far], [escort], time_step=env.time_steps, force=True, agent_known_ids=known,
-                                    max_tasks_per_agent=1)
-            names = [n for n, _ in out]
-            assert near.name in names, f"near fighter should be chosen, got {out}"
-            log["checks"] += 1
-            log["choices"].append((env.time_steps, escort.id, names))
-            return
-
-    coalition_rollout(env, hung_info["info"], classes, on_step=on_step)
+    """test_pi_schedule_impact_prefers_nearer (test_escort.py:244-276): an F1 at 5 and an F2 at 400 from an escort, both
+    idle and both knowing it (a caller-made visibility map) -> the near one is in PI's plan.  The escort (both fighter
+    slots still open, as in the reference test) comes from the rollout instead of env._create_escort_for."""
+    hung = classes[0](replan_interval=12, max_coord=env.max_coord)
+    log = {}
+    for _ in range(60):
+        result = hung.allocate_tasks(env.get_live_agents(), open_tasks(env), time_step=env.time_steps, events=events_of(info),
+                                     agent_known_ids=env.agent_visibility_map())
+        _, _, done, trunc, info = env.step(to_actions(env, result))
+        escorts = [t for t in env.tasks if getattr(t, "kind", None) == "Escort" and t.status != 2
+                   and int(t.required_agents) - len(t.allocationDetails) >= 2]
+        idle = [a for a in env.get_live_agents() if a.type in ("F1", "F2") and a.tasks[0].id == 0]
+        near = next((a for a in idle if a.type == "F1"), None)
+        far = next((a for a in idle if a.type == "F2"), None)
+        if not escorts or near is None or far is None:
+            continue
+        escort = escorts[0]
+        ex, ey = float(escort.position[0]), float(escort.position[1])
+        place(env, near, (ex + 5.0, ey))
+        place(env, far, (ex + 400.0 if ex < 600.0 else ex - 400.0, ey))
+        known = {near.name: {escort.id}, far.name: {escort.id}}
+        pi = classes[1](max_coord=env.max_coord, seed=0, replan_interval=1)
+        out = pi.allocate_tasks([near, far], [escort], time_step=env.time_steps, force=True, agent_known_ids=known,
+                                max_tasks_per_agent=1)
+        names = [n for n, _ in out]
+        assert near.name in names, f"near fighter should be chosen, got {out}"
+        slots = int(escort.required_agents) - len(escort.allocationDetails)
+        log = {"t": env.time_steps, "escort": escort.id, "names": names, "slots": slots,
+               "near": [float(x) for x in near.position], "far": [float(x) for x in far.position]}
+        break
+    assert log, "no escort with two idle fighters in 60 steps"
     return log
 
 
