@@ -653,6 +653,12 @@ class HungarianAllocator:
             return []
         if int(time_step) != int(env.time_steps):
             raise ValueError("time_step must be env.time_steps (the device allocator reads the env clock)")
+        ids = [a.id for a in agents]
+        if ids != sorted(ids):
+            # the rows of the cost matrix -- and with them SciPy's choice among equal-cost assignments and the order of the
+            # result -- follow the `agents` list (HungarianAllocator.py:128-141); the device builds the rows in agent-id
+            # order, which is what env.get_live_agents() and every order-preserving filter of it give
+            raise ValueError("agents must be listed in environment order (env.get_live_agents() or a filtered copy of it)")
         cfg = env._backend.cfg
         A, TC = cfg.n_agents, max(cfg.id_cap, cfg.task_cap)  # per-task arguments are indexed by task id
         reserved_names = set(reserved_agent_names or [])
@@ -696,7 +702,8 @@ class HungarianAllocator:
 def _in_caller_order(result, agents):
     """The market allocators list their plan agent by agent in the order of the `agents` argument
     (PerformanceImpact.py:205-218, CBBA.py:88-108,199-211); the device lists it in agent-id order, which is the same thing
-    for env.get_live_agents() -- every reference driver's argument -- and is re-ordered here for any other list."""
+    for env.get_live_agents() -- every reference driver's argument -- and is re-ordered here for any other list.  (Exact
+    ties between indistinguishable agents -- same type, same place -- are still broken in agent-id order on the device.)"""
     pos = {a.name: i for i, a in enumerate(agents)}
     return sorted(result, key=lambda item: pos.get(item[0], len(pos)))
 

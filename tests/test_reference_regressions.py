@@ -428,3 +428,14 @@ def test_att_coalition_v2_tokens_and_one_update(hostcheck):
     net2.load_state_dict(ck["state_dict"])
     assert (ck["max_tasks"], ck["d_model"], ck["n_layers"]) == (48, 64, 2)
     assert torch.equal(coalition_scores(net2.eval(), bt), coalition_scores(net.eval(), bt))
+
+
+def test_hungarian_rejects_a_permuted_agent_list():
+    """The device builds the cost rows in agent-id order; a caller list in another order would change SciPy's tie-breaks
+    (HungarianAllocator.py:128-141), so the facade class refuses it instead of answering differently."""
+    env, _ = facade_env(0)
+    hung = facade_classes()[0](replan_interval=1, max_coord=env.max_coord)
+    live = env.get_live_agents()
+    assert hung.allocate_tasks(live[::2], open_tasks(env), time_step=0, force=True)          # order-preserving subset: fine
+    with pytest.raises(ValueError):
+        hung.allocate_tasks(live[::-1], open_tasks(env), time_step=0, force=True)
