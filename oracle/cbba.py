@@ -5,13 +5,14 @@ Restates the reference's CBBA market baseline over the oracle's flat state (orac
   CBBAReplan (periodic / event-triggered replan, a fresh CBBA(seed + n_replans) per replan)
                                                  TaskAllocation/MarketBased/CBBA_Replan.py:15-69
 under the loops of experiments/wps_eval.py:134-146 (Local-CBBA-Replan, interval 20) and escort_eval.py:149-161
-(Local-CBBA-Coalition, interval 12), both with max_tasks_per_agent = 1.
+(Local-CBBA-Coalition, interval 12), both with max_tasks_per_agent = 1; bundles (max_tasks_per_agent > 1) as
+CBBA.py:128-190 builds them.
 
 The reference is deterministic only under a pinned string hash: every auction round starts from
 `ordered_keys = list(remaining)` of a SET of slot-key strings (CBBA.py:116,128) and shuffles that list with its own
 seeded generator.  oracle/pyset.py restates CPython's str hash and set order for PYTHONHASHSEED=0
-(tests/test_pyset.py compares them with the interpreter), and the fixtures tests/golden/wps_*_cbba.json.gz were
-generated from the unmodified reference in an interpreter started with PYTHONHASHSEED=0 (tests/golden/gen_golden.py).
+(tests/test_pyset.py compares them with the interpreter), and the fixtures tests/golden/wps_*_cbba.json.gz (one task per
+agent), wps_*_cbba2, wps_hard_cbba3 and wps_commit_cbba4 (bundles of two, three and four) were generated from the unmodified reference in an interpreter started with PYTHONHASHSEED=0 (tests/golden/gen_golden.py).
 
 Arithmetic (float64, one rounding per operation, CBBA.py:288-309):
     time  = temp_time + dist / max(speed, 1e-6)
