@@ -375,3 +375,66 @@ def test_replay_documents_are_identical(scenario, tmp_path):
             return pairs, committed
     doc = myreplay.record_replay(env, info, plan, cfg, scenario, 1)
     assert doc == want
+
+
+def _driver_module(name):
+    """experiments/wps_eval.py or escort_eval.py of the reference, imported as it is (its legacy RL imports stubbed as in
+    tests/golden/gen_eval_scores.py)."""
+    import importlib
+    import sys
+    import types
+
+    refshim.install()
+    for mod, attrs in (("tianshou", {}), ("tianshou.data", {"Batch": dict}),
+                       ("TaskAllocation.RL_Policies", {}), ("TaskAllocation.RL_Policies.Tianshou_Policy", {"_get_model": None}),
+                       ("RL_Policies", {}), ("RL_Policies.Tianshou_Policy", {"_get_model": None})):
+        if mod not in sys.modules:
+            m = types.ModuleType(mod)
+            m.__dict__.update(attrs)
+            m.__path__ = []
+            sys.modules[mod] = m
+    return importlib.import_module("experiments." + name)
+
+
+@pytest.mark.parametrize("module,fn,algo,case,seed", [
+    ("wps_eval", "run_wps_episode", "Local-Hungarian", "WPS_hard", 1),
+    ("wps_eval", "run_wps_episode", "Global-Hungarian", "WPS_hard", 2),
+    ("wps_eval", "run_wps_episode", "Local-PI", "WPS_commit", 0),
+    ("wps_eval", "run_wps_episode", "Urgency-Pair", "WPS_hard", 3),
+    ("wps_eval", "run_wps_episode", "Urgency-Commit", "WPS_commit", 1),
+    ("escort_eval", "run_escort_episode", "Coalition-Hungarian", "WPS_escort", 0),
+    ("escort_eval", "run_escort_episode", "Local-PI-Coalition", "WPS_escort", 1),
+    ("escort_eval", "run_escort_episode", "Urgency-Coalition", "WPS_escort", 2),
+])
+def test_reference_episode_drivers_run_unmodified_with_the_imports_swapped(module, fn, algo, case, seed, monkeypatch):
+    """the reference's episode drivers (experiments/wps_eval.py:76-290 run_wps_episode,
+    escort_eval.py:86-230 run_escort_episode) are executed UNMODIFIED twice -- as they are, and with the names
+    MultiUAVEnv / HungarianAllocator / PerformanceImpact / CBBAReplan of their module pointing at the drop-in classes --
+    and must return the same result dict (wall-clock entries aside)."""
+    from multi_uav_ta_gym_env_b200 import env as E
+
+    M = _driver_module(module)
+    kw = {}
+    if algo == "Urgency-Pair":
+        from TaskAllocation.Hybrid.PairCostHybrid import UrgencyPair
+        make = lambda: {"urg_pair": UrgencyPair()}  # noqa: E731
+    elif algo == "Urgency-Commit":
+        from TaskAllocation.Hybrid.AttentionCommit import UrgencyCommit
+        make = lambda: {"urg_commit": UrgencyCommit()}  # noqa: E731
+    elif algo == "Urgency-Coalition":
+        from TaskAllocation.Hybrid.AttentionEscort import UrgencyCoalition
+        make = lambda: {"urg": UrgencyCoalition()}  # noqa: E731
+    else:
+        make = lambda: kw  # noqa: E731
+    want = getattr(M, fn)(algo, case, seed, **make())
+    monkeypatch.setattr(M, "MultiUAVEnv", host_facade)
+    monkeypatch.setattr(M, "HungarianAllocator", E.HungarianAllocator)
+    monkeypatch.setattr(M, "PerformanceImpact", E.PerformanceImpact)
+    monkeypatch.setattr(M, "CBBAReplan", E.CBBAReplan)
+    got = getattr(M, fn)(algo, case, seed, **make())
+    clock = {"decision_ms_mean", "replan_ms_mean", "replan_ms_p95", "decision_ms_p95"}
+    assert set(got) == set(want)
+    for k in want:
+        if k in clock or k.endswith("_ms") or "_ms_" in k:
+            continue
+        assert got[k] == want[k] or (got[k] != got[k] and want[k] != want[k]), (k, got[k], want[k])
