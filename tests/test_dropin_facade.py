@@ -405,10 +405,14 @@ def _driver_module(name):
     ("escort_eval", "run_escort_episode", "Coalition-Hungarian", "WPS_escort", 0),
     ("escort_eval", "run_escort_episode", "Local-PI-Coalition", "WPS_escort", 1),
     ("escort_eval", "run_escort_episode", "Urgency-Coalition", "WPS_escort", 2),
+    ("paper_eval", "run_episode", "Hungarian", "static_strike", 0),
+    ("paper_eval", "run_episode", "Hungarian", "D1_attrition", 1),
+    ("paper_eval", "run_episode", "Hungarian", "D3_combined", 2),
 ])
 def test_reference_episode_drivers_run_unmodified_with_the_imports_swapped(module, fn, algo, case, seed, monkeypatch):
     """the reference's episode drivers (experiments/wps_eval.py:76-290 run_wps_episode,
-    escort_eval.py:86-230 run_escort_episode) are executed UNMODIFIED twice -- as they are, and with the names
+    escort_eval.py:86-230 run_escort_episode, paper_eval.py:108-290 run_episode on the legacy suite with TBTA_E3_FLAGS,
+    i.e. with the capability / saturation masks on) are executed UNMODIFIED twice -- as they are, and with the names
     MultiUAVEnv / HungarianAllocator / PerformanceImpact / CBBAReplan of their module pointing at the drop-in classes --
     and must return the same result dict (wall-clock entries aside)."""
     from multi_uav_ta_gym_env_b200 import env as E
@@ -426,12 +430,16 @@ def test_reference_episode_drivers_run_unmodified_with_the_imports_swapped(modul
         make = lambda: {"urg": UrgencyCoalition()}  # noqa: E731
     else:
         make = lambda: kw  # noqa: E731
-    want = getattr(M, fn)(algo, case, seed, **make())
+    args = (algo, case, seed)
+    if module == "paper_eval":   # the legacy suite (paper_eval.py:108-290) takes its environment flags as an argument
+        from experiments.paper_scenarios import TBTA_E3_FLAGS
+        args += (dict(TBTA_E3_FLAGS),)
+    want = getattr(M, fn)(*args, **make())
     monkeypatch.setattr(M, "MultiUAVEnv", host_facade)
     monkeypatch.setattr(M, "HungarianAllocator", E.HungarianAllocator)
-    monkeypatch.setattr(M, "PerformanceImpact", E.PerformanceImpact)
+    monkeypatch.setattr(M, "PerformanceImpact", E.PerformanceImpact, raising=False)
     monkeypatch.setattr(M, "CBBAReplan", E.CBBAReplan)
-    got = getattr(M, fn)(algo, case, seed, **make())
+    got = getattr(M, fn)(*args, **make())
     clock = {"decision_ms_mean", "replan_ms_mean", "replan_ms_p95", "decision_ms_p95"}
     assert set(got) == set(want)
     for k in want:
