@@ -446,3 +446,74 @@ def test_reference_episode_drivers_run_unmodified_with_the_imports_swapped(modul
         if k in clock or k.endswith("_ms") or "_ms_" in k:
             continue
         assert got[k] == want[k] or (got[k] != got[k] and want[k] != want[k]), (k, got[k], want[k])
+
+
+@pytest.mark.parametrize("phase", ["il", "rl"])
+def test_reference_pair_cost_trainer_episodes_run_unmodified_on_the_facade(phase):
+    """SURVEY 8(f) row 2 from the drop-in side: experiments/train_pair_cost.py's run_il_episode (:96-128, Global-Hungarian
+    expert, imitation steps on build_pair_tokens) and run_rl_episode (:131-156, exploration, reward dS_WPS / 20, replay
+    buffer, actor-critic updates) executed UNMODIFIED on the reference environment + allocator and on the facade ones,
+    same generator seeds: the same reset seeds are drawn, the same tokens are built, so the returned mean loss / final
+    S_WPS and the trained weights are identical."""
+    import random
+
+    import torch
+
+    M = _driver_module("train_pair_cost")
+    from TaskAllocation.Hybrid.PairCostHybrid import PairCostHybrid
+    from TaskAllocation.OptimizationBased.HungarianAllocator import HungarianAllocator as RefHung
+    from mUAV_TA.DroneEnv import MultiUAVEnv as RefEnv
+    from multi_uav_ta_gym_env_b200 import env as E
+
+    def run(env_cls, hung_cls):
+        random.seed(11)
+        np.random.seed(11)
+        torch.manual_seed(11)
+        cfg = refshim.wps_config("WPS_hard")
+        env = env_cls(cfg)
+        policy = PairCostHybrid(use_attention=True)
+        out = []
+        for _ in range(2):
+            if phase == "il":
+                out.append(M.run_il_episode(env, policy, hung_cls(20, env.max_coord), hung_cls(20, env.max_coord), il_batch=8))
+            else:
+                out.append(M.run_rl_episode(env, policy, hung_cls(10**9, env.max_coord), explore=True))
+        return out, [p.detach().clone() for p in policy.net.parameters()]
+
+    want, w_ref = run(RefEnv, RefHung)
+    got, w_mine = run(host_facade, E.HungarianAllocator)
+    assert got == want, (got, want)
+    assert all(torch.equal(a, b) for a, b in zip(w_ref, w_mine))
+    assert any(x != 0.0 for x in want)
+
+
+@pytest.mark.parametrize("module,case,policy_cls", [("train_att_commit", "WPS_commit", "AttentionCommit"),
+                                                    ("train_escort", "WPS_escort", "AttentionEscort")])
+def test_reference_commit_and_escort_trainer_episodes_run_unmodified_on_the_facade(module, case, policy_cls):
+    """experiments/train_att_commit.py:29-75 and train_escort.py:29-82 run_episode (tokens -> act with exploration ->
+    _plan_from_scores -> step -> push / update) UNMODIFIED on the reference environment + allocator and on the facade
+    ones with the same generator seeds: same returned episode statistics, identical trained weights."""
+    import importlib
+    import random
+
+    import torch
+
+    M = _driver_module(module)
+    hybrid = importlib.import_module("TaskAllocation.Hybrid." + policy_cls)
+    from TaskAllocation.OptimizationBased.HungarianAllocator import HungarianAllocator as RefHung
+    from mUAV_TA.DroneEnv import MultiUAVEnv as RefEnv
+    from multi_uav_ta_gym_env_b200 import env as E
+
+    def run(env_cls, hung_cls):
+        random.seed(4)
+        np.random.seed(4)
+        torch.manual_seed(4)
+        env = env_cls(refshim.wps_config(case))
+        policy = getattr(hybrid, policy_cls)(use_attention=True)
+        out = [M.run_episode(env, policy, hung_cls(10**9, env.max_coord), explore=True)]
+        return out, [p.detach().clone() for p in policy.net.parameters()]
+
+    want, w_ref = run(RefEnv, RefHung)
+    got, w_mine = run(host_facade, E.HungarianAllocator)
+    assert got == want, (got, want)
+    assert all(torch.equal(a, b) for a, b in zip(w_ref, w_mine))
