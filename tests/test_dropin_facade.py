@@ -396,6 +396,16 @@ def _driver_module(name):
     return importlib.import_module("experiments." + name)
 
 
+LEARNED_ROWS = {   # algorithm -> (module, class, keyword of the episode driver, constructor arguments)
+    "Att-Pair": ("PairCostHybrid", "PairCostHybrid", "att_pair", {"use_attention": True}),
+    "MLP-Pair": ("PairCostHybrid", "PairCostHybrid", "mlp_pair", {"use_attention": False}),
+    "Att-Commit": ("AttentionCommit", "AttentionCommit", "att_commit", {"use_attention": True}),
+    "Att-ContextPair": ("ContextPairHybrid", "ContextPairHybrid", "att_ctx", {"use_attention": True}),
+    "GNN-ContextPair": ("GNNPairHybrid", "GNNContextPairHybrid", "gnn_ctx", {}),
+    "Att-Coalition": ("AttentionEscort", "AttentionEscort", "att", {"use_attention": True}),
+}
+
+
 @pytest.mark.parametrize("module,fn,algo,case,seed", [
     ("wps_eval", "run_wps_episode", "Local-Hungarian", "WPS_hard", 1),
     ("wps_eval", "run_wps_episode", "Global-Hungarian", "WPS_hard", 2),
@@ -405,6 +415,14 @@ def _driver_module(name):
     ("escort_eval", "run_escort_episode", "Coalition-Hungarian", "WPS_escort", 0),
     ("escort_eval", "run_escort_episode", "Local-PI-Coalition", "WPS_escort", 1),
     ("escort_eval", "run_escort_episode", "Urgency-Coalition", "WPS_escort", 2),
+    ("wps_eval", "run_wps_episode", "Att-Pair", "WPS_hard", 4),
+    ("wps_eval", "run_wps_episode", "MLP-Pair", "WPS_commit", 2),
+    ("wps_eval", "run_wps_episode", "Att-Commit", "WPS_commit", 3),
+    ("wps_eval", "run_wps_episode", "Att-ContextPair", "WPS_attn", 1),
+    ("wps_eval", "run_wps_episode", "GNN-ContextPair", "WPS_attn", 2),
+    ("wps_eval", "run_wps_episode", "Local-Cap-Greedy", "WPS_hard", 5),
+    ("escort_eval", "run_escort_episode", "Att-Coalition", "WPS_escort", 3),
+    ("escort_eval", "run_escort_episode", "Global-Coalition", "WPS_escort", 4),
     ("paper_eval", "run_episode", "Hungarian", "static_strike", 0),
     ("paper_eval", "run_episode", "Hungarian", "D1_attrition", 1),
     ("paper_eval", "run_episode", "Hungarian", "D3_combined", 2),
@@ -428,6 +446,16 @@ def test_reference_episode_drivers_run_unmodified_with_the_imports_swapped(modul
     elif algo == "Urgency-Coalition":
         from TaskAllocation.Hybrid.AttentionEscort import UrgencyCoalition
         make = lambda: {"urg": UrgencyCoalition()}  # noqa: E731
+    elif algo in LEARNED_ROWS:   # a random-init network of the reference's own hybrid class, same weights in both runs
+        import importlib
+
+        import torch
+
+        mod, cls, arg, ckw = LEARNED_ROWS[algo]
+
+        def make():
+            torch.manual_seed(7)
+            return {arg: getattr(importlib.import_module("TaskAllocation.Hybrid." + mod), cls)(**ckw)}
     else:
         make = lambda: kw  # noqa: E731
     args = (algo, case, seed)
