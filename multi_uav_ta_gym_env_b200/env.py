@@ -42,6 +42,7 @@ class TaskProxy:
         self.eligible_agent_types = None
         self.required_agents = 0
         self.allocationDetails = {}
+        self.max_time_steps = getattr(env, "max_time_steps", None)
         if tid == 0:
             self.type = "Hold"
             self.typeIdx = 0
@@ -293,6 +294,9 @@ class MultiUAVEnv:
         self.window_length = int(g("window_length", 30) or 30)
         self.miss_penalty = float(g("miss_penalty", 25.0) or 0.0)
         self.on_time_bonus = float(g("on_time_bonus", 10.0) or 0.0)
+        self.burst_mode = bool(g("burst_mode", False))          # read by build_rah_state (ReserveAwareHybrid.py:56)
+        self.burst_size = int(g("burst_size", 3) or 3)
+        self.dual_region_bursts = bool(g("dual_region_bursts", False))
         self.share_knowledge = bool(g("share_knowledge", True))
         self.commit_horizon = int(g("commit_horizon", 0) or 0)
         self.reassign_penalty = float(g("reassign_penalty", 0.0) or 0.0)

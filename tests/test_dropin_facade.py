@@ -403,6 +403,10 @@ LEARNED_ROWS = {   # algorithm -> (module, class, keyword of the episode driver,
     "Att-ContextPair": ("ContextPairHybrid", "ContextPairHybrid", "att_ctx", {"use_attention": True}),
     "GNN-ContextPair": ("GNNPairHybrid", "GNNContextPairHybrid", "gnn_ctx", {}),
     "Att-Coalition": ("AttentionEscort", "AttentionEscort", "att", {"use_attention": True}),
+    # the reserve-aware hybrids drive the allocator's task_priorities / reserved_agent_names arguments
+    "RAH": ("ReserveAwareHybrid", "ReserveAwareHybrid", "rah", {}),
+    "RAH-no-reserve": ("ReserveAwareHybrid", "ReserveAwareHybrid", "rah", {}),
+    "Att-RAH": ("AttentionRAH", "AttentionRAH", "att_rah", {}),
 }
 
 
@@ -421,6 +425,9 @@ LEARNED_ROWS = {   # algorithm -> (module, class, keyword of the episode driver,
     ("wps_eval", "run_wps_episode", "Att-ContextPair", "WPS_attn", 1),
     ("wps_eval", "run_wps_episode", "GNN-ContextPair", "WPS_attn", 2),
     ("wps_eval", "run_wps_episode", "Local-Cap-Greedy", "WPS_hard", 5),
+    ("wps_eval", "run_wps_episode", "RAH", "WPS_hard", 6),
+    ("wps_eval", "run_wps_episode", "RAH-no-reserve", "WPS_hard", 7),
+    ("wps_eval", "run_wps_episode", "Att-RAH", "WPS_commit", 4),
     ("escort_eval", "run_escort_episode", "Att-Coalition", "WPS_escort", 3),
     ("escort_eval", "run_escort_episode", "Global-Coalition", "WPS_escort", 4),
     ("paper_eval", "run_episode", "Hungarian", "static_strike", 0),
@@ -545,3 +552,39 @@ def test_reference_commit_and_escort_trainer_episodes_run_unmodified_on_the_faca
     got, w_mine = run(host_facade, E.HungarianAllocator)
     assert got == want, (got, want)
     assert all(torch.equal(a, b) for a, b in zip(w_ref, w_mine))
+
+
+def test_facade_exposes_what_the_reference_callers_read():
+    """Attribute census of the drop-in surface: every `env.<name>` / `getattr(env, "<name>")` that the
+    reference's allocators, hybrids, episode drivers and trainers touch exists on the facade, and the agent / task proxies
+    carry every attribute of the reference objects that any of those callers reads.  (Found `burst_mode`, read by
+    build_rah_state, missing.)  Not offered, on purpose: the private escort mutators the reference's white-box tests call,
+    benchmark.py's get_initial_state and the AEC `last()` of the legacy RL stack."""
+    import glob
+    import os
+    import re
+
+    ref, _, _, mine, _, _ = make_pair("WPS_escort", 1)
+    ref.step({})
+    mine.step({})
+    root = refshim.REF_ROOT
+    files = (glob.glob(os.path.join(root, "TaskAllocation", "**", "*.py"), recursive=True)
+             + glob.glob(os.path.join(root, "experiments", "*.py")) + [os.path.join(root, "benchmark.py")])
+    pat = re.compile(r'\benv\.([A-Za-z_][A-Za-z0-9_]*)|getattr\(env,\s*"([A-Za-z_][A-Za-z0-9_]*)"')
+    used = set()
+    for f in files:
+        with open(f, errors="ignore") as fh:
+            used |= {m.group(1) or m.group(2) for m in pat.finditer(fh.read())}
+    assert len(used) >= 50
+    missing = {n for n in used if hasattr(ref, n) and not hasattr(mine, n)}
+    assert missing <= {"_create_escort_for", "_retire_escort", "_sync_escorts", "get_initial_state", "last"}, missing
+    text = ""
+    for f in files:
+        if "RL_Policies" in f or "swarm_gap" in f:
+            continue   # legacy stacks outside SURVEY section 8
+        with open(f, errors="ignore") as fh:
+            text += fh.read()
+    for robj, mobj in ((ref.agents_obj[0], mine.agents_obj[0]), (ref.tasks[1], mine.tasks[1])):
+        for name in vars(robj):
+            if not hasattr(mobj, name) and re.search(r"\.%s\b" % re.escape(name), text):
+                raise AssertionError(f"{type(robj).__name__}.{name} is read by a reference caller and missing on the proxy")
