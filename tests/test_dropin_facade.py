@@ -407,6 +407,11 @@ LEARNED_ROWS = {   # algorithm -> (module, class, keyword of the episode driver,
     "RAH": ("ReserveAwareHybrid", "ReserveAwareHybrid", "rah", {}),
     "RAH-no-reserve": ("ReserveAwareHybrid", "ReserveAwareHybrid", "rah", {}),
     "Att-RAH": ("AttentionRAH", "AttentionRAH", "att_rah", {}),
+    "Att-RAH-no-reserve": ("AttentionRAH", "AttentionRAH", "att_rah", {}),
+    "Att-RAH-no-priority": ("AttentionRAH", "AttentionRAH", "att_rah", {}),
+    "MLP-Commit": ("AttentionCommit", "AttentionCommit", "mlp_commit", {"use_attention": False}),
+    "MLP-ContextPair": ("ContextPairHybrid", "ContextPairHybrid", "mlp_ctx", {"use_attention": False}),
+    "MLP-Coalition": ("AttentionEscort", "AttentionEscort", "mlp", {"use_attention": False}),
 }
 
 
@@ -428,6 +433,11 @@ LEARNED_ROWS = {   # algorithm -> (module, class, keyword of the episode driver,
     ("wps_eval", "run_wps_episode", "RAH", "WPS_hard", 6),
     ("wps_eval", "run_wps_episode", "RAH-no-reserve", "WPS_hard", 7),
     ("wps_eval", "run_wps_episode", "Att-RAH", "WPS_commit", 4),
+    ("wps_eval", "run_wps_episode", "Att-RAH-no-reserve", "WPS_hard", 8),
+    ("wps_eval", "run_wps_episode", "Att-RAH-no-priority", "WPS_hard", 9),
+    ("wps_eval", "run_wps_episode", "MLP-Commit", "WPS_commit", 5),
+    ("wps_eval", "run_wps_episode", "MLP-ContextPair", "WPS_attn", 3),
+    ("escort_eval", "run_escort_episode", "MLP-Coalition", "WPS_escort", 5),
     ("escort_eval", "run_escort_episode", "Att-Coalition", "WPS_escort", 3),
     ("escort_eval", "run_escort_episode", "Global-Coalition", "WPS_escort", 4),
     ("paper_eval", "run_episode", "Hungarian", "static_strike", 0),
