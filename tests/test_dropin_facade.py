@@ -598,3 +598,32 @@ def test_facade_exposes_what_the_reference_callers_read():
         for name in vars(robj):
             if not hasattr(mobj, name) and re.search(r"\.%s\b" % re.escape(name), text):
                 raise AssertionError(f"{type(robj).__name__}.{name} is read by a reference caller and missing on the proxy")
+
+
+CBBA_ROWS = [("wps_eval", "run_wps_episode", "Local-CBBA-Replan", "WPS_hard", 2),
+             ("wps_eval", "run_wps_episode", "Local-CBBA-Replan", "WPS_commit", 1),
+             ("escort_eval", "run_escort_episode", "Local-CBBA-Coalition", "WPS_escort", 0)]
+
+
+if __import__("os").environ.get("MUAV_CBBA_INNER") == "1":   # collected only inside the PYTHONHASHSEED=0 child interpreter
+    @pytest.mark.parametrize("module,fn,algo,case,seed", CBBA_ROWS)
+    def test_cbba_rows_inner(module, fn, algo, case, seed, monkeypatch):
+        import os
+
+        assert os.environ.get("PYTHONHASHSEED") == "0"
+        test_reference_episode_drivers_run_unmodified_with_the_imports_swapped(module, fn, algo, case, seed, monkeypatch)
+
+
+def test_reference_cbba_drivers_run_unmodified_under_hashseed_zero():
+    """The CBBA rows of the unmodified-driver comparison: the reference's auction order depends on the interpreter's string
+    hash (CBBA.py:116,128), so both runs -- reference classes and facade classes -- happen in a child interpreter started
+    with PYTHONHASHSEED=0, the setting the device auction reproduces."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, PYTHONHASHSEED="0", MUAV_CBBA_INNER="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "test_cbba_rows_inner",
+                        "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert f"{len(CBBA_ROWS)} passed" in r.stdout, r.stdout[-2000:]
