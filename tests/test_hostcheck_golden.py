@@ -156,6 +156,8 @@ def test_market_bundles_match_the_oracle_on_fresh_seeds(hostcheck, case, market,
 
     cfg = wps_config(case)
     seeds = [2000 + 7 * bundle, 2001 + 7 * bundle, 2002 + 7 * bundle]
+    if case == "WPS_escort" and market == "pi":
+        seeds = seeds[:1]   # the oracle's escort PI with four-task paths takes ten seconds per episode
     env = hostcheck.make(cfg, seeds)
     O = alloc_opts_for("cbba_replan" if market == "cbba" else "local_pi")
     O.replan_interval = interval
