@@ -437,6 +437,10 @@ def run_gpu_arm(args):
     step_ms, kern_ms = t_all.tolist()
     value = world * E * K / (step_ms / 1e3)
 
+    # episode statistics of the line: the episodes that ended inside the timed window only (none in a 20-step run), not the
+    # probe calls below, which read the metrics of freshly reset environments
+    metric_acc_timed = metric_acc.clone()
+
     # ---- the episode end (metrics kernel + the path's only collective + rewind), timed on its own: a 20-step run never
     # reaches it, so the collective is measured explicitly
     env.restore()
@@ -463,7 +467,6 @@ def run_gpu_arm(args):
         dist.all_reduce(coll_us, op=dist.ReduceOp.MAX)
         dist.all_reduce(ep_end_ms, op=dist.ReduceOp.MAX)
     coll_us, ep_end_ms = coll_us.item(), ep_end_ms.item()
-    metric_acc_timed = metric_acc.clone()
 
     # ---- end-to-end through the host-buffer entry points (muav_ctx_allocate_host / muav_ctx_step_host): the allocator's
     # decision goes to pinned host memory, comes back as host actions, reward / terminated / truncated land in host memory
