@@ -856,3 +856,33 @@ class CBBAReplan:
                     out.append((env.agents_obj[a].name, [env._task(tid)]))
             return _in_caller_order(out, agents)
         return _in_caller_order([(env.agents_obj[a].name, [env._task(tid)]) for a, tid in pairs], agents)
+
+
+class CBBA:
+    """The bare auction class (TaskAllocation/MarketBased/CBBA.py:68-324): same constructor and allocate_tasks signature;
+    one auction with the generator `random.Random(seed)`, which is what `CBBAReplan` builds for every replan
+    (CBBA_Replan.py:62-69) and what the reference's own tests do with it (test_escort.py:166-189).  The reference keeps
+    drawing from the same generator when allocate_tasks is called again on one instance (the legacy "CBBA" algorithm of
+    paper_eval.py:187-195); the device generator is seeded per call, so a second call on the same instance raises instead
+    of answering with another stream.  Reproduces the reference under PYTHONHASHSEED=0 (see CBBAReplan)."""
+
+    def __init__(self, drones=None, tasks=None, max_dist: float = 1000.0, seed: int = 0):
+        self.max_dist = max_dist
+        self.seed = int(seed)
+        self._auctions = 0
+
+    def allocate_tasks(self, agents, tasks, Qs=None, agent_known_ids=None, reserved_agent_names=None, time_step: int = 0,
+                       max_tasks_per_agent: int = 1):
+        agents = list(agents)
+        tasks = list(tasks)
+        env = next((getattr(o, "_env", None) for o in agents + tasks if getattr(o, "_env", None) is not None), None)
+        if env is None or not agents or not tasks:
+            return []
+        if self._auctions:
+            raise NotImplementedError("one auction per CBBA instance: the device generator is seeded per call "
+                                      "(use CBBAReplan, or a fresh CBBA(seed) per call)")
+        self._auctions += 1
+        # CBBAReplan runs CBBA(seed + n_replans) with n_replans = 1 on its first replan
+        inner = CBBAReplan(None, None, self.max_dist, seed=self.seed - 1, replan_interval=1)
+        return inner.allocate_tasks(agents, tasks, time_step=env.time_steps, force=True, agent_known_ids=agent_known_ids,
+                                    reserved_agent_names=reserved_agent_names, max_tasks_per_agent=max_tasks_per_agent)

@@ -614,16 +614,50 @@ if __import__("os").environ.get("MUAV_CBBA_INNER") == "1":   # collected only in
         test_reference_episode_drivers_run_unmodified_with_the_imports_swapped(module, fn, algo, case, seed, monkeypatch)
 
 
+    @pytest.mark.parametrize("case,seed,bundle", [("WPS_hard", 3, 1), ("WPS_escort", 2, 2)])
+    def test_cbba_bare_inner(case, seed, bundle):
+        """The bare auction class (CBBA.py:68-324; one auction per instance) at four points of an episode."""
+        refshim.install()
+        from TaskAllocation.MarketBased.CBBA import CBBA as RefCBBA
+        from TaskAllocation.OptimizationBased.HungarianAllocator import HungarianAllocator as RefHung
+        from multi_uav_ta_gym_env_b200.env import CBBA, HungarianAllocator
+
+        ref, ro, ri, mine, mo, mi = make_pair(case, seed)
+        rh, mh = RefHung(20, ref.max_coord), HungarianAllocator(20, mine.max_coord)
+        n_pairs = 0
+        for t in range(100):
+            if t % 25 == 3:
+                want = RefCBBA(ref.agents_obj, ref.tasks, ref.max_coord, seed=seed + t).allocate_tasks(
+                    ref.get_live_agents(), ref_open_tasks(ref), agent_known_ids=ref.agent_visibility_map(), max_tasks_per_agent=bundle)
+                cb = CBBA(mine.agents_obj, mine.tasks, mine.max_coord, seed=seed + t)
+                got = cb.allocate_tasks(mine.get_live_agents(), ref_open_tasks(mine), agent_known_ids=mine.agent_visibility_map(),
+                                        max_tasks_per_agent=bundle)
+                assert [(n, [k.id for k in tl]) for n, tl in got] == [(n, [k.id for k in tl]) for n, tl in want], t
+                n_pairs += sum(len(tl) for _, tl in want)
+                with pytest.raises(NotImplementedError):
+                    cb.allocate_tasks(mine.get_live_agents(), ref_open_tasks(mine))
+            revents = list(ri.get("events") or []) if isinstance(ri, dict) else []
+            mevents = list(mi.get("events") or []) if isinstance(mi, dict) else []
+            ract = apply_assign(ref, rh.allocate_tasks(ref.get_live_agents(), ref_open_tasks(ref), time_step=ref.time_steps,
+                                                       events=revents, agent_known_ids=ref.agent_visibility_map()))
+            mact = apply_assign(mine, mh.allocate_tasks(mine.get_live_agents(), ref_open_tasks(mine), time_step=mine.time_steps,
+                                                        events=mevents, agent_known_ids=mine.agent_visibility_map()))
+            ro, _, _, _, ri = ref.step(ract)
+            mo, _, _, _, mi = mine.step(mact)
+        assert n_pairs >= 8
+
+
 def test_reference_cbba_drivers_run_unmodified_under_hashseed_zero():
     """The CBBA rows of the unmodified-driver comparison: the reference's auction order depends on the interpreter's string
     hash (CBBA.py:116,128), so both runs -- reference classes and facade classes -- happen in a child interpreter started
-    with PYTHONHASHSEED=0, the setting the device auction reproduces."""
+    with PYTHONHASHSEED=0, the setting the device auction reproduces.  The child also compares the bare `CBBA` class (one
+    auction per instance, bundles of one and two) with the reference class at several points of an episode."""
     import os
     import subprocess
     import sys
 
     env = dict(os.environ, PYTHONHASHSEED="0", MUAV_CBBA_INNER="1")
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "test_cbba_rows_inner",
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "test_cbba_rows_inner or test_cbba_bare_inner",
                         "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-    assert f"{len(CBBA_ROWS)} passed" in r.stdout, r.stdout[-2000:]
+    assert f"{len(CBBA_ROWS) + 2} passed" in r.stdout, r.stdout[-2000:]   # the driver rows and the two bare-CBBA cases

@@ -45,18 +45,19 @@ def reference_env(seed, **over):
 
 
 def facade_classes():
-    from multi_uav_ta_gym_env_b200.env import CBBAReplan, HungarianAllocator, PerformanceImpact
+    from multi_uav_ta_gym_env_b200.env import CBBA, CBBAReplan, HungarianAllocator, PerformanceImpact
 
-    return HungarianAllocator, PerformanceImpact, CBBAReplan
+    return HungarianAllocator, PerformanceImpact, CBBAReplan, CBBA
 
 
 def reference_classes():
     refshim.install()
+    from TaskAllocation.MarketBased.CBBA import CBBA
     from TaskAllocation.MarketBased.CBBA_Replan import CBBAReplan
     from TaskAllocation.MarketBased.PerformanceImpact import PerformanceImpact
     from TaskAllocation.OptimizationBased.HungarianAllocator import HungarianAllocator
 
-    return HungarianAllocator, PerformanceImpact, CBBAReplan
+    return HungarianAllocator, PerformanceImpact, CBBAReplan, CBBA
 
 
 def open_tasks(env):
@@ -271,6 +272,16 @@ def market_rollout(env, info, planner, steps, log, make_probe):
     return info
 
 
+class _BareCBBA:
+    """The bare CBBA class behind the probe's call shape (its allocate_tasks has no events / force arguments)."""
+
+    def __init__(self, cbba):
+        self.cbba = cbba
+
+    def allocate_tasks(self, agents, tasks, time_step=0, force=True, agent_known_ids=None, max_tasks_per_agent=1):
+        return self.cbba.allocate_tasks(agents, tasks, agent_known_ids=agent_known_ids, max_tasks_per_agent=max_tasks_per_agent)
+
+
 def scenario_pi_coalition_eligibility_visibility(env, info, classes):
     """test_cbba_pi_coalition_eligibility_visibility (test_escort.py:141-241), Performance-Impact half."""
     pi = classes[1](max_coord=env.max_coord, seed=3, replan_interval=12)
@@ -287,7 +298,7 @@ def scenario_cbba_coalition_eligibility_visibility(env, info, classes):
     the interpreter's string hash in the reference (CBBA.py:116,128), so only the properties are compared."""
     rp = classes[2](env.agents_obj, env.tasks, env.max_coord, seed=0, replan_interval=12)
     log = {"escort_assigns": 0, "plans": []}
-    market_rollout(env, info, rp, 60, log, lambda: classes[2](env.agents_obj, env.tasks, env.max_coord, seed=1, replan_interval=1))
+    market_rollout(env, info, rp, 60, log, lambda: _BareCBBA(classes[3](env.agents_obj, env.tasks, env.max_coord, seed=1)))
     assert len(log["restricted"][2]) >= 1
     assert log["escort_assigns"] >= 2
     far = classes[2](env.agents_obj, env.tasks, env.max_coord, seed=0, replan_interval=1000)
