@@ -3,7 +3,7 @@
 Public surface:
   agentEnvOptions, CASE_SPECS, WPS_ENV_FLAGS, make_config, wps_config   (config.py: every scenario of paper_scenarios.py)
   BatchedMultiUAVEnv, AllocSpec                                         (batched_env.py; needs the CUDA library)
-  MultiUAVEnv, HungarianAllocator, PerformanceImpact, CBBAReplan                                    (env.py: the single-environment drop-in facade)
+  MultiUAVEnv, HungarianAllocator, PerformanceImpact, CBBAReplan, CBBA  (env.py: the single-environment drop-in facade)
   core_sim                                                              (core_sim.py: the PyO3 module's stand-in)
   scorers                 AttPair / MLPPair / ContextPair / GNN / Commit / Coalition networks, fused Att-Pair kernel
   collectors              batched IL / RL data collectors of train_pair_cost.py
@@ -23,7 +23,7 @@ def __getattr__(name):
         from . import batched_env
 
         return getattr(batched_env, name)
-    if name in ("MultiUAVEnv", "HungarianAllocator", "PerformanceImpact", "CBBAReplan"):
+    if name in ("MultiUAVEnv", "HungarianAllocator", "PerformanceImpact", "CBBAReplan", "CBBA"):
         from . import env
 
         return getattr(env, name)
