@@ -418,6 +418,11 @@ LEARNED_ROWS = {   # algorithm -> (module, class, keyword of the episode driver,
 @pytest.mark.parametrize("module,fn,algo,case,seed", [
     ("wps_eval", "run_wps_episode", "Local-Hungarian", "WPS_hard", 1),
     ("wps_eval", "run_wps_episode", "Global-Hungarian", "WPS_hard", 2),
+    ("wps_eval", "run_wps_episode", "Local-Hungarian", "WPS_easy", 0),
+    ("wps_eval", "run_wps_episode", "Local-Hungarian", "WPS_burst", 1),
+    ("wps_eval", "run_wps_episode", "Local-PI", "WPS_burst", 2),
+    ("wps_eval", "run_wps_episode", "Local-Hungarian", "WPS_attn_XL", 0),
+    ("wps_eval", "run_wps_episode", "Urgency-Pair", "WPS_attn_COP_cue_d12", 1),
     ("wps_eval", "run_wps_episode", "Local-PI", "WPS_commit", 0),
     ("wps_eval", "run_wps_episode", "Urgency-Pair", "WPS_hard", 3),
     ("wps_eval", "run_wps_episode", "Urgency-Commit", "WPS_commit", 1),
